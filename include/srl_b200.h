@@ -1,0 +1,214 @@
+/* srl_b200.h -- C-ABI of the B200-native SRL trainer hot path (libsrl_b200.so).
+ *
+ * Every entry point takes raw DEVICE pointers, plain sizes and a cudaStream_t (as void*), launches
+ * asynchronously on that stream and returns an int status (SRL_OK == 0).  Nothing here aborts: the
+ * Python plugin turns a non-zero status into an exception, which is the reference's error
+ * convention at this boundary (exceptions propagate out of Trainer.step, api/trainer.py:117 /
+ * distributed/system/trainer_worker.py:171,496-498).  No torch types appear in any signature.
+ *
+ * Layout contract (reference: base/buffer.py:118-126): every per-transition leaf is TIME-MAJOR
+ * [L, N] with the N = B * n_agents lanes contiguous (the trailing size-1 dim of the reference's
+ * [L, B, (A,) 1] leaves is dropped).  Values are float32; flags are uint8 as the actor workers
+ * emit them (distributed/system/actor_worker.py:278-281) -- the reference inflates them to float32
+ * on device (api/trainer.py:217), this library does not.
+ *
+ * Each function names the reference code it replaces (paths relative to the SRL repo root).
+ */
+#ifndef SRL_B200_H_
+#define SRL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRL_B200_ABI_VERSION 1
+
+typedef void* srl_stream_t; /* cudaStream_t */
+
+enum srl_status {
+  SRL_OK = 0,
+  SRL_ERR_INVALID_ARG = 1, /* null pointer, negative size, misaligned pointer ... */
+  SRL_ERR_UNSUPPORTED = 2, /* valid request this build cannot serve (e.g. L too long for smem) */
+  SRL_ERR_CUDA = 3,        /* a CUDA runtime call failed; see srl_last_error() */
+  SRL_ERR_NO_DEVICE = 4    /* no sm_100 device visible */
+};
+
+/* Thread-local, NUL-terminated description of the last non-OK status returned on this thread. */
+const char* srl_last_error(void);
+int srl_abi_version(void);
+/* Fills SM count and compute capability of the current device. */
+int srl_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  GAE / value-target reverse-time scan.
+ * Replaces MultiAgentPPO._compute_adv_and_value_target (legacy/algorithm/ppo/mappo.py:118-144),
+ * modules.gae_trace (legacy/algorithm/modules/gae.py:8-97, float64 scan, float32 result), the
+ * zero-row padding at mappo.py:254-256 and, for the statistics, the reductions inside
+ * masked_normalization (legacy/algorithm/modules/utils.py:54-57) and RunningMeanStd.update
+ * (utils.py:113-120).
+ *
+ *   v'[t]  = (popart ? float(double(value)*std + mean) : value) * (1 - done[t])        (fp32)
+ *   d[t]   = reward[t] + gamma * v'[t+1] * (1 - on_reset[t+1]) - v'[t]                  (fp64, no FMA)
+ *   m[t]   = gamma * lmbda * (1 - on_reset[t+1]) * (1 - truncated[t+1])                 (fp64)
+ *   vtrace: rho_t = exp(new_logp - old_logp); d *= min(rho_t, rho); m *= min(rho_t, c)
+ *   A[t]   = d[t] + m[t] * A[t+1], A[L-1] = 0 ;  adv = float(A) ;  ret = adv + v'[t]   (fp32 add)
+ *   adv[L-1] = ret[L-1] = 0 (padding row).
+ *
+ * lane_part (optional, may be NULL): [SRL_LANE_PART][N] float64 per-lane sums over the loss rows
+ * t in [row_lo, row_hi) with mask[t] = 1 - on_reset[t+1] (mappo.py:259-261):
+ *   0: sum mask   1: sum adv*mask   2: sum (adv*mask)^2   3: sum ret*mask   4: sum (ret*mask)^2
+ *   5: sum done[t]   6: sum truncated[t]   7: reserved (0)
+ * ------------------------------------------------------------------------------------------ */
+#define SRL_LANE_PART 8
+
+int srl_gae_scan(const float* reward,          /* [L, N]; row L-1 is ignored                    */
+                 const float* value,           /* [L, N]                                        */
+                 const uint8_t* done,          /* [L, N]                                        */
+                 const uint8_t* truncated,     /* [L, N]                                        */
+                 const uint8_t* on_reset,      /* [L, N]                                        */
+                 const float* vtrace_new_logp, /* [L-1, N] or NULL (vtrace off)                 */
+                 const float* vtrace_old_logp, /* [L-1, N] or NULL                              */
+                 const double* popart_mean_std, /* device {mean, std} or NULL (popart off)      */
+                 int L, int N, int row_lo, int row_hi, double gamma, double lmbda, double rho, double c,
+                 float* adv,        /* [L, N] out */
+                 float* ret,        /* [L, N] out */
+                 double* lane_part, /* [SRL_LANE_PART, N] out or NULL */
+                 srl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Group statistics: out[g][k] = sum over the lanes of group g of lane_part[k][lane].
+ * Group g holds the `per` lanes idx[g*per .. (g+1)*per) (idx == NULL: identity).  One group per
+ * minibatch; with G == 1 and per == N this is the whole-batch reduction of utils.py:54-57 /
+ * utils.py:113-120.  The [G, SRL_LANE_PART] float64 table is what gets all-reduced (SUM) across
+ * ranks in place of the 3 + 3 one-element all-reduces of utils.py:58-61,121-124.
+ * Summation order is fixed (deterministic for a given G, per).
+ * ------------------------------------------------------------------------------------------ */
+int srl_group_stats(const double* lane_part, int N, const int32_t* idx, int G, int per, double* out,
+                    srl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  PopArt / RunningMeanStd update for a scalar critic (critic_dim == 1).
+ * Replaces RunningMeanStd.update + mean_std (utils.py:106-137) as called from
+ * PopArtValueHead.update (legacy/algorithm/modules/popart.py:42-47).
+ *   state = {mean, mean_sq, debias, update_count} (float64, device, updated in place)
+ *   batch_stats: one row of the group-stats table; uses [0] = sum mask, [3] = sum x, [4] = sum x^2.
+ *   mean_std_out = {mu, sigma}: mu = mean/max(debias,eps), sigma = sqrt(max(mean_sq/max(debias,eps) - mu^2, 1e-2)).
+ * ------------------------------------------------------------------------------------------ */
+int srl_popart_update(const double* batch_stats, double* state, double beta, double eps, double* mean_std_out,
+                      srl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  Fused PPO / MAPPO loss, forward + backward to (new_logp, state_values, entropy).
+ * Replaces MultiAgentPPO._compute_loss (mappo.py:146-217) + masked_normalization (utils.py:10-67)
+ * + get_clip_value_loss_fn / init_value_loss_fn (utils.py:228-265) + loss.backward() down to the
+ * three differentiable inputs (mappo.py:274) + the eleven .mean().item() stats (mappo.py:293-299).
+ * ------------------------------------------------------------------------------------------ */
+enum srl_value_loss { SRL_VL_MSE = 0, SRL_VL_HUBER = 1, SRL_VL_SMOOTHL1 = 2 };
+
+typedef struct srl_ppo_hyper {
+  double eps_clip;             /* mappo.py:75 */
+  double value_eps_clip;       /* mappo.py:90 */
+  double c_clip;               /* mappo.py:78 */
+  double value_loss_weight;    /* mappo.py:91 */
+  double entropy_bonus_weight; /* mappo.py:93 */
+  double vl_param;             /* HuberLoss delta / SmoothL1Loss beta (value_loss_config) */
+  double adv_eps;              /* masked_normalization eps, 1e-5 (utils.py:17) */
+  int32_t value_loss;          /* enum srl_value_loss */
+  int32_t clip_value;          /* mappo.py:76 */
+  int32_t dual_clip;           /* mappo.py:77 */
+  int32_t normalize_old_value; /* mappo.py:86 (needs popart_mean_std) */
+} srl_ppo_hyper;
+
+/* indices into the float64 result vector written by srl_ppo_loss_fwd_bwd */
+enum srl_loss_out {
+  SRL_OUT_LOSS = 0,
+  SRL_OUT_POLICY_LOSS = 1,
+  SRL_OUT_VALUE_LOSS = 2,
+  SRL_OUT_ENTROPY_LOSS = 3,
+  SRL_OUT_ADVANTAGE = 4,         /* mean(adv[mask])                    mappo.py:206 */
+  SRL_OUT_IMPORTANCE_WEIGHT = 5, /* mean(ratio[mask])                  mappo.py:212 */
+  SRL_OUT_CLIP_RATIO = 6,        /* mean((s2 < s1)[mask])              mappo.py:213 */
+  SRL_OUT_VALUE_TARGETS = 7,     /* mean(normalised target[mask])      mappo.py:214 */
+  SRL_OUT_DENORM_VALUE = 8,      /* mean(ret[mask]) (popart only)      mappo.py:215-216 */
+  SRL_OUT_MASK_SUM = 9,          /* local sum(mask)                                 */
+  SRL_LOSS_OUT_LEN = 16
+};
+
+/* Bytes of device scratch srl_ppo_loss_fwd_bwd needs for a [T, n] problem.  The first 8 bytes are
+ * a ticket counter and must be zero before the FIRST launch (the kernel re-zeroes it itself). */
+size_t srl_ppo_loss_workspace_bytes(int T, int n);
+
+int srl_ppo_loss_fwd_bwd(
+    /* policy side: dense [T, n], row stride ld_pol elements (analyze() output, mappo.py:244-246) */
+    const float* new_logp, const float* v_pred, const float* entropy, int64_t ld_pol,
+    /* sample side: row t of the loss = row (row_lo + t) of the [L, N] leaves; the caller passes
+     * pointers already offset to row_lo (on_reset_next to row_lo + 1), row stride ld_smp.
+     * lane_idx (int32[n]) selects columns (minibatch gather fused into the load) or NULL. */
+    const float* old_logp, const float* old_value, const float* ret, const float* adv,
+    const uint8_t* on_reset_next, int64_t ld_smp, const int32_t* lane_idx, int T, int n,
+    const double* norm_stats,      /* device [>=3]: GLOBAL (all-reduced) sum mask, sum x, sum x^2   */
+    const double* local_stats,     /* device [>=1]: this rank's sum mask (== norm_stats if 1 rank) */
+    const double* popart_mean_std, /* device {mu, sigma} or NULL                                  */
+    const srl_ppo_hyper* hyper,    /* HOST pointer, copied by value into the launch              */
+    float* g_logp, float* g_value, float* g_entropy, int64_t ld_grad, /* [T, n] out */
+    double* out,      /* device [SRL_LOSS_OUT_LEN] out */
+    float* out_f32,   /* device [4] out: loss, policy_loss, value_loss, entropy_loss, or NULL */
+    void* workspace, size_t workspace_bytes, srl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4b  Same loss, but starting from the actor head's logits: also replaces
+ * ActorCriticPolicy.__get_log_prob_and_entropy / get_action_distribution
+ * (legacy/algorithm/ppo/actor_critic_policies/actor_critic_policy.py:303-324): per head h with K_h
+ * logits z: lp = z - logsumexp(z); logp = sum_h lp[a_h]; H = sum_h -sum_k softmax(z)_k lp_k.
+ * Writes d loss / d logits ([T, n, sumK]) and d loss / d v_pred.
+ * ------------------------------------------------------------------------------------------ */
+#define SRL_MAX_HEADS 8
+int srl_ppo_loss_from_logits(
+    const float* logits,   /* [T, n, sumK] dense */
+    const int32_t* action, /* [T, n, heads]      */
+    const int32_t* head_sizes_host, int heads, const float* v_pred, /* [T, n] dense */
+    const float* old_logp, const float* old_value, const float* ret, const float* adv,
+    const uint8_t* on_reset_next, int64_t ld_smp, const int32_t* lane_idx, int T, int n,
+    const double* norm_stats, const double* local_stats, const double* popart_mean_std,
+    const srl_ppo_hyper* hyper, float* g_logits, /* [T, n, sumK] out */
+    float* g_value,                               /* [T, n] out */
+    float* logp_out, float* entropy_out,          /* [T, n] out or NULL */
+    double* out, float* out_f32, void* workspace, size_t workspace_bytes, srl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5a  Philox-keyed permutation of the environment axis (NEW capability: the reference has no
+ * minibatching; nearest relative SimpleReplayBuffer.get, base/buffer.py:262-277).
+ * out[e*group + a] = perm[e] * group + a for e in [0, n_env), a in [0, group): an 8-round Feistel
+ * bijection on ceil(log2 n_env) bits, round keys from Philox4x32-10(key = seed, counter =
+ * (block, epoch, 'SRLP', 0)), cycle-walked into [0, n_env).  Spec: oracle/ref_math.py:philox_perm_ref.
+ * ------------------------------------------------------------------------------------------ */
+int srl_philox_perm(uint64_t seed, uint32_t epoch, int n_env, int group, int32_t* out, srl_stream_t stream);
+/* Raw Philox4x32-10 blocks (for known-answer tests): out[i] = philox(counter[i], key[i]). */
+int srl_philox4x32_10(const uint32_t* counter, const uint32_t* key, int n_blocks, uint32_t* out,
+                      srl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1 / K5b  Batch assembly and minibatch gather over many leaves in one launch.
+ * For every leaf: dst[t, j, :] = src[t, idx[j], :] for t in [0, L), j in [0, B), rows of `row_bytes`.
+ * Replaces recursive_aggregate(samples, np.stack(axis=1)) in PriorityQueueBuffer.put
+ * (base/buffer.py:118-126, base/namedarray.py:598-633) when src is a slot slab, and
+ * SharedMemoryDock.get = buf[:, sorted(idx)] (base/shared_memory.py:85-99); bit-exact byte copy.
+ * ------------------------------------------------------------------------------------------ */
+#define SRL_MAX_LEAVES 32
+typedef struct srl_leaf_desc {
+  const void* src;   /* [L, src_slots, row_bytes] */
+  void* dst;         /* [L, B, row_bytes]         */
+  int64_t row_bytes; /* bytes per (t, slot) item  */
+  int64_t src_slots; /* slots (columns) in src    */
+} srl_leaf_desc;
+
+int srl_batch_gather(const srl_leaf_desc* leaves_host, int n_leaves, const int32_t* idx /* device [B] or NULL */,
+                     int L, int B, srl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRL_B200_H_ */

@@ -1,0 +1,221 @@
+"""TEST INFRASTRUCTURE ONLY -- writes tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (where /root/reference exists):
+
+    python -O -m oracle.make_golden      # -O as in production (apps/main.py:44): the data-invariant asserts of
+                                         # gae.py:67-78 do not hold for V-trace-scaled deltas at truncations
+
+Every fixture stores the exact inputs and what the reference's own functions returned for them
+(loaded through oracle/ref_loader.py): `MultiAgentPPO._compute_adv_and_value_target`,
+`MultiAgentPPO._compute_loss` + `loss.backward()`, `modules.masked_normalization`,
+`modules.PopArtValueHead`, `base.namedarray.recursive_aggregate`.  The GPU box has no reference;
+tests there compare the CUDA path and the oracle restatement against these files.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+from srl_b200 import synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+LOSS_VARIANTS = {
+    # name: (trainer kwargs, popart, shape cfg)
+    "atari": dict(kw=dict(eps_clip=0.2, clip_value=True, dual_clip=False, value_loss="huber",
+                          value_loss_config=dict(delta=10.0), value_loss_weight=1.0, entropy_bonus_weight=0.01),
+                  popart=False, A=1),
+    "smac": dict(kw=dict(eps_clip=0.2, clip_value=False, dual_clip=True, c_clip=3, value_loss="huber",
+                         value_loss_config=dict(delta=10.0), value_loss_weight=1.0, entropy_bonus_weight=0.01),
+                 popart=True, A=3, dead=0.2),
+    "football": dict(kw=dict(eps_clip=0.2, clip_value=True, dual_clip=True, c_clip=3, value_loss="huber",
+                             value_loss_config=dict(delta=10.0), value_loss_weight=1.0, normalize_old_value=True),
+                     popart=True, A=2),
+    "hns_mse": dict(kw=dict(eps_clip=0.2, clip_value=False, dual_clip=False, value_loss="mse", value_loss_weight=0.5),
+                    popart=True, A=1),
+    "mse_clip_dual": dict(kw=dict(eps_clip=0.1, clip_value=True, value_eps_clip=0.05, dual_clip=True, c_clip=2.0,
+                                  value_loss="mse", value_loss_weight=0.5, entropy_bonus_weight=0.02),
+                          popart=False, A=1),
+    "smoothl1": dict(kw=dict(eps_clip=0.3, clip_value=True, dual_clip=True, value_loss="smoothl1",
+                             value_loss_config=dict(beta=0.5), value_loss_weight=0.7),
+                     popart=False, A=1),
+    "huber_default": dict(kw=dict(clip_value=False, dual_clip=True, value_loss="huber"), popart=False, A=1),
+}
+
+
+def _popart_head(R, seed, n_updates=3):
+    """A PopArtValueHead whose running stats have seen a few batches (so mean/std are non-trivial)."""
+    g = torch.Generator().manual_seed(seed)
+    head = R.popart.PopArtValueHead(4, 1, beta=0.99)
+    for _ in range(n_updates):
+        head.update(torch.randn(50, 1, generator=g) * 3.0 + 1.5, mask=None)
+    return head
+
+
+def _rms_state(head):
+    rms = head._PopArtValueHead__rms
+    return np.array([rms._RunningMeanStd__mean.item(), rms._RunningMeanStd__mean_sq.item(),
+                     rms._RunningMeanStd__debiasing_term.item()], dtype=np.float64)
+
+
+def _sample_namedarray(R, t):
+    NA = R.namedarray.NamedArray
+    return R.trainer.SampleBatch(obs=None, on_reset=t["on_reset"], done=t["done"], truncated=t["truncated"],
+                                 reward=t["reward"],
+                                 analyzed_result=NA(value=t["value"], log_probs=t["old_logp"], adv=t.get("adv"),
+                                                    ret=t.get("ret")))
+
+
+def gen_gae(R):
+    out = {}
+    for name, cfg, popart, vtrace in (
+        ("cfg1", synth.CONFIGS["cfg1_atari_cpu"], False, False),
+        ("cfg1_boot50", synth.PathConfig("cfg1_boot50", T=80, B=32, bootstrap_steps=50, p_end=0.02), False, False),
+        ("smac_small", synth.PathConfig("smac_small", T=40, B=6, A=5, p_end=0.05, gamma=0.99, lmbda=0.95), True, False),
+        ("vtrace", synth.PathConfig("vtrace", T=33, B=20, p_end=0.05, gamma=0.97, lmbda=0.9), False, True),
+        ("ragged", synth.PathConfig("ragged", T=17, B=37, p_end=0.1, gamma=0.9, lmbda=0.8), True, False),
+    ):
+        s = synth.make_sample_scalars(cfg, seed=11)
+        t = {k: torch.from_numpy(v).float() for k, v in s.items()}  # the prefetcher's .float() (api/trainer.py:217)
+        head = _popart_head(R, 5) if popart else None
+        tr = R.mappo.MultiAgentPPO(ref_loader.FakePolicy(popart_head=head), discount_rate=cfg.gamma,
+                                   gae_lambda=cfg.lmbda, popart=popart, vtrace=vtrace)
+        analyzed = None
+        extra = {}
+        if vtrace:
+            g = torch.Generator().manual_seed(3)
+            newlp = t["old_logp"][:-1] + 0.3 * torch.randn(t["old_logp"][:-1].shape, generator=g)
+            analyzed = R.mappo.SampleAnalyzedResult(old_action_log_probs=t["old_logp"][:-1], new_action_log_probs=newlp,
+                                                    state_values=None)
+            extra["vtrace_new_logp"] = newlp.numpy()
+        adv, ret = tr._compute_adv_and_value_target(_sample_namedarray(R, t), analyzed)
+        fx = dict(s)
+        fx.update(extra)
+        fx.update(adv=adv.numpy(), ret=ret.numpy(), gamma=np.float64(cfg.gamma), lmbda=np.float64(cfg.lmbda),
+                  popart=np.bool_(popart), vtrace=np.bool_(vtrace))
+        if popart:
+            m, sd = head._PopArtValueHead__rms.mean_std()
+            fx.update(popart_mean_std=np.array([m.item(), sd.item()], dtype=np.float64))
+        out[name] = fx
+    for name, fx in out.items():
+        np.savez_compressed(os.path.join(GOLDEN, f"gae_{name}.npz"), **fx)
+    return list(out)
+
+
+def gen_loss(R):
+    names = []
+    for name, v in LOSS_VARIANTS.items():
+        A = v["A"]
+        cfg = synth.PathConfig(name, T=12, B=10, A=A, p_end=0.08, gamma=0.99, lmbda=0.95, popart=v["popart"],
+                               dead_agent_frac=v.get("dead", 0.0), num_actions=(18,))
+        s = synth.make_sample_scalars(cfg, seed=21)
+        pol = synth.make_policy_outputs(cfg, s, seed=22, epochs=1)
+        t = {k: torch.from_numpy(x).float() for k, x in s.items()}
+        head = _popart_head(R, 9) if v["popart"] else None
+        fake = ref_loader.FakePolicy(popart_head=head,
+                                     denormalize_value_during_rollout=v["kw"].get("normalize_old_value", False))
+        tr = R.mappo.MultiAgentPPO(fake, discount_rate=cfg.gamma, gae_lambda=cfg.lmbda, popart=v["popart"], **v["kw"])
+        adv, ret = tr._compute_adv_and_value_target(_sample_namedarray(R, t), None)
+        pad = lambda x: torch.cat([x, torch.zeros_like(x[:1])], 0)  # mappo.py:254-256
+        t["adv"], t["ret"] = pad(adv), pad(ret)
+        L = cfg.L
+        lo, hi = 0, L - 1
+        sample = _sample_namedarray(R, t)
+        valid = sample[lo:hi]
+        mask = 1 - t["on_reset"][lo + 1:hi + 1]  # mappo.py:260-261
+        pre_state = _rms_state(head) if head is not None else None
+        if v["popart"]:
+            fake.update_popart(valid.analyzed_result.ret, mask=mask)  # mappo.py:263-264
+        nl = torch.from_numpy(pol["new_logp"][0]).requires_grad_(True)
+        vp = torch.from_numpy(pol["v_pred"][0]).requires_grad_(True)
+        en = torch.from_numpy(pol["entropy"][0]).requires_grad_(True)
+        analyzed = R.mappo.SampleAnalyzedResult(old_action_log_probs=t["old_logp"][lo:hi], new_action_log_probs=nl,
+                                                state_values=vp, entropy=en)
+        loss, res = tr._compute_loss(valid, analyzed, mask)
+        loss.backward()
+        stats = {f"stat_{k}": np.float64(getattr(res, k).detach().float().mean().item())
+                 for k in ("advantage", "entropy", "policy_loss", "value_loss", "importance_weight", "clip_ratio",
+                           "value_targets")}
+        if res.denorm_value is not None:
+            stats["stat_denorm_value"] = np.float64(res.denorm_value.mean().item())
+        fx = dict(s)
+        fx.update(new_logp=pol["new_logp"][0], v_pred=pol["v_pred"][0], entropy=pol["entropy"][0],
+                  adv=t["adv"].numpy(), ret=t["ret"].numpy(), loss=np.float64(loss.item()), g_logp=nl.grad.numpy(),
+                  g_value=vp.grad.numpy(), g_entropy=en.grad.numpy(), gamma=np.float64(cfg.gamma),
+                  lmbda=np.float64(cfg.lmbda), **stats)
+        if head is not None:
+            m, sd = head._PopArtValueHead__rms.mean_std()
+            fx.update(popart_state_before=pre_state, popart_state_after=_rms_state(head),
+                      popart_mean_std_after=np.array([m.item(), sd.item()], dtype=np.float64), popart_beta=np.float64(0.99))
+        np.savez_compressed(os.path.join(GOLDEN, f"loss_{name}.npz"), **fx)
+        names.append(name)
+    return names
+
+
+def gen_masknorm_popart(R):
+    rng = np.random.Generator(np.random.PCG64(31))
+    adv = rng.standard_normal((10, 8, 1)).astype(np.float32)
+    mask = rng.integers(0, 2, (10, 8, 1)).astype(np.float32)
+    out = R.utils.masked_normalization(torch.from_numpy(adv), torch.from_numpy(mask)).numpy()
+    out_nomask = R.utils.masked_normalization(torch.from_numpy(adv), None).numpy()
+    # PopArt sequence: updates with and without mask, normalise / denormalise after each
+    head = R.popart.PopArtValueHead(4, 1, beta=0.999)
+    xs = rng.standard_normal((4, 30, 1)).astype(np.float32) * 2.0 + 0.5
+    ms = (rng.random((4, 30, 1)) < 0.7).astype(np.float32)
+    y = rng.standard_normal((20, 1)).astype(np.float32)
+    states, norms, denorms = [], [], []
+    for i in range(4):
+        head.update(torch.from_numpy(xs[i]), mask=torch.from_numpy(ms[i]) if i % 2 else None)
+        states.append(_rms_state(head))
+        norms.append(head.normalize(torch.from_numpy(y)).numpy())
+        denorms.append(head.denormalize(torch.from_numpy(y)).numpy())
+    np.savez_compressed(os.path.join(GOLDEN, "masknorm_popart.npz"), adv=adv, mask=mask, norm_adv=out,
+                        norm_adv_nomask=out_nomask, pa_x=xs, pa_mask=ms, pa_y=y, pa_states=np.stack(states),
+                        pa_norm=np.stack(norms), pa_denorm=np.stack(denorms), pa_beta=np.float64(0.999))
+
+
+def gen_stack(R):
+    """recursive_aggregate(np.stack(axis=1)) incl. a leaf that is None in some samples (namedarray.py:588-633)."""
+    NA = R.namedarray.NamedArray
+    rng = np.random.Generator(np.random.PCG64(41))
+    L, B = 5, 6
+    samples, flat = [], {}
+    for b in range(B):
+        obs = NA(frame=rng.integers(0, 256, (L, 2, 3, 3), dtype=np.uint8), vec=rng.standard_normal((L, 7)).astype(np.float32))
+        reward = rng.standard_normal((L, 1)).astype(np.float32)
+        on_reset = rng.integers(0, 2, (L, 1), dtype=np.uint8)
+        trunc = None if b % 2 == 0 else rng.integers(0, 2, (L, 1), dtype=np.uint8)
+        samples.append(R.trainer.SampleBatch(obs=obs, reward=reward, on_reset=on_reset, truncated=trunc))
+        flat[f"s{b}.obs.frame"], flat[f"s{b}.obs.vec"] = obs.frame, obs.vec
+        flat[f"s{b}.reward"], flat[f"s{b}.on_reset"] = reward, on_reset
+        if trunc is not None:
+            flat[f"s{b}.truncated"] = trunc
+    agg = R.namedarray.recursive_aggregate(samples, lambda x: np.stack(x, axis=1))
+    for k, v in R.namedarray.flatten(agg):
+        if v is not None:
+            flat[f"out.{k}"] = v
+    flat["out_keys"] = np.array([k for k, v in R.namedarray.flatten(agg) if v is not None])
+    np.savez_compressed(os.path.join(GOLDEN, "stack.npz"), **flat)
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.manual_seed(0)
+    R = ref_loader.load()
+    print("gae:", gen_gae(R))
+    print("loss:", gen_loss(R))
+    gen_masknorm_popart(R)
+    gen_stack(R)
+    total = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))
+    print(f"wrote {len(os.listdir(GOLDEN))} files, {total / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,51 @@
+// Library-level plumbing: status/error text, device queries.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace srl {
+namespace {
+thread_local char g_err[512] = "";
+}
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+}  // namespace srl
+
+extern "C" const char* srl_last_error(void) { return srl::g_err; }
+
+extern "C" int srl_abi_version(void) { return SRL_B200_ABI_VERSION; }
+
+extern "C" int srl_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  using namespace srl;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  SRL_REQUIRE(e == cudaSuccess && n > 0, SRL_ERR_NO_DEVICE, "no CUDA device visible (%s)", cudaGetErrorString(e));
+  int dev = 0;
+  SRL_CUDA(cudaGetDevice(&dev));
+  int sms = 0, maj = 0, min = 0;
+  SRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  SRL_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+  SRL_CUDA(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm_count) *sm_count = sms;
+  if (cc_major) *cc_major = maj;
+  if (cc_minor) *cc_minor = min;
+  return SRL_OK;
+}

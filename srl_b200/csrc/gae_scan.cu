@@ -1,0 +1,256 @@
+// K2: GAE / value-target reverse-time scan (see include/srl_b200.h for the contract and the
+// reference lines it replaces: mappo.py:118-144,254-256; gae.py:8-97; utils.py:54-57,113-120).
+//
+// Design (one CTA = a tile of LW adjacent lanes x all L rows, staged in shared memory):
+//   phase A1  all 256 threads: coalesced row-segment loads of value/done/truncated/on_reset,
+//             v' = (popart-denormalised) value * (1 - done)  -> smem (fp32) + flag byte
+//   phase A2  all threads: delta_t (fp64, explicit mul/add roundings, no FMA contraction -- the
+//             reference evaluates each torch op separately) and the carry factor m_t -> smem
+//   phase B   one warp: the only truly sequential part, A_t = delta_t + m_t * A_{t+1} in fp64 out of
+//             shared memory (loads do not depend on the chain, so they pipeline)
+//   phase C   all threads: ret = adv + v', coalesced stores of adv/ret (padding row zeroed) and the
+//             per-lane float64 partial sums that masked_normalization / PopArt need
+// Every global byte is read once and written once: 11 B in + 8 B out per scanned row-lane.
+#include "common.cuh"
+
+namespace srl {
+namespace {
+
+constexpr int kThreads = 256;
+
+struct GaeParams {
+  const float* reward;
+  const float* value;
+  const uint8_t* done;
+  const uint8_t* truncated;
+  const uint8_t* on_reset;
+  const float* vt_new_logp;
+  const float* vt_old_logp;
+  const double* popart;  // {mean, std} or null
+  float* adv;
+  float* ret;
+  double* lane_part;
+  int L, N, row_lo, row_hi;
+  double gamma, gamma_lmbda, rho, c;
+};
+
+__host__ __device__ constexpr size_t gae_smem_bytes(int L, int LW, bool vtrace) {
+  // delta (f64) [+ m (f64)] + v' (f32) + flags (u8) + kill (u8), each [L][LW]
+  // (the per-lane reduction scratch [kThreads/LW][7][LW] f64 = 14 KB aliases the same bytes)
+  const size_t tile = static_cast<size_t>(L) * LW * (8 + (vtrace ? 8 : 0) + 4 + 1 + 1);
+  const size_t scratch = static_cast<size_t>(kThreads) * 7 * 8;
+  return tile > scratch ? tile : scratch;
+}
+
+template <int LW, bool VTRACE>
+__global__ void __launch_bounds__(kThreads) gae_scan_kernel(const GaeParams p) {
+  constexpr int RPP = kThreads / LW;  // rows handled per pass of the CTA
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int L = p.L, N = p.N;
+  double* sd = reinterpret_cast<double*>(smem_raw);                 // [L][LW] delta, later adv(f32) in place
+  double* sm = sd + static_cast<size_t>(L) * LW;                    // [L][LW] m (VTRACE only)
+  float* sv = reinterpret_cast<float*>(VTRACE ? sm + static_cast<size_t>(L) * LW : sm);  // [L][LW] v'
+  uint8_t* sf = reinterpret_cast<uint8_t*>(sv + static_cast<size_t>(L) * LW);            // [L][LW] flags
+  uint8_t* sk = sf + static_cast<size_t>(L) * LW;                                        // [L][LW] kill
+
+  const int tid = threadIdx.x;
+  const int lane = tid % LW;
+  const int trow = tid / LW;
+  const int col = blockIdx.x * LW + lane;
+  const bool live = col < N;
+
+  double pa_mean = 0.0, pa_std = 1.0;
+  const bool popart = p.popart != nullptr;
+  if (popart) {
+    pa_mean = p.popart[0];
+    pa_std = p.popart[1];
+  }
+
+  // ---- A1: v'[t] and flag byte for every row --------------------------------------------------
+  for (int t = trow; t < L; t += RPP) {
+    float v = 0.f;
+    uint32_t f = 0;
+    if (live) {
+      const size_t g = static_cast<size_t>(t) * N + col;
+      v = ldg_stream(p.value + g);
+      const uint32_t dn = ldg_stream(p.done + g), tr = ldg_stream(p.truncated + g), rs = ldg_stream(p.on_reset + g);
+      if (popart)  // RunningMeanStd.denormalize: (x.double() * std + mean).float()   utils.py:146-151
+        v = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(v), pa_std), pa_mean));
+      v = __fmul_rn(v, 1.f - static_cast<float>(dn != 0));  // value * (1 - done), fp32   mappo.py:120-124
+      f = (dn != 0 ? 1u : 0u) | (tr != 0 ? 2u : 0u) | (rs != 0 ? 4u : 0u);
+    }
+    sv[t * LW + lane] = v;
+    sf[t * LW + lane] = static_cast<uint8_t>(f);
+  }
+  __syncthreads();
+
+  // ---- A2: delta_t and m_t for t in [0, L-1) --------------------------------------------------
+  for (int t = trow; t < L - 1; t += RPP) {
+    const uint32_t f1 = sf[(t + 1) * LW + lane];
+    const double alive = (f1 & 4u) ? 0.0 : 1.0;     // 1 - on_reset[t+1]
+    const double not_tr = (f1 & 2u) ? 0.0 : 1.0;    // 1 - truncated[t+1]
+    float r = 0.f;
+    if (live) r = ldg_stream(p.reward + static_cast<size_t>(t) * N + col);
+    const double v1 = static_cast<double>(sv[(t + 1) * LW + lane]);
+    const double v0 = static_cast<double>(sv[t * LW + lane]);
+    // gae.py:63  reward + gamma * value[1:] * (1 - on_reset[1:]) - value[:-1]
+    double d = __dmul_rn(__dmul_rn(p.gamma, v1), alive);
+    d = __dadd_rn(static_cast<double>(r), d);
+    d = __dsub_rn(d, v0);
+    if (VTRACE) {
+      // gae.py:87  gamma * lmbda * (1 - on_reset[1:]) * (1 - truncated[1:])
+      double m = __dmul_rn(__dmul_rn(p.gamma_lmbda, alive), not_tr);
+      float ratio = 1.f;
+      if (live) {
+        const size_t g = static_cast<size_t>(t) * N + col;
+        ratio = expf(ldg_stream(p.vt_new_logp + g) - ldg_stream(p.vt_old_logp + g));  // mappo.py:129-132
+      }
+      const double rd = static_cast<double>(ratio);
+      d = __dmul_rn(d, fmin(rd, p.rho));  // gae.py:64-65
+      m = __dmul_rn(m, fmin(rd, p.c));    // gae.py:88-89
+      sm[t * LW + lane] = m;
+    } else {
+      sk[t * LW + lane] = (f1 & 6u) ? 1 : 0;  // m is exactly 0 or gamma*lmbda
+    }
+    sd[t * LW + lane] = d;
+  }
+  __syncthreads();
+
+  // ---- B: the sequential scan, one warp -------------------------------------------------------
+  if (tid < LW) {
+    double g = 0.0;
+    const double gl = p.gamma_lmbda;
+#pragma unroll 8
+    for (int t = L - 2; t >= 0; --t) {
+      const double d = sd[t * LW + lane];
+      double m;
+      if (VTRACE)
+        m = sm[t * LW + lane];
+      else
+        m = sk[t * LW + lane] ? 0.0 : gl;
+      g = __dadd_rn(d, __dmul_rn(m, g));  // gae.py:92  (separate mul and add, as two torch ops)
+      reinterpret_cast<float*>(sd + t * LW + lane)[0] = static_cast<float>(g);  // adv.float(), gae.py:97
+    }
+  }
+  __syncthreads();
+
+  // ---- C: ret, stores, per-lane partial sums --------------------------------------------------
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0;
+  for (int t = trow; t < L; t += RPP) {
+    float a = 0.f, r = 0.f;
+    if (t < L - 1) {
+      a = reinterpret_cast<const float*>(sd + t * LW + lane)[0];
+      r = __fadd_rn(a, sv[t * LW + lane]);  // value_target = adv + v'[:-1], fp32   mappo.py:143
+      if (t >= p.row_lo && t < p.row_hi) {
+        const uint32_t f0 = sf[t * LW + lane], f1 = sf[(t + 1) * LW + lane];
+        const double mk = (f1 & 4u) ? 0.0 : 1.0;  // loss mask = 1 - on_reset[t+1]   mappo.py:260-261
+        const double x = __dmul_rn(static_cast<double>(a), mk);
+        const double y = __dmul_rn(static_cast<double>(r), mk);
+        s0 += mk;
+        s1 += x;
+        s2 = __dadd_rn(s2, __dmul_rn(x, x));
+        s3 += y;
+        s4 = __dadd_rn(s4, __dmul_rn(y, y));
+        s5 += (f0 & 1u) ? 1.0 : 0.0;
+        s6 += (f0 & 2u) ? 1.0 : 0.0;
+      }
+    }
+    if (live) {  // row L-1 is the zero padding row of mappo.py:254-256
+      const size_t g = static_cast<size_t>(t) * N + col;
+      stg_stream(p.adv + g, a);
+      stg_stream(p.ret + g, r);
+    }
+  }
+  if (p.lane_part != nullptr) {
+    __syncthreads();  // the tile is dead; reuse its bytes as [RPP][7][LW] f64
+    double* red = sd;
+    red[(trow * 7 + 0) * LW + lane] = s0;
+    red[(trow * 7 + 1) * LW + lane] = s1;
+    red[(trow * 7 + 2) * LW + lane] = s2;
+    red[(trow * 7 + 3) * LW + lane] = s3;
+    red[(trow * 7 + 4) * LW + lane] = s4;
+    red[(trow * 7 + 5) * LW + lane] = s5;
+    red[(trow * 7 + 6) * LW + lane] = s6;
+    __syncthreads();
+    // 8 * LW outputs; fixed summation order over the RPP row groups
+    for (int o = tid; o < SRL_LANE_PART * LW; o += kThreads) {
+      const int k = o / LW, ln = o % LW;
+      const int c2 = blockIdx.x * LW + ln;
+      if (c2 < N) {
+        double s = 0.0;
+        if (k < 7)
+          for (int rr = 0; rr < RPP; ++rr) s += red[(rr * 7 + k) * LW + ln];
+        p.lane_part[static_cast<size_t>(k) * N + c2] = s;
+      }
+    }
+  }
+}
+
+template <int LW, bool VTRACE>
+int launch(const GaeParams& p, cudaStream_t st) {
+  const size_t smem = gae_smem_bytes(p.L, LW, VTRACE);
+  auto kern = gae_scan_kernel<LW, VTRACE>;
+  SRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int grid = (p.N + LW - 1) / LW;
+  kern<<<grid, kThreads, smem, st>>>(p);
+  SRL_CUDA(cudaGetLastError());
+  return SRL_OK;
+}
+
+constexpr size_t kSmemBudget = 200 * 1024;
+
+}  // namespace
+}  // namespace srl
+
+extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8_t* done, const uint8_t* truncated,
+                            const uint8_t* on_reset, const float* vtrace_new_logp, const float* vtrace_old_logp,
+                            const double* popart_mean_std, int L, int N, int row_lo, int row_hi, double gamma,
+                            double lmbda, double rho, double c, float* adv, float* ret, double* lane_part,
+                            srl_stream_t stream) {
+  using namespace srl;
+  SRL_REQUIRE(L >= 2 && N >= 1, SRL_ERR_INVALID_ARG, "srl_gae_scan: need L >= 2 and N >= 1 (got L=%d N=%d)", L, N);
+  SRL_REQUIRE(reward && value && done && truncated && on_reset && adv && ret, SRL_ERR_INVALID_ARG,
+              "srl_gae_scan: null tensor pointer");
+  SRL_REQUIRE((vtrace_new_logp == nullptr) == (vtrace_old_logp == nullptr), SRL_ERR_INVALID_ARG,
+              "srl_gae_scan: vtrace needs both log-prob tensors");
+  SRL_REQUIRE(row_lo >= 0 && row_lo <= row_hi && row_hi <= L - 1, SRL_ERR_INVALID_ARG,
+              "srl_gae_scan: loss rows [%d, %d) must lie inside [0, L-1=%d]", row_lo, row_hi, L - 1);
+  const bool vtrace = vtrace_new_logp != nullptr;
+  GaeParams p;
+  p.reward = reward;
+  p.value = value;
+  p.done = done;
+  p.truncated = truncated;
+  p.on_reset = on_reset;
+  p.vt_new_logp = vtrace_new_logp;
+  p.vt_old_logp = vtrace_old_logp;
+  p.popart = popart_mean_std;
+  p.adv = adv;
+  p.ret = ret;
+  p.lane_part = lane_part;
+  p.L = L;
+  p.N = N;
+  p.row_lo = row_lo;
+  p.row_hi = row_hi;
+  p.gamma = gamma;
+  p.gamma_lmbda = gamma * lmbda;  // python evaluates gamma * lmbda first (gae.py:87)
+  p.rho = rho;
+  p.c = c;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  // Lane-tile width: the widest tile that (a) fits shared memory and (b) still gives every SM work.
+  const int sms = sm_count();
+  int lw = 32;
+  while (lw > 8 && (gae_smem_bytes(L, lw, vtrace) > kSmemBudget || (N + lw - 1) / lw < 2 * sms)) lw >>= 1;
+  SRL_REQUIRE(gae_smem_bytes(L, lw, vtrace) <= kSmemBudget, SRL_ERR_UNSUPPORTED,
+              "srl_gae_scan: L=%d does not fit the shared-memory tile (max L ~ %d)", L,
+              static_cast<int>(kSmemBudget / (8 * (vtrace ? 22 : 14))));
+  if (vtrace) {
+    if (lw == 32) return launch<32, true>(p, st);
+    if (lw == 16) return launch<16, true>(p, st);
+    return launch<8, true>(p, st);
+  }
+  if (lw == 32) return launch<32, false>(p, st);
+  if (lw == 16) return launch<16, false>(p, st);
+  return launch<8, false>(p, st);
+}

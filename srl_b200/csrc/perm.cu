@@ -1,0 +1,124 @@
+// K5a: Philox-keyed permutation of the environment axis (new capability).
+// Spec = oracle/ref_math.py:philox_perm_ref (numpy); this file must match it bit for bit.
+#include "common.cuh"
+
+namespace srl {
+
+struct Philox4 {
+  uint32_t c[4];
+};
+
+// Philox4x32-10, Salmon et al. SC'11 (Random123); constants as published.
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(Philox4 ctr, uint32_t k0, uint32_t k1) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = static_cast<uint64_t>(M0) * ctr.c[0];
+    const uint64_t p1 = static_cast<uint64_t>(M1) * ctr.c[2];
+    Philox4 n;
+    n.c[0] = static_cast<uint32_t>(p1 >> 32) ^ ctr.c[1] ^ k0;
+    n.c[1] = static_cast<uint32_t>(p1);
+    n.c[2] = static_cast<uint32_t>(p0 >> 32) ^ ctr.c[3] ^ k1;
+    n.c[3] = static_cast<uint32_t>(p0);
+    ctr = n;
+    k0 += W0;
+    k1 += W1;
+  }
+  return ctr;
+}
+
+struct PermKeys {
+  uint32_t rk[8];
+  uint32_t lb, lmask, hmask;
+};
+
+__host__ __device__ __forceinline__ uint32_t feistel8(uint32_t x, const PermKeys& k) {
+  uint32_t lo = x & k.lmask, hi = (x >> k.lb) & k.hmask;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    if ((r & 1) == 0) {
+      uint32_t f = static_cast<uint32_t>((static_cast<uint64_t>(0xD2511F53u) * (lo ^ k.rk[r])) >> 32);
+      f ^= (lo * 0x9E3779B9u) >> 16;
+      hi = (hi ^ f) & k.hmask;
+    } else {
+      uint32_t f = static_cast<uint32_t>((static_cast<uint64_t>(0xCD9E8D57u) * (hi ^ k.rk[r])) >> 32);
+      f ^= (hi * 0xBB67AE85u) >> 16;
+      lo = (lo ^ f) & k.lmask;
+    }
+  }
+  return (hi << k.lb) | lo;
+}
+
+namespace {
+
+__global__ void __launch_bounds__(256) philox_perm_kernel(uint32_t seed_lo, uint32_t seed_hi, uint32_t epoch, int n_env,
+                                                         int group, int bits, int32_t* __restrict__ out) {
+  __shared__ PermKeys keys;
+  if (threadIdx.x < 2) {  // two Philox blocks -> eight round keys
+    Philox4 ctr;
+    ctr.c[0] = threadIdx.x;
+    ctr.c[1] = epoch;
+    ctr.c[2] = 0x53524C50u;  // 'SRLP'
+    ctr.c[3] = 0u;
+    const Philox4 o = philox4x32_10(ctr, seed_lo, seed_hi);
+    for (int i = 0; i < 4; ++i) keys.rk[threadIdx.x * 4 + i] = o.c[i];
+  }
+  if (threadIdx.x == 2) {
+    const int lb = bits / 2, hb = bits - lb;
+    keys.lb = lb;
+    keys.lmask = (1u << lb) - 1u;
+    keys.hmask = (1u << hb) - 1u;
+  }
+  __syncthreads();
+  const PermKeys k = keys;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_env; e += gridDim.x * blockDim.x) {
+    uint32_t x = feistel8(static_cast<uint32_t>(e), k);
+    while (x >= static_cast<uint32_t>(n_env)) x = feistel8(x, k);  // cycle-walk back into [0, n_env)
+    for (int a = 0; a < group; ++a) out[static_cast<size_t>(e) * group + a] = static_cast<int32_t>(x) * group + a;
+  }
+}
+
+__global__ void philox_blocks_kernel(const uint32_t* __restrict__ counter, const uint32_t* __restrict__ key, int n,
+                                     uint32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Philox4 c;
+  for (int q = 0; q < 4; ++q) c.c[q] = counter[4 * i + q];
+  const Philox4 o = philox4x32_10(c, key[2 * i], key[2 * i + 1]);
+  for (int q = 0; q < 4; ++q) out[4 * i + q] = o.c[q];
+}
+
+}  // namespace
+}  // namespace srl
+
+extern "C" int srl_philox_perm(uint64_t seed, uint32_t epoch, int n_env, int group, int32_t* out, srl_stream_t stream) {
+  using namespace srl;
+  SRL_REQUIRE(n_env >= 0 && group >= 1, SRL_ERR_INVALID_ARG, "srl_philox_perm: need n_env >= 0 and group >= 1");
+  if (n_env == 0) return SRL_OK;
+  SRL_REQUIRE(out != nullptr, SRL_ERR_INVALID_ARG, "srl_philox_perm: null output");
+  SRL_REQUIRE(static_cast<long long>(n_env) * group < (1ll << 31), SRL_ERR_UNSUPPORTED,
+              "srl_philox_perm: n_env * group must fit int32");
+  int bits = 0;
+  while ((1ll << bits) < n_env) ++bits;  // == (n_env - 1).bit_length()
+  if (bits < 2) bits = 2;
+  const int threads = 256;
+  int grid = (n_env + threads - 1) / threads;
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  philox_perm_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint32_t>(seed & 0xffffffffull), static_cast<uint32_t>(seed >> 32), epoch, n_env, group, bits, out);
+  SRL_CUDA(cudaGetLastError());
+  return SRL_OK;
+}
+
+extern "C" int srl_philox4x32_10(const uint32_t* counter, const uint32_t* key, int n_blocks, uint32_t* out,
+                                 srl_stream_t stream) {
+  using namespace srl;
+  SRL_REQUIRE(n_blocks >= 0, SRL_ERR_INVALID_ARG, "srl_philox4x32_10: negative block count");
+  if (n_blocks == 0) return SRL_OK;
+  SRL_REQUIRE(counter && key && out, SRL_ERR_INVALID_ARG, "srl_philox4x32_10: null pointer");
+  philox_blocks_kernel<<<(n_blocks + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(counter, key, n_blocks,
+                                                                                             out);
+  SRL_CUDA(cudaGetLastError());
+  return SRL_OK;
+}

@@ -1,0 +1,112 @@
+// Group statistics over K2's per-lane partial sums, and the PopArt / RunningMeanStd update (K3).
+// See include/srl_b200.h: replaces the reductions + 3+3 single-element all-reduces of
+// utils.py:54-61 (masked_normalization) and utils.py:113-130 (RunningMeanStd.update).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace srl {
+namespace {
+
+constexpr int kClusterX = 8;  // CTAs cooperating on one group through distributed shared memory
+constexpr int kThreads = 256;
+
+// grid = (kClusterX, G).  CTA r of the cluster sums lanes [r*chunk, (r+1)*chunk) of group g, then CTA 0
+// adds the 8 CTA results in rank order through DSMEM: fixed summation order, no atomics, no scratch.
+__global__ void __cluster_dims__(kClusterX, 1, 1) __launch_bounds__(kThreads)
+    group_stats_kernel(const double* __restrict__ lane_part, int N, const int32_t* __restrict__ idx, int per,
+                       double* __restrict__ out) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int g = blockIdx.y;
+  const int r = static_cast<int>(cluster.block_rank());
+  const int chunk = (per + kClusterX - 1) / kClusterX;
+  const int j0 = r * chunk, j1 = min(per, j0 + chunk);
+
+  double acc[SRL_LANE_PART];
+#pragma unroll
+  for (int k = 0; k < SRL_LANE_PART; ++k) acc[k] = 0.0;
+  for (int j = j0 + threadIdx.x; j < j1; j += kThreads) {
+    const int lane = idx ? idx[static_cast<size_t>(g) * per + j] : g * per + j;
+#pragma unroll
+    for (int k = 0; k < SRL_LANE_PART - 1; ++k) acc[k] += __ldg(lane_part + static_cast<size_t>(k) * N + lane);
+  }
+  __shared__ double wsum[SRL_LANE_PART][kThreads / 32];
+  __shared__ double cta_sum[SRL_LANE_PART];
+  const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < SRL_LANE_PART; ++k) {
+    const double s = warp_sum(acc[k]);
+    if (ln == 0) wsum[k][warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < SRL_LANE_PART) {
+    double s = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) s += wsum[threadIdx.x][w];
+    cta_sum[threadIdx.x] = s;
+  }
+  cluster.sync();
+  if (r == 0 && threadIdx.x < SRL_LANE_PART) {
+    double s = 0.0;
+    for (int q = 0; q < kClusterX; ++q) {
+      const double* remote = cluster.map_shared_rank(cta_sum, q);
+      s += remote[threadIdx.x];
+    }
+    out[static_cast<size_t>(g) * SRL_LANE_PART + threadIdx.x] = s;
+  }
+  cluster.sync();  // keep every CTA's shared memory alive until rank 0 has read it
+}
+
+__global__ void popart_update_kernel(const double* __restrict__ bs, double* __restrict__ state, double beta,
+                                     double eps, double* __restrict__ ms) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double mean = state[0], mean_sq = state[1], debias = state[2];
+  // statistics before the update (PopArtValueHead.update reads them for the head rescale, popart.py:43)
+  {
+    const double d = fmax(debias, eps);
+    const double mu = mean / d;
+    ms[2] = mu;
+    ms[3] = sqrt(fmax(__dsub_rn(mean_sq / d, __dmul_rn(mu, mu)), 1e-2));
+  }
+  const double cnt = bs[0];
+  const double bm = bs[3] / cnt, bsq = bs[4] / cnt;  // utils.py:125-126
+  const double omb = 1.0 - beta;
+  mean = __dadd_rn(__dmul_rn(beta, mean), __dmul_rn(bm, omb));         // utils.py:128
+  mean_sq = __dadd_rn(__dmul_rn(beta, mean_sq), __dmul_rn(bsq, omb));  // utils.py:129
+  debias = __dsub_rn(__dadd_rn(__dmul_rn(beta, debias), 1.0), beta);   // utils.py:130
+  state[0] = mean;
+  state[1] = mean_sq;
+  state[2] = debias;
+  state[3] += 1.0;
+  const double d = fmax(debias, eps);  // utils.py:134-137
+  const double mu = mean / d;
+  ms[0] = mu;
+  ms[1] = sqrt(fmax(__dsub_rn(mean_sq / d, __dmul_rn(mu, mu)), 1e-2));
+}
+
+}  // namespace
+}  // namespace srl
+
+extern "C" int srl_group_stats(const double* lane_part, int N, const int32_t* idx, int G, int per, double* out,
+                               srl_stream_t stream) {
+  using namespace srl;
+  SRL_REQUIRE(lane_part && out, SRL_ERR_INVALID_ARG, "srl_group_stats: null pointer");
+  SRL_REQUIRE(N >= 1 && G >= 1 && per >= 1, SRL_ERR_INVALID_ARG, "srl_group_stats: need N, G, per >= 1");
+  SRL_REQUIRE(idx != nullptr || static_cast<long long>(G) * per <= N, SRL_ERR_INVALID_ARG,
+              "srl_group_stats: G*per=%lld exceeds N=%d", static_cast<long long>(G) * per, N);
+  SRL_REQUIRE(G <= 65535, SRL_ERR_UNSUPPORTED, "srl_group_stats: at most 65535 groups");
+  group_stats_kernel<<<dim3(kClusterX, G), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(lane_part, N, idx, per,
+                                                                                             out);
+  SRL_CUDA(cudaGetLastError());
+  return SRL_OK;
+}
+
+extern "C" int srl_popart_update(const double* batch_stats, double* state, double beta, double eps,
+                                 double* mean_std_out, srl_stream_t stream) {
+  using namespace srl;
+  SRL_REQUIRE(batch_stats && state && mean_std_out, SRL_ERR_INVALID_ARG, "srl_popart_update: null pointer");
+  popart_update_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(batch_stats, state, beta, eps, mean_std_out);
+  SRL_CUDA(cudaGetLastError());
+  return SRL_OK;
+}

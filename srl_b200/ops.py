@@ -1,0 +1,348 @@
+"""Tensor-level entry points: torch CUDA tensors in, C-ABI calls on the current stream, tensors out.
+
+torch is plumbing here (device memory, streams); every computation happens inside libsrl_b200.so.
+All functions raise (never fall back) when the library is missing or a tensor is not a contiguous
+CUDA tensor of the expected dtype.  Reference lines each op replaces are in include/srl_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from srl_b200 import _lib
+from srl_b200._lib import (SRL_LANE_PART, SRL_LOSS_OUT_LEN, SRL_MAX_HEADS, SRL_MAX_LEAVES, LeafDesc, PpoHyper,
+                           VALUE_LOSS_CODES)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _check(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (srl_b200 has no CPU path), got {type(t).__name__}"
+                         f"{'' if not isinstance(t, torch.Tensor) else ' on ' + str(t.device)}")
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor, got strides {t.stride()} for shape {tuple(t.shape)}")
+    return t
+
+
+def _rows_lanes(t: torch.Tensor) -> Tuple[int, int]:
+    """[L, B, (A,) 1] or [L, N] -> (L, N)."""
+    if t.dim() < 2:
+        raise ValueError(f"expected a time-major [L, N, ...] tensor, got shape {tuple(t.shape)}")
+    return t.shape[0], t[0].numel()
+
+
+# ------------------------------------------------------------------------------------------------
+# K2
+# ------------------------------------------------------------------------------------------------
+def gae_scan(reward, value, done, truncated, on_reset, gamma: float, lmbda: float, row_lo: int = 0,
+             row_hi: Optional[int] = None, popart_mean_std: Optional[torch.Tensor] = None,
+             vtrace_new_logp: Optional[torch.Tensor] = None, vtrace_old_logp: Optional[torch.Tensor] = None,
+             rho: float = 1.0, c: float = 1.0, adv: Optional[torch.Tensor] = None,
+             ret: Optional[torch.Tensor] = None, lane_part: Optional[torch.Tensor] = None, want_stats: bool = True):
+    """GAE + value target + zero padding row + per-lane statistics in one launch.
+
+    reward/value float32 and done/truncated/on_reset uint8, all `[L, N(, 1)]`; returns
+    (adv, ret) shaped like `value` and lane_part float64 `[8, N]` (or None).
+    Reference: MultiAgentPPO._compute_adv_and_value_target (mappo.py:118-144) + F.pad (mappo.py:254-256).
+    """
+    L, N = _rows_lanes(value)
+    for name, t in (("reward", reward), ("value", value)):
+        _check(t, torch.float32, name)
+    for name, t in (("done", done), ("truncated", truncated), ("on_reset", on_reset)):
+        _check(t, torch.uint8, name)
+    for name, t in (("reward", reward), ("done", done), ("truncated", truncated), ("on_reset", on_reset)):
+        if _rows_lanes(t) != (L, N):
+            raise ValueError(f"{name}: shape {tuple(t.shape)} does not match value {tuple(value.shape)}")
+    if row_hi is None:
+        row_hi = L - 1
+    if (vtrace_new_logp is None) != (vtrace_old_logp is None):
+        raise ValueError("vtrace needs both new and old log-probs")
+    for name, t in (("vtrace_new_logp", vtrace_new_logp), ("vtrace_old_logp", vtrace_old_logp)):
+        if t is not None:
+            _check(t, torch.float32, name)
+            if t.shape[0] < L - 1 or t[0].numel() != N:
+                raise ValueError(f"{name}: need at least L-1={L - 1} rows of {N} lanes, got {tuple(t.shape)}")
+    if popart_mean_std is not None:
+        _check(popart_mean_std, torch.float64, "popart_mean_std")
+    adv = torch.empty_like(value) if adv is None else _check(adv, torch.float32, "adv")
+    ret = torch.empty_like(value) if ret is None else _check(ret, torch.float32, "ret")
+    if want_stats and lane_part is None:
+        lane_part = torch.empty((SRL_LANE_PART, N), dtype=torch.float64, device=value.device)
+    if lane_part is not None:
+        _check(lane_part, torch.float64, "lane_part")
+        if tuple(lane_part.shape) != (SRL_LANE_PART, N):
+            raise ValueError(f"lane_part: expected shape {(SRL_LANE_PART, N)}, got {tuple(lane_part.shape)}")
+    _lib.call("srl_gae_scan", _ptr(reward), _ptr(value), _ptr(done), _ptr(truncated), _ptr(on_reset),
+              _ptr(vtrace_new_logp), _ptr(vtrace_old_logp), _ptr(popart_mean_std), L, N, int(row_lo), int(row_hi),
+              float(gamma), float(lmbda), float(rho), float(c), _ptr(adv), _ptr(ret), _ptr(lane_part), _stream())
+    return adv, ret, lane_part
+
+
+def group_stats(lane_part: torch.Tensor, idx: Optional[torch.Tensor] = None, groups: int = 1,
+                per: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[g, k] = sum of lane_part[k, lane] over the lanes of group g (fixed summation order)."""
+    _check(lane_part, torch.float64, "lane_part")
+    N = lane_part.shape[1]
+    if per is None:
+        per = (idx.numel() if idx is not None else N) // groups
+    if idx is not None:
+        _check(idx, torch.int32, "idx")
+        if idx.numel() < groups * per:
+            raise ValueError(f"idx has {idx.numel()} entries, need groups*per = {groups * per}")
+    out = torch.empty((groups, SRL_LANE_PART), dtype=torch.float64, device=lane_part.device) if out is None else out
+    _check(out, torch.float64, "out")
+    _lib.call("srl_group_stats", _ptr(lane_part), N, _ptr(idx), int(groups), int(per), _ptr(out), _stream())
+    return out
+
+
+def popart_update(batch_stats: torch.Tensor, state: torch.Tensor, beta: float, eps: float,
+                  mean_std: torch.Tensor) -> None:
+    """RunningMeanStd.update + mean_std (utils.py:106-137) on device; state/mean_std float64 [4]."""
+    _check(batch_stats, torch.float64, "batch_stats")
+    _check(state, torch.float64, "state")
+    _check(mean_std, torch.float64, "mean_std")
+    if batch_stats.numel() < 5 or state.numel() < 4 or mean_std.numel() < 4:
+        raise ValueError("popart_update: batch_stats needs >= 5, state and mean_std >= 4 float64 entries")
+    _lib.call("srl_popart_update", _ptr(batch_stats), _ptr(state), float(beta), float(eps), _ptr(mean_std), _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# K4
+# ------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class LossHyper:
+    """The hyper-parameters of mappo.py:71-112 that enter the loss."""
+    eps_clip: float = 0.2
+    clip_value: bool = False
+    value_eps_clip: Optional[float] = None  # defaults to eps_clip (mappo.py:90)
+    dual_clip: bool = True
+    c_clip: float = 3.0
+    value_loss: str = "mse"
+    value_loss_config: Optional[dict] = None
+    value_loss_weight: float = 0.5
+    entropy_bonus_weight: float = 0.01
+    normalize_old_value: bool = False
+    adv_eps: float = 1e-5
+
+    def to_c(self) -> PpoHyper:
+        if self.value_loss not in VALUE_LOSS_CODES:
+            # same failure the reference raises at utils.py:246-249
+            raise AssertionError(f"Value loss name {self.value_loss} does not match any implemented loss functions "
+                                 f"({list(VALUE_LOSS_CODES)})")
+        cfg = dict(self.value_loss_config or {})
+        if self.value_loss == "huber":
+            prm = cfg.pop("delta", 1.0)
+        elif self.value_loss == "smoothl1":
+            prm = cfg.pop("beta", 1.0)
+        else:
+            prm = 0.0
+        cfg.pop("reduction", None)
+        if cfg:
+            raise TypeError(f"unsupported value_loss_config keys for {self.value_loss}: {sorted(cfg)}")
+        veps = self.eps_clip if self.value_eps_clip is None else self.value_eps_clip
+        return PpoHyper(float(self.eps_clip), float(veps), float(self.c_clip), float(self.value_loss_weight),
+                        float(self.entropy_bonus_weight), float(prm), float(self.adv_eps),
+                        VALUE_LOSS_CODES[self.value_loss], int(bool(self.clip_value)), int(bool(self.dual_clip)),
+                        int(bool(self.normalize_old_value)))
+
+
+_workspaces = {}
+
+
+def loss_workspace(device) -> torch.Tensor:
+    """One zero-initialised scratch buffer per (device, stream): the ticket counter must start at 0."""
+    key = (torch.device(device).index, _stream())
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = _lib.load_library().srl_ppo_loss_workspace_bytes(1, 1)
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _sample_side(old_logp, old_value, ret, adv, on_reset_next, lane_idx, T, n, clip_value):
+    """Validates the sample-side views: row stride = stride(0), unit lane stride, >= T rows."""
+    ld = None
+    for name, t, dt in (("old_logp", old_logp, torch.float32), ("old_value", old_value, torch.float32),
+                        ("ret", ret, torch.float32), ("adv", adv, torch.float32),
+                        ("on_reset_next", on_reset_next, torch.uint8)):
+        if t is None:
+            if name == "old_value" and not clip_value:
+                continue
+            raise ValueError(f"{name} is required")
+        if not t.is_cuda or t.dtype != dt:
+            raise ValueError(f"{name}: expected CUDA {dt}, got {t.dtype} on {t.device}")
+        if t.dim() != 2 or t.stride(1) != 1 or t.shape[0] < T:
+            raise ValueError(f"{name}: expected a [>=T, N] view with unit lane stride, got shape {tuple(t.shape)} "
+                             f"strides {t.stride()}")
+        this_ld = t.stride(0) if t.shape[0] > 1 else t.shape[1]
+        if ld is None:
+            ld = this_ld
+        elif this_ld != ld:
+            raise ValueError(f"{name}: row stride {this_ld} differs from the other sample leaves ({ld})")
+        if lane_idx is None and t.shape[1] != n:
+            raise ValueError(f"{name}: {t.shape[1]} lanes but the policy side has {n}")
+    if lane_idx is not None:
+        _check(lane_idx, torch.int32, "lane_idx")
+        if lane_idx.numel() != n:
+            raise ValueError(f"lane_idx has {lane_idx.numel()} entries, policy side has {n} lanes")
+    return ld
+
+
+def ppo_loss_fwd_bwd(new_logp, v_pred, entropy, old_logp, old_value, ret, adv, on_reset_next, norm_stats, hyper: LossHyper,
+                     local_stats=None, popart_mean_std=None, lane_idx=None, grads=None, out=None, out_f32=None):
+    """One launch: loss, stats and d loss / d (new_logp, v_pred, entropy).
+
+    Policy side `[T, n]` float32 contiguous; sample side `[>=T, N]` row views already offset to the
+    first loss row (`on_reset_next` offset by one more row, mappo.py:260-261); `lane_idx` int32 `[n]`
+    fuses the minibatch gather into the loads.  norm_stats: float64 `[>=3]` = (sum mask, sum adv*mask,
+    sum (adv*mask)^2), all-reduced across ranks; local_stats: this rank's (defaults to norm_stats).
+    Returns (g_logp, g_value, g_entropy, out float64[16], out_f32 float32[4]).
+    """
+    T, n = _rows_lanes(new_logp)
+    for name, t in (("new_logp", new_logp), ("v_pred", v_pred), ("entropy", entropy)):
+        _check(t, torch.float32, name)
+        if _rows_lanes(t) != (T, n):
+            raise ValueError(f"{name}: shape {tuple(t.shape)} does not match new_logp {tuple(new_logp.shape)}")
+    ld_smp = _sample_side(old_logp, old_value, ret, adv, on_reset_next, lane_idx, T, n, hyper.clip_value)
+    _check(norm_stats, torch.float64, "norm_stats")
+    local_stats = norm_stats if local_stats is None else _check(local_stats, torch.float64, "local_stats")
+    if popart_mean_std is not None:
+        _check(popart_mean_std, torch.float64, "popart_mean_std")
+    dev = new_logp.device
+    if grads is None:
+        grads = tuple(torch.empty_like(new_logp) for _ in range(3))
+    out = torch.empty(SRL_LOSS_OUT_LEN, dtype=torch.float64, device=dev) if out is None else out
+    out_f32 = torch.empty(4, dtype=torch.float32, device=dev) if out_f32 is None else out_f32
+    ws = loss_workspace(dev)
+    hc = hyper.to_c()
+    _lib.call("srl_ppo_loss_fwd_bwd", _ptr(new_logp), _ptr(v_pred), _ptr(entropy), n, _ptr(old_logp), _ptr(old_value),
+              _ptr(ret), _ptr(adv), _ptr(on_reset_next), ld_smp, _ptr(lane_idx), T, n, _ptr(norm_stats),
+              _ptr(local_stats), _ptr(popart_mean_std), ctypes.byref(hc), _ptr(grads[0]), _ptr(grads[1]),
+              _ptr(grads[2]), n, _ptr(out), _ptr(out_f32), _ptr(ws), ws.numel(), _stream())
+    return grads[0], grads[1], grads[2], out, out_f32
+
+
+def ppo_loss_from_logits(logits, action, head_sizes: Sequence[int], v_pred, old_logp, old_value, ret, adv, on_reset_next,
+                         norm_stats, hyper: LossHyper, local_stats=None, popart_mean_std=None, lane_idx=None,
+                         want_logp_entropy: bool = False):
+    """Loss starting from the actor head's logits `[T, n, sum K]` and int32 actions `[T, n, heads]`
+    (actor_critic_policy.py:303-324 fused in).  Returns (g_logits, g_value, out, out_f32, logp, entropy)."""
+    _check(logits, torch.float32, "logits")
+    _check(action, torch.int32, "action")
+    _check(v_pred, torch.float32, "v_pred")
+    heads = len(head_sizes)
+    if not 1 <= heads <= SRL_MAX_HEADS:
+        raise ValueError(f"between 1 and {SRL_MAX_HEADS} action heads are supported, got {heads}")
+    SK = int(sum(head_sizes))
+    if logits.shape[-1] != SK or action.shape[-1] != heads:
+        raise ValueError(f"logits last dim {logits.shape[-1]} / action last dim {action.shape[-1]} do not match "
+                         f"head sizes {list(head_sizes)}")
+    T = logits.shape[0]
+    n = logits[0].numel() // SK
+    if _rows_lanes(v_pred) != (T, n) or action.numel() != T * n * heads:
+        raise ValueError("logits, action and v_pred disagree on [T, n]")
+    ld_smp = _sample_side(old_logp, old_value, ret, adv, on_reset_next, lane_idx, T, n, hyper.clip_value)
+    _check(norm_stats, torch.float64, "norm_stats")
+    local_stats = norm_stats if local_stats is None else _check(local_stats, torch.float64, "local_stats")
+    dev = logits.device
+    g_logits = torch.empty_like(logits)
+    g_value = torch.empty_like(v_pred)
+    logp = torch.empty_like(v_pred) if want_logp_entropy else None
+    ent = torch.empty_like(v_pred) if want_logp_entropy else None
+    out = torch.empty(SRL_LOSS_OUT_LEN, dtype=torch.float64, device=dev)
+    out_f32 = torch.empty(4, dtype=torch.float32, device=dev)
+    ws = loss_workspace(dev)
+    hc = hyper.to_c()
+    hs = (ctypes.c_int32 * heads)(*[int(k) for k in head_sizes])
+    _lib.call("srl_ppo_loss_from_logits", _ptr(logits), _ptr(action), hs, heads, _ptr(v_pred), _ptr(old_logp),
+              _ptr(old_value), _ptr(ret), _ptr(adv), _ptr(on_reset_next), ld_smp, _ptr(lane_idx), T, n,
+              _ptr(norm_stats), _ptr(local_stats), _ptr(popart_mean_std), ctypes.byref(hc), _ptr(g_logits),
+              _ptr(g_value), _ptr(logp), _ptr(ent), _ptr(out), _ptr(out_f32), _ptr(ws), ws.numel(), _stream())
+    return g_logits, g_value, out, out_f32, logp, ent
+
+
+class PPOLossFunction(torch.autograd.Function):
+    """Autograd node at the SampleAnalyzedResult boundary (mappo.py:21-33): forward returns the scalar
+    loss (float32) and the float64 stats vector; the gradients were already produced by the same launch."""
+
+    @staticmethod
+    def forward(ctx, new_logp, v_pred, entropy, old_logp, old_value, ret, adv, on_reset_next, norm_stats, local_stats,
+                popart_mean_std, lane_idx, hyper):
+        shape = new_logp.shape
+        g_lp, g_v, g_en, out, out_f32 = ppo_loss_fwd_bwd(new_logp.detach(), v_pred.detach(), entropy.detach(), old_logp,
+                                                        old_value, ret, adv, on_reset_next, norm_stats, hyper,
+                                                        local_stats=local_stats, popart_mean_std=popart_mean_std,
+                                                        lane_idx=lane_idx)
+        ctx.save_for_backward(g_lp.view(shape), g_v.view(shape), g_en.view(shape))
+        ctx.mark_non_differentiable(out)
+        return out_f32[0], out
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_out):
+        g_lp, g_v, g_en = ctx.saved_tensors
+        return (g_lp * grad_loss, g_v * grad_loss, g_en * grad_loss) + (None,) * 10
+
+
+# ------------------------------------------------------------------------------------------------
+# K5 / K1
+# ------------------------------------------------------------------------------------------------
+def philox_perm(seed: int, epoch: int, n_env: int, group: int = 1, out: Optional[torch.Tensor] = None,
+                device="cuda") -> torch.Tensor:
+    """Lane indices of a Philox-keyed permutation of the n_env environments (int32 [n_env * group])."""
+    if out is None:
+        out = torch.empty(n_env * group, dtype=torch.int32, device=device)
+    _check(out, torch.int32, "out")
+    if out.numel() < n_env * group:
+        raise ValueError(f"out has {out.numel()} entries, need {n_env * group}")
+    _lib.call("srl_philox_perm", int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, int(n_env), int(group),
+              _ptr(out), _stream())
+    return out
+
+
+def philox4x32_10(counter: torch.Tensor, key: torch.Tensor) -> torch.Tensor:
+    """Raw Philox blocks for known-answer tests: counter int32-viewed uint32 [n, 4], key [n, 2]."""
+    _check(counter, torch.int32, "counter")
+    _check(key, torch.int32, "key")
+    n = counter.shape[0]
+    out = torch.empty_like(counter)
+    _lib.call("srl_philox4x32_10", _ptr(counter), _ptr(key), n, _ptr(out), _stream())
+    return out
+
+
+def batch_gather(pairs: List[Tuple[torch.Tensor, torch.Tensor]], idx: Optional[torch.Tensor]) -> None:
+    """For every (src `[L, slots, ...]`, dst `[L, B, ...]`) pair: dst[:, j] = src[:, idx[j]] (bit-exact).
+    One call handles up to 32 leaves per launch group; longer lists are split."""
+    if not pairs:
+        return
+    L, B = pairs[0][1].shape[0], pairs[0][1].shape[1]
+    if idx is not None:
+        _check(idx, torch.int32, "idx")
+        if idx.numel() != B:
+            raise ValueError(f"idx has {idx.numel()} entries but dst has {B} columns")
+    descs = []
+    for k, (src, dst) in enumerate(pairs):
+        for name, t in (("src", src), ("dst", dst)):
+            if not t.is_cuda or not t.is_contiguous():
+                raise ValueError(f"leaf {k} {name}: expected a contiguous CUDA tensor")
+        if src.dtype != dst.dtype or src.shape[0] != L or dst.shape[:2] != (L, B) or src.shape[2:] != dst.shape[2:]:
+            raise ValueError(f"leaf {k}: src {tuple(src.shape)}/{src.dtype} and dst {tuple(dst.shape)}/{dst.dtype} "
+                             f"are not a [L, slots, ...] -> [L, B, ...] pair")
+        row_bytes = dst[0, 0].numel() * dst.element_size() if dst.dim() > 2 else dst.element_size()
+        descs.append(LeafDesc(src.data_ptr(), dst.data_ptr(), row_bytes, src.shape[1]))
+    for i in range(0, len(descs), SRL_MAX_LEAVES):
+        chunk = descs[i:i + SRL_MAX_LEAVES]
+        arr = (LeafDesc * len(chunk))(*chunk)
+        _lib.call("srl_batch_gather", arr, len(chunk), _ptr(idx), L, B, _stream())
