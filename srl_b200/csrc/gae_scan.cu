@@ -17,6 +17,7 @@ namespace srl {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr size_t kSmemBudget = 200 * 1024;
 
 struct GaeParams {
   const float* reward;
@@ -190,14 +191,18 @@ template <int LW, bool VTRACE>
 int launch(const GaeParams& p, cudaStream_t st) {
   const size_t smem = gae_smem_bytes(p.L, LW, VTRACE);
   auto kern = gae_scan_kernel<LW, VTRACE>;
-  SRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  static bool opted_in[64] = {};  // once per device and instantiation (keeps launches capturable and cheap)
+  int dev = 0;
+  SRL_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !opted_in[dev]) {
+    SRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+    opted_in[dev] = true;
+  }
   const int grid = (p.N + LW - 1) / LW;
   kern<<<grid, kThreads, smem, st>>>(p);
   SRL_CUDA(cudaGetLastError());
   return SRL_OK;
 }
-
-constexpr size_t kSmemBudget = 200 * 1024;
 
 }  // namespace
 }  // namespace srl

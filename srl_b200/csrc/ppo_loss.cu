@@ -557,8 +557,13 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
   p.out_f32 = out_f32;
   p.ticket = reinterpret_cast<unsigned int*>(workspace);
   p.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + kPartialsOffset);
-  SRL_CUDA(cudaFuncSetAttribute(ppo_loss_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(smem)));
+  static bool opted_in[64] = {};
+  int dev = 0;
+  SRL_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !opted_in[dev]) {
+    SRL_CUDA(cudaFuncSetAttribute(ppo_loss_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    opted_in[dev] = true;
+  }
   const long long tiles = (static_cast<long long>(T) * n + 255) / 256;
   const long long cap = static_cast<long long>(sm_count()) * 8 < kMaxGrid ? static_cast<long long>(sm_count()) * 8 : kMaxGrid;
   const int grid = static_cast<int>(tiles < cap ? tiles : cap);

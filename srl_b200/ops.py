@@ -161,14 +161,19 @@ class LossHyper:
 _workspaces = {}
 
 
+def new_loss_workspace(device) -> torch.Tensor:
+    """A zero-initialised scratch buffer for the loss kernels (the ticket counter must start at 0; the kernel
+    re-zeroes it).  Launches that may overlap (different streams) must not share one."""
+    nbytes = _lib.load_library().srl_ppo_loss_workspace_bytes(1, 1)
+    return torch.zeros(nbytes, dtype=torch.uint8, device=device)
+
+
 def loss_workspace(device) -> torch.Tensor:
-    """One zero-initialised scratch buffer per (device, stream): the ticket counter must start at 0."""
+    """Default scratch: one buffer per (device, stream)."""
     key = (torch.device(device).index, _stream())
     ws = _workspaces.get(key)
     if ws is None:
-        nbytes = _lib.load_library().srl_ppo_loss_workspace_bytes(1, 1)
-        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
+        ws = _workspaces[key] = new_loss_workspace(device)
     return ws
 
 
@@ -202,7 +207,8 @@ def _sample_side(old_logp, old_value, ret, adv, on_reset_next, lane_idx, T, n, c
 
 
 def ppo_loss_fwd_bwd(new_logp, v_pred, entropy, old_logp, old_value, ret, adv, on_reset_next, norm_stats, hyper: LossHyper,
-                     local_stats=None, popart_mean_std=None, lane_idx=None, grads=None, out=None, out_f32=None):
+                     local_stats=None, popart_mean_std=None, lane_idx=None, grads=None, out=None, out_f32=None,
+                     workspace=None):
     """One launch: loss, stats and d loss / d (new_logp, v_pred, entropy).
 
     Policy side `[T, n]` float32 contiguous; sample side `[>=T, N]` row views already offset to the
@@ -226,7 +232,7 @@ def ppo_loss_fwd_bwd(new_logp, v_pred, entropy, old_logp, old_value, ret, adv, o
         grads = tuple(torch.empty_like(new_logp) for _ in range(3))
     out = torch.empty(SRL_LOSS_OUT_LEN, dtype=torch.float64, device=dev) if out is None else out
     out_f32 = torch.empty(4, dtype=torch.float32, device=dev) if out_f32 is None else out_f32
-    ws = loss_workspace(dev)
+    ws = loss_workspace(dev) if workspace is None else workspace
     hc = hyper.to_c()
     _lib.call("srl_ppo_loss_fwd_bwd", _ptr(new_logp), _ptr(v_pred), _ptr(entropy), n, _ptr(old_logp), _ptr(old_value),
               _ptr(ret), _ptr(adv), _ptr(on_reset_next), ld_smp, _ptr(lane_idx), T, n, _ptr(norm_stats),

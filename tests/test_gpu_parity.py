@@ -1,0 +1,519 @@
+"""GPU parity tests: the CUDA path (through the C-ABI in libsrl_b200.so) against
+  (a) the fixtures the unmodified reference produced (tests/golden), and
+  (b) the CPU oracle (oracle/ref_math.py) on the same seeded inputs.
+Bars (BASELINE.json north_star): gathers / permutations bit-exact; returns, advantages, losses and
+gradients within 1e-5 * max(1, |ref|) in fp32 (gradients compared on the O(1) scale g * sum(mask)).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_math as M
+from srl_b200 import synth
+from tests.util import assert_close_ref, assert_grad_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+GAE_FIXTURES = ["cfg1", "cfg1_boot50", "smac_small", "vtrace", "ragged"]
+LOSS_FIXTURES = ["atari", "smac", "football", "hns_mse", "mse_clip_dual", "smoothl1", "huber_default"]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; there is no CPU fallback to test instead")
+    from srl_b200 import ops as _ops
+    _ops._lib.load_library()  # must load the in-tree .so, loudly
+    return _ops
+
+
+def dev(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def flat2(x):
+    """[L, B, (A,) 1] numpy -> [L, N]"""
+    return np.ascontiguousarray(x.reshape(x.shape[0], -1))
+
+
+def run_gae(ops, d, row_lo=0, row_hi=None, popart_ms=None, vtrace_new=None):
+    kw = {}
+    if vtrace_new is not None:
+        kw = dict(vtrace_new_logp=dev(flat2(vtrace_new)), vtrace_old_logp=dev(flat2(d["old_logp"][:-1])))
+    if popart_ms is not None:
+        kw["popart_mean_std"] = dev(np.asarray(popart_ms, dtype=np.float64))
+    adv, ret, part = ops.gae_scan(dev(flat2(d["reward"])), dev(flat2(d["value"])), dev(flat2(d["done"])),
+                                  dev(flat2(d["truncated"])), dev(flat2(d["on_reset"])), float(d["gamma"]),
+                                  float(d["lmbda"]), row_lo=row_lo, row_hi=row_hi, **kw)
+    torch.cuda.synchronize()
+    return adv.cpu().numpy(), ret.cpu().numpy(), part.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------
+# K2
+# ---------------------------------------------------------------------------------------------------
+def test_gae_known_answer_vector(ops):
+    """legacy/tests/modules_test.py:119-138 through the CUDA kernel (one lane, L = 9)."""
+    d = dict(on_reset=np.array([0, 0, 0, 1, 0, 0, 1, 0, 0], dtype=np.uint8)[:, None],
+             reward=np.array([1, 2, 0, 1, 3, 0, 1, 2, 3], dtype=np.float32)[:, None],
+             value=np.array([2, 0, 1, 2, 2, 0, 1, 1, 1], dtype=np.float32)[:, None],
+             truncated=np.array([0, 0, 1, 0, 0, 0, 0, 0, 0], dtype=np.uint8)[:, None],
+             done=np.array([0, 0, 0, 0, 0, 1, 0, 0, 0], dtype=np.uint8)[:, None], gamma=0.1, lmbda=0.1)
+    adv, ret, _ = run_gae(ops, d)
+    keep = 1 - d["on_reset"][1:, 0].astype(np.float64)
+    expect = np.array([2.1 * 0.01 - 1, 2.1, 0, -0.8 + 0.01, 1, 0, 0.111, 1.1])
+    np.testing.assert_array_almost_equal(adv[:-1, 0] * keep, expect * keep)
+    assert adv[-1, 0] == 0 and ret[-1, 0] == 0  # padding row, mappo.py:254-256
+
+
+@pytest.mark.parametrize("name", GAE_FIXTURES)
+def test_gae_matches_reference_fixture(ops, name):
+    d = load_golden(f"gae_{name}.npz")
+    adv, ret, _ = run_gae(ops, d, popart_ms=d["popart_mean_std"] if bool(d["popart"]) else None,
+                          vtrace_new=d["vtrace_new_logp"] if bool(d["vtrace"]) else None)
+    L = d["value"].shape[0]
+    ref_adv, ref_ret = flat2(d["adv"]), flat2(d["ret"])
+    if not bool(d["vtrace"]):
+        # fp64 scan with the reference's rounding sequence: bit-identical after the fp32 cast
+        assert np.array_equal(adv[:L - 1], ref_adv), f"{name}: adv not bit-exact, max diff {np.abs(adv[:L - 1] - ref_adv).max()}"
+        assert np.array_equal(ret[:L - 1], ref_ret), f"{name}: ret not bit-exact"
+    assert_close_ref(adv[:L - 1], ref_adv, what=f"{name} adv")
+    assert_close_ref(ret[:L - 1], ref_ret, what=f"{name} ret")
+    assert not adv[L - 1].any() and not ret[L - 1].any()
+
+
+@pytest.mark.parametrize("cfg_name,B", [("cfg1_atari_cpu", None), ("cfg3_smac_27m", 24), ("cfg4_football_11v11", 40),
+                                        ("cfg5_hns_scale", 1000)])
+def test_gae_vs_oracle_config_shapes(ops, cfg_name, B):
+    """BASELINE configs (full T, reduced B so the python-loop oracle finishes in seconds)."""
+    cfg = synth.CONFIGS[cfg_name]
+    s = synth.make_sample_scalars(cfg, seed=3, B=B)
+    d = dict(s, gamma=cfg.gamma, lmbda=cfg.lmbda)
+    pa, ms = None, None
+    if cfg.popart:
+        pa = M.RunningMeanStdRef((1,), beta=0.99)
+        pa.update(torch.randn(64, 1, generator=torch.Generator().manual_seed(2)) * 2.5 + 0.7)
+        m_, s_ = pa.mean_std()
+        ms = np.array([m_.item(), s_.item()])
+    lo, hi = cfg.burn_in_steps, cfg.L - cfg.bootstrap_steps
+    adv, ret, part = run_gae(ops, d, row_lo=lo, row_hi=hi, popart_ms=ms)
+    t = {k: torch.from_numpy(flat2(v)).float() for k, v in s.items()}
+    ra, rr = M.adv_and_value_target_ref(t["reward"], t["value"], t["truncated"], t["done"], t["on_reset"], cfg.gamma,
+                                        cfg.lmbda, popart=pa)
+    assert_close_ref(adv[:-1], ra, what="adv")
+    assert_close_ref(ret[:-1], rr, what="ret")
+    assert np.array_equal(adv[:-1], ra.numpy()) and np.array_equal(ret[:-1], rr.numpy())  # bit-exact
+    # per-lane partial sums feed masked_normalization / PopArt (utils.py:54-57,113-120)
+    mask = 1 - t["on_reset"][lo + 1:hi + 1].double()
+    x = torch.from_numpy(adv[lo:hi]).double() * mask
+    y = torch.from_numpy(ret[lo:hi]).double() * mask
+    np.testing.assert_allclose(part[0], mask.sum(0).numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(part[1], x.sum(0).numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(part[2], x.square().sum(0).numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(part[3], y.sum(0).numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(part[4], y.square().sum(0).numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_array_equal(part[5], t["done"][lo:hi].double().sum(0).numpy())
+    np.testing.assert_array_equal(part[6], t["truncated"][lo:hi].double().sum(0).numpy())
+    assert not part[7].any()
+
+
+@pytest.mark.parametrize("L,N", [(2, 1), (3, 5), (9, 31), (33, 33), (130, 257), (401, 100), (1000, 64)])
+def test_gae_ragged_and_extreme_shapes(ops, L, N):
+    """Edge shapes: shortest legal scan, lane counts that are not tile multiples, long horizons."""
+    cfg = synth.PathConfig("edge", T=L - 1, B=N, p_end=0.1, gamma=0.995, lmbda=0.9)
+    s = synth.make_sample_scalars(cfg, seed=L * 1000 + N)
+    adv, ret, _ = run_gae(ops, dict(s, gamma=cfg.gamma, lmbda=cfg.lmbda))
+    t = {k: torch.from_numpy(flat2(v)).float() for k, v in s.items()}
+    ra, rr = M.adv_and_value_target_ref(t["reward"], t["value"], t["truncated"], t["done"], t["on_reset"], cfg.gamma,
+                                        cfg.lmbda)
+    assert np.array_equal(adv[:-1], ra.numpy()) and np.array_equal(ret[:-1], rr.numpy())
+
+
+def test_gae_full_size_property_linearity(ops):
+    """cfg5 full size (T=160, 65 536 lanes): GAE is linear in (reward, value) for fixed flags, so
+    scan(a*x + b*y) == a*scan(x) + b*scan(y) up to fp32 rounding -- a size-independent check."""
+    cfg = synth.CONFIGS["cfg5_hns_scale"]
+    s1 = synth.make_sample_scalars(cfg, seed=1)
+    s2 = synth.make_sample_scalars(cfg, seed=2)
+    for k in ("done", "truncated", "on_reset"):
+        s2[k] = s1[k]
+    s2["reward"][:-1] *= (1 - s1["on_reset"][1:]).astype(np.float32)
+    a, b = np.float32(0.5), np.float32(2.0)  # exact scalings in binary floating point
+    s3 = dict(s1, reward=a * s1["reward"] + b * s2["reward"], value=a * s1["value"] + b * s2["value"])
+    outs = [run_gae(ops, dict(s, gamma=cfg.gamma, lmbda=cfg.lmbda))[0] for s in (s1, s2, s3)]
+    assert_close_ref(outs[2], a * outs[0] + b * outs[1], tol=2e-5, what="linearity")
+    # and a lane-subset cross-check against the oracle at full T
+    sel = np.arange(0, cfg.N, 997)
+    t = {k: torch.from_numpy(flat2(v)[:, sel]).float() for k, v in s1.items()}
+    ra, _ = M.adv_and_value_target_ref(t["reward"], t["value"], t["truncated"], t["done"], t["on_reset"], cfg.gamma,
+                                       cfg.lmbda)
+    assert np.array_equal(outs[0][:-1][:, sel], ra.numpy())
+
+
+def test_gae_rejects_bad_arguments(ops):
+    z = torch.zeros(4, 8, device="cuda")
+    f = torch.zeros(4, 8, dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError):
+        ops.gae_scan(z.cpu(), z, f, f, f, 0.99, 0.95)  # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        ops.gae_scan(z, z, f.float(), f, f, 0.99, 0.95)  # flags must be uint8
+    from srl_b200._lib import SrlCudaError
+    with pytest.raises(SrlCudaError):
+        ops.gae_scan(z, z, f, f, f, 0.99, 0.95, row_lo=0, row_hi=4)  # loss rows must stop at L-1
+    with pytest.raises(SrlCudaError):
+        ops.gae_scan(z[:1], z[:1], f[:1], f[:1], f[:1], 0.99, 0.95)  # L < 2
+
+
+# ---------------------------------------------------------------------------------------------------
+# group stats + PopArt
+# ---------------------------------------------------------------------------------------------------
+def test_group_stats_and_popart_update(ops):
+    rng = np.random.default_rng(0)
+    N = 1000
+    part = rng.standard_normal((8, N))
+    part[7] = 0
+    dp = dev(part)
+    whole = ops.group_stats(dp, groups=1, per=N).cpu().numpy()
+    np.testing.assert_allclose(whole[0], part.sum(1), rtol=1e-12, atol=1e-12)
+    perm = rng.permutation(N).astype(np.int32)
+    got = ops.group_stats(dp, idx=dev(perm), groups=8, per=125).cpu().numpy()
+    expect = part[:, perm].reshape(8, 8, 125).sum(-1).T
+    np.testing.assert_allclose(got, expect, rtol=1e-12, atol=1e-12)
+    # determinism: same launch twice gives identical bits
+    again = ops.group_stats(dp, idx=dev(perm), groups=8, per=125).cpu().numpy()
+    assert np.array_equal(got, again)
+
+    d = load_golden("masknorm_popart.npz")
+    state = torch.zeros(4, dtype=torch.float64, device="cuda")
+    ms = torch.zeros(4, dtype=torch.float64, device="cuda")
+    for i in range(4):
+        x = d["pa_x"][i].astype(np.float64)
+        m = d["pa_mask"][i].astype(np.float64) if i % 2 else np.ones_like(x)
+        bs = np.zeros(8)
+        bs[0], bs[3], bs[4] = m.sum(), (x * m).sum(), np.square(x * m).sum()
+        ops.popart_update(dev(bs), state, float(d["pa_beta"]), 1e-5, ms)
+        np.testing.assert_allclose(state.cpu().numpy()[:3], d["pa_states"][i], rtol=1e-13)
+    assert state[3].item() == 4
+
+
+# ---------------------------------------------------------------------------------------------------
+# K4
+# ---------------------------------------------------------------------------------------------------
+def _hyper(ops, name):
+    from oracle.make_golden import LOSS_VARIANTS
+    return ops.LossHyper(**LOSS_VARIANTS[name]["kw"]), LOSS_VARIANTS[name]["popart"]
+
+
+def run_loss(ops, hp, new_logp, v_pred, entropy, old_logp, old_value, ret, adv, on_reset, lo, hi, popart_ms=None,
+             lane_idx=None, norm_stats=None, local_stats=None):
+    """on_reset/old_*/ret/adv: numpy [L, N]; policy outputs numpy [T, n]."""
+    d_rs = dev(on_reset)
+    d_olp, d_ov, d_ret, d_adv = dev(old_logp), dev(old_value), dev(ret), dev(adv)
+    if norm_stats is None:
+        mask = 1.0 - on_reset[lo + 1:hi + 1].astype(np.float64)
+        x = adv[lo:hi].astype(np.float64) * mask
+        if lane_idx is not None:
+            mask, x = mask[:, lane_idx], x[:, lane_idx]
+        norm_stats = np.array([mask.sum(), x.sum(), np.square(x).sum(), 0, 0, 0, 0, 0])
+    ns = dev(np.asarray(norm_stats, dtype=np.float64))
+    ls = None if local_stats is None else dev(np.asarray(local_stats, dtype=np.float64))
+    pm = None if popart_ms is None else dev(np.asarray(popart_ms, dtype=np.float64))
+    li = None if lane_idx is None else dev(np.asarray(lane_idx, dtype=np.int32))
+    g_lp, g_v, g_en, out, out32 = ops.ppo_loss_fwd_bwd(dev(new_logp), dev(v_pred), dev(entropy), d_olp[lo:hi], d_ov[lo:hi],
+                                                       d_ret[lo:hi], d_adv[lo:hi], d_rs[lo + 1:hi + 1], ns, hp,
+                                                       local_stats=ls, popart_mean_std=pm, lane_idx=li)
+    torch.cuda.synchronize()
+    return g_lp.cpu().numpy(), g_v.cpu().numpy(), g_en.cpu().numpy(), out.cpu().numpy(), out32.cpu().numpy()
+
+
+STAT_SLOTS = dict(advantage=4, importance_weight=5, clip_ratio=6, value_targets=7, denorm_value=8)
+
+
+@pytest.mark.parametrize("name", LOSS_FIXTURES)
+def test_loss_matches_reference_fixture(ops, name):
+    d = load_golden(f"loss_{name}.npz")
+    hp, popart = _hyper(ops, name)
+    L = d["on_reset"].shape[0]
+    lo, hi = 0, L - 1
+    g_lp, g_v, g_en, out, out32 = run_loss(ops, hp, flat2(d["new_logp"]), flat2(d["v_pred"]), flat2(d["entropy"]),
+                                           flat2(d["old_logp"]), flat2(d["value"]), flat2(d["ret"]), flat2(d["adv"]),
+                                           flat2(d["on_reset"]), lo, hi,
+                                           popart_ms=d["popart_mean_std_after"] if popart else None)
+    msum = float((1 - flat2(d["on_reset"])[lo + 1:hi + 1].astype(np.float64)).sum())
+    assert out[9] == msum
+    assert_close_ref(out[0], d["loss"], what="loss")
+    assert_close_ref(out32[0], d["loss"], what="loss f32")
+    assert_close_ref(out[1], d["stat_policy_loss"], what="policy_loss")
+    assert_close_ref(out[2], d["stat_value_loss"], what="value_loss")
+    assert_close_ref(-out[3], d["stat_entropy"], what="entropy")
+    for k, slot in STAT_SLOTS.items():
+        if f"stat_{k}" in d:
+            assert_close_ref(out[slot], d[f"stat_{k}"], what=k)
+    assert_grad_close(g_lp, flat2(d["g_logp"]), msum, what="g_logp")
+    assert_grad_close(g_v, flat2(d["g_value"]), msum, what="g_value")
+    assert_grad_close(g_en, flat2(d["g_entropy"]), msum, what="g_entropy")
+    assert np.isfinite(g_lp).all(), "dead agents (new_logp = -inf) must not produce NaN gradients (SURVEY F8)"
+
+
+@pytest.mark.parametrize("cfg_name,B", [("cfg1_atari_cpu", None), ("cfg2_atari_large", 96), ("cfg3_smac_27m", 16),
+                                        ("cfg4_football_11v11", 32), ("cfg5_hns_scale", 1024)])
+def test_loss_vs_oracle_config_shapes(ops, cfg_name, B):
+    cfg = synth.CONFIGS[cfg_name]
+    s = synth.make_sample_scalars(cfg, seed=5, B=B)
+    pol = synth.make_policy_outputs(cfg, s, seed=6, epochs=1)
+    t = {k: torch.from_numpy(flat2(v)).float() for k, v in s.items()}
+    pa, ms = None, None
+    if cfg.popart:
+        pa = M.RunningMeanStdRef((1,), beta=0.999)
+        pa.update(torch.randn(64, 1, generator=torch.Generator().manual_seed(1)) * 2 + 1)
+        m_, s_ = pa.mean_std()
+        ms = np.array([m_.item(), s_.item()])
+    adv, ret = M.adv_and_value_target_ref(t["reward"], t["value"], t["truncated"], t["done"], t["on_reset"], cfg.gamma,
+                                          cfg.lmbda, popart=pa)
+    adv, ret = M.pad_last_row(adv), M.pad_last_row(ret)
+    lo, hi = cfg.burn_in_steps, cfg.L - cfg.bootstrap_steps
+    mask = 1 - t["on_reset"][lo + 1:hi + 1]
+    hp_kw = dict(eps_clip=cfg.eps_clip, clip_value=cfg.clip_value, dual_clip=cfg.dual_clip, c_clip=cfg.c_clip,
+                 value_loss=cfg.value_loss, value_loss_weight=cfg.value_loss_weight,
+                 entropy_bonus_weight=cfg.entropy_bonus_weight,
+                 value_loss_config=({"delta": cfg.value_loss_delta} if cfg.value_loss == "huber" else None))
+    nl, vp, en = (torch.from_numpy(flat2(pol[k][0])) for k in ("new_logp", "v_pred", "entropy"))
+    ref = M.ppo_loss_ref(nl, t["old_logp"][lo:hi], vp, t["value"][lo:hi], ret[lo:hi], adv[lo:hi], en, mask,
+                         M.LossHyper(**hp_kw), popart=pa)
+    g_lp, g_v, g_en, out, _ = run_loss(ops, ops.LossHyper(**hp_kw), nl.numpy(), vp.numpy(), en.numpy(),
+                                       t["old_logp"].numpy(), t["value"].numpy(), ret.numpy(), adv.numpy(),
+                                       flat2(s["on_reset"]), lo, hi, popart_ms=ms)
+    msum = float(mask.sum())
+    assert_close_ref(out[0], ref["loss"], what="loss")
+    assert_close_ref(out[1], ref["policy_loss"], what="policy_loss")
+    assert_close_ref(out[2], ref["value_loss"], what="value_loss")
+    assert_close_ref(out[3], ref["entropy_loss"], what="entropy_loss")
+    for k, slot in STAT_SLOTS.items():
+        if k in ref["stats"]:
+            assert_close_ref(out[slot], ref["stats"][k], what=k)
+    assert_grad_close(g_lp, ref["g_logp"], msum, what="g_logp")
+    assert_grad_close(g_v, ref["g_value"], msum, what="g_value")
+    assert_grad_close(g_en, ref["g_entropy"], msum, what="g_entropy")
+
+
+def test_loss_minibatch_gather_on_load_equals_explicit_gather(ops):
+    """lane_idx fused into the loads == running on x[:, idx] (numpy fancy indexing), bit for bit."""
+    cfg = synth.PathConfig("mb", T=24, B=64, p_end=0.05, clip_value=True, value_loss="huber")
+    s = synth.make_sample_scalars(cfg, 7)
+    fl = {k: flat2(v) for k, v in s.items()}
+    rng = np.random.default_rng(3)
+    adv = rng.standard_normal(fl["value"].shape).astype(np.float32)
+    ret = rng.standard_normal(fl["value"].shape).astype(np.float32)
+    idx = M.philox_perm_ref(11, 0, 64)[:16]
+    pol = {k: rng.standard_normal((24, 16)).astype(np.float32) * 0.1 for k in ("nl", "vp", "en")}
+    pol["nl"] += fl["old_logp"][:24][:, idx]
+    hp = ops.LossHyper(clip_value=True, value_loss="huber", value_loss_config=dict(delta=10.0))
+    a = run_loss(ops, hp, pol["nl"], pol["vp"], pol["en"], fl["old_logp"], fl["value"], ret, adv, fl["on_reset"], 0, 24,
+                 lane_idx=idx)
+    take = lambda x: np.ascontiguousarray(x[:, idx])
+    b = run_loss(ops, hp, pol["nl"], pol["vp"], pol["en"], take(fl["old_logp"]), take(fl["value"]), take(ret), take(adv),
+                 take(fl["on_reset"]), 0, 24)
+    for x, y in zip(a[:3], b[:3]):
+        assert np.array_equal(x, y)
+    np.testing.assert_allclose(a[3], b[3], rtol=1e-12)
+
+
+def test_loss_two_rank_statistics(ops):
+    """normalisation uses the all-reduced sums, the masked means stay rank-local.  Emulate two ranks
+    (lane halves) on one GPU and compare each with the oracle given the summed statistics."""
+    cfg = synth.PathConfig("ddp", T=16, B=32, p_end=0.1)
+    s = synth.make_sample_scalars(cfg, 9)
+    pol = synth.make_policy_outputs(cfg, s, 10, epochs=1)
+    t = {k: torch.from_numpy(flat2(v)).float() for k, v in s.items()}
+    adv, ret = M.adv_and_value_target_ref(t["reward"], t["value"], t["truncated"], t["done"], t["on_reset"], 0.99, 0.97)
+    adv, ret = M.pad_last_row(adv), M.pad_last_row(ret)
+    mask = 1 - t["on_reset"][1:17]
+    tot = M.masked_sums_ref(adv[:16], mask)
+    hp = M.LossHyper()
+    for half in (slice(0, 16), slice(16, 32)):
+        nl, vp, en = (torch.from_numpy(flat2(pol[k][0])[:, half]) for k in ("new_logp", "v_pred", "entropy"))
+        ref = M.ppo_loss_ref(nl, t["old_logp"][:16, half], vp, t["value"][:16, half], ret[:16, half], adv[:16, half], en,
+                             mask[:, half], hp, global_sums=tot)
+        loc = M.masked_sums_ref(adv[:16, half], mask[:, half])
+        c = np.ascontiguousarray
+        g_lp, g_v, g_en, out, _ = run_loss(
+            ops, ops.LossHyper(), c(nl.numpy()), c(vp.numpy()), c(en.numpy()), c(t["old_logp"][:, half].numpy()),
+            c(t["value"][:, half].numpy()), c(ret[:, half].numpy()), c(adv[:, half].numpy()),
+            c(flat2(s["on_reset"])[:, half]), 0, 16, norm_stats=[float(x) for x in tot] + [0] * 5,
+            local_stats=[float(x) for x in loc] + [0] * 5)
+        assert_close_ref(out[0], ref["loss"], what="loss")
+        assert_grad_close(g_lp, ref["g_logp"], float(loc[0]), what="g_logp")
+
+
+def test_loss_from_logits_matches_oracle(ops):
+    for cfg_name in ("cfg1_atari_cpu", "cfg5_hns_scale"):
+        cfg = synth.CONFIGS[cfg_name]
+        T, n = 20, 37
+        small = synth.PathConfig("fl", T=T, B=n, p_end=0.05, clip_value=cfg.clip_value, dual_clip=cfg.dual_clip)
+        s = synth.make_sample_scalars(small, 13)
+        fl = {k: flat2(v) for k, v in s.items()}
+        logits, actions = synth.make_logits_actions(cfg, (T, n), seed=4)
+        rng = np.random.default_rng(8)
+        adv = rng.standard_normal(fl["value"].shape).astype(np.float32)
+        ret = rng.standard_normal(fl["value"].shape).astype(np.float32)
+        vp = (fl["value"][:T] + 0.1 * rng.standard_normal((T, n))).astype(np.float32)
+        hp_kw = dict(clip_value=cfg.clip_value, dual_clip=cfg.dual_clip, value_loss="huber",
+                     value_loss_config=dict(delta=10.0), entropy_bonus_weight=0.05)
+        # oracle: Categorical log-prob / entropy (actor_critic_policy.py:303-324) feeding the loss, autograd to logits
+        zl = torch.from_numpy(logits).requires_grad_(True)
+        lp, en = M.logp_entropy_from_logits_ref(zl, torch.from_numpy(actions).long(), cfg.num_actions)
+        # the behaviour log-prob: a perturbed copy of the current one so ratios straddle the clip range
+        old_lp = (lp.detach().numpy()[..., 0] + 0.15 * rng.standard_normal((T, n))).astype(np.float32)
+        old_full = np.concatenate([old_lp, np.zeros((1, n), np.float32)], 0)
+        tt = lambda x: torch.from_numpy(np.ascontiguousarray(x))
+        mask = 1 - tt(fl["on_reset"][1:T + 1]).float()
+        vpt = tt(vp).requires_grad_(True)
+        hp = M.LossHyper(**hp_kw)
+        ratio_in = dict(new_logp=lp[..., 0], entropy=en[..., 0])
+        # ppo_loss_ref detaches its inputs, so rebuild the graph by hand here
+        res = M.ppo_loss_ref(lp[..., 0].detach(), tt(old_lp), vpt.detach(), tt(fl["value"][:T]), tt(ret[:T]), tt(adv[:T]),
+                             en[..., 0].detach(), mask, hp)
+        (lp[..., 0] * res["g_logp"]).sum().add((en[..., 0] * res["g_entropy"]).sum()).backward()
+        li = None
+        g_logits, g_value, out, out32, logp_d, ent_d = ops.ppo_loss_from_logits(
+            dev(logits), dev(actions), cfg.num_actions, dev(vp), dev(old_full)[:T], dev(fl["value"])[:T], dev(ret)[:T],
+            dev(adv)[:T], dev(fl["on_reset"])[1:T + 1],
+            dev(np.array([float(v) for v in M.masked_sums_ref(tt(adv[:T]), mask)] + [0] * 5)), ops.LossHyper(**hp_kw),
+            want_logp_entropy=True)
+        torch.cuda.synchronize()
+        msum = float(mask.sum())
+        assert_close_ref(logp_d.cpu(), lp.detach()[..., 0], what="logp")
+        assert_close_ref(ent_d.cpu(), en.detach()[..., 0], what="entropy")
+        assert_close_ref(out.cpu()[0], res["loss"], what="loss")
+        assert_grad_close(g_value.cpu(), res["g_value"], msum, what="g_value")
+        assert_grad_close(g_logits.cpu(), zl.grad, msum, what="g_logits")
+        del ratio_in, li
+
+
+def test_loss_autograd_function(ops):
+    """PPOLossFunction plugs the fused gradients into torch autograd (what the trainer uses)."""
+    d = load_golden("loss_atari.npz")
+    hp, _ = _hyper(ops, "atari")
+    L = d["on_reset"].shape[0]
+    T = L - 1
+    rs = flat2(d["on_reset"])
+    mask = 1.0 - rs[1:L].astype(np.float64)
+    x = flat2(d["adv"])[:T].astype(np.float64) * mask
+    ns = dev(np.array([mask.sum(), x.sum(), np.square(x).sum(), 0, 0, 0, 0, 0]))
+    nl, vp, en = (dev(flat2(d[k])).requires_grad_(True) for k in ("new_logp", "v_pred", "entropy"))
+    loss, out = ops.PPOLossFunction.apply(nl * 1.0, vp * 1.0, en * 1.0, dev(flat2(d["old_logp"]))[:T],
+                                          dev(flat2(d["value"]))[:T], dev(flat2(d["ret"]))[:T], dev(flat2(d["adv"]))[:T],
+                                          dev(rs)[1:L], ns, None, None, None, hp)
+    (2.0 * loss).backward()
+    assert_close_ref(loss.item(), d["loss"], what="loss")
+    assert_grad_close(nl.grad.cpu() / 2, flat2(d["g_logp"]), mask.sum(), what="g_logp via autograd")
+    assert_grad_close(vp.grad.cpu() / 2, flat2(d["g_value"]), mask.sum(), what="g_value via autograd")
+
+
+# ---------------------------------------------------------------------------------------------------
+# K5 / K1
+# ---------------------------------------------------------------------------------------------------
+def test_philox_known_answers_on_device(ops):
+    ctr = np.array([[0, 0, 0, 0], [0xffffffff] * 4, [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344]], dtype=np.uint32)
+    key = np.array([[0, 0], [0xffffffff] * 2, [0xa4093822, 0x299f31d0]], dtype=np.uint32)
+    got = ops.philox4x32_10(dev(ctr.view(np.int32)), dev(key.view(np.int32))).cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, M.philox4x32_10(ctr, key))
+    assert [hex(v) for v in got[0]] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+
+
+@pytest.mark.parametrize("n,group", [(1, 1), (2, 1), (3, 4), (31, 1), (512, 27), (4096, 1), (5000, 3), (65536, 1)])
+def test_philox_perm_bit_exact(ops, n, group):
+    for seed, epoch in ((0, 0), (0x1234567890ABCDEF, 3)):
+        got = ops.philox_perm(seed, epoch, n, group).cpu().numpy()
+        env = M.philox_perm_ref(seed, epoch, n)
+        expect = (env[:, None].astype(np.int64) * group + np.arange(group)[None]).reshape(-1).astype(np.int32)
+        assert np.array_equal(got, expect)
+        assert np.array_equal(np.sort(got), np.arange(n * group))
+
+
+def test_batch_gather_bit_exact_stack_fixture(ops):
+    """The reference's recursive_aggregate(np.stack(axis=1)) result (tests/golden/stack.npz), reproduced by writing
+    each sample into a slab slot and gathering the slots with one call."""
+    d = load_golden("stack.npz")
+    B = 6
+    keys = [str(k) for k in d["out_keys"]]
+    slots = np.array([4, 0, 7, 2, 5, 1], dtype=np.int32)  # sample b lives in slab slot slots[b]
+    pairs, expect = [], []
+    for k in keys:
+        ref = d[f"out.{k}"]
+        slab = np.zeros((ref.shape[0], 8) + ref.shape[2:], dtype=ref.dtype)
+        for b in range(B):
+            if f"s{b}.{k}" in d:  # leaves missing in a sample stay zero (namedarray.py:588-595)
+                slab[:, slots[b]] = d[f"s{b}.{k}"]
+        pairs.append((dev(slab), torch.empty(ref.shape, dtype=torch.from_numpy(ref[:1]).dtype, device="cuda")))
+        expect.append(ref)
+    ops.batch_gather(pairs, dev(slots))
+    torch.cuda.synchronize()
+    for (_, dst), ref, k in zip(pairs, expect, keys):
+        assert np.array_equal(dst.cpu().numpy(), ref), k
+
+
+@pytest.mark.parametrize("row_shape,dtype", [((), np.uint8), ((1,), np.float32), ((3,), np.uint8), ((7,), np.float32),
+                                             ((16,), np.float32), ((4, 84, 84), np.uint8), ((33, 5), np.float16),
+                                             ((1025,), np.uint8)])
+def test_batch_gather_row_shapes(ops, row_shape, dtype):
+    rng = np.random.default_rng(1)
+    L, slots, B = 5, 19, 11
+    src = rng.integers(0, 255, size=(L, slots) + row_shape).astype(dtype)
+    idx = rng.permutation(slots)[:B].astype(np.int32)
+    dst = torch.empty((L, B) + row_shape, dtype=torch.from_numpy(src[:1]).dtype, device="cuda")
+    ops.batch_gather([(dev(src), dst)], dev(idx))
+    assert np.array_equal(dst.cpu().numpy(), M.gather_lanes_ref(src, idx))
+    # sorted slot ids == SharedMemoryDock.get (shared_memory.py:85-99)
+    ops.batch_gather([(dev(src), dst)], dev(np.sort(idx)))
+    assert np.array_equal(dst.cpu().numpy(), M.slab_get_ref({"x": src}, idx)["x"])
+    # idx = None: identity on the first B slots
+    ops.batch_gather([(dev(src), dst)], None)
+    assert np.array_equal(dst.cpu().numpy(), src[:, :B])
+
+
+def test_batch_gather_many_leaves_one_call(ops):
+    rng = np.random.default_rng(2)
+    L, slots, B = 9, 16, 16
+    idx = M.philox_perm_ref(5, 1, slots)
+    shapes = [(), (1,), (4, 84, 84), (64,), (2,), (512,), (1,), (3, 3)] * 5  # 40 leaves -> two launch groups
+    srcs = [rng.integers(0, 255, size=(L, slots) + s).astype(np.uint8 if i % 2 else np.float32)
+            for i, s in enumerate(shapes)]
+    pairs = [(dev(s), torch.empty((L, B) + s.shape[2:], dtype=torch.from_numpy(s[:1]).dtype, device="cuda")) for s in srcs]
+    ops.batch_gather(pairs, dev(idx))
+    for s, (_, dst) in zip(srcs, pairs):
+        assert np.array_equal(dst.cpu().numpy(), s[:, idx])
+
+
+def test_full_size_cfg2_roundtrip_properties(ops):
+    """cfg2 full size (T=128, 4096 lanes), size-independent checks: (1) gather with a permutation followed by
+    gather with its inverse is the identity; (2) per-minibatch mask counts add up to the batch count;
+    (3) loss gradients of masked rows are exactly zero and sum(g_entropy) == -w_e."""
+    cfg = synth.CONFIGS["cfg2_atari_large"]
+    s = synth.make_sample_scalars(cfg, 0)
+    pol = synth.make_policy_outputs(cfg, s, 1, epochs=1)
+    fl = {k: dev(flat2(v)) for k, v in s.items()}
+    perm = ops.philox_perm(99, 0, cfg.N)
+    inv = torch.empty_like(perm)
+    inv[perm.long()] = torch.arange(cfg.N, dtype=torch.int32, device="cuda")
+    tmp, back = torch.empty_like(fl["value"]), torch.empty_like(fl["value"])
+    ops.batch_gather([(fl["value"].unsqueeze(-1), tmp.unsqueeze(-1))], perm)
+    ops.batch_gather([(tmp.unsqueeze(-1), back.unsqueeze(-1))], inv)
+    assert torch.equal(back, fl["value"])
+    adv, ret, part = ops.gae_scan(fl["reward"], fl["value"], fl["done"], fl["truncated"], fl["on_reset"], cfg.gamma,
+                                  cfg.lmbda, row_lo=0, row_hi=cfg.T)
+    whole = ops.group_stats(part, groups=1, per=cfg.N)
+    mb = ops.group_stats(part, idx=perm, groups=8, per=512)
+    assert mb[:, 0].sum().item() == whole[0, 0].item()
+    hp = ops.LossHyper(clip_value=True, dual_clip=False, value_loss="huber", value_loss_config=dict(delta=10.0),
+                       value_loss_weight=1.0)
+    nl, vp, en = (dev(flat2(pol[k][0])) for k in ("new_logp", "v_pred", "entropy"))
+    g_lp, g_v, g_en, out, _ = ops.ppo_loss_fwd_bwd(nl, vp, en, fl["old_logp"][:cfg.T], fl["value"][:cfg.T], ret[:cfg.T],
+                                                   adv[:cfg.T], fl["on_reset"][1:cfg.T + 1], whole[0], hp)
+    masked = fl["on_reset"][1:cfg.T + 1] != 0
+    assert not g_lp[masked].any() and not g_v[masked].any() and not g_en[masked].any()
+    assert abs(g_en.double().sum().item() + hp.entropy_bonus_weight) < 1e-6
+    assert out[9].item() == whole[0, 0].item()
