@@ -84,10 +84,12 @@ int srl_gae_scan(const float* reward,          /* [L, N]; row L-1 is ignored    
  * minibatch; with G == 1 and per == N this is the whole-batch reduction of utils.py:54-57 /
  * utils.py:113-120.  The [G, SRL_LANE_PART] float64 table is what gets all-reduced (SUM) across
  * ranks in place of the 3 + 3 one-element all-reduces of utils.py:58-61,121-124.
+ * whole_first != 0: out has G + 1 rows and row 0 is the sum over ALL N lanes (the batch statistics PopArt
+ * needs), rows 1..G are the groups -- one launch for the whole table.
  * Summation order is fixed (deterministic for a given G, per).
  * ------------------------------------------------------------------------------------------ */
-int srl_group_stats(const double* lane_part, int N, const int32_t* idx, int G, int per, double* out,
-                    srl_stream_t stream);
+int srl_group_stats(const double* lane_part, int N, const int32_t* idx, int G, int per, int whole_first,
+                    double* out, srl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3  PopArt / RunningMeanStd update for a scalar critic (critic_dim == 1).
@@ -95,7 +97,9 @@ int srl_group_stats(const double* lane_part, int N, const int32_t* idx, int G, i
  * PopArtValueHead.update (legacy/algorithm/modules/popart.py:42-47).
  *   state = {mean, mean_sq, debias, update_count} (float64, device, updated in place)
  *   batch_stats: one row of the group-stats table; uses [0] = sum mask, [3] = sum x, [4] = sum x^2.
- *   mean_std_out = {mu, sigma}: mu = mean/max(debias,eps), sigma = sqrt(max(mean_sq/max(debias,eps) - mu^2, 1e-2)).
+ *   mean_std_out = {mu, sigma, mu_before, sigma_before} (float64[4]): mu = mean/max(debias,eps),
+ *   sigma = sqrt(max(mean_sq/max(debias,eps) - mu^2, 1e-2)); the "before" pair is what PopArtValueHead.update
+ *   needs to rescale the head (popart.py:43,49-51).
  * ------------------------------------------------------------------------------------------ */
 int srl_popart_update(const double* batch_stats, double* state, double beta, double eps, double* mean_std_out,
                       srl_stream_t stream);
@@ -137,9 +141,16 @@ enum srl_loss_out {
   SRL_LOSS_OUT_LEN = 16
 };
 
-/* Bytes of device scratch srl_ppo_loss_fwd_bwd needs for a [T, n] problem.  The first 8 bytes are
- * a ticket counter and must be zero before the FIRST launch (the kernel re-zeroes it itself). */
+/* Bytes of one device scratch "slot" for a [T, n] problem: a 64-byte header + one float64[8] partial row per
+ * CTA.  A slot must be zero before its FIRST use (the ticket counter lives in the header and the kernel
+ * re-zeroes it); launches that may overlap in time need distinct slots. */
 size_t srl_ppo_loss_workspace_bytes(int T, int n);
+
+/* Deferred finalisation: when srl_ppo_loss_fwd_bwd / srl_ppo_loss_from_logits are called with out == NULL they
+ * stop after writing gradients and partial rows.  This folds n_slots consecutive slots (slot k at
+ * workspace + k * slot_bytes) into out[k][SRL_LOSS_OUT_LEN] (and out_f32[k][4] if not NULL) in one launch. */
+int srl_ppo_loss_finalize(const void* workspace, size_t slot_bytes, int n_slots, double* out, float* out_f32,
+                          srl_stream_t stream);
 
 int srl_ppo_loss_fwd_bwd(
     /* policy side: dense [T, n], row stride ld_pol elements (analyze() output, mappo.py:244-246) */
@@ -154,7 +165,7 @@ int srl_ppo_loss_fwd_bwd(
     const double* popart_mean_std, /* device {mu, sigma} or NULL                                  */
     const srl_ppo_hyper* hyper,    /* HOST pointer, copied by value into the launch              */
     float* g_logp, float* g_value, float* g_entropy, int64_t ld_grad, /* [T, n] out */
-    double* out,      /* device [SRL_LOSS_OUT_LEN] out */
+    double* out,      /* device [SRL_LOSS_OUT_LEN] out, or NULL = deferred (srl_ppo_loss_finalize) */
     float* out_f32,   /* device [4] out: loss, policy_loss, value_loss, entropy_loss, or NULL */
     void* workspace, size_t workspace_bytes, srl_stream_t stream);
 
@@ -181,11 +192,13 @@ int srl_ppo_loss_from_logits(
 /* ------------------------------------------------------------------------------------------
  * K5a  Philox-keyed permutation of the environment axis (NEW capability: the reference has no
  * minibatching; nearest relative SimpleReplayBuffer.get, base/buffer.py:262-277).
- * out[e*group + a] = perm[e] * group + a for e in [0, n_env), a in [0, group): an 8-round Feistel
+ * out is [n_epochs][n_env * group]; row r holds epoch (epoch + r):
+ * out[r][e*group + a] = perm_r[e] * group + a for e in [0, n_env), a in [0, group): an 8-round Feistel
  * bijection on ceil(log2 n_env) bits, round keys from Philox4x32-10(key = seed, counter =
  * (block, epoch, 'SRLP', 0)), cycle-walked into [0, n_env).  Spec: oracle/ref_math.py:philox_perm_ref.
  * ------------------------------------------------------------------------------------------ */
-int srl_philox_perm(uint64_t seed, uint32_t epoch, int n_env, int group, int32_t* out, srl_stream_t stream);
+int srl_philox_perm(uint64_t seed, uint32_t epoch, int n_epochs, int n_env, int group, int32_t* out,
+                    srl_stream_t stream);
 /* Raw Philox4x32-10 blocks (for known-answer tests): out[i] = philox(counter[i], key[i]). */
 int srl_philox4x32_10(const uint32_t* counter, const uint32_t* key, int n_blocks, uint32_t* out,
                       srl_stream_t stream);

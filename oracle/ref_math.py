@@ -431,7 +431,7 @@ def gather_lanes_ref(x, idx):
 
 def hot_path_ref(batch: dict, hp: LossHyper, gamma: float, lmbda: float, epochs: int, minibatches: int,
                  seed: int = 0, popart: Optional[RunningMeanStdRef] = None, bootstrap_steps: int = 1,
-                 burn_in_steps: int = 0, want_grads: bool = True):
+                 burn_in_steps: int = 0, want_grads: bool = True, lanes_per_env: int = 1):
     """GAE once (mappo.py:252-257) then epochs x minibatches of loss + backward
     (mappo.py:259-274) on lane subsets chosen by ``philox_perm_ref``.
 
@@ -445,11 +445,16 @@ def hot_path_ref(batch: dict, hp: LossHyper, gamma: float, lmbda: float, epochs:
     lo, hi = burn_in_steps, L - bootstrap_steps
     mask = 1 - batch["on_reset"][lo + 1:hi + 1]  # mappo.py:260-261
     N = mask.shape[1]
+    A = lanes_per_env  # whole environments are shuffled; an env's agents stay together
     results = []
     for e in range(epochs):
         if popart is not None:
             popart.update(ret[lo:hi], mask=mask)  # mappo.py:263-264
-        perm = philox_perm_ref(seed, e, N) if minibatches > 1 else np.arange(N)
+        if minibatches > 1:
+            env = philox_perm_ref(seed, e, N // A).astype(np.int64)
+            perm = (env[:, None] * A + np.arange(A)[None, :]).reshape(-1)
+        else:
+            perm = np.arange(N)
         per = N // minibatches
         for j in range(minibatches):
             idx = torch.from_numpy(perm[j * per:(j + 1) * per].astype(np.int64))

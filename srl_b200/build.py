@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libsrl_b200.so")
-SOURCES = ["api.cu", "gae_scan.cu", "ppo_loss.cu", "stats.cu", "perm.cu", "gather.cu"]
+SOURCES = ["api.cu", "gae_scan.cu", "gae_scan_tma.cu", "ppo_loss.cu", "stats.cu", "perm.cu", "gather.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",  # B200 only; no PTX for other archs, no fallback

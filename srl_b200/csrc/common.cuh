@@ -35,48 +35,18 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 // ---- device helpers ------------------------------------------------------------------------
 #ifdef __CUDACC__
 
-// Streaming (read-once) loads: bypass L1 allocation, keep the read-only path.
-__device__ __forceinline__ float ldg_stream(const float* p) {
-  float v;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ float4 ldg_stream(const float4* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-}
-__device__ __forceinline__ uint32_t ldg_stream(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ uint8_t ldg_stream(const uint8_t* p) {
-  uint32_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
-  return static_cast<uint8_t>(v);
-}
-__device__ __forceinline__ int4 ldg_stream(const int4* p) {
-  int4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p));
-  return v;
-}
-// Streaming stores: results are consumed by a later kernel, not by this SM.
-__device__ __forceinline__ void stg_stream(float* p, float v) {
-  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v));
-}
-__device__ __forceinline__ void stg_stream(float4* p, float4 v) {
-  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
-               "f"(v.w));
-}
-__device__ __forceinline__ void stg_stream(int4* p, int4 v) {
-  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
-               "r"(v.w));
-}
+// Streaming (read-once / write-once) accesses: evict-first cache hints through the compiler intrinsics.
+// (Not `asm volatile`: volatile asm pins the loads in program order, which serialises one DRAM round trip
+// per loop iteration -- measured in profiles/r1_notes.md.  The intrinsics stay schedulable, so independent
+// loads are hoisted and overlap.)
+__device__ __forceinline__ float ldg_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ uint32_t ldg_stream(const uint32_t* p) { return __ldcs(p); }
+__device__ __forceinline__ uint8_t ldg_stream(const uint8_t* p) { return __ldcs(p); }
+__device__ __forceinline__ int4 ldg_stream(const int4* p) { return __ldcs(p); }
+__device__ __forceinline__ void stg_stream(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void stg_stream(float4* p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ void stg_stream(int4* p, int4 v) { __stcs(p, v); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

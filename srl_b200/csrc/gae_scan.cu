@@ -2,16 +2,19 @@
 // reference lines it replaces: mappo.py:118-144,254-256; gae.py:8-97; utils.py:54-57,113-120).
 //
 // Design (one CTA = a tile of LW adjacent lanes x all L rows, staged in shared memory):
-//   phase A1  all 256 threads: coalesced row-segment loads of value/done/truncated/on_reset,
-//             v' = (popart-denormalised) value * (1 - done)  -> smem (fp32) + flag byte
-//   phase A2  all threads: delta_t (fp64, explicit mul/add roundings, no FMA contraction -- the
-//             reference evaluates each torch op separately) and the carry factor m_t -> smem
+//   phase A1  all 256 threads: every global load of the tile (coalesced row segments, 4 rows in flight
+//             per thread); v' = (popart-denormalised) value * (1 - done) -> smem (fp32) + flag byte
+//   phase A2  all threads, shared memory only: delta_t (fp64, explicit mul/add roundings, no FMA
+//             contraction -- the reference evaluates each torch op separately) and the carry factor m_t
 //   phase B   one warp: the only truly sequential part, A_t = delta_t + m_t * A_{t+1} in fp64 out of
 //             shared memory (loads do not depend on the chain, so they pipeline)
 //   phase C   all threads: ret = adv + v', coalesced stores of adv/ret (padding row zeroed) and the
 //             per-lane float64 partial sums that masked_normalization / PopArt need
 // Every global byte is read once and written once: 11 B in + 8 B out per scanned row-lane.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "gae_common.cuh"
 
 namespace srl {
 namespace {
@@ -19,40 +22,27 @@ namespace {
 constexpr int kThreads = 256;
 constexpr size_t kSmemBudget = 200 * 1024;
 
-struct GaeParams {
-  const float* reward;
-  const float* value;
-  const uint8_t* done;
-  const uint8_t* truncated;
-  const uint8_t* on_reset;
-  const float* vt_new_logp;
-  const float* vt_old_logp;
-  const double* popart;  // {mean, std} or null
-  float* adv;
-  float* ret;
-  double* lane_part;
-  int L, N, row_lo, row_hi;
-  double gamma, gamma_lmbda, rho, c;
-};
-
 __host__ __device__ constexpr size_t gae_smem_bytes(int L, int LW, bool vtrace) {
-  // delta (f64) [+ m (f64)] + v' (f32) + flags (u8) + kill (u8), each [L][LW]
+  // (delta, m) (2 x f64, interleaved) + adv (f32) + v' (f32) + flags (u8), each [L][LW]
   // (the per-lane reduction scratch [kThreads/LW][7][LW] f64 = 14 KB aliases the same bytes)
-  const size_t tile = static_cast<size_t>(L) * LW * (8 + (vtrace ? 8 : 0) + 4 + 1 + 1);
+  (void)vtrace;
+  const size_t tile = static_cast<size_t>(L) * LW * (16 + 4 + 4 + 1);
   const size_t scratch = static_cast<size_t>(kThreads) * 7 * 8;
   return tile > scratch ? tile : scratch;
 }
 
+constexpr int kUnroll = 4;  // rows per thread whose global loads are issued back to back
+
 template <int LW, bool VTRACE>
-__global__ void __launch_bounds__(kThreads) gae_scan_kernel(const GaeParams p) {
+__global__ void __launch_bounds__(kThreads, 4) gae_scan_kernel(const GaeParams p) {
   constexpr int RPP = kThreads / LW;  // rows handled per pass of the CTA
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int L = p.L, N = p.N;
-  double* sd = reinterpret_cast<double*>(smem_raw);                 // [L][LW] delta, later adv(f32) in place
-  double* sm = sd + static_cast<size_t>(L) * LW;                    // [L][LW] m (VTRACE only)
-  float* sv = reinterpret_cast<float*>(VTRACE ? sm + static_cast<size_t>(L) * LW : sm);  // [L][LW] v'
-  uint8_t* sf = reinterpret_cast<uint8_t*>(sv + static_cast<size_t>(L) * LW);            // [L][LW] flags
-  uint8_t* sk = sf + static_cast<size_t>(L) * LW;                                        // [L][LW] kill
+  const size_t cells = static_cast<size_t>(L) * LW;
+  double2* __restrict__ sdm = reinterpret_cast<double2*>(smem_raw);   // [L][LW] .x = reward -> delta -> A_t, .y = m
+  float* __restrict__ sa = reinterpret_cast<float*>(sdm + cells);      // [L][LW] vtrace importance ratio
+  float* __restrict__ sv = sa + cells;                                 // [L][LW] v'
+  uint8_t* __restrict__ sf = reinterpret_cast<uint8_t*>(sv + cells);   // [L][LW] done|trunc|reset bits
 
   const int tid = threadIdx.x;
   const int lane = tid % LW;
@@ -60,87 +50,132 @@ __global__ void __launch_bounds__(kThreads) gae_scan_kernel(const GaeParams p) {
   const int col = blockIdx.x * LW + lane;
   const bool live = col < N;
 
-  double pa_mean = 0.0, pa_std = 1.0;
   const bool popart = p.popart != nullptr;
+  double pa_mean = 0.0, pa_std = 1.0;
   if (popart) {
     pa_mean = p.popart[0];
     pa_std = p.popart[1];
   }
 
-  // ---- A1: v'[t] and flag byte for every row --------------------------------------------------
-  for (int t = trow; t < L; t += RPP) {
-    float v = 0.f;
-    uint32_t f = 0;
-    if (live) {
-      const size_t g = static_cast<size_t>(t) * N + col;
-      v = ldg_stream(p.value + g);
-      const uint32_t dn = ldg_stream(p.done + g), tr = ldg_stream(p.truncated + g), rs = ldg_stream(p.on_reset + g);
-      if (popart)  // RunningMeanStd.denormalize: (x.double() * std + mean).float()   utils.py:146-151
-        v = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(v), pa_std), pa_mean));
-      v = __fmul_rn(v, 1.f - static_cast<float>(dn != 0));  // value * (1 - done), fp32   mappo.py:120-124
-      f = (dn != 0 ? 1u : 0u) | (tr != 0 ? 2u : 0u) | (rs != 0 ? 4u : 0u);
+#ifdef SRL_DEBUG_PHASES
+  long long ck[6];
+  ck[0] = clock64();
+#define SRL_STAMP(i) ck[i] = clock64()
+#else
+#define SRL_STAMP(i)
+#endif
+  // ---- A1: every global load of the tile, kUnroll rows in flight per thread -------------------------
+  for (int t0 = trow; t0 < L; t0 += kUnroll * RPP) {
+    float v[kUnroll], rw[kUnroll], nl[kUnroll], ol[kUnroll];
+    uint32_t dn[kUnroll], tr[kUnroll], rs[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int t = t0 + u * RPP;
+      v[u] = rw[u] = nl[u] = ol[u] = 0.f;
+      dn[u] = tr[u] = rs[u] = 0u;
+      if (live && t < L) {
+        const size_t g = static_cast<size_t>(t) * N + col;
+        v[u] = ldg_stream(p.value + g);
+        dn[u] = ldg_stream(p.done + g);
+        tr[u] = ldg_stream(p.truncated + g);
+        rs[u] = ldg_stream(p.on_reset + g);
+        if (t < L - 1) {
+          rw[u] = ldg_stream(p.reward + g);
+          if (VTRACE) {
+            nl[u] = ldg_stream(p.vt_new_logp + g);
+            ol[u] = ldg_stream(p.vt_old_logp + g);
+          }
+        }
+      }
     }
-    sv[t * LW + lane] = v;
-    sf[t * LW + lane] = static_cast<uint8_t>(f);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int t = t0 + u * RPP;
+      if (t < L) {
+        float vv = v[u];
+        if (popart)  // RunningMeanStd.denormalize: (x.double() * std + mean).float()   utils.py:146-151
+          vv = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(vv), pa_std), pa_mean));
+        vv = __fmul_rn(vv, 1.f - static_cast<float>(dn[u] != 0));  // value * (1 - done), fp32   mappo.py:120-124
+        sv[t * LW + lane] = vv;
+        sf[t * LW + lane] = static_cast<uint8_t>((dn[u] != 0 ? 1u : 0u) | (tr[u] != 0 ? 2u : 0u) | (rs[u] != 0 ? 4u : 0u));
+        sdm[t * LW + lane].x = static_cast<double>(rw[u]);
+        if (VTRACE) sa[t * LW + lane] = expf(nl[u] - ol[u]);  // importance ratio, fp32   mappo.py:129-132
+      }
+    }
   }
   __syncthreads();
+  SRL_STAMP(1);
 
-  // ---- A2: delta_t and m_t for t in [0, L-1) --------------------------------------------------
+  // ---- A2: delta_t and m_t for t in [0, L-1), shared memory only -----------------------------------
   for (int t = trow; t < L - 1; t += RPP) {
     const uint32_t f1 = sf[(t + 1) * LW + lane];
-    const double alive = (f1 & 4u) ? 0.0 : 1.0;     // 1 - on_reset[t+1]
-    const double not_tr = (f1 & 2u) ? 0.0 : 1.0;    // 1 - truncated[t+1]
-    float r = 0.f;
-    if (live) r = ldg_stream(p.reward + static_cast<size_t>(t) * N + col);
+    const double alive = (f1 & 4u) ? 0.0 : 1.0;   // 1 - on_reset[t+1]
+    const double not_tr = (f1 & 2u) ? 0.0 : 1.0;  // 1 - truncated[t+1]
     const double v1 = static_cast<double>(sv[(t + 1) * LW + lane]);
     const double v0 = static_cast<double>(sv[t * LW + lane]);
     // gae.py:63  reward + gamma * value[1:] * (1 - on_reset[1:]) - value[:-1]
     double d = __dmul_rn(__dmul_rn(p.gamma, v1), alive);
-    d = __dadd_rn(static_cast<double>(r), d);
+    d = __dadd_rn(sdm[t * LW + lane].x, d);
     d = __dsub_rn(d, v0);
+    // gae.py:87  gamma * lmbda * (1 - on_reset[1:]) * (1 - truncated[1:])
+    double m = __dmul_rn(__dmul_rn(p.gamma_lmbda, alive), not_tr);
     if (VTRACE) {
-      // gae.py:87  gamma * lmbda * (1 - on_reset[1:]) * (1 - truncated[1:])
-      double m = __dmul_rn(__dmul_rn(p.gamma_lmbda, alive), not_tr);
-      float ratio = 1.f;
-      if (live) {
-        const size_t g = static_cast<size_t>(t) * N + col;
-        ratio = expf(ldg_stream(p.vt_new_logp + g) - ldg_stream(p.vt_old_logp + g));  // mappo.py:129-132
-      }
-      const double rd = static_cast<double>(ratio);
+      const double rd = static_cast<double>(sa[t * LW + lane]);
       d = __dmul_rn(d, fmin(rd, p.rho));  // gae.py:64-65
       m = __dmul_rn(m, fmin(rd, p.c));    // gae.py:88-89
-      sm[t * LW + lane] = m;
-    } else {
-      sk[t * LW + lane] = (f1 & 6u) ? 1 : 0;  // m is exactly 0 or gamma*lmbda
     }
-    sd[t * LW + lane] = d;
+    sdm[t * LW + lane] = make_double2(d, m);
   }
   __syncthreads();
+  SRL_STAMP(2);
 
-  // ---- B: the sequential scan, one warp -------------------------------------------------------
+  // ---- B: the sequential scan, one (partial) warp -----------------------------------------------------
+  // A_t = delta_t + m_t * A_{t+1}: separate fp64 multiply and add, as the reference's two torch ops
+  // (gae.py:92).  Software-pipelined: the (delta, m) pairs of the next 4 steps are already in registers
+  // while the dependent DMUL/DADD chain of the current 4 runs, so shared-memory latency is off the chain.
   if (tid < LW) {
+    constexpr int CH = 4;
     double g = 0.0;
-    const double gl = p.gamma_lmbda;
-#pragma unroll 8
-    for (int t = L - 2; t >= 0; --t) {
-      const double d = sd[t * LW + lane];
-      double m;
-      if (VTRACE)
-        m = sm[t * LW + lane];
-      else
-        m = sk[t * LW + lane] ? 0.0 : gl;
-      g = __dadd_rn(d, __dmul_rn(m, g));  // gae.py:92  (separate mul and add, as two torch ops)
-      reinterpret_cast<float*>(sd + t * LW + lane)[0] = static_cast<float>(g);  // adv.float(), gae.py:97
+    int t = L - 2;
+    double2 q[CH];
+    if (t >= CH - 1) {
+#pragma unroll
+      for (int u = 0; u < CH; ++u) q[u] = sdm[(t - u) * LW + lane];
+    }
+    for (; t >= CH - 1; t -= CH) {
+      double2 nq[CH];
+      const bool more = (t - CH) >= CH - 1;
+      if (more) {
+#pragma unroll
+        for (int u = 0; u < CH; ++u) nq[u] = sdm[(t - CH - u) * LW + lane];
+      }
+      // the float64 results go back to shared memory as they are: converting here would put a 17-cycle F2F
+      // (profiles/microbench/f2f.cu) behind every 16-cycle DMUL+DADD link; phase C converts in parallel instead
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        g = __dadd_rn(q[u].x, __dmul_rn(q[u].y, g));
+        sdm[(t - u) * LW + lane].x = g;
+      }
+      if (more) {
+#pragma unroll
+        for (int u = 0; u < CH; ++u) q[u] = nq[u];
+      }
+    }
+    for (; t >= 0; --t) {
+      const double2 dm = sdm[t * LW + lane];
+      g = __dadd_rn(dm.x, __dmul_rn(dm.y, g));
+      sdm[t * LW + lane].x = g;
     }
   }
   __syncthreads();
+  SRL_STAMP(3);
 
-  // ---- C: ret, stores, per-lane partial sums --------------------------------------------------
+  // ---- C: ret, stores, per-lane partial sums ------------------------------------------------------------
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0;
   for (int t = trow; t < L; t += RPP) {
     float a = 0.f, r = 0.f;
     if (t < L - 1) {
-      a = reinterpret_cast<const float*>(sd + t * LW + lane)[0];
+      a = static_cast<float>(sdm[t * LW + lane].x);  // adv.float(), gae.py:97
       r = __fadd_rn(a, sv[t * LW + lane]);  // value_target = adv + v'[:-1], fp32   mappo.py:143
       if (t >= p.row_lo && t < p.row_hi) {
         const uint32_t f0 = sf[t * LW + lane], f1 = sf[(t + 1) * LW + lane];
@@ -162,9 +197,10 @@ __global__ void __launch_bounds__(kThreads) gae_scan_kernel(const GaeParams p) {
       stg_stream(p.ret + g, r);
     }
   }
+  SRL_STAMP(4);
   if (p.lane_part != nullptr) {
     __syncthreads();  // the tile is dead; reuse its bytes as [RPP][7][LW] f64
-    double* red = sd;
+    double* red = reinterpret_cast<double*>(smem_raw);
     red[(trow * 7 + 0) * LW + lane] = s0;
     red[(trow * 7 + 1) * LW + lane] = s1;
     red[(trow * 7 + 2) * LW + lane] = s2;
@@ -185,6 +221,12 @@ __global__ void __launch_bounds__(kThreads) gae_scan_kernel(const GaeParams p) {
       }
     }
   }
+#ifdef SRL_DEBUG_PHASES
+  SRL_STAMP(5);
+  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1))
+    printf("gae block %d: A1 %lld  A2 %lld  B %lld  C %lld  red %lld  total %lld cycles\n", blockIdx.x, ck[1] - ck[0],
+           ck[2] - ck[1], ck[3] - ck[2], ck[4] - ck[3], ck[5] - ck[4], ck[5] - ck[0]);
+#endif
 }
 
 template <int LW, bool VTRACE>
@@ -243,13 +285,26 @@ extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8
   p.c = c;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
+  // Throughput path: TMA-pipelined warp-per-32-lanes scan (gae_scan_tma.cu); needs 16-byte aligned rows and
+  // enough lane groups to give every SM several warps (it is issue-bound per warp, so few warps = long tail).
+  // Latency path (few lanes) and ragged shapes: the shared-memory tile kernel below.
+  bool use_tma = gae_tma_eligible(p) && (N + 31) / 32 >= 2 * sm_count();
+#ifdef SRL_DEBUG_PHASES
+  if (const char* e = getenv("SRL_GAE_PATH")) use_tma = gae_tma_eligible(p) && e[1] == 'm';  // "tma" / "tile"
+#endif
+  if (use_tma) return launch_gae_tma(p, st);
+
+  // General path (any N, any alignment): shared-memory tile kernel below.
   // Lane-tile width: the widest tile that (a) fits shared memory and (b) still gives every SM work.
   const int sms = sm_count();
   int lw = 32;
   while (lw > 8 && (gae_smem_bytes(L, lw, vtrace) > kSmemBudget || (N + lw - 1) / lw < 2 * sms)) lw >>= 1;
+#ifdef SRL_DEBUG_PHASES
+  if (const char* e = getenv("SRL_GAE_LW")) lw = atoi(e);  // tuning knob of the instrumented build only
+#endif
   SRL_REQUIRE(gae_smem_bytes(L, lw, vtrace) <= kSmemBudget, SRL_ERR_UNSUPPORTED,
               "srl_gae_scan: L=%d does not fit the shared-memory tile (max L ~ %d)", L,
-              static_cast<int>(kSmemBudget / (8 * (vtrace ? 22 : 14))));
+              static_cast<int>(kSmemBudget / (8 * 25)));
   if (vtrace) {
     if (lw == 32) return launch<32, true>(p, st);
     if (lw == 16) return launch<16, true>(p, st);

@@ -51,9 +51,11 @@ __host__ __device__ __forceinline__ uint32_t feistel8(uint32_t x, const PermKeys
 
 namespace {
 
-__global__ void __launch_bounds__(256) philox_perm_kernel(uint32_t seed_lo, uint32_t seed_hi, uint32_t epoch, int n_env,
+__global__ void __launch_bounds__(256) philox_perm_kernel(uint32_t seed_lo, uint32_t seed_hi, uint32_t epoch0, int n_env,
                                                          int group, int bits, int32_t* __restrict__ out) {
   __shared__ PermKeys keys;
+  const uint32_t epoch = epoch0 + blockIdx.y;  // one grid row per epoch
+  out += static_cast<size_t>(blockIdx.y) * n_env * group;
   if (threadIdx.x < 2) {  // two Philox blocks -> eight round keys
     Philox4 ctr;
     ctr.c[0] = threadIdx.x;
@@ -91,10 +93,12 @@ __global__ void philox_blocks_kernel(const uint32_t* __restrict__ counter, const
 }  // namespace
 }  // namespace srl
 
-extern "C" int srl_philox_perm(uint64_t seed, uint32_t epoch, int n_env, int group, int32_t* out, srl_stream_t stream) {
+extern "C" int srl_philox_perm(uint64_t seed, uint32_t epoch, int n_epochs, int n_env, int group, int32_t* out,
+                               srl_stream_t stream) {
   using namespace srl;
-  SRL_REQUIRE(n_env >= 0 && group >= 1, SRL_ERR_INVALID_ARG, "srl_philox_perm: need n_env >= 0 and group >= 1");
-  if (n_env == 0) return SRL_OK;
+  SRL_REQUIRE(n_env >= 0 && group >= 1 && n_epochs >= 0 && n_epochs <= 65535, SRL_ERR_INVALID_ARG,
+              "srl_philox_perm: need n_env >= 0, group >= 1 and 0 <= n_epochs <= 65535");
+  if (n_env == 0 || n_epochs == 0) return SRL_OK;
   SRL_REQUIRE(out != nullptr, SRL_ERR_INVALID_ARG, "srl_philox_perm: null output");
   SRL_REQUIRE(static_cast<long long>(n_env) * group < (1ll << 31), SRL_ERR_UNSUPPORTED,
               "srl_philox_perm: n_env * group must fit int32");
@@ -105,7 +109,7 @@ extern "C" int srl_philox_perm(uint64_t seed, uint32_t epoch, int n_env, int gro
   int grid = (n_env + threads - 1) / threads;
   const int cap = sm_count() * 8;
   if (grid > cap) grid = cap;
-  philox_perm_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  philox_perm_kernel<<<dim3(grid, n_epochs), threads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<uint32_t>(seed & 0xffffffffull), static_cast<uint32_t>(seed >> 32), epoch, n_env, group, bits, out);
   SRL_CUDA(cudaGetLastError());
   return SRL_OK;

@@ -4,9 +4,13 @@
 // One pass over the [T, n] minibatch: each element reads 29 B (25 B without value clipping) and
 // writes 12 B of gradients.  The advantage-normalisation statistics arrive pre-reduced (and, on
 // several GPUs, pre-all-reduced) from K2 + srl_group_stats, so there is no second pass and no grid
-// barrier.  Seven masked sums are reduced warp-shuffle -> shared memory -> one float64 partial row per
-// CTA; the last CTA to finish (atomic ticket) folds the partials in a fixed order and writes the loss
-// scalars and the stats vector -- deterministic for a given launch shape, and no host sync anywhere.
+// barrier.  Eight masked sums are reduced warp-shuffle -> shared memory -> one float64 partial row per
+// CTA in the caller's workspace slot.  Two ways to turn the rows into the loss scalars + stats vector:
+//   immediate (out != NULL): the last CTA to finish (atomic ticket) folds the rows in a fixed order;
+//   deferred  (out == NULL): the kernel ends right after its stores -- the gradients are all the backward
+//     pass needs -- and srl_ppo_loss_finalize folds any number of slots later in ONE launch (the reference
+//     pays eleven .item() syncs per epoch for the same numbers, mappo.py:293-299).
+// Either way the result is deterministic for a given launch shape and nothing syncs with the host.
 #include <float.h>
 
 #include "common.cuh"
@@ -17,6 +21,16 @@ namespace {
 constexpr int kMaxGrid = 2048;
 constexpr int kNumSums = 8;
 constexpr size_t kPartialsOffset = 64;
+
+// First 64 bytes of a workspace slot; the partial rows [n_rows][8] f64 follow.
+struct SlotHeader {
+  unsigned int ticket;  // immediate mode only; zero between launches
+  unsigned int n_rows;  // CTAs that wrote a partial row
+  double mask_sum;      // this rank's sum(mask) for the minibatch
+  double wv, we;        // loss weights, so the finaliser needs nothing but the slot
+  double pad[4];
+};
+static_assert(sizeof(SlotHeader) == kPartialsOffset, "slot header must stay 64 bytes");
 
 struct LossHyperDev {
   float clip_lo, clip_hi;  // (float)(1 -/+ eps_clip)
@@ -51,7 +65,7 @@ struct LossParams {
   double* out;
   float* out_f32;
   double* partials;
-  unsigned int* ticket;
+  SlotHeader* slot;
   LossHyperDev h;
 };
 
@@ -91,6 +105,37 @@ struct Uniforms {
 struct Acc {
   double pl = 0, vl = 0, en = 0, adv = 0, ratio = 0, clip = 0, vt = 0, ret = 0;
 };
+
+// The six scalars every thread needs.  Loading them is split from the math on them so that the (long) fp64
+// divide / sqrt latency overlaps the element loads instead of preceding them.
+struct RawStats {
+  double cnt, s1, s2, m_local, pa_mu, pa_sd;
+  bool popart;
+};
+
+__device__ __forceinline__ RawStats load_raw_stats(const LossParams& p) {
+  RawStats r;
+  r.cnt = __ldg(p.norm_stats);
+  r.s1 = __ldg(p.norm_stats + 1);
+  r.s2 = __ldg(p.norm_stats + 2);
+  r.m_local = __ldg(p.local_stats);
+  r.popart = p.popart != nullptr;
+  r.pa_mu = r.popart ? __ldg(p.popart) : 0.0;
+  r.pa_sd = r.popart ? __ldg(p.popart + 1) : 1.0;
+  return r;
+}
+
+__device__ __forceinline__ Uniforms make_uniforms(const RawStats& r, double adv_eps) {
+  Uniforms u;
+  u.popart = r.popart;
+  u.pa_mu = r.pa_mu;
+  u.pa_sd = r.pa_sd;
+  u.mean = r.s1 / r.cnt;
+  const double var = r.s2 / r.cnt - u.mean * u.mean;  // biased variance, utils.py:62-64
+  u.denom = sqrt(var) + adv_eps;                      // eps outside the sqrt, utils.py:67
+  u.inv_m = 1.f / static_cast<float>(r.m_local);
+  return u;
+}
 
 __device__ __forceinline__ float popart_normalize(float x, const Uniforms& u) {
   // RunningMeanStd.normalize: ((x.double() - mean) / std).clip(-5, 5).float()   utils.py:139-144
@@ -155,47 +200,22 @@ __device__ __forceinline__ void element(const LossHyperDev& h, const Uniforms& u
   }
 }
 
-// Block reduction of the 8 masked sums, per-CTA partial row, last-CTA finalisation.
-__device__ __forceinline__ void reduce_and_finalize(const LossParams& p, const Acc& acc) {
-  const LossHyperDev& h = p.h;
-  __shared__ double sred[kNumSums][8];
-  __shared__ bool is_last;
-  double v[kNumSums] = {acc.pl, acc.vl, acc.en, acc.adv, acc.ratio, acc.clip, acc.vt, acc.ret};
+// Folds n_rows partial rows (fixed order: lane-strided, then the warp-shuffle tree) and writes the results.
+// Called by one CTA; sred is [kNumSums][8] shared scratch.
+__device__ __forceinline__ void fold_rows_and_write(const double* __restrict__ partials, int n_rows, double M, double wv,
+                                                    double we, double (*sred)[8], double* __restrict__ o,
+                                                    float* __restrict__ o32) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-#pragma unroll
-  for (int k = 0; k < kNumSums; ++k) {
-    const double s = warp_sum(v[k]);
-    if (lane == 0) sred[k][warp] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < kNumSums) {
-    double s = 0.0;
-    for (int w = 0; w < nwarps; ++w) s += sred[threadIdx.x][w];
-    p.partials[static_cast<size_t>(blockIdx.x) * kNumSums + threadIdx.x] = s;
-    __threadfence();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int done = atomicAdd(p.ticket, 1u);
-    is_last = (done == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-
-  // ---- last CTA: fold the per-CTA partials in a fixed order, finalise ----------------------------
-  __threadfence();
   for (int k = warp; k < kNumSums; k += nwarps) {
     double s = 0.0;
-    for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) s += __ldcg(p.partials + static_cast<size_t>(b) * kNumSums + k);
+    for (int b = lane; b < n_rows; b += 32) s += __ldcg(partials + static_cast<size_t>(b) * kNumSums + k);
     s = warp_sum(s);
     if (lane == 0) sred[k][0] = s;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const double M = p.local_stats[0];
     const double pl = sred[0][0] / M, vl = sred[1][0] / M, el = -sred[2][0] / M;
-    const double loss = pl + static_cast<double>(h.wv) * vl + static_cast<double>(h.we) * el;
-    double* o = p.out;
+    const double loss = pl + wv * vl + we * el;
     o[SRL_OUT_LOSS] = loss;
     o[SRL_OUT_POLICY_LOSS] = pl;
     o[SRL_OUT_VALUE_LOSS] = vl;
@@ -207,30 +227,87 @@ __device__ __forceinline__ void reduce_and_finalize(const LossParams& p, const A
     o[SRL_OUT_DENORM_VALUE] = sred[7][0] / M;
     o[SRL_OUT_MASK_SUM] = M;
     for (int k = SRL_OUT_MASK_SUM + 1; k < SRL_LOSS_OUT_LEN; ++k) o[k] = 0.0;
-    if (p.out_f32) {
-      p.out_f32[0] = static_cast<float>(loss);
-      p.out_f32[1] = static_cast<float>(pl);
-      p.out_f32[2] = static_cast<float>(vl);
-      p.out_f32[3] = static_cast<float>(el);
+    if (o32) {
+      o32[0] = static_cast<float>(loss);
+      o32[1] = static_cast<float>(pl);
+      o32[2] = static_cast<float>(vl);
+      o32[3] = static_cast<float>(el);
     }
-    *p.ticket = 0u;  // ready for the next launch on this workspace
   }
+}
+
+// Block reduction of the 8 masked sums -> this CTA's partial row; then either done (deferred) or ticket.
+__device__ __forceinline__ void reduce_and_finalize(const LossParams& p, const Acc& acc, double mask_sum) {
+  const LossHyperDev& h = p.h;
+  __shared__ double sred[kNumSums][8];
+  __shared__ bool is_last;
+  double v[kNumSums] = {acc.pl, acc.vl, acc.en, acc.adv, acc.ratio, acc.clip, acc.vt, acc.ret};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // butterfly level by level over all 8 sums: 8 independent shuffle+add chains per level hide each other's latency
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double w[kNumSums];
+#pragma unroll
+    for (int k = 0; k < kNumSums; ++k) w[k] = __shfl_xor_sync(0xffffffffu, v[k], o);
+#pragma unroll
+    for (int k = 0; k < kNumSums; ++k) v[k] += w[k];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kNumSums; ++k) sred[k][warp] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumSums) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += sred[threadIdx.x][w];
+    p.partials[static_cast<size_t>(blockIdx.x) * kNumSums + threadIdx.x] = s;
+  }
+  if (p.out == nullptr) {  // deferred: publish what the finaliser needs and leave
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      p.slot->n_rows = gridDim.x;
+      p.slot->mask_sum = mask_sum;
+      p.slot->wv = static_cast<double>(h.wv);
+      p.slot->we = static_cast<double>(h.we);
+    }
+    return;
+  }
+  if (threadIdx.x < kNumSums) __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(&p.slot->ticket, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  fold_rows_and_write(p.partials, static_cast<int>(gridDim.x), mask_sum, static_cast<double>(h.wv),
+                      static_cast<double>(h.we), sred, p.out, p.out_f32);
+  if (threadIdx.x == 0) p.slot->ticket = 0u;  // ready for the next launch on this slot
+}
+
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const unsigned char* __restrict__ ws, size_t slot_bytes,
+                                                            double* __restrict__ out, float* __restrict__ out_f32) {
+  __shared__ double sred[kNumSums][8];
+  const unsigned char* base = ws + static_cast<size_t>(blockIdx.x) * slot_bytes;
+  const SlotHeader* hd = reinterpret_cast<const SlotHeader*>(base);
+  fold_rows_and_write(reinterpret_cast<const double*>(base + kPartialsOffset), static_cast<int>(hd->n_rows),
+                      hd->mask_sum, hd->wv, hd->we, sred, out + static_cast<size_t>(blockIdx.x) * SRL_LOSS_OUT_LEN,
+                      out_f32 ? out_f32 + static_cast<size_t>(blockIdx.x) * 4 : nullptr);
 }
 
 template <bool VEC4>
 __global__ void __launch_bounds__(256) ppo_loss_kernel(const LossParams p) {
   const LossHyperDev& h = p.h;
+#ifdef SRL_DEBUG_PHASES
+  const long long dbg0 = clock64();
+#endif
+  const RawStats raw = load_raw_stats(p);  // loads only; the math on them runs under the element loads
   Uniforms u;
-  {
-    const double cnt = p.norm_stats[0], s1 = p.norm_stats[1], s2 = p.norm_stats[2];
-    u.mean = s1 / cnt;
-    const double var = s2 / cnt - u.mean * u.mean;  // biased variance, utils.py:62-64
-    u.denom = sqrt(var) + h.adv_eps;                // eps outside the sqrt, utils.py:67
-    u.inv_m = 1.f / static_cast<float>(p.local_stats[0]);
-    u.popart = p.popart != nullptr;
-    u.pa_mu = u.popart ? p.popart[0] : 0.0;
-    u.pa_sd = u.popart ? p.popart[1] : 1.0;
-  }
+  bool have_u = false;
+  const double mask_sum = raw.m_local;
+#ifdef SRL_DEBUG_PHASES
+  const long long dbg1 = clock64();
+#endif
   Acc acc;
   const int n = p.n, T = p.T;
   if (VEC4) {
@@ -250,6 +327,10 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const LossParams p) {
       float4 ov = make_float4(0.f, 0.f, 0.f, 0.f);
       if (h.clip_value) ov = ldg_stream(reinterpret_cast<const float4*>(p.old_value + os));
       const uint32_t rs = ldg_stream(reinterpret_cast<const uint32_t*>(p.reset_next + os));
+      if (!have_u) {
+        u = make_uniforms(raw, h.adv_eps);
+        have_u = true;
+      }
       float4 glp, gv, ge;
       element(h, u, nl.x, vp.x, en.x, ol.x, ov.x, rt.x, ad.x, rs & 0xffu, glp.x, gv.x, ge.x, acc);
       element(h, u, nl.y, vp.y, en.y, ol.y, ov.y, rt.y, ad.y, (rs >> 8) & 0xffu, glp.y, gv.y, ge.y, acc);
@@ -265,12 +346,16 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const LossParams p) {
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
       const int t = static_cast<int>(i / n);
       const int j = static_cast<int>(i - static_cast<long long>(t) * n);
-      const int c = p.lane_idx ? p.lane_idx[j] : j;  // minibatch gather fused into the load
+      const int c = p.lane_idx ? __ldg(p.lane_idx + j) : j;  // minibatch gather fused into the load
       const long long op = t * p.ld_pol + j, os = t * p.ld_smp + c, og = t * p.ld_grad + j;
       const float nl = ldg_stream(p.new_logp + op), vp = ldg_stream(p.v_pred + op), en = ldg_stream(p.entropy + op);
       const float ol = __ldg(p.old_logp + os), rt = __ldg(p.ret + os), ad = __ldg(p.adv + os);
       const float ov = h.clip_value ? __ldg(p.old_value + os) : 0.f;
       const uint32_t rs = __ldg(p.reset_next + os);
+      if (!have_u) {
+        u = make_uniforms(raw, h.adv_eps);
+        have_u = true;
+      }
       float glp, gv, ge;
       element(h, u, nl, vp, en, ol, ov, rt, ad, rs, glp, gv, ge, acc);
       stg_stream(p.g_logp + og, glp);
@@ -278,8 +363,15 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const LossParams p) {
       stg_stream(p.g_entropy + og, ge);
     }
   }
-
-  reduce_and_finalize(p, acc);
+#ifdef SRL_DEBUG_PHASES
+  const long long dbg2 = clock64() + (acc.pl == 123.0);
+#endif
+  reduce_and_finalize(p, acc, mask_sum);
+#ifdef SRL_DEBUG_PHASES
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+    printf("loss block %d/%d (%d thr): uniforms %lld  elements %lld  reduce %lld cycles\n", blockIdx.x, gridDim.x, blockDim.x,
+           dbg1 - dbg0, dbg2 - dbg1, clock64() - dbg2);
+#endif
 }
 
 
@@ -303,17 +395,9 @@ __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const LogitsParams
   extern __shared__ float srow[];  // [256][SK + 1]
   const LossParams& p = q.c;
   const LossHyperDev& h = p.h;
-  Uniforms u;
-  {
-    const double cnt = p.norm_stats[0], s1 = p.norm_stats[1], s2 = p.norm_stats[2];
-    u.mean = s1 / cnt;
-    const double var = s2 / cnt - u.mean * u.mean;
-    u.denom = sqrt(var) + h.adv_eps;
-    u.inv_m = 1.f / static_cast<float>(p.local_stats[0]);
-    u.popart = p.popart != nullptr;
-    u.pa_mu = u.popart ? p.popart[0] : 0.0;
-    u.pa_sd = u.popart ? p.popart[1] : 1.0;
-  }
+  const RawStats raw = load_raw_stats(p);
+  const double mask_sum = raw.m_local;
+  const Uniforms u = make_uniforms(raw, h.adv_eps);
   Acc acc;
   const int SK = q.SK, stride = SK + 1;
   const long long W = static_cast<long long>(p.T) * p.n;
@@ -394,7 +478,7 @@ __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const LogitsParams
     }
     __syncthreads();
   }
-  reduce_and_finalize(p, acc);
+  reduce_and_finalize(p, acc, mask_sum);
 }
 
 }  // namespace
@@ -402,6 +486,20 @@ __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const LogitsParams
 
 extern "C" size_t srl_ppo_loss_workspace_bytes(int, int) {
   return srl::kPartialsOffset + static_cast<size_t>(srl::kMaxGrid) * srl::kNumSums * sizeof(double);
+}
+
+extern "C" int srl_ppo_loss_finalize(const void* workspace, size_t slot_bytes, int n_slots, double* out, float* out_f32,
+                                     srl_stream_t stream) {
+  using namespace srl;
+  SRL_REQUIRE(n_slots >= 0, SRL_ERR_INVALID_ARG, "srl_ppo_loss_finalize: negative slot count");
+  if (n_slots == 0) return SRL_OK;
+  SRL_REQUIRE(workspace && out, SRL_ERR_INVALID_ARG, "srl_ppo_loss_finalize: null pointer");
+  SRL_REQUIRE(slot_bytes >= srl_ppo_loss_workspace_bytes(1, 1) && slot_bytes % 8 == 0, SRL_ERR_INVALID_ARG,
+              "srl_ppo_loss_finalize: slot_bytes=%zu smaller than one workspace or not 8-byte aligned", slot_bytes);
+  loss_finalize_kernel<<<n_slots, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const unsigned char*>(workspace), slot_bytes, out, out_f32);
+  SRL_CUDA(cudaGetLastError());
+  return SRL_OK;
 }
 
 namespace srl {
@@ -438,7 +536,7 @@ extern "C" int srl_ppo_loss_fwd_bwd(const float* new_logp, const float* v_pred, 
   using namespace srl;
   SRL_REQUIRE(T >= 1 && n >= 1, SRL_ERR_INVALID_ARG, "srl_ppo_loss_fwd_bwd: need T >= 1 and n >= 1 (got %d, %d)", T, n);
   SRL_REQUIRE(new_logp && v_pred && entropy && old_logp && ret && adv && on_reset_next && g_logp && g_value &&
-                  g_entropy && out && norm_stats && local_stats && workspace,
+                  g_entropy && norm_stats && local_stats && workspace,
               SRL_ERR_INVALID_ARG, "srl_ppo_loss_fwd_bwd: null pointer");
   SRL_REQUIRE(ld_pol >= n && ld_grad >= n && ld_smp >= (lane_idx ? 1 : n), SRL_ERR_INVALID_ARG,
               "srl_ppo_loss_fwd_bwd: row strides smaller than the row");
@@ -471,7 +569,7 @@ extern "C" int srl_ppo_loss_fwd_bwd(const float* new_logp, const float* v_pred, 
   p.ld_grad = ld_grad;
   p.out = out;
   p.out_f32 = out_f32;
-  p.ticket = reinterpret_cast<unsigned int*>(workspace);
+  p.slot = reinterpret_cast<SlotHeader*>(workspace);
   p.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + kPartialsOffset);
 
   const bool vec4 = lane_idx == nullptr && (n % 4 == 0) && (ld_pol % 4 == 0) && (ld_smp % 4 == 0) &&
@@ -479,14 +577,16 @@ extern "C" int srl_ppo_loss_fwd_bwd(const float* new_logp, const float* v_pred, 
                     aligned(old_logp, 16) && aligned(ret, 16) && aligned(adv, 16) &&
                     (!p.h.clip_value || aligned(old_value, 16)) && aligned(on_reset_next, 4) && aligned(g_logp, 16) &&
                     aligned(g_value, 16) && aligned(g_entropy, 16);
-  const long long W = static_cast<long long>(T) * (vec4 ? n / 4 : n);
   const int sms = sm_count();
+  // small problems are latency-bound: one element per thread keeps the per-thread dependency chain short
+  const bool use_vec4 = vec4 && static_cast<long long>(T) * n >= static_cast<long long>(sms) * 256 * 8;
+  const long long W = static_cast<long long>(T) * (use_vec4 ? n / 4 : n);
   const int threads = (W <= static_cast<long long>(sms) * 256) ? 128 : 256;
   long long grid = (W + threads - 1) / threads;
   const long long cap = static_cast<long long>(sms) * 8 < kMaxGrid ? static_cast<long long>(sms) * 8 : kMaxGrid;
   if (grid > cap) grid = cap;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (vec4)
+  if (use_vec4)
     ppo_loss_kernel<true><<<static_cast<int>(grid), threads, 0, st>>>(p);
   else
     ppo_loss_kernel<false><<<static_cast<int>(grid), threads, 0, st>>>(p);
@@ -507,7 +607,7 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
   SRL_REQUIRE(T >= 1 && n >= 1, SRL_ERR_INVALID_ARG, "srl_ppo_loss_from_logits: need T >= 1 and n >= 1");
   SRL_REQUIRE(heads >= 1 && heads <= SRL_MAX_HEADS && head_sizes_host, SRL_ERR_INVALID_ARG,
               "srl_ppo_loss_from_logits: heads=%d outside [1, %d]", heads, SRL_MAX_HEADS);
-  SRL_REQUIRE(logits && action && v_pred && old_logp && ret && adv && on_reset_next && g_logits && g_value && out &&
+  SRL_REQUIRE(logits && action && v_pred && old_logp && ret && adv && on_reset_next && g_logits && g_value &&
                   norm_stats && local_stats && workspace,
               SRL_ERR_INVALID_ARG, "srl_ppo_loss_from_logits: null pointer");
   SRL_REQUIRE(ld_smp >= (lane_idx ? 1 : n), SRL_ERR_INVALID_ARG, "srl_ppo_loss_from_logits: ld_smp smaller than the row");
@@ -555,7 +655,7 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
   p.ld_grad = n;
   p.out = out;
   p.out_f32 = out_f32;
-  p.ticket = reinterpret_cast<unsigned int*>(workspace);
+  p.slot = reinterpret_cast<SlotHeader*>(workspace);
   p.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + kPartialsOffset);
   static bool opted_in[64] = {};
   int dev = 0;

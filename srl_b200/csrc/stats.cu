@@ -16,11 +16,15 @@ constexpr int kThreads = 256;
 // grid = (kClusterX, G).  CTA r of the cluster sums lanes [r*chunk, (r+1)*chunk) of group g, then CTA 0
 // adds the 8 CTA results in rank order through DSMEM: fixed summation order, no atomics, no scratch.
 __global__ void __cluster_dims__(kClusterX, 1, 1) __launch_bounds__(kThreads)
-    group_stats_kernel(const double* __restrict__ lane_part, int N, const int32_t* __restrict__ idx, int per,
-                       double* __restrict__ out) {
+    group_stats_kernel(const double* __restrict__ lane_part, int N, const int32_t* __restrict__ idx, int per_group,
+                       int whole_first, double* __restrict__ out) {
   cg::cluster_group cluster = cg::this_cluster();
-  const int g = blockIdx.y;
   const int r = static_cast<int>(cluster.block_rank());
+  // output row blockIdx.y; with whole_first, row 0 is the identity group over all N lanes
+  const bool whole = whole_first && blockIdx.y == 0;
+  const int g = static_cast<int>(blockIdx.y) - (whole_first ? 1 : 0);
+  const int per = whole ? N : per_group;
+  if (whole) idx = nullptr;
   const int chunk = (per + kClusterX - 1) / kClusterX;
   const int j0 = r * chunk, j1 = min(per, j0 + chunk);
 
@@ -28,7 +32,7 @@ __global__ void __cluster_dims__(kClusterX, 1, 1) __launch_bounds__(kThreads)
 #pragma unroll
   for (int k = 0; k < SRL_LANE_PART; ++k) acc[k] = 0.0;
   for (int j = j0 + threadIdx.x; j < j1; j += kThreads) {
-    const int lane = idx ? idx[static_cast<size_t>(g) * per + j] : g * per + j;
+    const int lane = whole ? j : (idx ? idx[static_cast<size_t>(g) * per + j] : g * per + j);
 #pragma unroll
     for (int k = 0; k < SRL_LANE_PART - 1; ++k) acc[k] += __ldg(lane_part + static_cast<size_t>(k) * N + lane);
   }
@@ -53,7 +57,7 @@ __global__ void __cluster_dims__(kClusterX, 1, 1) __launch_bounds__(kThreads)
       const double* remote = cluster.map_shared_rank(cta_sum, q);
       s += remote[threadIdx.x];
     }
-    out[static_cast<size_t>(g) * SRL_LANE_PART + threadIdx.x] = s;
+    out[static_cast<size_t>(blockIdx.y) * SRL_LANE_PART + threadIdx.x] = s;
   }
   cluster.sync();  // keep every CTA's shared memory alive until rank 0 has read it
 }
@@ -88,16 +92,17 @@ __global__ void popart_update_kernel(const double* __restrict__ bs, double* __re
 }  // namespace
 }  // namespace srl
 
-extern "C" int srl_group_stats(const double* lane_part, int N, const int32_t* idx, int G, int per, double* out,
-                               srl_stream_t stream) {
+extern "C" int srl_group_stats(const double* lane_part, int N, const int32_t* idx, int G, int per, int whole_first,
+                               double* out, srl_stream_t stream) {
   using namespace srl;
   SRL_REQUIRE(lane_part && out, SRL_ERR_INVALID_ARG, "srl_group_stats: null pointer");
-  SRL_REQUIRE(N >= 1 && G >= 1 && per >= 1, SRL_ERR_INVALID_ARG, "srl_group_stats: need N, G, per >= 1");
+  SRL_REQUIRE(N >= 1 && G >= (whole_first ? 0 : 1) && per >= 1, SRL_ERR_INVALID_ARG,
+              "srl_group_stats: need N, G, per >= 1");
   SRL_REQUIRE(idx != nullptr || static_cast<long long>(G) * per <= N, SRL_ERR_INVALID_ARG,
               "srl_group_stats: G*per=%lld exceeds N=%d", static_cast<long long>(G) * per, N);
   SRL_REQUIRE(G <= 65535, SRL_ERR_UNSUPPORTED, "srl_group_stats: at most 65535 groups");
-  group_stats_kernel<<<dim3(kClusterX, G), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(lane_part, N, idx, per,
-                                                                                             out);
+  group_stats_kernel<<<dim3(kClusterX, G + (whole_first ? 1 : 0)), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      lane_part, N, idx, per, whole_first, out);
   SRL_CUDA(cudaGetLastError());
   return SRL_OK;
 }

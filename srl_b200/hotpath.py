@@ -1,0 +1,308 @@
+"""Device-resident executor of the trainer hot path for one batch shape.
+
+Owns every HBM buffer the path needs (allocated once, reused every step), the pinned host staging
+buffers for the host-facing entry point, the statistics tables and -- optionally -- a CUDA graph of the
+whole step.  `srl_b200.trainer.MultiAgentPPOB200` and `bench.py` both drive this class.
+
+Step structure (reference: MultiAgentPPO.step, legacy/algorithm/ppo/mappo.py:219-328):
+
+    load_sample        H2D of the six scalar leaves                      (api/trainer.py:215-217)
+    advantages         K2 GAE scan -> adv, ret, per-lane partial sums    (mappo.py:252-257)
+                       K5 Philox permutations for all epochs             (new)
+                       group statistics for the batch and every minibatch
+                       [one all-reduce of the whole table across ranks]  (utils.py:58-61,121-124)
+    per epoch          PopArt update                                      (mappo.py:263-264)
+      per minibatch    K4 fused loss forward+backward, gather fused in   (mappo.py:270-274)
+
+HBM layout: every leaf is time-major [L, N], lanes contiguous; N = B * n_agents; flags stay uint8.
+Statistics table: float64 [1 + E*M, 8]; row 0 = whole batch, row 1 + e*M + j = minibatch j of epoch e.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from srl_b200 import ops
+from srl_b200._lib import SRL_LANE_PART, SRL_LOSS_OUT_LEN
+
+SAMPLE_F32 = ("reward", "value", "old_logp")
+SAMPLE_U8 = ("done", "truncated", "on_reset")
+
+
+class HotPath:
+
+    def __init__(self, L: int, B: int, A: int = 1, *, gamma: float, lmbda: float, hyper: ops.LossHyper,
+                 bootstrap_steps: int = 1, burn_in_steps: int = 0, epochs: int = 1, minibatches: int = 1, seed: int = 0,
+                 popart: bool = False, popart_beta: float = 0.99999, popart_eps: float = 1e-5,
+                 device: Optional[torch.device] = None, process_group=None, fuse_gather: bool = True,
+                 graph_branches: int = 8):
+        if not torch.cuda.is_available():
+            raise RuntimeError("srl_b200.HotPath needs a CUDA device (there is no CPU path)")
+        if bootstrap_steps < 1:
+            # mappo.py:259-261 slices on_reset[1 + burn_in : 1 + L - bootstrap]; with bootstrap_steps == 0 the
+            # reference's mask is one row short of the data and the loss raises.  Same restriction here.
+            raise ValueError("bootstrap_steps must be >= 1")
+        if B % minibatches != 0:
+            raise ValueError(f"B={B} environments do not split into {minibatches} equal minibatches")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.L, self.B, self.A, self.N = L, B, A, B * A
+        self.gamma, self.lmbda, self.hyper = float(gamma), float(lmbda), hyper
+        self.row_lo, self.row_hi = burn_in_steps, L - bootstrap_steps
+        self.T = self.row_hi - self.row_lo
+        if self.T < 1:
+            raise ValueError(f"no loss rows: L={L}, burn_in={burn_in_steps}, bootstrap={bootstrap_steps}")
+        self.epochs, self.minibatches, self.seed = epochs, minibatches, int(seed)
+        self.n_mb = self.N // minibatches  # lanes per minibatch
+        self.popart, self.popart_beta, self.popart_eps = popart, popart_beta, popart_eps
+        self.pg = process_group
+        self.fuse_gather = fuse_gather
+        self.graph_branches = max(1, int(graph_branches))
+        self.step_count = 0
+
+        dev, N = self.device, self.N
+        f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        u8 = lambda *s: torch.empty(s, dtype=torch.uint8, device=dev)
+        self.leaf: Dict[str, torch.Tensor] = {k: f32(L, N) for k in SAMPLE_F32}
+        self.leaf.update({k: u8(L, N) for k in SAMPLE_U8})
+        self.adv, self.ret = f32(L, N), f32(L, N)
+        self.lane_part = torch.empty((SRL_LANE_PART, N), dtype=torch.float64, device=dev)
+        G = 1 + epochs * minibatches
+        self.local_stats = torch.zeros((G, SRL_LANE_PART), dtype=torch.float64, device=dev)
+        self.global_stats = self.local_stats if process_group is None else torch.zeros_like(self.local_stats)
+        self.perm = torch.empty((epochs, N), dtype=torch.int32, device=dev) if minibatches > 1 else None
+        self.popart_state = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.popart_ms = torch.tensor([0.0, 0.1, 0.0, 0.1], dtype=torch.float64, device=dev)  # sqrt(1e-2) floor
+        n = self.n_mb
+        self.grads = [[tuple(f32(self.T, n) for _ in range(3)) for _ in range(minibatches)] for _ in range(epochs)]
+        self.out = torch.zeros((epochs * minibatches, SRL_LOSS_OUT_LEN), dtype=torch.float64, device=dev)
+        self.out_f32 = torch.zeros((epochs * minibatches, 4), dtype=torch.float32, device=dev)
+        self.workspace = ops.new_loss_workspace(dev, slots=epochs * minibatches)  # one slot per (epoch, minibatch)
+        if not fuse_gather and minibatches > 1:  # explicit K5 gather into contiguous minibatch leaves
+            self.mb_leaf = {k: f32(L, n) for k in ("old_logp", "value", "ret", "adv")}
+            self.mb_leaf["on_reset"] = u8(L, n)
+        # pinned host mirrors for the host-facing call
+        self._pin: Dict[str, torch.Tensor] = {}
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_pol = None
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------------------------------
+    def popart_mean_std(self) -> Optional[torch.Tensor]:
+        return self.popart_ms if self.popart else None
+
+    def _pinned(self, key: str, like: np.ndarray) -> torch.Tensor:
+        t = self._pin.get(key)
+        if t is None or t.numel() != like.size or t.dtype != torch.from_numpy(like.reshape(-1)[:1]).dtype:
+            t = torch.empty(like.size, dtype=torch.from_numpy(like.reshape(-1)[:1]).dtype).pin_memory()
+            self._pin[key] = t
+        return t
+
+    def load_sample(self, sample: Dict[str, np.ndarray], non_blocking: bool = True) -> int:
+        """Host -> HBM copy of the scalar leaves (reward, value, old_logp float32; done, truncated,
+        on_reset uint8, each [L, B, (A,) 1] or [L, N]).  Float flags are narrowed to uint8 on the host:
+        the reference's device representation is float32 (api/trainer.py:217), ours is one byte.
+        Returns the bytes moved."""
+        moved = 0
+        for k in SAMPLE_F32 + SAMPLE_U8:
+            x = sample[k]
+            want = np.float32 if k in SAMPLE_F32 else np.uint8
+            if isinstance(x, torch.Tensor):
+                if x.is_pinned() and x.dtype == (torch.float32 if k in SAMPLE_F32 else torch.uint8) and \
+                        x.numel() == self.L * self.N and x.is_contiguous():
+                    self.leaf[k].view(-1).copy_(x.view(-1), non_blocking=non_blocking)  # already page-locked
+                    moved += x.numel() * x.element_size()
+                    continue
+                x = x.numpy()
+            if x.size != self.L * self.N:
+                raise ValueError(f"{k}: {x.shape} does not hold L*N = {self.L}*{self.N} elements")
+            if x.dtype != want:
+                x = x.astype(want)
+            pin = self._pinned(k, x)
+            pin.numpy()[:] = x.reshape(-1)
+            self.leaf[k].view(-1).copy_(pin, non_blocking=non_blocking)
+            moved += x.nbytes
+        return moved
+
+    # ------------------------------------------------------------------------------------------
+    def advantages(self) -> None:
+        """K2, then all epochs' permutations in one launch, then the whole statistics table in one launch
+        (+ the one small all-reduce when distributed)."""
+        lf = self.leaf
+        ops.gae_scan(lf["reward"], lf["value"], lf["done"], lf["truncated"], lf["on_reset"], self.gamma, self.lmbda,
+                     row_lo=self.row_lo, row_hi=self.row_hi, popart_mean_std=self.popart_mean_std(), adv=self.adv,
+                     ret=self.ret, lane_part=self.lane_part)
+        if self.minibatches > 1:
+            ops.philox_perm(self.seed + self.step_count, 0, self.B, self.A, out=self.perm, n_epochs=self.epochs)
+            ops.group_stats(self.lane_part, idx=self.perm.view(-1), groups=self.epochs * self.minibatches, per=self.n_mb,
+                            out=self.local_stats, whole_first=True)
+        else:
+            ops.group_stats(self.lane_part, groups=1, per=self.N, out=self.local_stats[0:1])
+        if self.pg is not None:
+            self.global_stats.copy_(self.local_stats)
+            torch.distributed.all_reduce(self.global_stats, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    def stats_row(self, e: int, j: int) -> int:
+        return 0 if self.minibatches == 1 else 1 + e * self.minibatches + j
+
+    def minibatch_lanes(self, e: int, j: int) -> Optional[torch.Tensor]:
+        """int32 lane indices of minibatch j in epoch e (None = the whole batch in order)."""
+        if self.minibatches == 1:
+            return None
+        return self.perm[e, j * self.n_mb:(j + 1) * self.n_mb]
+
+    def update_popart(self) -> None:
+        """Once per epoch before the loss (mappo.py:263-264), on the whole-batch (all-reduced) row."""
+        ops.popart_update(self.global_stats[0], self.popart_state, self.popart_beta, self.popart_eps, self.popart_ms)
+
+    def loss(self, e: int, j: int, new_logp: torch.Tensor, v_pred: torch.Tensor, entropy: torch.Tensor):
+        """K4 for minibatch (e, j) in deferred mode: gradients now, loss scalars + stats at finalize().
+        Policy outputs are [T, n_mb] float32.  Returns (g_logp, g_value, g_entropy, None, None)."""
+        lo, hi = self.row_lo, self.row_hi
+        row = self.stats_row(e, j)
+        k = e * self.minibatches + j
+        idx = self.minibatch_lanes(e, j)
+        lf = self.leaf
+        if idx is not None and not self.fuse_gather:
+            m = self.mb_leaf
+            ops.batch_gather([(lf["old_logp"].unsqueeze(-1), m["old_logp"].unsqueeze(-1)),
+                              (lf["value"].unsqueeze(-1), m["value"].unsqueeze(-1)),
+                              (self.ret.unsqueeze(-1), m["ret"].unsqueeze(-1)),
+                              (self.adv.unsqueeze(-1), m["adv"].unsqueeze(-1)),
+                              (lf["on_reset"].unsqueeze(-1), m["on_reset"].unsqueeze(-1))], idx)
+            olp, ov, rt, ad, rs, idx = m["old_logp"], m["value"], m["ret"], m["adv"], m["on_reset"], None
+        else:
+            olp, ov, rt, ad, rs = lf["old_logp"], lf["value"], self.ret, self.adv, lf["on_reset"]
+        return ops.ppo_loss_fwd_bwd(new_logp, v_pred, entropy, olp[lo:hi], ov[lo:hi], rt[lo:hi], ad[lo:hi],
+                                    rs[lo + 1:hi + 1], self.global_stats[row], self.hyper,
+                                    local_stats=self.local_stats[row], popart_mean_std=self.popart_mean_std(),
+                                    lane_idx=idx, grads=self.grads[e][j], workspace=self.workspace[k], defer=True)
+
+    def finalize(self) -> None:
+        """One launch: fold every minibatch's partial rows into self.out / self.out_f32 (loss scalars + stats)."""
+        ops.loss_finalize(self.workspace, self.out, self.out_f32)
+
+    # ------------------------------------------------------------------------------------------
+    def _run_losses(self, pol, branches: int = 1) -> None:
+        """Every (epoch, minibatch) loss launch, then finalize().  With branches > 1 the launches of one epoch are
+        spread round-robin over side streams (fork/join around each epoch): under CUDA-graph capture this
+        becomes parallel graph branches, so the small per-minibatch kernels overlap instead of queueing.
+        (PopArt re-normalises between epochs, hence the join per epoch.)"""
+        main = torch.cuda.current_stream()
+        if branches > 1 and not hasattr(self, "_side"):
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(branches)]
+        for e in range(self.epochs):
+            if self.popart:
+                self.update_popart()
+            if branches <= 1:
+                for j in range(self.minibatches):
+                    self.loss(e, j, *pol[e][j])
+                continue
+            used = self._side[:min(branches, self.minibatches)]
+            for st in used:
+                st.wait_stream(main)
+            for j in range(self.minibatches):
+                with torch.cuda.stream(used[j % len(used)]):
+                    self.loss(e, j, *pol[e][j])
+            for st in used:
+                main.wait_stream(st)
+        self.finalize()
+
+    def run_device(self, pol, use_graph: bool = True) -> None:
+        """The whole step on resident inputs: advantages() then every (epoch, minibatch) loss.
+        pol[e][j] = (new_logp, v_pred, entropy), each [T, n_mb] float32 on device.  With use_graph the
+        launches are captured once into a CUDA graph (two graphs around the all-reduce when distributed)."""
+        if not use_graph:
+            self.advantages()
+            self._run_losses(pol)
+            self.step_count += 1
+            return
+        if self._graph is None or self._graph_pol is not pol:
+            self._capture(pol)
+        if self.pg is None:
+            self._graph.replay()
+        else:
+            self._graph_a.replay()
+            self.global_stats.copy_(self.local_stats)
+            torch.distributed.all_reduce(self.global_stats, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            self._graph.replay()
+        self.step_count += 1
+
+    def _capture(self, pol) -> None:
+        # NOTE: launch arguments are frozen at capture, so a replayed graph re-uses the permutations of
+        # step_count == 0 every step (what a benchmark wants); the trainer launches eagerly and reseeds per step.
+        pg, self.pg = self.pg, None  # collectives stay outside the captured region
+        try:
+            # warm-up on a side stream (allocations, module loading) before capture
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                saved = self.step_count
+                self.step_count = 0
+                self.advantages()
+                self._run_losses(pol)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            if pg is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.advantages()
+                    self._run_losses(pol, self.graph_branches)
+                self._graph = g
+            else:
+                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga):
+                    self.advantages()
+                with torch.cuda.graph(gb):
+                    self._run_losses(pol, self.graph_branches)
+                self._graph_a, self._graph = ga, gb
+            self.step_count = saved
+        finally:
+            self.pg = pg
+        self._graph_pol = pol
+        self.launches_per_step = self.count_launches()
+
+    def count_launches(self) -> int:
+        """Kernels of this library launched by one step (the claim behind bench.py's gpu_launches)."""
+        n = 2  # gae_scan + group_stats
+        if self.minibatches > 1:
+            n += 1  # all epochs' permutations
+        per_loss = 1 if (self.fuse_gather or self.minibatches == 1) else 2
+        n += self.epochs * self.minibatches * per_loss
+        n += 1  # loss_finalize
+        if self.popart:
+            n += self.epochs
+        return n
+
+    # ------------------------------------------------------------------------------------------
+    def run_host(self, sample: Dict[str, np.ndarray], pol_host: List[List[tuple]], out_host: Dict[str, torch.Tensor],
+                 use_graph: bool = True) -> Dict[str, int]:
+        """Host buffers in, host buffers out: H2D of the sample scalars and of the policy outputs of every
+        minibatch, the device step, D2H of adv/ret (the reference mirrors them into the host sample,
+        mappo.py:254-257), of the three gradient tensors of every minibatch and of the stats table.
+        pol_host[e][j] = three pinned [T, n_mb] float32 tensors; out_host holds pinned destinations
+        'adv', 'ret' [L, N], 'grads' [E, M, 3, T, n_mb], 'out' [E*M, 16].  Returns byte counts."""
+        h2d = self.load_sample(sample)
+        if not hasattr(self, "_pol_dev"):
+            self._pol_dev = [[tuple(torch.empty((self.T, self.n_mb), dtype=torch.float32, device=self.device)
+                                    for _ in range(3)) for _ in range(self.minibatches)] for _ in range(self.epochs)]
+        for e in range(self.epochs):
+            for j in range(self.minibatches):
+                for d, h in zip(self._pol_dev[e][j], pol_host[e][j]):
+                    d.copy_(h, non_blocking=True)
+                    h2d += h.numel() * 4
+        self.run_device(self._pol_dev, use_graph=use_graph)
+        d2h = 0
+        out_host["adv"].copy_(self.adv, non_blocking=True)
+        out_host["ret"].copy_(self.ret, non_blocking=True)
+        d2h += 2 * self.adv.numel() * 4
+        for e in range(self.epochs):
+            for j in range(self.minibatches):
+                for q in range(3):
+                    out_host["grads"][e, j, q].copy_(self.grads[e][j][q], non_blocking=True)
+                    d2h += self.T * self.n_mb * 4
+        out_host["out"].copy_(self.out, non_blocking=True)
+        d2h += self.out.numel() * 8
+        torch.cuda.current_stream().synchronize()
+        return dict(h2d_bytes=h2d, d2h_bytes=d2h)

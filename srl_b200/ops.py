@@ -91,8 +91,9 @@ def gae_scan(reward, value, done, truncated, on_reset, gamma: float, lmbda: floa
 
 
 def group_stats(lane_part: torch.Tensor, idx: Optional[torch.Tensor] = None, groups: int = 1,
-                per: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[g, k] = sum of lane_part[k, lane] over the lanes of group g (fixed summation order)."""
+                per: Optional[int] = None, out: Optional[torch.Tensor] = None, whole_first: bool = False) -> torch.Tensor:
+    """out[g, k] = sum of lane_part[k, lane] over the lanes of group g (fixed summation order).
+    whole_first: out gets groups + 1 rows, row 0 = the sum over all N lanes (one launch for the whole table)."""
     _check(lane_part, torch.float64, "lane_part")
     N = lane_part.shape[1]
     if per is None:
@@ -101,9 +102,13 @@ def group_stats(lane_part: torch.Tensor, idx: Optional[torch.Tensor] = None, gro
         _check(idx, torch.int32, "idx")
         if idx.numel() < groups * per:
             raise ValueError(f"idx has {idx.numel()} entries, need groups*per = {groups * per}")
-    out = torch.empty((groups, SRL_LANE_PART), dtype=torch.float64, device=lane_part.device) if out is None else out
+    rows = groups + (1 if whole_first else 0)
+    out = torch.empty((rows, SRL_LANE_PART), dtype=torch.float64, device=lane_part.device) if out is None else out
     _check(out, torch.float64, "out")
-    _lib.call("srl_group_stats", _ptr(lane_part), N, _ptr(idx), int(groups), int(per), _ptr(out), _stream())
+    if out.numel() < rows * SRL_LANE_PART:
+        raise ValueError(f"out has {out.numel()} entries, need {rows * SRL_LANE_PART}")
+    _lib.call("srl_group_stats", _ptr(lane_part), N, _ptr(idx), int(groups), int(per), int(bool(whole_first)), _ptr(out),
+              _stream())
     return out
 
 
@@ -161,11 +166,25 @@ class LossHyper:
 _workspaces = {}
 
 
-def new_loss_workspace(device) -> torch.Tensor:
-    """A zero-initialised scratch buffer for the loss kernels (the ticket counter must start at 0; the kernel
-    re-zeroes it).  Launches that may overlap (different streams) must not share one."""
-    nbytes = _lib.load_library().srl_ppo_loss_workspace_bytes(1, 1)
-    return torch.zeros(nbytes, dtype=torch.uint8, device=device)
+def loss_slot_bytes() -> int:
+    return int(_lib.load_library().srl_ppo_loss_workspace_bytes(1, 1))
+
+
+def new_loss_workspace(device, slots: int = 1) -> torch.Tensor:
+    """Zero-initialised scratch for the loss kernels, uint8 [slots, slot_bytes] (the ticket counter must start at
+    0; the kernel re-zeroes it).  Launches that may overlap in time must use different slots."""
+    return torch.zeros((slots, loss_slot_bytes()), dtype=torch.uint8, device=device)
+
+
+def loss_finalize(workspace: torch.Tensor, out: torch.Tensor, out_f32: Optional[torch.Tensor] = None) -> None:
+    """Folds every slot of a deferred-mode workspace [slots, slot_bytes] into out [slots, 16] (float64) and
+    out_f32 [slots, 4] in one launch."""
+    _check(workspace, torch.uint8, "workspace")
+    _check(out, torch.float64, "out")
+    slots = workspace.shape[0]
+    if out.numel() < slots * SRL_LOSS_OUT_LEN or (out_f32 is not None and out_f32.numel() < slots * 4):
+        raise ValueError("loss_finalize: output tensors smaller than the number of slots")
+    _lib.call("srl_ppo_loss_finalize", _ptr(workspace), workspace.shape[1], slots, _ptr(out), _ptr(out_f32), _stream())
 
 
 def loss_workspace(device) -> torch.Tensor:
@@ -208,7 +227,7 @@ def _sample_side(old_logp, old_value, ret, adv, on_reset_next, lane_idx, T, n, c
 
 def ppo_loss_fwd_bwd(new_logp, v_pred, entropy, old_logp, old_value, ret, adv, on_reset_next, norm_stats, hyper: LossHyper,
                      local_stats=None, popart_mean_std=None, lane_idx=None, grads=None, out=None, out_f32=None,
-                     workspace=None):
+                     workspace=None, defer: bool = False):
     """One launch: loss, stats and d loss / d (new_logp, v_pred, entropy).
 
     Policy side `[T, n]` float32 contiguous; sample side `[>=T, N]` row views already offset to the
@@ -230,8 +249,13 @@ def ppo_loss_fwd_bwd(new_logp, v_pred, entropy, old_logp, old_value, ret, adv, o
     dev = new_logp.device
     if grads is None:
         grads = tuple(torch.empty_like(new_logp) for _ in range(3))
-    out = torch.empty(SRL_LOSS_OUT_LEN, dtype=torch.float64, device=dev) if out is None else out
-    out_f32 = torch.empty(4, dtype=torch.float32, device=dev) if out_f32 is None else out_f32
+    if defer:  # gradients + partial rows only; loss_finalize() folds the slot(s) later
+        if workspace is None:
+            raise ValueError("deferred finalisation needs an explicit workspace slot")
+        out = out_f32 = None
+    else:
+        out = torch.empty(SRL_LOSS_OUT_LEN, dtype=torch.float64, device=dev) if out is None else out
+        out_f32 = torch.empty(4, dtype=torch.float32, device=dev) if out_f32 is None else out_f32
     ws = loss_workspace(dev) if workspace is None else workspace
     hc = hyper.to_c()
     _lib.call("srl_ppo_loss_fwd_bwd", _ptr(new_logp), _ptr(v_pred), _ptr(entropy), n, _ptr(old_logp), _ptr(old_value),
@@ -306,14 +330,17 @@ class PPOLossFunction(torch.autograd.Function):
 # K5 / K1
 # ------------------------------------------------------------------------------------------------
 def philox_perm(seed: int, epoch: int, n_env: int, group: int = 1, out: Optional[torch.Tensor] = None,
-                device="cuda") -> torch.Tensor:
-    """Lane indices of a Philox-keyed permutation of the n_env environments (int32 [n_env * group])."""
+                device="cuda", n_epochs: Optional[int] = None) -> torch.Tensor:
+    """Lane indices of a Philox-keyed permutation of the n_env environments: int32 [n_env * group], or
+    [n_epochs, n_env * group] for epochs epoch .. epoch + n_epochs - 1 in one launch."""
+    rows = 1 if n_epochs is None else int(n_epochs)
     if out is None:
-        out = torch.empty(n_env * group, dtype=torch.int32, device=device)
+        shape = (n_env * group,) if n_epochs is None else (rows, n_env * group)
+        out = torch.empty(shape, dtype=torch.int32, device=device)
     _check(out, torch.int32, "out")
-    if out.numel() < n_env * group:
-        raise ValueError(f"out has {out.numel()} entries, need {n_env * group}")
-    _lib.call("srl_philox_perm", int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, int(n_env), int(group),
+    if out.numel() < rows * n_env * group:
+        raise ValueError(f"out has {out.numel()} entries, need {rows * n_env * group}")
+    _lib.call("srl_philox_perm", int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, rows, int(n_env), int(group),
               _ptr(out), _stream())
     return out
 

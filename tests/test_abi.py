@@ -51,7 +51,7 @@ def test_abi_version_and_error_text(lib):
                           None, None)
     assert rc == 1
     assert b"L >= 2" in lib.srl_last_error()
-    rc = lib.srl_philox_perm(0, 0, -1, 1, None, None)
+    rc = lib.srl_philox_perm(0, 0, 1, -1, 1, None, None)
     assert rc == 1 and b"n_env" in lib.srl_last_error()
     with pytest.raises(_lib.SrlCudaError, match="srl_batch_gather"):
         _lib.call("srl_batch_gather", None, 99, None, 1, 1, None)

@@ -517,3 +517,52 @@ def test_full_size_cfg2_roundtrip_properties(ops):
     assert not g_lp[masked].any() and not g_v[masked].any() and not g_en[masked].any()
     assert abs(g_en.double().sum().item() + hp.entropy_bonus_weight) < 1e-6
     assert out[9].item() == whole[0, 0].item()
+
+
+def test_deferred_finalize_equals_immediate(ops):
+    """out == NULL stops after gradients + partial rows; srl_ppo_loss_finalize folds many slots in one launch and
+    must give exactly what the in-kernel (ticket) finalisation gives."""
+    d = load_golden("loss_smac.npz")
+    hp, _ = _hyper(ops, "smac")
+    L = d["on_reset"].shape[0]
+    T = L - 1
+    rs = flat2(d["on_reset"])
+    mask = 1.0 - rs[1:L].astype(np.float64)
+    x = flat2(d["adv"])[:T].astype(np.float64) * mask
+    ns = dev(np.array([mask.sum(), x.sum(), np.square(x).sum(), 0, 0, 0, 0, 0]))
+    pm = dev(d["popart_mean_std_after"])
+    args = [dev(flat2(d[k])) for k in ("new_logp", "v_pred", "entropy")]
+    smp = [dev(flat2(d["old_logp"]))[:T], dev(flat2(d["value"]))[:T], dev(flat2(d["ret"]))[:T], dev(flat2(d["adv"]))[:T],
+           dev(rs)[1:L]]
+    g1 = ops.ppo_loss_fwd_bwd(*args, *smp, ns, hp, popart_mean_std=pm)
+    ws = ops.new_loss_workspace("cuda", slots=3)
+    outs = []
+    for k in range(3):
+        outs.append(ops.ppo_loss_fwd_bwd(*args, *smp, ns, hp, popart_mean_std=pm, workspace=ws[k], defer=True))
+        assert outs[-1][3] is None
+    out = torch.zeros((3, 16), dtype=torch.float64, device="cuda")
+    out32 = torch.zeros((3, 4), dtype=torch.float32, device="cuda")
+    ops.loss_finalize(ws, out, out32)
+    torch.cuda.synchronize()
+    for k in range(3):
+        assert torch.equal(out[k], g1[3]) and torch.equal(out32[k], g1[4])
+        for q in range(3):
+            assert torch.equal(outs[k][q], g1[q])
+
+
+def test_group_stats_whole_first_and_multi_epoch_perm(ops):
+    rng = np.random.default_rng(5)
+    N, E, Mb = 96, 3, 4
+    part = rng.standard_normal((8, N))
+    part[7] = 0
+    perm = ops.philox_perm(42, 0, N // 3, 3, n_epochs=E)  # 32 envs x 3 agents
+    assert perm.shape == (E, N)
+    for e in range(E):
+        env = M.philox_perm_ref(42, e, N // 3).astype(np.int64)
+        assert np.array_equal(perm[e].cpu().numpy(), (env[:, None] * 3 + np.arange(3)[None]).reshape(-1))
+    table = ops.group_stats(dev(part), idx=perm.view(-1), groups=E * Mb, per=N // Mb, whole_first=True).cpu().numpy()
+    assert table.shape == (1 + E * Mb, 8)
+    np.testing.assert_allclose(table[0], part.sum(1), rtol=1e-12, atol=1e-12)
+    p = perm.cpu().numpy().reshape(E * Mb, N // Mb)
+    for g in range(E * Mb):
+        np.testing.assert_allclose(table[1 + g], part[:, p[g]].sum(1), rtol=1e-12, atol=1e-12)
