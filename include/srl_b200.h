@@ -78,6 +78,13 @@ int srl_gae_scan(const float* reward,          /* [L, N]; row L-1 is ignored    
                  double* lane_part, /* [SRL_LANE_PART, N] out or NULL */
                  srl_stream_t stream);
 
+/* The same [SRL_LANE_PART][N] table from adv / ret that already exist: a sample re-served by the buffer carries
+ * them in its host copy and MultiAgentPPO.step skips GAE for it (mappo.py:224-225,249 with
+ * recompute_adv_on_reuse=False; base/buffer.py:142-162 re-serves a ReplayEntry `reuses` times). */
+int srl_lane_stats(const float* adv, const float* ret, const uint8_t* done, const uint8_t* truncated,
+                   const uint8_t* on_reset, int L, int N, int row_lo, int row_hi, double* lane_part,
+                   srl_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Group statistics: out[g][k] = sum over the lanes of group g of lane_part[k][lane].
  * Group g holds the `per` lanes idx[g*per .. (g+1)*per) (idx == NULL: identity).  One group per

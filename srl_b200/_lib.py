@@ -68,6 +68,7 @@ SIGNATURES = {
     "srl_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "srl_gae_scan": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double] +
                      [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "srl_lane_stats": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "srl_group_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "srl_popart_update": (c_int, [c_void_p, c_void_p, c_double, c_double, c_void_p, c_void_p]),
     "srl_ppo_loss_workspace_bytes": (c_size_t, [c_int, c_int]),

@@ -62,6 +62,41 @@ __global__ void __cluster_dims__(kClusterX, 1, 1) __launch_bounds__(kThreads)
   cluster.sync();  // keep every CTA's shared memory alive until rank 0 has read it
 }
 
+// Per-lane partial sums from adv / ret that already exist (a re-served sample whose host copy carries them,
+// mappo.py:224-225 with recompute_adv_on_reuse=False): the same eight rows K2 writes, one thread per lane,
+// rows walked newest-first exactly like the scan so both producers sum in the same order.
+__global__ void __launch_bounds__(256) lane_stats_kernel(const float* __restrict__ adv, const float* __restrict__ ret,
+                                                         const uint8_t* __restrict__ done,
+                                                         const uint8_t* __restrict__ truncated,
+                                                         const uint8_t* __restrict__ on_reset, int N, int row_lo,
+                                                         int row_hi, double* __restrict__ lane_part) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= N) return;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0;
+  for (int t = row_hi - 1; t >= row_lo; --t) {
+    const size_t g = static_cast<size_t>(t) * N + col;
+    const double mk = on_reset[g + N] ? 0.0 : 1.0;  // 1 - on_reset[t+1]   mappo.py:260-261
+    const double x = __dmul_rn(static_cast<double>(adv[g]), mk);
+    const double y = __dmul_rn(static_cast<double>(ret[g]), mk);
+    s0 += mk;
+    s1 += x;
+    s2 = __dadd_rn(s2, __dmul_rn(x, x));
+    s3 += y;
+    s4 = __dadd_rn(s4, __dmul_rn(y, y));
+    s5 += done[g] ? 1.0 : 0.0;
+    s6 += truncated[g] ? 1.0 : 0.0;
+  }
+  double* o = lane_part + col;
+  o[0] = s0;
+  o[static_cast<size_t>(1) * N] = s1;
+  o[static_cast<size_t>(2) * N] = s2;
+  o[static_cast<size_t>(3) * N] = s3;
+  o[static_cast<size_t>(4) * N] = s4;
+  o[static_cast<size_t>(5) * N] = s5;
+  o[static_cast<size_t>(6) * N] = s6;
+  o[static_cast<size_t>(7) * N] = 0.0;
+}
+
 __global__ void popart_update_kernel(const double* __restrict__ bs, double* __restrict__ state, double beta,
                                      double eps, double* __restrict__ ms) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -112,6 +147,20 @@ extern "C" int srl_popart_update(const double* batch_stats, double* state, doubl
   using namespace srl;
   SRL_REQUIRE(batch_stats && state && mean_std_out, SRL_ERR_INVALID_ARG, "srl_popart_update: null pointer");
   popart_update_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(batch_stats, state, beta, eps, mean_std_out);
+  SRL_CUDA(cudaGetLastError());
+  return SRL_OK;
+}
+
+extern "C" int srl_lane_stats(const float* adv, const float* ret, const uint8_t* done, const uint8_t* truncated,
+                              const uint8_t* on_reset, int L, int N, int row_lo, int row_hi, double* lane_part,
+                              srl_stream_t stream) {
+  using namespace srl;
+  SRL_REQUIRE(adv && ret && done && truncated && on_reset && lane_part, SRL_ERR_INVALID_ARG, "srl_lane_stats: null pointer");
+  SRL_REQUIRE(L >= 2 && N >= 1 && row_lo >= 0 && row_lo <= row_hi && row_hi <= L - 1, SRL_ERR_INVALID_ARG,
+              "srl_lane_stats: need L >= 2, N >= 1 and 0 <= row_lo <= row_hi <= L-1 (got L=%d N=%d rows [%d, %d))", L, N,
+              row_lo, row_hi);
+  lane_stats_kernel<<<(N + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(adv, ret, done, truncated, on_reset,
+                                                                                      N, row_lo, row_hi, lane_part);
   SRL_CUDA(cudaGetLastError());
   return SRL_OK;
 }

@@ -31,6 +31,17 @@ SAMPLE_F32 = ("reward", "value", "old_logp")
 SAMPLE_U8 = ("done", "truncated", "on_reset")
 
 
+def exchange_stats(local: torch.Tensor, out: torch.Tensor, group=None) -> torch.Tensor:
+    """The one data-path collective of the step: SUM all-reduce of the float64 statistics table
+    [1 + E*M, 8] (row 0 = batch, row 1 + e*M + j = minibatch (e, j)).  It replaces the 3 one-element all-reduces
+    per loss call of masked_normalization (utils.py:58-61) and the 3 per PopArt update (utils.py:121-124);
+    the masked means of the loss stay rank-local, as in the reference.  Works on any backend
+    (nccl on the GPUs, gloo in the CPU tests)."""
+    out.copy_(local)
+    torch.distributed.all_reduce(out, op=torch.distributed.ReduceOp.SUM, group=group)
+    return out
+
+
 class HotPath:
 
     def __init__(self, L: int, B: int, A: int = 1, *, gamma: float, lmbda: float, hyper: ops.LossHyper,
@@ -126,13 +137,21 @@ class HotPath:
         return moved
 
     # ------------------------------------------------------------------------------------------
-    def advantages(self) -> None:
-        """K2, then all epochs' permutations in one launch, then the whole statistics table in one launch
-        (+ the one small all-reduce when distributed)."""
+    def advantages(self, cached: bool = False, vtrace_new_logp: Optional[torch.Tensor] = None) -> None:
+        """K2 (or, for cached adv/ret already in self.adv / self.ret, only their per-lane sums), then all epochs'
+        permutations in one launch, then the whole statistics table in one launch (+ the one small all-reduce
+        when distributed)."""
         lf = self.leaf
-        ops.gae_scan(lf["reward"], lf["value"], lf["done"], lf["truncated"], lf["on_reset"], self.gamma, self.lmbda,
-                     row_lo=self.row_lo, row_hi=self.row_hi, popart_mean_std=self.popart_mean_std(), adv=self.adv,
-                     ret=self.ret, lane_part=self.lane_part)
+        if cached:
+            ops.lane_stats(self.adv, self.ret, lf["done"], lf["truncated"], lf["on_reset"], self.row_lo, self.row_hi,
+                           lane_part=self.lane_part)
+        else:
+            kw = {}
+            if vtrace_new_logp is not None:  # V-trace: rho_t from the current policy (mappo.py:129-132)
+                kw = dict(vtrace_new_logp=vtrace_new_logp, vtrace_old_logp=lf["old_logp"])
+            ops.gae_scan(lf["reward"], lf["value"], lf["done"], lf["truncated"], lf["on_reset"], self.gamma, self.lmbda,
+                         row_lo=self.row_lo, row_hi=self.row_hi, popart_mean_std=self.popart_mean_std(), adv=self.adv,
+                         ret=self.ret, lane_part=self.lane_part, **kw)
         if self.minibatches > 1:
             ops.philox_perm(self.seed + self.step_count, 0, self.B, self.A, out=self.perm, n_epochs=self.epochs)
             ops.group_stats(self.lane_part, idx=self.perm.view(-1), groups=self.epochs * self.minibatches, per=self.n_mb,
@@ -140,8 +159,7 @@ class HotPath:
         else:
             ops.group_stats(self.lane_part, groups=1, per=self.N, out=self.local_stats[0:1])
         if self.pg is not None:
-            self.global_stats.copy_(self.local_stats)
-            torch.distributed.all_reduce(self.global_stats, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            exchange_stats(self.local_stats, self.global_stats, self.pg)
 
     def stats_row(self, e: int, j: int) -> int:
         return 0 if self.minibatches == 1 else 1 + e * self.minibatches + j
@@ -224,8 +242,7 @@ class HotPath:
             self._graph.replay()
         else:
             self._graph_a.replay()
-            self.global_stats.copy_(self.local_stats)
-            torch.distributed.all_reduce(self.global_stats, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            exchange_stats(self.local_stats, self.global_stats, self.pg)
             self._graph.replay()
         self.step_count += 1
 

@@ -90,6 +90,24 @@ def gae_scan(reward, value, done, truncated, on_reset, gamma: float, lmbda: floa
     return adv, ret, lane_part
 
 
+def lane_stats(adv, ret, done, truncated, on_reset, row_lo: int, row_hi: int,
+               lane_part: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-lane partial sums [8, N] from existing adv / ret (cached advantages of a re-served sample)."""
+    L, N = _rows_lanes(adv)
+    for name, t in (("adv", adv), ("ret", ret)):
+        _check(t, torch.float32, name)
+    for name, t in (("done", done), ("truncated", truncated), ("on_reset", on_reset)):
+        _check(t, torch.uint8, name)
+        if _rows_lanes(t) != (L, N):
+            raise ValueError(f"{name}: shape {tuple(t.shape)} does not match adv {tuple(adv.shape)}")
+    if lane_part is None:
+        lane_part = torch.empty((SRL_LANE_PART, N), dtype=torch.float64, device=adv.device)
+    _check(lane_part, torch.float64, "lane_part")
+    _lib.call("srl_lane_stats", _ptr(adv), _ptr(ret), _ptr(done), _ptr(truncated), _ptr(on_reset), L, N, int(row_lo),
+              int(row_hi), _ptr(lane_part), _stream())
+    return lane_part
+
+
 def group_stats(lane_part: torch.Tensor, idx: Optional[torch.Tensor] = None, groups: int = 1,
                 per: Optional[int] = None, out: Optional[torch.Tensor] = None, whole_first: bool = False) -> torch.Tensor:
     """out[g, k] = sum of lane_part[k, lane] over the lanes of group g (fixed summation order).
