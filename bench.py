@@ -191,27 +191,22 @@ def run_ours(args, cfg, rank, world, local_rank):
     E, Mb, T, N = cfg.epochs, cfg.minibatches, cfg.T, cfg.N
     hp = HotPath(cfg.L, cfg.B, cfg.A, gamma=cfg.gamma, lmbda=cfg.lmbda, hyper=ops.LossHyper(**hyper_kwargs(cfg)),
                  bootstrap_steps=cfg.bootstrap_steps, burn_in_steps=cfg.burn_in_steps, epochs=E, minibatches=Mb, seed=0,
-                 popart=cfg.popart, device=dev, process_group=pg, fuse_gather=not args.explicit_gather)
+                 popart=cfg.popart, device=dev, process_group=pg, fuse_gather=not args.explicit_gather,
+                 graph_branches=args.branches, shuffle_block=args.shuffle_block)
     n = hp.n_mb
     pinned = {k: torch.from_numpy(np.ascontiguousarray(v.reshape(cfg.L, N))).pin_memory() for k, v in s.items()}
     hp.load_sample(pinned)
     # policy outputs as the policy would emit them: one contiguous [T, n] block per (epoch, minibatch)
-    perm = [ops.philox_perm(0, e, cfg.B, cfg.A).long() if Mb > 1 else None for e in range(E)]
-    pol_dev, pol_host = [], []
+    blk = args.shuffle_block
+    perm = [ops.philox_perm(0, e, cfg.B // blk, cfg.A * blk).long() if Mb > 1 else None for e in range(E)]
+    pol_all = torch.empty((E, Mb, 3, T, n), dtype=torch.float32, device=dev)
     for e in range(E):
-        row_d, row_h = [], []
-        for j in range(Mb):
-            trip_d, trip_h = [], []
-            for k in ("new_logp", "v_pred", "entropy"):
-                full = torch.from_numpy(pol[k][e].reshape(T, N)).to(dev)
-                blk = full if Mb == 1 else full.index_select(1, perm[e][j * n:(j + 1) * n])
-                blk = blk.contiguous()
-                trip_d.append(blk)
-                trip_h.append(blk.cpu().pin_memory())
-            row_d.append(tuple(trip_d))
-            row_h.append(tuple(trip_h))
-        pol_dev.append(row_d)
-        pol_host.append(row_h)
+        for q, k in enumerate(("new_logp", "v_pred", "entropy")):
+            full = torch.from_numpy(pol[k][e].reshape(T, N)).to(dev)
+            for j in range(Mb):
+                pol_all[e, j, q] = full if Mb == 1 else full.index_select(1, perm[e][j * n:(j + 1) * n])
+    pol_dev = [[tuple(pol_all[e, j, q] for q in range(3)) for j in range(Mb)] for e in range(E)]
+    pol_host = pol_all.cpu().pin_memory()
     out_host = dict(adv=torch.empty((cfg.L, N), dtype=torch.float32).pin_memory(),
                     ret=torch.empty((cfg.L, N), dtype=torch.float32).pin_memory(),
                     grads=torch.empty((E, Mb, 3, T, n), dtype=torch.float32).pin_memory(),
@@ -336,7 +331,9 @@ def run_ours(args, cfg, rank, world, local_rank):
                            f"{step_bytes / 1e6:.0f} MB algorithmic)",
                         timing="CUDA events per step on the launch stream, sum over steps, max over ranks",
                         launch="one CUDA graph per step" if world == 1 else "two CUDA graphs per step around one NCCL all-reduce of the float64 stats table",
-                        minibatch_gather="fused into the loss loads (lane_idx)" if hp.fuse_gather else "explicit K5 gather"),
+                        minibatch_gather=("fused into the loss loads (lane_idx)" if hp.fuse_gather else "explicit K5 gather") +
+                        f", Philox permutation of {hp.shuffle_block}-environment blocks",
+                        graph_branches=hp.graph_branches),
             clocks=clocks,
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=nbytes["h2d_bytes"],
                      d2h_bytes_per_step=nbytes["d2h_bytes"], ms_per_step=e2e_t.item() / e2e_steps * 1e3, steps=e2e_steps,
@@ -365,6 +362,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shuffle-block", type=int, default=1,
+                    help="environments per shuffled block (1 = per-environment permutation; 8 = one 32-byte sector)")
+    ap.add_argument("--branches", type=int, default=16, help="parallel CUDA-graph branches for the per-minibatch launches")
     ap.add_argument("--explicit-gather", action="store_true", help="separate K5 gather launch instead of gather-on-load")
     args = ap.parse_args()
     cfg = synth.CONFIGS[args.config]

@@ -55,6 +55,7 @@ struct LossParams {
   long long ld_smp;
   const int32_t* lane_idx;
   int T, n;
+  int smp_vec_ok;  // sample-side leaves allow 128-bit loads at 4-aligned lanes (alignment + row stride)
   const double* norm_stats;
   const double* local_stats;
   const double* popart;
@@ -311,22 +312,45 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const LossParams p) {
   Acc acc;
   const int n = p.n, T = p.T;
   if (VEC4) {
+    // four consecutive lanes per thread: 128-bit loads/stores on the dense policy side; the sample side is either
+    // dense too (128-bit) or gathered through lane_idx (four independent 32-bit gathers per leaf, all in flight)
     const int n4 = n >> 2;
     const long long W = static_cast<long long>(T) * n4;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < W;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
       const int t = static_cast<int>(i / n4);
       const int j = static_cast<int>(i - static_cast<long long>(t) * n4) << 2;
-      const long long op = t * p.ld_pol + j, os = t * p.ld_smp + j, og = t * p.ld_grad + j;
+      const long long op = t * p.ld_pol + j, og = t * p.ld_grad + j;
+      int4 c = make_int4(j, j + 1, j + 2, j + 3);
+      if (p.lane_idx) c = __ldg(reinterpret_cast<const int4*>(p.lane_idx + j));
       const float4 nl = ldg_stream(reinterpret_cast<const float4*>(p.new_logp + op));
       const float4 vp = ldg_stream(reinterpret_cast<const float4*>(p.v_pred + op));
       const float4 en = ldg_stream(reinterpret_cast<const float4*>(p.entropy + op));
-      const float4 ol = ldg_stream(reinterpret_cast<const float4*>(p.old_logp + os));
-      const float4 rt = ldg_stream(reinterpret_cast<const float4*>(p.ret + os));
-      const float4 ad = ldg_stream(reinterpret_cast<const float4*>(p.adv + os));
-      float4 ov = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (h.clip_value) ov = ldg_stream(reinterpret_cast<const float4*>(p.old_value + os));
-      const uint32_t rs = ldg_stream(reinterpret_cast<const uint32_t*>(p.reset_next + os));
+      float4 ol, rt, ad, ov = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint32_t rs;
+      const long long ob = t * p.ld_smp;
+      // a run of four consecutive, 4-aligned lanes (dense batches, or permutations of >= 4-lane blocks: agents of
+      // one environment, sector-aligned environment blocks) is fetched with one 128-bit load per leaf
+      const bool run4 = (c.y == c.x + 1) && (c.z == c.x + 2) && (c.w == c.x + 3) && ((c.x & 3) == 0) && p.smp_vec_ok;
+      if (run4) {
+        const long long os = ob + c.x;
+        ol = ldg_stream(reinterpret_cast<const float4*>(p.old_logp + os));
+        rt = ldg_stream(reinterpret_cast<const float4*>(p.ret + os));
+        ad = ldg_stream(reinterpret_cast<const float4*>(p.adv + os));
+        if (h.clip_value) ov = ldg_stream(reinterpret_cast<const float4*>(p.old_value + os));
+        rs = ldg_stream(reinterpret_cast<const uint32_t*>(p.reset_next + os));
+      } else {
+        ol = make_float4(__ldg(p.old_logp + ob + c.x), __ldg(p.old_logp + ob + c.y), __ldg(p.old_logp + ob + c.z),
+                         __ldg(p.old_logp + ob + c.w));
+        rt = make_float4(__ldg(p.ret + ob + c.x), __ldg(p.ret + ob + c.y), __ldg(p.ret + ob + c.z), __ldg(p.ret + ob + c.w));
+        ad = make_float4(__ldg(p.adv + ob + c.x), __ldg(p.adv + ob + c.y), __ldg(p.adv + ob + c.z), __ldg(p.adv + ob + c.w));
+        if (h.clip_value)
+          ov = make_float4(__ldg(p.old_value + ob + c.x), __ldg(p.old_value + ob + c.y), __ldg(p.old_value + ob + c.z),
+                           __ldg(p.old_value + ob + c.w));
+        rs = static_cast<uint32_t>(__ldg(p.reset_next + ob + c.x)) | (static_cast<uint32_t>(__ldg(p.reset_next + ob + c.y)) << 8) |
+             (static_cast<uint32_t>(__ldg(p.reset_next + ob + c.z)) << 16) |
+             (static_cast<uint32_t>(__ldg(p.reset_next + ob + c.w)) << 24);
+      }
       if (!have_u) {
         u = make_uniforms(raw, h.adv_eps);
         have_u = true;
@@ -572,15 +596,19 @@ extern "C" int srl_ppo_loss_fwd_bwd(const float* new_logp, const float* v_pred, 
   p.slot = reinterpret_cast<SlotHeader*>(workspace);
   p.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + kPartialsOffset);
 
-  const bool vec4 = lane_idx == nullptr && (n % 4 == 0) && (ld_pol % 4 == 0) && (ld_smp % 4 == 0) &&
-                    (ld_grad % 4 == 0) && aligned(new_logp, 16) && aligned(v_pred, 16) && aligned(entropy, 16) &&
-                    aligned(old_logp, 16) && aligned(ret, 16) && aligned(adv, 16) &&
-                    (!p.h.clip_value || aligned(old_value, 16)) && aligned(on_reset_next, 4) && aligned(g_logp, 16) &&
-                    aligned(g_value, 16) && aligned(g_entropy, 16);
+  // four lanes per thread whenever the dense side allows 128-bit accesses; the sample side may be gathered
+  const bool dense_ok = (n % 4 == 0) && (ld_pol % 4 == 0) && (ld_grad % 4 == 0) && aligned(new_logp, 16) &&
+                        aligned(v_pred, 16) && aligned(entropy, 16) && aligned(g_logp, 16) && aligned(g_value, 16) &&
+                        aligned(g_entropy, 16);
+  const bool smp_vec = (ld_smp % 4 == 0) && aligned(old_logp, 16) && aligned(ret, 16) && aligned(adv, 16) &&
+                       (!p.h.clip_value || aligned(old_value, 16)) && aligned(on_reset_next, 4);
+  p.smp_vec_ok = smp_vec ? 1 : 0;
+  const bool use_vec4 = dense_ok && (lane_idx == nullptr || aligned(lane_idx, 16));
   const int sms = sm_count();
-  // small problems are latency-bound: one element per thread keeps the per-thread dependency chain short
-  const bool use_vec4 = vec4 && static_cast<long long>(T) * n >= static_cast<long long>(sms) * 256 * 8;
   const long long W = static_cast<long long>(T) * (use_vec4 ? n / 4 : n);
+  // The kernel is latency-bound at minibatch sizes (profiles/r1_notes.md): what matters is how many elements
+  // are in flight per SM, so threads carry four elements and CTAs stay small enough for several launches to
+  // share the machine when the caller runs them on parallel streams / graph branches.
   const int threads = (W <= static_cast<long long>(sms) * 256) ? 128 : 256;
   long long grid = (W + threads - 1) / threads;
   const long long cap = static_cast<long long>(sms) * 8 < kMaxGrid ? static_cast<long long>(sms) * 8 : kMaxGrid;
@@ -651,6 +679,7 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
   p.local_stats = local_stats;
   p.popart = popart_mean_std;
   p.g_logp = p.g_entropy = nullptr;
+  p.smp_vec_ok = 0;
   p.g_value = g_value;
   p.ld_grad = n;
   p.out = out;

@@ -48,15 +48,20 @@ class HotPath:
                  bootstrap_steps: int = 1, burn_in_steps: int = 0, epochs: int = 1, minibatches: int = 1, seed: int = 0,
                  popart: bool = False, popart_beta: float = 0.99999, popart_eps: float = 1e-5,
                  device: Optional[torch.device] = None, process_group=None, fuse_gather: bool = True,
-                 graph_branches: int = 8):
+                 graph_branches: int = 16, shuffle_block: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("srl_b200.HotPath needs a CUDA device (there is no CPU path)")
         if bootstrap_steps < 1:
             # mappo.py:259-261 slices on_reset[1 + burn_in : 1 + L - bootstrap]; with bootstrap_steps == 0 the
             # reference's mask is one row short of the data and the loss raises.  Same restriction here.
             raise ValueError("bootstrap_steps must be >= 1")
-        if B % minibatches != 0:
-            raise ValueError(f"B={B} environments do not split into {minibatches} equal minibatches")
+        # Minibatches are drawn by permuting blocks of `shuffle_block` consecutive environments (1 = every
+        # environment on its own, the textbook shuffle).  Blocks of 8 single-agent environments are exactly one
+        # 32-byte sector of every float32 leaf, which turns the gather-on-load into full-sector 128-bit loads.
+        if shuffle_block < 1 or B % shuffle_block != 0 or (B // shuffle_block) % minibatches != 0:
+            raise ValueError(f"B={B} environments do not split into {minibatches} equal minibatches of "
+                             f"{shuffle_block}-environment blocks")
+        self.shuffle_block = int(shuffle_block)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.L, self.B, self.A, self.N = L, B, A, B * A
         self.gamma, self.lmbda, self.hyper = float(gamma), float(lmbda), hyper
@@ -86,7 +91,10 @@ class HotPath:
         self.popart_state = torch.zeros(4, dtype=torch.float64, device=dev)
         self.popart_ms = torch.tensor([0.0, 0.1, 0.0, 0.1], dtype=torch.float64, device=dev)  # sqrt(1e-2) floor
         n = self.n_mb
-        self.grads = [[tuple(f32(self.T, n) for _ in range(3)) for _ in range(minibatches)] for _ in range(epochs)]
+        # gradients of every (epoch, minibatch) in one allocation so the host-facing call moves them with one copy
+        self.grads_all = f32(epochs, minibatches, 3, self.T, n)
+        self.grads = [[tuple(self.grads_all[e, j, q] for q in range(3)) for j in range(minibatches)]
+                      for e in range(epochs)]
         self.out = torch.zeros((epochs * minibatches, SRL_LOSS_OUT_LEN), dtype=torch.float64, device=dev)
         self.out_f32 = torch.zeros((epochs * minibatches, 4), dtype=torch.float32, device=dev)
         self.workspace = ops.new_loss_workspace(dev, slots=epochs * minibatches)  # one slot per (epoch, minibatch)
@@ -153,13 +161,18 @@ class HotPath:
                          row_lo=self.row_lo, row_hi=self.row_hi, popart_mean_std=self.popart_mean_std(), adv=self.adv,
                          ret=self.ret, lane_part=self.lane_part, **kw)
         if self.minibatches > 1:
-            ops.philox_perm(self.seed + self.step_count, 0, self.B, self.A, out=self.perm, n_epochs=self.epochs)
+            self.permute()
             ops.group_stats(self.lane_part, idx=self.perm.view(-1), groups=self.epochs * self.minibatches, per=self.n_mb,
                             out=self.local_stats, whole_first=True)
         else:
             ops.group_stats(self.lane_part, groups=1, per=self.N, out=self.local_stats[0:1])
         if self.pg is not None:
             exchange_stats(self.local_stats, self.global_stats, self.pg)
+
+    def permute(self) -> None:
+        """K5a: the environment(-block) permutations of every epoch of this step, one launch."""
+        blk = self.shuffle_block
+        ops.philox_perm(self.seed + self.step_count, 0, self.B // blk, self.A * blk, out=self.perm, n_epochs=self.epochs)
 
     def stats_row(self, e: int, j: int) -> int:
         return 0 if self.minibatches == 1 else 1 + e * self.minibatches + j
@@ -210,18 +223,30 @@ class HotPath:
         main = torch.cuda.current_stream()
         if branches > 1 and not hasattr(self, "_side"):
             self._side = [torch.cuda.Stream(device=self.device) for _ in range(branches)]
-        for e in range(self.epochs):
-            if self.popart:
-                self.update_popart()
-            if branches <= 1:
+        if branches <= 1:
+            for e in range(self.epochs):
+                if self.popart:
+                    self.update_popart()
                 for j in range(self.minibatches):
                     self.loss(e, j, *pol[e][j])
-                continue
+        elif self.popart:  # fork / join around every epoch: K3 re-normalises between epochs
             used = self._side[:min(branches, self.minibatches)]
+            for e in range(self.epochs):
+                self.update_popart()
+                for st in used:
+                    st.wait_stream(main)
+                for j in range(self.minibatches):
+                    with torch.cuda.stream(used[j % len(used)]):
+                        self.loss(e, j, *pol[e][j])
+                for st in used:
+                    main.wait_stream(st)
+        else:  # all E*M launches are independent: fork once, join once
+            used = self._side[:min(branches, self.epochs * self.minibatches)]
             for st in used:
                 st.wait_stream(main)
-            for j in range(self.minibatches):
-                with torch.cuda.stream(used[j % len(used)]):
+            for k in range(self.epochs * self.minibatches):
+                e, j = divmod(k, self.minibatches)
+                with torch.cuda.stream(used[k % len(used)]):
                     self.loss(e, j, *pol[e][j])
             for st in used:
                 main.wait_stream(st)
@@ -293,33 +318,120 @@ class HotPath:
         return n
 
     # ------------------------------------------------------------------------------------------
-    def run_host(self, sample: Dict[str, np.ndarray], pol_host: List[List[tuple]], out_host: Dict[str, torch.Tensor],
+    def run_host(self, sample: Dict[str, np.ndarray], pol_host: torch.Tensor, out_host: Dict[str, torch.Tensor],
                  use_graph: bool = True) -> Dict[str, int]:
-        """Host buffers in, host buffers out: H2D of the sample scalars and of the policy outputs of every
-        minibatch, the device step, D2H of adv/ret (the reference mirrors them into the host sample,
-        mappo.py:254-257), of the three gradient tensors of every minibatch and of the stats table.
-        pol_host[e][j] = three pinned [T, n_mb] float32 tensors; out_host holds pinned destinations
-        'adv', 'ret' [L, N], 'grads' [E, M, 3, T, n_mb], 'out' [E*M, 16].  Returns byte counts."""
-        h2d = self.load_sample(sample)
-        if not hasattr(self, "_pol_dev"):
-            self._pol_dev = [[tuple(torch.empty((self.T, self.n_mb), dtype=torch.float32, device=self.device)
-                                    for _ in range(3)) for _ in range(self.minibatches)] for _ in range(self.epochs)]
-        for e in range(self.epochs):
-            for j in range(self.minibatches):
-                for d, h in zip(self._pol_dev[e][j], pol_host[e][j]):
-                    d.copy_(h, non_blocking=True)
-                    h2d += h.numel() * 4
-        self.run_device(self._pol_dev, use_graph=use_graph)
-        d2h = 0
-        out_host["adv"].copy_(self.adv, non_blocking=True)
-        out_host["ret"].copy_(self.ret, non_blocking=True)
-        d2h += 2 * self.adv.numel() * 4
-        for e in range(self.epochs):
-            for j in range(self.minibatches):
-                for q in range(3):
-                    out_host["grads"][e, j, q].copy_(self.grads[e][j][q], non_blocking=True)
-                    d2h += self.T * self.n_mb * 4
+        """Host buffers in, host buffers out -- the call a host-side user of the path makes.
+
+        sample: the six scalar leaves (pinned tensors are copied directly, numpy arrays are staged through pinned
+        memory); pol_host: pinned float32 [E, M, 3, T, n_mb] = (new_logp, v_pred, entropy) of every minibatch;
+        out_host: pinned destinations 'adv', 'ret' [L, N] (the reference mirrors them into the host sample,
+        mappo.py:254-257), 'grads' [E, M, 3, T, n_mb] and 'out' [E*M, 16].
+
+        Three streams: copy-in (sample, then one epoch of policy outputs at a time), compute (advantages, then one
+        CUDA graph per epoch as soon as its inputs have landed) and copy-out (adv/ret while epoch 0 computes, each
+        epoch's gradients while the next epoch computes), so H2D, kernels and D2H overlap on the full-duplex link.
+        Returns the bytes moved each way."""
+        E, Mb = self.epochs, self.minibatches
+        if not hasattr(self, "_pol_dev_all"):
+            self._pol_dev_all = torch.empty((E, Mb, 3, self.T, self.n_mb), dtype=torch.float32, device=self.device)
+            self._pol_dev = [[tuple(self._pol_dev_all[e, j, q] for q in range(3)) for j in range(Mb)] for e in range(E)]
+            self._s_in, self._s_out = torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)
+            self._host_graphs = None
+        main = torch.cuda.current_stream()
+        s_in, s_out = self._s_in, self._s_out
+        if use_graph and self._host_graphs is None:
+            self._capture_host()
+        s_in.wait_stream(main)
+        with torch.cuda.stream(s_in):
+            h2d = self.load_sample(sample)
+            ev_sample = torch.cuda.Event()
+            ev_sample.record(s_in)
+            ev_pol = []
+            for e in range(E):
+                self._pol_dev_all[e].copy_(pol_host[e], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+                ev_pol.append(ev)
+            h2d += pol_host.numel() * 4
+        main.wait_event(ev_sample)
+        pg, graphs = self.pg, self._host_graphs
+        if use_graph:
+            graphs["adv"].replay()
+            if pg is not None:
+                exchange_stats(self.local_stats, self.global_stats, pg)
+        else:
+            self.advantages()
+        ev_adv = torch.cuda.Event()
+        ev_adv.record(main)
+        s_out.wait_event(ev_adv)
+        with torch.cuda.stream(s_out):
+            out_host["adv"].copy_(self.adv, non_blocking=True)
+            out_host["ret"].copy_(self.ret, non_blocking=True)
+        for e in range(E):
+            main.wait_event(ev_pol[e])
+            if use_graph:
+                graphs["epoch"][e].replay()
+            else:
+                if self.popart:
+                    self.update_popart()
+                for j in range(Mb):
+                    self.loss(e, j, *self._pol_dev[e][j])
+            ev = torch.cuda.Event()
+            ev.record(main)
+            s_out.wait_event(ev)
+            with torch.cuda.stream(s_out):
+                out_host["grads"][e].copy_(self.grads_all[e], non_blocking=True)
+        self.finalize()
         out_host["out"].copy_(self.out, non_blocking=True)
-        d2h += self.out.numel() * 8
-        torch.cuda.current_stream().synchronize()
+        self.step_count += 1
+        main.wait_stream(s_out)
+        main.synchronize()
+        d2h = 2 * self.adv.numel() * 4 + self.grads_all.numel() * 4 + self.out.numel() * 8
         return dict(h2d_bytes=h2d, d2h_bytes=d2h)
+
+    def _capture_host(self) -> None:
+        """One CUDA graph for advantages() and one per epoch (its PopArt update + its minibatch launches on
+        parallel branches), so run_host can start an epoch the moment its policy outputs have landed."""
+        pg, self.pg = self.pg, None
+        saved = self.step_count
+        self.step_count = 0
+        try:
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):  # warm-up outside capture
+                self.advantages()
+                self._run_epoch(0, 1)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g_adv = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_adv):
+                self.advantages()
+            epochs = []
+            for e in range(self.epochs):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_epoch(e, self.graph_branches)
+                epochs.append(g)
+            self._host_graphs = dict(adv=g_adv, epoch=epochs)
+        finally:
+            self.pg = pg
+            self.step_count = saved
+
+    def _run_epoch(self, e: int, branches: int) -> None:
+        main = torch.cuda.current_stream()
+        if self.popart:
+            self.update_popart()
+        if branches <= 1:
+            for j in range(self.minibatches):
+                self.loss(e, j, *self._pol_dev[e][j])
+            return
+        if not hasattr(self, "_side") or len(self._side) < branches:
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(branches)]
+        used = self._side[:min(branches, self.minibatches)]
+        for st in used:
+            st.wait_stream(main)
+        for j in range(self.minibatches):
+            with torch.cuda.stream(used[j % len(used)]):
+                self.loss(e, j, *self._pol_dev[e][j])
+        for st in used:
+            main.wait_stream(st)

@@ -140,6 +140,7 @@ class MultiAgentPPOB200(PytorchTrainer):
         # ---- new capabilities (absent from the reference) ----------------------------------
         self.num_minibatches = int(kwargs.get("num_minibatches", 1))
         self.shuffle_seed = int(kwargs.get("shuffle_seed", 0))
+        self.shuffle_block = int(kwargs.get("shuffle_block", 1))  # environments per shuffled block
         self.prefetch = bool(kwargs.get("prefetch", True))  # one-call delay of api/trainer.py:219-228
         if self.vtrace and (self.num_minibatches > 1 or self.recompute_adv_among_epochs):
             raise ValueError("vtrace supports num_minibatches == 1 without recompute_adv_among_epochs")
@@ -165,7 +166,7 @@ class MultiAgentPPOB200(PytorchTrainer):
                          minibatches=self.num_minibatches, seed=self.shuffle_seed, popart=self.popart,
                          popart_beta=self._popart.beta if self._popart else 0.99999,
                          popart_eps=self._popart.eps if self._popart else 1e-5, device=torch.device(self.policy.device),
-                         process_group=pg)
+                         process_group=pg, shuffle_block=self.shuffle_block)
             self._hp = hp
         hp.hyper = self._hyper()  # entropy_bonus_weight decays over time (mappo.py:310-311)
         return hp
@@ -223,7 +224,7 @@ class MultiAgentPPOB200(PytorchTrainer):
                 idx = hp.minibatch_lanes(e, j) if have_adv else None
                 if self.num_minibatches > 1 and not have_adv:
                     # the first analyze of the step needs the permutation before the advantages exist
-                    ops.philox_perm(hp.seed + hp.step_count, 0, hp.B, hp.A, out=hp.perm, n_epochs=hp.epochs)
+                    hp.permute()
                     idx = hp.minibatch_lanes(e, j)
                 mb = tensor_sample if idx is None else self._gather_minibatch(tensor_sample, idx, hp)
                 # mappo.py:243-246

@@ -124,12 +124,13 @@ def test_host_entry_point_roundtrip():
     cfg = CASES["atari_mb"]
     hp, pol_dev, ref, pa = _setup(cfg, seed=6)
     n = cfg.N // cfg.minibatches
-    pol_host = [[tuple(t.cpu().pin_memory() for t in trip) for trip in row] for row in pol_dev]
+    pol_host = torch.stack([torch.stack([torch.stack(list(trip)) for trip in row]) for row in pol_dev]).cpu().pin_memory()
     out_host = dict(adv=torch.empty((cfg.L, cfg.N)).pin_memory(), ret=torch.empty((cfg.L, cfg.N)).pin_memory(),
                     grads=torch.empty((cfg.epochs, cfg.minibatches, 3, cfg.T, n)).pin_memory(),
                     out=torch.empty((cfg.epochs * cfg.minibatches, 16), dtype=torch.float64).pin_memory())
     s = synth.make_sample_scalars(cfg, 6)
     nbytes = hp.run_host(s, pol_host, out_host, use_graph=False)
+    ref_grads = out_host["grads"].clone()  # permutations of step 0, the ones pol_host was laid out for
     assert nbytes["h2d_bytes"] == cfg.L * cfg.N * 15 + cfg.epochs * cfg.T * cfg.N * 12
     assert nbytes["d2h_bytes"] == cfg.L * cfg.N * 8 + cfg.epochs * cfg.T * cfg.N * 12 + cfg.epochs * cfg.minibatches * 128
     assert np.array_equal(out_host["adv"].numpy(), ref["adv"].numpy()[..., 0])
@@ -141,3 +142,36 @@ def test_host_entry_point_roundtrip():
     s32 = {k: v.astype(np.float32) for k, v in s.items()}
     hp.run_host(s32, pol_host, out_host, use_graph=False)
     assert np.array_equal(out_host["adv"].numpy(), ref["adv"].numpy()[..., 0])
+    # the per-epoch-graph variant (arguments frozen at capture: the permutations of step 0) returns the same bytes
+    out_host["grads"].zero_()
+    hp.run_host(s, pol_host, out_host, use_graph=True)
+    hp.run_host(s, pol_host, out_host, use_graph=True)
+    assert torch.equal(out_host["grads"], ref_grads)
+    assert np.array_equal(out_host["adv"].numpy(), ref["adv"].numpy()[..., 0])
+
+
+def test_block_shuffle_matches_oracle():
+    """shuffle_block = 4: the permutation moves 4-environment blocks (16-byte runs of every float32 leaf), which the
+    loss kernel fetches with 128-bit loads; results must equal the oracle run on the same lane order."""
+    from srl_b200 import ops
+    from srl_b200.hotpath import HotPath
+    cfg = CASES["atari_mb"]
+    blk = 4
+    s = synth.make_sample_scalars(cfg, 8)
+    pol = synth.make_policy_outputs(cfg, s, 9)
+    hp = HotPath(cfg.L, cfg.B, cfg.A, gamma=cfg.gamma, lmbda=cfg.lmbda, hyper=ops.LossHyper(**_hp_kwargs(cfg)),
+                 epochs=cfg.epochs, minibatches=cfg.minibatches, seed=77, shuffle_block=blk)
+    hp.load_sample(s)
+    batch = {k: torch.from_numpy(v.reshape(cfg.L, cfg.N, 1)).float() for k, v in s.items()}
+    batch.update({k: torch.from_numpy(v.reshape(cfg.epochs, cfg.T, cfg.N, 1)) for k, v in pol.items()})
+    ref = M.hot_path_ref(batch, M.LossHyper(**_hp_kwargs(cfg)), cfg.gamma, cfg.lmbda, cfg.epochs, cfg.minibatches, seed=77,
+                         lanes_per_env=blk)
+    n = cfg.N // cfg.minibatches
+    pol_dev = []
+    for e in range(cfg.epochs):
+        env = M.philox_perm_ref(77, e, cfg.B // blk).astype(np.int64)
+        perm = (env[:, None] * blk + np.arange(blk)[None]).reshape(-1)
+        pol_dev.append([tuple(torch.from_numpy(np.ascontiguousarray(pol[k][e].reshape(cfg.T, cfg.N)[:, perm[j * n:(j + 1) * n]])).cuda()
+                              for k in ("new_logp", "v_pred", "entropy")) for j in range(cfg.minibatches)])
+    hp.run_device(pol_dev, use_graph=False)
+    _compare(hp, cfg, ref, None)

@@ -98,3 +98,17 @@ def test_popart_mirror_matches_oracle():
         ref.update(x, m)
     y = torch.randn(9, 1, generator=g)
     assert torch.equal(head.normalize(y), ref.normalize(y)) and torch.equal(head.denormalize(y), ref.denormalize(y))
+
+
+def test_plugin_registers_into_srl_registry_when_srl_is_importable():
+    """`import srl_b200.srl_plugin` inside an SRL checkout adds 'mappo_b200' next to 'mappo'."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference not present on this box")
+    R = ref_loader.load()
+    import importlib
+
+    import srl_b200.srl_plugin as plugin
+    importlib.reload(plugin)
+    assert plugin.REGISTERED_IN_SRL
+    assert {"mappo", "mappo_b200"} <= set(R.trainer.ALL_TRAINER_CLASSES)
