@@ -192,7 +192,8 @@ def run_ours(args, cfg, rank, world, local_rank):
     hp = HotPath(cfg.L, cfg.B, cfg.A, gamma=cfg.gamma, lmbda=cfg.lmbda, hyper=ops.LossHyper(**hyper_kwargs(cfg)),
                  bootstrap_steps=cfg.bootstrap_steps, burn_in_steps=cfg.burn_in_steps, epochs=E, minibatches=Mb, seed=0,
                  popart=cfg.popart, device=dev, process_group=pg, fuse_gather=not args.explicit_gather,
-                 graph_branches=args.branches, shuffle_block=args.shuffle_block)
+                 graph_branches=args.branches, shuffle_block=args.shuffle_block, use_pack=not args.no_pack,
+                 batch_losses=not args.no_batch)
     n = hp.n_mb
     pinned = {k: torch.from_numpy(np.ascontiguousarray(v.reshape(cfg.L, N))).pin_memory() for k, v in s.items()}
     hp.load_sample(pinned)
@@ -284,23 +285,27 @@ def run_ours(args, cfg, rank, world, local_rank):
         return g
 
     pg_saved, hp.pg = hp.pg, None
-    g_loss = graph_of(lambda: [hp.loss(e, j, *pol_dev[e][j]) for e in range(E) for j in range(Mb)])
+    # the loss launches exactly as the step issues them (one batched launch, one per epoch with PopArt, or one per
+    # minibatch with --no-batch); PopArt's tiny update kernels ride along in the per-epoch case
+    loss_launches = (E if cfg.popart else -(-(E * Mb) // 32)) if hp._immediate else E * Mb
+    g_loss = graph_of(lambda: hp._run_losses(pol_dev))
     lf = hp.leaf
+    pack_kw = dict(old_logp=lf["old_logp"], pack=hp.pack) if hp.pack is not None else {}
     g_gae = graph_of(lambda: ops.gae_scan(lf["reward"], lf["value"], lf["done"], lf["truncated"], lf["on_reset"], cfg.gamma,
                                           cfg.lmbda, row_lo=hp.row_lo, row_hi=hp.row_hi,
                                           popart_mean_std=hp.popart_mean_std(), adv=hp.adv, ret=hp.ret,
-                                          lane_part=hp.lane_part))
+                                          lane_part=hp.lane_part, **pack_kw))
     hp.pg = pg_saved
-    loss_ms = statistics.mean(timed_steps(k_reps, g_loss.replay)) / (E * Mb)
+    loss_ms = statistics.mean(timed_steps(k_reps, g_loss.replay)) / loss_launches
     gae_ms = statistics.mean(timed_steps(k_reps, g_gae.replay))
-    loss_ms_warm = statistics.mean(timed_steps(k_reps, g_loss.replay, flush_l2=False)) / (E * Mb)
+    loss_ms_warm = statistics.mean(timed_steps(k_reps, g_loss.replay, flush_l2=False)) / loss_launches
     gae_ms_warm = statistics.mean(timed_steps(k_reps, g_gae.replay, flush_l2=False))
-    loss_bytes = LOSS_BYTES[bool(cfg.clip_value)] * T * n
+    loss_bytes = LOSS_BYTES[bool(cfg.clip_value)] * T * n * (E * Mb // loss_launches)
     gae_bytes = GAE_BYTES * (cfg.L - 1) * N
     kern = {
-        "ppo_loss_kernel": dict(launches_per_step=E * Mb, ms_per_launch=loss_ms, bytes_per_launch=loss_bytes,
+        "ppo_loss_kernel": dict(launches_per_step=loss_launches, ms_per_launch=loss_ms, bytes_per_launch=loss_bytes,
                                 gbs=loss_bytes / loss_ms / 1e6, gbs_l2_warm=loss_bytes / loss_ms_warm / 1e6,
-                                step_share=loss_ms * E * Mb / ms_per_step),
+                                step_share=loss_ms * loss_launches / ms_per_step),
         "gae_scan_kernel": dict(launches_per_step=1, ms_per_launch=gae_ms, bytes_per_launch=gae_bytes,
                                 gbs=gae_bytes / gae_ms / 1e6, gbs_l2_warm=gae_bytes / gae_ms_warm / 1e6,
                                 step_share=gae_ms / ms_per_step),
@@ -331,6 +336,9 @@ def run_ours(args, cfg, rank, world, local_rank):
                            f"{step_bytes / 1e6:.0f} MB algorithmic)",
                         timing="CUDA events per step on the launch stream, sum over steps, max over ranks",
                         launch="one CUDA graph per step" if world == 1 else "two CUDA graphs per step around one NCCL all-reduce of the float64 stats table",
+                        loss_launch=("batched: %d launch(es) per step covering %d minibatches each" %
+                                     (loss_launches, E * Mb // loss_launches)) if hp._immediate else "one launch per minibatch",
+                        sample_side="K2 pack (float4 per transition)" if hp.pack is not None else "separate leaves",
                         minibatch_gather=("fused into the loss loads (lane_idx)" if hp.fuse_gather else "explicit K5 gather") +
                         f", Philox permutation of {hp.shuffle_block}-environment blocks",
                         graph_branches=hp.graph_branches),
@@ -366,6 +374,8 @@ def main():
                     help="environments per shuffled block (1 = per-environment permutation; 8 = one 32-byte sector)")
     ap.add_argument("--branches", type=int, default=16, help="parallel CUDA-graph branches for the per-minibatch launches")
     ap.add_argument("--explicit-gather", action="store_true", help="separate K5 gather launch instead of gather-on-load")
+    ap.add_argument("--no-pack", action="store_true", help="A/B: gather the five sample leaves instead of K2's pack")
+    ap.add_argument("--no-batch", action="store_true", help="A/B: one loss launch per minibatch (parallel graph branches)")
     args = ap.parse_args()
     cfg = synth.CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))

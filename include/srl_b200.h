@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SRL_B200_ABI_VERSION 1
+#define SRL_B200_ABI_VERSION 2
 
 typedef void* srl_stream_t; /* cudaStream_t */
 
@@ -57,6 +57,12 @@ int srl_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   A[t]   = d[t] + m[t] * A[t+1], A[L-1] = 0 ;  adv = float(A) ;  ret = adv + v'[t]   (fp32 add)
  *   adv[L-1] = ret[L-1] = 0 (padding row).
  *
+ * pack (optional, may be NULL; needs old_logp): [L, N, 4] float32, 16-byte aligned -- the sample side of the loss
+ * as ONE 16-byte item per transition, {old_logp[t], value[t] (as stored in the sample), ret[t],
+ * mask[t] ? adv[t] : NaN} with mask[t] = 1 - on_reset[t+1] (row L-1: NaN).  A minibatch that gathers lanes
+ * through a permutation (srl_ppo_loss_fwd_bwd_batched, `pack`) then issues one 128-bit load per transition
+ * instead of five narrow ones.
+ *
  * lane_part (optional, may be NULL): [SRL_LANE_PART][N] float64 per-lane sums over the loss rows
  * t in [row_lo, row_hi) with mask[t] = 1 - on_reset[t+1] (mappo.py:259-261):
  *   0: sum mask   1: sum adv*mask   2: sum (adv*mask)^2   3: sum ret*mask   4: sum (ret*mask)^2
@@ -72,10 +78,12 @@ int srl_gae_scan(const float* reward,          /* [L, N]; row L-1 is ignored    
                  const float* vtrace_new_logp, /* [L-1, N] or NULL (vtrace off)                 */
                  const float* vtrace_old_logp, /* [L-1, N] or NULL                              */
                  const double* popart_mean_std, /* device {mean, std} or NULL (popart off)      */
+                 const float* old_logp,        /* [L, N] or NULL (only read when pack != NULL)  */
                  int L, int N, int row_lo, int row_hi, double gamma, double lmbda, double rho, double c,
                  float* adv,        /* [L, N] out */
                  float* ret,        /* [L, N] out */
                  double* lane_part, /* [SRL_LANE_PART, N] out or NULL */
+                 float* pack,       /* [L, N, 4] out or NULL */
                  srl_stream_t stream);
 
 /* The same [SRL_LANE_PART][N] table from adv / ret that already exist: a sample re-served by the buffer carries
@@ -175,6 +183,34 @@ int srl_ppo_loss_fwd_bwd(
     double* out,      /* device [SRL_LOSS_OUT_LEN] out, or NULL = deferred (srl_ppo_loss_finalize) */
     float* out_f32,   /* device [4] out: loss, policy_loss, value_loss, entropy_loss, or NULL */
     void* workspace, size_t workspace_bytes, srl_stream_t stream);
+
+/* Several minibatches of ONE shape in one launch (a PPO step runs epochs x minibatches of them; launched one by
+ * one each is a ~3 MB kernel that cannot fill 148 SMs).  Every problem carries its own policy-side tensors,
+ * permutation slice, statistics rows, gradient tensors, outputs and workspace slot; the sample side is shared.
+ * The sample side is either the five leaves of srl_ppo_loss_fwd_bwd (pack == NULL) or K2's pack
+ * ([T, N, 4] float32, pointer already offset to the first loss row; the leaf pointers may then be NULL).
+ * Either every problem has a lane_idx or none has.  n_problems > SRL_MAX_LOSS_BATCH is split into several launches. */
+#define SRL_MAX_LOSS_BATCH 32
+typedef struct srl_loss_problem {
+  const float* new_logp;     /* [T, n], row stride ld_pol */
+  const float* v_pred;
+  const float* entropy;
+  const int32_t* lane_idx;   /* device int32[n] or NULL */
+  const double* norm_stats;  /* device [>=3] */
+  const double* local_stats; /* device [>=1] */
+  float* g_logp;             /* [T, n] out, row stride ld_grad */
+  float* g_value;
+  float* g_entropy;
+  double* out;               /* device [SRL_LOSS_OUT_LEN] or NULL = deferred */
+  float* out_f32;            /* device [4] or NULL */
+  void* workspace;           /* one slot of srl_ppo_loss_workspace_bytes() bytes, zero before first use */
+} srl_loss_problem;
+
+int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems_host, int n_problems, int64_t ld_pol,
+                                 int64_t ld_grad, const float* old_logp, const float* old_value, const float* ret,
+                                 const float* adv, const uint8_t* on_reset_next, int64_t ld_smp, const float* pack,
+                                 int T, int n, const double* popart_mean_std, const srl_ppo_hyper* hyper,
+                                 size_t workspace_bytes_per_slot, srl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4b  Same loss, but starting from the actor head's logits: also replaces

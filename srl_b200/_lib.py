@@ -19,7 +19,8 @@ SRL_LANE_PART = 8
 SRL_LOSS_OUT_LEN = 16
 SRL_MAX_LEAVES = 32
 SRL_MAX_HEADS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
+SRL_MAX_LOSS_BATCH = 32
 
 # enum srl_loss_out
 OUT_LOSS, OUT_POLICY_LOSS, OUT_VALUE_LOSS, OUT_ENTROPY_LOSS = 0, 1, 2, 3
@@ -56,6 +57,12 @@ class PpoHyper(ctypes.Structure):
     ]
 
 
+class LossProblem(ctypes.Structure):
+    """struct srl_loss_problem"""
+    _fields_ = [(k, c_void_p) for k in ("new_logp", "v_pred", "entropy", "lane_idx", "norm_stats", "local_stats",
+                                        "g_logp", "g_value", "g_entropy", "out", "out_f32", "workspace")]
+
+
 class LeafDesc(ctypes.Structure):
     """struct srl_leaf_desc"""
     _fields_ = [("src", c_void_p), ("dst", c_void_p), ("row_bytes", c_int64), ("src_slots", c_int64)]
@@ -66,8 +73,8 @@ SIGNATURES = {
     "srl_last_error": (c_char_p, []),
     "srl_abi_version": (c_int, []),
     "srl_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
-    "srl_gae_scan": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double] +
-                     [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "srl_gae_scan": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double] +
+                     [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "srl_lane_stats": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "srl_group_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "srl_popart_update": (c_int, [c_void_p, c_void_p, c_double, c_double, c_void_p, c_void_p]),
@@ -78,6 +85,9 @@ SIGNATURES = {
                                      c_int, c_int, c_void_p, c_void_p, c_void_p, POINTER(PpoHyper),
                                      c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
                                      c_void_p]),
+    "srl_ppo_loss_fwd_bwd_batched": (c_int, [POINTER(LossProblem), c_int, c_int64, c_int64,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                             c_int, c_int, c_void_p, POINTER(PpoHyper), c_size_t, c_void_p]),
     "srl_ppo_loss_from_logits": (c_int, [c_void_p, c_void_p, POINTER(c_int32), c_int, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                          c_int, c_int, c_void_p, c_void_p, c_void_p, POINTER(PpoHyper),

@@ -14,9 +14,11 @@ struct GaeParams {
   const float* vt_new_logp;
   const float* vt_old_logp;
   const double* popart;  // {mean, std} or null
+  const float* old_logp;  // [L, N] or null (only for the pack)
   float* adv;
   float* ret;
   double* lane_part;
+  float* pack;  // [L, N, 4] or null
   int L, N, row_lo, row_hi;
   double gamma, gamma_lmbda, rho, c;
 };

@@ -195,6 +195,11 @@ __global__ void __launch_bounds__(kThreads, 4) gae_scan_kernel(const GaeParams p
       const size_t g = static_cast<size_t>(t) * N + col;
       stg_stream(p.adv + g, a);
       stg_stream(p.ret + g, r);
+      if (p.pack != nullptr) {  // sample side of the loss as one 16-byte item (see include/srl_b200.h)
+        const bool keep = t < L - 1 && (sf[(t + 1) * LW + lane] & 4u) == 0u;
+        __stcg(reinterpret_cast<float4*>(p.pack) + g,
+               make_float4(__ldg(p.old_logp + g), __ldg(p.value + g), r, keep ? a : __int_as_float(0x7fc00000)));
+      }
     }
   }
   SRL_STAMP(4);
@@ -251,9 +256,9 @@ int launch(const GaeParams& p, cudaStream_t st) {
 
 extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8_t* done, const uint8_t* truncated,
                             const uint8_t* on_reset, const float* vtrace_new_logp, const float* vtrace_old_logp,
-                            const double* popart_mean_std, int L, int N, int row_lo, int row_hi, double gamma,
-                            double lmbda, double rho, double c, float* adv, float* ret, double* lane_part,
-                            srl_stream_t stream) {
+                            const double* popart_mean_std, const float* old_logp, int L, int N, int row_lo,
+                            int row_hi, double gamma, double lmbda, double rho, double c, float* adv, float* ret,
+                            double* lane_part, float* pack, srl_stream_t stream) {
   using namespace srl;
   SRL_REQUIRE(L >= 2 && N >= 1, SRL_ERR_INVALID_ARG, "srl_gae_scan: need L >= 2 and N >= 1 (got L=%d N=%d)", L, N);
   SRL_REQUIRE(reward && value && done && truncated && on_reset && adv && ret, SRL_ERR_INVALID_ARG,
@@ -262,6 +267,8 @@ extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8
               "srl_gae_scan: vtrace needs both log-prob tensors");
   SRL_REQUIRE(row_lo >= 0 && row_lo <= row_hi && row_hi <= L - 1, SRL_ERR_INVALID_ARG,
               "srl_gae_scan: loss rows [%d, %d) must lie inside [0, L-1=%d]", row_lo, row_hi, L - 1);
+  SRL_REQUIRE(pack == nullptr || (old_logp != nullptr && aligned(pack, 16)), SRL_ERR_INVALID_ARG,
+              "srl_gae_scan: the pack needs old_logp and a 16-byte aligned destination");
   const bool vtrace = vtrace_new_logp != nullptr;
   GaeParams p;
   p.reward = reward;
@@ -272,6 +279,8 @@ extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8
   p.vt_new_logp = vtrace_new_logp;
   p.vt_old_logp = vtrace_old_logp;
   p.popart = popart_mean_std;
+  p.old_logp = old_logp;
+  p.pack = pack;
   p.adv = adv;
   p.ret = ret;
   p.lane_part = lane_part;
@@ -288,10 +297,13 @@ extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8
   // Throughput path: TMA-pipelined warp-per-32-lanes scan (gae_scan_tma.cu); needs 16-byte aligned rows and
   // enough lane groups to give every SM several warps (it is issue-bound per warp, so few warps = long tail).
   // Latency path (few lanes) and ragged shapes: the shared-memory tile kernel below.
-  bool use_tma = gae_tma_eligible(p) && (N + 31) / 32 >= 2 * sm_count();
-#ifdef SRL_DEBUG_PHASES
-  if (const char* e = getenv("SRL_GAE_PATH")) use_tma = gae_tma_eligible(p) && e[1] == 'm';  // "tma" / "tile"
-#endif
+  // SRL_GAE_TMA_MIN_GROUPS (read once) overrides the threshold: a tuning knob for profiles/, not an API.
+  static const int min_groups_env = [] {
+    const char* e = getenv("SRL_GAE_TMA_MIN_GROUPS");
+    return e ? atoi(e) : -1;
+  }();
+  const int min_groups = min_groups_env >= 0 ? min_groups_env : 2 * sm_count();
+  const bool use_tma = gae_tma_eligible(p) && (N + 31) / 32 >= min_groups;
   if (use_tma) return launch_gae_tma(p, st);
 
   // General path (any N, any alignment): shared-memory tile kernel below.

@@ -1,16 +1,23 @@
 // K2, fast path: TMA-pipelined GAE scan.  One warp owns 32 adjacent lanes for the whole trajectory, so
-// EVERY thread is a scanning thread (the tile kernel in gae_scan.cu idles 7 of 8 warps during the scan and
-// exposes one DRAM round trip per load batch -- profiles/r1_notes.md).  Rows are processed in stages of
-// 8 rows, newest first; each stage is five 2-D TMA tile loads ([8 rows x 32 lanes] boxes of reward, value,
-// done, truncated, on_reset; seven with V-trace) landing in a 6-deep shared-memory ring, completion tracked
+// EVERY thread is a scanning thread (the tile kernel in gae_scan.cu idles most warps during the scan and
+// exposes one DRAM round trip per load batch).  Rows are processed in stages of 8 rows, newest first; each
+// stage is five 2-D TMA tile loads ([8 rows x 32 lanes] boxes of reward, value, done, truncated, on_reset;
+// six with the loss pack, seven with V-trace) landing in a 4-deep shared-memory ring, completion tracked
 // with one mbarrier per slot.  The warp that consumes a slot re-arms it, so there is no CTA-level barrier
-// anywhere; 48 rows x 352 B = 16.5 KB are in flight per warp and ~10 warps fit per SM, which is what it takes
-// to cover HBM latency at 6.5 TB/s.  Outputs leave straight from registers as 128-byte coalesced stores;
-// the per-lane float64 statistics never leave the thread until the end.
+// anywhere; 32 rows x 352 B = 11 KB are in flight per warp and 14+ warps fit per SM (all 2048 warps of a
+// 65536-lane batch are resident at once), which is what it takes to cover HBM latency at 6.5 TB/s.  Outputs
+// leave straight from registers as 128-byte coalesced stores (512-byte for the pack); the per-lane float64
+// statistics never leave the thread until the end.
 //
-// Arithmetic is identical, operation for operation, to the tile kernel (same explicit roundings), so both
-// paths are bit-identical to the reference's float64 scan.
+// r1c: the kernel was issue-bound (ncu: 91 warp instructions per row, 61 % of issue slots busy, DRAM at 33 %;
+// profiles/r1b_ncu_cfg5_before.txt).  Now stages that lie entirely inside the loss rows run a specialised body
+// with no per-row range tests, masks are selects instead of fp64 multiplies, the mask / done / truncated counts
+// are integers, and squares accumulate with one DFMA.
+//
+// Arithmetic on adv / ret is identical, operation for operation, to the tile kernel (same explicit roundings),
+// so both paths are bit-identical to the reference's float64 scan.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gae_common.cuh"
@@ -22,14 +29,14 @@ namespace {
 #define SRL_TMA_ROWS 8
 #endif
 #ifndef SRL_TMA_STAGES
-#define SRL_TMA_STAGES 6
+#define SRL_TMA_STAGES 4
 #endif
 constexpr int kRows = SRL_TMA_ROWS;      // rows per stage
 constexpr int kStages = SRL_TMA_STAGES;  // ring depth
-constexpr int kLanes = 32;   // lanes per warp / CTA
+constexpr int kLanes = 32;               // lanes per warp / CTA
 
 struct alignas(64) GaeTmaMaps {
-  CUtensorMap reward, value, done, truncated, on_reset, vt_new, vt_old;
+  CUtensorMap reward, value, done, truncated, on_reset, old_logp, vt_new;
 };
 
 struct GaeTmaParams {
@@ -37,17 +44,18 @@ struct GaeTmaParams {
   GaeTmaMaps maps;
 };
 
-template <bool VTRACE>
+// OLDLP: the stage also carries old_logp (needed by the pack and by V-trace)
+template <bool VTRACE, bool OLDLP>
 struct StageLayout {
   // byte offsets inside one stage; every sub-buffer is 128-byte aligned
   static constexpr int value = 0;
   static constexpr int reward = value + kRows * kLanes * 4;
-  static constexpr int vt_new = reward + kRows * kLanes * 4;
-  static constexpr int vt_old = vt_new + (VTRACE ? kRows * kLanes * 4 : 0);
-  static constexpr int done = vt_old + (VTRACE ? kRows * kLanes * 4 : 0);
+  static constexpr int old_logp = reward + kRows * kLanes * 4;
+  static constexpr int vt_new = old_logp + (OLDLP ? kRows * kLanes * 4 : 0);
+  static constexpr int done = vt_new + (VTRACE ? kRows * kLanes * 4 : 0);
   static constexpr int truncated = done + kRows * kLanes;
   static constexpr int on_reset = truncated + kRows * kLanes;
-  static constexpr int bytes = on_reset + kRows * kLanes;            // payload = what the mbarrier expects
+  static constexpr int bytes = on_reset + kRows * kLanes;  // payload = what the mbarrier expects
   static constexpr int stride = (bytes + 127) / 128 * 128;
 };
 
@@ -80,24 +88,140 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-template <bool VTRACE>
+template <bool VTRACE, bool OLDLP>
 __device__ __forceinline__ void issue_stage(const GaeTmaParams& q, unsigned char* slot, uint64_t* bar, int col0, int row0) {
-  using SL = StageLayout<VTRACE>;
+  using SL = StageLayout<VTRACE, OLDLP>;
   mbar_expect_tx(bar, SL::bytes);
   tma_load_2d(slot + SL::value, &q.maps.value, col0, row0, bar);
   tma_load_2d(slot + SL::reward, &q.maps.reward, col0, row0, bar);
   tma_load_2d(slot + SL::done, &q.maps.done, col0, row0, bar);
   tma_load_2d(slot + SL::truncated, &q.maps.truncated, col0, row0, bar);
   tma_load_2d(slot + SL::on_reset, &q.maps.on_reset, col0, row0, bar);
-  if (VTRACE) {
-    tma_load_2d(slot + SL::vt_new, &q.maps.vt_new, col0, row0, bar);
-    tma_load_2d(slot + SL::vt_old, &q.maps.vt_old, col0, row0, bar);
-  }
+  if (OLDLP) tma_load_2d(slot + SL::old_logp, &q.maps.old_logp, col0, row0, bar);
+  if (VTRACE) tma_load_2d(slot + SL::vt_new, &q.maps.vt_new, col0, row0, bar);
 }
 
-template <bool VTRACE>
+// What a lane carries from row t+1 into row t, and its running statistics.
+struct Carry {
+  double vd_next = 0.0;  // float64 image of v'[t+1]
+  double g = 0.0;        // A[t+1]
+  bool reset_next = false, trunc_next = false;
+};
+struct LaneStats {
+  double s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+  int cnt = 0, dn = 0, tr = 0;
+};
+
+// One stage of kRows rows.  EDGE = false: every row t of the stage satisfies row_lo <= t < row_hi (<= L-1), so all
+// rows are scanned, stored and counted -- no per-row range tests.  EDGE = true: the general body.
+// Straight-line code on purpose: the 8 rows of a stage are independent except for the two-instruction chain in
+// pass 2, so the scheduler can overlap their shared-memory, conversion and fp64 latencies.
+template <bool VTRACE, bool PACK, bool EDGE>
+__device__ __forceinline__ void run_stage(const GaeParams& p, const unsigned char* slot, int tbase, int lane, int col,
+                                          bool live, bool popart, double pa_mean, double pa_std, Carry& cy,
+                                          LaneStats& st) {
+  using SL = StageLayout<VTRACE, PACK || VTRACE>;
+  const float* sv = reinterpret_cast<const float*>(slot + SL::value);
+  const float* sr = reinterpret_cast<const float*>(slot + SL::reward);
+  const uint8_t* sdn = slot + SL::done;
+  const uint8_t* str_ = slot + SL::truncated;
+  const uint8_t* srs = slot + SL::on_reset;
+  const int L = p.L, N = p.N;
+  const double gamma = p.gamma, gl = p.gamma_lmbda;
+
+  // ---- pass 1: v', flags, delta_t, m_t for the 8 rows (independent) -----------------------------------------
+  float v[kRows];
+  double vd[kRows], dl[kRows], mm[kRows];
+  bool dnf[kRows], trf[kRows], rsf[kRows];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    float x = sv[r * kLanes + lane];
+    dnf[r] = sdn[r * kLanes + lane] != 0;
+    trf[r] = str_[r * kLanes + lane] != 0;
+    rsf[r] = srs[r * kLanes + lane] != 0;
+    if (popart)  // RunningMeanStd.denormalize: (x.double() * std + mean).float()   utils.py:146-151
+      x = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(x), pa_std), pa_mean));
+    v[r] = __fmul_rn(x, dnf[r] ? 0.f : 1.f);  // value * (1 - done), fp32   mappo.py:120-124
+    vd[r] = static_cast<double>(v[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    const double vn = (r == kRows - 1) ? cy.vd_next : vd[r + 1];
+    const bool rn = (r == kRows - 1) ? cy.reset_next : rsf[r + 1];
+    const bool tn = (r == kRows - 1) ? cy.trunc_next : trf[r + 1];
+    // gae.py:63  reward + gamma * value[1:] * (1 - on_reset[1:]) - value[:-1]
+    double d = __dmul_rn(__dmul_rn(gamma, vn), rn ? 0.0 : 1.0);
+    d = __dadd_rn(static_cast<double>(sr[r * kLanes + lane]), d);
+    d = __dsub_rn(d, vd[r]);
+    // gae.py:87  gamma * lmbda * (1 - on_reset[1:]) * (1 - truncated[1:]): exactly 0 or gamma*lmbda
+    double m = (rn || tn) ? 0.0 : gl;
+    if (VTRACE) {
+      const float* snl = reinterpret_cast<const float*>(slot + SL::vt_new);
+      const float* sol = reinterpret_cast<const float*>(slot + SL::old_logp);
+      const double rd = static_cast<double>(expf(snl[r * kLanes + lane] - sol[r * kLanes + lane]));  // mappo.py:129-132
+      d = __dmul_rn(d, fmin(rd, p.rho));  // gae.py:64-65
+      m = __dmul_rn(m, fmin(rd, p.c));    // gae.py:88-89
+    }
+    if (EDGE) {
+      const bool scanned = tbase + r < L - 1;  // rows L-1 (padding row) and beyond carry no advantage
+      d = scanned ? d : 0.0;
+      m = scanned ? m : 0.0;
+    }
+    dl[r] = d;
+    mm[r] = m;
+  }
+  // ---- pass 2: the only sequential part, A_t = delta_t + m_t * A_{t+1} (two roundings, gae.py:92) -------------
+  float a[kRows];
+  double g = cy.g;
+#pragma unroll
+  for (int r = kRows - 1; r >= 0; --r) {
+    g = __dadd_rn(dl[r], __dmul_rn(mm[r], g));
+    a[r] = static_cast<float>(g);  // adv.float(), gae.py:97
+  }
+  cy.g = g;
+  // ---- pass 3: value target, stores, per-lane statistics (independent) ------------------------------------------
+  size_t gi = static_cast<size_t>(tbase + kRows - 1) * N + col;
+#pragma unroll
+  for (int r = kRows - 1; r >= 0; --r, gi -= N) {
+    const int t = tbase + r;
+    const bool rn = (r == kRows - 1) ? cy.reset_next : rsf[r + 1];
+    float rt = __fadd_rn(a[r], v[r]);  // value_target = adv + v'[:-1]   mappo.py:143
+    if (EDGE) rt = (t < L - 1) ? rt : 0.f;
+    const bool store = EDGE ? (live && t < L) : live;  // row L-1 is the zero padding row of mappo.py:254-256
+    // loss rows [row_lo, row_hi), mask = 1 - on_reset[t+1]   mappo.py:259-261
+    const bool in_rows = EDGE ? (t >= p.row_lo && t < p.row_hi) : true;
+    const bool mk = in_rows && !rn;
+#ifndef SRL_DEBUG_NO_STORES
+    if (store) {
+      stg_stream(p.adv + gi, a[r]);
+      stg_stream(p.ret + gi, rt);
+      if (PACK) {
+        const float* sol = reinterpret_cast<const float*>(slot + SL::old_logp);
+        const bool keep = EDGE ? (!rn && t < L - 1) : !rn;
+        __stcg(reinterpret_cast<float4*>(p.pack) + gi,
+               make_float4(sol[r * kLanes + lane], sv[r * kLanes + lane], rt, keep ? a[r] : __int_as_float(0x7fc00000)));
+      }
+    }
+#endif
+    const double x = static_cast<double>(mk ? a[r] : 0.f);
+    const double y = static_cast<double>(mk ? rt : 0.f);
+    st.cnt += mk ? 1 : 0;
+    st.s1 += x;
+    st.s2 = __fma_rn(x, x, st.s2);
+    st.s3 += y;
+    st.s4 = __fma_rn(y, y, st.s4);
+    st.dn += (in_rows && dnf[r]) ? 1 : 0;
+    st.tr += (in_rows && trf[r]) ? 1 : 0;
+  }
+  cy.vd_next = vd[0];
+  cy.reset_next = rsf[0];
+  cy.trunc_next = trf[0];
+}
+
+template <bool VTRACE, bool PACK>
 __global__ void __launch_bounds__(kLanes) gae_scan_tma_kernel(const __grid_constant__ GaeTmaParams q) {
-  using SL = StageLayout<VTRACE>;
+  constexpr bool OLDLP = PACK || VTRACE;
+  using SL = StageLayout<VTRACE, OLDLP>;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * SL::stride);
   const GaeParams& p = q.p;
@@ -118,7 +242,7 @@ __global__ void __launch_bounds__(kLanes) gae_scan_tma_kernel(const __grid_const
   __syncwarp();
   if (lane == 0) {  // prologue: fill the ring, newest rows first
     for (int i = 0; i < kStages && i < n_stages; ++i)
-      issue_stage<VTRACE>(q, smem + i * SL::stride, &bars[i], col0, (n_stages - 1 - i) * kRows);
+      issue_stage<VTRACE, OLDLP>(q, smem + i * SL::stride, &bars[i], col0, (n_stages - 1 - i) * kRows);
   }
 
   const bool popart = p.popart != nullptr;
@@ -127,13 +251,8 @@ __global__ void __launch_bounds__(kLanes) gae_scan_tma_kernel(const __grid_const
     pa_mean = p.popart[0];
     pa_std = p.popart[1];
   }
-  const double gamma = p.gamma, gl = p.gamma_lmbda;
-
-  // carried from row t+1
-  float v_next = 0.f;
-  bool reset_next = false, trunc_next = false;
-  double g = 0.0;
-  double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0;
+  Carry cy;
+  LaneStats st;
 
 #ifdef SRL_DEBUG_PHASES
   long long dbg_wait = 0;
@@ -150,93 +269,15 @@ __global__ void __launch_bounds__(kLanes) gae_scan_tma_kernel(const __grid_const
 #ifdef SRL_DEBUG_PHASES
     dbg_wait += clock64() - w0;
 #endif
-    const float* sv = reinterpret_cast<const float*>(slot + SL::value);
-    const float* sr = reinterpret_cast<const float*>(slot + SL::reward);
-    const uint8_t* sdn = slot + SL::done;
-    const uint8_t* str_ = slot + SL::truncated;
-    const uint8_t* srs = slot + SL::on_reset;
     const int tbase = k * kRows;
-
-    // Straight-line code on purpose (no per-row branches): the 8 rows of a stage are independent except for
-    // the two-instruction chain in pass 2, so the scheduler can overlap their shared-memory, conversion and
-    // fp64 latencies.  Rows t >= L (top stage only) were zero-filled by TMA and are forced to delta = m = 0.
-
-    // ---- pass 1: v', flags, delta_t, m_t for the 8 rows (independent) ---------------------------------------
-    float v[kRows];
-    double dl[kRows], mm[kRows];
-    bool dnf[kRows], trf[kRows], rsf[kRows];
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      float x = sv[r * kLanes + lane];
-      dnf[r] = sdn[r * kLanes + lane] != 0;
-      trf[r] = str_[r * kLanes + lane] != 0;
-      rsf[r] = srs[r * kLanes + lane] != 0;
-      if (popart)  // RunningMeanStd.denormalize: (x.double() * std + mean).float()   utils.py:146-151
-        x = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(x), pa_std), pa_mean));
-      v[r] = __fmul_rn(x, dnf[r] ? 0.f : 1.f);  // value * (1 - done), fp32   mappo.py:120-124
-    }
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const float vn = (r == kRows - 1) ? v_next : v[r + 1];
-      const bool rn = (r == kRows - 1) ? reset_next : rsf[r + 1];
-      const bool tn = (r == kRows - 1) ? trunc_next : trf[r + 1];
-      const double alive = rn ? 0.0 : 1.0;  // 1 - on_reset[t+1]
-      // gae.py:63  reward + gamma * value[1:] * (1 - on_reset[1:]) - value[:-1]
-      double d = __dmul_rn(__dmul_rn(gamma, static_cast<double>(vn)), alive);
-      d = __dadd_rn(static_cast<double>(sr[r * kLanes + lane]), d);
-      d = __dsub_rn(d, static_cast<double>(v[r]));
-      // gae.py:87  gamma * lmbda * (1 - on_reset[1:]) * (1 - truncated[1:]): exactly 0 or gamma*lmbda
-      double m = (rn || tn) ? 0.0 : gl;
-      if (VTRACE) {
-        const float* snl = reinterpret_cast<const float*>(slot + SL::vt_new);
-        const float* sol = reinterpret_cast<const float*>(slot + SL::vt_old);
-        const double rd = static_cast<double>(expf(snl[r * kLanes + lane] - sol[r * kLanes + lane]));  // mappo.py:129-132
-        d = __dmul_rn(d, fmin(rd, p.rho));  // gae.py:64-65
-        m = __dmul_rn(m, fmin(rd, p.c));    // gae.py:88-89
-      }
-      const bool scanned = tbase + r < L - 1;  // rows L-1 (padding row) and beyond carry no advantage
-      dl[r] = scanned ? d : 0.0;
-      mm[r] = scanned ? m : 0.0;
-    }
-    // ---- pass 2: the only sequential part, A_t = delta_t + m_t * A_{t+1} (two roundings, gae.py:92) ----------
-    float a[kRows];
-#pragma unroll
-    for (int r = kRows - 1; r >= 0; --r) {
-      g = __dadd_rn(dl[r], __dmul_rn(mm[r], g));
-      a[r] = static_cast<float>(g);  // adv.float(), gae.py:97
-    }
-    // ---- pass 3: value target, stores, per-lane statistics (independent) ---------------------------------------
-#pragma unroll
-    for (int r = kRows - 1; r >= 0; --r) {
-      const int t = tbase + r;
-      const bool rn = (r == kRows - 1) ? reset_next : rsf[r + 1];
-      const float rt = (t < L - 1) ? __fadd_rn(a[r], v[r]) : 0.f;  // value_target = adv + v'[:-1]   mappo.py:143
-#ifndef SRL_DEBUG_NO_STORES
-      if (live && t < L) {  // row L-1 is the zero padding row of mappo.py:254-256
-        const size_t gi = static_cast<size_t>(t) * N + col;
-        stg_stream(p.adv + gi, a[r]);
-        stg_stream(p.ret + gi, rt);
-      }
-#endif
-      // loss rows [row_lo, row_hi), mask = 1 - on_reset[t+1]   mappo.py:259-261
-      const bool in_rows = t >= p.row_lo && t < p.row_hi;
-      const double mk = (in_rows && !rn) ? 1.0 : 0.0;
-      const double x = __dmul_rn(static_cast<double>(a[r]), mk);
-      const double y = __dmul_rn(static_cast<double>(rt), mk);
-      s0 += mk;
-      s1 += x;
-      s2 = __dadd_rn(s2, __dmul_rn(x, x));
-      s3 += y;
-      s4 = __dadd_rn(s4, __dmul_rn(y, y));
-      s5 += (in_rows && dnf[r]) ? 1.0 : 0.0;
-      s6 += (in_rows && trf[r]) ? 1.0 : 0.0;
-    }
-    v_next = v[0];
-    reset_next = rsf[0];
-    trunc_next = trf[0];
+    const bool interior = !VTRACE && tbase >= p.row_lo && tbase + kRows <= p.row_hi;
+    if (interior)
+      run_stage<VTRACE, PACK, false>(p, slot, tbase, lane, col, live, popart, pa_mean, pa_std, cy, st);
+    else
+      run_stage<VTRACE, PACK, true>(p, slot, tbase, lane, col, live, popart, pa_mean, pa_std, cy, st);
     __syncwarp();  // every lane is done reading this slot
     if (lane == 0 && it + kStages < n_stages)
-      issue_stage<VTRACE>(q, slot, &bars[slot_i], col0, (n_stages - 1 - (it + kStages)) * kRows);
+      issue_stage<VTRACE, OLDLP>(q, slot, &bars[slot_i], col0, (n_stages - 1 - (it + kStages)) * kRows);
   }
 #ifdef SRL_DEBUG_PHASES
   if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1))
@@ -245,13 +286,13 @@ __global__ void __launch_bounds__(kLanes) gae_scan_tma_kernel(const __grid_const
 #endif
   if (p.lane_part != nullptr && live) {
     double* o = p.lane_part + col;
-    o[0] = s0;
-    o[static_cast<size_t>(1) * N] = s1;
-    o[static_cast<size_t>(2) * N] = s2;
-    o[static_cast<size_t>(3) * N] = s3;
-    o[static_cast<size_t>(4) * N] = s4;
-    o[static_cast<size_t>(5) * N] = s5;
-    o[static_cast<size_t>(6) * N] = s6;
+    o[0] = static_cast<double>(st.cnt);
+    o[static_cast<size_t>(1) * N] = st.s1;
+    o[static_cast<size_t>(2) * N] = st.s2;
+    o[static_cast<size_t>(3) * N] = st.s3;
+    o[static_cast<size_t>(4) * N] = st.s4;
+    o[static_cast<size_t>(5) * N] = static_cast<double>(st.dn);
+    o[static_cast<size_t>(6) * N] = static_cast<double>(st.tr);
     o[static_cast<size_t>(7) * N] = 0.0;
   }
 }
@@ -290,11 +331,11 @@ int make_map(CUtensorMap* m, const void* base, int rows, int N, int elem) {
   return SRL_OK;
 }
 
-template <bool VTRACE>
+template <bool VTRACE, bool PACK>
 int launch(const GaeTmaParams& q, cudaStream_t st) {
-  using SL = StageLayout<VTRACE>;
+  using SL = StageLayout<VTRACE, PACK || VTRACE>;
   const size_t smem = static_cast<size_t>(kStages) * SL::stride + kStages * sizeof(uint64_t);
-  auto kern = gae_scan_tma_kernel<VTRACE>;
+  auto kern = gae_scan_tma_kernel<VTRACE, PACK>;
   static bool opted_in[64] = {};
   int dev = 0;
   SRL_CUDA(cudaGetDevice(&dev));
@@ -317,6 +358,7 @@ bool gae_tma_eligible(const GaeParams& p) {
   for (const void* q : ptrs)
     if (!aligned(q, 16)) return false;
   if (p.vt_new_logp && (!aligned(p.vt_new_logp, 16) || !aligned(p.vt_old_logp, 16))) return false;
+  if (p.pack && !aligned(p.old_logp, 16)) return false;
   return true;
 }
 
@@ -330,12 +372,18 @@ int launch_gae_tma(const GaeParams& p, cudaStream_t st) {
   if ((rc = make_map(&q.maps.truncated, p.truncated, p.L, p.N, 1)) != SRL_OK) return rc;
   if ((rc = make_map(&q.maps.on_reset, p.on_reset, p.L, p.N, 1)) != SRL_OK) return rc;
   const bool vtrace = p.vt_new_logp != nullptr;
+  const bool pack = p.pack != nullptr;
   if (vtrace) {  // [L-1, N]: the last row of the top stage reads as zero and is never used
     if ((rc = make_map(&q.maps.vt_new, p.vt_new_logp, p.L - 1, p.N, 4)) != SRL_OK) return rc;
-    if ((rc = make_map(&q.maps.vt_old, p.vt_old_logp, p.L - 1, p.N, 4)) != SRL_OK) return rc;
-    return launch<true>(q, st);
+    if ((rc = make_map(&q.maps.old_logp, p.vt_old_logp, p.L - 1, p.N, 4)) != SRL_OK) return rc;
+    // the pack's old_logp is the sample leaf the V-trace ratio uses as well
+    return pack ? launch<true, true>(q, st) : launch<true, false>(q, st);
   }
-  return launch<false>(q, st);
+  if (pack) {
+    if ((rc = make_map(&q.maps.old_logp, p.old_logp, p.L, p.N, 4)) != SRL_OK) return rc;
+    return launch<false, true>(q, st);
+  }
+  return launch<false, false>(q, st);
 }
 
 }  // namespace srl

@@ -4,12 +4,27 @@
 // One pass over the [T, n] minibatch: each element reads 29 B (25 B without value clipping) and
 // writes 12 B of gradients.  The advantage-normalisation statistics arrive pre-reduced (and, on
 // several GPUs, pre-all-reduced) from K2 + srl_group_stats, so there is no second pass and no grid
-// barrier.  Eight masked sums are reduced warp-shuffle -> shared memory -> one float64 partial row per
-// CTA in the caller's workspace slot.  Two ways to turn the rows into the loss scalars + stats vector:
-//   immediate (out != NULL): the last CTA to finish (atomic ticket) folds the rows in a fixed order;
-//   deferred  (out == NULL): the kernel ends right after its stores -- the gradients are all the backward
-//     pass needs -- and srl_ppo_loss_finalize folds any number of slots later in ONE launch (the reference
-//     pays eleven .item() syncs per epoch for the same numbers, mappo.py:293-299).
+// barrier.
+//
+// Work decomposition (r1c; profiles/r1c_notes.md has the ncu evidence behind each choice):
+//  * a launch covers up to SRL_MAX_LOSS_BATCH minibatches ("problems") of one shape -- blockIdx.y picks the
+//    problem -- so the 32 tiny per-minibatch launches of a 4 x 8 PPO schedule become one grid that fills the
+//    machine;
+//  * inside a problem a CTA walks tiles of `rows_per_tile` rows x (blockDim * 4) lanes; a thread owns four
+//    adjacent lanes (128-bit accesses on the dense policy side) and keeps its four gather indices in
+//    registers for all rows of the tile, so index loads and the run-of-4 test are paid once per tile;
+//  * the sample side comes in one of three forms: dense leaves (whole batch, no permutation), leaves
+//    gathered through lane_idx (any alignment), or K2's `pack` ([T, N] float4 = old_logp, old_value, ret,
+//    adv-or-NaN): one 16-byte gather per element instead of five 1..4-byte ones -- the L1 wavefront count,
+//    which is what bounds a per-lane gather, drops 5x;
+//  * per-element arithmetic is fp32 except the advantage / PopArt normalisation, which stays in float64
+//    (reference: utils.py:38-67,139-144) as subtract + multiply by a correctly rounded reciprocal + one
+//    Newton residual step (3 fp64 instructions instead of a ~25-instruction IEEE division; the quotient is
+//    the correctly rounded one, then cast to float as the reference does);
+//  * eight masked sums: four lanes are summed in fp32, then accumulated in float64 per thread, reduced
+//    warp-shuffle -> shared memory -> one float64 partial row per CTA in the problem's workspace slot.
+// Finalisation: immediate (out != NULL): the last CTA of the problem (atomic ticket) folds the rows in a fixed
+// order; deferred (out == NULL): srl_ppo_loss_finalize folds any number of slots later in ONE launch.
 // Either way the result is deterministic for a given launch shape and nothing syncs with the host.
 #include <float.h>
 
@@ -18,7 +33,11 @@
 namespace srl {
 namespace {
 
-constexpr int kMaxGrid = 2048;
+#ifndef SRL_LOSS_UNROLL
+#define SRL_LOSS_UNROLL 2
+#endif
+constexpr int kLossUnroll = SRL_LOSS_UNROLL;  // rows of a tile whose loads are in flight together
+constexpr int kMaxGrid = 2048;  // partial rows per workspace slot
 constexpr int kNumSums = 8;
 constexpr size_t kPartialsOffset = 64;
 
@@ -42,69 +61,71 @@ struct LossHyperDev {
   int value_loss, clip_value, dual_clip, normalize_old_value;
 };
 
-struct LossParams {
+// Per-minibatch pointers.
+struct Problem {
   const float* new_logp;
   const float* v_pred;
   const float* entropy;
-  long long ld_pol;
+  const int32_t* lane_idx;
+  const double* norm_stats;
+  const double* local_stats;
+  float* g_logp;
+  float* g_value;
+  float* g_entropy;
+  double* out;
+  float* out_f32;
+  SlotHeader* slot;
+};
+
+// What every problem of a launch shares.
+struct LossShared {
   const float* old_logp;
   const float* old_value;
   const float* ret;
   const float* adv;
   const uint8_t* reset_next;
-  long long ld_smp;
-  const int32_t* lane_idx;
-  int T, n;
-  int smp_vec_ok;  // sample-side leaves allow 128-bit loads at 4-aligned lanes (alignment + row stride)
-  const double* norm_stats;
-  const double* local_stats;
+  const float4* pack;
   const double* popart;
-  float* g_logp;
-  float* g_value;
-  float* g_entropy;
-  long long ld_grad;
-  double* out;
-  float* out_f32;
-  double* partials;
-  SlotHeader* slot;
+  long long ld_pol, ld_grad, ld_smp;
+  int T, n;
+  int rows_per_tile, col_tiles, n_tiles;
+  int smp_vec_ok;  // sample-side leaves allow 128-bit loads at 4-aligned lanes (alignment + row stride)
   LossHyperDev h;
 };
 
+template <int NB>
+struct LossBatch {
+  LossShared s;
+  Problem prob[NB];
+};
+
 // torch.nn.{MSELoss,HuberLoss,SmoothL1Loss}(reduction='none') value and derivative wrt the input.
+// `kind` is uniform across the launch; inside a kind both branches are evaluated and selected (the quadratic /
+// linear choice is per element, and a divergent branch costs more than the three spare flops).
 __device__ __forceinline__ void pointwise_loss(int kind, float prm, float d, float& l, float& dl) {
   if (kind == SRL_VL_MSE) {
     l = d * d;
     dl = 2.f * d;
   } else if (kind == SRL_VL_HUBER) {
     const float z = fabsf(d);
-    if (z < prm) {
-      l = 0.5f * z * z;
-      dl = d;
-    } else {
-      l = prm * (z - 0.5f * prm);
-      dl = d > 0.f ? prm : -prm;
-    }
+    const bool quad = z < prm;
+    const float lq = 0.5f * z * z, ll = prm * (z - 0.5f * prm);
+    l = quad ? lq : ll;
+    dl = quad ? d : (d > 0.f ? prm : -prm);
   } else {
     const float z = fabsf(d);
-    if (z < prm) {
-      l = 0.5f * z * z / prm;
-      dl = d / prm;
-    } else {
-      l = z - 0.5f * prm;
-      dl = d > 0.f ? 1.f : -1.f;
-    }
+    const bool quad = z < prm;
+    const float lq = 0.5f * z * z / prm, ll = z - 0.5f * prm;
+    l = quad ? lq : ll;
+    dl = quad ? d / prm : (d > 0.f ? 1.f : -1.f);
   }
 }
 
 struct Uniforms {
-  double mean, denom;   // advantage normalisation: (x - mean) / denom
-  double pa_mu, pa_sd;  // popart
-  float inv_m;          // 1 / local sum(mask)
+  double mean, denom, rdenom;    // advantage normalisation: (x - mean) / denom, rdenom = 1 / denom
+  double pa_mu, pa_sd, pa_rsd;   // popart: (x - mu) / sd
+  float inv_m;                   // 1 / local sum(mask)
   bool popart;
-};
-
-struct Acc {
-  double pl = 0, vl = 0, en = 0, adv = 0, ratio = 0, clip = 0, vt = 0, ret = 0;
 };
 
 // The six scalars every thread needs.  Loading them is split from the math on them so that the (long) fp64
@@ -114,15 +135,16 @@ struct RawStats {
   bool popart;
 };
 
-__device__ __forceinline__ RawStats load_raw_stats(const LossParams& p) {
+__device__ __forceinline__ RawStats load_raw_stats(const double* norm_stats, const double* local_stats,
+                                                   const double* popart) {
   RawStats r;
-  r.cnt = __ldg(p.norm_stats);
-  r.s1 = __ldg(p.norm_stats + 1);
-  r.s2 = __ldg(p.norm_stats + 2);
-  r.m_local = __ldg(p.local_stats);
-  r.popart = p.popart != nullptr;
-  r.pa_mu = r.popart ? __ldg(p.popart) : 0.0;
-  r.pa_sd = r.popart ? __ldg(p.popart + 1) : 1.0;
+  r.cnt = __ldg(norm_stats);
+  r.s1 = __ldg(norm_stats + 1);
+  r.s2 = __ldg(norm_stats + 2);
+  r.m_local = __ldg(local_stats);
+  r.popart = popart != nullptr;
+  r.pa_mu = r.popart ? __ldg(popart) : 0.0;
+  r.pa_sd = r.popart ? __ldg(popart + 1) : 1.0;
   return r;
 }
 
@@ -131,26 +153,59 @@ __device__ __forceinline__ Uniforms make_uniforms(const RawStats& r, double adv_
   u.popart = r.popart;
   u.pa_mu = r.pa_mu;
   u.pa_sd = r.pa_sd;
+  u.pa_rsd = 1.0 / r.pa_sd;
   u.mean = r.s1 / r.cnt;
   const double var = r.s2 / r.cnt - u.mean * u.mean;  // biased variance, utils.py:62-64
   u.denom = sqrt(var) + adv_eps;                      // eps outside the sqrt, utils.py:67
+  u.rdenom = 1.0 / u.denom;
   u.inv_m = 1.f / static_cast<float>(r.m_local);
   return u;
 }
 
-__device__ __forceinline__ float popart_normalize(float x, const Uniforms& u) {
-  // RunningMeanStd.normalize: ((x.double() - mean) / std).clip(-5, 5).float()   utils.py:139-144
-  double z = (static_cast<double>(x) - u.pa_mu) / u.pa_sd;
-  z = fmin(fmax(z, -5.0), 5.0);
-  return static_cast<float>(z);
+// a / d in float64 given rd = 1 / d (correctly rounded): product, exact residual, one correction.  This is the
+// tail of the IEEE division sequence without its reciprocal refinement and special-case handling; d is a
+// positive finite scale here (sqrt(var) + eps, or PopArt's sigma >= 0.1).
+__device__ __forceinline__ double div_by(double a, double d, double rd) {
+  const double q = __dmul_rn(a, rd);
+  const double r = __fma_rn(-d, q, a);
+  return __fma_rn(r, rd, q);
 }
 
+__device__ __forceinline__ float popart_normalize(float x, const Uniforms& u) {
+  // RunningMeanStd.normalize: ((x.double() - mean) / std).clip(-5, 5).float()   utils.py:139-144
+  // (clipping after the cast gives the same float: +-5 are exact and rounding is monotonic)
+  const float z = static_cast<float>(div_by(__dsub_rn(static_cast<double>(x), u.pa_mu), u.pa_sd, u.pa_rsd));
+  return fminf(fmaxf(z, -5.f), 5.f);
+}
+
+// Per-row (4 lanes) fp32 partial sums; folded into the thread's float64 accumulators once per row.
+struct RowSums {
+  float pl = 0.f, vl = 0.f, en = 0.f, adv = 0.f, ratio = 0.f, vt = 0.f, ret = 0.f;
+  int clip = 0;
+};
+
+struct Acc {
+  double pl = 0, vl = 0, en = 0, adv = 0, ratio = 0, vt = 0, ret = 0;
+  int clip = 0;
+  __device__ __forceinline__ void add(const RowSums& r) {
+    pl += static_cast<double>(r.pl);
+    vl += static_cast<double>(r.vl);
+    en += static_cast<double>(r.en);
+    adv += static_cast<double>(r.adv);
+    ratio += static_cast<double>(r.ratio);
+    vt += static_cast<double>(r.vt);
+    ret += static_cast<double>(r.ret);
+    clip += r.clip;
+  }
+};
+
+// One transition.  Masked transitions (valid == false) produce zero gradients and enter no sum: in the reference
+// every term is multiplied by mask before it is summed (mappo.py:184,197,199) and the stats go through
+// masked_select (mappo.py:206-216).
 __device__ __forceinline__ void element(const LossHyperDev& h, const Uniforms& u, float nl, float vp, float en,
-                                        float ol, float ov, float rt, float ad, uint32_t rs, float& g_lp,
-                                        float& g_v, float& g_en, Acc& acc) {
-  const bool valid = (rs == 0);
-  const float mk = valid ? 1.f : 0.f;
-  const float scale = mk * u.inv_m;  // d(masked mean)/d(element) = mask / M
+                                        float ol, float ov, float rt, float ad, bool valid, float& g_lp,
+                                        float& g_v, float& g_en, RowSums& rs) {
+  const float scale = valid ? u.inv_m : 0.f;  // d(masked mean)/d(element) = mask / M
 
   // ---- critic: mappo.py:172-184, utils.py:228-239 ---------------------------------------------
   const float vt = u.popart ? popart_normalize(rt, u) : rt;
@@ -168,12 +223,13 @@ __device__ __forceinline__ void element(const LossHyperDev& h, const Uniforms& u
     vl = fmaxf(l, l2);
     gv = l > l2 ? dl : (l < l2 ? dl2 : 0.5f * (dl + dl2));  // torch.max splits ties evenly
   }
-  g_v = h.wv * scale * gv;
+  g_v = valid ? h.wv * scale * gv : 0.f;
 
   // ---- actor: mappo.py:157-158,186-197 ---------------------------------------------------------
   const float ratio = expf(nl - ol);
-  const double x = static_cast<double>(ad) * static_cast<double>(mk);  // masked BEFORE centring (utils.py:54)
-  const float nadv = static_cast<float>((x - u.mean) / u.denom);
+  // masked_normalization (utils.py:38-67) in float64, cast to float at the end; masked entries are centred
+  // zeros there (x = adv * mask) but they never reach the loss or the gradients
+  const float nadv = static_cast<float>(div_by(__dsub_rn(static_cast<double>(ad), u.mean), u.denom, u.rdenom));
   const float s1 = ratio * nadv;
   const float s2 = fminf(fmaxf(ratio, h.clip_lo), h.clip_hi) * nadv;
   const float in_clip = (ratio >= h.clip_lo && ratio <= h.clip_hi) ? 1.f : 0.f;
@@ -186,19 +242,17 @@ __device__ __forceinline__ void element(const LossHyperDev& h, const Uniforms& u
     gsum *= obj > s3 ? 1.f : (obj < s3 ? 0.f : 0.5f);
     obj = fmaxf(obj, s3);
   }
-  g_lp = -scale * gsum;
+  g_lp = valid ? -scale * gsum : 0.f;
   g_en = -h.we * scale;  // entropy_loss = -sum(entropy * mask) / M   mappo.py:199
 
-  if (valid) {
-    acc.pl += static_cast<double>(-obj);
-    acc.vl += static_cast<double>(vl);
-    acc.en += static_cast<double>(en);
-    acc.adv += static_cast<double>(ad);
-    acc.ratio += static_cast<double>(ratio);
-    acc.clip += (s2 < s1) ? 1.0 : 0.0;
-    acc.vt += static_cast<double>(vt);
-    acc.ret += static_cast<double>(rt);
-  }
+  rs.pl += valid ? -obj : 0.f;
+  rs.vl += valid ? vl : 0.f;
+  rs.en += valid ? en : 0.f;
+  rs.adv += valid ? ad : 0.f;
+  rs.ratio += valid ? ratio : 0.f;
+  rs.vt += valid ? vt : 0.f;
+  rs.ret += valid ? rt : 0.f;
+  rs.clip += (valid && s2 < s1) ? 1 : 0;
 }
 
 // Folds n_rows partial rows (fixed order: lane-strided, then the warp-shuffle tree) and writes the results.
@@ -238,11 +292,13 @@ __device__ __forceinline__ void fold_rows_and_write(const double* __restrict__ p
 }
 
 // Block reduction of the 8 masked sums -> this CTA's partial row; then either done (deferred) or ticket.
-__device__ __forceinline__ void reduce_and_finalize(const LossParams& p, const Acc& acc, double mask_sum) {
-  const LossHyperDev& h = p.h;
+// `row` / `n_rows`: this CTA's row and the number of CTAs working on the same problem.
+__device__ __forceinline__ void reduce_and_finalize(const Problem& pr, const LossHyperDev& h, const Acc& acc,
+                                                    double mask_sum, int row, int n_rows) {
   __shared__ double sred[kNumSums][8];
   __shared__ bool is_last;
-  double v[kNumSums] = {acc.pl, acc.vl, acc.en, acc.adv, acc.ratio, acc.clip, acc.vt, acc.ret};
+  double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(pr.slot) + kPartialsOffset);
+  double v[kNumSums] = {acc.pl, acc.vl, acc.en, acc.adv, acc.ratio, static_cast<double>(acc.clip), acc.vt, acc.ret};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   // butterfly level by level over all 8 sums: 8 independent shuffle+add chains per level hide each other's latency
 #pragma unroll
@@ -261,29 +317,29 @@ __device__ __forceinline__ void reduce_and_finalize(const LossParams& p, const A
   if (threadIdx.x < kNumSums) {
     double s = 0.0;
     for (int w = 0; w < nwarps; ++w) s += sred[threadIdx.x][w];
-    p.partials[static_cast<size_t>(blockIdx.x) * kNumSums + threadIdx.x] = s;
+    partials[static_cast<size_t>(row) * kNumSums + threadIdx.x] = s;
   }
-  if (p.out == nullptr) {  // deferred: publish what the finaliser needs and leave
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      p.slot->n_rows = gridDim.x;
-      p.slot->mask_sum = mask_sum;
-      p.slot->wv = static_cast<double>(h.wv);
-      p.slot->we = static_cast<double>(h.we);
+  if (pr.out == nullptr) {  // deferred: publish what the finaliser needs and leave
+    if (row == 0 && threadIdx.x == 0) {
+      pr.slot->n_rows = n_rows;
+      pr.slot->mask_sum = mask_sum;
+      pr.slot->wv = static_cast<double>(h.wv);
+      pr.slot->we = static_cast<double>(h.we);
     }
     return;
   }
   if (threadIdx.x < kNumSums) __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int done = atomicAdd(&p.slot->ticket, 1u);
-    is_last = (done == gridDim.x - 1);
+    const unsigned int done = atomicAdd(&pr.slot->ticket, 1u);
+    is_last = (done == static_cast<unsigned int>(n_rows) - 1u);
   }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  fold_rows_and_write(p.partials, static_cast<int>(gridDim.x), mask_sum, static_cast<double>(h.wv),
-                      static_cast<double>(h.we), sred, p.out, p.out_f32);
-  if (threadIdx.x == 0) p.slot->ticket = 0u;  // ready for the next launch on this slot
+  fold_rows_and_write(partials, n_rows, mask_sum, static_cast<double>(h.wv), static_cast<double>(h.we), sred, pr.out,
+                      pr.out_f32);
+  if (threadIdx.x == 0) pr.slot->ticket = 0u;  // ready for the next launch on this slot
 }
 
 __global__ void __launch_bounds__(256) loss_finalize_kernel(const unsigned char* __restrict__ ws, size_t slot_bytes,
@@ -296,108 +352,142 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const unsigned char*
                       out_f32 ? out_f32 + static_cast<size_t>(blockIdx.x) * 4 : nullptr);
 }
 
-template <bool VEC4>
-__global__ void __launch_bounds__(256) ppo_loss_kernel(const LossParams p) {
-  const LossHyperDev& h = p.h;
-#ifdef SRL_DEBUG_PHASES
-  const long long dbg0 = clock64();
-#endif
-  const RawStats raw = load_raw_stats(p);  // loads only; the math on them runs under the element loads
+__device__ __forceinline__ void unpack4(const float4 v, float (&a)[4]) { a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w; }
+
+// Sample-side forms
+constexpr int kDense = 0;   // separate leaves, lanes in policy order, 128-bit loads
+constexpr int kGather = 1;  // separate leaves through lane_idx (or any alignment)
+constexpr int kPack = 2;    // K2's float4 pack through lane_idx (or in order)
+
+// LANES = 4: a thread owns four adjacent policy-side lanes (n % 4 == 0, 16-byte aligned rows); LANES = 1: any shape.
+template <int LANES, int MODE, int NB>
+__global__ void __launch_bounds__(256) ppo_loss_kernel(const __grid_constant__ LossBatch<NB> b) {
+  const LossShared& s = b.s;
+  const LossHyperDev& h = s.h;
+  const Problem& pr = b.prob[blockIdx.y];
+  const RawStats raw = load_raw_stats(pr.norm_stats, pr.local_stats, s.popart);  // loads only
   Uniforms u;
   bool have_u = false;
-  const double mask_sum = raw.m_local;
-#ifdef SRL_DEBUG_PHASES
-  const long long dbg1 = clock64();
-#endif
   Acc acc;
-  const int n = p.n, T = p.T;
-  if (VEC4) {
-    // four consecutive lanes per thread: 128-bit loads/stores on the dense policy side; the sample side is either
-    // dense too (128-bit) or gathered through lane_idx (four independent 32-bit gathers per leaf, all in flight)
-    const int n4 = n >> 2;
-    const long long W = static_cast<long long>(T) * n4;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < W;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-      const int t = static_cast<int>(i / n4);
-      const int j = static_cast<int>(i - static_cast<long long>(t) * n4) << 2;
-      const long long op = t * p.ld_pol + j, og = t * p.ld_grad + j;
-      int4 c = make_int4(j, j + 1, j + 2, j + 3);
-      if (p.lane_idx) c = __ldg(reinterpret_cast<const int4*>(p.lane_idx + j));
-      const float4 nl = ldg_stream(reinterpret_cast<const float4*>(p.new_logp + op));
-      const float4 vp = ldg_stream(reinterpret_cast<const float4*>(p.v_pred + op));
-      const float4 en = ldg_stream(reinterpret_cast<const float4*>(p.entropy + op));
-      float4 ol, rt, ad, ov = make_float4(0.f, 0.f, 0.f, 0.f);
-      uint32_t rs;
-      const long long ob = t * p.ld_smp;
-      // a run of four consecutive, 4-aligned lanes (dense batches, or permutations of >= 4-lane blocks: agents of
-      // one environment, sector-aligned environment blocks) is fetched with one 128-bit load per leaf
-      const bool run4 = (c.y == c.x + 1) && (c.z == c.x + 2) && (c.w == c.x + 3) && ((c.x & 3) == 0) && p.smp_vec_ok;
-      if (run4) {
-        const long long os = ob + c.x;
-        ol = ldg_stream(reinterpret_cast<const float4*>(p.old_logp + os));
-        rt = ldg_stream(reinterpret_cast<const float4*>(p.ret + os));
-        ad = ldg_stream(reinterpret_cast<const float4*>(p.adv + os));
-        if (h.clip_value) ov = ldg_stream(reinterpret_cast<const float4*>(p.old_value + os));
-        rs = ldg_stream(reinterpret_cast<const uint32_t*>(p.reset_next + os));
+  const int T = s.T, n = s.n;
+  const int tile_lanes = blockDim.x * LANES;
+
+  for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x) {
+    const int rt_i = tile / s.col_tiles;
+    const int ct_i = tile - rt_i * s.col_tiles;
+    const int j = ct_i * tile_lanes + threadIdx.x * LANES;
+    if (j >= n) continue;
+    const int t0 = rt_i * s.rows_per_tile;
+    const int t1 = min(T, t0 + s.rows_per_tile);
+
+    // gather indices of this thread's lanes: once per tile
+    int c[LANES];
+    if (pr.lane_idx) {
+      if constexpr (LANES == 4) {
+        const int4 q = __ldg(reinterpret_cast<const int4*>(pr.lane_idx + j));
+        c[0] = q.x, c[1] = q.y, c[2] = q.z, c[3] = q.w;
       } else {
-        ol = make_float4(__ldg(p.old_logp + ob + c.x), __ldg(p.old_logp + ob + c.y), __ldg(p.old_logp + ob + c.z),
-                         __ldg(p.old_logp + ob + c.w));
-        rt = make_float4(__ldg(p.ret + ob + c.x), __ldg(p.ret + ob + c.y), __ldg(p.ret + ob + c.z), __ldg(p.ret + ob + c.w));
-        ad = make_float4(__ldg(p.adv + ob + c.x), __ldg(p.adv + ob + c.y), __ldg(p.adv + ob + c.z), __ldg(p.adv + ob + c.w));
-        if (h.clip_value)
-          ov = make_float4(__ldg(p.old_value + ob + c.x), __ldg(p.old_value + ob + c.y), __ldg(p.old_value + ob + c.z),
-                           __ldg(p.old_value + ob + c.w));
-        rs = static_cast<uint32_t>(__ldg(p.reset_next + ob + c.x)) | (static_cast<uint32_t>(__ldg(p.reset_next + ob + c.y)) << 8) |
-             (static_cast<uint32_t>(__ldg(p.reset_next + ob + c.z)) << 16) |
-             (static_cast<uint32_t>(__ldg(p.reset_next + ob + c.w)) << 24);
+        c[0] = __ldg(pr.lane_idx + j);
       }
-      if (!have_u) {
-        u = make_uniforms(raw, h.adv_eps);
-        have_u = true;
-      }
-      float4 glp, gv, ge;
-      element(h, u, nl.x, vp.x, en.x, ol.x, ov.x, rt.x, ad.x, rs & 0xffu, glp.x, gv.x, ge.x, acc);
-      element(h, u, nl.y, vp.y, en.y, ol.y, ov.y, rt.y, ad.y, (rs >> 8) & 0xffu, glp.y, gv.y, ge.y, acc);
-      element(h, u, nl.z, vp.z, en.z, ol.z, ov.z, rt.z, ad.z, (rs >> 16) & 0xffu, glp.z, gv.z, ge.z, acc);
-      element(h, u, nl.w, vp.w, en.w, ol.w, ov.w, rt.w, ad.w, (rs >> 24) & 0xffu, glp.w, gv.w, ge.w, acc);
-      stg_stream(reinterpret_cast<float4*>(p.g_logp + og), glp);
-      stg_stream(reinterpret_cast<float4*>(p.g_value + og), gv);
-      stg_stream(reinterpret_cast<float4*>(p.g_entropy + og), ge);
+    } else {
+#pragma unroll
+      for (int q = 0; q < LANES; ++q) c[q] = j + q;
     }
-  } else {
-    const long long W = static_cast<long long>(T) * n;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < W;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-      const int t = static_cast<int>(i / n);
-      const int j = static_cast<int>(i - static_cast<long long>(t) * n);
-      const int c = p.lane_idx ? __ldg(p.lane_idx + j) : j;  // minibatch gather fused into the load
-      const long long op = t * p.ld_pol + j, os = t * p.ld_smp + c, og = t * p.ld_grad + j;
-      const float nl = ldg_stream(p.new_logp + op), vp = ldg_stream(p.v_pred + op), en = ldg_stream(p.entropy + op);
-      const float ol = __ldg(p.old_logp + os), rt = __ldg(p.ret + os), ad = __ldg(p.adv + os);
-      const float ov = h.clip_value ? __ldg(p.old_value + os) : 0.f;
-      const uint32_t rs = __ldg(p.reset_next + os);
+    // a run of four consecutive, 4-aligned lanes (dense batches, agents of one environment, sector-aligned
+    // environment blocks) is fetched with one 128-bit load per leaf
+    bool run4 = false;
+    if constexpr (LANES == 4 && MODE == kGather)
+      run4 = s.smp_vec_ok && (c[1] == c[0] + 1) && (c[2] == c[0] + 2) && (c[3] == c[0] + 3) && ((c[0] & 3) == 0);
+
+    const float* p_nl = pr.new_logp + static_cast<long long>(t0) * s.ld_pol + j;
+    const float* p_vp = pr.v_pred + static_cast<long long>(t0) * s.ld_pol + j;
+    const float* p_en = pr.entropy + static_cast<long long>(t0) * s.ld_pol + j;
+    float* p_glp = pr.g_logp + static_cast<long long>(t0) * s.ld_grad + j;
+    float* p_gv = pr.g_value + static_cast<long long>(t0) * s.ld_grad + j;
+    float* p_ge = pr.g_entropy + static_cast<long long>(t0) * s.ld_grad + j;
+    long long ob = static_cast<long long>(t0) * s.ld_smp;
+
+#pragma unroll kLossUnroll
+    for (int t = t0; t < t1; ++t) {
+      float nl[LANES], vp[LANES], en[LANES], ol[LANES], ov[LANES], rt[LANES], ad[LANES];
+      bool valid[LANES];
+      // ---- policy side: dense ------------------------------------------------------------------------
+      if constexpr (LANES == 4) {
+        unpack4(ldg_stream(reinterpret_cast<const float4*>(p_nl)), nl);
+        unpack4(ldg_stream(reinterpret_cast<const float4*>(p_vp)), vp);
+        unpack4(ldg_stream(reinterpret_cast<const float4*>(p_en)), en);
+      } else {
+        nl[0] = ldg_stream(p_nl);
+        vp[0] = ldg_stream(p_vp);
+        en[0] = ldg_stream(p_en);
+      }
+      // ---- sample side -------------------------------------------------------------------------------
+      bool vec_rows = false;
+      if constexpr (LANES == 4) vec_rows = (MODE == kDense) || run4;
+      if constexpr (MODE == kPack) {
+#pragma unroll
+        for (int q = 0; q < LANES; ++q) {
+          const float4 k = __ldg(s.pack + ob + c[q]);
+          ol[q] = k.x;
+          ov[q] = k.y;
+          rt[q] = k.z;
+          ad[q] = k.w;
+          valid[q] = (k.w == k.w);  // K2 stores NaN in the advantage slot of masked transitions
+        }
+      } else if (vec_rows) {
+        if constexpr (LANES == 4) {
+          const long long os = ob + c[0];
+          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.old_logp + os)), ol);
+          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.ret + os)), rt);
+          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.adv + os)), ad);
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (h.clip_value) o = ldg_stream(reinterpret_cast<const float4*>(s.old_value + os));
+          unpack4(o, ov);
+          const uint32_t m = ldg_stream(reinterpret_cast<const uint32_t*>(s.reset_next + os));
+#pragma unroll
+          for (int q = 0; q < LANES; ++q) valid[q] = ((m >> (8 * q)) & 0xffu) == 0u;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < LANES; ++q) {
+          const long long os = ob + c[q];
+          ol[q] = __ldg(s.old_logp + os);
+          rt[q] = __ldg(s.ret + os);
+          ad[q] = __ldg(s.adv + os);
+          ov[q] = h.clip_value ? __ldg(s.old_value + os) : 0.f;
+          valid[q] = __ldg(s.reset_next + os) == 0;
+        }
+      }
       if (!have_u) {
         u = make_uniforms(raw, h.adv_eps);
         have_u = true;
       }
-      float glp, gv, ge;
-      element(h, u, nl, vp, en, ol, ov, rt, ad, rs, glp, gv, ge, acc);
-      stg_stream(p.g_logp + og, glp);
-      stg_stream(p.g_value + og, gv);
-      stg_stream(p.g_entropy + og, ge);
+      float glp[LANES], gv[LANES], ge[LANES];
+      RowSums rs;
+#pragma unroll
+      for (int q = 0; q < LANES; ++q)
+        element(h, u, nl[q], vp[q], en[q], ol[q], ov[q], rt[q], ad[q], valid[q], glp[q], gv[q], ge[q], rs);
+      acc.add(rs);
+      if constexpr (LANES == 4) {
+        stg_stream(reinterpret_cast<float4*>(p_glp), make_float4(glp[0], glp[1], glp[2], glp[3]));
+        stg_stream(reinterpret_cast<float4*>(p_gv), make_float4(gv[0], gv[1], gv[2], gv[3]));
+        stg_stream(reinterpret_cast<float4*>(p_ge), make_float4(ge[0], ge[1], ge[2], ge[3]));
+      } else {
+        stg_stream(p_glp, glp[0]);
+        stg_stream(p_gv, gv[0]);
+        stg_stream(p_ge, ge[0]);
+      }
+      p_nl += s.ld_pol;
+      p_vp += s.ld_pol;
+      p_en += s.ld_pol;
+      p_glp += s.ld_grad;
+      p_gv += s.ld_grad;
+      p_ge += s.ld_grad;
+      ob += s.ld_smp;
     }
   }
-#ifdef SRL_DEBUG_PHASES
-  const long long dbg2 = clock64() + (acc.pl == 123.0);
-#endif
-  reduce_and_finalize(p, acc, mask_sum);
-#ifdef SRL_DEBUG_PHASES
-  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
-    printf("loss block %d/%d (%d thr): uniforms %lld  elements %lld  reduce %lld cycles\n", blockIdx.x, gridDim.x, blockDim.x,
-           dbg1 - dbg0, dbg2 - dbg1, clock64() - dbg2);
-#endif
+  reduce_and_finalize(pr, h, acc, raw.m_local, blockIdx.x, gridDim.x);
 }
-
 
 // ---- K4b: the same loss starting from the actor head's logits -----------------------------------
 // (actor_critic_policy.py:303-324: Categorical(logits=slice).log_prob / .entropy per head, summed.)
@@ -405,7 +495,8 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const LossParams p) {
 // it is staged through shared memory with coalesced loads (row stride sumK+1 words: conflict-free
 // per-thread row walks), turned into d loss / d logits in place, and streamed back out coalesced.
 struct LogitsParams {
-  LossParams c;           // policy-side pointers new_logp/entropy/g_logp/g_entropy are unused here
+  LossShared s;
+  Problem pr;             // new_logp / entropy / g_logp / g_entropy are unused here
   const float* logits;    // [T*n, SK]
   const int32_t* action;  // [T*n, heads]
   float* g_logits;        // [T*n, SK]
@@ -415,12 +506,12 @@ struct LogitsParams {
   int head_size[SRL_MAX_HEADS];
 };
 
-__global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const LogitsParams q) {
+__global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const __grid_constant__ LogitsParams q) {
   extern __shared__ float srow[];  // [256][SK + 1]
-  const LossParams& p = q.c;
+  const LossShared& p = q.s;
+  const Problem& pr = q.pr;
   const LossHyperDev& h = p.h;
-  const RawStats raw = load_raw_stats(p);
-  const double mask_sum = raw.m_local;
+  const RawStats raw = load_raw_stats(pr.norm_stats, pr.local_stats, p.popart);
   const Uniforms u = make_uniforms(raw, h.adv_eps);
   Acc acc;
   const int SK = q.SK, stride = SK + 1;
@@ -440,7 +531,7 @@ __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const LogitsParams
       const long long i = i0 + threadIdx.x;
       const int t = static_cast<int>(i / p.n);
       const int j = static_cast<int>(i - static_cast<long long>(t) * p.n);
-      const int c = p.lane_idx ? p.lane_idx[j] : j;
+      const int c = pr.lane_idx ? pr.lane_idx[j] : j;
       const long long os = t * p.ld_smp + c;
       float* z = srow + threadIdx.x * stride;
       float lse[SRL_MAX_HEADS], hent[SRL_MAX_HEADS];
@@ -470,13 +561,15 @@ __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const LogitsParams
           off += K;
         }
       }
-      const float vp = ldg_stream(p.v_pred + i);
+      const float vp = ldg_stream(pr.v_pred + i);
       const float ol = __ldg(p.old_logp + os), rt = __ldg(p.ret + os), ad = __ldg(p.adv + os);
       const float ov = h.clip_value ? __ldg(p.old_value + os) : 0.f;
-      const uint32_t rs = __ldg(p.reset_next + os);
+      const bool valid = __ldg(p.reset_next + os) == 0;
       float g_lp, g_v, g_en;
-      element(h, u, logp, vp, ent, ol, ov, rt, ad, rs, g_lp, g_v, g_en, acc);
-      stg_stream(p.g_value + i, g_v);
+      RowSums rs;
+      element(h, u, logp, vp, ent, ol, ov, rt, ad, valid, g_lp, g_v, g_en, rs);
+      acc.add(rs);
+      stg_stream(pr.g_value + i, g_v);
       if (q.logp_out) q.logp_out[i] = logp;
       if (q.entropy_out) q.entropy_out[i] = ent;
       off = 0;
@@ -502,7 +595,91 @@ __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const LogitsParams
     }
     __syncthreads();
   }
-  reduce_and_finalize(p, acc, mask_sum);
+  reduce_and_finalize(pr, h, acc, raw.m_local, blockIdx.x, gridDim.x);
+}
+
+int fill_loss_hyper(const srl_ppo_hyper* hyper, const double* popart_mean_std, LossHyperDev& h) {
+  SRL_REQUIRE(hyper != nullptr, SRL_ERR_INVALID_ARG, "ppo loss: null hyper pointer");
+  SRL_REQUIRE(hyper->value_loss >= SRL_VL_MSE && hyper->value_loss <= SRL_VL_SMOOTHL1, SRL_ERR_INVALID_ARG,
+              "ppo loss: unknown value_loss %d (0 mse, 1 huber, 2 smoothl1)", hyper->value_loss);
+  SRL_REQUIRE(!(hyper->normalize_old_value && popart_mean_std == nullptr), SRL_ERR_INVALID_ARG,
+              "ppo loss: normalize_old_value needs popart statistics");
+  h.clip_lo = static_cast<float>(1.0 - hyper->eps_clip);  // python: 1 - self.eps_clip, then cast by torch.clamp
+  h.clip_hi = static_cast<float>(1.0 + hyper->eps_clip);
+  h.veps = static_cast<float>(hyper->value_eps_clip);
+  h.c_clip = static_cast<float>(hyper->c_clip);
+  h.wv = static_cast<float>(hyper->value_loss_weight);
+  h.we = static_cast<float>(hyper->entropy_bonus_weight);
+  h.vl_param = static_cast<float>(hyper->vl_param);
+  h.adv_eps = hyper->adv_eps;
+  h.value_loss = hyper->value_loss;
+  h.clip_value = hyper->clip_value;
+  h.dual_clip = hyper->dual_clip;
+  h.normalize_old_value = hyper->normalize_old_value;
+  return SRL_OK;
+}
+
+template <int LANES, int MODE, int NB>
+struct LossLauncher {
+  // CTAs of `threads` threads one SM holds (register-limited), asked once per device and block size
+  static int resident(int threads) {
+    static int cached[64][2] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 2;
+    int& c = cached[dev][threads >= 256 ? 1 : 0];
+    if (c == 0) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ppo_loss_kernel<LANES, MODE, NB>, threads, 0) != cudaSuccess ||
+          n < 1)
+        n = 1;
+      c = n;
+    }
+    return c;
+  }
+
+  static int launch(LossBatch<NB>& b, int n_problems, cudaStream_t st) {
+    LossShared& s = b.s;
+    const int per_row = (s.n + LANES - 1) / LANES;  // threads one row needs
+    const int threads = per_row <= 128 ? 128 : 256;
+    s.col_tiles = (per_row + threads - 1) / threads;
+    const long long capacity = static_cast<long long>(sm_count()) * resident(threads);
+    // rows per tile: the tallest tile (index loads amortised over more rows) whose tile count still fills the
+    // machine about as evenly as the best choice does
+    int best_rows = 1;
+    double best_eff = -1.0;
+    for (int rows = 8; rows >= 1; rows >>= 1) {
+      const long long tiles = static_cast<long long>(s.col_tiles) * ((s.T + rows - 1) / rows) * n_problems;
+      const long long waves = (tiles + capacity - 1) / capacity;
+      const double eff = static_cast<double>(tiles) / static_cast<double>(waves * capacity);
+      if (eff > best_eff + 0.05) {
+        best_eff = eff;
+        best_rows = rows;
+      }
+    }
+    s.rows_per_tile = best_rows;
+    const long long tiles_pp = static_cast<long long>(s.col_tiles) * ((s.T + best_rows - 1) / best_rows);
+    SRL_REQUIRE(tiles_pp < (1ll << 31), SRL_ERR_UNSUPPORTED, "ppo loss: problem too large (%lld tiles)", tiles_pp);
+    s.n_tiles = static_cast<int>(tiles_pp);
+    long long gx = (capacity + n_problems - 1) / n_problems;  // CTAs per problem when the grid is persistent
+    if (gx > tiles_pp) gx = tiles_pp;
+    if (gx > kMaxGrid) gx = kMaxGrid;
+    if (gx < 1) gx = 1;
+    const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(n_problems));
+    ppo_loss_kernel<LANES, MODE, NB><<<grid, threads, 0, st>>>(b);
+    SRL_CUDA(cudaGetLastError());
+    return SRL_OK;
+  }
+};
+
+template <int NB>
+int launch_batch(LossBatch<NB>& b, int n_problems, bool lanes4, int mode, cudaStream_t st) {
+  if (lanes4) {
+    if (mode == kDense) return LossLauncher<4, kDense, NB>::launch(b, n_problems, st);
+    if (mode == kGather) return LossLauncher<4, kGather, NB>::launch(b, n_problems, st);
+    return LossLauncher<4, kPack, NB>::launch(b, n_problems, st);
+  }
+  if (mode == kPack) return LossLauncher<1, kPack, NB>::launch(b, n_problems, st);
+  return LossLauncher<1, kGather, NB>::launch(b, n_problems, st);
 }
 
 }  // namespace
@@ -526,28 +703,96 @@ extern "C" int srl_ppo_loss_finalize(const void* workspace, size_t slot_bytes, i
   return SRL_OK;
 }
 
-namespace srl {
-int fill_loss_hyper(const srl_ppo_hyper* hyper, const double* popart_mean_std, LossHyperDev& h) {
-  SRL_REQUIRE(hyper != nullptr, SRL_ERR_INVALID_ARG, "ppo loss: null hyper pointer");
-  SRL_REQUIRE(hyper->value_loss >= SRL_VL_MSE && hyper->value_loss <= SRL_VL_SMOOTHL1, SRL_ERR_INVALID_ARG,
-              "ppo loss: unknown value_loss %d (0 mse, 1 huber, 2 smoothl1)", hyper->value_loss);
-  SRL_REQUIRE(!(hyper->normalize_old_value && popart_mean_std == nullptr), SRL_ERR_INVALID_ARG,
-              "ppo loss: normalize_old_value needs popart statistics");
-  h.clip_lo = static_cast<float>(1.0 - hyper->eps_clip);  // python: 1 - self.eps_clip, then cast by torch.clamp
-  h.clip_hi = static_cast<float>(1.0 + hyper->eps_clip);
-  h.veps = static_cast<float>(hyper->value_eps_clip);
-  h.c_clip = static_cast<float>(hyper->c_clip);
-  h.wv = static_cast<float>(hyper->value_loss_weight);
-  h.we = static_cast<float>(hyper->entropy_bonus_weight);
-  h.vl_param = static_cast<float>(hyper->vl_param);
-  h.adv_eps = hyper->adv_eps;
-  h.value_loss = hyper->value_loss;
-  h.clip_value = hyper->clip_value;
-  h.dual_clip = hyper->dual_clip;
-  h.normalize_old_value = hyper->normalize_old_value;
+extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, int n_problems, int64_t ld_pol,
+                                            int64_t ld_grad, const float* old_logp, const float* old_value,
+                                            const float* ret, const float* adv, const uint8_t* on_reset_next,
+                                            int64_t ld_smp, const float* pack, int T, int n,
+                                            const double* popart_mean_std, const srl_ppo_hyper* hyper,
+                                            size_t workspace_bytes, srl_stream_t stream) {
+  using namespace srl;
+  SRL_REQUIRE(n_problems >= 0, SRL_ERR_INVALID_ARG, "srl_ppo_loss_fwd_bwd_batched: negative problem count");
+  if (n_problems == 0) return SRL_OK;
+  SRL_REQUIRE(problems != nullptr, SRL_ERR_INVALID_ARG, "srl_ppo_loss_fwd_bwd_batched: null problem table");
+  SRL_REQUIRE(T >= 1 && n >= 1, SRL_ERR_INVALID_ARG, "srl_ppo_loss_fwd_bwd: need T >= 1 and n >= 1 (got %d, %d)", T, n);
+  SRL_REQUIRE(workspace_bytes >= srl_ppo_loss_workspace_bytes(T, n), SRL_ERR_INVALID_ARG,
+              "srl_ppo_loss_fwd_bwd: workspace too small (%zu bytes)", workspace_bytes);
+  LossShared s;
+  int rc = fill_loss_hyper(hyper, popart_mean_std, s.h);
+  if (rc != SRL_OK) return rc;
+  if (pack == nullptr) {
+    SRL_REQUIRE(old_logp && ret && adv && on_reset_next, SRL_ERR_INVALID_ARG, "srl_ppo_loss_fwd_bwd: null pointer");
+    SRL_REQUIRE(!(s.h.clip_value && old_value == nullptr), SRL_ERR_INVALID_ARG,
+                "srl_ppo_loss_fwd_bwd: clip_value needs old_value");
+  } else {
+    SRL_REQUIRE(aligned(pack, 16), SRL_ERR_INVALID_ARG, "srl_ppo_loss_fwd_bwd: pack must be 16-byte aligned");
+  }
+  bool any_idx = false, all_idx = true;
+  bool dense_ok = (n % 4 == 0) && (ld_pol % 4 == 0) && (ld_grad % 4 == 0);
+  for (int k = 0; k < n_problems; ++k) {
+    const srl_loss_problem& q = problems[k];
+    SRL_REQUIRE(q.new_logp && q.v_pred && q.entropy && q.g_logp && q.g_value && q.g_entropy && q.norm_stats &&
+                    q.local_stats && q.workspace,
+                SRL_ERR_INVALID_ARG, "srl_ppo_loss_fwd_bwd: null pointer");
+    any_idx = any_idx || q.lane_idx != nullptr;
+    all_idx = all_idx && q.lane_idx != nullptr;
+    dense_ok = dense_ok && aligned(q.new_logp, 16) && aligned(q.v_pred, 16) && aligned(q.entropy, 16) &&
+               aligned(q.g_logp, 16) && aligned(q.g_value, 16) && aligned(q.g_entropy, 16) &&
+               (q.lane_idx == nullptr || aligned(q.lane_idx, 16));
+  }
+  SRL_REQUIRE(any_idx == all_idx, SRL_ERR_INVALID_ARG,
+              "srl_ppo_loss_fwd_bwd_batched: either every problem has a lane_idx or none has");
+  SRL_REQUIRE(ld_pol >= n && ld_grad >= n && ld_smp >= (any_idx ? 1 : n), SRL_ERR_INVALID_ARG,
+              "srl_ppo_loss_fwd_bwd: row strides smaller than the row");
+  s.old_logp = old_logp;
+  s.old_value = old_value;
+  s.ret = ret;
+  s.adv = adv;
+  s.reset_next = on_reset_next;
+  s.pack = reinterpret_cast<const float4*>(pack);
+  s.popart = popart_mean_std;
+  s.ld_pol = ld_pol;
+  s.ld_grad = ld_grad;
+  s.ld_smp = ld_smp;
+  s.T = T;
+  s.n = n;
+  const bool smp_vec = pack == nullptr && (ld_smp % 4 == 0) && aligned(old_logp, 16) && aligned(ret, 16) &&
+                       aligned(adv, 16) && (!s.h.clip_value || aligned(old_value, 16)) && aligned(on_reset_next, 4);
+  s.smp_vec_ok = smp_vec ? 1 : 0;
+  const int mode = pack ? kPack : ((!any_idx && dense_ok && smp_vec) ? kDense : kGather);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto fill = [](Problem& p, const srl_loss_problem& q) {
+    p.new_logp = q.new_logp;
+    p.v_pred = q.v_pred;
+    p.entropy = q.entropy;
+    p.lane_idx = q.lane_idx;
+    p.norm_stats = q.norm_stats;
+    p.local_stats = q.local_stats;
+    p.g_logp = q.g_logp;
+    p.g_value = q.g_value;
+    p.g_entropy = q.g_entropy;
+    p.out = q.out;
+    p.out_f32 = q.out_f32;
+    p.slot = reinterpret_cast<SlotHeader*>(q.workspace);
+  };
+  for (int k0 = 0; k0 < n_problems;) {
+    const int nb = n_problems - k0 < SRL_MAX_LOSS_BATCH ? n_problems - k0 : SRL_MAX_LOSS_BATCH;
+    if (nb == 1) {
+      LossBatch<1> b;
+      b.s = s;
+      fill(b.prob[0], problems[k0]);
+      rc = launch_batch<1>(b, 1, dense_ok, mode, st);
+    } else {
+      LossBatch<SRL_MAX_LOSS_BATCH> b;
+      b.s = s;
+      for (int k = 0; k < nb; ++k) fill(b.prob[k], problems[k0 + k]);
+      for (int k = nb; k < SRL_MAX_LOSS_BATCH; ++k) b.prob[k] = b.prob[0];
+      rc = launch_batch<SRL_MAX_LOSS_BATCH>(b, nb, dense_ok, mode, st);
+    }
+    if (rc != SRL_OK) return rc;
+    k0 += nb;
+  }
   return SRL_OK;
 }
-}  // namespace srl
 
 extern "C" int srl_ppo_loss_fwd_bwd(const float* new_logp, const float* v_pred, const float* entropy, int64_t ld_pol,
                                     const float* old_logp, const float* old_value, const float* ret,
@@ -557,69 +802,21 @@ extern "C" int srl_ppo_loss_fwd_bwd(const float* new_logp, const float* v_pred, 
                                     const srl_ppo_hyper* hyper, float* g_logp, float* g_value, float* g_entropy,
                                     int64_t ld_grad, double* out, float* out_f32, void* workspace,
                                     size_t workspace_bytes, srl_stream_t stream) {
-  using namespace srl;
-  SRL_REQUIRE(T >= 1 && n >= 1, SRL_ERR_INVALID_ARG, "srl_ppo_loss_fwd_bwd: need T >= 1 and n >= 1 (got %d, %d)", T, n);
-  SRL_REQUIRE(new_logp && v_pred && entropy && old_logp && ret && adv && on_reset_next && g_logp && g_value &&
-                  g_entropy && norm_stats && local_stats && workspace,
-              SRL_ERR_INVALID_ARG, "srl_ppo_loss_fwd_bwd: null pointer");
-  SRL_REQUIRE(ld_pol >= n && ld_grad >= n && ld_smp >= (lane_idx ? 1 : n), SRL_ERR_INVALID_ARG,
-              "srl_ppo_loss_fwd_bwd: row strides smaller than the row");
-  SRL_REQUIRE(workspace_bytes >= srl_ppo_loss_workspace_bytes(T, n), SRL_ERR_INVALID_ARG,
-              "srl_ppo_loss_fwd_bwd: workspace too small (%zu bytes)", workspace_bytes);
-  LossParams p;
-  int rc = fill_loss_hyper(hyper, popart_mean_std, p.h);
-  if (rc != SRL_OK) return rc;
-  SRL_REQUIRE(!(p.h.clip_value && old_value == nullptr), SRL_ERR_INVALID_ARG,
-              "srl_ppo_loss_fwd_bwd: clip_value needs old_value");
-  p.new_logp = new_logp;
-  p.v_pred = v_pred;
-  p.entropy = entropy;
-  p.ld_pol = ld_pol;
-  p.old_logp = old_logp;
-  p.old_value = old_value;
-  p.ret = ret;
-  p.adv = adv;
-  p.reset_next = on_reset_next;
-  p.ld_smp = ld_smp;
-  p.lane_idx = lane_idx;
-  p.T = T;
-  p.n = n;
-  p.norm_stats = norm_stats;
-  p.local_stats = local_stats;
-  p.popart = popart_mean_std;
-  p.g_logp = g_logp;
-  p.g_value = g_value;
-  p.g_entropy = g_entropy;
-  p.ld_grad = ld_grad;
-  p.out = out;
-  p.out_f32 = out_f32;
-  p.slot = reinterpret_cast<SlotHeader*>(workspace);
-  p.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + kPartialsOffset);
-
-  // four lanes per thread whenever the dense side allows 128-bit accesses; the sample side may be gathered
-  const bool dense_ok = (n % 4 == 0) && (ld_pol % 4 == 0) && (ld_grad % 4 == 0) && aligned(new_logp, 16) &&
-                        aligned(v_pred, 16) && aligned(entropy, 16) && aligned(g_logp, 16) && aligned(g_value, 16) &&
-                        aligned(g_entropy, 16);
-  const bool smp_vec = (ld_smp % 4 == 0) && aligned(old_logp, 16) && aligned(ret, 16) && aligned(adv, 16) &&
-                       (!p.h.clip_value || aligned(old_value, 16)) && aligned(on_reset_next, 4);
-  p.smp_vec_ok = smp_vec ? 1 : 0;
-  const bool use_vec4 = dense_ok && (lane_idx == nullptr || aligned(lane_idx, 16));
-  const int sms = sm_count();
-  const long long W = static_cast<long long>(T) * (use_vec4 ? n / 4 : n);
-  // The kernel is latency-bound at minibatch sizes (profiles/r1_notes.md): what matters is how many elements
-  // are in flight per SM, so threads carry four elements and CTAs stay small enough for several launches to
-  // share the machine when the caller runs them on parallel streams / graph branches.
-  const int threads = (W <= static_cast<long long>(sms) * 256) ? 128 : 256;
-  long long grid = (W + threads - 1) / threads;
-  const long long cap = static_cast<long long>(sms) * 8 < kMaxGrid ? static_cast<long long>(sms) * 8 : kMaxGrid;
-  if (grid > cap) grid = cap;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (use_vec4)
-    ppo_loss_kernel<true><<<static_cast<int>(grid), threads, 0, st>>>(p);
-  else
-    ppo_loss_kernel<false><<<static_cast<int>(grid), threads, 0, st>>>(p);
-  SRL_CUDA(cudaGetLastError());
-  return SRL_OK;
+  srl_loss_problem q;
+  q.new_logp = new_logp;
+  q.v_pred = v_pred;
+  q.entropy = entropy;
+  q.lane_idx = lane_idx;
+  q.norm_stats = norm_stats;
+  q.local_stats = local_stats;
+  q.g_logp = g_logp;
+  q.g_value = g_value;
+  q.g_entropy = g_entropy;
+  q.out = out;
+  q.out_f32 = out_f32;
+  q.workspace = workspace;
+  return srl_ppo_loss_fwd_bwd_batched(&q, 1, ld_pol, ld_grad, old_logp, old_value, ret, adv, on_reset_next, ld_smp,
+                                      nullptr, T, n, popart_mean_std, hyper, workspace_bytes, stream);
 }
 
 extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* action, const int32_t* head_sizes_host,
@@ -642,9 +839,9 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
   SRL_REQUIRE(workspace_bytes >= srl_ppo_loss_workspace_bytes(T, n), SRL_ERR_INVALID_ARG,
               "srl_ppo_loss_from_logits: workspace too small (%zu bytes)", workspace_bytes);
   LogitsParams q;
-  int rc = fill_loss_hyper(hyper, popart_mean_std, q.c.h);
+  int rc = fill_loss_hyper(hyper, popart_mean_std, q.s.h);
   if (rc != SRL_OK) return rc;
-  SRL_REQUIRE(!(q.c.h.clip_value && old_value == nullptr), SRL_ERR_INVALID_ARG,
+  SRL_REQUIRE(!(q.s.h.clip_value && old_value == nullptr), SRL_ERR_INVALID_ARG,
               "srl_ppo_loss_from_logits: clip_value needs old_value");
   int sk = 0;
   for (int i = 0; i < SRL_MAX_HEADS; ++i) {
@@ -662,30 +859,32 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
   q.g_logits = g_logits;
   q.logp_out = logp_out;
   q.entropy_out = entropy_out;
-  LossParams& p = q.c;
-  p.new_logp = p.entropy = nullptr;
-  p.v_pred = v_pred;
-  p.ld_pol = n;
+  LossShared& p = q.s;
   p.old_logp = old_logp;
   p.old_value = old_value;
   p.ret = ret;
   p.adv = adv;
   p.reset_next = on_reset_next;
+  p.pack = nullptr;
+  p.popart = popart_mean_std;
+  p.ld_pol = n;
+  p.ld_grad = n;
   p.ld_smp = ld_smp;
-  p.lane_idx = lane_idx;
   p.T = T;
   p.n = n;
-  p.norm_stats = norm_stats;
-  p.local_stats = local_stats;
-  p.popart = popart_mean_std;
-  p.g_logp = p.g_entropy = nullptr;
+  p.rows_per_tile = p.col_tiles = p.n_tiles = 0;
   p.smp_vec_ok = 0;
-  p.g_value = g_value;
-  p.ld_grad = n;
-  p.out = out;
-  p.out_f32 = out_f32;
-  p.slot = reinterpret_cast<SlotHeader*>(workspace);
-  p.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + kPartialsOffset);
+  Problem& pr = q.pr;
+  pr.new_logp = pr.entropy = nullptr;
+  pr.v_pred = v_pred;
+  pr.lane_idx = lane_idx;
+  pr.norm_stats = norm_stats;
+  pr.local_stats = local_stats;
+  pr.g_logp = pr.g_entropy = nullptr;
+  pr.g_value = g_value;
+  pr.out = out;
+  pr.out_f32 = out_f32;
+  pr.slot = reinterpret_cast<SlotHeader*>(workspace);
   static bool opted_in[64] = {};
   int dev = 0;
   SRL_CUDA(cudaGetDevice(&dev));

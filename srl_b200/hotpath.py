@@ -48,7 +48,7 @@ class HotPath:
                  bootstrap_steps: int = 1, burn_in_steps: int = 0, epochs: int = 1, minibatches: int = 1, seed: int = 0,
                  popart: bool = False, popart_beta: float = 0.99999, popart_eps: float = 1e-5,
                  device: Optional[torch.device] = None, process_group=None, fuse_gather: bool = True,
-                 graph_branches: int = 16, shuffle_block: int = 1):
+                 graph_branches: int = 16, shuffle_block: int = 1, use_pack: bool = True, batch_losses: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("srl_b200.HotPath needs a CUDA device (there is no CPU path)")
         if bootstrap_steps < 1:
@@ -75,6 +75,11 @@ class HotPath:
         self.pg = process_group
         self.fuse_gather = fuse_gather
         self.graph_branches = max(1, int(graph_branches))
+        self.batch_losses = bool(batch_losses)
+        # batched launches finalise their loss scalars themselves (last CTA of each minibatch); the per-minibatch
+        # launches of the trainer path defer to finalize()
+        self._immediate = self.batch_losses and (fuse_gather or minibatches == 1)
+        self.pack_valid = False
         self.step_count = 0
 
         dev, N = self.device, self.N
@@ -88,6 +93,10 @@ class HotPath:
         self.local_stats = torch.zeros((G, SRL_LANE_PART), dtype=torch.float64, device=dev)
         self.global_stats = self.local_stats if process_group is None else torch.zeros_like(self.local_stats)
         self.perm = torch.empty((epochs, N), dtype=torch.int32, device=dev) if minibatches > 1 else None
+        # K2's pack: the loss's sample side as one 16-byte item per transition (only a permuted minibatch gathers
+        # lane by lane, so only then is it worth its extra 16 B/transition of GAE writes)
+        self.pack = f32(L, N, 4) if (minibatches > 1 and fuse_gather and use_pack) else None
+        self._perm_stream = torch.cuda.Stream(device=dev) if minibatches > 1 else None
         self.popart_state = torch.zeros(4, dtype=torch.float64, device=dev)
         self.popart_ms = torch.tensor([0.0, 0.1, 0.0, 0.1], dtype=torch.float64, device=dev)  # sqrt(1e-2) floor
         n = self.n_mb
@@ -145,11 +154,18 @@ class HotPath:
         return moved
 
     # ------------------------------------------------------------------------------------------
-    def advantages(self, cached: bool = False, vtrace_new_logp: Optional[torch.Tensor] = None) -> None:
+    def advantages(self, cached: bool = False, vtrace_new_logp: Optional[torch.Tensor] = None,
+                   permute: bool = True) -> None:
         """K2 (or, for cached adv/ret already in self.adv / self.ret, only their per-lane sums), then all epochs'
         permutations in one launch, then the whole statistics table in one launch (+ the one small all-reduce
         when distributed)."""
         lf = self.leaf
+        main = torch.cuda.current_stream()
+        if self.minibatches > 1 and permute:  # the permutations do not depend on the scan: parallel branch
+            self._perm_stream.wait_stream(main)
+            with torch.cuda.stream(self._perm_stream):
+                self.permute()
+        self.pack_valid = False
         if cached:
             ops.lane_stats(self.adv, self.ret, lf["done"], lf["truncated"], lf["on_reset"], self.row_lo, self.row_hi,
                            lane_part=self.lane_part)
@@ -157,11 +173,15 @@ class HotPath:
             kw = {}
             if vtrace_new_logp is not None:  # V-trace: rho_t from the current policy (mappo.py:129-132)
                 kw = dict(vtrace_new_logp=vtrace_new_logp, vtrace_old_logp=lf["old_logp"])
+            elif self.pack is not None:
+                kw = dict(old_logp=lf["old_logp"], pack=self.pack)
+                self.pack_valid = True
             ops.gae_scan(lf["reward"], lf["value"], lf["done"], lf["truncated"], lf["on_reset"], self.gamma, self.lmbda,
                          row_lo=self.row_lo, row_hi=self.row_hi, popart_mean_std=self.popart_mean_std(), adv=self.adv,
                          ret=self.ret, lane_part=self.lane_part, **kw)
         if self.minibatches > 1:
-            self.permute()
+            if permute:
+                main.wait_stream(self._perm_stream)
             ops.group_stats(self.lane_part, idx=self.perm.view(-1), groups=self.epochs * self.minibatches, per=self.n_mb,
                             out=self.local_stats, whole_first=True)
         else:
@@ -203,12 +223,39 @@ class HotPath:
                               (self.adv.unsqueeze(-1), m["adv"].unsqueeze(-1)),
                               (lf["on_reset"].unsqueeze(-1), m["on_reset"].unsqueeze(-1))], idx)
             olp, ov, rt, ad, rs, idx = m["old_logp"], m["value"], m["ret"], m["adv"], m["on_reset"], None
+        elif idx is not None and self.pack is not None and self.pack_valid:
+            ops.ppo_loss_batched([self._problem(e, j, new_logp, v_pred, entropy, deferred=True)], None, None, None, None,
+                                 None, self.hyper, popart_mean_std=self.popart_mean_std(), pack=self.pack[lo:hi])
+            return self.grads[e][j] + (None, None)
         else:
             olp, ov, rt, ad, rs = lf["old_logp"], lf["value"], self.ret, self.adv, lf["on_reset"]
         return ops.ppo_loss_fwd_bwd(new_logp, v_pred, entropy, olp[lo:hi], ov[lo:hi], rt[lo:hi], ad[lo:hi],
                                     rs[lo + 1:hi + 1], self.global_stats[row], self.hyper,
                                     local_stats=self.local_stats[row], popart_mean_std=self.popart_mean_std(),
                                     lane_idx=idx, grads=self.grads[e][j], workspace=self.workspace[k], defer=True)
+
+    def _problem(self, e: int, j: int, new_logp, v_pred, entropy, deferred: bool) -> dict:
+        row = self.stats_row(e, j)
+        k = e * self.minibatches + j
+        q = dict(new_logp=new_logp, v_pred=v_pred, entropy=entropy, lane_idx=self.minibatch_lanes(e, j),
+                 norm_stats=self.global_stats[row], local_stats=self.local_stats[row], grads=self.grads[e][j],
+                 workspace=self.workspace[k])
+        if not deferred:
+            q.update(out=self.out[k], out_f32=self.out_f32[k])
+        return q
+
+    def loss_batch(self, pairs, pol) -> None:
+        """K4 for several (epoch, minibatch) pairs in ONE launch, loss scalars + stats finalised by the last CTA of
+        each minibatch (no separate finalize launch).  pol[e][j] = (new_logp, v_pred, entropy)."""
+        lo, hi = self.row_lo, self.row_hi
+        lf = self.leaf
+        probs = [self._problem(e, j, *pol[e][j], deferred=False) for e, j in pairs]
+        if self.minibatches > 1 and self.pack is not None and self.pack_valid:
+            ops.ppo_loss_batched(probs, None, None, None, None, None, self.hyper,
+                                 popart_mean_std=self.popart_mean_std(), pack=self.pack[lo:hi])
+        else:
+            ops.ppo_loss_batched(probs, lf["old_logp"][lo:hi], lf["value"][lo:hi], self.ret[lo:hi], self.adv[lo:hi],
+                                 lf["on_reset"][lo + 1:hi + 1], self.hyper, popart_mean_std=self.popart_mean_std())
 
     def finalize(self) -> None:
         """One launch: fold every minibatch's partial rows into self.out / self.out_f32 (loss scalars + stats)."""
@@ -220,6 +267,14 @@ class HotPath:
         spread round-robin over side streams (fork/join around each epoch): under CUDA-graph capture this
         becomes parallel graph branches, so the small per-minibatch kernels overlap instead of queueing.
         (PopArt re-normalises between epochs, hence the join per epoch.)"""
+        if self._immediate:
+            if self.popart:  # K3 re-normalises between epochs: one launch per epoch
+                for e in range(self.epochs):
+                    self.update_popart()
+                    self.loss_batch([(e, j) for j in range(self.minibatches)], pol)
+            else:  # every (epoch, minibatch) is independent: one launch
+                self.loss_batch([(e, j) for e in range(self.epochs) for j in range(self.minibatches)], pol)
+            return
         main = torch.cuda.current_stream()
         if branches > 1 and not hasattr(self, "_side"):
             self._side = [torch.cuda.Stream(device=self.device) for _ in range(branches)]
@@ -310,6 +365,13 @@ class HotPath:
         n = 2  # gae_scan + group_stats
         if self.minibatches > 1:
             n += 1  # all epochs' permutations
+        if self._immediate:
+            per_launch = 32  # SRL_MAX_LOSS_BATCH
+            if self.popart:
+                n += self.epochs * (1 + -(-self.minibatches // per_launch))
+            else:
+                n += -(-(self.epochs * self.minibatches) // per_launch)
+            return n
         per_loss = 1 if (self.fuse_gather or self.minibatches == 1) else 2
         n += self.epochs * self.minibatches * per_loss
         n += 1  # loss_finalize
@@ -372,16 +434,14 @@ class HotPath:
             if use_graph:
                 graphs["epoch"][e].replay()
             else:
-                if self.popart:
-                    self.update_popart()
-                for j in range(Mb):
-                    self.loss(e, j, *self._pol_dev[e][j])
+                self._run_epoch(e, 1)
             ev = torch.cuda.Event()
             ev.record(main)
             s_out.wait_event(ev)
             with torch.cuda.stream(s_out):
                 out_host["grads"][e].copy_(self.grads_all[e], non_blocking=True)
-        self.finalize()
+        if not self._immediate:
+            self.finalize()
         out_host["out"].copy_(self.out, non_blocking=True)
         self.step_count += 1
         main.wait_stream(s_out)
@@ -421,6 +481,9 @@ class HotPath:
         main = torch.cuda.current_stream()
         if self.popart:
             self.update_popart()
+        if self._immediate:
+            self.loss_batch([(e, j) for j in range(self.minibatches)], self._pol_dev)
+            return
         if branches <= 1:
             for j in range(self.minibatches):
                 self.loss(e, j, *self._pol_dev[e][j])

@@ -13,8 +13,8 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from srl_b200 import _lib
-from srl_b200._lib import (SRL_LANE_PART, SRL_LOSS_OUT_LEN, SRL_MAX_HEADS, SRL_MAX_LEAVES, LeafDesc, PpoHyper,
-                           VALUE_LOSS_CODES)
+from srl_b200._lib import (SRL_LANE_PART, SRL_LOSS_OUT_LEN, SRL_MAX_HEADS, SRL_MAX_LEAVES, LeafDesc, LossProblem,
+                           PpoHyper, VALUE_LOSS_CODES)
 
 
 def _stream() -> int:
@@ -36,6 +36,15 @@ def _check(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t
 
 
+def _check_view(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    """Like _check but for row-offset views (not necessarily contiguous as a whole)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (srl_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t
+
+
 def _rows_lanes(t: torch.Tensor) -> Tuple[int, int]:
     """[L, B, (A,) 1] or [L, N] -> (L, N)."""
     if t.dim() < 2:
@@ -50,11 +59,14 @@ def gae_scan(reward, value, done, truncated, on_reset, gamma: float, lmbda: floa
              row_hi: Optional[int] = None, popart_mean_std: Optional[torch.Tensor] = None,
              vtrace_new_logp: Optional[torch.Tensor] = None, vtrace_old_logp: Optional[torch.Tensor] = None,
              rho: float = 1.0, c: float = 1.0, adv: Optional[torch.Tensor] = None,
-             ret: Optional[torch.Tensor] = None, lane_part: Optional[torch.Tensor] = None, want_stats: bool = True):
+             ret: Optional[torch.Tensor] = None, lane_part: Optional[torch.Tensor] = None, want_stats: bool = True,
+             old_logp: Optional[torch.Tensor] = None, pack: Optional[torch.Tensor] = None):
     """GAE + value target + zero padding row + per-lane statistics in one launch.
 
     reward/value float32 and done/truncated/on_reset uint8, all `[L, N(, 1)]`; returns
     (adv, ret) shaped like `value` and lane_part float64 `[8, N]` (or None).
+    `pack` (float32 `[L, N, 4]`, needs `old_logp` `[L, N]`): additionally writes the loss's sample side as one
+    16-byte item per transition, {old_logp, value, ret, mask ? adv : NaN} (see include/srl_b200.h).
     Reference: MultiAgentPPO._compute_adv_and_value_target (mappo.py:118-144) + F.pad (mappo.py:254-256).
     """
     L, N = _rows_lanes(value)
@@ -84,9 +96,19 @@ def gae_scan(reward, value, done, truncated, on_reset, gamma: float, lmbda: floa
         _check(lane_part, torch.float64, "lane_part")
         if tuple(lane_part.shape) != (SRL_LANE_PART, N):
             raise ValueError(f"lane_part: expected shape {(SRL_LANE_PART, N)}, got {tuple(lane_part.shape)}")
+    if pack is not None:
+        _check(pack, torch.float32, "pack")
+        if old_logp is None:
+            raise ValueError("pack needs old_logp")
+        _check(old_logp, torch.float32, "old_logp")
+        if pack.numel() != L * N * 4 or _rows_lanes(old_logp) != (L, N):
+            raise ValueError(f"pack must hold [L, N, 4] = {L * N * 4} floats and old_logp [L, N]; got "
+                             f"{tuple(pack.shape)} and {tuple(old_logp.shape)}")
     _lib.call("srl_gae_scan", _ptr(reward), _ptr(value), _ptr(done), _ptr(truncated), _ptr(on_reset),
-              _ptr(vtrace_new_logp), _ptr(vtrace_old_logp), _ptr(popart_mean_std), L, N, int(row_lo), int(row_hi),
-              float(gamma), float(lmbda), float(rho), float(c), _ptr(adv), _ptr(ret), _ptr(lane_part), _stream())
+              _ptr(vtrace_new_logp), _ptr(vtrace_old_logp), _ptr(popart_mean_std),
+              _ptr(old_logp) if pack is not None else None, L, N, int(row_lo), int(row_hi),
+              float(gamma), float(lmbda), float(rho), float(c), _ptr(adv), _ptr(ret), _ptr(lane_part), _ptr(pack),
+              _stream())
     return adv, ret, lane_part
 
 
@@ -281,6 +303,69 @@ def ppo_loss_fwd_bwd(new_logp, v_pred, entropy, old_logp, old_value, ret, adv, o
               _ptr(local_stats), _ptr(popart_mean_std), ctypes.byref(hc), _ptr(grads[0]), _ptr(grads[1]),
               _ptr(grads[2]), n, _ptr(out), _ptr(out_f32), _ptr(ws), ws.numel(), _stream())
     return grads[0], grads[1], grads[2], out, out_f32
+
+
+def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on_reset_next, hyper: LossHyper,
+                     popart_mean_std=None, pack: Optional[torch.Tensor] = None) -> None:
+    """Several minibatches of one shape in ONE launch (srl_ppo_loss_fwd_bwd_batched).
+
+    Each problem is a dict with `new_logp`, `v_pred`, `entropy` (`[T, n]` float32), `norm_stats`, `local_stats`
+    (float64), `grads` (three `[T, n]` float32 outputs), `workspace` (one uint8 slot row), optional `lane_idx`
+    (int32 `[n]`), `out` (float64 `[16]`) and `out_f32` (float32 `[4]`); without `out` the problem is deferred
+    (loss_finalize folds its slot later).  The sample side is shared: the five leaf views of ppo_loss_fwd_bwd, or
+    `pack` = K2's `[>=T, N, 4]` float32 view already offset to the first loss row."""
+    if not problems:
+        return
+    T, n = _rows_lanes(problems[0]["new_logp"])
+    has_idx = problems[0].get("lane_idx") is not None
+    arr = (LossProblem * len(problems))()
+    slot_bytes = None
+    for k, q in enumerate(problems):
+        for name in ("new_logp", "v_pred", "entropy"):
+            _check(q[name], torch.float32, f"problem {k} {name}")
+            if _rows_lanes(q[name]) != (T, n):
+                raise ValueError(f"problem {k} {name}: shape {tuple(q[name].shape)}, expected [T, n] = [{T}, {n}]")
+        for g in q["grads"]:
+            _check(g, torch.float32, f"problem {k} gradient")
+            if g.numel() != T * n:
+                raise ValueError(f"problem {k}: gradient tensor holds {g.numel()} elements, expected {T * n}")
+        _check(q["norm_stats"], torch.float64, f"problem {k} norm_stats")
+        ls = q.get("local_stats")
+        ls = q["norm_stats"] if ls is None else _check(ls, torch.float64, f"problem {k} local_stats")
+        li = q.get("lane_idx")
+        if (li is not None) != has_idx:
+            raise ValueError("either every problem has a lane_idx or none has")
+        if li is not None:
+            _check(li, torch.int32, f"problem {k} lane_idx")
+            if li.numel() != n:
+                raise ValueError(f"problem {k}: lane_idx has {li.numel()} entries, policy side has {n} lanes")
+        ws = _check(q["workspace"], torch.uint8, f"problem {k} workspace")
+        slot_bytes = ws.numel() if slot_bytes is None else min(slot_bytes, ws.numel())
+        out, out_f32 = q.get("out"), q.get("out_f32")
+        if out is not None:
+            _check(out, torch.float64, f"problem {k} out")
+        if out_f32 is not None:
+            _check(out_f32, torch.float32, f"problem {k} out_f32")
+        arr[k] = LossProblem(_ptr(q["new_logp"]), _ptr(q["v_pred"]), _ptr(q["entropy"]), _ptr(li), _ptr(q["norm_stats"]),
+                             _ptr(ls), _ptr(q["grads"][0]), _ptr(q["grads"][1]), _ptr(q["grads"][2]), _ptr(out),
+                             _ptr(out_f32), _ptr(ws))
+    if pack is not None:
+        _check_view(pack, torch.float32, "pack")
+        if pack.dim() != 3 or pack.shape[2] != 4 or pack.shape[0] < T or pack.stride(2) != 1 or pack.stride(1) != 4:
+            raise ValueError(f"pack: expected a [>=T, N, 4] float32 view, got shape {tuple(pack.shape)} strides {pack.stride()}")
+        ld_smp = pack.stride(0) // 4 if pack.shape[0] > 1 else pack.shape[1]
+        if not has_idx and pack.shape[1] != n:
+            raise ValueError(f"pack has {pack.shape[1]} lanes but the policy side has {n}")
+        old_logp = old_value = ret = adv = on_reset_next = None
+    else:
+        ld_smp = _sample_side(old_logp, old_value, ret, adv, on_reset_next, problems[0].get("lane_idx"), T, n,
+                              hyper.clip_value)
+    if popart_mean_std is not None:
+        _check(popart_mean_std, torch.float64, "popart_mean_std")
+    hc = hyper.to_c()
+    _lib.call("srl_ppo_loss_fwd_bwd_batched", arr, len(problems), n, n, _ptr(old_logp), _ptr(old_value), _ptr(ret),
+              _ptr(adv), _ptr(on_reset_next), ld_smp, _ptr(pack), T, n, _ptr(popart_mean_std), ctypes.byref(hc),
+              slot_bytes, _stream())
 
 
 def ppo_loss_from_logits(logits, action, head_sizes: Sequence[int], v_pred, old_logp, old_value, ret, adv, on_reset_next,

@@ -234,7 +234,7 @@ class MultiAgentPPOB200(PytorchTrainer):
                     vt = None
                     if self.vtrace and not cached_adv:
                         vt = res.new_action_log_probs.detach().reshape(-1, hp.N).contiguous()
-                    hp.advantages(cached=cached_adv, vtrace_new_logp=vt)
+                    hp.advantages(cached=cached_adv, vtrace_new_logp=vt, permute=False)
                     have_adv = True
                 if self._popart and j == 0:  # once per epoch, before the loss (mappo.py:263-264)
                     hp.update_popart()

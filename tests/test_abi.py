@@ -47,8 +47,8 @@ def test_library_is_sm100a_only(lib):
 def test_abi_version_and_error_text(lib):
     assert lib.srl_abi_version() == _lib.ABI_VERSION
     # invalid arguments are rejected on the host, before any CUDA call: status + message, no abort
-    rc = lib.srl_gae_scan(None, None, None, None, None, None, None, None, 1, 1, 0, 0, 0.99, 0.95, 1.0, 1.0, None, None,
-                          None, None)
+    rc = lib.srl_gae_scan(None, None, None, None, None, None, None, None, None, 1, 1, 0, 0, 0.99, 0.95, 1.0, 1.0, None,
+                          None, None, None, None)
     assert rc == 1
     assert b"L >= 2" in lib.srl_last_error()
     rc = lib.srl_philox_perm(0, 0, 1, -1, 1, None, None)
@@ -60,6 +60,7 @@ def test_abi_version_and_error_text(lib):
 def test_struct_layouts_match_header(lib):
     assert ctypes.sizeof(_lib.PpoHyper) == 7 * 8 + 4 * 4
     assert ctypes.sizeof(_lib.LeafDesc) == 32
+    assert ctypes.sizeof(_lib.LossProblem) == 12 * 8
     assert lib.srl_ppo_loss_workspace_bytes(128, 4096) >= 64 + 148 * 8 * 8 * 8
 
 

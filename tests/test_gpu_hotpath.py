@@ -19,14 +19,15 @@ def _hp_kwargs(cfg):
                 value_loss_config=({"delta": cfg.value_loss_delta} if cfg.value_loss == "huber" else None))
 
 
-def _setup(cfg, seed, fuse_gather=True):
+def _setup(cfg, seed, fuse_gather=True, **hp_kw):
     from srl_b200 import ops
     from srl_b200.hotpath import HotPath
     s = synth.make_sample_scalars(cfg, seed)
     pol = synth.make_policy_outputs(cfg, s, seed + 1)
     hp = HotPath(cfg.L, cfg.B, cfg.A, gamma=cfg.gamma, lmbda=cfg.lmbda, hyper=ops.LossHyper(**_hp_kwargs(cfg)),
                  bootstrap_steps=cfg.bootstrap_steps, burn_in_steps=cfg.burn_in_steps, epochs=cfg.epochs,
-                 minibatches=cfg.minibatches, seed=77, popart=cfg.popart, popart_beta=0.99, fuse_gather=fuse_gather)
+                 minibatches=cfg.minibatches, seed=77, popart=cfg.popart, popart_beta=0.99, fuse_gather=fuse_gather,
+                 **hp_kw)
     hp.load_sample(s)
     # oracle
     batch = {k: torch.from_numpy(v.reshape(cfg.L, cfg.N, 1)).float() for k, v in s.items()}
@@ -108,7 +109,7 @@ def test_step_graph_replay_matches_oracle(name):
 
 def test_step_explicit_gather_equals_fused_gather():
     cfg = CASES["atari_mb"]
-    a, pol_dev, ref, pa = _setup(cfg, seed=5, fuse_gather=True)
+    a, pol_dev, ref, pa = _setup(cfg, seed=5, fuse_gather=True, batch_losses=False)
     b, _, _, _ = _setup(cfg, seed=5, fuse_gather=False)
     a.run_device(pol_dev, use_graph=False)
     b.run_device(pol_dev, use_graph=False)
@@ -175,3 +176,21 @@ def test_block_shuffle_matches_oracle():
                               for k in ("new_logp", "v_pred", "entropy")) for j in range(cfg.minibatches)])
     hp.run_device(pol_dev, use_graph=False)
     _compare(hp, cfg, ref, None)
+
+
+@pytest.mark.parametrize("hp_kw", [dict(use_pack=False), dict(batch_losses=False), dict(use_pack=False, batch_losses=False)])
+@pytest.mark.parametrize("name", ["atari_mb", "smac_popart"])
+def test_step_variants_match_oracle(name, hp_kw):
+    """The same step with the loss pack and / or the batched launch switched off (the per-minibatch launches the
+    trainer uses) agrees with the oracle too, eagerly and replayed from a CUDA graph."""
+    cfg = CASES[name]
+    hp, pol_dev, ref, pa = _setup(cfg, 21, **hp_kw)
+    hp.run_device(pol_dev, use_graph=False)
+    _compare(hp, cfg, ref, pa)
+    hp.step_count = 0
+    hp.run_device(pol_dev, use_graph=True)  # capture (with a warm-up run) + first replay
+    hp.popart_state.zero_()
+    hp.popart_ms.copy_(torch.tensor([0.0, 0.1, 0.0, 0.1], dtype=torch.float64))
+    hp.step_count = 0
+    hp.run_device(pol_dev, use_graph=True)
+    _compare(hp, cfg, ref, pa)

@@ -566,3 +566,107 @@ def test_group_stats_whole_first_and_multi_epoch_perm(ops):
     p = perm.cpu().numpy().reshape(E * Mb, N // Mb)
     for g in range(E * Mb):
         np.testing.assert_allclose(table[1 + g], part[:, p[g]].sum(1), rtol=1e-12, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------
+# K2 pack + batched K4 (r1c)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L,N", [(9, 31), (33, 64), (130, 272), (129, 16 * 700)])
+def test_gae_pack_matches_leaves(ops, L, N):
+    """The loss pack is {old_logp, value, ret, mask ? adv : NaN} of the same launch's adv / ret, bit for bit, on the
+    tile kernel (ragged N, small N) and on the TMA kernel (N % 16 == 0 with enough lane groups)."""
+    cfg = synth.PathConfig("pack", T=L - 1, B=N, p_end=0.1, gamma=0.995, lmbda=0.9)
+    s = synth.make_sample_scalars(cfg, seed=L + N)
+    d = {k: dev(flat2(v)) for k, v in s.items()}
+    pack = torch.full((L, N, 4), 7.0, dtype=torch.float32, device="cuda")
+    adv, ret, part = ops.gae_scan(d["reward"], d["value"], d["done"], d["truncated"], d["on_reset"], cfg.gamma, cfg.lmbda,
+                                  old_logp=d["old_logp"], pack=pack)
+    adv2, ret2, part2 = ops.gae_scan(d["reward"], d["value"], d["done"], d["truncated"], d["on_reset"], cfg.gamma,
+                                     cfg.lmbda)
+    torch.cuda.synchronize()
+    assert torch.equal(adv, adv2) and torch.equal(ret, ret2) and torch.equal(part, part2)
+    pk = pack.cpu().numpy()
+    assert np.array_equal(pk[..., 0], flat2(s["old_logp"]))
+    assert np.array_equal(pk[..., 1], flat2(s["value"]))
+    assert np.array_equal(pk[..., 2], ret.cpu().numpy())
+    keep = np.ones((L, N), dtype=bool)
+    keep[:-1] = flat2(s["on_reset"])[1:] == 0
+    keep[-1] = False
+    assert np.array_equal(np.isnan(pk[..., 3]), ~keep)
+    assert np.array_equal(pk[..., 3][keep], adv.cpu().numpy()[keep])
+
+
+@pytest.mark.parametrize("mode", ["dense", "gather", "pack"])
+@pytest.mark.parametrize("T,N,n,K", [(16, 64, 16, 4), (33, 200, 40, 5), (7, 36, 9, 3)])
+def test_loss_batched_equals_single_launches(ops, mode, T, N, n, K):
+    """K problems in one launch == K single launches: gradients bit-identical (same per-element arithmetic),
+    loss scalars within 1e-12 (different CTA partition of the same float64 sums)."""
+    cfg = synth.PathConfig("b", T=T, B=N, p_end=0.1, clip_value=True, dual_clip=True, value_loss="huber",
+                           value_loss_delta=1.0)
+    s = synth.make_sample_scalars(cfg, seed=5)
+    L = cfg.L
+    d = {k: dev(flat2(v)) for k, v in s.items()}
+    pack = torch.empty((L, N, 4), dtype=torch.float32, device="cuda")
+    adv, ret, part = ops.gae_scan(d["reward"], d["value"], d["done"], d["truncated"], d["on_reset"], cfg.gamma, cfg.lmbda,
+                                  row_lo=0, row_hi=T, old_logp=d["old_logp"], pack=pack)
+    rng = np.random.default_rng(1)
+    hp = ops.LossHyper(clip_value=True, dual_clip=True, value_loss="huber", value_loss_config=dict(delta=1.0))
+    if mode == "dense":
+        n = N
+        idxs = [None] * K
+    else:
+        idxs = [dev(rng.permutation(N)[:n].astype(np.int32)) for _ in range(K)]
+    probs, singles = [], []
+    ws = ops.new_loss_workspace("cuda", slots=2 * K)
+    for k in range(K):
+        li = idxs[k]
+        sel = slice(None) if li is None else li.long()
+        stats = ops.group_stats(part, idx=li, groups=1, per=n)[0]
+        olp = d["old_logp"][:T][:, sel]
+        nl = (olp + 0.1 * torch.randn(T, n, device="cuda")).contiguous()
+        vp = (d["value"][:T][:, sel] + 0.1 * torch.randn(T, n, device="cuda")).contiguous()
+        en = torch.rand(T, n, device="cuda")
+        grads = tuple(torch.empty(T, n, device="cuda") for _ in range(3))
+        out = torch.zeros(16, dtype=torch.float64, device="cuda")
+        probs.append(dict(new_logp=nl, v_pred=vp, entropy=en, lane_idx=li, norm_stats=stats, local_stats=stats, grads=grads,
+                          workspace=ws[k], out=out, out_f32=torch.zeros(4, device="cuda")))
+        singles.append(ops.ppo_loss_fwd_bwd(nl, vp, en, d["old_logp"][:T], d["value"][:T], ret[:T], adv[:T],
+                                            d["on_reset"][1:T + 1], stats, hp, lane_idx=li, workspace=ws[K + k]))
+    if mode == "pack":
+        ops.ppo_loss_batched(probs, None, None, None, None, None, hp, pack=pack[:T])
+    else:
+        ops.ppo_loss_batched(probs, d["old_logp"][:T], d["value"][:T], ret[:T], adv[:T], d["on_reset"][1:T + 1], hp)
+    torch.cuda.synchronize()
+    for k in range(K):
+        g_lp, g_v, g_en, out, out32 = singles[k]
+        for a, b in zip(probs[k]["grads"], (g_lp, g_v, g_en)):
+            assert torch.equal(a, b), f"problem {k}: batched gradient differs from the single launch"
+        np.testing.assert_allclose(probs[k]["out"].cpu().numpy(), out.cpu().numpy(), rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(probs[k]["out_f32"].cpu().numpy(), out32.cpu().numpy(), rtol=1e-6)
+
+
+def test_loss_batched_more_problems_than_one_launch(ops):
+    """n_problems > SRL_MAX_LOSS_BATCH is split into several launches; deferred slots fold in one finalize."""
+    T, N, K = 8, 64, 37
+    cfg = synth.PathConfig("b", T=T, B=N, p_end=0.1)
+    s = synth.make_sample_scalars(cfg, seed=9)
+    d = {k: dev(flat2(v)) for k, v in s.items()}
+    adv, ret, part = ops.gae_scan(d["reward"], d["value"], d["done"], d["truncated"], d["on_reset"], cfg.gamma, cfg.lmbda,
+                                  row_lo=0, row_hi=T)
+    stats = ops.group_stats(part, groups=1, per=N)[0]
+    hp = ops.LossHyper()
+    ws = ops.new_loss_workspace("cuda", slots=K)
+    probs = []
+    for k in range(K):
+        nl = (d["old_logp"][:T] + 0.05 * (k + 1) * torch.randn(T, N, device="cuda")).contiguous()
+        probs.append(dict(new_logp=nl, v_pred=d["value"][:T].contiguous(), entropy=torch.rand(T, N, device="cuda"),
+                          norm_stats=stats, grads=tuple(torch.empty(T, N, device="cuda") for _ in range(3)),
+                          workspace=ws[k]))
+    ops.ppo_loss_batched(probs, d["old_logp"][:T], d["value"][:T], ret[:T], adv[:T], d["on_reset"][1:T + 1], hp)
+    out = torch.zeros((K, 16), dtype=torch.float64, device="cuda")
+    ops.loss_finalize(ws, out)
+    for k in (0, 31, 32, 36):
+        q = probs[k]
+        _, _, _, o, _ = ops.ppo_loss_fwd_bwd(q["new_logp"], q["v_pred"], q["entropy"], d["old_logp"][:T], d["value"][:T],
+                                             ret[:T], adv[:T], d["on_reset"][1:T + 1], stats, hp)
+        np.testing.assert_allclose(out[k].cpu().numpy(), o.cpu().numpy(), rtol=1e-12, atol=1e-14)
