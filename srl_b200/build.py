@@ -14,13 +14,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libsrl_b200.so")
-SOURCES = ["api.cu", "gae_scan.cu", "gae_scan_tma.cu", "ppo_loss.cu", "stats.cu", "perm.cu", "gather.cu"]
+SOURCES = ["api.cu", "gae_scan.cu", "gae_scan_tma.cu", "ppo_loss.cu", "ppo_loss_dense.cu", "ppo_loss_gather.cu",
+           "ppo_loss_pack.cu", "stats.cu", "perm.cu", "gather.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",  # B200 only; no PTX for other archs, no fallback
     "-O3", "-std=c++17", "-lineinfo",
     "-fmad=false",  # the reference evaluates every torch op with its own rounding; these kernels are HBM-bound
     "-Xcompiler", "-fPIC", "-shared",
+    "--threads", "0",  # one compile job per source file
 ]
 
 
@@ -39,10 +41,12 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, out: str = LIB, extra_flags=()) -> str:
+    """`out` / `extra_flags` (e.g. -DSRL_LOSS_UNROLL=2) build tuning variants next to the product library; load one
+    with SRL_B200_LIB=<path> (profiles/ scripts only)."""
+    if out == LIB and not force and not _stale():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", LIB]
+    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", out]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
@@ -51,12 +55,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError(f"nvcc failed ({proc.returncode}):\n{proc.stdout}\n{proc.stderr}")
     if verbose:
         print(proc.stderr, file=sys.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--out", default=LIB)
+    ap.add_argument("flags", nargs="*", help="extra nvcc flags after --, e.g. -- -DSRL_LOSS_UNROLL=2")
     a = ap.parse_args()
-    print(build(force=a.force, verbose=a.verbose))
+    print(build(force=a.force, verbose=a.verbose, out=a.out, extra_flags=a.flags))
