@@ -212,18 +212,28 @@ def run_ours(args, cfg, rank, world, local_rank):
                     ret=torch.empty((cfg.L, N), dtype=torch.float32).pin_memory(),
                     grads=torch.empty((E, Mb, 3, T, n), dtype=torch.float32).pin_memory(),
                     out=torch.empty((E * Mb, 16), dtype=torch.float64).pin_memory())
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # L2 flush between timed iterations: write a 256 MiB buffer (> 126 MB L2), then READ a second one.  The write
+    # alone leaves the L2 full of dirty lines whose write-back the timed kernels would then pay for (it showed as
+    # ~20 us on a 65 us kernel); the read pass evicts them and leaves clean lines, so the step starts cold.
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_rd = torch.zeros(64 << 20, dtype=torch.int32, device=dev)  # 256 MiB
+
+    def flush_l2():
+        flush.zero_()
+        flush_rd.max()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    flush_l2_fn = flush_l2
+
     def timed_steps(k, fn, flush_l2=True):
         pairs = []
         for _ in range(k):
             if flush_l2:
-                flush.zero_()
+                flush_l2_fn()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
@@ -235,7 +245,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     step = lambda: hp.run_device(pol_dev, use_graph=True)
     for _ in range(max(args.warmup, 3)):
-        flush.zero_()
+        flush_l2()
         step()
     barrier()
     t_region0 = time.perf_counter()
@@ -258,7 +268,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     wall = []
     nbytes = None
     for _ in range(e2e_steps):
-        flush.zero_()
+        flush_l2()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         nbytes = hp.run_host(pinned, pol_host, out_host)
@@ -332,7 +342,7 @@ def run_ours(args, cfg, rank, world, local_rank):
             ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
             data="synthetic",
             config=dict(workload=workload_name(cfg), transitions_per_step_per_gpu=cfg.transitions,
-                        l2="flushed between timed iterations (256 MiB device write before each step; working set "
+                        l2="flushed between timed iterations (256 MiB device write, then 256 MiB device read, before each step; working set "
                            f"{step_bytes / 1e6:.0f} MB algorithmic)",
                         timing="CUDA events per step on the launch stream, sum over steps, max over ranks",
                         launch="one CUDA graph per step" if world == 1 else "two CUDA graphs per step around one NCCL all-reduce of the float64 stats table",

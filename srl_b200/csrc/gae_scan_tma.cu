@@ -120,6 +120,7 @@ template <bool VTRACE, bool PACK, bool EDGE>
 __device__ __forceinline__ void run_stage(const GaeParams& p, const unsigned char* slot, int tbase, int lane, int col,
                                           bool live, bool popart, double pa_mean, double pa_std, Carry& cy,
                                           LaneStats& st) {
+  // `live` and `popart` are compile-time constants in the specialised instantiations (FULL / POPART below)
   using SL = StageLayout<VTRACE, PACK || VTRACE>;
   const float* sv = reinterpret_cast<const float*>(slot + SL::value);
   const float* sr = reinterpret_cast<const float*>(slot + SL::reward);
@@ -218,7 +219,9 @@ __device__ __forceinline__ void run_stage(const GaeParams& p, const unsigned cha
   cy.trunc_next = trf[0];
 }
 
-template <bool VTRACE, bool PACK>
+// SPEC = true: the hot instantiations, N % 32 == 0 (no dead lanes, so no per-row store predicate and no
+// reconvergence barrier around the stores) and PopArt known at compile time (POPART); SPEC = false: general.
+template <bool VTRACE, bool PACK, bool SPEC, bool POPART>
 __global__ void __launch_bounds__(kLanes) gae_scan_tma_kernel(const __grid_constant__ GaeTmaParams q) {
   constexpr bool OLDLP = PACK || VTRACE;
   using SL = StageLayout<VTRACE, OLDLP>;
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(kLanes) gae_scan_tma_kernel(const __grid_const
   const int lane = threadIdx.x;
   const int col0 = blockIdx.x * kLanes;
   const int col = col0 + lane;
-  const bool live = col < p.N;
+  const bool live = SPEC ? true : col < p.N;
   const int L = p.L, N = p.N;
   const int n_stages = (L + kRows - 1) / kRows;  // stage k covers rows [k*kRows, (k+1)*kRows); rows >= L read as 0
 
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(kLanes) gae_scan_tma_kernel(const __grid_const
       issue_stage<VTRACE, OLDLP>(q, smem + i * SL::stride, &bars[i], col0, (n_stages - 1 - i) * kRows);
   }
 
-  const bool popart = p.popart != nullptr;
+  const bool popart = SPEC ? POPART : p.popart != nullptr;
   double pa_mean = 0.0, pa_std = 1.0;
   if (popart) {
     pa_mean = p.popart[0];
@@ -331,11 +334,11 @@ int make_map(CUtensorMap* m, const void* base, int rows, int N, int elem) {
   return SRL_OK;
 }
 
-template <bool VTRACE, bool PACK>
+template <bool VTRACE, bool PACK, bool SPEC, bool POPART>
 int launch(const GaeTmaParams& q, cudaStream_t st) {
   using SL = StageLayout<VTRACE, PACK || VTRACE>;
   const size_t smem = static_cast<size_t>(kStages) * SL::stride + kStages * sizeof(uint64_t);
-  auto kern = gae_scan_tma_kernel<VTRACE, PACK>;
+  auto kern = gae_scan_tma_kernel<VTRACE, PACK, SPEC, POPART>;
   static bool opted_in[64] = {};
   int dev = 0;
   SRL_CUDA(cudaGetDevice(&dev));
@@ -377,13 +380,16 @@ int launch_gae_tma(const GaeParams& p, cudaStream_t st) {
     if ((rc = make_map(&q.maps.vt_new, p.vt_new_logp, p.L - 1, p.N, 4)) != SRL_OK) return rc;
     if ((rc = make_map(&q.maps.old_logp, p.vt_old_logp, p.L - 1, p.N, 4)) != SRL_OK) return rc;
     // the pack's old_logp is the sample leaf the V-trace ratio uses as well
-    return pack ? launch<true, true>(q, st) : launch<true, false>(q, st);
+    return pack ? launch<true, true, false, false>(q, st) : launch<true, false, false, false>(q, st);
   }
+  const bool full = p.N % kLanes == 0, popart = p.popart != nullptr;
   if (pack) {
     if ((rc = make_map(&q.maps.old_logp, p.old_logp, p.L, p.N, 4)) != SRL_OK) return rc;
-    return launch<false, true>(q, st);
+    if (!full) return launch<false, true, false, false>(q, st);
+    return popart ? launch<false, true, true, true>(q, st) : launch<false, true, true, false>(q, st);
   }
-  return launch<false, false>(q, st);
+  if (!full) return launch<false, false, false, false>(q, st);
+  return popart ? launch<false, false, true, true>(q, st) : launch<false, false, true, false>(q, st);
 }
 
 }  // namespace srl

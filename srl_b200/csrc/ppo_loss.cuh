@@ -20,6 +20,7 @@ constexpr int kMaxGrid = 2048;                // partial rows per workspace slot
 constexpr int kNumSums = 8;
 constexpr size_t kPartialsOffset = 64;
 constexpr int kMaxBatch = SRL_MAX_LOSS_BATCH;
+constexpr int kFlushRows = 8;  // rows whose masked terms are summed in fp32 before they enter the float64 sums
 
 // First 64 bytes of a workspace slot; the partial rows [n_rows][8] f64 follow.
 struct SlotHeader {
@@ -161,7 +162,7 @@ __device__ __forceinline__ float popart_normalize(float x, const Uniforms& u) {
   return fminf(fmaxf(z, -5.f), 5.f);
 }
 
-// Per-row (4 lanes) fp32 partial sums; folded into the thread's float64 accumulators once per row.
+// fp32 partial sums of a few rows (kFlushRows x 4 lanes); folded into the thread's float64 accumulators in blocks.
 struct RowSums {
   float pl = 0.f, vl = 0.f, en = 0.f, adv = 0.f, ratio = 0.f, vt = 0.f, ret = 0.f;
   int clip = 0;
@@ -189,7 +190,9 @@ template <class CFG>
 __device__ __forceinline__ void element(const LossHyperDev& h, const Uniforms& u, float nl, float vp, float en,
                                         float ol, float ov, float rt, float ad, bool valid, float& g_lp,
                                         float& g_v, float& g_en, RowSums& rs) {
+  const float mk = valid ? 1.f : 0.f;
   const float scale = valid ? u.inv_m : 0.f;  // d(masked mean)/d(element) = mask / M
+  ad = valid ? ad : 0.f;                      // the pack marks masked transitions with a NaN advantage
 
   // ---- critic: mappo.py:172-184, utils.py:228-239 ---------------------------------------------
   const float vt = u.popart ? popart_normalize(rt, u) : rt;
@@ -207,12 +210,12 @@ __device__ __forceinline__ void element(const LossHyperDev& h, const Uniforms& u
     vl = fmaxf(l, l2);
     gv = l > l2 ? dl : (l < l2 ? dl2 : 0.5f * (dl + dl2));  // torch.max splits ties evenly
   }
-  g_v = valid ? h.wv * scale * gv : 0.f;
+  g_v = h.wv * scale * gv;
 
   // ---- actor: mappo.py:157-158,186-197 ---------------------------------------------------------
   const float ratio = expf(nl - ol);
   // masked_normalization (utils.py:38-67) in float64, cast to float at the end; masked entries are centred
-  // zeros there (x = adv * mask) but they never reach the loss or the gradients
+  // zeros there (x = adv * mask) and here
   const float nadv = static_cast<float>(div_by(__dsub_rn(static_cast<double>(ad), u.mean), u.denom, u.rdenom));
   const float s1 = ratio * nadv;
   const float s2 = fminf(fmaxf(ratio, h.clip_lo), h.clip_hi) * nadv;
@@ -228,19 +231,20 @@ __device__ __forceinline__ void element(const LossHyperDev& h, const Uniforms& u
     gsum = obj > s3 ? gsum : (obj < s3 ? 0.f : 0.5f * gsum);
     obj = fmaxf(obj, s3);
   }
-  g_lp = valid ? -scale * gsum : 0.f;
+  g_lp = -scale * gsum;
   g_en = -h.we * scale;  // entropy_loss = -sum(entropy * mask) / M   mappo.py:199
 
-  if (valid) {
-    rs.pl -= obj;
-    rs.vl += vl;
-    rs.en += en;
-    rs.adv += ad;
-    rs.ratio += ratio;
-    rs.vt += vt;
-    rs.ret += rt;
-    rs.clip += (s2 < s1) ? 1 : 0;
-  }
+  // masked sums: multiply by the mask as the reference does (mappo.py:184,197,199).  Like there, a non-finite
+  // term of a masked transition would poison the sum; the inputs of masked transitions are finite in practice
+  // (dead agents carry new_logp = -inf, i.e. ratio = 0).
+  rs.pl -= mk * obj;
+  rs.vl += mk * vl;
+  rs.en += mk * en;
+  rs.adv += mk * ad;
+  rs.ratio += mk * ratio;
+  rs.vt += mk * vt;
+  rs.ret += mk * rt;
+  rs.clip += (valid && s2 < s1) ? 1 : 0;
 }
 
 // Folds n_rows partial rows (fixed order: lane-strided, then the warp-shuffle tree) and writes the results.
@@ -341,6 +345,8 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
   double mask_sum;
   const Uniforms u = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
   Acc acc;
+  RowSums rs;
+  int pending = 0;
   const int T = s.T, n = s.n;
   const int tile_lanes = blockDim.x * LANES;
 
@@ -371,31 +377,38 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
     if constexpr (LANES == 4 && MODE == kGather)
       run4 = s.smp_vec_ok && (c[1] == c[0] + 1) && (c[2] == c[0] + 2) && (c[3] == c[0] + 3) && ((c[0] & 3) == 0);
 
-    long long op = static_cast<long long>(t0) * s.ld_pol + j;   // policy-side element offset of row t
-    long long og = static_cast<long long>(t0) * s.ld_grad + j;  // gradient-side
-    long long ob = static_cast<long long>(t0) * s.ld_smp;       // sample-side row base
+    // row base pointers are warp-uniform (64-bit, advanced once per row); per-thread offsets stay 32-bit
+    const float* nl_row = pr.new_logp + static_cast<long long>(t0) * s.ld_pol;
+    const float* vp_row = pr.v_pred + static_cast<long long>(t0) * s.ld_pol;
+    const float* en_row = pr.entropy + static_cast<long long>(t0) * s.ld_pol;
+    float* glp_row = pr.g_logp + static_cast<long long>(t0) * s.ld_grad;
+    float* gv_row = pr.g_value + static_cast<long long>(t0) * s.ld_grad;
+    float* ge_row = pr.g_entropy + static_cast<long long>(t0) * s.ld_grad;
+    long long ob = static_cast<long long>(t0) * s.ld_smp;  // sample-side row base (elements)
 
 #pragma unroll kLossUnroll
-    for (int t = t0; t < t1; ++t, op += s.ld_pol, og += s.ld_grad, ob += s.ld_smp) {
+    for (int t = t0; t < t1; ++t, nl_row += s.ld_pol, vp_row += s.ld_pol, en_row += s.ld_pol, glp_row += s.ld_grad,
+             gv_row += s.ld_grad, ge_row += s.ld_grad, ob += s.ld_smp) {
       float nl[LANES], vp[LANES], en[LANES], ol[LANES], ov[LANES], rt[LANES], ad[LANES];
       bool valid[LANES];
       // ---- policy side: dense ------------------------------------------------------------------------
       if constexpr (LANES == 4) {
-        unpack4(ldg_stream(reinterpret_cast<const float4*>(pr.new_logp + op)), nl);
-        unpack4(ldg_stream(reinterpret_cast<const float4*>(pr.v_pred + op)), vp);
-        unpack4(ldg_stream(reinterpret_cast<const float4*>(pr.entropy + op)), en);
+        unpack4(ldg_stream(reinterpret_cast<const float4*>(nl_row + j)), nl);
+        unpack4(ldg_stream(reinterpret_cast<const float4*>(vp_row + j)), vp);
+        unpack4(ldg_stream(reinterpret_cast<const float4*>(en_row + j)), en);
       } else {
-        nl[0] = ldg_stream(pr.new_logp + op);
-        vp[0] = ldg_stream(pr.v_pred + op);
-        en[0] = ldg_stream(pr.entropy + op);
+        nl[0] = ldg_stream(nl_row + j);
+        vp[0] = ldg_stream(vp_row + j);
+        en[0] = ldg_stream(en_row + j);
       }
       // ---- sample side -------------------------------------------------------------------------------
       bool vec_rows = false;
       if constexpr (LANES == 4) vec_rows = (MODE == kDense) || run4;
       if constexpr (MODE == kPack) {
+        const float4* pack_row = s.pack + ob;
 #pragma unroll
         for (int q = 0; q < LANES; ++q) {
-          const float4 k = __ldg(s.pack + ob + c[q]);
+          const float4 k = __ldg(pack_row + c[q]);
           ol[q] = k.x;
           ov[q] = k.y;
           rt[q] = k.z;
@@ -404,45 +417,52 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
         }
       } else if (vec_rows) {
         if constexpr (LANES == 4) {
-          const long long os = ob + c[0];
-          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.old_logp + os)), ol);
-          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.ret + os)), rt);
-          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.adv + os)), ad);
+          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.old_logp + ob + c[0])), ol);
+          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.ret + ob + c[0])), rt);
+          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.adv + ob + c[0])), ad);
           float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (CFG::clip(h)) o = ldg_stream(reinterpret_cast<const float4*>(s.old_value + os));
+          if (CFG::clip(h)) o = ldg_stream(reinterpret_cast<const float4*>(s.old_value + ob + c[0]));
           unpack4(o, ov);
-          const uint32_t m = ldg_stream(reinterpret_cast<const uint32_t*>(s.reset_next + os));
+          const uint32_t m = ldg_stream(reinterpret_cast<const uint32_t*>(s.reset_next + ob + c[0]));
 #pragma unroll
           for (int q = 0; q < LANES; ++q) valid[q] = ((m >> (8 * q)) & 0xffu) == 0u;
         }
       } else {
+        const float* ol_row = s.old_logp + ob;
+        const float* rt_row = s.ret + ob;
+        const float* ad_row = s.adv + ob;
+        const float* ov_row = CFG::clip(h) ? s.old_value + ob : nullptr;
+        const uint8_t* rs_row = s.reset_next + ob;
 #pragma unroll
         for (int q = 0; q < LANES; ++q) {
-          const long long os = ob + c[q];
-          ol[q] = __ldg(s.old_logp + os);
-          rt[q] = __ldg(s.ret + os);
-          ad[q] = __ldg(s.adv + os);
-          ov[q] = CFG::clip(h) ? __ldg(s.old_value + os) : 0.f;
-          valid[q] = __ldg(s.reset_next + os) == 0;
+          ol[q] = __ldg(ol_row + c[q]);
+          rt[q] = __ldg(rt_row + c[q]);
+          ad[q] = __ldg(ad_row + c[q]);
+          ov[q] = CFG::clip(h) ? __ldg(ov_row + c[q]) : 0.f;
+          valid[q] = __ldg(rs_row + c[q]) == 0;
         }
       }
       float glp[LANES], gv[LANES], ge[LANES];
-      RowSums rs;
 #pragma unroll
       for (int q = 0; q < LANES; ++q)
         element<CFG>(h, u, nl[q], vp[q], en[q], ol[q], ov[q], rt[q], ad[q], valid[q], glp[q], gv[q], ge[q], rs);
-      acc.add(rs);
+      if (++pending == kFlushRows) {  // fp32 partial sums of at most kFlushRows * LANES terms, then float64
+        acc.add(rs);
+        rs = RowSums();
+        pending = 0;
+      }
       if constexpr (LANES == 4) {
-        stg_stream(reinterpret_cast<float4*>(pr.g_logp + og), make_float4(glp[0], glp[1], glp[2], glp[3]));
-        stg_stream(reinterpret_cast<float4*>(pr.g_value + og), make_float4(gv[0], gv[1], gv[2], gv[3]));
-        stg_stream(reinterpret_cast<float4*>(pr.g_entropy + og), make_float4(ge[0], ge[1], ge[2], ge[3]));
+        stg_stream(reinterpret_cast<float4*>(glp_row + j), make_float4(glp[0], glp[1], glp[2], glp[3]));
+        stg_stream(reinterpret_cast<float4*>(gv_row + j), make_float4(gv[0], gv[1], gv[2], gv[3]));
+        stg_stream(reinterpret_cast<float4*>(ge_row + j), make_float4(ge[0], ge[1], ge[2], ge[3]));
       } else {
-        stg_stream(pr.g_logp + og, glp[0]);
-        stg_stream(pr.g_value + og, gv[0]);
-        stg_stream(pr.g_entropy + og, ge[0]);
+        stg_stream(glp_row + j, glp[0]);
+        stg_stream(gv_row + j, gv[0]);
+        stg_stream(ge_row + j, ge[0]);
       }
     }
   }
+  acc.add(rs);
   reduce_and_finalize(pr, h, acc, mask_sum, blockIdx.x, gridDim.x);
 }
 
