@@ -102,9 +102,12 @@ int srl_lane_stats(const float* adv, const float* ret, const uint8_t* done, cons
  * whole_first != 0: out has G + 1 rows and row 0 is the sum over ALL N lanes (the batch statistics PopArt
  * needs), rows 1..G are the groups -- one launch for the whole table.
  * Summation order is fixed (deterministic for a given G, per).
+ * Rows longer than 1024 lanes are summed by several CTAs through `workspace` (srl_group_stats_workspace_bytes()
+ * bytes, 8-byte aligned, zero before its FIRST use; the kernel leaves it zeroed); shorter rows need none (NULL).
  * ------------------------------------------------------------------------------------------ */
+size_t srl_group_stats_workspace_bytes(int G, int whole_first);
 int srl_group_stats(const double* lane_part, int N, const int32_t* idx, int G, int per, int whole_first,
-                    double* out, srl_stream_t stream);
+                    double* out, void* workspace, size_t workspace_bytes, srl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3  PopArt / RunningMeanStd update for a scalar critic (critic_dim == 1).

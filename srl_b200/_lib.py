@@ -76,7 +76,8 @@ SIGNATURES = {
     "srl_gae_scan": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double] +
                      [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "srl_lane_stats": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "srl_group_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "srl_group_stats_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "srl_group_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "srl_popart_update": (c_int, [c_void_p, c_void_p, c_double, c_double, c_void_p, c_void_p]),
     "srl_ppo_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
     "srl_ppo_loss_finalize": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p]),

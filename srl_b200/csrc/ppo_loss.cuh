@@ -88,16 +88,18 @@ constexpr int kPack = 2;    // K2's float4 pack through lane_idx (or in order)
 // (StaticCfg): ncu showed ~25 % of the executed instructions of the first batched kernel were uniform branches,
 // constant-bank reloads and reconvergence barriers around `if (h.clip_value)`-style tests inside the element loop
 // (profiles/r1c_notes.md).  RuntimeCfg keeps one general instantiation for the rare combinations.
-template <int VL, bool CLIP, bool DUAL>
+template <int VL, bool CLIP, bool DUAL, bool POPART>
 struct StaticCfg {
   __device__ static __forceinline__ int vl(const LossHyperDev&) { return VL; }
   __device__ static __forceinline__ bool clip(const LossHyperDev&) { return CLIP; }
   __device__ static __forceinline__ bool dual(const LossHyperDev&) { return DUAL; }
+  __device__ static __forceinline__ bool popart(bool) { return POPART; }
 };
 struct RuntimeCfg {
   __device__ static __forceinline__ int vl(const LossHyperDev& h) { return h.value_loss; }
   __device__ static __forceinline__ bool clip(const LossHyperDev& h) { return h.clip_value != 0; }
   __device__ static __forceinline__ bool dual(const LossHyperDev& h) { return h.dual_clip != 0; }
+  __device__ static __forceinline__ bool popart(bool have) { return have; }
 };
 
 // torch.nn.{MSELoss,HuberLoss,SmoothL1Loss}(reduction='none') value and derivative wrt the input.
@@ -195,12 +197,12 @@ __device__ __forceinline__ void element(const LossHyperDev& h, const Uniforms& u
   ad = valid ? ad : 0.f;                      // the pack marks masked transitions with a NaN advantage
 
   // ---- critic: mappo.py:172-184, utils.py:228-239 ---------------------------------------------
-  const float vt = u.popart ? popart_normalize(rt, u) : rt;
+  const float vt = CFG::popart(u.popart) ? popart_normalize(rt, u) : rt;
   float l, dl;
   pointwise_loss(CFG::vl(h), h.vl_param, vp - vt, l, dl);
   float vl = l, gv = dl;
   if (CFG::clip(h)) {
-    const float ovn = h.normalize_old_value ? popart_normalize(ov, u) : ov;
+    const float ovn = (CFG::popart(u.popart) && h.normalize_old_value) ? popart_normalize(ov, u) : ov;
     const float dv = vp - ovn;
     const float vc = ovn + fminf(fmaxf(dv, -h.veps), h.veps);
     const bool in = fabsf(dv) <= h.veps;  // clamp passes grad on the closed interval
@@ -336,147 +338,276 @@ __device__ __forceinline__ void reduce_and_finalize(const Problem& pr, const Los
 
 __device__ __forceinline__ void unpack4(const float4 v, float (&a)[4]) { a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w; }
 
-// LANES = 4: a thread owns four adjacent policy-side lanes (n % 4 == 0, 16-byte aligned rows); LANES = 1: any shape.
+// ---- asynchronous global -> shared copies (LDGSTS): the loads of the next rows are in flight while the current
+// row is computed, without holding registers for them -----------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+#ifndef SRL_LOSS_STAGES
+#define SRL_LOSS_STAGES 2
+#endif
+#ifndef SRL_LOSS_PIPE
+#define SRL_LOSS_PIPE 0  // measured on B200 (profiles/r1c_notes.md): no gain over the register path at cfg2 or cfg5
+#endif
+constexpr bool kUsePipe = SRL_LOSS_PIPE != 0;
+constexpr int kStages = SRL_LOSS_STAGES;  // rows in flight per thread in the pipelined kernels
+constexpr int kPlanes = 7;                // 16-byte items per thread and row: 3 policy + 4 sample side
+
+// Dynamic shared memory of the pipelined kernels: [kStages][kPlanes][threads] float4 + [kStages][threads] uint32.
+__host__ __device__ constexpr size_t loss_smem_bytes(int threads) {
+  return static_cast<size_t>(kStages) * threads * (kPlanes * 16 + 4);
+}
+
+// Work decomposition: grid = (column tiles, row groups, problems).  A CTA owns `blockDim * LANES` adjacent policy-side
+// lanes and the rows [r0, r1) of one problem: its gather indices are loaded once, and it walks its rows in order.
+// LANES = 4: a thread owns four adjacent lanes (n % 4 == 0, 16-byte aligned rows); LANES = 1: any shape.
+// PIPE (dense and pack forms, LANES = 4): row t + kStages is copied global -> shared (16 bytes per cp.async, each
+// thread into its own slots, so no block barrier) while row t is computed.
 template <int LANES, int MODE, class CFG>
 __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(const __grid_constant__ LossBatch b) {
+  constexpr bool PIPE = kUsePipe && (LANES == 4) && (MODE == kDense || MODE == kPack);
   const LossShared& s = b.s;
   const LossHyperDev& h = s.h;
-  const Problem& pr = b.prob[blockIdx.y];
-  double mask_sum;
-  const Uniforms u = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
+  const Problem& pr = b.prob[blockIdx.z];
+  const int T = s.T, n = s.n;
+  const int r0 = blockIdx.y * s.rows_per_tile;
+  const int r1 = min(T, r0 + s.rows_per_tile);
   Acc acc;
   RowSums rs;
   int pending = 0;
-  const int T = s.T, n = s.n;
-  const int tile_lanes = blockDim.x * LANES;
+  double mask_sum = 0.0;
+  Uniforms u;
+  bool have_u = false;
 
-  for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x) {
-    const int rt_i = tile / s.col_tiles;
-    const int ct_i = tile - rt_i * s.col_tiles;
-    const int j = ct_i * tile_lanes + threadIdx.x * LANES;
-    if (j >= n) continue;
-    const int t0 = rt_i * s.rows_per_tile;
-    const int t1 = min(T, t0 + s.rows_per_tile);
-
-    // gather indices of this thread's lanes: once per tile
-    int c[LANES];
-    if (pr.lane_idx) {
-      if constexpr (LANES == 4) {
-        const int4 q = __ldg(reinterpret_cast<const int4*>(pr.lane_idx + j));
-        c[0] = q.x, c[1] = q.y, c[2] = q.z, c[3] = q.w;
-      } else {
-        c[0] = __ldg(pr.lane_idx + j);
-      }
+  // normally one column tile per CTA (gridDim.x == col_tiles); only batches wider than kMaxGrid tiles loop here
+  for (int ct = blockIdx.x; ct < s.col_tiles; ct += gridDim.x) {
+  const int j = (ct * blockDim.x + threadIdx.x) * LANES;
+  const bool active = j < n;
+  // gather indices of this thread's lanes: once per column tile
+  int c[LANES];
+  if (pr.lane_idx && active) {
+    if constexpr (LANES == 4) {
+      const int4 q = __ldg(reinterpret_cast<const int4*>(pr.lane_idx + j));
+      c[0] = q.x, c[1] = q.y, c[2] = q.z, c[3] = q.w;
     } else {
-#pragma unroll
-      for (int q = 0; q < LANES; ++q) c[q] = j + q;
+      c[0] = __ldg(pr.lane_idx + j);
     }
-    // a run of four consecutive, 4-aligned lanes (dense batches, agents of one environment, sector-aligned
-    // environment blocks) is fetched with one 128-bit load per leaf
-    bool run4 = false;
-    if constexpr (LANES == 4 && MODE == kGather)
-      run4 = s.smp_vec_ok && (c[1] == c[0] + 1) && (c[2] == c[0] + 2) && (c[3] == c[0] + 3) && ((c[0] & 3) == 0);
-
-    // row base pointers are warp-uniform (64-bit, advanced once per row); per-thread offsets stay 32-bit
-    const float* nl_row = pr.new_logp + static_cast<long long>(t0) * s.ld_pol;
-    const float* vp_row = pr.v_pred + static_cast<long long>(t0) * s.ld_pol;
-    const float* en_row = pr.entropy + static_cast<long long>(t0) * s.ld_pol;
-    float* glp_row = pr.g_logp + static_cast<long long>(t0) * s.ld_grad;
-    float* gv_row = pr.g_value + static_cast<long long>(t0) * s.ld_grad;
-    float* ge_row = pr.g_entropy + static_cast<long long>(t0) * s.ld_grad;
-    long long ob = static_cast<long long>(t0) * s.ld_smp;  // sample-side row base (elements)
-
-#pragma unroll kLossUnroll
-    for (int t = t0; t < t1; ++t, nl_row += s.ld_pol, vp_row += s.ld_pol, en_row += s.ld_pol, glp_row += s.ld_grad,
-             gv_row += s.ld_grad, ge_row += s.ld_grad, ob += s.ld_smp) {
-      float nl[LANES], vp[LANES], en[LANES], ol[LANES], ov[LANES], rt[LANES], ad[LANES];
-      bool valid[LANES];
-      // ---- policy side: dense ------------------------------------------------------------------------
-      if constexpr (LANES == 4) {
-        unpack4(ldg_stream(reinterpret_cast<const float4*>(nl_row + j)), nl);
-        unpack4(ldg_stream(reinterpret_cast<const float4*>(vp_row + j)), vp);
-        unpack4(ldg_stream(reinterpret_cast<const float4*>(en_row + j)), en);
-      } else {
-        nl[0] = ldg_stream(nl_row + j);
-        vp[0] = ldg_stream(vp_row + j);
-        en[0] = ldg_stream(en_row + j);
-      }
-      // ---- sample side -------------------------------------------------------------------------------
-      bool vec_rows = false;
-      if constexpr (LANES == 4) vec_rows = (MODE == kDense) || run4;
-      if constexpr (MODE == kPack) {
-        const float4* pack_row = s.pack + ob;
+  } else {
 #pragma unroll
-        for (int q = 0; q < LANES; ++q) {
-          const float4 k = __ldg(pack_row + c[q]);
+    for (int q = 0; q < LANES; ++q) c[q] = j + q;
+  }
+
+  if constexpr (PIPE) {
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    float4* ring = reinterpret_cast<float4*>(ring_raw);
+    uint32_t* fring = reinterpret_cast<uint32_t*>(ring_raw + static_cast<size_t>(kStages) * kPlanes * blockDim.x * 16);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    auto slot = [&](int st, int plane) { return ring + (st * kPlanes + plane) * nthr + tid; };
+    auto issue = [&](int t, int st) {  // all loads of row t into stage st
+      if (active && t < r1) {
+        const long long op = static_cast<long long>(t) * s.ld_pol + j;
+        cp_async16(slot(st, 0), pr.new_logp + op);
+        cp_async16(slot(st, 1), pr.v_pred + op);
+        cp_async16(slot(st, 2), pr.entropy + op);
+        const long long ob = static_cast<long long>(t) * s.ld_smp;
+        if constexpr (MODE == kPack) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cp_async16(slot(st, 3 + q), s.pack + ob + c[q]);
+        } else {
+          cp_async16(slot(st, 3), s.old_logp + ob + j);
+          cp_async16(slot(st, 4), s.ret + ob + j);
+          cp_async16(slot(st, 5), s.adv + ob + j);
+          if (CFG::clip(h)) cp_async16(slot(st, 6), s.old_value + ob + j);
+          cp_async4(fring + st * nthr + tid, s.reset_next + ob + j);
+        }
+      }
+      cp_async_commit();  // one group per row, issued or not, so wait_group counts rows
+    };
+#pragma unroll
+    for (int k = 0; k < kStages; ++k) issue(r0 + k, k);
+    // the statistics loads and the float64 divisions / sqrt on them run under the first rows' copies
+    if (!have_u) {
+      u = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
+      have_u = true;
+    }
+    float* glp_row = pr.g_logp + static_cast<long long>(r0) * s.ld_grad + j;
+    float* gv_row = pr.g_value + static_cast<long long>(r0) * s.ld_grad + j;
+    float* ge_row = pr.g_entropy + static_cast<long long>(r0) * s.ld_grad + j;
+    int st = 0;
+    for (int t = r0; t < r1; ++t, glp_row += s.ld_grad, gv_row += s.ld_grad, ge_row += s.ld_grad) {
+      cp_async_wait<kStages - 1>();  // row t has landed (rows t+1 .. t+kStages-1 may still be in flight)
+      float nl[4], vp[4], en[4], ol[4], ov[4], rt[4], ad[4];
+      bool valid[4];
+      unpack4(*slot(st, 0), nl);
+      unpack4(*slot(st, 1), vp);
+      unpack4(*slot(st, 2), en);
+      if constexpr (MODE == kPack) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 k = *slot(st, 3 + q);
           ol[q] = k.x;
           ov[q] = k.y;
           rt[q] = k.z;
           ad[q] = k.w;
           valid[q] = (k.w == k.w);  // K2 stores NaN in the advantage slot of masked transitions
         }
-      } else if (vec_rows) {
+      } else {
+        unpack4(*slot(st, 3), ol);
+        unpack4(*slot(st, 4), rt);
+        unpack4(*slot(st, 5), ad);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (CFG::clip(h)) o = *slot(st, 6);
+        unpack4(o, ov);
+        const uint32_t m = fring[st * nthr + tid];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) valid[q] = ((m >> (8 * q)) & 0xffu) == 0u;
+      }
+      issue(t + kStages, st);  // refill the stage just drained (its values are in registers now)
+      st = (st + 1 == kStages) ? 0 : st + 1;
+      if (active) {
+        float glp[4], gv[4], ge[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          element<CFG>(h, u, nl[q], vp[q], en[q], ol[q], ov[q], rt[q], ad[q], valid[q], glp[q], gv[q], ge[q], rs);
+        if (++pending == kFlushRows) {  // fp32 partial sums of at most kFlushRows * LANES terms, then float64
+          acc.add(rs);
+          rs = RowSums();
+          pending = 0;
+        }
+        stg_stream(reinterpret_cast<float4*>(glp_row), make_float4(glp[0], glp[1], glp[2], glp[3]));
+        stg_stream(reinterpret_cast<float4*>(gv_row), make_float4(gv[0], gv[1], gv[2], gv[3]));
+        stg_stream(reinterpret_cast<float4*>(ge_row), make_float4(ge[0], ge[1], ge[2], ge[3]));
+      }
+    }
+    cp_async_wait<0>();
+  } else {
+    if (!have_u) {
+      u = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
+      have_u = true;
+    }
+    // a run of four consecutive, 4-aligned lanes (agents of one environment, sector-aligned environment blocks) is
+    // fetched with one 128-bit load per leaf
+    bool run4 = false;
+    if constexpr (LANES == 4 && MODE == kGather)
+      run4 = s.smp_vec_ok && (c[1] == c[0] + 1) && (c[2] == c[0] + 2) && (c[3] == c[0] + 3) && ((c[0] & 3) == 0);
+    // row base pointers are warp-uniform (64-bit, advanced once per row); per-thread offsets stay 32-bit
+    const float* nl_row = pr.new_logp + static_cast<long long>(r0) * s.ld_pol;
+    const float* vp_row = pr.v_pred + static_cast<long long>(r0) * s.ld_pol;
+    const float* en_row = pr.entropy + static_cast<long long>(r0) * s.ld_pol;
+    float* glp_row = pr.g_logp + static_cast<long long>(r0) * s.ld_grad;
+    float* gv_row = pr.g_value + static_cast<long long>(r0) * s.ld_grad;
+    float* ge_row = pr.g_entropy + static_cast<long long>(r0) * s.ld_grad;
+    long long ob = static_cast<long long>(r0) * s.ld_smp;  // sample-side row base (elements)
+    if (active) {
+#pragma unroll kLossUnroll
+      for (int t = r0; t < r1; ++t, nl_row += s.ld_pol, vp_row += s.ld_pol, en_row += s.ld_pol, glp_row += s.ld_grad,
+               gv_row += s.ld_grad, ge_row += s.ld_grad, ob += s.ld_smp) {
+        float nl[LANES], vp[LANES], en[LANES], ol[LANES], ov[LANES], rt[LANES], ad[LANES];
+        bool valid[LANES];
         if constexpr (LANES == 4) {
-          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.old_logp + ob + c[0])), ol);
-          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.ret + ob + c[0])), rt);
-          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.adv + ob + c[0])), ad);
-          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (CFG::clip(h)) o = ldg_stream(reinterpret_cast<const float4*>(s.old_value + ob + c[0]));
-          unpack4(o, ov);
-          const uint32_t m = ldg_stream(reinterpret_cast<const uint32_t*>(s.reset_next + ob + c[0]));
-#pragma unroll
-          for (int q = 0; q < LANES; ++q) valid[q] = ((m >> (8 * q)) & 0xffu) == 0u;
+          unpack4(ldg_stream(reinterpret_cast<const float4*>(nl_row + j)), nl);
+          unpack4(ldg_stream(reinterpret_cast<const float4*>(vp_row + j)), vp);
+          unpack4(ldg_stream(reinterpret_cast<const float4*>(en_row + j)), en);
+        } else {
+          nl[0] = ldg_stream(nl_row + j);
+          vp[0] = ldg_stream(vp_row + j);
+          en[0] = ldg_stream(en_row + j);
         }
-      } else {
-        const float* ol_row = s.old_logp + ob;
-        const float* rt_row = s.ret + ob;
-        const float* ad_row = s.adv + ob;
-        const float* ov_row = CFG::clip(h) ? s.old_value + ob : nullptr;
-        const uint8_t* rs_row = s.reset_next + ob;
+        if constexpr (MODE == kPack) {
+          const float4* pack_row = s.pack + ob;
 #pragma unroll
-        for (int q = 0; q < LANES; ++q) {
-          ol[q] = __ldg(ol_row + c[q]);
-          rt[q] = __ldg(rt_row + c[q]);
-          ad[q] = __ldg(ad_row + c[q]);
-          ov[q] = CFG::clip(h) ? __ldg(ov_row + c[q]) : 0.f;
-          valid[q] = __ldg(rs_row + c[q]) == 0;
+          for (int q = 0; q < LANES; ++q) {
+            const float4 k = __ldg(pack_row + c[q]);
+            ol[q] = k.x;
+            ov[q] = k.y;
+            rt[q] = k.z;
+            ad[q] = k.w;
+            valid[q] = (k.w == k.w);
+          }
+        } else if (run4) {
+          if constexpr (LANES == 4) {
+            unpack4(ldg_stream(reinterpret_cast<const float4*>(s.old_logp + ob + c[0])), ol);
+            unpack4(ldg_stream(reinterpret_cast<const float4*>(s.ret + ob + c[0])), rt);
+            unpack4(ldg_stream(reinterpret_cast<const float4*>(s.adv + ob + c[0])), ad);
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (CFG::clip(h)) o = ldg_stream(reinterpret_cast<const float4*>(s.old_value + ob + c[0]));
+            unpack4(o, ov);
+            const uint32_t m = ldg_stream(reinterpret_cast<const uint32_t*>(s.reset_next + ob + c[0]));
+#pragma unroll
+            for (int q = 0; q < LANES; ++q) valid[q] = ((m >> (8 * q)) & 0xffu) == 0u;
+          }
+        } else {
+          const float* ol_row = s.old_logp + ob;
+          const float* rt_row = s.ret + ob;
+          const float* ad_row = s.adv + ob;
+          const float* ov_row = CFG::clip(h) ? s.old_value + ob : nullptr;
+          const uint8_t* rs_row = s.reset_next + ob;
+#pragma unroll
+          for (int q = 0; q < LANES; ++q) {
+            ol[q] = __ldg(ol_row + c[q]);
+            rt[q] = __ldg(rt_row + c[q]);
+            ad[q] = __ldg(ad_row + c[q]);
+            ov[q] = CFG::clip(h) ? __ldg(ov_row + c[q]) : 0.f;
+            valid[q] = __ldg(rs_row + c[q]) == 0;
+          }
         }
-      }
-      float glp[LANES], gv[LANES], ge[LANES];
+        float glp[LANES], gv[LANES], ge[LANES];
 #pragma unroll
-      for (int q = 0; q < LANES; ++q)
-        element<CFG>(h, u, nl[q], vp[q], en[q], ol[q], ov[q], rt[q], ad[q], valid[q], glp[q], gv[q], ge[q], rs);
-      if (++pending == kFlushRows) {  // fp32 partial sums of at most kFlushRows * LANES terms, then float64
-        acc.add(rs);
-        rs = RowSums();
-        pending = 0;
-      }
-      if constexpr (LANES == 4) {
-        stg_stream(reinterpret_cast<float4*>(glp_row + j), make_float4(glp[0], glp[1], glp[2], glp[3]));
-        stg_stream(reinterpret_cast<float4*>(gv_row + j), make_float4(gv[0], gv[1], gv[2], gv[3]));
-        stg_stream(reinterpret_cast<float4*>(ge_row + j), make_float4(ge[0], ge[1], ge[2], ge[3]));
-      } else {
-        stg_stream(glp_row + j, glp[0]);
-        stg_stream(gv_row + j, gv[0]);
-        stg_stream(ge_row + j, ge[0]);
+        for (int q = 0; q < LANES; ++q)
+          element<CFG>(h, u, nl[q], vp[q], en[q], ol[q], ov[q], rt[q], ad[q], valid[q], glp[q], gv[q], ge[q], rs);
+        if (++pending == kFlushRows) {
+          acc.add(rs);
+          rs = RowSums();
+          pending = 0;
+        }
+        if constexpr (LANES == 4) {
+          stg_stream(reinterpret_cast<float4*>(glp_row + j), make_float4(glp[0], glp[1], glp[2], glp[3]));
+          stg_stream(reinterpret_cast<float4*>(gv_row + j), make_float4(gv[0], gv[1], gv[2], gv[3]));
+          stg_stream(reinterpret_cast<float4*>(ge_row + j), make_float4(ge[0], ge[1], ge[2], ge[3]));
+        } else {
+          stg_stream(glp_row + j, glp[0]);
+          stg_stream(gv_row + j, gv[0]);
+          stg_stream(ge_row + j, ge[0]);
+        }
       }
     }
   }
+  }  // column tiles
   acc.add(rs);
-  reduce_and_finalize(pr, h, acc, mask_sum, blockIdx.x, gridDim.x);
+  const int row = blockIdx.y * gridDim.x + blockIdx.x;
+  reduce_and_finalize(pr, h, acc, mask_sum, row, static_cast<int>(gridDim.x * gridDim.y));
 }
 
 template <int LANES, int MODE, class CFG>
 struct LossLauncher {
-  // CTAs of `threads` threads one SM holds (register-limited), asked once per device and block size
+  static constexpr bool PIPE = kUsePipe && (LANES == 4) && (MODE == kDense || MODE == kPack);
+
+  // CTAs of `threads` threads one SM holds (registers / shared memory), asked once per device and block size
   static int resident(int threads) {
     static int cached[64][2] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 2;
     int& c = cached[dev][threads >= 256 ? 1 : 0];
     if (c == 0) {
+      auto kern = ppo_loss_kernel<LANES, MODE, CFG>;
+      const size_t smem = PIPE ? loss_smem_bytes(256) : 0;
+      if (PIPE) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       int n = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ppo_loss_kernel<LANES, MODE, CFG>, threads, 0) != cudaSuccess ||
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, PIPE ? loss_smem_bytes(threads) : 0) !=
+              cudaSuccess ||
           n < 1)
         n = 1;
       c = n;
@@ -490,36 +621,26 @@ struct LossLauncher {
     const int threads = per_row <= 128 ? 128 : 256;
     s.col_tiles = (per_row + threads - 1) / threads;
     const long long capacity = static_cast<long long>(sm_count()) * resident(threads);  // CTAs resident at once
-    long long share = capacity / n_problems;  // CTAs one problem may keep resident: the whole grid is ONE wave
-    if (share < 1) share = 1;
-    if (share > kMaxGrid) share = kMaxGrid;
-    // rows per tile: minimise the rows the busiest CTA walks (= the kernel's critical path); ties go to the taller
-    // tile, whose index loads and run-of-4 test are amortised over more rows
-    int best_rows = 1;
-    long long best_path = -1, best_gx = 1;
-    for (int rows = 8; rows >= 1; rows >>= 1) {
-      const long long tiles = static_cast<long long>(s.col_tiles) * ((s.T + rows - 1) / rows);
-      const long long gx = tiles < share ? tiles : share;
-      const long long path = ((tiles + gx - 1) / gx) * rows;
-      if (best_path < 0 || path < best_path) {
-        best_path = path;
-        best_rows = rows;
-        best_gx = gx;
-      }
-    }
-    s.rows_per_tile = best_rows;
-    const long long tiles_pp = static_cast<long long>(s.col_tiles) * ((s.T + best_rows - 1) / best_rows);
-    SRL_REQUIRE(tiles_pp < (1ll << 31), SRL_ERR_UNSUPPORTED, "ppo loss: problem too large (%lld tiles)", tiles_pp);
-    s.n_tiles = static_cast<int>(tiles_pp);
-    const dim3 grid(static_cast<unsigned>(best_gx), static_cast<unsigned>(n_problems));
-    ppo_loss_kernel<LANES, MODE, CFG><<<grid, threads, 0, st>>>(b);
+    // row groups: as many as keep the whole grid resident in ONE wave (a second, partial wave would double the
+    // kernel's duration); every CTA then walks ceil(T / groups) consecutive rows of its column tile
+    long long groups = capacity / (static_cast<long long>(s.col_tiles) * n_problems);
+    if (groups < 1) groups = 1;
+    if (groups > s.T) groups = s.T;
+    int rows = static_cast<int>((s.T + groups - 1) / groups);
+    groups = (s.T + rows - 1) / rows;
+    long long gx = s.col_tiles;  // CTAs along the lanes; wider batches loop over column tiles inside the kernel
+    if (gx * groups > kMaxGrid) gx = kMaxGrid / groups;  // one partial row per CTA in the workspace slot
+    s.rows_per_tile = rows;
+    s.n_tiles = static_cast<int>(groups);
+    const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(groups), static_cast<unsigned>(n_problems));
+    ppo_loss_kernel<LANES, MODE, CFG><<<grid, threads, PIPE ? loss_smem_bytes(threads) : 0, st>>>(b);
     SRL_CUDA(cudaGetLastError());
     return SRL_OK;
   }
 };
 
 // Picks the instantiation for the launch's hyper-parameters.  Static configurations: {mse, huber} x clip_value x
-// dual_clip with four lanes per thread; everything else (smoothl1, odd shapes) runs the general instantiation.
+// dual_clip x popart with four lanes per thread; everything else (smoothl1, odd shapes) runs the general instantiation.
 template <int MODE>
 int launch_loss_mode(LossBatch& b, int n_problems, bool lanes4, cudaStream_t st) {
   const LossHyperDev& h = b.s.h;
@@ -529,19 +650,33 @@ int launch_loss_mode(LossBatch& b, int n_problems, bool lanes4, cudaStream_t st)
     else
       return LossLauncher<1, MODE, RuntimeCfg>::launch(b, n_problems, st);
   }
-  const int key = (h.value_loss == SRL_VL_MSE ? 0 : h.value_loss == SRL_VL_HUBER ? 1 : 2) * 4 + (h.clip_value ? 2 : 0) +
-                  (h.dual_clip ? 1 : 0);
+  const bool popart = b.s.popart != nullptr;
+  const int key = (h.value_loss == SRL_VL_MSE ? 0 : h.value_loss == SRL_VL_HUBER ? 1 : 2) * 8 + (h.clip_value ? 4 : 0) +
+                  (h.dual_clip ? 2 : 0) + (popart ? 1 : 0);
+#define SRL_LOSS_CASE(k, vl, clip, dual, pa) \
+  case k:                                    \
+    return LossLauncher<4, MODE, StaticCfg<vl, clip, dual, pa>>::launch(b, n_problems, st)
   switch (key) {
-    case 0: return LossLauncher<4, MODE, StaticCfg<SRL_VL_MSE, false, false>>::launch(b, n_problems, st);
-    case 1: return LossLauncher<4, MODE, StaticCfg<SRL_VL_MSE, false, true>>::launch(b, n_problems, st);
-    case 2: return LossLauncher<4, MODE, StaticCfg<SRL_VL_MSE, true, false>>::launch(b, n_problems, st);
-    case 3: return LossLauncher<4, MODE, StaticCfg<SRL_VL_MSE, true, true>>::launch(b, n_problems, st);
-    case 4: return LossLauncher<4, MODE, StaticCfg<SRL_VL_HUBER, false, false>>::launch(b, n_problems, st);
-    case 5: return LossLauncher<4, MODE, StaticCfg<SRL_VL_HUBER, false, true>>::launch(b, n_problems, st);
-    case 6: return LossLauncher<4, MODE, StaticCfg<SRL_VL_HUBER, true, false>>::launch(b, n_problems, st);
-    case 7: return LossLauncher<4, MODE, StaticCfg<SRL_VL_HUBER, true, true>>::launch(b, n_problems, st);
-    default: return LossLauncher<4, MODE, RuntimeCfg>::launch(b, n_problems, st);
+    SRL_LOSS_CASE(0, SRL_VL_MSE, false, false, false);
+    SRL_LOSS_CASE(1, SRL_VL_MSE, false, false, true);
+    SRL_LOSS_CASE(2, SRL_VL_MSE, false, true, false);
+    SRL_LOSS_CASE(3, SRL_VL_MSE, false, true, true);
+    SRL_LOSS_CASE(4, SRL_VL_MSE, true, false, false);
+    SRL_LOSS_CASE(5, SRL_VL_MSE, true, false, true);
+    SRL_LOSS_CASE(6, SRL_VL_MSE, true, true, false);
+    SRL_LOSS_CASE(7, SRL_VL_MSE, true, true, true);
+    SRL_LOSS_CASE(8, SRL_VL_HUBER, false, false, false);
+    SRL_LOSS_CASE(9, SRL_VL_HUBER, false, false, true);
+    SRL_LOSS_CASE(10, SRL_VL_HUBER, false, true, false);
+    SRL_LOSS_CASE(11, SRL_VL_HUBER, false, true, true);
+    SRL_LOSS_CASE(12, SRL_VL_HUBER, true, false, false);
+    SRL_LOSS_CASE(13, SRL_VL_HUBER, true, false, true);
+    SRL_LOSS_CASE(14, SRL_VL_HUBER, true, true, false);
+    SRL_LOSS_CASE(15, SRL_VL_HUBER, true, true, true);
+    default:
+      return LossLauncher<4, MODE, RuntimeCfg>::launch(b, n_problems, st);
   }
+#undef SRL_LOSS_CASE
 }
 
 // defined in ppo_loss_dense.cu / ppo_loss_gather.cu / ppo_loss_pack.cu

@@ -1,32 +1,43 @@
 // Group statistics over K2's per-lane partial sums, and the PopArt / RunningMeanStd update (K3).
 // See include/srl_b200.h: replaces the reductions + 3+3 single-element all-reduces of
 // utils.py:54-61 (masked_normalization) and utils.py:113-130 (RunningMeanStd.update).
-#include <cooperative_groups.h>
-
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace srl {
 namespace {
 
-constexpr int kClusterX = 8;  // CTAs cooperating on one group through distributed shared memory
 constexpr int kThreads = 256;
+constexpr int kChunkLanes = 1024;  // lanes one CTA sums (4 per thread): 8 rows x 1024 lanes x 8 B = 64 KB per CTA
+constexpr int kMaxChunks = 256;    // chunks per output row (longer rows use longer chunks)
 
-// grid = (kClusterX, G).  CTA r of the cluster sums lanes [r*chunk, (r+1)*chunk) of group g, then CTA 0
-// adds the 8 CTA results in rank order through DSMEM: fixed summation order, no atomics, no scratch.
-__global__ void __cluster_dims__(kClusterX, 1, 1) __launch_bounds__(kThreads)
-    group_stats_kernel(const double* __restrict__ lane_part, int N, const int32_t* __restrict__ idx, int per_group,
-                       int whole_first, double* __restrict__ out) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int r = static_cast<int>(cluster.block_rank());
+__host__ __device__ inline int chunks_of(int lanes) {
+  int c = (lanes + kChunkLanes - 1) / kChunkLanes;
+  return c < 1 ? 1 : (c > kMaxChunks ? kMaxChunks : c);
+}
+
+// Workspace: [rows] tickets (uint32, padded to 256 B) then [rows][kMaxChunks][8] float64 chunk partials.
+struct GroupWs {
+  unsigned int* ticket;
+  double* partial;
+};
+__host__ __device__ inline size_t ticket_bytes(int rows) { return (static_cast<size_t>(rows) * 4 + 255) / 256 * 256; }
+
+// grid = (chunks, rows).  CTA (c, r) sums chunk c of output row r in a fixed order (lane-strided per thread, warp
+// shuffle tree, warps in order); rows of one chunk are written directly, longer rows go through per-chunk partials
+// that the last CTA to arrive (atomic ticket) adds in chunk order: deterministic, no float atomics.  The first
+// version ran 8 CTAs per row whatever its length -- 68 us for the 65536-lane batch row of cfg5 (profiles/).
+__global__ void __launch_bounds__(kThreads) group_stats_kernel(const double* __restrict__ lane_part, int N,
+                                                               const int32_t* __restrict__ idx, int per_group,
+                                                               int whole_first, double* __restrict__ out, GroupWs ws) {
   // output row blockIdx.y; with whole_first, row 0 is the identity group over all N lanes
   const bool whole = whole_first && blockIdx.y == 0;
   const int g = static_cast<int>(blockIdx.y) - (whole_first ? 1 : 0);
   const int per = whole ? N : per_group;
   if (whole) idx = nullptr;
-  const int chunk = (per + kClusterX - 1) / kClusterX;
-  const int j0 = r * chunk, j1 = min(per, j0 + chunk);
+  const int n_chunks = chunks_of(per);
+  if (static_cast<int>(blockIdx.x) >= n_chunks) return;
+  const int chunk = (per + n_chunks - 1) / n_chunks;
+  const int j0 = blockIdx.x * chunk, j1 = min(per, j0 + chunk);
 
   double acc[SRL_LANE_PART];
 #pragma unroll
@@ -37,7 +48,7 @@ __global__ void __cluster_dims__(kClusterX, 1, 1) __launch_bounds__(kThreads)
     for (int k = 0; k < SRL_LANE_PART - 1; ++k) acc[k] += __ldg(lane_part + static_cast<size_t>(k) * N + lane);
   }
   __shared__ double wsum[SRL_LANE_PART][kThreads / 32];
-  __shared__ double cta_sum[SRL_LANE_PART];
+  __shared__ bool is_last;
   const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < SRL_LANE_PART; ++k) {
@@ -45,21 +56,29 @@ __global__ void __cluster_dims__(kClusterX, 1, 1) __launch_bounds__(kThreads)
     if (ln == 0) wsum[k][warp] = s;
   }
   __syncthreads();
+  double mine = 0.0;
+  if (threadIdx.x < SRL_LANE_PART) {
+    for (int w = 0; w < kThreads / 32; ++w) mine += wsum[threadIdx.x][w];
+    if (n_chunks == 1) {
+      out[static_cast<size_t>(blockIdx.y) * SRL_LANE_PART + threadIdx.x] = mine;
+    } else {
+      ws.partial[(static_cast<size_t>(blockIdx.y) * kMaxChunks + blockIdx.x) * SRL_LANE_PART + threadIdx.x] = mine;
+      __threadfence();
+    }
+  }
+  if (n_chunks == 1) return;
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&ws.ticket[blockIdx.y], 1u) == static_cast<unsigned int>(n_chunks) - 1u;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
   if (threadIdx.x < SRL_LANE_PART) {
     double s = 0.0;
-    for (int w = 0; w < kThreads / 32; ++w) s += wsum[threadIdx.x][w];
-    cta_sum[threadIdx.x] = s;
-  }
-  cluster.sync();
-  if (r == 0 && threadIdx.x < SRL_LANE_PART) {
-    double s = 0.0;
-    for (int q = 0; q < kClusterX; ++q) {
-      const double* remote = cluster.map_shared_rank(cta_sum, q);
-      s += remote[threadIdx.x];
-    }
+    for (int c = 0; c < n_chunks; ++c)
+      s += __ldcg(ws.partial + (static_cast<size_t>(blockIdx.y) * kMaxChunks + c) * SRL_LANE_PART + threadIdx.x);
     out[static_cast<size_t>(blockIdx.y) * SRL_LANE_PART + threadIdx.x] = s;
   }
-  cluster.sync();  // keep every CTA's shared memory alive until rank 0 has read it
+  if (threadIdx.x == 0) ws.ticket[blockIdx.y] = 0u;  // ready for the next launch
 }
 
 // Per-lane partial sums from adv / ret that already exist (a re-served sample whose host copy carries them,
@@ -127,8 +146,13 @@ __global__ void popart_update_kernel(const double* __restrict__ bs, double* __re
 }  // namespace
 }  // namespace srl
 
+extern "C" size_t srl_group_stats_workspace_bytes(int G, int whole_first) {
+  const int rows = G + (whole_first ? 1 : 0);
+  return srl::ticket_bytes(rows) + static_cast<size_t>(rows) * srl::kMaxChunks * SRL_LANE_PART * sizeof(double);
+}
+
 extern "C" int srl_group_stats(const double* lane_part, int N, const int32_t* idx, int G, int per, int whole_first,
-                               double* out, srl_stream_t stream) {
+                               double* out, void* workspace, size_t workspace_bytes, srl_stream_t stream) {
   using namespace srl;
   SRL_REQUIRE(lane_part && out, SRL_ERR_INVALID_ARG, "srl_group_stats: null pointer");
   SRL_REQUIRE(N >= 1 && G >= (whole_first ? 0 : 1) && per >= 1, SRL_ERR_INVALID_ARG,
@@ -136,8 +160,20 @@ extern "C" int srl_group_stats(const double* lane_part, int N, const int32_t* id
   SRL_REQUIRE(idx != nullptr || static_cast<long long>(G) * per <= N, SRL_ERR_INVALID_ARG,
               "srl_group_stats: G*per=%lld exceeds N=%d", static_cast<long long>(G) * per, N);
   SRL_REQUIRE(G <= 65535, SRL_ERR_UNSUPPORTED, "srl_group_stats: at most 65535 groups");
-  group_stats_kernel<<<dim3(kClusterX, G + (whole_first ? 1 : 0)), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      lane_part, N, idx, per, whole_first, out);
+  const int rows = G + (whole_first ? 1 : 0);
+  int max_chunks = G > 0 ? chunks_of(per) : 1;
+  if (whole_first && chunks_of(N) > max_chunks) max_chunks = chunks_of(N);
+  GroupWs ws{nullptr, nullptr};
+  if (max_chunks > 1) {
+    SRL_REQUIRE(workspace != nullptr && workspace_bytes >= srl_group_stats_workspace_bytes(G, whole_first) &&
+                    aligned(workspace, 8),
+                SRL_ERR_INVALID_ARG, "srl_group_stats: rows longer than %d lanes need a workspace of %zu bytes", kChunkLanes,
+                srl_group_stats_workspace_bytes(G, whole_first));
+    ws.ticket = static_cast<unsigned int*>(workspace);
+    ws.partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + ticket_bytes(rows));
+  }
+  group_stats_kernel<<<dim3(max_chunks, rows), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(lane_part, N, idx, per,
+                                                                                                 whole_first, out, ws);
   SRL_CUDA(cudaGetLastError());
   return SRL_OK;
 }

@@ -107,6 +107,7 @@ class HotPath:
         self.out = torch.zeros((epochs * minibatches, SRL_LOSS_OUT_LEN), dtype=torch.float64, device=dev)
         self.out_f32 = torch.zeros((epochs * minibatches, 4), dtype=torch.float32, device=dev)
         self.workspace = ops.new_loss_workspace(dev, slots=epochs * minibatches)  # one slot per (epoch, minibatch)
+        self.stats_ws = ops.group_stats_workspace(dev, epochs * minibatches if minibatches > 1 else 1, minibatches > 1)
         if not fuse_gather and minibatches > 1:  # explicit K5 gather into contiguous minibatch leaves
             self.mb_leaf = {k: f32(L, n) for k in ("old_logp", "value", "ret", "adv")}
             self.mb_leaf["on_reset"] = u8(L, n)
@@ -183,9 +184,9 @@ class HotPath:
             if permute:
                 main.wait_stream(self._perm_stream)
             ops.group_stats(self.lane_part, idx=self.perm.view(-1), groups=self.epochs * self.minibatches, per=self.n_mb,
-                            out=self.local_stats, whole_first=True)
+                            out=self.local_stats, whole_first=True, workspace=self.stats_ws)
         else:
-            ops.group_stats(self.lane_part, groups=1, per=self.N, out=self.local_stats[0:1])
+            ops.group_stats(self.lane_part, groups=1, per=self.N, out=self.local_stats[0:1], workspace=self.stats_ws)
         if self.pg is not None:
             exchange_stats(self.local_stats, self.global_stats, self.pg)
 

@@ -130,8 +130,18 @@ def lane_stats(adv, ret, done, truncated, on_reset, row_lo: int, row_hi: int,
     return lane_part
 
 
+_stats_ws = {}
+
+
+def group_stats_workspace(device, groups: int, whole_first: bool) -> torch.Tensor:
+    """Zeroed scratch for group_stats (ticket counters + per-chunk partial rows); one per concurrent stream."""
+    nbytes = int(_lib.load_library().srl_group_stats_workspace_bytes(int(groups), int(bool(whole_first))))
+    return torch.zeros(nbytes, dtype=torch.uint8, device=device)
+
+
 def group_stats(lane_part: torch.Tensor, idx: Optional[torch.Tensor] = None, groups: int = 1,
-                per: Optional[int] = None, out: Optional[torch.Tensor] = None, whole_first: bool = False) -> torch.Tensor:
+                per: Optional[int] = None, out: Optional[torch.Tensor] = None, whole_first: bool = False,
+                workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[g, k] = sum of lane_part[k, lane] over the lanes of group g (fixed summation order).
     whole_first: out gets groups + 1 rows, row 0 = the sum over all N lanes (one launch for the whole table)."""
     _check(lane_part, torch.float64, "lane_part")
@@ -147,8 +157,14 @@ def group_stats(lane_part: torch.Tensor, idx: Optional[torch.Tensor] = None, gro
     _check(out, torch.float64, "out")
     if out.numel() < rows * SRL_LANE_PART:
         raise ValueError(f"out has {out.numel()} entries, need {rows * SRL_LANE_PART}")
+    if workspace is None:  # default scratch: one per (device, stream, table shape)
+        key = (lane_part.device.index, _stream(), int(groups), bool(whole_first))
+        workspace = _stats_ws.get(key)
+        if workspace is None:
+            workspace = _stats_ws[key] = group_stats_workspace(lane_part.device, groups, whole_first)
+    _check(workspace, torch.uint8, "workspace")
     _lib.call("srl_group_stats", _ptr(lane_part), N, _ptr(idx), int(groups), int(per), int(bool(whole_first)), _ptr(out),
-              _stream())
+              _ptr(workspace), workspace.numel(), _stream())
     return out
 
 
