@@ -345,7 +345,8 @@ def run_ours(args, cfg, rank, world, local_rank):
                         l2="flushed between timed iterations (256 MiB device write, then 256 MiB device read, before each step; working set "
                            f"{step_bytes / 1e6:.0f} MB algorithmic)",
                         timing="CUDA events per step on the launch stream, sum over steps, max over ranks",
-                        launch="one CUDA graph per step" if world == 1 else "two CUDA graphs per step around one NCCL all-reduce of the float64 stats table",
+                        launch="one CUDA graph per step" + ("" if world == 1 else (" (NCCL all-reduce of the float64 stats table captured inside)"
+                                                                     if hp._graph_a is None else " split in two around the NCCL all-reduce of the float64 stats table")),
                         loss_launch=("batched: %d launch(es) per step covering %d minibatches each" %
                                      (loss_launches, E * Mb // loss_launches)) if hp._immediate else "one launch per minibatch",
                         sample_side="K2 pack (float4 per transition)" if hp.pack is not None else "separate leaves",

@@ -114,6 +114,7 @@ class HotPath:
         # pinned host mirrors for the host-facing call
         self._pin: Dict[str, torch.Tensor] = {}
         self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_a: Optional[torch.cuda.CUDAGraph] = None
         self._graph_pol = None
         self.launches_per_step = 0
 
@@ -319,8 +320,8 @@ class HotPath:
             return
         if self._graph is None or self._graph_pol is not pol:
             self._capture(pol)
-        if self.pg is None:
-            self._graph.replay()
+        if self._graph_a is None:
+            self._graph.replay()  # the whole step, the statistics all-reduce included when distributed
         else:
             self._graph_a.replay()
             exchange_stats(self.local_stats, self.global_stats, self.pg)
@@ -330,34 +331,40 @@ class HotPath:
     def _capture(self, pol) -> None:
         # NOTE: launch arguments are frozen at capture, so a replayed graph re-uses the permutations of
         # step_count == 0 every step (what a benchmark wants); the trainer launches eagerly and reseeds per step.
-        pg, self.pg = self.pg, None  # collectives stay outside the captured region
+        # warm-up on a side stream (allocations, module loading, NCCL channel set-up) before capture
+        saved = self.step_count
+        self.step_count = 0
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.advantages()
+            self._run_losses(pol)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._graph_a = None
         try:
-            # warm-up on a side stream (allocations, module loading) before capture
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                saved = self.step_count
-                self.step_count = 0
+            # one graph for the whole step; NCCL collectives are capturable, so the statistics all-reduce becomes a
+            # graph node between K2 and the loss launches instead of a host-launched call between two graphs
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
                 self.advantages()
-                self._run_losses(pol)
-            torch.cuda.current_stream().wait_stream(s)
+                self._run_losses(pol, self.graph_branches)
+            self._graph = g
+        except RuntimeError:
+            if self.pg is None:
+                raise
             torch.cuda.synchronize()
-            if pg is None:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self.advantages()
-                    self._run_losses(pol, self.graph_branches)
-                self._graph = g
-            else:
+            pg, self.pg = self.pg, None  # this NCCL / driver pair cannot capture the collective: keep it between graphs
+            try:
                 ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                 with torch.cuda.graph(ga):
                     self.advantages()
                 with torch.cuda.graph(gb):
                     self._run_losses(pol, self.graph_branches)
                 self._graph_a, self._graph = ga, gb
-            self.step_count = saved
-        finally:
-            self.pg = pg
+            finally:
+                self.pg = pg
+        self.step_count = saved
         self._graph_pol = pol
         self.launches_per_step = self.count_launches()
 
