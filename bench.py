@@ -210,7 +210,6 @@ def run_ours(args, cfg, rank, world, local_rank):
     pol_host = pol_all.cpu().pin_memory()
     out_host = dict(adv=torch.empty((cfg.L, N), dtype=torch.float32).pin_memory(),
                     ret=torch.empty((cfg.L, N), dtype=torch.float32).pin_memory(),
-                    grads=torch.empty((E, Mb, 3, T, n), dtype=torch.float32).pin_memory(),
                     out=torch.empty((E * Mb, 16), dtype=torch.float64).pin_memory())
     # L2 flush between timed iterations: write a 256 MiB buffer (> 126 MB L2), then READ a second one.  The write
     # alone leaves the L2 full of dirty lines whose write-back the timed kernels would then pay for (it showed as
@@ -356,8 +355,9 @@ def run_ours(args, cfg, rank, world, local_rank):
             clocks=clocks,
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=nbytes["h2d_bytes"],
                      d2h_bytes_per_step=nbytes["d2h_bytes"], ms_per_step=e2e_t.item() / e2e_steps * 1e3, steps=e2e_steps,
-                     what="HotPath.run_host: pinned host sample + policy outputs -> H2D -> step -> D2H of adv, ret, "
-                          "gradients and stats; wall clock incl. final stream sync"),
+                     what="HotPath.run_host: pinned host sample + policy outputs -> H2D -> step -> D2H of adv, ret (the "
+                          "reference's host mirror, mappo.py:254-257) and the loss/stats table; gradients stay in HBM for "
+                          "the policy's backward; one CUDA graph; wall clock incl. final stream sync"),
             gpu_launches=hp.count_launches() * args.steps,
             gpu_launches_per_step=hp.count_launches(),
             roofline=roofline, kernels=kern,

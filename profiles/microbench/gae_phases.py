@@ -8,11 +8,10 @@ dbg = os.path.join(ROOT, "gpurun_out", "libsrl_dbg.so")
 extra = [a for a in sys.argv if a.startswith("-D")]
 if extra and "--phases" not in sys.argv:
     dbg = os.path.join(ROOT, "gpurun_out", "libsrl_var.so")
-    subprocess.check_call([build.find_nvcc()] + build.NVCC_FLAGS + extra + ["-I", build.INCLUDE, "-o", dbg] + [os.path.join(build.CSRC, s) for s in build.SOURCES])
+    build.build(out=dbg, extra_flags=extra)
     os.environ["SRL_B200_LIB"] = dbg
 if "--phases" in sys.argv:
-    cmd = [build.find_nvcc()] + build.NVCC_FLAGS + ["-DSRL_DEBUG_PHASES", "-I", build.INCLUDE, "-o", dbg] + [os.path.join(build.CSRC, s) for s in build.SOURCES]
-    subprocess.check_call(cmd)
+    build.build(out=dbg, extra_flags=["-DSRL_DEBUG_PHASES"])
     os.environ["SRL_B200_LIB"] = dbg
 from srl_b200 import ops
 cfg = synth.CONFIGS[sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "cfg2_atari_large"]

@@ -22,19 +22,21 @@ namespace {
 constexpr int kThreads = 256;
 constexpr size_t kSmemBudget = 200 * 1024;
 
-__host__ __device__ constexpr size_t gae_smem_bytes(int L, int LW, bool vtrace) {
-  // (delta, m) (2 x f64, interleaved) + adv (f32) + v' (f32) + flags (u8), each [L][LW]
+__host__ __device__ constexpr size_t gae_smem_bytes(int L, int LW, bool pack) {
+  // (delta, m) (2 x f64, interleaved) + adv (f32) + v' (f32) + flags (u8), each [L][LW]; with the loss pack also
+  // old_logp and the raw value (2 x f32)
   // (the per-lane reduction scratch [kThreads/LW][7][LW] f64 = 14 KB aliases the same bytes)
-  (void)vtrace;
-  const size_t tile = static_cast<size_t>(L) * LW * (16 + 4 + 4 + 1);
+  const size_t tile = static_cast<size_t>(L) * LW * (16 + 4 + 4 + 1 + (pack ? 8 : 0));
   const size_t scratch = static_cast<size_t>(kThreads) * 7 * 8;
   return tile > scratch ? tile : scratch;
 }
 
-constexpr int kUnroll = 4;  // rows per thread whose global loads are issued back to back
-
-template <int LW, bool VTRACE>
+// UN = rows per thread whose global loads are issued back to back.  (UN = 8 -- the whole cfg2 trajectory in one
+// batch -- was measured: the 40 loads in flight spill at 64 registers and phase A1 got slower, 13.6 K vs 8.6 K
+// cycles; profiles/r1c_notes.md.)
+template <int LW, bool VTRACE, bool PACK, int UN>
 __global__ void __launch_bounds__(kThreads, 4) gae_scan_kernel(const GaeParams p) {
+  constexpr int kUnroll = UN;
   constexpr int RPP = kThreads / LW;  // rows handled per pass of the CTA
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int L = p.L, N = p.N;
@@ -42,7 +44,9 @@ __global__ void __launch_bounds__(kThreads, 4) gae_scan_kernel(const GaeParams p
   double2* __restrict__ sdm = reinterpret_cast<double2*>(smem_raw);   // [L][LW] .x = reward -> delta -> A_t, .y = m
   float* __restrict__ sa = reinterpret_cast<float*>(sdm + cells);      // [L][LW] vtrace importance ratio
   float* __restrict__ sv = sa + cells;                                 // [L][LW] v'
-  uint8_t* __restrict__ sf = reinterpret_cast<uint8_t*>(sv + cells);   // [L][LW] done|trunc|reset bits
+  float* __restrict__ sol = sv + cells;                                // [L][LW] old_logp   (PACK only)
+  float* __restrict__ svr = sol + (PACK ? cells : 0);                  // [L][LW] raw value  (PACK only)
+  uint8_t* __restrict__ sf = reinterpret_cast<uint8_t*>(svr + (PACK ? cells : 0));  // [L][LW] done|trunc|reset bits
 
   const int tid = threadIdx.x;
   const int lane = tid % LW;
@@ -79,6 +83,7 @@ __global__ void __launch_bounds__(kThreads, 4) gae_scan_kernel(const GaeParams p
         dn[u] = ldg_stream(p.done + g);
         tr[u] = ldg_stream(p.truncated + g);
         rs[u] = ldg_stream(p.on_reset + g);
+        if (PACK && !VTRACE) ol[u] = ldg_stream(p.old_logp + g);
         if (t < L - 1) {
           rw[u] = ldg_stream(p.reward + g);
           if (VTRACE) {
@@ -93,6 +98,10 @@ __global__ void __launch_bounds__(kThreads, 4) gae_scan_kernel(const GaeParams p
       const int t = t0 + u * RPP;
       if (t < L) {
         float vv = v[u];
+        if (PACK) {
+          svr[t * LW + lane] = vv;
+          sol[t * LW + lane] = ol[u];
+        }
         if (popart)  // RunningMeanStd.denormalize: (x.double() * std + mean).float()   utils.py:146-151
           vv = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(vv), pa_std), pa_mean));
         vv = __fmul_rn(vv, 1.f - static_cast<float>(dn[u] != 0));  // value * (1 - done), fp32   mappo.py:120-124
@@ -195,10 +204,10 @@ __global__ void __launch_bounds__(kThreads, 4) gae_scan_kernel(const GaeParams p
       const size_t g = static_cast<size_t>(t) * N + col;
       stg_stream(p.adv + g, a);
       stg_stream(p.ret + g, r);
-      if (p.pack != nullptr) {  // sample side of the loss as one 16-byte item (see include/srl_b200.h)
+      if (PACK) {  // sample side of the loss as one 16-byte item (see include/srl_b200.h)
         const bool keep = t < L - 1 && (sf[(t + 1) * LW + lane] & 4u) == 0u;
         __stcg(reinterpret_cast<float4*>(p.pack) + g,
-               make_float4(__ldg(p.old_logp + g), __ldg(p.value + g), r, keep ? a : __int_as_float(0x7fc00000)));
+               make_float4(sol[t * LW + lane], svr[t * LW + lane], r, keep ? a : __int_as_float(0x7fc00000)));
       }
     }
   }
@@ -234,10 +243,10 @@ __global__ void __launch_bounds__(kThreads, 4) gae_scan_kernel(const GaeParams p
 #endif
 }
 
-template <int LW, bool VTRACE>
-int launch(const GaeParams& p, cudaStream_t st) {
-  const size_t smem = gae_smem_bytes(p.L, LW, VTRACE);
-  auto kern = gae_scan_kernel<LW, VTRACE>;
+template <int LW, bool VTRACE, bool PACK, int UN>
+int launch_un(const GaeParams& p, cudaStream_t st) {
+  const size_t smem = gae_smem_bytes(p.L, LW, PACK);
+  auto kern = gae_scan_kernel<LW, VTRACE, PACK, UN>;
   static bool opted_in[64] = {};  // once per device and instantiation (keeps launches capturable and cheap)
   int dev = 0;
   SRL_CUDA(cudaGetDevice(&dev));
@@ -249,6 +258,14 @@ int launch(const GaeParams& p, cudaStream_t st) {
   kern<<<grid, kThreads, smem, st>>>(p);
   SRL_CUDA(cudaGetLastError());
   return SRL_OK;
+}
+
+template <int LW, bool VTRACE>
+int launch(const GaeParams& p, cudaStream_t st) {
+  // with V-trace the pack's old_logp is the V-trace leaf [L-1, N]: the general phase-A load of that leaf is
+  // reused, so row L-1 of the pack carries old_logp = 0 there (never read by the loss)
+  if (p.pack != nullptr) return launch_un<LW, VTRACE, true, 4>(p, st);
+  return launch_un<LW, VTRACE, false, 4>(p, st);
 }
 
 }  // namespace
@@ -310,11 +327,12 @@ extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8
   // Lane-tile width: the widest tile that (a) fits shared memory and (b) still gives every SM work.
   const int sms = sm_count();
   int lw = 32;
-  while (lw > 8 && (gae_smem_bytes(L, lw, vtrace) > kSmemBudget || (N + lw - 1) / lw < 2 * sms)) lw >>= 1;
+  const bool with_pack = pack != nullptr;
+  while (lw > 8 && (gae_smem_bytes(L, lw, with_pack) > kSmemBudget || (N + lw - 1) / lw < 2 * sms)) lw >>= 1;
 #ifdef SRL_DEBUG_PHASES
   if (const char* e = getenv("SRL_GAE_LW")) lw = atoi(e);  // tuning knob of the instrumented build only
 #endif
-  SRL_REQUIRE(gae_smem_bytes(L, lw, vtrace) <= kSmemBudget, SRL_ERR_UNSUPPORTED,
+  SRL_REQUIRE(gae_smem_bytes(L, lw, with_pack) <= kSmemBudget, SRL_ERR_UNSUPPORTED,
               "srl_gae_scan: L=%d does not fit the shared-memory tile (max L ~ %d)", L,
               static_cast<int>(kSmemBudget / (8 * 25)));
   if (vtrace) {

@@ -395,25 +395,71 @@ class HotPath:
         sample: the six scalar leaves (pinned tensors are copied directly, numpy arrays are staged through pinned
         memory); pol_host: pinned float32 [E, M, 3, T, n_mb] = (new_logp, v_pred, entropy) of every minibatch;
         out_host: pinned destinations 'adv', 'ret' [L, N] (the reference mirrors them into the host sample,
-        mappo.py:254-257), 'grads' [E, M, 3, T, n_mb] and 'out' [E*M, 16].
+        mappo.py:254-257), 'out' [E*M, 16] (loss scalars + stats) and optionally 'grads' [E, M, 3, T, n_mb] (the
+        gradients otherwise stay in HBM, where the policy's backward pass consumes them).
 
-        Three streams: copy-in (sample, then one epoch of policy outputs at a time), compute (advantages, then one
-        CUDA graph per epoch as soon as its inputs have landed) and copy-out (adv/ret while epoch 0 computes, each
-        epoch's gradients while the next epoch computes), so H2D, kernels and D2H overlap on the full-duplex link.
+        Three streams: copy-in (sample, then one epoch of policy outputs at a time), compute (advantages, then each
+        epoch as soon as its inputs have landed) and copy-out (adv/ret while epoch 0 computes, each epoch's gradients
+        while the next epoch computes), so H2D, kernels and D2H overlap on the full-duplex link.  With use_graph the
+        whole choreography -- copies, kernels, cross-stream dependencies -- is ONE CUDA graph keyed by the host buffer
+        addresses (the ~40 host-side launches of the eager version cost more wall clock than the kernels).
         Returns the bytes moved each way."""
         E, Mb = self.epochs, self.minibatches
         if not hasattr(self, "_pol_dev_all"):
             self._pol_dev_all = torch.empty((E, Mb, 3, self.T, self.n_mb), dtype=torch.float32, device=self.device)
             self._pol_dev = [[tuple(self._pol_dev_all[e, j, q] for q in range(3)) for j in range(Mb)] for e in range(E)]
             self._s_in, self._s_out = torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)
-            self._host_graphs = None
+            self._host_graph, self._host_graph_key = None, None
+        pinned = self._stage_sample(sample)
+        if use_graph:
+            key = tuple(pinned[k].data_ptr() for k in SAMPLE_F32 + SAMPLE_U8) + (pol_host.data_ptr(),) + \
+                tuple(out_host[k].data_ptr() for k in ("adv", "ret", "grads", "out") if k in out_host)
+            if self._host_graph is None or self._host_graph_key != key:
+                self._capture_host(pinned, pol_host, out_host)
+                self._host_graph_key = key
+            self._host_graph.replay()
+        else:
+            self._host_pipeline(pinned, pol_host, out_host, 1)
+        self.step_count += 1
+        torch.cuda.current_stream().synchronize()
+        h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in pinned) + pol_host.numel() * 4
+        d2h = 2 * self.adv.numel() * 4 + self.out.numel() * 8
+        if "grads" in out_host:
+            d2h += self.grads_all.numel() * 4
+        return dict(h2d_bytes=h2d, d2h_bytes=d2h)
+
+    def _stage_sample(self, sample) -> Dict[str, torch.Tensor]:
+        """Pinned float32 / uint8 [L*N] images of the six leaves: pinned tensors of the right type pass through,
+        anything else is converted and copied into this object's own pinned staging buffers (host work)."""
+        out = {}
+        for k in SAMPLE_F32 + SAMPLE_U8:
+            x = sample[k]
+            want_t = torch.float32 if k in SAMPLE_F32 else torch.uint8
+            if isinstance(x, torch.Tensor) and x.is_pinned() and x.dtype == want_t and x.is_contiguous() and \
+                    x.numel() == self.L * self.N:
+                out[k] = x.view(-1)
+                continue
+            if isinstance(x, torch.Tensor):
+                x = x.numpy()
+            if x.size != self.L * self.N:
+                raise ValueError(f"{k}: {x.shape} does not hold L*N = {self.L}*{self.N} elements")
+            want = np.float32 if k in SAMPLE_F32 else np.uint8
+            if x.dtype != want:
+                x = x.astype(want)
+            pin = self._pinned(k, x)
+            pin.numpy()[:] = x.reshape(-1)
+            out[k] = pin
+        return out
+
+    def _host_pipeline(self, pinned, pol_host, out_host, branches: int) -> None:
+        """The three-stream choreography of run_host (run eagerly, or under capture into one graph)."""
+        E = self.epochs
         main = torch.cuda.current_stream()
         s_in, s_out = self._s_in, self._s_out
-        if use_graph and self._host_graphs is None:
-            self._capture_host()
         s_in.wait_stream(main)
         with torch.cuda.stream(s_in):
-            h2d = self.load_sample(sample)
+            for k in SAMPLE_F32 + SAMPLE_U8:
+                self.leaf[k].view(-1).copy_(pinned[k], non_blocking=True)
             ev_sample = torch.cuda.Event()
             ev_sample.record(s_in)
             ev_pol = []
@@ -422,15 +468,8 @@ class HotPath:
                 ev = torch.cuda.Event()
                 ev.record(s_in)
                 ev_pol.append(ev)
-            h2d += pol_host.numel() * 4
         main.wait_event(ev_sample)
-        pg, graphs = self.pg, self._host_graphs
-        if use_graph:
-            graphs["adv"].replay()
-            if pg is not None:
-                exchange_stats(self.local_stats, self.global_stats, pg)
-        else:
-            self.advantages()
+        self.advantages()
         ev_adv = torch.cuda.Event()
         ev_adv.record(main)
         s_out.wait_event(ev_adv)
@@ -439,50 +478,33 @@ class HotPath:
             out_host["ret"].copy_(self.ret, non_blocking=True)
         for e in range(E):
             main.wait_event(ev_pol[e])
-            if use_graph:
-                graphs["epoch"][e].replay()
-            else:
-                self._run_epoch(e, 1)
-            ev = torch.cuda.Event()
-            ev.record(main)
-            s_out.wait_event(ev)
-            with torch.cuda.stream(s_out):
-                out_host["grads"][e].copy_(self.grads_all[e], non_blocking=True)
+            self._run_epoch(e, branches)
+            if "grads" in out_host:  # optional: the gradients normally stay in HBM for the policy's backward pass
+                ev = torch.cuda.Event()
+                ev.record(main)
+                s_out.wait_event(ev)
+                with torch.cuda.stream(s_out):
+                    out_host["grads"][e].copy_(self.grads_all[e], non_blocking=True)
         if not self._immediate:
             self.finalize()
         out_host["out"].copy_(self.out, non_blocking=True)
-        self.step_count += 1
         main.wait_stream(s_out)
-        main.synchronize()
-        d2h = 2 * self.adv.numel() * 4 + self.grads_all.numel() * 4 + self.out.numel() * 8
-        return dict(h2d_bytes=h2d, d2h_bytes=d2h)
 
-    def _capture_host(self) -> None:
-        """One CUDA graph for advantages() and one per epoch (its PopArt update + its minibatch launches on
-        parallel branches), so run_host can start an epoch the moment its policy outputs have landed."""
-        pg, self.pg = self.pg, None
+    def _capture_host(self, pinned, pol_host, out_host) -> None:
         saved = self.step_count
         self.step_count = 0
         try:
             s = torch.cuda.Stream(device=self.device)
             s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):  # warm-up outside capture
-                self.advantages()
-                self._run_epoch(0, 1)
+            with torch.cuda.stream(s):  # warm-up outside capture (allocations, NCCL channels)
+                self._host_pipeline(pinned, pol_host, out_host, 1)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
-            g_adv = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_adv):
-                self.advantages()
-            epochs = []
-            for e in range(self.epochs):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._run_epoch(e, self.graph_branches)
-                epochs.append(g)
-            self._host_graphs = dict(adv=g_adv, epoch=epochs)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._host_pipeline(pinned, pol_host, out_host, self.graph_branches)
+            self._host_graph = g
         finally:
-            self.pg = pg
             self.step_count = saved
 
     def _run_epoch(self, e: int, branches: int) -> None:
