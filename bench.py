@@ -193,7 +193,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                  bootstrap_steps=cfg.bootstrap_steps, burn_in_steps=cfg.burn_in_steps, epochs=E, minibatches=Mb, seed=0,
                  popart=cfg.popart, device=dev, process_group=pg, fuse_gather=not args.explicit_gather,
                  graph_branches=args.branches, shuffle_block=args.shuffle_block, use_pack=not args.no_pack,
-                 batch_losses=not args.no_batch)
+                 batch_losses=not args.no_batch, stats_exchange=args.exchange)
     n = hp.n_mb
     pinned = {k: torch.from_numpy(np.ascontiguousarray(v.reshape(cfg.L, N))).pin_memory() for k, v in s.items()}
     hp.load_sample(pinned)
@@ -344,8 +344,9 @@ def run_ours(args, cfg, rank, world, local_rank):
                         l2="flushed between timed iterations (256 MiB device write, then 256 MiB device read, before each step; working set "
                            f"{step_bytes / 1e6:.0f} MB algorithmic)",
                         timing="CUDA events per step on the launch stream, sum over steps, max over ranks",
-                        launch="one CUDA graph per step" + ("" if world == 1 else (" (NCCL all-reduce of the float64 stats table captured inside)"
-                                                                     if hp._graph_a is None else " split in two around the NCCL all-reduce of the float64 stats table")),
+                        launch="one CUDA graph per step" + ("" if world == 1 else (
+                            f" ({hp.exchange_kind} exchange of the float64 stats table captured inside)"
+                            if hp._graph_a is None else f" split in two around the {hp.exchange_kind} exchange of the float64 stats table")),
                         loss_launch=("batched: %d launch(es) per step covering %d minibatches each" %
                                      (loss_launches, E * Mb // loss_launches)) if hp._immediate else "one launch per minibatch",
                         sample_side="K2 pack (float4 per transition)" if hp.pack is not None else "separate leaves",
@@ -367,7 +368,10 @@ def run_ours(args, cfg, rank, world, local_rank):
                       value_l2_warm=cfg.transitions * world / (statistics.mean(ms_warm) * 1e-3)),
             cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
+    del hp, g_loss, g_gae  # CUDA graphs and peer mailboxes go before the process group does
+    torch.cuda.synchronize()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -385,6 +389,8 @@ def main():
                     help="environments per shuffled block (1 = per-environment permutation; 8 = one 32-byte sector)")
     ap.add_argument("--branches", type=int, default=16, help="parallel CUDA-graph branches for the per-minibatch launches")
     ap.add_argument("--explicit-gather", action="store_true", help="separate K5 gather launch instead of gather-on-load")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="statistics exchange across ranks: NVLink peer-memory mailboxes (p2p) or NCCL all-reduce")
     ap.add_argument("--no-pack", action="store_true", help="A/B: gather the five sample leaves instead of K2's pack")
     ap.add_argument("--no-batch", action="store_true", help="A/B: one loss launch per minibatch (parallel graph branches)")
     args = ap.parse_args()

@@ -267,6 +267,27 @@ typedef struct srl_leaf_desc {
 int srl_batch_gather(const srl_leaf_desc* leaves_host, int n_leaves, const int32_t* idx /* device [B] or NULL */,
                      int L, int B, srl_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * One-shot SUM all-reduce of a small float64 table over NVLink peer memory (one process per GPU of ONE node).
+ * Replaces the dist.all_reduce calls of masked_normalization / RunningMeanStd.update
+ * (legacy/algorithm/modules/utils.py:58-61,121-124) for the step's statistics table: every rank stores its table into
+ * every peer's mailbox, publishes a sequence number, waits for the peers' numbers in its own memory and adds the tables
+ * in rank order (bit-identical result on every rank).  One kernel launch, capturable in a CUDA graph.
+ *   create  : allocates this rank's mailbox (cudaMalloc on the CURRENT device) for tables of <= capacity doubles
+ *   handle  : 64-byte IPC handle of the local mailbox, to be sent to every peer (any host channel)
+ *   connect : `handles` = world * 64 bytes, rank-major; opens the peers' mailboxes
+ *   allreduce_sum : global[i] = sum over ranks of local[i], i < n; every rank must call it the same number of times
+ *   status  : 0, or 1 when a wait timed out (a peer never arrived); synchronises the device
+ * ------------------------------------------------------------------------------------------ */
+#define SRL_XCHG_HANDLE_BYTES 64
+typedef struct srl_xchg srl_xchg;
+int srl_xchg_create(int world, int rank, int capacity_doubles, srl_xchg** out);
+int srl_xchg_local_handle(srl_xchg* x, void* handle_out);
+int srl_xchg_connect(srl_xchg* x, const void* handles);
+int srl_xchg_allreduce_sum(srl_xchg* x, const double* local, double* global, int n, srl_stream_t stream);
+int srl_xchg_status(srl_xchg* x, int* status_out);
+int srl_xchg_destroy(srl_xchg* x);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,12 @@ SIGNATURES = {
     "srl_philox_perm": (c_int, [c_uint64, c_uint32, c_int, c_int, c_int, c_void_p, c_void_p]),
     "srl_philox4x32_10": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "srl_batch_gather": (c_int, [POINTER(LeafDesc), c_int, c_void_p, c_int, c_int, c_void_p]),
+    "srl_xchg_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),
+    "srl_xchg_local_handle": (c_int, [c_void_p, c_void_p]),
+    "srl_xchg_connect": (c_int, [c_void_p, c_void_p]),
+    "srl_xchg_allreduce_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "srl_xchg_status": (c_int, [c_void_p, POINTER(c_int)]),
+    "srl_xchg_destroy": (c_int, [c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,196 @@
+// One-shot SUM all-reduce of a small float64 table over NVLink peer memory (one process per GPU, one node).
+//
+// The only data-path collective of the step is the statistics table ([1 + E*M, 8] float64, <= a few KB): the reference
+// issues 3 + 3 one-element NCCL all-reduces per loss call for it (legacy/algorithm/modules/utils.py:58-61,121-124).
+// A tree/ring collective is pure latency at this size (NCCL: ~20 us between two graph launches at 2 GPUs, measured),
+// so every rank instead STORES its table straight into every peer's mailbox (P2P stores through NVSwitch), publishes
+// a sequence number, waits for the peers' numbers in its OWN memory, and adds the world's tables in rank order --
+// bit-identical on every rank, one kernel, capturable in the step's CUDA graph.
+//
+// Memory: each rank cudaMalloc's  mailbox[2][world][cap] float64  +  flag[2][world] uint64  +  {seq, status};
+// the allocation is exported with cudaIpcGetMemHandle and opened by the peers (host side: srl_b200/xchg.py exchanges
+// the 64-byte handles with torch.distributed.all_gather_object).  Double buffering by sequence parity makes the
+// mailbox of step s+1 independent of stragglers still reading step s.
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace srl {
+namespace {
+
+constexpr int kMaxWorld = 16;
+constexpr unsigned long long kSpinLimit = 4000000000ull;  // ~2 s of clock64 ticks: then give up with an error status
+
+struct XchgView {
+  double* mailbox[kMaxWorld];              // peer p's mailbox base (mailbox[rank] = local)
+  unsigned long long* flag[kMaxWorld];     // peer p's flag base
+  unsigned long long* seq;                 // local: launches so far
+  int* status;                             // local: 0 ok, 1 timed out
+  int world, rank, cap;
+};
+
+__global__ void __launch_bounds__(256) xchg_allreduce_kernel(const XchgView v, const double* __restrict__ local,
+                                                             double* __restrict__ global, int n) {
+  __shared__ unsigned long long s_seq;
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) {
+    s_seq = *v.seq + 1ull;
+    s_ok = 1;
+  }
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  const int par = static_cast<int>(seq & 1ull);
+  // 1. my table into every mailbox (mine included), slot [par][rank]
+  for (int p = 0; p < v.world; ++p) {
+    double* dst = v.mailbox[p] + (static_cast<size_t>(par) * v.world + v.rank) * v.cap;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = local[i];
+  }
+  __threadfence_system();  // the data is visible to the peers before the flag is
+  __syncthreads();
+  // 2. publish: flag[par][rank] = seq on every peer
+  if (threadIdx.x < v.world) {
+    volatile unsigned long long* f = v.flag[threadIdx.x] + par * v.world + v.rank;
+    *f = seq;
+  }
+  // 3. wait for everybody's flag in my own memory
+  if (threadIdx.x < v.world) {
+    volatile unsigned long long* f = v.flag[v.rank] + par * v.world + threadIdx.x;
+    const unsigned long long t0 = clock64();
+    while (*f < seq) {
+      if (static_cast<unsigned long long>(clock64()) - t0 > kSpinLimit) {
+        s_ok = 0;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  // 4. sum in rank order (same order on every rank -> bit-identical tables)
+  const double* mine = v.mailbox[v.rank] + static_cast<size_t>(par) * v.world * v.cap;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double s = 0.0;
+    for (int q = 0; q < v.world; ++q) s += __ldcv(mine + static_cast<size_t>(q) * v.cap + i);
+    global[i] = s;
+  }
+  if (threadIdx.x == 0) {
+    *v.seq = seq;
+    if (!s_ok) *v.status = 1;
+  }
+}
+
+}  // namespace
+
+struct Xchg {
+  XchgView view;
+  void* local_base = nullptr;             // my allocation
+  void* peer_base[kMaxWorld] = {};        // opened peer allocations (null for myself)
+  size_t bytes = 0;
+  bool connected = false;
+};
+
+namespace {
+size_t mailbox_bytes(int world, int cap) { return static_cast<size_t>(2) * world * cap * sizeof(double); }
+size_t flag_bytes(int world) { return (static_cast<size_t>(2) * world * sizeof(unsigned long long) + 255) / 256 * 256; }
+
+void fill_view_for(XchgView& v, int p, void* base, int world, int cap) {
+  char* b = static_cast<char*>(base);
+  v.mailbox[p] = reinterpret_cast<double*>(b);
+  v.flag[p] = reinterpret_cast<unsigned long long*>(b + mailbox_bytes(world, cap));
+}
+}  // namespace
+}  // namespace srl
+
+extern "C" int srl_xchg_create(int world, int rank, int capacity_doubles, srl_xchg** out) {
+  using namespace srl;
+  SRL_REQUIRE(out != nullptr, SRL_ERR_INVALID_ARG, "srl_xchg_create: null output");
+  SRL_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world && capacity_doubles >= 1,
+              SRL_ERR_INVALID_ARG, "srl_xchg_create: need 1 <= world <= %d, 0 <= rank < world, capacity >= 1", kMaxWorld);
+  Xchg* x = new (std::nothrow) Xchg();
+  SRL_REQUIRE(x != nullptr, SRL_ERR_CUDA, "srl_xchg_create: out of host memory");
+  x->bytes = mailbox_bytes(world, capacity_doubles) + flag_bytes(world) + 256;
+  cudaError_t e = cudaMalloc(&x->local_base, x->bytes);
+  if (e == cudaSuccess) e = cudaMemset(x->local_base, 0, x->bytes);
+  if (e != cudaSuccess) {
+    set_error("srl_xchg_create: cudaMalloc/cudaMemset of %zu bytes failed: %s", x->bytes, cudaGetErrorString(e));
+    if (x->local_base) cudaFree(x->local_base);
+    delete x;
+    return SRL_ERR_CUDA;
+  }
+  x->view.world = world;
+  x->view.rank = rank;
+  x->view.cap = capacity_doubles;
+  for (int p = 0; p < kMaxWorld; ++p) {
+    x->view.mailbox[p] = nullptr;
+    x->view.flag[p] = nullptr;
+  }
+  fill_view_for(x->view, rank, x->local_base, world, capacity_doubles);
+  char* tail = static_cast<char*>(x->local_base) + mailbox_bytes(world, capacity_doubles) + flag_bytes(world);
+  x->view.seq = reinterpret_cast<unsigned long long*>(tail);
+  x->view.status = reinterpret_cast<int*>(tail + 64);
+  x->connected = (world == 1);
+  *out = reinterpret_cast<srl_xchg*>(x);
+  return SRL_OK;
+}
+
+extern "C" int srl_xchg_local_handle(srl_xchg* h, void* handle_out) {
+  using namespace srl;
+  SRL_REQUIRE(h && handle_out, SRL_ERR_INVALID_ARG, "srl_xchg_local_handle: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == SRL_XCHG_HANDLE_BYTES, "IPC handle size");
+  Xchg* x = reinterpret_cast<Xchg*>(h);
+  cudaIpcMemHandle_t mh;
+  SRL_CUDA(cudaIpcGetMemHandle(&mh, x->local_base));
+  memcpy(handle_out, &mh, sizeof(mh));
+  return SRL_OK;
+}
+
+extern "C" int srl_xchg_connect(srl_xchg* h, const void* handles) {
+  using namespace srl;
+  SRL_REQUIRE(h && handles, SRL_ERR_INVALID_ARG, "srl_xchg_connect: null pointer");
+  Xchg* x = reinterpret_cast<Xchg*>(h);
+  const char* hb = static_cast<const char*>(handles);
+  for (int p = 0; p < x->view.world; ++p) {
+    if (p == x->view.rank || x->peer_base[p] != nullptr) continue;
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, hb + static_cast<size_t>(p) * SRL_XCHG_HANDLE_BYTES, sizeof(mh));
+    void* base = nullptr;
+    SRL_CUDA(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+    x->peer_base[p] = base;
+    fill_view_for(x->view, p, base, x->view.world, x->view.cap);
+  }
+  x->connected = true;
+  return SRL_OK;
+}
+
+extern "C" int srl_xchg_allreduce_sum(srl_xchg* h, const double* local, double* global, int n, srl_stream_t stream) {
+  using namespace srl;
+  SRL_REQUIRE(h && local && global, SRL_ERR_INVALID_ARG, "srl_xchg_allreduce_sum: null pointer");
+  Xchg* x = reinterpret_cast<Xchg*>(h);
+  SRL_REQUIRE(x->connected, SRL_ERR_INVALID_ARG, "srl_xchg_allreduce_sum: peers not connected (srl_xchg_connect)");
+  SRL_REQUIRE(n >= 0 && n <= x->view.cap, SRL_ERR_INVALID_ARG, "srl_xchg_allreduce_sum: n=%d exceeds the capacity %d", n,
+              x->view.cap);
+  if (n == 0) return SRL_OK;
+  xchg_allreduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(x->view, local, global, n);
+  SRL_CUDA(cudaGetLastError());
+  return SRL_OK;
+}
+
+extern "C" int srl_xchg_status(srl_xchg* h, int* status_out) {
+  using namespace srl;
+  SRL_REQUIRE(h && status_out, SRL_ERR_INVALID_ARG, "srl_xchg_status: null pointer");
+  Xchg* x = reinterpret_cast<Xchg*>(h);
+  SRL_CUDA(cudaMemcpy(status_out, x->view.status, sizeof(int), cudaMemcpyDeviceToHost));
+  return SRL_OK;
+}
+
+extern "C" int srl_xchg_destroy(srl_xchg* h) {
+  using namespace srl;
+  if (h == nullptr) return SRL_OK;
+  Xchg* x = reinterpret_cast<Xchg*>(h);
+  for (int p = 0; p < kMaxWorld; ++p)
+    if (x->peer_base[p]) cudaIpcCloseMemHandle(x->peer_base[p]);
+  if (x->local_base) cudaFree(x->local_base);
+  delete x;
+  return SRL_OK;
+}

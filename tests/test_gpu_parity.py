@@ -670,3 +670,25 @@ def test_loss_batched_more_problems_than_one_launch(ops):
         _, _, _, o, _ = ops.ppo_loss_fwd_bwd(q["new_logp"], q["v_pred"], q["entropy"], d["old_logp"][:T], d["value"][:T],
                                              ret[:T], adv[:T], d["on_reset"][1:T + 1], stats, hp)
         np.testing.assert_allclose(out[k].cpu().numpy(), o.cpu().numpy(), rtol=1e-12, atol=1e-14)
+
+
+def test_peer_exchange_single_rank(ops):
+    """world == 1: the mailbox exchange degenerates to a copy through the local mailbox; sequence numbers advance."""
+    import ctypes
+    from srl_b200 import _lib
+    h = ctypes.c_void_p()
+    _lib.call("srl_xchg_create", 1, 0, 64, ctypes.byref(h))
+    try:
+        for it in range(5):
+            a = torch.randn(40, dtype=torch.float64, device="cuda")
+            out = torch.zeros_like(a)
+            _lib.call("srl_xchg_allreduce_sum", h, a.data_ptr(), out.data_ptr(), 40, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert torch.equal(a, out)
+        st = ctypes.c_int(-1)
+        _lib.call("srl_xchg_status", h, ctypes.byref(st))
+        assert st.value == 0
+        with pytest.raises(_lib.SrlCudaError, match="capacity"):
+            _lib.call("srl_xchg_allreduce_sum", h, a.data_ptr(), out.data_ptr(), 65, None)
+    finally:
+        _lib.call("srl_xchg_destroy", h)
