@@ -7,10 +7,16 @@
 // a sequence number, waits for the peers' numbers in its OWN memory, and adds the world's tables in rank order --
 // bit-identical on every rank, one kernel, capturable in the step's CUDA graph.
 //
-// Memory: each rank cudaMalloc's  mailbox[2][world][cap] float64  +  flag[2][world] uint64  +  {seq, status};
-// the allocation is exported with cudaIpcGetMemHandle and opened by the peers (host side: srl_b200/xchg.py exchanges
-// the 64-byte handles with torch.distributed.all_gather_object).  Double buffering by sequence parity makes the
-// mailbox of step s+1 independent of stragglers still reading step s.
+// Protocol ("LL", as in low-latency collectives): every 8-byte store carries 4 bytes of payload and the 4-byte
+// sequence number of the exchange, and an aligned 8-byte store is delivered atomically -- so there is no separate flag,
+// no system-wide fence and no second round: the receiver spins on each word until its sequence number matches.  A
+// float64 travels as two such words.
+//
+// Memory: each rank cudaMalloc's  mailbox[2][world][cap][2] x uint64  +  {seq, status}; the allocation is exported with
+// cudaIpcGetMemHandle and opened by the peers (host side: srl_b200/xchg.py exchanges the 64-byte handles with
+// torch.distributed.all_gather_object).  Double buffering by sequence parity makes the mailbox of exchange s+1
+// independent of stragglers still reading exchange s (a rank can only reach s+2 after everybody published s+1, i.e.
+// finished reading s).
 #include <string.h>
 
 #include <new>
@@ -21,62 +27,60 @@ namespace srl {
 namespace {
 
 constexpr int kMaxWorld = 16;
-constexpr unsigned long long kSpinLimit = 4000000000ull;  // ~2 s of clock64 ticks: then give up with an error status
+constexpr long long kSpinLimit = 4000000000ll;  // ~2 s of clock64 ticks: then give up with an error status
 
 struct XchgView {
-  double* mailbox[kMaxWorld];              // peer p's mailbox base (mailbox[rank] = local)
-  unsigned long long* flag[kMaxWorld];     // peer p's flag base
-  unsigned long long* seq;                 // local: launches so far
-  int* status;                             // local: 0 ok, 1 timed out
+  unsigned long long* mailbox[kMaxWorld];  // peer p's mailbox base (mailbox[rank] = local); words = seq << 32 | payload
+  unsigned int* seq;          // local: exchanges so far
+  int* status;                // local: 0 ok, 1 timed out
   int world, rank, cap;
 };
 
 __global__ void __launch_bounds__(256) xchg_allreduce_kernel(const XchgView v, const double* __restrict__ local,
                                                              double* __restrict__ global, int n) {
-  __shared__ unsigned long long s_seq;
-  __shared__ int s_ok;
-  if (threadIdx.x == 0) {
-    s_seq = *v.seq + 1ull;
-    s_ok = 1;
-  }
-  __syncthreads();
-  const unsigned long long seq = s_seq;
-  const int par = static_cast<int>(seq & 1ull);
-  // 1. my table into every mailbox (mine included), slot [par][rank]
-  for (int p = 0; p < v.world; ++p) {
-    double* dst = v.mailbox[p] + (static_cast<size_t>(par) * v.world + v.rank) * v.cap;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = local[i];
-  }
-  __threadfence_system();  // the data is visible to the peers before the flag is
-  __syncthreads();
-  // 2. publish: flag[par][rank] = seq on every peer
-  if (threadIdx.x < v.world) {
-    volatile unsigned long long* f = v.flag[threadIdx.x] + par * v.world + v.rank;
-    *f = seq;
-  }
-  // 3. wait for everybody's flag in my own memory
-  if (threadIdx.x < v.world) {
-    volatile unsigned long long* f = v.flag[v.rank] + par * v.world + threadIdx.x;
-    const unsigned long long t0 = clock64();
-    while (*f < seq) {
-      if (static_cast<unsigned long long>(clock64()) - t0 > kSpinLimit) {
-        s_ok = 0;
-        break;
-      }
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  unsigned int seq = *v.seq + 1u;
+  if (seq == 0u) seq = 1u;  // 0 is the mailbox's initial state
+  const int par = static_cast<int>(seq & 1u);
+  __syncthreads();  // everybody has read the old sequence number before thread 0 updates it
+  // 1. my table, two {payload, seq} words per float64, into every mailbox (mine included), slot [par][rank]
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double x = local[i];
+    const unsigned long long tag = static_cast<unsigned long long>(seq) << 32;
+    const unsigned long long lo = tag | static_cast<unsigned int>(__double2loint(x));
+    const unsigned long long hi = tag | static_cast<unsigned int>(__double2hiint(x));
+    for (int p = 0; p < v.world; ++p) {
+      volatile unsigned long long* dst = v.mailbox[p] + ((static_cast<size_t>(par) * v.world + v.rank) * v.cap + i) * 2;
+      dst[0] = lo;
+      dst[1] = hi;
     }
   }
-  __syncthreads();
-  __threadfence_system();
-  // 4. sum in rank order (same order on every rank -> bit-identical tables)
-  const double* mine = v.mailbox[v.rank] + static_cast<size_t>(par) * v.world * v.cap;
+  // 2. collect: spin on each word of each rank's slot in my own mailbox, add in rank order (the same order on every
+  //    rank -> bit-identical tables)
+  const unsigned long long* mine = v.mailbox[v.rank] + static_cast<size_t>(par) * v.world * v.cap * 2;
+  const long long t0 = clock64();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double s = 0.0;
-    for (int q = 0; q < v.world; ++q) s += __ldcv(mine + static_cast<size_t>(q) * v.cap + i);
+    for (int q = 0; q < v.world; ++q) {
+      const volatile unsigned long long* src = mine + (static_cast<size_t>(q) * v.cap + i) * 2;
+      unsigned long long lo = src[0], hi = src[1];
+      while (static_cast<unsigned int>(lo >> 32) != seq || static_cast<unsigned int>(hi >> 32) != seq) {
+        if (clock64() - t0 > kSpinLimit) {
+          s_bad = 1;
+          break;
+        }
+        lo = src[0];
+        hi = src[1];
+      }
+      s += __hiloint2double(static_cast<int>(static_cast<unsigned int>(hi)), static_cast<int>(static_cast<unsigned int>(lo)));
+    }
     global[i] = s;
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
     *v.seq = seq;
-    if (!s_ok) *v.status = 1;
+    if (s_bad) *v.status = 1;
   }
 }
 
@@ -91,14 +95,11 @@ struct Xchg {
 };
 
 namespace {
-size_t mailbox_bytes(int world, int cap) { return static_cast<size_t>(2) * world * cap * sizeof(double); }
-size_t flag_bytes(int world) { return (static_cast<size_t>(2) * world * sizeof(unsigned long long) + 255) / 256 * 256; }
-
-void fill_view_for(XchgView& v, int p, void* base, int world, int cap) {
-  char* b = static_cast<char*>(base);
-  v.mailbox[p] = reinterpret_cast<double*>(b);
-  v.flag[p] = reinterpret_cast<unsigned long long*>(b + mailbox_bytes(world, cap));
+size_t mailbox_bytes(int world, int cap) {
+  return (static_cast<size_t>(2) * world * cap * 2 * sizeof(unsigned long long) + 255) / 256 * 256;
 }
+
+void fill_view_for(XchgView& v, int p, void* base, int, int) { v.mailbox[p] = static_cast<unsigned long long*>(base); }
 }  // namespace
 }  // namespace srl
 
@@ -109,7 +110,7 @@ extern "C" int srl_xchg_create(int world, int rank, int capacity_doubles, srl_xc
               SRL_ERR_INVALID_ARG, "srl_xchg_create: need 1 <= world <= %d, 0 <= rank < world, capacity >= 1", kMaxWorld);
   Xchg* x = new (std::nothrow) Xchg();
   SRL_REQUIRE(x != nullptr, SRL_ERR_CUDA, "srl_xchg_create: out of host memory");
-  x->bytes = mailbox_bytes(world, capacity_doubles) + flag_bytes(world) + 256;
+  x->bytes = mailbox_bytes(world, capacity_doubles) + 256;
   cudaError_t e = cudaMalloc(&x->local_base, x->bytes);
   if (e == cudaSuccess) e = cudaMemset(x->local_base, 0, x->bytes);
   if (e != cudaSuccess) {
@@ -121,13 +122,10 @@ extern "C" int srl_xchg_create(int world, int rank, int capacity_doubles, srl_xc
   x->view.world = world;
   x->view.rank = rank;
   x->view.cap = capacity_doubles;
-  for (int p = 0; p < kMaxWorld; ++p) {
-    x->view.mailbox[p] = nullptr;
-    x->view.flag[p] = nullptr;
-  }
+  for (int p = 0; p < kMaxWorld; ++p) x->view.mailbox[p] = nullptr;
   fill_view_for(x->view, rank, x->local_base, world, capacity_doubles);
-  char* tail = static_cast<char*>(x->local_base) + mailbox_bytes(world, capacity_doubles) + flag_bytes(world);
-  x->view.seq = reinterpret_cast<unsigned long long*>(tail);
+  char* tail = static_cast<char*>(x->local_base) + mailbox_bytes(world, capacity_doubles);
+  x->view.seq = reinterpret_cast<unsigned int*>(tail);
   x->view.status = reinterpret_cast<int*>(tail + 64);
   x->connected = (world == 1);
   *out = reinterpret_cast<srl_xchg*>(x);
