@@ -320,8 +320,14 @@ def run_ours(args, cfg, rank, world, local_rank):
                                 step_share=gae_ms / ms_per_step),
     }
     dom = max(kern, key=lambda k_: kern[k_]["step_share"])
+    traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(cfg.name, {}).get(dom)
+    except Exception:
+        pass
     roofline = dict(bound="hbm", kernel=dom, achieved=kern[dom]["gbs"], peak=peak, unit="GB/s",
-                    frac=kern[dom]["gbs"] / peak, traffic=None, peak_source=peak_src,
+                    frac=kern[dom]["gbs"] / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=kern[dom]["bytes_per_launch"],
                     ms_per_launch=kern[dom]["ms_per_launch"])
     step_bytes = gae_bytes + LOSS_BYTES[bool(cfg.clip_value)] * T * N * E

@@ -33,7 +33,31 @@ WANT = [
 ]
 
 
+def traffic(rep):
+    """{kernel base name: DRAM bytes (read + write) per launch, averaged over the profiled launches}."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = {}
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]]
+        base = "ppo_loss_kernel" if "ppo_loss_kernel" in name else "gae_scan_kernel" if "gae_scan" in name else name.split("(")[0]
+        tot = sum(float(r[idx[k]]) * scale[units[idx[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        acc.setdefault(base, []).append(tot)
+    return {k: sum(v) / len(v) for k, v in acc.items()}
+
+
 def main():
+    if sys.argv[1] == "--traffic":  # python profiles/summarize_ncu.py --traffic cfg=report.ncu-rep ... > profiles/traffic.json
+        import json
+        out = {}
+        for arg in sys.argv[2:]:
+            cfg, rep = arg.split("=", 1)
+            out[cfg] = dict(traffic(rep), source=rep.split("/")[-1])
+        print(json.dumps(out, indent=1))
+        return
     rep = sys.argv[1]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))

@@ -264,6 +264,14 @@ template <int LW, bool VTRACE>
 int launch(const GaeParams& p, cudaStream_t st) {
   // with V-trace the pack's old_logp is the V-trace leaf [L-1, N]: the general phase-A load of that leaf is
   // reused, so row L-1 of the pack carries old_logp = 0 there (never read by the loss)
+  constexpr int RPP = kThreads / LW;
+  const int rows_per_thread = (p.L + RPP - 1) / RPP;
+  // 5 or 6 rows per thread (cfg2: L = 129 over 32 rows per pass): all loads of the tile in ONE batch, i.e. one exposed
+  // DRAM round trip in phase A1 instead of two
+  if (!VTRACE && rows_per_thread == 5)
+    return p.pack != nullptr ? launch_un<LW, false, true, 5>(p, st) : launch_un<LW, false, false, 5>(p, st);
+  if (!VTRACE && rows_per_thread == 6)
+    return p.pack != nullptr ? launch_un<LW, false, true, 6>(p, st) : launch_un<LW, false, false, 6>(p, st);
   if (p.pack != nullptr) return launch_un<LW, VTRACE, true, 4>(p, st);
   return launch_un<LW, VTRACE, false, 4>(p, st);
 }
