@@ -258,10 +258,13 @@ int srl_philox4x32_10(const uint32_t* counter, const uint32_t* key, int n_blocks
  * ------------------------------------------------------------------------------------------ */
 #define SRL_MAX_LEAVES 32
 typedef struct srl_leaf_desc {
-  const void* src;   /* [L, src_slots, row_bytes] */
-  void* dst;         /* [L, B, row_bytes]         */
-  int64_t row_bytes; /* bytes per (t, slot) item  */
-  int64_t src_slots; /* slots (columns) in src    */
+  const void* src;         /* item (t, slot) at src + t * src_t_stride + slot * src_slot_stride                      */
+  void* dst;               /* [L, B, row_bytes]                                                                       */
+  int64_t row_bytes;       /* bytes per (t, slot) item                                                                */
+  int64_t src_slots;       /* slots addressable in src                                                                */
+  int64_t src_t_stride;    /* 0 = row_bytes * src_slots: src is [L, src_slots, row] (SharedMemoryDock's slab layout)  */
+  int64_t src_slot_stride; /* 0 = row_bytes; L * row_bytes with src_t_stride = row_bytes: src is [slots, L, row],
+                              i.e. whole samples staged one after another -- the gather is np.stack(axis=1)           */
 } srl_leaf_desc;
 
 int srl_batch_gather(const srl_leaf_desc* leaves_host, int n_leaves, const int32_t* idx /* device [B] or NULL */,

@@ -65,7 +65,8 @@ class LossProblem(ctypes.Structure):
 
 class LeafDesc(ctypes.Structure):
     """struct srl_leaf_desc"""
-    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("row_bytes", c_int64), ("src_slots", c_int64)]
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("row_bytes", c_int64), ("src_slots", c_int64),
+                ("src_t_stride", c_int64), ("src_slot_stride", c_int64)]
 
 
 # name -> (restype, argtypes); must list every symbol include/srl_b200.h declares

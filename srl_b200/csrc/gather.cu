@@ -1,5 +1,6 @@
 // K1 / K5b: batch assembly and minibatch gather over many leaves in one call (bit-exact byte copy).
-// dst[t, j, :] = src[t, idx[j], :] -- replaces recursive_aggregate(np.stack(axis=1)) of
+// dst[t, j, :] = src(t, idx[j], :) with src either [L, slots, row] (a slot slab) or [slots, L, row] (per-sample
+// staging: the np.stack(axis=1) transpose itself) -- replaces recursive_aggregate(np.stack(axis=1)) of
 // PriorityQueueBuffer.put (base/buffer.py:118-126, base/namedarray.py:598-633) and
 // SharedMemoryDock.get (base/shared_memory.py:85-99).
 //
@@ -19,7 +20,8 @@ struct GatherLeaf {
   const unsigned char* src;
   unsigned char* dst;
   long long row_bytes;
-  long long src_slots;
+  long long t_stride;     // bytes from (t, slot) to (t + 1, slot) in src
+  long long slot_stride;  // bytes from (t, slot) to (t, slot + 1) in src
   long long item_begin;  // prefix sum of items (L * B per leaf) inside this bucket
   int unit;              // copy granule: 16, 4 or 1 bytes
 };
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
     const long long t = local / p.B;
     const int j = static_cast<int>(local - t * p.B);
     const long long slot = p.idx ? p.idx[j] : j;
-    const unsigned char* s = lf.src + (t * lf.src_slots + slot) * lf.row_bytes;
+    const unsigned char* s = lf.src + t * lf.t_stride + slot * lf.slot_stride;
     unsigned char* d = lf.dst + local * lf.row_bytes;
     if (lf.unit == 16)
       copy_row<16, GS>(s, d, lf.row_bytes, member);
@@ -131,10 +133,13 @@ extern "C" int srl_batch_gather(const srl_leaf_desc* leaves, int n_leaves, const
                 "srl_batch_gather: leaf %d has a null pointer or non-positive size", i);
     SRL_REQUIRE(idx != nullptr || d.src_slots >= B, SRL_ERR_INVALID_ARG,
                 "srl_batch_gather: leaf %d has %lld slots < B=%d", i, static_cast<long long>(d.src_slots), B);
+    const long long t_stride = d.src_t_stride ? d.src_t_stride : d.row_bytes * d.src_slots;
+    const long long slot_stride = d.src_slot_stride ? d.src_slot_stride : d.row_bytes;
+    SRL_REQUIRE(t_stride > 0 && slot_stride > 0, SRL_ERR_INVALID_ARG, "srl_batch_gather: leaf %d has a negative stride", i);
     int unit = 1;
-    if (d.row_bytes % 16 == 0 && aligned(d.src, 16) && aligned(d.dst, 16))
+    if (d.row_bytes % 16 == 0 && aligned(d.src, 16) && aligned(d.dst, 16) && t_stride % 16 == 0 && slot_stride % 16 == 0)
       unit = 16;
-    else if (d.row_bytes % 4 == 0 && aligned(d.src, 4) && aligned(d.dst, 4))
+    else if (d.row_bytes % 4 == 0 && aligned(d.src, 4) && aligned(d.dst, 4) && t_stride % 4 == 0 && slot_stride % 4 == 0)
       unit = 4;
     const int which = d.row_bytes >= 4096 ? 2 : (d.row_bytes >= 64 ? 1 : 0);
     GatherParams& b = bucket[which];
@@ -142,7 +147,8 @@ extern "C" int srl_batch_gather(const srl_leaf_desc* leaves, int n_leaves, const
     g.src = static_cast<const unsigned char*>(d.src);
     g.dst = static_cast<unsigned char*>(d.dst);
     g.row_bytes = d.row_bytes;
-    g.src_slots = d.src_slots;
+    g.t_stride = t_stride;
+    g.slot_stride = slot_stride;
     g.item_begin = b.total_items;
     g.unit = unit;
     b.total_items += static_cast<long long>(L) * B;

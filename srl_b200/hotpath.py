@@ -153,6 +153,11 @@ class HotPath:
         for k in SAMPLE_F32 + SAMPLE_U8:
             x = sample[k]
             want = np.float32 if k in SAMPLE_F32 else np.uint8
+            if isinstance(x, torch.Tensor) and x.is_cuda:  # device-resident batch: a device copy (+ dtype narrowing)
+                if x.numel() != self.L * self.N:
+                    raise ValueError(f"{k}: {tuple(x.shape)} does not hold L*N = {self.L}*{self.N} elements")
+                self.leaf[k].view(-1).copy_(x.reshape(-1), non_blocking=True)
+                continue
             if isinstance(x, torch.Tensor):
                 if x.is_pinned() and x.dtype == (torch.float32 if k in SAMPLE_F32 else torch.uint8) and \
                         x.numel() == self.L * self.N and x.is_contiguous():

@@ -464,6 +464,19 @@ def philox_perm(seed: int, epoch: int, n_env: int, group: int = 1, out: Optional
     return out
 
 
+def stack_samples(descs: Sequence[LeafDesc], idx: Optional[torch.Tensor], L: int, B: int) -> None:
+    """Raw form of batch_gather for callers that build their own leaf descriptors (srl_b200.buffer: samples staged
+    one after another, [slots, L, row], gathered into [L, B, row] = np.stack(axis=1))."""
+    if idx is not None:
+        _check(idx, torch.int32, "idx")
+        if idx.numel() != B:
+            raise ValueError(f"idx has {idx.numel()} entries, expected B = {B}")
+    for i in range(0, len(descs), SRL_MAX_LEAVES):
+        chunk = list(descs[i:i + SRL_MAX_LEAVES])
+        arr = (LeafDesc * len(chunk))(*chunk)
+        _lib.call("srl_batch_gather", arr, len(chunk), _ptr(idx), int(L), int(B), _stream())
+
+
 def philox4x32_10(counter: torch.Tensor, key: torch.Tensor) -> torch.Tensor:
     """Raw Philox blocks for known-answer tests: counter int32-viewed uint32 [n, 4], key [n, 2]."""
     _check(counter, torch.int32, "counter")
@@ -493,7 +506,7 @@ def batch_gather(pairs: List[Tuple[torch.Tensor, torch.Tensor]], idx: Optional[t
             raise ValueError(f"leaf {k}: src {tuple(src.shape)}/{src.dtype} and dst {tuple(dst.shape)}/{dst.dtype} "
                              f"are not a [L, slots, ...] -> [L, B, ...] pair")
         row_bytes = dst[0, 0].numel() * dst.element_size() if dst.dim() > 2 else dst.element_size()
-        descs.append(LeafDesc(src.data_ptr(), dst.data_ptr(), row_bytes, src.shape[1]))
+        descs.append(LeafDesc(src.data_ptr(), dst.data_ptr(), row_bytes, src.shape[1], 0, 0))
     for i in range(0, len(descs), SRL_MAX_LEAVES):
         chunk = descs[i:i + SRL_MAX_LEAVES]
         arr = (LeafDesc * len(chunk))(*chunk)

@@ -173,9 +173,13 @@ class MultiAgentPPOB200(PytorchTrainer):
 
     def _stage(self, sample):
         """Host -> device copy of the whole sample as float32 on a side stream: the tensors `policy.analyze`
-        receives, exactly what PyTorchGPUPrefetcher builds (api/trainer.py:211-217)."""
+        receives, exactly what PyTorchGPUPrefetcher builds (api/trainer.py:211-217).  A batch that already lives in
+        HBM (srl_b200.buffer.DeviceSlabBuffer) is only cast, on the same side stream."""
+        self._copy_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._copy_stream):
-            tensors = recursive_apply(sample, lambda x: torch.from_numpy(x).cuda(non_blocking=True).float())
+            tensors = recursive_apply(
+                sample, lambda x: x.float() if isinstance(x, torch.Tensor) else
+                torch.from_numpy(x).cuda(non_blocking=True).float())
         return sample, tensors
 
     @staticmethod
@@ -189,8 +193,9 @@ class MultiAgentPPOB200(PytorchTrainer):
 
     # ----------------------------------------------------------------------------------------------------
     def step(self, sample) -> TrainerStepResult:
+        on_device = isinstance(sample.on_reset, torch.Tensor)  # a DeviceSlabBuffer batch: nothing crosses PCIe
         if sample.truncated is None:  # mappo.py:222-223
-            sample.truncated = np.zeros_like(sample.done)
+            sample.truncated = torch.zeros_like(sample.done) if on_device else np.zeros_like(sample.done)
         if self.recompute_adv_on_reuse:  # mappo.py:224-225
             sample.analyzed_result.adv = sample.analyzed_result.ret = None
 
@@ -201,6 +206,7 @@ class MultiAgentPPOB200(PytorchTrainer):
                 return TrainerStepResult({}, 0)  # api/trainer.py:220-223: the first call only primes the pipeline
         torch.cuda.current_stream().wait_stream(self._copy_stream)
         sample, tensor_sample = staged
+        on_device = isinstance(sample.on_reset, torch.Tensor)
 
         L = tensor_sample.on_reset.shape[0]
         B, A = self._lanes(sample.on_reset)
@@ -263,6 +269,9 @@ class MultiAgentPPOB200(PytorchTrainer):
         n_loss = self.ppo_epochs * self.num_minibatches
         if self.recompute_adv_among_epochs:  # mappo.py:287-289 leaves the host copies cleared
             ar.adv = ar.ret = None
+        elif on_device:  # the cached copies stay in HBM next to the batch
+            ar.adv = hp.adv.reshape((L,) + lead).clone()
+            ar.ret = hp.ret.reshape((L,) + lead).clone()
         else:  # mappo.py:254-257: the buffer may serve this sample again and reuse them
             ar.adv = hp.adv.cpu().numpy().reshape((L,) + lead)
             ar.ret = hp.ret.cpu().numpy().reshape((L,) + lead)
@@ -285,7 +294,7 @@ class MultiAgentPPOB200(PytorchTrainer):
         self.frames += int(np.prod(sample.on_reset[valid].shape))
         info = {}
         if getattr(sample, "info_mask", None) is not None and sample.info is not None:  # mappo.py:317-324
-            elapsed = sample.info_mask[valid].sum()
+            elapsed = float(sample.info_mask[valid].sum())
             if elapsed != 0:
                 info = {k: float((v[valid] * sample.info_mask[valid]).sum() / elapsed) for k, v in flatten(sample.info)
                         if v is not None}

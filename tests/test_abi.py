@@ -59,7 +59,7 @@ def test_abi_version_and_error_text(lib):
 
 def test_struct_layouts_match_header(lib):
     assert ctypes.sizeof(_lib.PpoHyper) == 7 * 8 + 4 * 4
-    assert ctypes.sizeof(_lib.LeafDesc) == 32
+    assert ctypes.sizeof(_lib.LeafDesc) == 48
     assert ctypes.sizeof(_lib.LossProblem) == 12 * 8
     assert lib.srl_ppo_loss_workspace_bytes(128, 4096) >= 64 + 148 * 8 * 8 * 8
 
