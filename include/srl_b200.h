@@ -86,6 +86,15 @@ int srl_gae_scan(const float* reward,          /* [L, N]; row L-1 is ignored    
                  float* pack,       /* [L, N, 4] out or NULL */
                  srl_stream_t stream);
 
+/* n-step return on the same [rows, N] layout (rows = n + T - 1): replaces modules.n_step_return
+ * (legacy/algorithm/modules/n_step_return.py:11-50; the return estimator of the DQN / QMIX trainers), float64 with the
+ * reference's operation order, float32 result out[T, N]:
+ *   ret += reward[t+i] * disc;  ret += disc * gamma * nex_truncated[t+i] * nex_value[t+i];
+ *   disc *= gamma * (1 - nex_done[t+i]) * (1 - nex_truncated[t+i])   for i in [0, n);  out[t] = ret + disc * nex_value[t+n-1] */
+int srl_n_step_return(const float* reward, const float* nex_value, const uint8_t* nex_done,
+                      const uint8_t* nex_truncated, int n, int rows, int N, double gamma, float* out,
+                      srl_stream_t stream);
+
 /* The same [SRL_LANE_PART][N] table from adv / ret that already exist: a sample re-served by the buffer carries
  * them in its host copy and MultiAgentPPO.step skips GAE for it (mappo.py:224-225,249 with
  * recompute_adv_on_reuse=False; base/buffer.py:142-162 re-serves a ReplayEntry `reuses` times). */

@@ -205,14 +205,36 @@ def gen_stack(R):
     np.savez_compressed(os.path.join(GOLDEN, "stack.npz"), **flat)
 
 
+def gen_nstep(R):
+    """modules.n_step_return (legacy/algorithm/modules/n_step_return.py:11-50): random trajectories with episode ends
+    and truncations, several n; plus the reference's own known-answer inputs (legacy/tests/modules_test.py:180-209)."""
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    for name, (rows, B, n, gamma) in dict(a=(40, 7, 1, 0.99), b=(40, 7, 3, 0.99), c=(65, 33, 5, 0.997), d=(12, 4, 12, 0.9)).items():
+        reward = torch.randn(rows, B, 1, generator=g)
+        nex_value = torch.randn(rows, B, 1, generator=g) * 3
+        nex_done = (torch.rand(rows, B, 1, generator=g) < 0.08).float()
+        nex_trunc = ((torch.rand(rows, B, 1, generator=g) < 0.08).float() * (1 - nex_done))
+        ret = R.nstep.n_step_return(n, reward, nex_value, nex_done, nex_trunc, gamma)
+        out.update({f"{name}.reward": reward.numpy(), f"{name}.nex_value": nex_value.numpy(),
+                    f"{name}.nex_done": nex_done.numpy().astype(np.uint8), f"{name}.nex_truncated": nex_trunc.numpy().astype(np.uint8),
+                    f"{name}.n": np.int64(n), f"{name}.gamma": np.float64(gamma), f"{name}.ret": ret.numpy()})
+    np.savez_compressed(os.path.join(GOLDEN, "nstep.npz"), **out)
+    return sorted({k.split(".")[0] for k in out})
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
     R = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "nstep":  # only the n-step fixture (added after the others)
+        print("nstep:", gen_nstep(R))
+        return
     print("gae:", gen_gae(R))
     print("loss:", gen_loss(R))
     gen_masknorm_popart(R)
     gen_stack(R)
+    print("nstep:", gen_nstep(R))
     total = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))
     print(f"wrote {len(os.listdir(GOLDEN))} files, {total / 1024:.0f} KiB")
 

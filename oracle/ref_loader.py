@@ -93,7 +93,8 @@ def load():
     utils = _exec_file("legacy.algorithm.modules.utils", "legacy/algorithm/modules/utils.py")
     gae = _exec_file("legacy.algorithm.modules.gae", "legacy/algorithm/modules/gae.py")
     popart = _exec_file("legacy.algorithm.modules.popart", "legacy/algorithm/modules/popart.py")
-    for m in (utils, gae, popart):
+    nstep = _exec_file("legacy.algorithm.modules.n_step_return", "legacy/algorithm/modules/n_step_return.py")
+    for m in (utils, gae, popart, nstep):
         for k, v in vars(m).items():
             if not k.startswith("_"):
                 setattr(modules, k, v)
@@ -107,7 +108,7 @@ def load():
     mappo.PyTorchGPUPrefetcher = _NoPrefetch
 
     _LOADED = types.SimpleNamespace(namedarray=namedarray, policy=api.policy, trainer=api.trainer,
-                                    utils=utils, gae=gae, popart=popart, mappo=mappo,
+                                    utils=utils, gae=gae, popart=popart, nstep=nstep, mappo=mappo,
                                     modules=modules)
     return _LOADED
 

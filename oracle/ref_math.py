@@ -78,6 +78,23 @@ def adv_and_value_target_ref(reward, value, truncated, done, on_reset, gamma, lm
     return adv, adv + boot[:-1]  # mappo.py:143
 
 
+@torch.no_grad()
+def n_step_return_ref(n, reward, nex_value, nex_done, nex_truncated, gamma):
+    """legacy/algorithm/modules/n_step_return.py:11-50 (high_precision=True): float64 window sums in the reference's
+    operation order; inputs [n+T-1, ...], output [T, ...] float32."""
+    reward, nex_value, nex_done, nex_truncated = (x.to(torch.float64) for x in (reward, nex_value, nex_done, nex_truncated))
+    T = nex_value.shape[0] - n + 1
+    assert T >= 1
+    ret = torch.zeros_like(reward[:T])
+    discount = torch.ones_like(reward[:T])
+    for i in range(n):
+        ret += reward[i:i + T] * discount
+        # a truncated next step bootstraps its value right away; `discount` is 0 afterwards
+        ret += discount * gamma * nex_truncated[i:i + T] * nex_value[i:i + T]
+        discount *= gamma * (1 - nex_done[i:i + T]) * (1 - nex_truncated[i:i + T])
+    return (ret + discount * nex_value[n - 1:n - 1 + T]).float()
+
+
 def pad_last_row(x):
     """mappo.py:254-256: F.pad with one zero row at the end of the time axis."""
     return torch.cat([x, torch.zeros_like(x[:1])], dim=0)

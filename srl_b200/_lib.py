@@ -76,6 +76,7 @@ SIGNATURES = {
     "srl_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "srl_gae_scan": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double] +
                      [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "srl_n_step_return": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_double, c_void_p, c_void_p]),
     "srl_lane_stats": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "srl_group_stats_workspace_bytes": (c_size_t, [c_int, c_int]),
     "srl_group_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

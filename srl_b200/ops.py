@@ -112,6 +112,31 @@ def gae_scan(reward, value, done, truncated, on_reset, gamma: float, lmbda: floa
     return adv, ret, lane_part
 
 
+def n_step_return(n: int, reward, nex_value, nex_done, nex_truncated, gamma: float,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """n-step return: reward / nex_value float32 and nex_done / nex_truncated uint8, all `[n+T-1, N(, 1)]`; returns
+    float32 `[T, N(, 1)]`.  Reference: modules.n_step_return (legacy/algorithm/modules/n_step_return.py:11-50)."""
+    rows, N = _rows_lanes(reward)
+    for name, t in (("reward", reward), ("nex_value", nex_value)):
+        _check(t, torch.float32, name)
+    for name, t in (("nex_done", nex_done), ("nex_truncated", nex_truncated)):
+        _check(t, torch.uint8, name)
+    for name, t in (("nex_value", nex_value), ("nex_done", nex_done), ("nex_truncated", nex_truncated)):
+        if _rows_lanes(t) != (rows, N):
+            raise ValueError(f"{name}: shape {tuple(t.shape)} does not match reward {tuple(reward.shape)}")
+    if not 1 <= n <= rows:
+        raise ValueError(f"need 1 <= n <= rows = {rows}, got n = {n}")
+    T = rows - n + 1
+    if out is None:
+        out = torch.empty((T,) + tuple(reward.shape[1:]), dtype=torch.float32, device=reward.device)
+    _check(out, torch.float32, "out")
+    if out.numel() != T * N:
+        raise ValueError(f"out holds {out.numel()} elements, expected T*N = {T * N}")
+    _lib.call("srl_n_step_return", _ptr(reward), _ptr(nex_value), _ptr(nex_done), _ptr(nex_truncated), int(n), rows, N,
+              float(gamma), _ptr(out), _stream())
+    return out
+
+
 def lane_stats(adv, ret, done, truncated, on_reset, row_lo: int, row_hi: int,
                lane_part: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Per-lane partial sums [8, N] from existing adv / ret (cached advantages of a re-served sample)."""

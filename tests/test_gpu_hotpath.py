@@ -194,3 +194,34 @@ def test_step_variants_match_oracle(name, hp_kw):
     hp.step_count = 0
     hp.run_device(pol_dev, use_graph=True)
     _compare(hp, cfg, ref, pa)
+
+
+def test_full_size_cfg2_pack_and_batch_equal_per_minibatch_launches():
+    """BASELINE cfg2 at full size (T=128, B=4096, 4 x 8 minibatches): the batched launch on K2's pack and the 32
+    per-minibatch launches on the five gathered leaves give bit-identical gradients and the same loss scalars."""
+    from srl_b200 import ops
+    from srl_b200.hotpath import HotPath
+    cfg = synth.CONFIGS["cfg2_atari_large"]
+    s = synth.make_sample_scalars(cfg, 0)
+    kw = dict(gamma=cfg.gamma, lmbda=cfg.lmbda, hyper=ops.LossHyper(**_hp_kwargs(cfg)), epochs=cfg.epochs,
+              minibatches=cfg.minibatches, seed=1)
+    a = HotPath(cfg.L, cfg.B, cfg.A, **kw)
+    b = HotPath(cfg.L, cfg.B, cfg.A, use_pack=False, batch_losses=False, **kw)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = cfg.N // cfg.minibatches
+    pol = [[(-torch.rand(cfg.T, n, device="cuda", generator=g), torch.randn(cfg.T, n, device="cuda", generator=g),
+             torch.rand(cfg.T, n, device="cuda", generator=g)) for _ in range(cfg.minibatches)] for _ in range(cfg.epochs)]
+    for hp in (a, b):
+        hp.load_sample(s)
+        hp.run_device(pol, use_graph=False)
+    torch.cuda.synchronize()
+    assert torch.equal(a.adv, b.adv) and torch.equal(a.ret, b.ret) and torch.equal(a.perm, b.perm)
+    assert torch.equal(a.grads_all, b.grads_all), "pack / batched gradients differ from the per-minibatch launches"
+    np.testing.assert_allclose(a.out.cpu().numpy(), b.out.cpu().numpy(), rtol=1e-9, atol=1e-12)
+    # round trip property at full size: the same step from a CUDA graph reproduces itself
+    a.run_device(pol, use_graph=True)
+    a.step_count = 0
+    ref_grads = a.grads_all.clone()
+    a.run_device(pol, use_graph=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a.grads_all, ref_grads)

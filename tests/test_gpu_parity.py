@@ -692,3 +692,23 @@ def test_peer_exchange_single_rank(ops):
             _lib.call("srl_xchg_allreduce_sum", h, a.data_ptr(), out.data_ptr(), 65, None)
     finally:
         _lib.call("srl_xchg_destroy", h)
+
+
+def test_n_step_return_bit_exact(ops):
+    """srl_n_step_return vs the unmodified reference's outputs (tests/golden/nstep.npz): float64 with the reference's
+    operation order -> bit-identical; plus a large random case against the oracle."""
+    d = load_golden("nstep.npz")
+    for name in sorted({k.split(".")[0] for k in d}):
+        got = ops.n_step_return(int(d[f"{name}.n"]), dev(d[f"{name}.reward"]), dev(d[f"{name}.nex_value"]),
+                                dev(d[f"{name}.nex_done"]), dev(d[f"{name}.nex_truncated"]), float(d[f"{name}.gamma"]))
+        assert np.array_equal(got.cpu().numpy(), d[f"{name}.ret"]), name
+    g = torch.Generator().manual_seed(5)
+    rows, N, n = 300, 4096, 7
+    reward, value = torch.randn(rows, N, generator=g), torch.randn(rows, N, generator=g) * 2
+    done = (torch.rand(rows, N, generator=g) < 0.02)
+    trunc = (torch.rand(rows, N, generator=g) < 0.02) & ~done
+    got = ops.n_step_return(n, reward.cuda(), value.cuda(), done.to(torch.uint8).cuda(), trunc.to(torch.uint8).cuda(), 0.99)
+    want = M.n_step_return_ref(n, reward, value, done.float(), trunc.float(), 0.99)
+    assert torch.equal(got.cpu(), want)
+    with pytest.raises(ValueError, match="1 <= n"):
+        ops.n_step_return(rows + 1, reward.cuda(), value.cuda(), done.to(torch.uint8).cuda(), trunc.to(torch.uint8).cuda(), 0.99)

@@ -296,3 +296,25 @@ def test_live_gae_and_loss_vs_reference(seed):
     assert torch.equal(mine["loss"], loss.detach())
     for k, g in (("g_logp", nl.grad), ("g_value", vp.grad), ("g_entropy", en.grad)):
         assert torch.equal(mine[k], g), k
+
+
+def test_n_step_return_known_answers_and_fixture():
+    """legacy/tests/modules_test.py:180-209 (hand-computed) and the fixture written by the unmodified reference."""
+    rew = [1, 2, 1, -3, 0, 3, -1, 2, 1, -2, 10, 1]
+    value = [2, 10, 1, 5, 0, 3, 2, -2, -10, 5, -1, -100]
+    done = [0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0]
+    truncated = [0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0]
+    args = (torch.tensor(rew[:-1], dtype=torch.float32), torch.tensor(value[1:], dtype=torch.float32),
+            torch.tensor(done[1:], dtype=torch.float32), torch.tensor(truncated[1:], dtype=torch.float32))
+    ret = M.n_step_return_ref(2, *args, 0.1)
+    np.testing.assert_almost_equal(ret[:4].numpy(), [1.21, 2.15, 0.7, -3], decimal=6)
+    np.testing.assert_almost_equal(ret[5:9].numpy(), [2.88, -0.9, 2.15, 1.5], decimal=6)
+    ret = M.n_step_return_ref(3, *args, 0.1)
+    np.testing.assert_almost_equal(ret[:4].numpy(), [1.215, 2.07, 0.7, -3], decimal=6)
+    np.testing.assert_almost_equal(ret[5:].numpy(), [2.91, -0.79 + 5e-3, 2.15, 1.5], decimal=6)
+    d = load_golden("nstep.npz")
+    for name in sorted({k.split(".")[0] for k in d}):
+        got = M.n_step_return_ref(int(d[f"{name}.n"]), torch.from_numpy(d[f"{name}.reward"]),
+                                  torch.from_numpy(d[f"{name}.nex_value"]), torch.from_numpy(d[f"{name}.nex_done"]).float(),
+                                  torch.from_numpy(d[f"{name}.nex_truncated"]).float(), float(d[f"{name}.gamma"]))
+        assert np.array_equal(got.numpy(), d[f"{name}.ret"]), name
