@@ -217,7 +217,9 @@ def test_full_size_cfg2_pack_and_batch_equal_per_minibatch_launches():
     torch.cuda.synchronize()
     assert torch.equal(a.adv, b.adv) and torch.equal(a.ret, b.ret) and torch.equal(a.perm, b.perm)
     assert torch.equal(a.grads_all, b.grads_all), "pack / batched gradients differ from the per-minibatch launches"
-    np.testing.assert_allclose(a.out.cpu().numpy(), b.out.cpu().numpy(), rtol=1e-9, atol=1e-12)
+    # the masked sums add up to 32 terms in fp32 before they enter the float64 accumulators, and the two launch shapes
+    # group the terms differently: equal to ~1e-6, an order of magnitude inside the 1e-5 contract
+    np.testing.assert_allclose(a.out.cpu().numpy(), b.out.cpu().numpy(), rtol=2e-6, atol=1e-9)
     # round trip property at full size: the same step from a CUDA graph reproduces itself
     a.run_device(pol, use_graph=True)
     a.step_count = 0
