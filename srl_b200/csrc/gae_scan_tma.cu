@@ -33,7 +33,7 @@ namespace {
 #endif
 constexpr int kRows = SRL_TMA_ROWS;      // rows per stage
 constexpr int kStages = SRL_TMA_STAGES;  // ring depth
-constexpr int kLanes = 32;               // lanes per warp / CTA
+constexpr int kMaxLanes = 32;            // lanes per CTA (LPW below): one full warp
 
 struct alignas(64) GaeTmaMaps {
   CUtensorMap reward, value, done, truncated, on_reset, old_logp, vt_new;
@@ -45,17 +45,17 @@ struct GaeTmaParams {
 };
 
 // OLDLP: the stage also carries old_logp (needed by the pack and by V-trace)
-template <bool VTRACE, bool OLDLP>
+template <bool VTRACE, bool OLDLP, int LPW>
 struct StageLayout {
   // byte offsets inside one stage; every sub-buffer is 128-byte aligned
   static constexpr int value = 0;
-  static constexpr int reward = value + kRows * kLanes * 4;
-  static constexpr int old_logp = reward + kRows * kLanes * 4;
-  static constexpr int vt_new = old_logp + (OLDLP ? kRows * kLanes * 4 : 0);
-  static constexpr int done = vt_new + (VTRACE ? kRows * kLanes * 4 : 0);
-  static constexpr int truncated = done + kRows * kLanes;
-  static constexpr int on_reset = truncated + kRows * kLanes;
-  static constexpr int bytes = on_reset + kRows * kLanes;  // payload = what the mbarrier expects
+  static constexpr int reward = value + kRows * LPW * 4;
+  static constexpr int old_logp = reward + kRows * LPW * 4;
+  static constexpr int vt_new = old_logp + (OLDLP ? kRows * LPW * 4 : 0);
+  static constexpr int done = vt_new + (VTRACE ? kRows * LPW * 4 : 0);
+  static constexpr int truncated = done + kRows * LPW;
+  static constexpr int on_reset = truncated + kRows * LPW;
+  static constexpr int bytes = on_reset + kRows * LPW;  // payload = what the mbarrier expects
   static constexpr int stride = (bytes + 127) / 128 * 128;
 };
 
@@ -88,9 +88,9 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-template <bool VTRACE, bool OLDLP>
+template <bool VTRACE, bool OLDLP, int LPW>
 __device__ __forceinline__ void issue_stage(const GaeTmaParams& q, unsigned char* slot, uint64_t* bar, int col0, int row0) {
-  using SL = StageLayout<VTRACE, OLDLP>;
+  using SL = StageLayout<VTRACE, OLDLP, LPW>;
   mbar_expect_tx(bar, SL::bytes);
   tma_load_2d(slot + SL::value, &q.maps.value, col0, row0, bar);
   tma_load_2d(slot + SL::reward, &q.maps.reward, col0, row0, bar);
@@ -116,12 +116,12 @@ struct LaneStats {
 // rows are scanned, stored and counted -- no per-row range tests.  EDGE = true: the general body.
 // Straight-line code on purpose: the 8 rows of a stage are independent except for the two-instruction chain in
 // pass 2, so the scheduler can overlap their shared-memory, conversion and fp64 latencies.
-template <bool VTRACE, bool PACK, bool EDGE>
+template <bool VTRACE, bool PACK, bool EDGE, int LPW>
 __device__ __forceinline__ void run_stage(const GaeParams& p, const unsigned char* slot, int tbase, int lane, int col,
                                           bool live, bool popart, double pa_mean, double pa_std, Carry& cy,
                                           LaneStats& st) {
   // `live` and `popart` are compile-time constants in the specialised instantiations (FULL / POPART below)
-  using SL = StageLayout<VTRACE, PACK || VTRACE>;
+  using SL = StageLayout<VTRACE, PACK || VTRACE, LPW>;
   const float* sv = reinterpret_cast<const float*>(slot + SL::value);
   const float* sr = reinterpret_cast<const float*>(slot + SL::reward);
   const uint8_t* sdn = slot + SL::done;
@@ -136,10 +136,10 @@ __device__ __forceinline__ void run_stage(const GaeParams& p, const unsigned cha
   bool dnf[kRows], trf[kRows], rsf[kRows];
 #pragma unroll
   for (int r = 0; r < kRows; ++r) {
-    float x = sv[r * kLanes + lane];
-    dnf[r] = sdn[r * kLanes + lane] != 0;
-    trf[r] = str_[r * kLanes + lane] != 0;
-    rsf[r] = srs[r * kLanes + lane] != 0;
+    float x = sv[r * LPW + lane];
+    dnf[r] = sdn[r * LPW + lane] != 0;
+    trf[r] = str_[r * LPW + lane] != 0;
+    rsf[r] = srs[r * LPW + lane] != 0;
     if (popart)  // RunningMeanStd.denormalize: (x.double() * std + mean).float()   utils.py:146-151
       x = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(x), pa_std), pa_mean));
     v[r] = __fmul_rn(x, dnf[r] ? 0.f : 1.f);  // value * (1 - done), fp32   mappo.py:120-124
@@ -152,14 +152,14 @@ __device__ __forceinline__ void run_stage(const GaeParams& p, const unsigned cha
     const bool tn = (r == kRows - 1) ? cy.trunc_next : trf[r + 1];
     // gae.py:63  reward + gamma * value[1:] * (1 - on_reset[1:]) - value[:-1]
     double d = __dmul_rn(__dmul_rn(gamma, vn), rn ? 0.0 : 1.0);
-    d = __dadd_rn(static_cast<double>(sr[r * kLanes + lane]), d);
+    d = __dadd_rn(static_cast<double>(sr[r * LPW + lane]), d);
     d = __dsub_rn(d, vd[r]);
     // gae.py:87  gamma * lmbda * (1 - on_reset[1:]) * (1 - truncated[1:]): exactly 0 or gamma*lmbda
     double m = (rn || tn) ? 0.0 : gl;
     if (VTRACE) {
       const float* snl = reinterpret_cast<const float*>(slot + SL::vt_new);
       const float* sol = reinterpret_cast<const float*>(slot + SL::old_logp);
-      const double rd = static_cast<double>(expf(snl[r * kLanes + lane] - sol[r * kLanes + lane]));  // mappo.py:129-132
+      const double rd = static_cast<double>(expf(snl[r * LPW + lane] - sol[r * LPW + lane]));  // mappo.py:129-132
       d = __dmul_rn(d, fmin(rd, p.rho));  // gae.py:64-65
       m = __dmul_rn(m, fmin(rd, p.c));    // gae.py:88-89
     }
@@ -200,7 +200,7 @@ __device__ __forceinline__ void run_stage(const GaeParams& p, const unsigned cha
         const float* sol = reinterpret_cast<const float*>(slot + SL::old_logp);
         const bool keep = EDGE ? (!rn && t < L - 1) : !rn;
         __stcg(reinterpret_cast<float4*>(p.pack) + gi,
-               make_float4(sol[r * kLanes + lane], sv[r * kLanes + lane], rt, keep ? a[r] : __int_as_float(0x7fc00000)));
+               make_float4(sol[r * LPW + lane], sv[r * LPW + lane], rt, keep ? a[r] : __int_as_float(0x7fc00000)));
       }
     }
 #endif
@@ -221,15 +221,15 @@ __device__ __forceinline__ void run_stage(const GaeParams& p, const unsigned cha
 
 // SPEC = true: the hot instantiations, N % 32 == 0 (no dead lanes, so no per-row store predicate and no
 // reconvergence barrier around the stores) and PopArt known at compile time (POPART); SPEC = false: general.
-template <bool VTRACE, bool PACK, bool SPEC, bool POPART>
-__global__ void __launch_bounds__(kLanes) gae_scan_tma_kernel(const __grid_constant__ GaeTmaParams q) {
+template <bool VTRACE, bool PACK, bool SPEC, bool POPART, int LPW>
+__global__ void __launch_bounds__(LPW) gae_scan_tma_kernel(const __grid_constant__ GaeTmaParams q) {
   constexpr bool OLDLP = PACK || VTRACE;
-  using SL = StageLayout<VTRACE, OLDLP>;
+  using SL = StageLayout<VTRACE, OLDLP, LPW>;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * SL::stride);
   const GaeParams& p = q.p;
   const int lane = threadIdx.x;
-  const int col0 = blockIdx.x * kLanes;
+  const int col0 = blockIdx.x * LPW;
   const int col = col0 + lane;
   const bool live = SPEC ? true : col < p.N;
   const int L = p.L, N = p.N;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kLanes) gae_scan_tma_kernel(const __grid_const
   __syncwarp();
   if (lane == 0) {  // prologue: fill the ring, newest rows first
     for (int i = 0; i < kStages && i < n_stages; ++i)
-      issue_stage<VTRACE, OLDLP>(q, smem + i * SL::stride, &bars[i], col0, (n_stages - 1 - i) * kRows);
+      issue_stage<VTRACE, OLDLP, LPW>(q, smem + i * SL::stride, &bars[i], col0, (n_stages - 1 - i) * kRows);
   }
 
   const bool popart = SPEC ? POPART : p.popart != nullptr;
@@ -275,12 +275,12 @@ __global__ void __launch_bounds__(kLanes) gae_scan_tma_kernel(const __grid_const
     const int tbase = k * kRows;
     const bool interior = !VTRACE && tbase >= p.row_lo && tbase + kRows <= p.row_hi;
     if (interior)
-      run_stage<VTRACE, PACK, false>(p, slot, tbase, lane, col, live, popart, pa_mean, pa_std, cy, st);
+      run_stage<VTRACE, PACK, false, LPW>(p, slot, tbase, lane, col, live, popart, pa_mean, pa_std, cy, st);
     else
-      run_stage<VTRACE, PACK, true>(p, slot, tbase, lane, col, live, popart, pa_mean, pa_std, cy, st);
+      run_stage<VTRACE, PACK, true, LPW>(p, slot, tbase, lane, col, live, popart, pa_mean, pa_std, cy, st);
     __syncwarp();  // every lane is done reading this slot
     if (lane == 0 && it + kStages < n_stages)
-      issue_stage<VTRACE, OLDLP>(q, slot, &bars[slot_i], col0, (n_stages - 1 - (it + kStages)) * kRows);
+      issue_stage<VTRACE, OLDLP, LPW>(q, slot, &bars[slot_i], col0, (n_stages - 1 - (it + kStages)) * kRows);
   }
 #ifdef SRL_DEBUG_PHASES
   if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1))
@@ -318,13 +318,13 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [rows, N] row-major tensor of `elem` bytes per element, box = [kRows, 32 lanes]
-int make_map(CUtensorMap* m, const void* base, int rows, int N, int elem) {
+// [rows, N] row-major tensor of `elem` bytes per element, box = [kRows, lpw lanes]
+int make_map(CUtensorMap* m, const void* base, int rows, int N, int elem, int lpw) {
   EncodeTiledFn fn = encode_fn();
   SRL_REQUIRE(fn != nullptr, SRL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(rows)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(N) * elem};
-  const cuuint32_t box[2] = {kLanes, kRows};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(lpw), kRows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(m, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -334,11 +334,11 @@ int make_map(CUtensorMap* m, const void* base, int rows, int N, int elem) {
   return SRL_OK;
 }
 
-template <bool VTRACE, bool PACK, bool SPEC, bool POPART>
+template <bool VTRACE, bool PACK, bool SPEC, bool POPART, int LPW>
 int launch(const GaeTmaParams& q, cudaStream_t st) {
-  using SL = StageLayout<VTRACE, PACK || VTRACE>;
+  using SL = StageLayout<VTRACE, PACK || VTRACE, LPW>;
   const size_t smem = static_cast<size_t>(kStages) * SL::stride + kStages * sizeof(uint64_t);
-  auto kern = gae_scan_tma_kernel<VTRACE, PACK, SPEC, POPART>;
+  auto kern = gae_scan_tma_kernel<VTRACE, PACK, SPEC, POPART, LPW>;
   static bool opted_in[64] = {};
   int dev = 0;
   SRL_CUDA(cudaGetDevice(&dev));
@@ -346,8 +346,8 @@ int launch(const GaeTmaParams& q, cudaStream_t st) {
     SRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     opted_in[dev] = true;
   }
-  const int grid = (q.p.N + kLanes - 1) / kLanes;
-  kern<<<grid, kLanes, smem, st>>>(q);
+  const int grid = (q.p.N + LPW - 1) / LPW;
+  kern<<<grid, LPW, smem, st>>>(q);
   SRL_CUDA(cudaGetLastError());
   return SRL_OK;
 }
@@ -365,31 +365,39 @@ bool gae_tma_eligible(const GaeParams& p) {
   return true;
 }
 
-int launch_gae_tma(const GaeParams& p, cudaStream_t st) {
+// Lanes per CTA: always a full warp.  Half-warp CTAs (LPW = 16: twice the CTAs for mid-size batches such as cfg3's
+// 432 lane groups on 148 SMs) were measured and LOST -- cfg3 K2 41 -> 53 us, cfg4 31 -> 39 us: the kernel is bound by
+// instruction issue, and a half-empty warp instruction costs a full issue slot (profiles/r1c_notes.md).
+template <int LPW>
+int launch_gae_tma_lpw(const GaeParams& p, cudaStream_t st) {
   GaeTmaParams q;
   q.p = p;
   int rc;
-  if ((rc = make_map(&q.maps.value, p.value, p.L, p.N, 4)) != SRL_OK) return rc;
-  if ((rc = make_map(&q.maps.reward, p.reward, p.L, p.N, 4)) != SRL_OK) return rc;
-  if ((rc = make_map(&q.maps.done, p.done, p.L, p.N, 1)) != SRL_OK) return rc;
-  if ((rc = make_map(&q.maps.truncated, p.truncated, p.L, p.N, 1)) != SRL_OK) return rc;
-  if ((rc = make_map(&q.maps.on_reset, p.on_reset, p.L, p.N, 1)) != SRL_OK) return rc;
+  if ((rc = make_map(&q.maps.value, p.value, p.L, p.N, 4, LPW)) != SRL_OK) return rc;
+  if ((rc = make_map(&q.maps.reward, p.reward, p.L, p.N, 4, LPW)) != SRL_OK) return rc;
+  if ((rc = make_map(&q.maps.done, p.done, p.L, p.N, 1, LPW)) != SRL_OK) return rc;
+  if ((rc = make_map(&q.maps.truncated, p.truncated, p.L, p.N, 1, LPW)) != SRL_OK) return rc;
+  if ((rc = make_map(&q.maps.on_reset, p.on_reset, p.L, p.N, 1, LPW)) != SRL_OK) return rc;
   const bool vtrace = p.vt_new_logp != nullptr;
   const bool pack = p.pack != nullptr;
   if (vtrace) {  // [L-1, N]: the last row of the top stage reads as zero and is never used
-    if ((rc = make_map(&q.maps.vt_new, p.vt_new_logp, p.L - 1, p.N, 4)) != SRL_OK) return rc;
-    if ((rc = make_map(&q.maps.old_logp, p.vt_old_logp, p.L - 1, p.N, 4)) != SRL_OK) return rc;
+    if ((rc = make_map(&q.maps.vt_new, p.vt_new_logp, p.L - 1, p.N, 4, LPW)) != SRL_OK) return rc;
+    if ((rc = make_map(&q.maps.old_logp, p.vt_old_logp, p.L - 1, p.N, 4, LPW)) != SRL_OK) return rc;
     // the pack's old_logp is the sample leaf the V-trace ratio uses as well
-    return pack ? launch<true, true, false, false>(q, st) : launch<true, false, false, false>(q, st);
+    return pack ? launch<true, true, false, false, LPW>(q, st) : launch<true, false, false, false, LPW>(q, st);
   }
-  const bool full = p.N % kLanes == 0, popart = p.popart != nullptr;
+  const bool full = p.N % LPW == 0, popart = p.popart != nullptr;
   if (pack) {
-    if ((rc = make_map(&q.maps.old_logp, p.old_logp, p.L, p.N, 4)) != SRL_OK) return rc;
-    if (!full) return launch<false, true, false, false>(q, st);
-    return popart ? launch<false, true, true, true>(q, st) : launch<false, true, true, false>(q, st);
+    if ((rc = make_map(&q.maps.old_logp, p.old_logp, p.L, p.N, 4, LPW)) != SRL_OK) return rc;
+    if (!full) return launch<false, true, false, false, LPW>(q, st);
+    return popart ? launch<false, true, true, true, LPW>(q, st) : launch<false, true, true, false, LPW>(q, st);
   }
-  if (!full) return launch<false, false, false, false>(q, st);
-  return popart ? launch<false, false, true, true>(q, st) : launch<false, false, true, false>(q, st);
+  if (!full) return launch<false, false, false, false, LPW>(q, st);
+  return popart ? launch<false, false, true, true, LPW>(q, st) : launch<false, false, true, false, LPW>(q, st);
+}
+
+int launch_gae_tma(const GaeParams& p, cudaStream_t st) {
+  return launch_gae_tma_lpw<32>(p, st);
 }
 
 }  // namespace srl
