@@ -111,7 +111,7 @@ int srl_lane_stats(const float* adv, const float* ret, const uint8_t* done, cons
  * whole_first != 0: out has G + 1 rows and row 0 is the sum over ALL N lanes (the batch statistics PopArt
  * needs), rows 1..G are the groups -- one launch for the whole table.
  * Summation order is fixed (deterministic for a given G, per).
- * Rows longer than 1024 lanes are summed by several CTAs through `workspace` (srl_group_stats_workspace_bytes()
+ * Rows longer than 512 lanes are summed by several CTAs through `workspace` (srl_group_stats_workspace_bytes()
  * bytes, 8-byte aligned, zero before its FIRST use; the kernel leaves it zeroed); shorter rows need none (NULL).
  * ------------------------------------------------------------------------------------------ */
 size_t srl_group_stats_workspace_bytes(int G, int whole_first);

@@ -7,7 +7,7 @@ namespace srl {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kChunkLanes = 1024;  // lanes one CTA sums (4 per thread): 8 rows x 1024 lanes x 8 B = 64 KB per CTA
+constexpr int kChunkLanes = 512;   // lanes one CTA sums: 2 per thread, all 14 loads of a thread in flight together
 constexpr int kMaxChunks = 256;    // chunks per output row (longer rows use longer chunks)
 
 __host__ __device__ inline int chunks_of(int lanes) {
@@ -42,10 +42,25 @@ __global__ void __launch_bounds__(kThreads) group_stats_kernel(const double* __r
   double acc[SRL_LANE_PART];
 #pragma unroll
   for (int k = 0; k < SRL_LANE_PART; ++k) acc[k] = 0.0;
-  for (int j = j0 + threadIdx.x; j < j1; j += kThreads) {
-    const int lane = whole ? j : (idx ? idx[static_cast<size_t>(g) * per + j] : g * per + j);
+  // two lanes per thread and iteration: both index loads, then all 14 value loads, are issued before the first use
+  // (one exposed round trip for the indices, one for the values)
+  for (int j = j0 + threadIdx.x; j < j1; j += 2 * kThreads) {
+    const int ja = j, jb = j + kThreads;
+    const bool has_b = jb < j1;
+    const size_t base = static_cast<size_t>(g) * per;
+    const int la = whole ? ja : (idx ? __ldg(idx + base + ja) : g * per + ja);
+    const int lb = !has_b ? la : (whole ? jb : (idx ? __ldg(idx + base + jb) : g * per + jb));
+    double va[SRL_LANE_PART - 1], vb[SRL_LANE_PART - 1];
 #pragma unroll
-    for (int k = 0; k < SRL_LANE_PART - 1; ++k) acc[k] += __ldg(lane_part + static_cast<size_t>(k) * N + lane);
+    for (int k = 0; k < SRL_LANE_PART - 1; ++k) {
+      va[k] = __ldg(lane_part + static_cast<size_t>(k) * N + la);
+      vb[k] = __ldg(lane_part + static_cast<size_t>(k) * N + lb);
+    }
+#pragma unroll
+    for (int k = 0; k < SRL_LANE_PART - 1; ++k) {
+      acc[k] += va[k];
+      if (has_b) acc[k] += vb[k];
+    }
   }
   __shared__ double wsum[SRL_LANE_PART][kThreads / 32];
   __shared__ bool is_last;
