@@ -571,7 +571,7 @@ def test_group_stats_whole_first_and_multi_epoch_perm(ops):
 # ---------------------------------------------------------------------------------------------------
 # K2 pack + batched K4 (r1c)
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("L,N", [(9, 31), (33, 64), (130, 272), (129, 16 * 700)])
+@pytest.mark.parametrize("L,N", [(9, 31), (33, 64), (130, 272), (129, 16 * 700), (61, 16 * 701)])
 def test_gae_pack_matches_leaves(ops, L, N):
     """The loss pack is {old_logp, value, ret, mask ? adv : NaN} of the same launch's adv / ret, bit for bit, on the
     tile kernel (ragged N, small N) and on the TMA kernel (N % 16 == 0 with enough lane groups)."""
@@ -712,3 +712,78 @@ def test_n_step_return_bit_exact(ops):
     assert torch.equal(got.cpu(), want)
     with pytest.raises(ValueError, match="1 <= n"):
         ops.n_step_return(rows + 1, reward.cuda(), value.cuda(), done.to(torch.uint8).cuda(), trunc.to(torch.uint8).cuda(), 0.99)
+
+
+def _loss_against_oracle(ops, T, N, n, seed, hyper_kw, lane_idx=None):
+    cfg = synth.PathConfig("edge", T=T, B=N, p_end=0.1, **{k: v for k, v in hyper_kw.items() if k in ("clip_value", "dual_clip")})
+    s = synth.make_sample_scalars(cfg, seed=seed)
+    d = {k: dev(flat2(v)) for k, v in s.items()}
+    adv, ret, part = ops.gae_scan(d["reward"], d["value"], d["done"], d["truncated"], d["on_reset"], cfg.gamma, cfg.lmbda,
+                                  row_lo=0, row_hi=T)
+    li = None if lane_idx is None else dev(lane_idx.astype(np.int32))
+    stats = ops.group_stats(part, idx=li, groups=1, per=n)[0]
+    g = torch.Generator().manual_seed(seed)
+    sel = slice(None) if lane_idx is None else torch.from_numpy(lane_idx.astype(np.int64))
+    t = {k: torch.from_numpy(flat2(v)).float() for k, v in s.items()}
+    olp = t["old_logp"][:T][:, sel]
+    nl = olp + 0.1 * torch.randn(T, n, generator=g)
+    vp = t["value"][:T][:, sel] + 0.1 * torch.randn(T, n, generator=g)
+    en = torch.rand(T, n, generator=g)
+    hp = ops.LossHyper(**hyper_kw)
+    g_lp, g_v, g_en, out, _ = ops.ppo_loss_fwd_bwd(nl.cuda().contiguous(), vp.cuda().contiguous(), en.cuda().contiguous(),
+                                                   d["old_logp"][:T], d["value"][:T], ret[:T], adv[:T], d["on_reset"][1:T + 1],
+                                                   stats, hp, lane_idx=li)
+    ra, rr = adv[:T].cpu()[:, sel], ret[:T].cpu()[:, sel]
+    mask = (1 - t["on_reset"][1:T + 1])[:, sel]
+    ref = M.ppo_loss_ref(nl, olp, vp, t["value"][:T][:, sel], rr, ra, en, mask, M.LossHyper(**hyper_kw))
+    msum = float(mask.sum())
+    assert_close_ref(out[0].item(), float(ref["loss"]), what=f"loss T={T} n={n}")
+    assert_grad_close(g_lp.cpu(), ref["g_logp"], msum, what="g_logp")
+    assert_grad_close(g_v.cpu(), ref["g_value"], msum, what="g_value")
+    assert_grad_close(g_en.cpu(), ref["g_entropy"], msum, what="g_entropy")
+
+
+@pytest.mark.parametrize("T,N", [(1, 4), (3, 1028), (2, 7), (5, 1021), (33, 2052)])
+def test_loss_edge_shapes(ops, T, N):
+    """One row; column tiles with a nearly empty last tile; lane counts that are not multiples of four (scalar path)."""
+    _loss_against_oracle(ops, T, N, N, seed=T * 100 + N, hyper_kw=dict(clip_value=True, dual_clip=True, value_loss="huber"))
+
+
+def test_loss_gather_edge_shapes(ops):
+    rng = np.random.default_rng(0)
+    for T, N, n in [(2, 64, 5), (7, 300, 36), (4, 4096, 1028)]:
+        _loss_against_oracle(ops, T, N, n, seed=n, hyper_kw=dict(clip_value=False, dual_clip=False, value_loss="mse"),
+                             lane_idx=rng.permutation(N)[:n])
+
+
+def test_loss_wider_than_one_grid_of_column_tiles(ops):
+    """More column tiles than partial rows in a workspace slot (2048): CTAs loop over column tiles."""
+    T, n = 2, 4 * 256 * 2100
+    g = torch.Generator(device="cuda").manual_seed(1)
+    rnd = lambda: torch.randn(T, n, device="cuda", generator=g)
+    nl, vp, en = -torch.rand(T, n, device="cuda", generator=g), rnd(), torch.rand(T, n, device="cuda", generator=g)
+    olp, ov, rt, ad = nl + 0.05 * rnd(), vp + 0.1 * rnd(), rnd(), rnd()
+    rs = (torch.rand(T, n, device="cuda", generator=g) < 0.1).to(torch.uint8)
+    mask = (rs == 0).double()
+    x = ad.double() * mask
+    stats = torch.tensor([mask.sum().item(), x.sum().item(), (x * x).sum().item(), 0, 0, 0, 0, 0], dtype=torch.float64,
+                         device="cuda")
+    hp = ops.LossHyper(clip_value=False, dual_clip=False, value_loss="mse")
+    g_lp, g_v, g_en, out, _ = ops.ppo_loss_fwd_bwd(nl, vp, en, olp, ov, rt, ad, rs, stats, hp)
+    half = n // 2  # the same problem as two column halves must give the same gradients and (summed) the same loss
+    o = []
+    for sl in (slice(0, half), slice(half, n)):
+        c = lambda z: z[:, sl].contiguous()
+        a_lp, _, _, out_h, _ = ops.ppo_loss_fwd_bwd(c(nl), c(vp), c(en), c(olp), c(ov), c(rt), c(ad), c(rs), stats, hp)
+        assert torch.equal(a_lp, g_lp[:, sl])
+        o.append(out_h[0].item())
+    # both halves divide by the whole mask sum (local_stats == stats), so the losses add up
+    assert abs(out[0].item() - (o[0] + o[1])) <= 1e-6 * max(1.0, abs(out[0].item()))
+
+
+def test_group_stats_long_rows(ops):
+    """Rows longer than 256 chunks x 512 lanes (chunks grow) and rows of exactly one chunk."""
+    for N in (300_000, 512, 513):
+        part = torch.rand(8, N, dtype=torch.float64, device="cuda")
+        out = ops.group_stats(part, groups=1, per=N)
+        np.testing.assert_allclose(out[0, :7].cpu().numpy(), part[:7].sum(1).cpu().numpy(), rtol=1e-12)
