@@ -217,7 +217,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                  bootstrap_steps=cfg.bootstrap_steps, burn_in_steps=cfg.burn_in_steps, epochs=E, minibatches=Mb, seed=0,
                  popart=cfg.popart, device=dev, process_group=pg, fuse_gather=not args.explicit_gather,
                  graph_branches=args.branches, shuffle_block=args.shuffle_block, use_pack=not args.no_pack,
-                 batch_losses=not args.no_batch, stats_exchange=args.exchange)
+                 batch_losses=not args.no_batch, stats_exchange=args.exchange, fuse_stats=not args.no_fuse_stats)
     n = hp.n_mb
     pinned = {k: torch.from_numpy(np.ascontiguousarray(v.reshape(cfg.L, N))).pin_memory() for k, v in s.items()}
     hp.load_sample(pinned)
@@ -382,6 +382,8 @@ def run_ours(args, cfg, rank, world, local_rank):
                         loss_launch=("batched: %d launch(es) per step covering %d minibatches each" %
                                      (loss_launches, E * Mb // loss_launches)) if hp._immediate else "one launch per minibatch",
                         sample_side="K2 pack (float4 per transition)" if hp.pack is not None else "separate leaves",
+                        minibatch_stats="added inside the loss kernel from K2's per-lane sums (table on a side branch)"
+                        if hp.fuse_stats else "srl_group_stats table between K2 and the loss",
                         minibatch_gather=("fused into the loss loads (lane_idx)" if hp.fuse_gather else "explicit K5 gather") +
                         f", Philox permutation of {hp.shuffle_block}-environment blocks",
                         graph_branches=hp.graph_branches),
@@ -423,6 +425,8 @@ def main():
     ap.add_argument("--explicit-gather", action="store_true", help="separate K5 gather launch instead of gather-on-load")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="statistics exchange across ranks: NVLink peer-memory mailboxes (p2p) or NCCL all-reduce")
+    ap.add_argument("--no-fuse-stats", action="store_true",
+                    help="A/B: minibatch statistics from the srl_group_stats table instead of inside the loss kernel")
     ap.add_argument("--no-pack", action="store_true", help="A/B: gather the five sample leaves instead of K2's pack")
     ap.add_argument("--no-batch", action="store_true", help="A/B: one loss launch per minibatch (parallel graph branches)")
     args = ap.parse_args()

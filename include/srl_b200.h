@@ -201,7 +201,10 @@ int srl_ppo_loss_fwd_bwd(
  * permutation slice, statistics rows, gradient tensors, outputs and workspace slot; the sample side is shared.
  * The sample side is either the five leaves of srl_ppo_loss_fwd_bwd (pack == NULL) or K2's pack
  * ([T, N, 4] float32, pointer already offset to the first loss row; the leaf pointers may then be NULL).
- * Either every problem has a lane_idx or none has.  n_problems > SRL_MAX_LOSS_BATCH is split into several launches. */
+ * Either every problem has a lane_idx or none has.  n_problems > SRL_MAX_LOSS_BATCH is split into several launches.
+ * lane_part != NULL (K2's [SRL_LANE_PART, lane_part_n] table; one GPU, no PopArt, n <= 1024 lanes): every CTA adds the
+ * per-lane sums of ITS minibatch's lanes itself and the problems' norm_stats / local_stats are ignored (may be NULL) --
+ * no srl_group_stats launch between K2 and the loss. */
 #define SRL_MAX_LOSS_BATCH 32
 typedef struct srl_loss_problem {
   const float* new_logp;     /* [T, n], row stride ld_pol */
@@ -221,7 +224,8 @@ typedef struct srl_loss_problem {
 int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems_host, int n_problems, int64_t ld_pol,
                                  int64_t ld_grad, const float* old_logp, const float* old_value, const float* ret,
                                  const float* adv, const uint8_t* on_reset_next, int64_t ld_smp, const float* pack,
-                                 int T, int n, const double* popart_mean_std, const srl_ppo_hyper* hyper,
+                                 const double* lane_part, int lane_part_n, int T, int n,
+                                 const double* popart_mean_std, const srl_ppo_hyper* hyper,
                                  size_t workspace_bytes_per_slot, srl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

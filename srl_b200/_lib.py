@@ -90,7 +90,8 @@ SIGNATURES = {
                                      c_void_p]),
     "srl_ppo_loss_fwd_bwd_batched": (c_int, [POINTER(LossProblem), c_int, c_int64, c_int64,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
-                                             c_int, c_int, c_void_p, POINTER(PpoHyper), c_size_t, c_void_p]),
+                                             c_void_p, c_int, c_int, c_int, c_void_p, POINTER(PpoHyper), c_size_t,
+                                             c_void_p]),
     "srl_ppo_loss_from_logits": (c_int, [c_void_p, c_void_p, POINTER(c_int32), c_int, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                          c_int, c_int, c_void_p, c_void_p, c_void_p, POINTER(PpoHyper),

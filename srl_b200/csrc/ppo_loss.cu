@@ -198,8 +198,8 @@ extern "C" int srl_ppo_loss_finalize(const void* workspace, size_t slot_bytes, i
 extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, int n_problems, int64_t ld_pol,
                                             int64_t ld_grad, const float* old_logp, const float* old_value,
                                             const float* ret, const float* adv, const uint8_t* on_reset_next,
-                                            int64_t ld_smp, const float* pack, int T, int n,
-                                            const double* popart_mean_std, const srl_ppo_hyper* hyper,
+                                            int64_t ld_smp, const float* pack, const double* lane_part, int lane_part_n,
+                                            int T, int n, const double* popart_mean_std, const srl_ppo_hyper* hyper,
                                             size_t workspace_bytes, srl_stream_t stream) {
   using namespace srl;
   using namespace srl::loss;
@@ -223,8 +223,8 @@ extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, in
   bool dense_ok = (n % 4 == 0) && (ld_pol % 4 == 0) && (ld_grad % 4 == 0);
   for (int k = 0; k < n_problems; ++k) {
     const srl_loss_problem& q = problems[k];
-    SRL_REQUIRE(q.new_logp && q.v_pred && q.entropy && q.g_logp && q.g_value && q.g_entropy && q.norm_stats &&
-                    q.local_stats && q.workspace,
+    SRL_REQUIRE(q.new_logp && q.v_pred && q.entropy && q.g_logp && q.g_value && q.g_entropy && q.workspace &&
+                    (lane_part != nullptr || (q.norm_stats && q.local_stats)),
                 SRL_ERR_INVALID_ARG, "srl_ppo_loss_fwd_bwd: null pointer");
     any_idx = any_idx || q.lane_idx != nullptr;
     all_idx = all_idx && q.lane_idx != nullptr;
@@ -243,6 +243,10 @@ extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, in
   s.reset_next = on_reset_next;
   s.pack = reinterpret_cast<const float4*>(pack);
   s.popart = popart_mean_std;
+  SRL_REQUIRE(lane_part == nullptr || (popart_mean_std == nullptr && lane_part_n >= 1), SRL_ERR_INVALID_ARG,
+              "srl_ppo_loss_fwd_bwd_batched: self-computed statistics (lane_part) exclude PopArt and need lane_part_n >= 1");
+  s.lane_part = lane_part;
+  s.lane_part_n = lane_part_n;
   s.ld_pol = ld_pol;
   s.ld_grad = ld_grad;
   s.ld_smp = ld_smp;
@@ -305,7 +309,7 @@ extern "C" int srl_ppo_loss_fwd_bwd(const float* new_logp, const float* v_pred, 
   q.out_f32 = out_f32;
   q.workspace = workspace;
   return srl_ppo_loss_fwd_bwd_batched(&q, 1, ld_pol, ld_grad, old_logp, old_value, ret, adv, on_reset_next, ld_smp,
-                                      nullptr, T, n, popart_mean_std, hyper, workspace_bytes, stream);
+                                      nullptr, nullptr, 0, T, n, popart_mean_std, hyper, workspace_bytes, stream);
 }
 
 extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* action, const int32_t* head_sizes_host,
@@ -356,6 +360,8 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
   p.adv = adv;
   p.reset_next = on_reset_next;
   p.pack = nullptr;
+  p.lane_part = nullptr;
+  p.lane_part_n = 0;
   p.popart = popart_mean_std;
   p.ld_pol = n;
   p.ld_grad = n;

@@ -67,6 +67,8 @@ struct LossShared {
   const uint8_t* reset_next;
   const float4* pack;
   const double* popart;
+  const double* lane_part;  // [SRL_LANE_PART, lane_part_n] from K2, or null; see self_uniforms()
+  int lane_part_n;
   long long ld_pol, ld_grad, ld_smp;
   int T, n;
   int rows_per_tile, col_tiles, n_tiles;
@@ -146,6 +148,65 @@ __device__ __forceinline__ Uniforms load_uniforms(const double* norm_stats, cons
   u.rdenom = 1.0 / u.denom;
   u.inv_m = 1.f / static_cast<float>(mask_sum);
   return u;
+}
+
+__device__ __forceinline__ Uniforms uniforms_from(double cnt, double s1, double s2, double m_local, const double* popart,
+                                                  double adv_eps) {
+  Uniforms u;
+  u.popart = popart != nullptr;
+  u.pa_mu = u.popart ? __ldg(popart) : 0.0;
+  u.pa_sd = u.popart ? __ldg(popart + 1) : 1.0;
+  u.pa_rsd = 1.0 / u.pa_sd;
+  u.mean = s1 / cnt;
+  const double var = s2 / cnt - u.mean * u.mean;
+  u.denom = sqrt(var) + adv_eps;
+  u.rdenom = 1.0 / u.denom;
+  u.inv_m = 1.f / static_cast<float>(m_local);
+  return u;
+}
+
+// Self-computed statistics (one GPU, no PopArt, the CTA's column tile spans the whole minibatch): the CTA adds K2's
+// per-lane sums over ITS minibatch's lanes -- the indices are in registers already -- instead of waiting for a
+// srl_group_stats launch between K2 and K4.  Every CTA of a minibatch adds the same values in the same order (lanes of
+// a thread, warp shuffle tree, warps in order), so they all normalise with bit-identical statistics.
+template <int LANES>
+__device__ __forceinline__ Uniforms self_uniforms(const double* __restrict__ lane_part, int N, const int (&c)[LANES],
+                                                  bool active, double adv_eps, double& mask_sum) {
+  __shared__ double s_part[3][8];
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  if (active) {
+    double v0[LANES], v1[LANES], v2[LANES];
+#pragma unroll
+    for (int q = 0; q < LANES; ++q) {
+      v0[q] = __ldg(lane_part + c[q]);
+      v1[q] = __ldg(lane_part + static_cast<size_t>(N) + c[q]);
+      v2[q] = __ldg(lane_part + 2 * static_cast<size_t>(N) + c[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < LANES; ++q) {
+      a0 += v0[q];
+      a1 += v1[q];
+      a2 += v2[q];
+    }
+  }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  a2 = warp_sum(a2);
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    s_part[0][warp] = a0;
+    s_part[1][warp] = a1;
+    s_part[2][warp] = a2;
+  }
+  __syncthreads();
+  double cnt = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int w = 0; w < nwarps; ++w) {
+    cnt += s_part[0][w];
+    s1 += s_part[1][w];
+    s2 += s_part[2][w];
+  }
+  mask_sum = cnt;
+  return uniforms_from(cnt, s1, s2, cnt, nullptr, adv_eps);
 }
 
 // a / d in float64 given rd = 1 / d (correctly rounded): product, exact residual, one correction.  This is the
@@ -440,7 +501,10 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
     for (int k = 0; k < kStages; ++k) issue(r0 + k, k);
     // the statistics loads and the float64 divisions / sqrt on them run under the first rows' copies
     if (!have_u) {
-      u = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
+      if (s.lane_part != nullptr)
+        u = self_uniforms<LANES>(s.lane_part, s.lane_part_n, c, active, h.adv_eps, mask_sum);
+      else
+        u = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
       have_u = true;
     }
     float* glp_row = pr.g_logp + static_cast<long long>(r0) * s.ld_grad + j;
@@ -495,7 +559,10 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
     cp_async_wait<0>();
   } else {
     if (!have_u) {
-      u = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
+      if (s.lane_part != nullptr)
+        u = self_uniforms<LANES>(s.lane_part, s.lane_part_n, c, active, h.adv_eps, mask_sum);
+      else
+        u = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
       have_u = true;
     }
     // a run of four consecutive, 4-aligned lanes (agents of one environment, sector-aligned environment blocks) is
@@ -620,6 +687,9 @@ struct LossLauncher {
     const int per_row = (s.n + LANES - 1) / LANES;  // threads one row needs
     const int threads = per_row <= 128 ? 128 : 256;
     s.col_tiles = (per_row + threads - 1) / threads;
+    SRL_REQUIRE(s.lane_part == nullptr || s.col_tiles == 1, SRL_ERR_UNSUPPORTED,
+                "ppo loss: self-computed statistics need the whole minibatch in one column tile (n <= %d lanes)",
+                256 * LANES);
     const long long capacity = static_cast<long long>(sm_count()) * resident(threads);  // CTAs resident at once
     // row groups: as many as keep the whole grid resident in ONE wave (a second, partial wave would double the
     // kernel's duration); every CTA then walks ceil(T / groups) consecutive rows of its column tile

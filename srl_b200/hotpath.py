@@ -49,7 +49,7 @@ class HotPath:
                  popart: bool = False, popart_beta: float = 0.99999, popart_eps: float = 1e-5,
                  device: Optional[torch.device] = None, process_group=None, fuse_gather: bool = True,
                  graph_branches: int = 16, shuffle_block: int = 1, use_pack: bool = True, batch_losses: bool = True,
-                 stats_exchange: str = "auto"):
+                 stats_exchange: str = "auto", fuse_stats: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("srl_b200.HotPath needs a CUDA device (there is no CPU path)")
         if bootstrap_steps < 1:
@@ -95,6 +95,12 @@ class HotPath:
         # launches of the trainer path defer to finalize()
         self._immediate = self.batch_losses and (fuse_gather or minibatches == 1)
         self.pack_valid = False
+        # One GPU, no PopArt, minibatches of <= 1024 lanes: the batched loss kernel adds K2's per-lane sums over its own
+        # minibatch (its indices are in registers anyway), so the statistics table is no longer on the critical path
+        # K2 -> K4; it is still produced (the trainer reports done / truncated from its batch row), on a side branch.
+        self.fuse_stats = bool(fuse_stats) and process_group is None and not popart and self._immediate and \
+            self.n_mb <= 1024 and self.n_mb % 4 == 0
+        self._stats_pending = False
         self.step_count = 0
 
         dev, N = self.device, self.N
@@ -201,13 +207,20 @@ class HotPath:
             ops.gae_scan(lf["reward"], lf["value"], lf["done"], lf["truncated"], lf["on_reset"], self.gamma, self.lmbda,
                          row_lo=self.row_lo, row_hi=self.row_hi, popart_mean_std=self.popart_mean_std(), adv=self.adv,
                          ret=self.ret, lane_part=self.lane_part, **kw)
-        if self.minibatches > 1:
-            if permute:
-                main.wait_stream(self._perm_stream)
-            ops.group_stats(self.lane_part, idx=self.perm.view(-1), groups=self.epochs * self.minibatches, per=self.n_mb,
-                            out=self.local_stats, whole_first=True, workspace=self.stats_ws)
-        else:
-            ops.group_stats(self.lane_part, groups=1, per=self.N, out=self.local_stats[0:1], workspace=self.stats_ws)
+        if self.minibatches > 1 and permute:
+            main.wait_stream(self._perm_stream)
+        side = self.fuse_stats and not cached
+        if side:  # off the critical path: joined by _join_stats() after the loss launches
+            if self._perm_stream is None:
+                self._perm_stream = torch.cuda.Stream(device=self.device)
+            self._perm_stream.wait_stream(main)
+        with torch.cuda.stream(self._perm_stream if side else main):
+            if self.minibatches > 1:
+                ops.group_stats(self.lane_part, idx=self.perm.view(-1), groups=self.epochs * self.minibatches,
+                                per=self.n_mb, out=self.local_stats, whole_first=True, workspace=self.stats_ws)
+            else:
+                ops.group_stats(self.lane_part, groups=1, per=self.N, out=self.local_stats[0:1], workspace=self.stats_ws)
+        self._stats_pending = side
         if self.pg is not None:
             self.exchange()
 
@@ -217,6 +230,11 @@ class HotPath:
             self.peer.allreduce_sum(self.local_stats, self.global_stats)
         else:
             exchange_stats(self.local_stats, self.global_stats, self.pg)
+
+    def _join_stats(self) -> None:
+        if self._stats_pending:
+            torch.cuda.current_stream().wait_stream(self._perm_stream)
+            self._stats_pending = False
 
     def permute(self) -> None:
         """K5a: the environment(-block) permutations of every epoch of this step, one launch."""
@@ -239,6 +257,7 @@ class HotPath:
     def loss(self, e: int, j: int, new_logp: torch.Tensor, v_pred: torch.Tensor, entropy: torch.Tensor):
         """K4 for minibatch (e, j) in deferred mode: gradients now, loss scalars + stats at finalize().
         Policy outputs are [T, n_mb] float32.  Returns (g_logp, g_value, g_entropy, None, None)."""
+        self._join_stats()  # the per-minibatch launch reads its statistics from the table
         lo, hi = self.row_lo, self.row_hi
         row = self.stats_row(e, j)
         k = e * self.minibatches + j
@@ -279,12 +298,14 @@ class HotPath:
         lo, hi = self.row_lo, self.row_hi
         lf = self.leaf
         probs = [self._problem(e, j, *pol[e][j], deferred=False) for e, j in pairs]
+        own = self.lane_part if (self.fuse_stats and self._stats_pending) else None
         if self.minibatches > 1 and self.pack is not None and self.pack_valid:
             ops.ppo_loss_batched(probs, None, None, None, None, None, self.hyper,
-                                 popart_mean_std=self.popart_mean_std(), pack=self.pack[lo:hi])
+                                 popart_mean_std=self.popart_mean_std(), pack=self.pack[lo:hi], lane_part=own)
         else:
             ops.ppo_loss_batched(probs, lf["old_logp"][lo:hi], lf["value"][lo:hi], self.ret[lo:hi], self.adv[lo:hi],
-                                 lf["on_reset"][lo + 1:hi + 1], self.hyper, popart_mean_std=self.popart_mean_std())
+                                 lf["on_reset"][lo + 1:hi + 1], self.hyper, popart_mean_std=self.popart_mean_std(),
+                                 lane_part=own)
 
     def finalize(self) -> None:
         """One launch: fold every minibatch's partial rows into self.out / self.out_f32 (loss scalars + stats)."""
@@ -303,6 +324,7 @@ class HotPath:
                     self.loss_batch([(e, j) for j in range(self.minibatches)], pol)
             else:  # every (epoch, minibatch) is independent: one launch
                 self.loss_batch([(e, j) for e in range(self.epochs) for j in range(self.minibatches)], pol)
+            self._join_stats()
             return
         main = torch.cuda.current_stream()
         if branches > 1 and not hasattr(self, "_side"):
@@ -514,6 +536,7 @@ class HotPath:
         if not self._immediate:
             self.finalize()
         out_host["out"].copy_(self.out, non_blocking=True)
+        self._join_stats()
         main.wait_stream(s_out)
 
     def _capture_host(self, pinned, pol_host, out_host) -> None:

@@ -347,14 +347,17 @@ def ppo_loss_fwd_bwd(new_logp, v_pred, entropy, old_logp, old_value, ret, adv, o
 
 
 def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on_reset_next, hyper: LossHyper,
-                     popart_mean_std=None, pack: Optional[torch.Tensor] = None) -> None:
+                     popart_mean_std=None, pack: Optional[torch.Tensor] = None,
+                     lane_part: Optional[torch.Tensor] = None) -> None:
     """Several minibatches of one shape in ONE launch (srl_ppo_loss_fwd_bwd_batched).
 
     Each problem is a dict with `new_logp`, `v_pred`, `entropy` (`[T, n]` float32), `norm_stats`, `local_stats`
     (float64), `grads` (three `[T, n]` float32 outputs), `workspace` (one uint8 slot row), optional `lane_idx`
     (int32 `[n]`), `out` (float64 `[16]`) and `out_f32` (float32 `[4]`); without `out` the problem is deferred
     (loss_finalize folds its slot later).  The sample side is shared: the five leaf views of ppo_loss_fwd_bwd, or
-    `pack` = K2's `[>=T, N, 4]` float32 view already offset to the first loss row."""
+    `pack` = K2's `[>=T, N, 4]` float32 view already offset to the first loss row.  `lane_part` (K2's `[8, N]` float64
+    table; one GPU, no PopArt, n <= 1024): the kernel adds the minibatch statistics itself and `norm_stats` /
+    `local_stats` of the problems are not read (may be omitted)."""
     if not problems:
         return
     T, n = _rows_lanes(problems[0]["new_logp"])
@@ -370,9 +373,13 @@ def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on
             _check(g, torch.float32, f"problem {k} gradient")
             if g.numel() != T * n:
                 raise ValueError(f"problem {k}: gradient tensor holds {g.numel()} elements, expected {T * n}")
-        _check(q["norm_stats"], torch.float64, f"problem {k} norm_stats")
+        ns = q.get("norm_stats")
+        if ns is None and lane_part is None:
+            raise ValueError(f"problem {k}: norm_stats is required unless lane_part is given")
+        if ns is not None:
+            _check(ns, torch.float64, f"problem {k} norm_stats")
         ls = q.get("local_stats")
-        ls = q["norm_stats"] if ls is None else _check(ls, torch.float64, f"problem {k} local_stats")
+        ls = ns if ls is None else _check(ls, torch.float64, f"problem {k} local_stats")
         li = q.get("lane_idx")
         if (li is not None) != has_idx:
             raise ValueError("either every problem has a lane_idx or none has")
@@ -387,7 +394,7 @@ def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on
             _check(out, torch.float64, f"problem {k} out")
         if out_f32 is not None:
             _check(out_f32, torch.float32, f"problem {k} out_f32")
-        arr[k] = LossProblem(_ptr(q["new_logp"]), _ptr(q["v_pred"]), _ptr(q["entropy"]), _ptr(li), _ptr(q["norm_stats"]),
+        arr[k] = LossProblem(_ptr(q["new_logp"]), _ptr(q["v_pred"]), _ptr(q["entropy"]), _ptr(li), _ptr(ns),
                              _ptr(ls), _ptr(q["grads"][0]), _ptr(q["grads"][1]), _ptr(q["grads"][2]), _ptr(out),
                              _ptr(out_f32), _ptr(ws))
     if pack is not None:
@@ -403,10 +410,16 @@ def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on
                               hyper.clip_value)
     if popart_mean_std is not None:
         _check(popart_mean_std, torch.float64, "popart_mean_std")
+    lp_n = 0
+    if lane_part is not None:
+        _check(lane_part, torch.float64, "lane_part")
+        if lane_part.dim() != 2 or lane_part.shape[0] != SRL_LANE_PART:
+            raise ValueError(f"lane_part: expected [{SRL_LANE_PART}, N] float64, got {tuple(lane_part.shape)}")
+        lp_n = lane_part.shape[1]
     hc = hyper.to_c()
     _lib.call("srl_ppo_loss_fwd_bwd_batched", arr, len(problems), n, n, _ptr(old_logp), _ptr(old_value), _ptr(ret),
-              _ptr(adv), _ptr(on_reset_next), ld_smp, _ptr(pack), T, n, _ptr(popart_mean_std), ctypes.byref(hc),
-              slot_bytes, _stream())
+              _ptr(adv), _ptr(on_reset_next), ld_smp, _ptr(pack), _ptr(lane_part), lp_n, T, n, _ptr(popart_mean_std),
+              ctypes.byref(hc), slot_bytes, _stream())
 
 
 def ppo_loss_from_logits(logits, action, head_sizes: Sequence[int], v_pred, old_logp, old_value, ret, adv, on_reset_next,

@@ -178,7 +178,8 @@ def test_block_shuffle_matches_oracle():
     _compare(hp, cfg, ref, None)
 
 
-@pytest.mark.parametrize("hp_kw", [dict(use_pack=False), dict(batch_losses=False), dict(use_pack=False, batch_losses=False)])
+@pytest.mark.parametrize("hp_kw", [dict(use_pack=False), dict(batch_losses=False), dict(use_pack=False, batch_losses=False),
+                                   dict(fuse_stats=False), dict(fuse_stats=False, use_pack=False)])
 @pytest.mark.parametrize("name", ["atari_mb", "smac_popart"])
 def test_step_variants_match_oracle(name, hp_kw):
     """The same step with the loss pack and / or the batched launch switched off (the per-minibatch launches the
