@@ -297,6 +297,11 @@ int srl_batch_gather(const srl_leaf_desc* leaves_host, int n_leaves, const int32
  * ------------------------------------------------------------------------------------------ */
 #define SRL_XCHG_HANDLE_BYTES 64
 typedef struct srl_xchg srl_xchg;
+/* srl_group_stats with the exchange fused in: the CTA that completes the table's last row sends it to the peers at once
+ * (local_out = this rank's table, global_out = the sum over ranks); always needs the workspace. */
+int srl_group_stats_xchg(const double* lane_part, int N, const int32_t* idx, int G, int per, int whole_first,
+                         double* local_out, double* global_out, void* workspace, size_t workspace_bytes, srl_xchg* x,
+                         srl_stream_t stream);
 int srl_xchg_create(int world, int rank, int capacity_doubles, srl_xchg** out);
 int srl_xchg_local_handle(srl_xchg* x, void* handle_out);
 int srl_xchg_connect(srl_xchg* x, const void* handles);

@@ -2,6 +2,7 @@
 // See include/srl_b200.h: replaces the reductions + 3+3 single-element all-reduces of
 // utils.py:54-61 (masked_normalization) and utils.py:113-130 (RunningMeanStd.update).
 #include "common.cuh"
+#include "xchg.cuh"
 
 namespace srl {
 namespace {
@@ -17,10 +18,19 @@ __host__ __device__ inline int chunks_of(int lanes) {
 
 // Workspace: [rows] tickets (uint32, padded to 256 B) then [rows][kMaxChunks][8] float64 chunk partials.
 struct GroupWs {
-  unsigned int* ticket;
+  unsigned int* ticket;     // [rows] chunk tickets, then one "rows finished" counter (fused exchange only)
   double* partial;
 };
-__host__ __device__ inline size_t ticket_bytes(int rows) { return (static_cast<size_t>(rows) * 4 + 255) / 256 * 256; }
+__host__ __device__ inline size_t ticket_bytes(int rows) { return (static_cast<size_t>(rows + 1) * 4 + 255) / 256 * 256; }
+
+// Fused exchange (srl_group_stats_xchg): the CTA that completes the LAST row of the table runs the peer-memory exchange
+// right away -- the table goes out over NVLink from the kernel that produced it, one launch and one dependency edge
+// less between K2 and the loss than group_stats -> exchange kernel -> loss.
+struct FusedXchg {
+  XchgView view;
+  double* global_out;  // null = no exchange
+  int n_rows;
+};
 
 // grid = (chunks, rows).  CTA (c, r) sums chunk c of output row r in a fixed order (lane-strided per thread, warp
 // shuffle tree, warps in order); rows of one chunk are written directly, longer rows go through per-chunk partials
@@ -28,7 +38,8 @@ __host__ __device__ inline size_t ticket_bytes(int rows) { return (static_cast<s
 // version ran 8 CTAs per row whatever its length -- 68 us for the 65536-lane batch row of cfg5 (profiles/).
 __global__ void __launch_bounds__(kThreads) group_stats_kernel(const double* __restrict__ lane_part, int N,
                                                                const int32_t* __restrict__ idx, int per_group,
-                                                               int whole_first, double* __restrict__ out, GroupWs ws) {
+                                                               int whole_first, double* __restrict__ out, GroupWs ws,
+                                                               const FusedXchg fx) {
   // output row blockIdx.y; with whole_first, row 0 is the identity group over all N lanes
   const bool whole = whole_first && blockIdx.y == 0;
   const int g = static_cast<int>(blockIdx.y) - (whole_first ? 1 : 0);
@@ -63,7 +74,7 @@ __global__ void __launch_bounds__(kThreads) group_stats_kernel(const double* __r
     }
   }
   __shared__ double wsum[SRL_LANE_PART][kThreads / 32];
-  __shared__ bool is_last;
+  __shared__ bool is_last, table_done;
   const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < SRL_LANE_PART; ++k) {
@@ -76,24 +87,36 @@ __global__ void __launch_bounds__(kThreads) group_stats_kernel(const double* __r
     for (int w = 0; w < kThreads / 32; ++w) mine += wsum[threadIdx.x][w];
     if (n_chunks == 1) {
       out[static_cast<size_t>(blockIdx.y) * SRL_LANE_PART + threadIdx.x] = mine;
+      if (fx.global_out) __threadfence();
     } else {
       ws.partial[(static_cast<size_t>(blockIdx.y) * kMaxChunks + blockIdx.x) * SRL_LANE_PART + threadIdx.x] = mine;
       __threadfence();
     }
   }
-  if (n_chunks == 1) return;
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(&ws.ticket[blockIdx.y], 1u) == static_cast<unsigned int>(n_chunks) - 1u;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  if (threadIdx.x < SRL_LANE_PART) {
-    double s = 0.0;
-    for (int c = 0; c < n_chunks; ++c)
-      s += __ldcg(ws.partial + (static_cast<size_t>(blockIdx.y) * kMaxChunks + c) * SRL_LANE_PART + threadIdx.x);
-    out[static_cast<size_t>(blockIdx.y) * SRL_LANE_PART + threadIdx.x] = s;
+  if (n_chunks > 1) {
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&ws.ticket[blockIdx.y], 1u) == static_cast<unsigned int>(n_chunks) - 1u;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < SRL_LANE_PART) {
+      double s = 0.0;
+      for (int c = 0; c < n_chunks; ++c)
+        s += __ldcg(ws.partial + (static_cast<size_t>(blockIdx.y) * kMaxChunks + c) * SRL_LANE_PART + threadIdx.x);
+      out[static_cast<size_t>(blockIdx.y) * SRL_LANE_PART + threadIdx.x] = s;
+      if (fx.global_out) __threadfence();
+    }
+    if (threadIdx.x == 0) ws.ticket[blockIdx.y] = 0u;  // ready for the next launch
   }
-  if (threadIdx.x == 0) ws.ticket[blockIdx.y] = 0u;  // ready for the next launch
+  if (fx.global_out == nullptr) return;
+  // this CTA completed row blockIdx.y; the one that completes the table's last row exchanges it with the peers
+  __syncthreads();
+  if (threadIdx.x == 0) table_done = atomicAdd(&ws.ticket[gridDim.y], 1u) == static_cast<unsigned int>(fx.n_rows) - 1u;
+  __syncthreads();
+  if (!table_done) return;
+  __threadfence();
+  if (threadIdx.x == 0) ws.ticket[gridDim.y] = 0u;
+  xchg_exchange(fx.view, out, fx.global_out, fx.n_rows * SRL_LANE_PART);
 }
 
 // Per-lane partial sums from adv / ret that already exist (a re-served sample whose host copy carries them,
@@ -161,6 +184,48 @@ __global__ void popart_update_kernel(const double* __restrict__ bs, double* __re
 }  // namespace
 }  // namespace srl
 
+
+namespace srl {
+namespace {
+int launch_group_stats(const char* fn, const double* lane_part, int N, const int32_t* idx, int G, int per, int whole_first,
+                       double* out, void* workspace, size_t workspace_bytes, const srl_xchg* x, double* global_out,
+                       srl_stream_t stream) {
+  SRL_REQUIRE(lane_part && out, SRL_ERR_INVALID_ARG, "%s: null pointer", fn);
+  SRL_REQUIRE(N >= 1 && G >= (whole_first ? 0 : 1) && per >= 1, SRL_ERR_INVALID_ARG, "%s: need N, G, per >= 1", fn);
+  SRL_REQUIRE(idx != nullptr || static_cast<long long>(G) * per <= N, SRL_ERR_INVALID_ARG, "%s: G*per=%lld exceeds N=%d", fn,
+              static_cast<long long>(G) * per, N);
+  SRL_REQUIRE(G <= 65534, SRL_ERR_UNSUPPORTED, "%s: at most 65534 groups", fn);
+  const int rows = G + (whole_first ? 1 : 0);
+  int max_chunks = G > 0 ? chunks_of(per) : 1;
+  if (whole_first && chunks_of(N) > max_chunks) max_chunks = chunks_of(N);
+  GroupWs ws{nullptr, nullptr};
+  FusedXchg fx;
+  fx.global_out = nullptr;
+  fx.n_rows = rows;
+  if (x != nullptr) {
+    const XchgView* v = xchg_view(x);
+    SRL_REQUIRE(v != nullptr && global_out != nullptr, SRL_ERR_INVALID_ARG, "%s: exchange not connected or null output", fn);
+    SRL_REQUIRE(rows * SRL_LANE_PART <= v->cap, SRL_ERR_INVALID_ARG, "%s: table of %d doubles exceeds the exchange capacity %d",
+                fn, rows * SRL_LANE_PART, v->cap);
+    fx.view = *v;
+    fx.global_out = global_out;
+  }
+  if (max_chunks > 1 || x != nullptr) {
+    SRL_REQUIRE(workspace != nullptr && workspace_bytes >= srl_group_stats_workspace_bytes(G, whole_first) &&
+                    aligned(workspace, 8),
+                SRL_ERR_INVALID_ARG, "%s: rows longer than %d lanes (or a fused exchange) need a workspace of %zu bytes", fn,
+                kChunkLanes, srl_group_stats_workspace_bytes(G, whole_first));
+    ws.ticket = static_cast<unsigned int*>(workspace);
+    ws.partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + ticket_bytes(rows));
+  }
+  group_stats_kernel<<<dim3(max_chunks, rows), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(lane_part, N, idx, per,
+                                                                                                 whole_first, out, ws, fx);
+  SRL_CUDA(cudaGetLastError());
+  return SRL_OK;
+}
+}  // namespace
+}  // namespace srl
+
 extern "C" size_t srl_group_stats_workspace_bytes(int G, int whole_first) {
   const int rows = G + (whole_first ? 1 : 0);
   return srl::ticket_bytes(rows) + static_cast<size_t>(rows) * srl::kMaxChunks * SRL_LANE_PART * sizeof(double);
@@ -168,29 +233,17 @@ extern "C" size_t srl_group_stats_workspace_bytes(int G, int whole_first) {
 
 extern "C" int srl_group_stats(const double* lane_part, int N, const int32_t* idx, int G, int per, int whole_first,
                                double* out, void* workspace, size_t workspace_bytes, srl_stream_t stream) {
+  return srl::launch_group_stats("srl_group_stats", lane_part, N, idx, G, per, whole_first, out, workspace, workspace_bytes,
+                                 nullptr, nullptr, stream);
+}
+
+extern "C" int srl_group_stats_xchg(const double* lane_part, int N, const int32_t* idx, int G, int per, int whole_first,
+                                    double* local_out, double* global_out, void* workspace, size_t workspace_bytes,
+                                    srl_xchg* x, srl_stream_t stream) {
   using namespace srl;
-  SRL_REQUIRE(lane_part && out, SRL_ERR_INVALID_ARG, "srl_group_stats: null pointer");
-  SRL_REQUIRE(N >= 1 && G >= (whole_first ? 0 : 1) && per >= 1, SRL_ERR_INVALID_ARG,
-              "srl_group_stats: need N, G, per >= 1");
-  SRL_REQUIRE(idx != nullptr || static_cast<long long>(G) * per <= N, SRL_ERR_INVALID_ARG,
-              "srl_group_stats: G*per=%lld exceeds N=%d", static_cast<long long>(G) * per, N);
-  SRL_REQUIRE(G <= 65535, SRL_ERR_UNSUPPORTED, "srl_group_stats: at most 65535 groups");
-  const int rows = G + (whole_first ? 1 : 0);
-  int max_chunks = G > 0 ? chunks_of(per) : 1;
-  if (whole_first && chunks_of(N) > max_chunks) max_chunks = chunks_of(N);
-  GroupWs ws{nullptr, nullptr};
-  if (max_chunks > 1) {
-    SRL_REQUIRE(workspace != nullptr && workspace_bytes >= srl_group_stats_workspace_bytes(G, whole_first) &&
-                    aligned(workspace, 8),
-                SRL_ERR_INVALID_ARG, "srl_group_stats: rows longer than %d lanes need a workspace of %zu bytes", kChunkLanes,
-                srl_group_stats_workspace_bytes(G, whole_first));
-    ws.ticket = static_cast<unsigned int*>(workspace);
-    ws.partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + ticket_bytes(rows));
-  }
-  group_stats_kernel<<<dim3(max_chunks, rows), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(lane_part, N, idx, per,
-                                                                                                 whole_first, out, ws);
-  SRL_CUDA(cudaGetLastError());
-  return SRL_OK;
+  SRL_REQUIRE(x != nullptr, SRL_ERR_INVALID_ARG, "srl_group_stats_xchg: null exchange handle");
+  return launch_group_stats("srl_group_stats_xchg", lane_part, N, idx, G, per, whole_first, local_out, workspace,
+                            workspace_bytes, x, global_out, stream);
 }
 
 extern "C" int srl_popart_update(const double* batch_stats, double* state, double beta, double eps,

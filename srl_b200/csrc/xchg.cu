@@ -21,67 +21,14 @@
 
 #include <new>
 
-#include "common.cuh"
+#include "xchg.cuh"
 
 namespace srl {
 namespace {
 
-constexpr int kMaxWorld = 16;
-constexpr long long kSpinLimit = 4000000000ll;  // ~2 s of clock64 ticks: then give up with an error status
-
-struct XchgView {
-  unsigned long long* mailbox[kMaxWorld];  // peer p's mailbox base (mailbox[rank] = local); words = seq << 32 | payload
-  unsigned int* seq;          // local: exchanges so far
-  int* status;                // local: 0 ok, 1 timed out
-  int world, rank, cap;
-};
-
 __global__ void __launch_bounds__(256) xchg_allreduce_kernel(const XchgView v, const double* __restrict__ local,
                                                              double* __restrict__ global, int n) {
-  __shared__ int s_bad;
-  if (threadIdx.x == 0) s_bad = 0;
-  unsigned int seq = *v.seq + 1u;
-  if (seq == 0u) seq = 1u;  // 0 is the mailbox's initial state
-  const int par = static_cast<int>(seq & 1u);
-  __syncthreads();  // everybody has read the old sequence number before thread 0 updates it
-  // 1. my table, two {payload, seq} words per float64, into every mailbox (mine included), slot [par][rank]
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double x = local[i];
-    const unsigned long long tag = static_cast<unsigned long long>(seq) << 32;
-    const unsigned long long lo = tag | static_cast<unsigned int>(__double2loint(x));
-    const unsigned long long hi = tag | static_cast<unsigned int>(__double2hiint(x));
-    for (int p = 0; p < v.world; ++p) {
-      volatile unsigned long long* dst = v.mailbox[p] + ((static_cast<size_t>(par) * v.world + v.rank) * v.cap + i) * 2;
-      dst[0] = lo;
-      dst[1] = hi;
-    }
-  }
-  // 2. collect: spin on each word of each rank's slot in my own mailbox, add in rank order (the same order on every
-  //    rank -> bit-identical tables)
-  const unsigned long long* mine = v.mailbox[v.rank] + static_cast<size_t>(par) * v.world * v.cap * 2;
-  const long long t0 = clock64();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    double s = 0.0;
-    for (int q = 0; q < v.world; ++q) {
-      const volatile unsigned long long* src = mine + (static_cast<size_t>(q) * v.cap + i) * 2;
-      unsigned long long lo = src[0], hi = src[1];
-      while (static_cast<unsigned int>(lo >> 32) != seq || static_cast<unsigned int>(hi >> 32) != seq) {
-        if (clock64() - t0 > kSpinLimit) {
-          s_bad = 1;
-          break;
-        }
-        lo = src[0];
-        hi = src[1];
-      }
-      s += __hiloint2double(static_cast<int>(static_cast<unsigned int>(hi)), static_cast<int>(static_cast<unsigned int>(lo)));
-    }
-    global[i] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    *v.seq = seq;
-    if (s_bad) *v.status = 1;
-  }
+  xchg_exchange(v, local, global, n);
 }
 
 }  // namespace
@@ -93,6 +40,11 @@ struct Xchg {
   size_t bytes = 0;
   bool connected = false;
 };
+
+const XchgView* xchg_view(const srl_xchg* h) {
+  const Xchg* x = reinterpret_cast<const Xchg*>(h);
+  return (x != nullptr && x->connected) ? &x->view : nullptr;
+}
 
 namespace {
 size_t mailbox_bytes(int world, int cap) {

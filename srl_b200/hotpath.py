@@ -214,13 +214,18 @@ class HotPath:
             if self._perm_stream is None:
                 self._perm_stream = torch.cuda.Stream(device=self.device)
             self._perm_stream.wait_stream(main)
+        # with the peer-memory exchange the table is sent from the kernel that produces it (fused), see stats.cu
+        xk = dict(exchange=self.peer, global_out=self.global_stats) if (self.peer is not None and self.pg is not None) else {}
         with torch.cuda.stream(self._perm_stream if side else main):
             if self.minibatches > 1:
                 ops.group_stats(self.lane_part, idx=self.perm.view(-1), groups=self.epochs * self.minibatches,
-                                per=self.n_mb, out=self.local_stats, whole_first=True, workspace=self.stats_ws)
+                                per=self.n_mb, out=self.local_stats, whole_first=True, workspace=self.stats_ws, **xk)
             else:
-                ops.group_stats(self.lane_part, groups=1, per=self.N, out=self.local_stats[0:1], workspace=self.stats_ws)
+                ops.group_stats(self.lane_part, groups=1, per=self.N, out=self.local_stats[0:1], workspace=self.stats_ws,
+                                **xk)
         self._stats_pending = side
+        if xk:
+            return
         if self.pg is not None:
             self.exchange()
 

@@ -166,7 +166,8 @@ def group_stats_workspace(device, groups: int, whole_first: bool) -> torch.Tenso
 
 def group_stats(lane_part: torch.Tensor, idx: Optional[torch.Tensor] = None, groups: int = 1,
                 per: Optional[int] = None, out: Optional[torch.Tensor] = None, whole_first: bool = False,
-                workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+                workspace: Optional[torch.Tensor] = None, exchange=None,
+                global_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[g, k] = sum of lane_part[k, lane] over the lanes of group g (fixed summation order).
     whole_first: out gets groups + 1 rows, row 0 = the sum over all N lanes (one launch for the whole table)."""
     _check(lane_part, torch.float64, "lane_part")
@@ -188,6 +189,15 @@ def group_stats(lane_part: torch.Tensor, idx: Optional[torch.Tensor] = None, gro
         if workspace is None:
             workspace = _stats_ws[key] = group_stats_workspace(lane_part.device, groups, whole_first)
     _check(workspace, torch.uint8, "workspace")
+    if exchange is not None:  # srl_b200.xchg.PeerExchange: the table goes to the peers from this very kernel
+        if global_out is None:
+            raise ValueError("a fused exchange needs global_out")
+        _check(global_out, torch.float64, "global_out")
+        if global_out.numel() < rows * SRL_LANE_PART:
+            raise ValueError(f"global_out has {global_out.numel()} entries, need {rows * SRL_LANE_PART}")
+        _lib.call("srl_group_stats_xchg", _ptr(lane_part), N, _ptr(idx), int(groups), int(per), int(bool(whole_first)),
+                  _ptr(out), _ptr(global_out), _ptr(workspace), workspace.numel(), exchange._h, _stream())
+        return out
     _lib.call("srl_group_stats", _ptr(lane_part), N, _ptr(idx), int(groups), int(per), int(bool(whole_first)), _ptr(out),
               _ptr(workspace), workspace.numel(), _stream())
     return out

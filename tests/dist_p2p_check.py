@@ -54,6 +54,26 @@ def main():
         torch.cuda.synchronize()
         want = float(sum(q + it for q in range(world)))
         assert torch.equal(out.cpu(), torch.full((n,), want, dtype=torch.float64)), f"rank {rank} replay {it}"
+    # fused: srl_group_stats_xchg sends the table from the kernel that produces it
+    from srl_b200 import ops
+    N, G, per = 4096, 32, 512
+    gen = torch.Generator(device="cpu").manual_seed(100 + rank)
+    part = torch.rand(8, N, dtype=torch.float64, generator=gen).to(dev)
+    idx = torch.stack([torch.randperm(N, generator=gen) for _ in range(4)]).to(torch.int32).reshape(-1).to(dev)
+    ws = ops.group_stats_workspace(dev, G, True)
+    local = torch.zeros((G + 1, 8), dtype=torch.float64, device=dev)
+    fused = torch.zeros_like(local)
+    for it in range(10):
+        ops.group_stats(part, idx=idx, groups=G, per=per, out=local, whole_first=True, workspace=ws, exchange=px,
+                        global_out=fused)
+        ref = local.clone()
+        torch.cuda.synchronize()
+        dist.all_reduce(ref)
+        assert torch.allclose(fused, ref, rtol=1e-13, atol=1e-13), f"rank {rank}: fused exchange differs from all_reduce"
+        everyone = [torch.empty_like(fused) for _ in range(world)]
+        dist.all_gather(everyone, fused)
+        assert all(torch.equal(everyone[0], e) for e in everyone), "fused tables are not bit-identical across ranks"
+        part.mul_(1.01)
     # latency: p2p kernel vs NCCL all-reduce, CUDA events over 200 back-to-back calls
     def timed(fn, reps=200):
         for _ in range(20):
