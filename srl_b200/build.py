@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libsrl_b200.so")
-SOURCES = ["api.cu", "gae_scan.cu", "gae_scan_tma.cu", "ppo_loss.cu", "ppo_loss_dense.cu", "ppo_loss_gather.cu",
+SOURCES = ["api.cu", "gae_scan.cu", "gae_scan_tma.cu", "gae_scan_ws.cu", "ppo_loss.cu", "ppo_loss_dense.cu", "ppo_loss_gather.cu",
            "ppo_loss_pack.cu", "stats.cu", "perm.cu", "gather.cu", "xchg.cu", "nstep.cu"]
 
 NVCC_FLAGS = [
@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 # there (its roundings are explicit __dmul_rn / __dadd_rn as well; the flag is the belt to those braces).  The
 # loss kernels are compared at 1e-5, so they keep nvcc's default contraction (ncu: FMUL + FADD pairs were a
 # quarter of their instructions).
-FILE_FLAGS = {"gae_scan.cu": ["-fmad=false"], "gae_scan_tma.cu": ["-fmad=false"], "stats.cu": ["-fmad=false"],
+FILE_FLAGS = {"gae_scan.cu": ["-fmad=false"], "gae_scan_tma.cu": ["-fmad=false"], "gae_scan_ws.cu": ["-fmad=false"], "stats.cu": ["-fmad=false"],
               "nstep.cu": ["-fmad=false"]}
 
 

@@ -25,5 +25,7 @@ struct GaeParams {
 
 bool gae_tma_eligible(const GaeParams& p);
 int launch_gae_tma(const GaeParams& p, cudaStream_t st);
+bool gae_ws_eligible(const GaeParams& p);
+int launch_gae_ws(const GaeParams& p, cudaStream_t st);
 
 }  // namespace srl

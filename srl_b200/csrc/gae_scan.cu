@@ -319,17 +319,31 @@ extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8
   p.c = c;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-  // Throughput path: TMA-pipelined warp-per-32-lanes scan (gae_scan_tma.cu); needs 16-byte aligned rows and
-  // enough lane groups to give every SM several warps (it is issue-bound per warp, so few warps = long tail).
-  // Latency path (few lanes) and ragged shapes: the shared-memory tile kernel below.
-  // SRL_GAE_TMA_MIN_GROUPS (read once) overrides the threshold: a tuning knob for profiles/, not an API.
+  // Three kernels, picked by how many 32-lane groups the batch has (SRL_GAE_PATH=tile|tma|ws, read once, overrides:
+  // a tuning knob for profiles/, not an API):
+  //   >= 2 groups per SM : one warp per lane group, TMA ring (gae_scan_tma.cu): fewest instructions per row
+  //   fewer              : warp-specialised CTA per lane group (gae_scan_ws.cu): the chain runs in its own warp and 16
+  //                        worker warps keep a lone CTA's latency per chunk short (measured at mid sizes -- cfg3, cfg4 --
+  //                        it only ties or loses: there the machine is issue-bound and it executes more instructions)
+  //   ragged / unaligned / V-trace on few lanes: the shared-memory tile kernel below
+  static const int path_env = [] {
+    const char* e = getenv("SRL_GAE_PATH");
+    if (e == nullptr) return 0;
+    return e[0] == 't' && e[1] == 'i' ? 1 : (e[0] == 't' ? 2 : (e[0] == 'w' ? 3 : 0));
+  }();
   static const int min_groups_env = [] {
     const char* e = getenv("SRL_GAE_TMA_MIN_GROUPS");
     return e ? atoi(e) : -1;
   }();
+  const int groups = (N + 31) / 32;
   const int min_groups = min_groups_env >= 0 ? min_groups_env : 2 * sm_count();
-  const bool use_tma = gae_tma_eligible(p) && (N + 31) / 32 >= min_groups;
+  bool use_tma = gae_tma_eligible(p) && groups >= min_groups;
+  bool use_ws = !use_tma && groups >= 8 && gae_ws_eligible(p);  // a handful of lanes: the tile kernel's many short CTAs win
+  if (path_env == 1) use_tma = use_ws = false;
+  if (path_env == 2) use_tma = gae_tma_eligible(p), use_ws = false;
+  if (path_env == 3) use_ws = gae_ws_eligible(p), use_tma = use_tma && !use_ws;
   if (use_tma) return launch_gae_tma(p, st);
+  if (use_ws) return launch_gae_ws(p, st);
 
   // General path (any N, any alignment): shared-memory tile kernel below.
   // Lane-tile width: the widest tile that (a) fits shared memory and (b) still gives every SM work.
