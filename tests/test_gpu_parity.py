@@ -120,7 +120,10 @@ def test_gae_vs_oracle_config_shapes(ops, cfg_name, B):
     assert not part[7].any()
 
 
-@pytest.mark.parametrize("L,N", [(2, 1), (3, 5), (9, 31), (33, 33), (130, 257), (401, 100), (1000, 64)])
+@pytest.mark.parametrize("L,N", [(2, 1), (3, 5), (9, 31), (33, 33), (130, 257), (401, 100), (1000, 64),
+                                 # 8 .. 295 lane groups of 16-byte aligned rows: the warp-specialised kernel, with chunk
+                                 # counts around the ring depth and trajectories that end inside / at a chunk boundary
+                                 (2, 256), (16, 256), (17, 512), (33, 1024), (49, 272), (401, 1040), (129, 4096)])
 def test_gae_ragged_and_extreme_shapes(ops, L, N):
     """Edge shapes: shortest legal scan, lane counts that are not tile multiples, long horizons."""
     cfg = synth.PathConfig("edge", T=L - 1, B=N, p_end=0.1, gamma=0.995, lmbda=0.9)
@@ -787,3 +790,33 @@ def test_group_stats_long_rows(ops):
         part = torch.rand(8, N, dtype=torch.float64, device="cuda")
         out = ops.group_stats(part, groups=1, per=N)
         np.testing.assert_allclose(out[0, :7].cpu().numpy(), part[:7].sum(1).cpu().numpy(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("L,N,lo,boot", [(40, 512, 3, 5), (65, 1024, 0, 17), (18, 256, 1, 1)])
+def test_gae_ws_kernel_popart_rows_and_stats(ops, L, N, lo, boot):
+    """Shapes that route to the warp-specialised kernel, with PopArt denormalisation, burn-in / bootstrap rows and the
+    per-lane statistics checked against the oracle (adv / ret bit-exact)."""
+    cfg = synth.PathConfig("ws", T=L - lo - boot, B=N, bootstrap_steps=boot, burn_in_steps=lo, p_end=0.1, gamma=0.995,
+                           lmbda=0.9)
+    s = synth.make_sample_scalars(cfg, seed=L + N)
+    pa = M.RunningMeanStdRef((1,), beta=0.99)
+    pa.update(torch.randn(64, 1, generator=torch.Generator().manual_seed(2)) * 2.5 + 0.7)
+    m_, s_ = pa.mean_std()
+    hi = L - boot
+    adv, ret, part = run_gae(ops, dict(s, gamma=cfg.gamma, lmbda=cfg.lmbda), row_lo=lo, row_hi=hi,
+                             popart_ms=np.array([m_.item(), s_.item()]))
+    t = {k: torch.from_numpy(flat2(v)).float() for k, v in s.items()}
+    ra, rr = M.adv_and_value_target_ref(t["reward"], t["value"], t["truncated"], t["done"], t["on_reset"], cfg.gamma,
+                                        cfg.lmbda, popart=pa)
+    assert np.array_equal(adv[:-1], ra.numpy()) and np.array_equal(ret[:-1], rr.numpy())
+    assert not adv[-1].any() and not ret[-1].any()
+    mask = 1 - t["on_reset"][lo + 1:hi + 1].double()
+    x = torch.from_numpy(adv[lo:hi]).double() * mask
+    y = torch.from_numpy(ret[lo:hi]).double() * mask
+    np.testing.assert_array_equal(part[0], mask.sum(0).numpy())
+    np.testing.assert_allclose(part[1], x.sum(0).numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(part[2], x.square().sum(0).numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(part[3], y.sum(0).numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(part[4], y.square().sum(0).numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_array_equal(part[5], t["done"][lo:hi].double().sum(0).numpy())
+    np.testing.assert_array_equal(part[6], t["truncated"][lo:hi].double().sum(0).numpy())
