@@ -820,3 +820,29 @@ def test_gae_ws_kernel_popart_rows_and_stats(ops, L, N, lo, boot):
     np.testing.assert_allclose(part[4], y.square().sum(0).numpy(), rtol=1e-12, atol=1e-12)
     np.testing.assert_array_equal(part[5], t["done"][lo:hi].double().sum(0).numpy())
     np.testing.assert_array_equal(part[6], t["truncated"][lo:hi].double().sum(0).numpy())
+
+
+def test_gae_ws_kernel_repeatable_under_load(ops):
+    """The warp-specialised kernel hands chunks between warps through mbarriers (release / acquire); 200 launches of
+    the cfg2 shape back to back, with another stream keeping the SMs busy, must reproduce the first result bit for
+    bit (a missing ordering edge would show up as an occasional stale read)."""
+    cfg = synth.CONFIGS["cfg2_atari_large"]
+    s = synth.make_sample_scalars(cfg, seed=11)
+    d = {k: dev(flat2(v)) for k, v in s.items()}
+    L, N = cfg.L, cfg.N
+    pack = torch.empty((L, N, 4), dtype=torch.float32, device="cuda")
+    run = lambda: ops.gae_scan(d["reward"], d["value"], d["done"], d["truncated"], d["on_reset"], cfg.gamma, cfg.lmbda,
+                               row_lo=0, row_hi=cfg.T, old_logp=d["old_logp"], pack=pack)
+    adv0, ret0, part0 = (x.clone() for x in run())
+    pack0 = pack.clone()
+    noise_stream = torch.cuda.Stream()
+    junk = torch.randn(1 << 22, device="cuda")
+    for it in range(200):
+        if it % 4 == 0:
+            with torch.cuda.stream(noise_stream):
+                junk.mul_(1.0001).add_(0.5)
+        pack.fill_(7.0)
+        adv, ret, part = run()
+        ok = torch.equal(adv, adv0) and torch.equal(ret, ret0) and torch.equal(part, part0) and \
+            torch.equal(pack.view(torch.int32), pack0.view(torch.int32))
+        assert ok, f"launch {it} differs from the first launch"
