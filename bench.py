@@ -8,7 +8,7 @@ A "step" = one pass of the hot path over one synthetic batch: G
 `value` = T*N transitions per step (x ranks) / device time with inputs resident in HBM; `e2e` = the same
 through `HotPath.run_host` with pinned HOST buffers in and out (H2D + D2H inside the timed region).
 N > 1 (torchrun): every rank owns its own slice of environments (weak scaling, the full config per GPU);
-the only data-path collective is the all-reduce of the float64 statistics table.
+the only data-path exchange is the SUM of the float64 statistics table (NVLink peer-memory mailboxes, or NCCL).
 `--impl reference` times the reference's CPU path (the oracle port: /root/reference is a Python tree that
 does not exist on the GPU box) on the host cores, same config / metric / unit.
 """

@@ -7,12 +7,14 @@ whole step.  `srl_b200.trainer.MultiAgentPPOB200` and `bench.py` both drive this
 Step structure (reference: MultiAgentPPO.step, legacy/algorithm/ppo/mappo.py:219-328):
 
     load_sample        H2D of the six scalar leaves                      (api/trainer.py:215-217)
-    advantages         K2 GAE scan -> adv, ret, per-lane partial sums    (mappo.py:252-257)
-                       K5 Philox permutations for all epochs             (new)
-                       group statistics for the batch and every minibatch
-                       [one all-reduce of the whole table across ranks]  (utils.py:58-61,121-124)
+    advantages         K2 GAE scan -> adv, ret, loss pack, per-lane sums (mappo.py:252-257)
+                       K5 Philox permutations for all epochs, on a parallel branch (new)
+                       group statistics for the batch and every minibatch; with several ranks the same kernel
+                       exchanges the table over NVLink peer memory       (utils.py:58-61,121-124)
     per epoch          PopArt update                                      (mappo.py:263-264)
-      per minibatch    K4 fused loss forward+backward, gather fused in   (mappo.py:270-274)
+      all minibatches  K4 fused loss forward+backward in ONE launch, gather fused in   (mappo.py:270-274)
+                       (one GPU, no PopArt, minibatches <= 1024 lanes: K4 adds its own minibatch statistics and the
+                       table is produced on a side branch; the trainer's per-minibatch launches read the table)
 
 HBM layout: every leaf is time-major [L, N], lanes contiguous; N = B * n_agents; flags stay uint8.
 Statistics table: float64 [1 + E*M, 8]; row 0 = whole batch, row 1 + e*M + j = minibatch j of epoch e.
