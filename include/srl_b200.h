@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SRL_B200_ABI_VERSION 2
+#define SRL_B200_ABI_VERSION 3
 
 typedef void* srl_stream_t; /* cudaStream_t */
 
@@ -85,6 +85,40 @@ int srl_gae_scan(const float* reward,          /* [L, N]; row L-1 is ignored    
                  double* lane_part, /* [SRL_LANE_PART, N] out or NULL */
                  float* pack,       /* [L, N, 4] out or NULL */
                  srl_stream_t stream);
+
+/* The general form of the same scan: everything modules.gae_trace (legacy/algorithm/modules/gae.py:8-97) accepts
+ * beyond what MultiAgentPPO passes -- vector critics (reward / value / adv / ret are [.., N, critic_dim], the flags stay
+ * [.., N] and broadcast over the critic axis, gae.py:26-30), per-element discount / lambda tensors (gamma_t, lmbda_t:
+ * [L-1, N] float32 or NULL = the scalar; gae.py:31-34,51-60: gamma_t * lmbda_t is a float64 product per element) and a
+ * ready-made importance ratio (imp_ratio [L-1, N] or NULL; gae.py:36,64-65,88-89).
+ *   done == NULL : `value` is used as it is (plain gae_trace); else v' = value * (1 - done) in float32 (mappo.py:120-124)
+ *   ret  == NULL : advantages only (gae_trace's return value); else ret = adv + v' in float32 (mappo.py:143)
+ *   pad_last_row : adv / ret have L rows and row L-1 is zeroed (mappo.py:254-256); else they have L-1 rows.
+ * Same float64 rounding sequence as srl_gae_scan (bit-identical where both apply); no statistics, no pack. */
+int srl_gae_trace(const float* reward,       /* [>= L-1, N, critic_dim]                    */
+                  const float* value,        /* [L, N, critic_dim]                         */
+                  const uint8_t* done,       /* [L, N] or NULL                             */
+                  const uint8_t* truncated,  /* [L, N]                                     */
+                  const uint8_t* on_reset,   /* [L, N]                                     */
+                  const float* gamma_t,      /* [L-1, N] or NULL                           */
+                  const float* lmbda_t,      /* [L-1, N] or NULL                           */
+                  const float* imp_ratio,    /* [L-1, N] or NULL (V-trace off)             */
+                  int L, int N, int critic_dim, double gamma, double lmbda, double rho, double c, int pad_last_row,
+                  float* adv, float* ret, srl_stream_t stream);
+
+/* GAE along whole episodes: replaces TrajGAE.process (legacy/algorithm/modules/gae.py:100-139, the 'gae' trajectory
+ * post-processor of api/trainer.py:84-99,249-262) for MANY episodes in one launch.  Episode k occupies steps
+ * [offsets[k], offsets[k+1]) of reward / value / adv / ret, each [total_steps, width] in the arrays' own dtype
+ * (float32, or float64 when is_float64 != 0 -- numpy semantics: the python scalars gamma and gamma * lmbda are rounded
+ * to the array dtype, every operation rounds in that dtype).  For steps s = len-2 .. 0 of an episode:
+ *   boot  = s == len-2 ? (final_has_value[k] ? value[last] * final_truncated[k] : 0) : value[s+1]
+ *   delta = reward[s] + gamma * boot - value[s];  gae = gamma * lmbda * gae + delta
+ *   adv[s] = gae;  ret[s] = gae + value[s]
+ * The last step of every episode is left untouched, as in the reference. */
+int srl_traj_gae(const void* reward, const void* value, const int64_t* offsets /* device [n_traj + 1] */,
+                 const uint8_t* final_truncated /* device [n_traj, width] */,
+                 const uint8_t* final_has_value /* device [n_traj] */, int n_traj, int width, int is_float64,
+                 double gamma, double lmbda, void* adv, void* ret, srl_stream_t stream);
 
 /* n-step return on the same [rows, N] layout (rows = n + T - 1): replaces modules.n_step_return
  * (legacy/algorithm/modules/n_step_return.py:11-50; the return estimator of the DQN / QMIX trainers), float64 with the

@@ -223,6 +223,81 @@ def gen_nstep(R):
     return sorted({k.split(".")[0] for k in out})
 
 
+def _episodes(seed, dtype, W, n_eps):
+    """Random finished episodes: lengths 2..40 (and one of length 1), final step done / truncated / without value."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    eps = []
+    for k in range(n_eps):
+        n = 1 if k == 3 else int(rng.integers(2, 41))
+        kind = k % 3  # 0: truncated with final value, 1: done with final value, 2: done without analyzed_result
+        eps.append(dict(reward=rng.standard_normal((n, W)).astype(dtype), value=(3 * rng.standard_normal((n, W))).astype(dtype),
+                        truncated=np.full((W,), kind == 0, dtype=np.uint8), has_value=kind != 2))
+    return eps
+
+
+def gen_traj_gae(R):
+    """TrajGAE.process (legacy/algorithm/modules/gae.py:100-139) of the unmodified reference on random episodes, fed as
+    lists of per-step SampleBatches exactly as an actor worker does (actor_worker.py:152-155); plus the two hand-made
+    episodes of the reference's own test (legacy/tests/modules_test.py:140-178)."""
+    SB, AR = R.trainer.SampleBatch, R.namedarray.NamedArray
+    out = {}
+    for name, (dtype, W, gamma, lmbda) in dict(f32w1=(np.float32, 1, 0.99, 0.97), f32w3=(np.float32, 3, 0.997, 0.95),
+                                               f64w2=(np.float64, 2, 0.9, 0.8)).items():
+        eps = _episodes(7, dtype, W, 12)
+        proc = R.gae.TrajGAE(gamma=gamma, lmbda=lmbda)
+        rw, vl, tr, hv, lens, adv, ret = [], [], [], [], [], [], []
+        for ep in eps:
+            n = ep["reward"].shape[0]
+            memory = []
+            for i in range(n):
+                last = i == n - 1
+                ar = None if (last and not ep["has_value"]) else AR(value=ep["value"][i].copy(), adv=None, ret=None)
+                trunc = ep["truncated"] if last else np.zeros((W,), np.uint8)
+                memory.append(SB(obs=None, reward=ep["reward"][i].copy(), analyzed_result=ar,
+                                 done=(1 - trunc).astype(np.uint8) if last else np.zeros((W,), np.uint8), truncated=trunc))
+            memory = proc.process(memory)
+            a = np.stack([m.analyzed_result.adv for m in memory[:-1]]) if n > 1 else np.zeros((0, W), dtype)
+            r = np.stack([m.analyzed_result.ret for m in memory[:-1]]) if n > 1 else np.zeros((0, W), dtype)
+            assert a.dtype == dtype and r.dtype == dtype
+            rw.append(ep["reward"]); vl.append(ep["value"]); tr.append(ep["truncated"]); hv.append(ep["has_value"])
+            lens.append(n); adv.append(a); ret.append(r)
+        out.update({f"{name}.reward": np.concatenate(rw), f"{name}.value": np.concatenate(vl),
+                    f"{name}.final_truncated": np.stack(tr), f"{name}.final_has_value": np.array(hv, np.uint8),
+                    f"{name}.lens": np.array(lens, np.int64), f"{name}.adv": np.concatenate(adv),
+                    f"{name}.ret": np.concatenate(ret), f"{name}.gamma": np.float64(gamma), f"{name}.lmbda": np.float64(lmbda)})
+    np.savez_compressed(os.path.join(GOLDEN, "traj_gae.npz"), **out)
+    return sorted({k.split(".")[0] for k in out})
+
+
+def gen_gae_general(R):
+    """modules.gae_trace itself (gae.py:8-97) on what MultiAgentPPO never passes: vector critics, per-element gamma /
+    lambda tensors, a ready-made importance ratio.  Run with -O: the data asserts of gae.py:69-77 assume zero rewards
+    and values at episode ends, which random vector-critic data does not satisfy."""
+    g = torch.Generator().manual_seed(23)
+    out = {}
+    for name, (T, B, Nc, gt, lt, vt) in dict(nc3=(21, 9, 3, False, False, False), gam=(33, 17, 1, True, False, False),
+                                             lam=(18, 40, 1, False, True, False), both_nc2=(25, 6, 2, True, True, False),
+                                             all=(30, 11, 4, True, True, True), vt_nc1=(16, 35, 1, False, False, True)).items():
+        cfg = synth.PathConfig(name, T=T, B=B, p_end=0.08)
+        s = synth.make_sample_scalars(cfg, seed=5)
+        flags = {k: torch.from_numpy(s[k]).float() for k in ("done", "truncated", "on_reset")}
+        reward = torch.randn(T, B, Nc, generator=g) * (1 - flags["on_reset"][1:])
+        value = torch.randn(T + 1, B, Nc, generator=g) * 2
+        gamma = (0.9 + 0.1 * torch.rand(T, B, 1, generator=g)) if gt else 0.99
+        lmbda = (0.8 + 0.2 * torch.rand(T, B, 1, generator=g)) if lt else 0.95
+        ratio = torch.exp(0.5 * torch.randn(T, B, 1, generator=g)) if vt else None
+        adv = R.gae.gae_trace(reward, value, flags["truncated"], flags["done"], flags["on_reset"], gamma, lmbda,
+                              vtrace=vt, imp_ratio=ratio, rho=1.0, c=0.9)
+        out.update({f"{name}.reward": reward.numpy(), f"{name}.value": value.numpy(), f"{name}.adv": adv.numpy(),
+                    **{f"{name}.{k}": s[k] for k in ("done", "truncated", "on_reset")}})
+        out[f"{name}.gamma"] = gamma.numpy() if gt else np.float64(gamma)
+        out[f"{name}.lmbda"] = lmbda.numpy() if lt else np.float64(lmbda)
+        if vt:
+            out[f"{name}.imp_ratio"] = ratio.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "gae_general.npz"), **out)
+    return sorted({k.split(".")[0] for k in out})
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
@@ -230,11 +305,17 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "nstep":  # only the n-step fixture (added after the others)
         print("nstep:", gen_nstep(R))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "family":  # TrajGAE + general gae_trace fixtures (added later still)
+        print("traj_gae:", gen_traj_gae(R))
+        print("gae_general:", gen_gae_general(R))
+        return
     print("gae:", gen_gae(R))
     print("loss:", gen_loss(R))
     gen_masknorm_popart(R)
     gen_stack(R)
     print("nstep:", gen_nstep(R))
+    print("traj_gae:", gen_traj_gae(R))
+    print("gae_general:", gen_gae_general(R))
     total = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))
     print(f"wrote {len(os.listdir(GOLDEN))} files, {total / 1024:.0f} KiB")
 

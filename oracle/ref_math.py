@@ -119,6 +119,30 @@ def traj_gae_ref(rewards, values, last_truncated: bool, last_has_value: bool, ga
     return adv, ret
 
 
+def traj_gae_process_ref(reward, value, last_truncated, last_has_value: bool, gamma: float, lmbda: float):
+    """gae.py:106-139 on one episode given as arrays: reward / value `[n, W]` in their own dtype (numpy semantics:
+    float32 arrays stay float32, python-float gamma and gamma * lmbda are rounded to the array dtype by the ufunc),
+    last_truncated `[W]`.  Returns (adv, ret) `[n-1, W]`; the loop and its op order are the reference's."""
+    n = reward.shape[0]
+    adv, ret = [None] * max(n - 1, 0), [None] * max(n - 1, 0)
+    gae = np.zeros_like(reward[0])  # gae.py:112
+    step = n - 2
+    while step >= 0:
+        if step == n - 2:
+            bootstrap = value[step + 1] * last_truncated if last_has_value else 0  # gae.py:117-123
+        else:
+            bootstrap = value[step + 1]
+        delta = reward[step] + gamma * bootstrap - value[step]  # gae.py:127
+        gae = gamma * lmbda * gae + delta  # gae.py:128
+        adv[step] = gae
+        ret[step] = gae + value[step]
+        step -= 1
+    if n < 2:
+        empty = np.zeros((0,) + reward.shape[1:], dtype=np.result_type(reward.dtype, value.dtype))
+        return empty, empty.copy()
+    return np.stack(adv), np.stack(ret)
+
+
 # --------------------------------------------------------------------------------------------
 # A4: masked normalisation (legacy/algorithm/modules/utils.py:10-67)
 # --------------------------------------------------------------------------------------------

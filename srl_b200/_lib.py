@@ -19,7 +19,7 @@ SRL_LANE_PART = 8
 SRL_LOSS_OUT_LEN = 16
 SRL_MAX_LEAVES = 32
 SRL_MAX_HEADS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 SRL_MAX_LOSS_BATCH = 32
 
 # enum srl_loss_out
@@ -76,6 +76,9 @@ SIGNATURES = {
     "srl_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "srl_gae_scan": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double] +
                      [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "srl_gae_trace": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_double, c_double, c_double, c_double, c_int,
+                              c_void_p, c_void_p, c_void_p]),
+    "srl_traj_gae": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "srl_n_step_return": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_double, c_void_p, c_void_p]),
     "srl_lane_stats": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "srl_group_stats_workspace_bytes": (c_size_t, [c_int, c_int]),

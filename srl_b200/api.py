@@ -9,6 +9,7 @@ Inside an SRL checkout, use SRL's own classes: `srl_b200.srl_plugin.register_int
   Trainer              api/trainer.py:109-157
   PytorchTrainer       api/trainer.py:160-193    (policy property, distributed(), device selection)
   register / make      api/trainer.py:231-246
+  TrajPostprocessor, register_traj_postprocessor / make_traj_postprocessor   api/trainer.py:84-99,249-262
 """
 from __future__ import annotations
 
@@ -104,3 +105,33 @@ def make(cfg, policy):
     if hasattr(policy, "train_mode"):
         policy.train_mode()
     return ALL_TRAINER_CLASSES[type_](policy=policy, **args)
+
+
+class TrajPostprocessor:
+    """Post-process trajectories in actor workers before sending to trainers (api/trainer.py:84-91)."""
+
+    def process(self, memory):
+        raise NotImplementedError()
+
+
+class NullTrajPostprocessor(TrajPostprocessor):
+
+    def process(self, memory):
+        return memory
+
+
+ALL_TRAJ_POSTPROCESSOR_CLASSES: Dict[str, Any] = {}
+
+
+def register_traj_postprocessor(name, cls_) -> None:
+    ALL_TRAJ_POSTPROCESSOR_CLASSES[name] = cls_
+
+
+register_traj_postprocessor("null", NullTrajPostprocessor)
+
+
+def make_traj_postprocessor(cfg):
+    """api/trainer.py:255-262: `cfg` is a name or an object with .type_/.args."""
+    type_ = cfg if isinstance(cfg, str) else cfg.type_
+    args = {} if isinstance(cfg, str) else (cfg.args or {})
+    return ALL_TRAJ_POSTPROCESSOR_CLASSES[type_](**args)

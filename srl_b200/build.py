@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libsrl_b200.so")
 SOURCES = ["api.cu", "gae_scan.cu", "gae_scan_tma.cu", "gae_scan_ws.cu", "ppo_loss.cu", "ppo_loss_dense.cu", "ppo_loss_gather.cu",
-           "ppo_loss_pack.cu", "stats.cu", "perm.cu", "gather.cu", "xchg.cu", "nstep.cu"]
+           "ppo_loss_pack.cu", "stats.cu", "perm.cu", "gather.cu", "xchg.cu", "nstep.cu", "gae_general.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",  # B200 only; no PTX for other archs, no fallback
@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 # loss kernels are compared at 1e-5, so they keep nvcc's default contraction (ncu: FMUL + FADD pairs were a
 # quarter of their instructions).
 FILE_FLAGS = {"gae_scan.cu": ["-fmad=false"], "gae_scan_tma.cu": ["-fmad=false"], "gae_scan_ws.cu": ["-fmad=false"], "stats.cu": ["-fmad=false"],
-              "nstep.cu": ["-fmad=false"]}
+              "nstep.cu": ["-fmad=false"], "gae_general.cu": ["-fmad=false"]}
 
 
 def find_nvcc() -> str:

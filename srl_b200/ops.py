@@ -112,6 +112,84 @@ def gae_scan(reward, value, done, truncated, on_reset, gamma: float, lmbda: floa
     return adv, ret, lane_part
 
 
+def gae_trace(reward, value, truncated, done, on_reset, gamma, lmbda, vtrace: bool = False, imp_ratio=None,
+              rho: float = 1.0, c: float = 1.0, high_precision: bool = True, apply_done: bool = False,
+              want_ret: bool = False, pad_last_row: bool = False):
+    """Same signature and meaning as modules.gae_trace (legacy/algorithm/modules/gae.py:8-97), on device:
+    reward float32 `[T, bs, Nc]`, value `[T+1, bs, Nc]`, truncated / done / on_reset uint8 `[T+1, bs, 1]`; `gamma` /
+    `lmbda` a python float or a float32 tensor `[T, bs, 1]`; `imp_ratio` float32 `[T, bs, 1]` with `vtrace`.
+    Returns adv float32 `[T, bs, Nc]` (`[T+1, ..]` with a zero row when `pad_last_row`, mappo.py:254-256).
+    `apply_done` multiplies value by (1 - done) first and `want_ret` also returns the value target -- together they are
+    MultiAgentPPO._compute_adv_and_value_target (mappo.py:118-144) for vector critics and per-element discounts.
+    `done` is otherwise only shape-checked: the reference reads it in its data asserts alone (gae.py:69-77)."""
+    if not high_precision:
+        raise NotImplementedError("gae_trace: only the float64 scan (high_precision=True, the reference's default)")
+    for name, t in (("reward", reward), ("value", value)):
+        _check(t, torch.float32, name)
+    for name, t in (("truncated", truncated), ("done", done), ("on_reset", on_reset)):
+        _check(t, torch.uint8, name)
+    L = value.shape[0]
+    if L < 2 or reward.shape[0] < L - 1:
+        raise ValueError(f"value needs >= 2 rows and reward >= L-1 rows; got {tuple(value.shape)}, {tuple(reward.shape)}")
+    N = on_reset[0].numel()
+    if value[0].numel() % N != 0:
+        raise ValueError(f"value {tuple(value.shape)} is not on_reset {tuple(on_reset.shape)} x critic_dim")
+    Nc = value[0].numel() // N
+    if reward[0].numel() != N * Nc:
+        raise ValueError(f"reward {tuple(reward.shape)} does not match value {tuple(value.shape)}")
+    for name, t in (("truncated", truncated), ("done", done)):
+        if t.shape[0] != L or t[0].numel() != N:
+            raise ValueError(f"{name}: shape {tuple(t.shape)} does not match on_reset {tuple(on_reset.shape)}")
+    per = {}
+    for name, x in (("gamma", gamma), ("lmbda", lmbda)):
+        if isinstance(x, torch.Tensor):
+            _check(x, torch.float32, name)
+            if x.shape[0] != L - 1 or x[0].numel() != N:  # gae.py:53,58: same shape as on_reset[:-1]
+                raise AssertionError(tuple(x.shape))
+            per[name] = x
+        elif not isinstance(x, float):
+            raise AssertionError(type(x))  # gae.py:52,57
+    if vtrace:
+        if imp_ratio is None:
+            raise ValueError("vtrace needs imp_ratio")
+        _check(imp_ratio, torch.float32, "imp_ratio")
+        if imp_ratio.shape[0] < L - 1 or imp_ratio[0].numel() != N:
+            raise ValueError(f"imp_ratio: need [>= {L - 1}, {N}], got {tuple(imp_ratio.shape)}")
+    rows = L if pad_last_row else L - 1
+    adv = torch.empty((rows,) + tuple(value.shape[1:]), dtype=torch.float32, device=value.device)
+    ret = torch.empty_like(adv) if want_ret else None
+    _lib.call("srl_gae_trace", _ptr(reward), _ptr(value), _ptr(done) if apply_done else None, _ptr(truncated),
+              _ptr(on_reset), _ptr(per.get("gamma")), _ptr(per.get("lmbda")), _ptr(imp_ratio) if vtrace else None, L, N,
+              Nc, 0.0 if "gamma" in per else float(gamma), 0.0 if "lmbda" in per else float(lmbda), float(rho), float(c),
+              int(bool(pad_last_row)), _ptr(adv), _ptr(ret), _stream())
+    return (adv, ret) if want_ret else adv
+
+
+def traj_gae(reward, value, offsets, final_truncated, final_has_value, gamma: float, lmbda: float):
+    """GAE along whole episodes laid out one after another (TrajGAE.process, gae.py:100-139, for many episodes):
+    reward / value `[total_steps, W]` float32 or float64 (one dtype), offsets int64 `[n + 1]`, final_truncated uint8
+    `[n, W]`, final_has_value uint8 `[n]`.  Returns (adv, ret) like reward; the last step of each episode is left 0."""
+    if reward.dtype not in (torch.float32, torch.float64):
+        raise ValueError(f"reward: expected float32 or float64, got {reward.dtype}")
+    _check(reward, reward.dtype, "reward")
+    _check(value, reward.dtype, "value")
+    _check(offsets, torch.int64, "offsets")
+    _check(final_truncated, torch.uint8, "final_truncated")
+    _check(final_has_value, torch.uint8, "final_has_value")
+    if reward.dim() != 2 or value.shape != reward.shape:
+        raise ValueError(f"reward / value: expected equal [total_steps, W] shapes, got {tuple(reward.shape)}, "
+                         f"{tuple(value.shape)}")
+    n = offsets.numel() - 1
+    W = reward.shape[1]
+    if n < 0 or final_has_value.numel() != n or final_truncated.numel() != n * W:
+        raise ValueError("offsets / final_truncated / final_has_value disagree on the number of episodes")
+    adv = torch.zeros_like(reward)
+    ret = torch.zeros_like(reward)
+    _lib.call("srl_traj_gae", _ptr(reward), _ptr(value), _ptr(offsets), _ptr(final_truncated), _ptr(final_has_value), n,
+              W, int(reward.dtype == torch.float64), float(gamma), float(lmbda), _ptr(adv), _ptr(ret), _stream())
+    return adv, ret
+
+
 def n_step_return(n: int, reward, nex_value, nex_done, nex_truncated, gamma: float,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """n-step return: reward / nex_value float32 and nex_done / nex_truncated uint8, all `[n+T-1, N(, 1)]`; returns
@@ -559,3 +637,74 @@ def batch_gather(pairs: List[Tuple[torch.Tensor, torch.Tensor]], idx: Optional[t
         chunk = descs[i:i + SRL_MAX_LEAVES]
         arr = (LeafDesc * len(chunk))(*chunk)
         _lib.call("srl_batch_gather", arr, len(chunk), _ptr(idx), L, B, _stream())
+
+
+_chunk_idx = {}
+
+
+def _row_split(row_bytes: int, items: int) -> int:
+    """Pieces a moved row is cut into so that a reshape of a few huge rows (an observation leaf: B x 28 KB per time
+    step) still spreads over every SM: pieces of >= 16 KB, 16-byte granules kept, at most ~64 K items."""
+    want = min(row_bytes // 16384, max(1, 65536 // max(items, 1)))
+    for cand in range(int(want), 1, -1):
+        if row_bytes % cand == 0 and (row_bytes // cand) % 16 == 0:
+            return cand
+    return 1
+
+
+def _split_index(device, outer: int, outer_stride: int, split: int) -> torch.Tensor:
+    """int32 [outer * split]: idx[o * split + k] = o * outer_stride + k (cached per shape and device)."""
+    key = (torch.device(device).index, outer, outer_stride, split)
+    idx = _chunk_idx.get(key)
+    if idx is None:
+        o = torch.arange(outer, dtype=torch.int32, device=device).view(-1, 1) * outer_stride
+        idx = _chunk_idx[key] = (o + torch.arange(split, dtype=torch.int32, device=device).view(1, -1)).reshape(-1)
+    return idx
+
+
+def to_chunk(x: torch.Tensor, num_chunks: int) -> torch.Tensor:
+    """modules.to_chunk (legacy/algorithm/modules/utils.py:164-180): `[T, B, *D]` -> `[T//C, B*C, *D]`, chunk c of the
+    time axis becomes columns [c*B, (c+1)*B) -- one K1 launch (dst[t', c] = src row c*(T//C) + t'), bit-exact."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise ValueError("to_chunk: expected a CUDA tensor (srl_b200 has no CPU path)")
+    T = x.shape[0]
+    if T % num_chunks != 0:  # same error as the reference (utils.py:176-179)
+        raise IndexError(f"The first dimension(usually the step/time) {T} must be a multiple of "
+                         f"num_chunks {num_chunks}. This usually means the sample_steps(config:AgentSpec) "
+                         f"is not dividable by chunk_len(config:Policy).")
+    Tc = T // num_chunks
+    B = x.shape[1]
+    x = x if x.is_contiguous() else x.contiguous()
+    out = torch.empty((Tc, B * num_chunks) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+    if x.numel() == 0:
+        return out
+    row_bytes = x[0].numel() * x.element_size()
+    split = _row_split(row_bytes, T)
+    piece = row_bytes // split
+    # item (t', j = c*split + k): piece k of source row c*Tc + t' -> slot c*Tc*split + k, time stride = one row
+    idx = _split_index(x.device, num_chunks, Tc * split, split)
+    d = LeafDesc(x.data_ptr(), out.data_ptr(), piece, T * split, row_bytes, piece)
+    _lib.call("srl_batch_gather", (LeafDesc * 1)(d), 1, _ptr(idx), Tc, num_chunks * split, _stream())
+    return out
+
+
+def back_to_trajectory(x: torch.Tensor, num_chunks: int) -> torch.Tensor:
+    """modules.back_to_trajectory (utils.py:183-195), the inverse of to_chunk: `[T//C, B*C, *D]` -> `[T, B, *D]`."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise ValueError("back_to_trajectory: expected a CUDA tensor (srl_b200 has no CPU path)")
+    Tc, BC = x.shape[0], x.shape[1]
+    if BC % num_chunks != 0:
+        raise IndexError(f"The second dimension {BC} must be a multiple of num_chunks {num_chunks}.")
+    B = BC // num_chunks
+    x = x if x.is_contiguous() else x.contiguous()
+    out = torch.empty((Tc * num_chunks, B) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+    if x.numel() == 0:
+        return out
+    blk = (x[0].numel() // num_chunks) * x.element_size()  # one [B, *D] block
+    split = _row_split(blk, Tc * num_chunks)
+    piece = blk // split
+    # destination row c*Tc + t' is item (t = c, j = t'*split + k): piece k of source block t'*C + c
+    idx = _split_index(x.device, Tc, num_chunks * split, split)
+    d = LeafDesc(x.data_ptr(), out.data_ptr(), piece, Tc * num_chunks * split, blk, piece)
+    _lib.call("srl_batch_gather", (LeafDesc * 1)(d), 1, _ptr(idx), num_chunks, Tc * split, _stream())
+    return out

@@ -11,6 +11,7 @@ Nothing else in SRL changes: `api.trainer.make` builds the policy and calls `cls
 (api/trainer.py:238-246); `GPUThread` calls `trainer.distributed(...)` once and `trainer.step(sample)` in a loop
 (distributed/system/trainer_worker.py:94,171).
 """
+from srl_b200.postprocess import TrajGAEB200
 from srl_b200.trainer import MultiAgentPPOB200
 
 
@@ -21,6 +22,8 @@ def register_into_srl(name: str = "mappo_b200") -> bool:
     except Exception:
         return False
     srl_trainer.register(name, MultiAgentPPOB200)
+    # the actor-side sibling: api.config.TrajPostprocessor('gae_b200', args=dict(gamma=..., lmbda=...))
+    srl_trainer.register_traj_postprocessor("gae_b200", TrajGAEB200)
     return True
 
 

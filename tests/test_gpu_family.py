@@ -1,0 +1,192 @@
+"""GPU parity tests of the rest of the GAE family and the chunk reshapes, all through the C-ABI:
+  srl_gae_trace   vs the unmodified modules.gae_trace (tests/golden/gae_general.npz) and vs srl_gae_scan -- bit-exact
+  srl_traj_gae    vs the unmodified TrajGAE.process (tests/golden/traj_gae.npz) and the reference's own KAT -- bit-exact
+  to_chunk / back_to_trajectory (K1 launches) vs torch.cat(torch.split) and the reference's KAT -- bit-exact
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_math as M
+from srl_b200 import synth
+from tests.test_oracle import GENERAL_FIXTURES, TRAJ_FIXTURES, split_episodes
+from tests.util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; there is no CPU fallback to test instead")
+    from srl_b200 import ops as _ops
+    _ops._lib.load_library()
+    return _ops
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+# ---- srl_gae_trace ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", GENERAL_FIXTURES)
+def test_gae_trace_matches_reference_fixture(ops, name):
+    fx = load_golden("gae_general.npz")
+    g = lambda k: fx[f"{name}.{k}"]
+    as_arg = lambda x: float(x) if x.ndim == 0 else dev(x)
+    vt = f"{name}.imp_ratio" in fx
+    adv = ops.gae_trace(dev(g("reward")), dev(g("value")), dev(g("truncated")), dev(g("done")), dev(g("on_reset")),
+                        as_arg(g("gamma")), as_arg(g("lmbda")), vtrace=vt, imp_ratio=dev(g("imp_ratio")) if vt else None,
+                        rho=1.0, c=0.9)
+    torch.cuda.synchronize()
+    assert adv.shape == g("adv").shape
+    assert np.array_equal(adv.cpu().numpy(), g("adv"))
+
+
+@pytest.mark.parametrize("cfg_name,B", [("cfg1_atari_cpu", None), ("cfg3_smac_27m", 24), ("cfg2_atari_large", 320)])
+def test_gae_trace_equals_gae_scan(ops, cfg_name, B):
+    """With a scalar critic and scalar discounts both entry points run the same arithmetic: identical bits, including
+    the zero padding row and the value target."""
+    import dataclasses
+    cfg = synth.CONFIGS[cfg_name]
+    if B is not None:
+        cfg = dataclasses.replace(cfg, B=B)
+    s = synth.make_sample_scalars(cfg, 4)
+    d = {k: dev(v) for k, v in s.items()}
+    adv1, ret1, _ = ops.gae_scan(d["reward"], d["value"], d["done"], d["truncated"], d["on_reset"], cfg.gamma, cfg.lmbda)
+    adv2, ret2 = ops.gae_trace(d["reward"], d["value"], d["truncated"], d["done"], d["on_reset"], cfg.gamma, cfg.lmbda,
+                               apply_done=True, want_ret=True, pad_last_row=True)
+    torch.cuda.synchronize()
+    assert torch.equal(adv1, adv2) and torch.equal(ret1, ret2)
+
+
+def test_gae_trace_vector_critic_is_per_column_scalar_scan(ops):
+    """critic_dim = 5 at a size that spans many CTAs: column k of the vector result == the scalar scan of column k
+    (the flags broadcast over the critic axis, gae.py:26-30); the oracle checks one column end to end."""
+    T, B, Nc = 47, 333, 5
+    cfg = synth.PathConfig("vc", T=T, B=B, p_end=0.05)
+    s = synth.make_sample_scalars(cfg, 9)
+    g = torch.Generator().manual_seed(1)
+    reward = torch.randn(T + 1, B, Nc, generator=g)
+    value = torch.randn(T + 1, B, Nc, generator=g)
+    fl = {k: dev(s[k]) for k in ("done", "truncated", "on_reset")}
+    adv, ret = ops.gae_trace(reward.cuda(), value.cuda(), fl["truncated"], fl["done"], fl["on_reset"], 0.99, 0.95,
+                             apply_done=True, want_ret=True)
+    for k in (0, 3, 4):
+        a1, r1 = ops.gae_trace(reward[..., k:k + 1].contiguous().cuda(), value[..., k:k + 1].contiguous().cuda(),
+                               fl["truncated"], fl["done"], fl["on_reset"], 0.99, 0.95, apply_done=True, want_ret=True)
+        assert torch.equal(adv[..., k:k + 1], a1) and torch.equal(ret[..., k:k + 1], r1)
+    f32 = {k: torch.from_numpy(s[k]).float() for k in ("done", "truncated", "on_reset")}
+    ra, rr = M.adv_and_value_target_ref(reward[..., 2:3], value[..., 2:3], f32["truncated"], f32["done"], f32["on_reset"],
+                                        0.99, 0.95)
+    assert torch.equal(adv[..., 2:3].cpu(), ra) and torch.equal(ret[..., 2:3].cpu(), rr)
+
+
+def test_gae_trace_rejects_bad_arguments(ops):
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device="cuda")
+    u = lambda *s: z(*s, dt=torch.uint8)
+    with pytest.raises(AssertionError):  # gae.py:52: gamma must be a float or a FloatTensor
+        ops.gae_trace(z(4, 3, 1), z(5, 3, 1), u(5, 3, 1), u(5, 3, 1), u(5, 3, 1), 1, 0.9)
+    with pytest.raises(AssertionError):  # gae.py:53: gamma tensor shaped like on_reset[:-1]
+        ops.gae_trace(z(4, 3, 1), z(5, 3, 1), u(5, 3, 1), u(5, 3, 1), u(5, 3, 1), z(5, 3, 1), 0.9)
+    with pytest.raises(ValueError):
+        ops.gae_trace(z(4, 3, 1).cpu(), z(5, 3, 1), u(5, 3, 1), u(5, 3, 1), u(5, 3, 1), 0.9, 0.9)
+    with pytest.raises(ValueError):
+        ops.gae_trace(z(4, 3, 1), z(5, 3, 1), u(5, 3, 1), u(5, 3, 1), u(5, 3, 1), 0.9, 0.9, vtrace=True)
+
+
+# ---- srl_traj_gae ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", TRAJ_FIXTURES)
+def test_traj_gae_matches_reference_fixture(ops, name):
+    """All episodes of a fixture in ONE launch; bit-exact in the arrays' own dtype."""
+    fx = load_golden("traj_gae.npz")
+    lens = fx[f"{name}.lens"]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    adv, ret = ops.traj_gae(dev(fx[f"{name}.reward"]), dev(fx[f"{name}.value"]), dev(offsets),
+                            dev(fx[f"{name}.final_truncated"]), dev(fx[f"{name}.final_has_value"]),
+                            float(fx[f"{name}.gamma"]), float(fx[f"{name}.lmbda"]))
+    torch.cuda.synchronize()
+    adv, ret = adv.cpu().numpy(), ret.cpu().numpy()
+    assert adv.dtype == fx[f"{name}.adv"].dtype
+    for k, _, _, ref_adv, ref_ret in split_episodes(fx, name):
+        lo, n = offsets[k], lens[k]
+        assert np.array_equal(adv[lo:lo + n - 1], ref_adv) and np.array_equal(ret[lo:lo + n - 1], ref_ret), f"episode {k}"
+        assert not adv[lo + n - 1].any() and not ret[lo + n - 1].any()  # final step untouched
+
+
+def _memory(rew, value, done, truncated, final_value=True):
+    from srl_b200.api import AnalyzedResult, SampleBatch
+    n = len(rew)
+    return [SampleBatch(obs=None, reward=np.array([r]),
+                        analyzed_result=AnalyzedResult(value=np.array([v])) if (final_value or i < n - 1) else None,
+                        done=np.array([d]), truncated=np.array([t]))
+            for i, (r, v, d, t) in enumerate(zip(rew, value, done, truncated))]
+
+
+def test_traj_gae_postprocessor_reference_known_answers(ops):
+    """legacy/tests/modules_test.py:140-178 through the registered post-processor (int64 arrays -> float64)."""
+    from srl_b200 import api, postprocess  # noqa: F401  (registers 'gae_b200')
+    proc = api.make_traj_postprocessor(type("Cfg", (), dict(type_="gae_b200", args=dict(gamma=0.1, lmbda=0.1)))())
+    memory = proc.process(_memory([1, 2, 0], [2, 0, 1], [0, 0, 0], [0, 0, 1]))
+    for a, b in zip([m.analyzed_result.adv.item() for m in memory[:-1]], [2.1 * 0.01 - 1, 2.1]):
+        assert a == pytest.approx(b, abs=1e-7)
+    memory = proc.process(_memory([1, 3, 0], [2, 2, 0], [0, 0, 1], [0, 0, 0]))
+    for a, b in zip([m.analyzed_result.adv.item() for m in memory[:-1]], [-0.8 + 0.01, 1]):
+        assert a == pytest.approx(b, abs=1e-7)
+    assert memory[-1].analyzed_result.adv is None  # the final step is not written (gae.py:113)
+    with pytest.raises(AssertionError):  # gae.py:110: the last step must end the episode
+        proc.process(_memory([1, 2], [1, 1], [0, 0], [0, 0]))
+
+
+def test_traj_gae_postprocessor_many_episodes_vs_oracle(ops):
+    """process_many: 200 float32 episodes of ragged lengths (width 2) in one launch vs the numpy restatement."""
+    from srl_b200.api import AnalyzedResult, SampleBatch
+    from srl_b200.postprocess import TrajGAEB200
+    rng = np.random.default_rng(0)
+    memories, refs = [], []
+    for k in range(200):
+        n = int(rng.integers(1, 60))
+        reward = rng.standard_normal((n, 2, 1)).astype(np.float32)
+        value = rng.standard_normal((n, 2, 1)).astype(np.float32)
+        trunc = np.full((2, 1), k % 2, np.uint8)
+        has = k % 5 != 0
+        memories.append([SampleBatch(obs=None, reward=reward[i], done=1 - trunc, truncated=trunc,
+                                     analyzed_result=None if (i == n - 1 and not has) else AnalyzedResult(value=value[i]))
+                         for i in range(n)])
+        refs.append(M.traj_gae_process_ref(reward, value, trunc, has, 0.99, 0.95))
+    out = TrajGAEB200(0.99, 0.95).process_many(memories)
+    for memory, (ra, rr) in zip(out, refs):
+        for i in range(len(memory) - 1):
+            ar = memory[i].analyzed_result
+            assert ar.adv.dtype == np.float32 and ar.adv.shape == (2, 1)
+            assert np.array_equal(ar.adv, ra[i]) and np.array_equal(ar.ret, rr[i])
+
+
+# ---- to_chunk / back_to_trajectory -------------------------------------------------------------------------------
+def test_to_chunk_reference_known_answer(ops):
+    """legacy/tests/modules_test.py:79-89."""
+    x = torch.randn(24, 8, 1)
+    x_ = ops.to_chunk(x.cuda(), 8)
+    assert torch.equal(x_.cpu(), x.view(8, 3, 8, 1).transpose(0, 1).reshape(3, 64, 1))
+    assert torch.equal(ops.back_to_trajectory(x_, 8).cpu(), x)
+
+
+@pytest.mark.parametrize("shape,C,dtype", [((24, 8, 1), 8, torch.float32), ((128, 96, 1), 16, torch.uint8),
+                                             ((40, 33, 7), 5, torch.float32), ((16, 64, 4, 84, 84), 4, torch.uint8),
+                                             ((6, 3), 1, torch.float64), ((12, 5, 3), 12, torch.int32)])
+def test_to_chunk_bit_exact(ops, shape, C, dtype):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randint(0, 255, shape, generator=g).to(dtype)
+    ref = torch.cat(torch.split(x, shape[0] // C, dim=0), dim=1)  # utils.py:180
+    got = ops.to_chunk(x.cuda(), C)
+    assert got.shape == ref.shape and torch.equal(got.cpu(), ref)
+    back = ops.back_to_trajectory(got, C)
+    assert torch.equal(back.cpu(), torch.cat(torch.split(ref, ref.shape[1] // C, dim=1), dim=0))  # utils.py:195
+    assert torch.equal(back.cpu(), x)
+
+
+def test_to_chunk_rejects_indivisible_time_axis(ops):
+    with pytest.raises(IndexError):  # utils.py:176-179
+        ops.to_chunk(torch.zeros(10, 4, 1, device="cuda"), 3)
+    with pytest.raises(ValueError):
+        ops.to_chunk(torch.zeros(10, 4, 1), 2)

@@ -318,3 +318,70 @@ def test_n_step_return_known_answers_and_fixture():
                                   torch.from_numpy(d[f"{name}.nex_value"]), torch.from_numpy(d[f"{name}.nex_done"]).float(),
                                   torch.from_numpy(d[f"{name}.nex_truncated"]).float(), float(d[f"{name}.gamma"]))
         assert np.array_equal(got.numpy(), d[f"{name}.ret"]), name
+
+
+# ---- GAE family: TrajGAE and the general gae_trace surface ------------------------------------------------
+TRAJ_FIXTURES = ["f32w1", "f32w3", "f64w2"]
+GENERAL_FIXTURES = ["nc3", "gam", "lam", "both_nc2", "all", "vt_nc1"]
+
+
+def split_episodes(fx, name):
+    lens = fx[f"{name}.lens"]
+    lo = np.concatenate([[0], np.cumsum(lens)])
+    alo = np.concatenate([[0], np.cumsum(np.maximum(lens - 1, 0))])
+    for k, n in enumerate(lens):
+        yield (k, fx[f"{name}.reward"][lo[k]:lo[k + 1]], fx[f"{name}.value"][lo[k]:lo[k + 1]],
+               fx[f"{name}.adv"][alo[k]:alo[k + 1]], fx[f"{name}.ret"][alo[k]:alo[k + 1]])
+
+
+@pytest.mark.parametrize("name", TRAJ_FIXTURES)
+def test_traj_gae_restatement_matches_reference_fixture(name):
+    """Bit-exact against what the unmodified TrajGAE.process wrote (gae.py:100-139), in the arrays' own dtype."""
+    fx = load_golden("traj_gae.npz")
+    for k, reward, value, adv, ret in split_episodes(fx, name):
+        a, r = M.traj_gae_process_ref(reward, value, fx[f"{name}.final_truncated"][k], bool(fx[f"{name}.final_has_value"][k]),
+                                      float(fx[f"{name}.gamma"]), float(fx[f"{name}.lmbda"]))
+        assert a.dtype == adv.dtype
+        assert np.array_equal(a, adv) and np.array_equal(r, ret), f"episode {k}"
+
+
+def test_traj_gae_restatement_known_answer_integer_arrays():
+    """legacy/tests/modules_test.py:140-178 with the test's own int64 arrays (numpy promotes to float64)."""
+    a, _ = M.traj_gae_process_ref(np.array([[1], [2], [0]]), np.array([[2], [0], [1]]), np.array([1]), True, 0.1, 0.1)
+    np.testing.assert_allclose(a[:, 0], [2.1 * 0.01 - 1, 2.1])
+    a, _ = M.traj_gae_process_ref(np.array([[1], [3], [0]]), np.array([[2], [2], [0]]), np.array([0]), True, 0.1, 0.1)
+    np.testing.assert_allclose(a[:, 0], [-0.8 + 0.01, 1])
+
+
+@pytest.mark.parametrize("name", GENERAL_FIXTURES)
+def test_gae_trace_restatement_vector_critic_and_tensor_discounts(name):
+    """gae_trace_ref against the unmodified gae_trace on vector critics / per-element gamma, lambda / importance ratio."""
+    fx = load_golden("gae_general.npz")
+    g = lambda k: fx[f"{name}.{k}"]
+    as_arg = lambda x: float(x) if x.ndim == 0 else torch.from_numpy(x)
+    vt = f"{name}.imp_ratio" in fx
+    got = M.gae_trace_ref(torch.from_numpy(g("reward")), torch.from_numpy(g("value")), torch.from_numpy(g("truncated")).float(),
+                          torch.from_numpy(g("done")).float(), torch.from_numpy(g("on_reset")).float(), as_arg(g("gamma")),
+                          as_arg(g("lmbda")), vtrace=vt, imp_ratio=torch.from_numpy(g("imp_ratio")) if vt else None, rho=1.0,
+                          c=0.9)
+    assert np.array_equal(got.numpy(), g("adv"))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="live reference only in the build container")
+def test_traj_gae_restatement_vs_live_reference():
+    R = ref_loader.load()
+    rng = np.random.default_rng(3)
+    for trial in range(6):
+        n, W = int(rng.integers(2, 30)), int(rng.integers(1, 4))
+        reward = rng.standard_normal((n, W)).astype(np.float32)
+        value = rng.standard_normal((n, W)).astype(np.float32)
+        trunc = np.full((W,), trial % 2, np.uint8)
+        has = trial % 3 != 0
+        memory = [R.trainer.SampleBatch(obs=None, reward=reward[i].copy(), done=1 - trunc, truncated=trunc,
+                                        analyzed_result=None if (i == n - 1 and not has) else
+                                        R.namedarray.NamedArray(value=value[i].copy(), adv=None, ret=None))
+                  for i in range(n)]
+        memory = R.gae.TrajGAE(0.98, 0.9).process(memory)
+        a, r = M.traj_gae_process_ref(reward, value, trunc, has, 0.98, 0.9)
+        assert np.array_equal(a, np.stack([m.analyzed_result.adv for m in memory[:-1]]))
+        assert np.array_equal(r, np.stack([m.analyzed_result.ret for m in memory[:-1]]))
