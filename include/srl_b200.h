@@ -39,6 +39,14 @@ enum srl_status {
 /* Thread-local, NUL-terminated description of the last non-OK status returned on this thread. */
 const char* srl_last_error(void);
 int srl_abi_version(void);
+/* Programmatic dependent launch between the kernels of a step (default on; SRL_PDL=0 in the environment or
+ * srl_set_pdl(0) turns it off; srl_set_pdl returns the previous setting).  On: srl_gae_scan and the loss kernels are
+ * launched with cudaLaunchAttributeProgrammaticStreamSerialization, so that on ONE stream the order
+ * srl_philox_perm -> srl_gae_scan -> srl_ppo_loss_* overlaps: the scan starts beside the permutation kernel, and the loss
+ * kernel's CTAs become resident and pull their policy-side rows into L2 while the scan still runs; each kernel waits
+ * (griddepcontrol.wait) before it touches anything an earlier kernel writes, so results do not change. */
+int srl_pdl_enabled(void);
+int srl_set_pdl(int on);
 /* Fills SM count and compute capability of the current device. */
 int srl_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

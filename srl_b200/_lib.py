@@ -73,6 +73,8 @@ class LeafDesc(ctypes.Structure):
 SIGNATURES = {
     "srl_last_error": (c_char_p, []),
     "srl_abi_version": (c_int, []),
+    "srl_pdl_enabled": (c_int, []),
+    "srl_set_pdl": (c_int, [c_int]),
     "srl_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "srl_gae_scan": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double] +
                      [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -1,6 +1,9 @@
 // Library-level plumbing: status/error text, device queries.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <atomic>
 
 #include "common.cuh"
 
@@ -14,6 +17,20 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+namespace {
+std::atomic<int> g_pdl{-1};  // -1: not decided yet (SRL_PDL in the environment, default on)
+}
+
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("SRL_PDL");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
 }
 
 int sm_count() {
@@ -32,6 +49,14 @@ int sm_count() {
 extern "C" const char* srl_last_error(void) { return srl::g_err; }
 
 extern "C" int srl_abi_version(void) { return SRL_B200_ABI_VERSION; }
+
+extern "C" int srl_pdl_enabled(void) { return srl::pdl_enabled() ? 1 : 0; }
+
+extern "C" int srl_set_pdl(int on) {
+  const int before = srl::pdl_enabled() ? 1 : 0;
+  srl::g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
+  return before;
+}
 
 extern "C" int srl_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   using namespace srl;

@@ -30,6 +30,12 @@ void set_error(const char* fmt, ...);
 
 int sm_count();  // cached per device
 
+// Programmatic dependent launch (srl_set_pdl / SRL_PDL, api.cu): a kernel launched with launch_pdl() may become
+// resident while the kernel before it on the stream still runs -- once every CTA of that kernel has executed
+// pdl_launch_dependents() (or exited) -- and must execute pdl_wait() before it touches anything the earlier kernel
+// writes.  Off: plain launches (the device-side instructions are no-ops then).
+bool pdl_enabled();
+
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 // ---- device helpers ------------------------------------------------------------------------
@@ -47,6 +53,27 @@ __device__ __forceinline__ int4 ldg_stream(const int4* p) { return __ldcs(p); }
 __device__ __forceinline__ void stg_stream(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void stg_stream(float4* p, float4 v) { __stcs(p, v); }
 __device__ __forceinline__ void stg_stream(int4* p, int4 v) { __stcs(p, v); }
+
+// griddepcontrol.wait returns once every prerequisite grid has COMPLETED and its memory is visible (immediately when the
+// kernel was launched without the programmatic attribute).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

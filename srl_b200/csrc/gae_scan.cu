@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(kThreads, 4) gae_scan_kernel(const GaeParams p
   uint8_t* __restrict__ sf = reinterpret_cast<uint8_t*>(svr + (PACK ? cells : 0));  // [L][LW] done|trunc|reset bits
 
   const int tid = threadIdx.x;
+  pdl_launch_dependents();  // see gae_scan_ws.cu: the loss kernel behind this one may become resident
   const int lane = tid % LW;
   const int trow = tid / LW;
   const int col = blockIdx.x * LW + lane;
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(kThreads, 4) gae_scan_kernel(const GaeParams p
       }
     }
   }
+  if (tid == 0) pdl_wait();  // scan complete => permutation kernel complete (see gae_scan_ws.cu)
 #ifdef SRL_DEBUG_PHASES
   SRL_STAMP(5);
   if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1))
@@ -255,8 +257,7 @@ int launch_un(const GaeParams& p, cudaStream_t st) {
     opted_in[dev] = true;
   }
   const int grid = (p.N + LW - 1) / LW;
-  kern<<<grid, kThreads, smem, st>>>(p);
-  SRL_CUDA(cudaGetLastError());
+  SRL_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, st, p));
   return SRL_OK;
 }
 

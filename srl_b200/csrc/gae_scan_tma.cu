@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(LPW) gae_scan_tma_kernel(const __grid_constant
   const bool live = SPEC ? true : col < p.N;
   const int L = p.L, N = p.N;
   const int n_stages = (L + kRows - 1) / kRows;  // stage k covers rows [k*kRows, (k+1)*kRows); rows >= L read as 0
+  pdl_launch_dependents();  // see gae_scan_ws.cu: the loss kernel behind this one may become resident
 
   if (lane == 0) {
     const CUtensorMap* maps[] = {&q.maps.value, &q.maps.reward, &q.maps.done, &q.maps.truncated, &q.maps.on_reset};
@@ -298,6 +299,7 @@ __global__ void __launch_bounds__(LPW) gae_scan_tma_kernel(const __grid_constant
     o[static_cast<size_t>(6) * N] = static_cast<double>(st.tr);
     o[static_cast<size_t>(7) * N] = 0.0;
   }
+  if (lane == 0) pdl_wait();  // scan complete => permutation kernel complete (see gae_scan_ws.cu)
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -347,8 +349,7 @@ int launch(const GaeTmaParams& q, cudaStream_t st) {
     opted_in[dev] = true;
   }
   const int grid = (q.p.N + LPW - 1) / LPW;
-  kern<<<grid, LPW, smem, st>>>(q);
-  SRL_CUDA(cudaGetLastError());
+  SRL_CUDA(launch_pdl(kern, dim3(grid), dim3(LPW), smem, st, q));
   return SRL_OK;
 }
 

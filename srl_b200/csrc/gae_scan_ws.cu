@@ -13,6 +13,8 @@
 // of ~200.  The extra row of every box (row t+16) gives each chunk its own copy of the next-row inputs: no state crosses
 // chunks except the scanner's A.  Per-cell arithmetic is the TMA kernel's, operation for operation (bit-identical).
 // V-trace is not handled here (the other two kernels do).
+#include <stdlib.h>
+
 #include "gae_common.cuh"
 #include "tma_util.cuh"
 
@@ -22,7 +24,11 @@ namespace {
 using namespace srl::tma;
 
 constexpr int kR = 16;  // rows per chunk
-constexpr int kS = 3;   // ring depth
+// Ring depth kS (template parameter): 3 slots when several CTAs share an SM; kDeep when the batch has at most one CTA per
+// SM anyway (cfg2: 128 lane groups) -- the whole trajectory of up to kDeep * kR rows is requested from HBM at once (one
+// exposed DRAM round trip instead of one per ring turn), and the workers run the delta pass of all resident chunks ahead
+// of the scanner.
+constexpr int kDeep = 9;
 // W = worker warps per CTA (kR / W rows of every chunk each).  The kernel serves batches with fewer CTAs than the SMs can
 // hold (cfg2: 128 lane groups), where a CTA's time per chunk is the latency of one worker's rows: W = 16, one row per
 // worker warp.  (W = 4 was measured on mid-size batches -- cfg3: 38 us, 129 warp instructions per row-lane, issue slots
@@ -53,17 +59,23 @@ struct Slot {
   static_assert(bytes % 128 == 0, "slots stay 128-byte aligned");
 };
 
+template <int kS>
 struct Bars {
   uint64_t tma_full[kS], pass1[kS], scanned[kS], empty[kS];
 };
 
-template <bool PACK, int kW>
+template <bool PACK, int kW, int kS>
 __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid_constant__ WsParams q) {
   constexpr int kRowsPerWorker = kR / kW;
+  constexpr int kAhead = kS > 3 ? kS - 1 : 1;  // chunks the workers' delta pass runs ahead of their store pass
+  constexpr int kStatsOff = (sizeof(Bars<kS>) + 255) / 256 * 256;
   constexpr int kThreads = 32 * (2 + kW);
   using SL = Slot<PACK>;
   extern __shared__ __align__(128) unsigned char smem[];
-  Bars* bars = reinterpret_cast<Bars*>(smem + kS * SL::bytes);
+  Bars<kS>* bars = reinterpret_cast<Bars<kS>*>(smem + kS * SL::bytes);
+  // the kernel behind this one on the stream (the loss) may become resident now; it waits for this grid's completion
+  // before it reads anything written here
+  pdl_launch_dependents();
   const GaeParams& p = q.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col0 = blockIdx.x * 32, col = col0 + lane;
@@ -228,14 +240,14 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
       if (lane == 0) mbar_arrive(&bars->empty[s]);
     };
 
-    pass1(0);
+    for (int c = 0; c < kAhead && c < n_chunks; ++c) pass1(c);
     for (int c = 0; c < n_chunks; ++c) {
-      if (c + 1 < n_chunks) pass1(c + 1);  // stay one chunk ahead of the scanner
+      if (c + kAhead < n_chunks) pass1(c + kAhead);  // stay ahead of the scanner
       pass3(c);
     }
     // per-lane statistics of this worker -> shared memory; the workers' tables are added in worker order below (fixed)
     if (p.lane_part != nullptr) {
-      double* red = reinterpret_cast<double*>(smem + kS * SL::bytes + 256) + (w * 7) * 32;  // [kW][7][32] f64, own region
+      double* red = reinterpret_cast<double*>(smem + kS * SL::bytes + kStatsOff) + (w * 7) * 32;  // [kW][7][32] f64, own region
       red[0 * 32 + lane] = static_cast<double>(cnt);
       red[1 * 32 + lane] = s1;
       red[2 * 32 + lane] = s2;
@@ -247,7 +259,7 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
   }
   __syncthreads();
   if (p.lane_part != nullptr) {
-    const double* red = reinterpret_cast<const double*>(smem + kS * SL::bytes + 256);
+    const double* red = reinterpret_cast<const double*>(smem + kS * SL::bytes + kStatsOff);
     for (int o = threadIdx.x; o < SRL_LANE_PART * 32; o += kThreads) {
       const int k = o >> 5, ln = o & 31;
       const int c2 = col0 + ln;
@@ -259,12 +271,17 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
       }
     }
   }
+  // Launched programmatically behind the permutation kernel, this grid never waited for it (it does not read the
+  // permutation).  Waiting here, before the grid completes, makes "scan complete" imply "permutation complete and
+  // visible" for the loss kernel, whose own griddepcontrol.wait only covers this grid.
+  if (threadIdx.x == 0) pdl_wait();
 }
 
-template <bool PACK, int kW>
+template <bool PACK, int kW, int kS>
 int launch_ws(const WsParams& q, cudaStream_t st) {
-  const size_t smem = static_cast<size_t>(kS) * Slot<PACK>::bytes + 256 + static_cast<size_t>(kW) * 7 * 32 * sizeof(double);
-  auto kern = gae_scan_ws_kernel<PACK, kW>;
+  const size_t smem = static_cast<size_t>(kS) * Slot<PACK>::bytes + (sizeof(Bars<kS>) + 255) / 256 * 256 +
+                      static_cast<size_t>(kW) * 7 * 32 * sizeof(double);
+  auto kern = gae_scan_ws_kernel<PACK, kW, kS>;
   static bool opted_in[64] = {};
   int dev = 0;
   SRL_CUDA(cudaGetDevice(&dev));
@@ -273,8 +290,7 @@ int launch_ws(const WsParams& q, cudaStream_t st) {
     opted_in[dev] = true;
   }
   const int grid = (q.p.N + 31) / 32;
-  kern<<<grid, 32 * (2 + kW), smem, st>>>(q);
-  SRL_CUDA(cudaGetLastError());
+  SRL_CUDA(launch_pdl(kern, dim3(grid), dim3(32 * (2 + kW)), smem, st, q));
   return SRL_OK;
 }
 
@@ -294,6 +310,13 @@ int launch_gae_ws(const GaeParams& p, cudaStream_t st) {
   WsParams q;
   q.p = p;
   int rc;
+  // at most one CTA per SM anyway: spend the SM's shared memory on a ring that holds the whole trajectory
+  // (SRL_GAE_WS_DEEP=0: the 3-slot ring, a tuning knob for profiles/)
+  static const bool deep_ok = [] {
+    const char* e = getenv("SRL_GAE_WS_DEEP");
+    return e == nullptr || e[0] != '0';
+  }();
+  const bool deep = deep_ok && (p.N + 31) / 32 <= sm_count();
   if ((rc = tma::make_map(&q.maps.value, p.value, p.L, p.N, 4, 32, kR + 1)) != SRL_OK) return rc;
   if ((rc = tma::make_map(&q.maps.reward, p.reward, p.L, p.N, 4, 32, kR)) != SRL_OK) return rc;
   if ((rc = tma::make_map(&q.maps.done, p.done, p.L, p.N, 1, 32, kR + 1)) != SRL_OK) return rc;
@@ -301,9 +324,9 @@ int launch_gae_ws(const GaeParams& p, cudaStream_t st) {
   if ((rc = tma::make_map(&q.maps.on_reset, p.on_reset, p.L, p.N, 1, 32, kR + 1)) != SRL_OK) return rc;
   if (p.pack != nullptr) {
     if ((rc = tma::make_map(&q.maps.old_logp, p.old_logp, p.L, p.N, 4, 32, kR)) != SRL_OK) return rc;
-    return launch_ws<true, 16>(q, st);
+    return deep ? launch_ws<true, 16, kDeep>(q, st) : launch_ws<true, 16, 3>(q, st);
   }
-  return launch_ws<false, 16>(q, st);
+  return deep ? launch_ws<false, 16, kDeep>(q, st) : launch_ws<false, 16, 3>(q, st);
 }
 
 }  // namespace srl

@@ -54,6 +54,7 @@ namespace {
 __global__ void __launch_bounds__(256) philox_perm_kernel(uint32_t seed_lo, uint32_t seed_hi, uint32_t epoch0, int n_env,
                                                          int group, int bits, int32_t* __restrict__ out) {
   __shared__ PermKeys keys;
+  pdl_launch_dependents();  // the scan that follows on the stream does not read the permutation: let it start now
   const uint32_t epoch = epoch0 + blockIdx.y;  // one grid row per epoch
   out += static_cast<size_t>(blockIdx.y) * n_env * group;
   if (threadIdx.x < 2) {  // two Philox blocks -> eight round keys

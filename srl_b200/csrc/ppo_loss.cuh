@@ -453,6 +453,24 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
   Uniforms u;
   bool have_u = false;
 
+  // Launched programmatically behind the scan (common.cuh), this CTA may be resident while the scan still runs.  The
+  // policy-side rows do not depend on it: ask for this CTA's share (three tensors x its rows, one request per 128-byte
+  // line) to be brought into L2 under the scan, then wait for the scan's results.
+  if constexpr (LANES == 4) {
+    if ((threadIdx.x & 7) == 0) {
+      const int j = (blockIdx.x * blockDim.x + threadIdx.x) * LANES;
+      if (j < n) {
+        long long o = static_cast<long long>(r0) * s.ld_pol + j;
+        for (int t = r0; t < r1; ++t, o += s.ld_pol) {
+          prefetch_l2(pr.new_logp + o);
+          prefetch_l2(pr.v_pred + o);
+          prefetch_l2(pr.entropy + o);
+        }
+      }
+    }
+  }
+  pdl_wait();
+
   // normally one column tile per CTA (gridDim.x == col_tiles); only batches wider than kMaxGrid tiles loop here
   for (int ct = blockIdx.x; ct < s.col_tiles; ct += gridDim.x) {
   const int j = (ct * blockDim.x + threadIdx.x) * LANES;
@@ -703,8 +721,7 @@ struct LossLauncher {
     s.rows_per_tile = rows;
     s.n_tiles = static_cast<int>(groups);
     const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(groups), static_cast<unsigned>(n_problems));
-    ppo_loss_kernel<LANES, MODE, CFG><<<grid, threads, PIPE ? loss_smem_bytes(threads) : 0, st>>>(b);
-    SRL_CUDA(cudaGetLastError());
+    SRL_CUDA(launch_pdl(ppo_loss_kernel<LANES, MODE, CFG>, grid, dim3(threads), PIPE ? loss_smem_bytes(threads) : 0, st, b));
     return SRL_OK;
   }
 };

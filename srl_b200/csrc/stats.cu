@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(kThreads) group_stats_kernel(const double* __r
                                                                const int32_t* __restrict__ idx, int per_group,
                                                                int whole_first, double* __restrict__ out, GroupWs ws,
                                                                const FusedXchg fx) {
+  pdl_launch_dependents();  // a loss kernel launched behind this one may become resident (it waits before reading)
   // output row blockIdx.y; with whole_first, row 0 is the identity group over all N lanes
   const bool whole = whole_first && blockIdx.y == 0;
   const int g = static_cast<int>(blockIdx.y) - (whole_first ? 1 : 0);
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(256) lane_stats_kernel(const float* __restrict
 
 __global__ void popart_update_kernel(const double* __restrict__ bs, double* __restrict__ state, double beta,
                                      double eps, double* __restrict__ ms) {
+  pdl_launch_dependents();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double mean = state[0], mean_sq = state[1], debias = state[2];
   // statistics before the update (PopArtValueHead.update reads them for the head rescale, popart.py:43)

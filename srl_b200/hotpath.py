@@ -191,7 +191,14 @@ class HotPath:
         when distributed)."""
         lf = self.leaf
         main = torch.cuda.current_stream()
-        if self.minibatches > 1 and permute:  # the permutations do not depend on the scan: parallel branch
+        # The permutations do not depend on the scan.  With programmatic dependent launch the order K5a -> K2 -> K4 on
+        # ONE stream already overlaps (K2 is launched beside K5a and only joins it when it ends; K4 becomes resident under
+        # K2): no fork / join, three nodes in a line in the step graph.  Without it: a parallel branch.
+        inline_perm = self.minibatches > 1 and permute and ops.pdl_enabled() and not cached
+        fork_perm = self.minibatches > 1 and permute and not inline_perm
+        if inline_perm:
+            self.permute()
+        if fork_perm:
             self._perm_stream.wait_stream(main)
             with torch.cuda.stream(self._perm_stream):
                 self.permute()
@@ -209,7 +216,7 @@ class HotPath:
             ops.gae_scan(lf["reward"], lf["value"], lf["done"], lf["truncated"], lf["on_reset"], self.gamma, self.lmbda,
                          row_lo=self.row_lo, row_hi=self.row_hi, popart_mean_std=self.popart_mean_std(), adv=self.adv,
                          ret=self.ret, lane_part=self.lane_part, **kw)
-        if self.minibatches > 1 and permute:
+        if fork_perm:
             main.wait_stream(self._perm_stream)
         side = self.fuse_stats and not cached
         if side:  # off the critical path: joined by _join_stats() after the loss launches

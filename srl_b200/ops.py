@@ -52,6 +52,16 @@ def _rows_lanes(t: torch.Tensor) -> Tuple[int, int]:
     return t.shape[0], t[0].numel()
 
 
+def pdl_enabled() -> bool:
+    """Programmatic dependent launch between perm -> scan -> loss on one stream (include/srl_b200.h: srl_set_pdl)."""
+    return bool(_lib.load_library().srl_pdl_enabled())
+
+
+def set_pdl(on: bool) -> bool:
+    """Switches programmatic dependent launch for later launches; returns the previous setting."""
+    return bool(_lib.load_library().srl_set_pdl(int(bool(on))))
+
+
 # ------------------------------------------------------------------------------------------------
 # K2
 # ------------------------------------------------------------------------------------------------
