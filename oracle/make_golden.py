@@ -298,6 +298,35 @@ def gen_gae_general(R):
     return sorted({k.split(".")[0] for k in out})
 
 
+def gen_wire(R):
+    """base.namedarray.dumps of the unmodified reference for the methods that need no third-party codec
+    ('raw_bytes', 'pickle_dict'; blosc is not installed) on a nested sample with a None leaf, a bool leaf and metadata.
+    Stored as one uint8 stream + frame lengths per method, plus the leaves for comparison."""
+    NA = R.namedarray.NamedArray
+    rng = np.random.Generator(np.random.PCG64(17))
+    L = 5
+    x = R.trainer.SampleBatch(
+        obs=NA(frame=rng.integers(0, 255, (L, 2, 6, 6), dtype=np.uint8), vec=rng.standard_normal((L, 3)).astype(np.float32)),
+        on_reset=(rng.random((L, 1)) < 0.3), done=np.zeros((L, 1), np.uint8), truncated=None,
+        action=NA(x=rng.integers(0, 18, (L, 1)).astype(np.int32)), reward=rng.standard_normal((L, 1)).astype(np.float32),
+        analyzed_result=NA(value=rng.standard_normal((L, 1)).astype(np.float32), log_probs=rng.standard_normal((L, 1)),
+                           adv=None, ret=None),
+        policy_version_steps=np.full((L, 1), 7, np.int64), sampling_weight=2.5)
+    out = {}
+    for method in ("raw_bytes", "pickle_dict"):
+        frames = R.namedarray.dumps(x, method=method)
+        out[f"{method}.stream"] = np.frombuffer(b"".join(frames), dtype=np.uint8)
+        out[f"{method}.lens"] = np.array([len(f) for f in frames], np.int64)
+        back = R.namedarray.loads(frames)
+        assert back.metadata == x.metadata
+    for k, v in R.namedarray.flatten(x):
+        if v is not None:
+            out[f"leaf.{k}"] = v
+    out["none_leaves"] = np.array([k for k, v in R.namedarray.flatten(x) if v is None])
+    np.savez_compressed(os.path.join(GOLDEN, "wire.npz"), **out)
+    return sorted(k for k in out if k.startswith("leaf."))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
@@ -309,6 +338,9 @@ def main():
         print("traj_gae:", gen_traj_gae(R))
         print("gae_general:", gen_gae_general(R))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "wire":
+        print("wire:", gen_wire(R))
+        return
     print("gae:", gen_gae(R))
     print("loss:", gen_loss(R))
     gen_masknorm_popart(R)
@@ -316,6 +348,7 @@ def main():
     print("nstep:", gen_nstep(R))
     print("traj_gae:", gen_traj_gae(R))
     print("gae_general:", gen_gae_general(R))
+    print("wire:", gen_wire(R))
     total = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))
     print(f"wrote {len(os.listdir(GOLDEN))} files, {total / 1024:.0f} KiB")
 

@@ -29,7 +29,7 @@ from typing import Any, Dict, List, Optional, Tuple
 import numpy as np
 import torch
 
-from srl_b200 import ops
+from srl_b200 import ops, wire
 from srl_b200._lib import LeafDesc
 from srl_b200.namedarray import flatten, from_flattened
 
@@ -100,7 +100,7 @@ class DeviceSlabBuffer:
         self._layout: Optional[_Layout] = None
         self._n_slots = max(1, batch_size) * max(1, staging_batches)
         self._free: List[int] = []
-        self._pending: List[Tuple[int, set, Any]] = []  # (slot, names present, metadata source) of the next batch
+        self._pending: List[Tuple[int, set, Any]] = []  # (slot, names present, (leaves, metadata)) of the next batch
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._slot_ready: Dict[int, torch.cuda.Event] = {}
         self._slot_free_after: Dict[int, torch.cuda.Event] = {}
@@ -126,7 +126,25 @@ class DeviceSlabBuffer:
             return False
         x.trainer_worker_recv_timestamp = np.full(shape=x.on_reset.shape, fill_value=int(time.time()),
                                                   dtype=np.int64)  # base/buffer.py:114-116
-        self._stage(x)
+        self._stage(flatten(x), getattr(x, "metadata", None))
+        return self._batch_if_complete()
+
+    def put_frames(self, b) -> bool:
+        """`put(namedarray.loads(b))` for a raw_bytes message (base/namedarray.py:115-128,166-218) without building the
+        sample: every leaf's payload is copied once, from the received bytes into the pinned staging block."""
+        if not self.batch_size:
+            return self.put(wire.loads(b))
+        entries, metadata = wire.frames(b)
+        leaves = [(k, None if dt is None else np.frombuffer(p, dtype=dt).reshape(shape)) for k, dt, shape, p in entries]
+        shape = next(v.shape for k, v in leaves if k == "on_reset")
+        stamp = np.full(shape=shape, fill_value=int(time.time()), dtype=np.int64)  # base/buffer.py:114-116
+        leaves = [(k, stamp if k == "trainer_worker_recv_timestamp" else v) for k, v in leaves]
+        if not any(k == "trainer_worker_recv_timestamp" for k, _ in leaves):
+            leaves = sorted(leaves + [("trainer_worker_recv_timestamp", stamp)], key=lambda kv: kv[0])
+        self._stage(leaves, metadata)
+        return self._batch_if_complete()
+
+    def _batch_if_complete(self) -> bool:
         if len(self._pending) >= self.batch_size:
             data = self._assemble(self._pending[:self.batch_size])
             self._pending = self._pending[self.batch_size:]
@@ -167,12 +185,11 @@ class DeviceSlabBuffer:
         self._slot_ready.clear()
         self._slot_free_after.clear()
         self._pending = []
-        for _, _, old in pending:
-            self._stage(old)
+        for _, _, (old_leaves, old_meta) in pending:
+            self._stage(old_leaves, old_meta)
 
-    def _stage(self, x) -> None:
-        """One sample -> one pinned block -> one async H2D into a device staging slot."""
-        leaves = flatten(x)
+    def _stage(self, leaves, metadata) -> None:
+        """One sample (its flattened leaves) -> one pinned block -> one async H2D into a device staging slot."""
         if self._layout is None:
             self._init_layout(leaves)
         elif any(v is not None and k not in self._layout.spec for k, v in leaves):
@@ -203,7 +220,7 @@ class DeviceSlabBuffer:
             done.record(self._copy_stream)
         self._slot_ready[slot] = done
         self.bytes_staged += lay.bytes
-        self._pending.append((slot, present, x))
+        self._pending.append((slot, present, (leaves, metadata)))
 
     def _assemble(self, items) -> Any:
         """np.stack(axis=1) of the staged samples, every leaf in one srl_batch_gather call."""
@@ -241,7 +258,7 @@ class DeviceSlabBuffer:
             self._slot_free_after[s] = done
             self._free.append(s)
         batch = from_flattened([(k, out[k]) for k in names])
-        meta = getattr(items[0][2], "metadata", None)
+        meta = items[0][2][1]
         if meta is not None and hasattr(batch, "register_metadata"):
             batch.register_metadata(**meta)
         return batch

@@ -153,3 +153,35 @@ def _with_cached(host_batch, dev_batch):
     hb.analyzed_result.adv = dev_batch.analyzed_result.adv.cpu().numpy()
     hb.analyzed_result.ret = dev_batch.analyzed_result.ret.cpu().numpy()
     return hb
+
+
+def test_put_frames_equals_put_of_decoded_sample():
+    """Wire decode straight into the staging block: a batch assembled from raw_bytes messages
+    (base/namedarray.py:115-128) is bit-identical to the batch assembled from the decoded samples, including a leaf that
+    is None in some messages (zero-filled, namedarray.py:588-595) and the metadata of the first sample."""
+    from srl_b200 import wire
+    from srl_b200.buffer import DeviceSlabBuffer
+    rng = np.random.default_rng(5)
+    B = 5
+    samples = [_sample(rng, big=True, with_info=(j % 2 == 0)) for j in range(B)]
+    for s in samples:
+        s.register_metadata(sampling_weight=1.5)
+    a, b = DeviceSlabBuffer(batch_size=B), DeviceSlabBuffer(batch_size=B)
+    formed = [b.put_frames(wire.dumps(s, "raw_bytes")) for s in samples]
+    for s in samples:
+        a.put(copy.deepcopy(s))
+    assert formed == [False] * (B - 1) + [True]
+    xa, xb = a.get().sample, b.get().sample
+    fa, fb = dict(flatten(xa)), dict(flatten(xb))
+    assert sorted(fa) == sorted(fb)
+    for k, v in fa.items():
+        if v is None:
+            assert fb[k] is None, k
+        elif k == "trainer_worker_recv_timestamp":
+            assert fb[k].shape == v.shape and fb[k].dtype == v.dtype
+        else:
+            assert fb[k].dtype == v.dtype and torch.equal(fb[k], v), k
+    assert not fb["info.ret"][:, 1].any() and fb["info.ret"][:, 0].any()  # zero-filled where the message had None
+    assert xb.metadata == dict(sampling_weight=1.5)
+    with pytest.raises(ValueError):  # only raw_bytes messages carry leaf frames
+        b.put_frames(wire.dumps(samples[0], "pickle_dict"))

@@ -1,0 +1,107 @@
+"""CPU tests of the sample wire format (srl_b200/wire.py) against messages the UNMODIFIED reference produced
+(tests/golden/wire.npz, written by oracle/make_golden.py from base.namedarray.dumps, namedarray.py:100-163)."""
+import pickle
+
+import numpy as np
+import pytest
+
+from oracle import ref_loader
+from srl_b200 import wire
+from srl_b200.api import AnalyzedResult, SampleBatch
+from srl_b200.namedarray import NamedArray, flatten
+from tests.util import load_golden
+
+
+def _message(fx, method):
+    stream, lens = fx[f"{method}.stream"].tobytes(), fx[f"{method}.lens"]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    return [stream[off[i]:off[i + 1]] for i in range(len(lens))]
+
+
+def _same_sample(fx):
+    """The fixture's sample rebuilt with this repo's containers."""
+    leaf = lambda k: fx[f"leaf.{k}"]
+    return SampleBatch(obs=NamedArray(frame=leaf("obs.frame"), vec=leaf("obs.vec")), on_reset=leaf("on_reset"),
+                       done=leaf("done"), truncated=None, action=NamedArray(x=leaf("action.x")), reward=leaf("reward"),
+                       analyzed_result=AnalyzedResult(value=leaf("analyzed_result.value"),
+                                                      log_probs=leaf("analyzed_result.log_probs")),
+                       policy_version_steps=leaf("policy_version_steps"), sampling_weight=2.5)
+
+
+def test_raw_bytes_decode_of_reference_message():
+    fx = load_golden("wire.npz")
+    x = wire.loads(_message(fx, "raw_bytes"))
+    got = dict(flatten(x))
+    for k in [k[5:] for k in fx if k.startswith("leaf.")]:
+        ref = fx[f"leaf.{k}"]
+        want_dtype = np.uint8 if ref.dtype == np.bool_ else ref.dtype  # bool travels as uint8 (numpy_utils.py:65-66)
+        assert got[k].dtype == want_dtype and got[k].shape == ref.shape
+        assert np.array_equal(got[k], ref.astype(want_dtype)), k
+    for k in fx["none_leaves"]:
+        assert got[str(k)] is None
+    assert x.metadata == dict(sampling_weight=2.5)
+
+
+def test_raw_bytes_encode_is_byte_identical_to_reference():
+    fx = load_golden("wire.npz")
+    ours = wire.dumps(_same_sample(fx), "raw_bytes")
+    ref = _message(fx, "raw_bytes")
+    assert len(ours) == len(ref)
+    assert ours[:-1] == ref[:-1]  # code + four frames per leaf, in the reference's (sorted) leaf order
+    assert pickle.loads(ours[-1]) == pickle.loads(ref[-1])
+
+
+def test_pickle_dict_decode_of_reference_message():
+    fx = load_golden("wire.npz")
+    x = wire.loads(_message(fx, "pickle_dict"))
+    got = dict(flatten(x))
+    assert np.array_equal(got["obs.frame"], fx["leaf.obs.frame"]) and got["on_reset"].dtype == np.bool_
+    assert got["truncated"] is None and x.metadata == dict(sampling_weight=2.5)
+
+
+@pytest.mark.parametrize("method", ["raw_bytes", "pickle_dict", "pickle"])
+def test_round_trip(method):
+    fx = load_golden("wire.npz")
+    x = _same_sample(fx)
+    y = wire.loads(wire.dumps(x, method))
+    for (ka, va), (kb, vb) in zip(flatten(x), flatten(y)):
+        assert ka == kb and ((va is None and vb is None) or np.array_equal(np.asarray(va).astype(vb.dtype), vb))
+    assert y.metadata == x.metadata
+
+
+def test_frames_are_zero_copy_views_and_checked():
+    fx = load_golden("wire.npz")
+    msg = _message(fx, "raw_bytes")
+    entries, meta = wire.frames(msg)
+    by_key = {k: (dt, shape, p) for k, dt, shape, p in entries}
+    dt, shape, p = by_key["obs.frame"]
+    i = 1 + 4 * [k for k, *_ in entries].index("obs.frame") + 3
+    assert p.obj is msg[i] and p.nbytes == int(np.prod(shape)) * dt.itemsize  # a view of the received bytes
+    bad = list(msg)
+    bad[i] = bad[i][:-1]
+    with pytest.raises(ValueError, match="payload"):
+        wire.frames(bad)
+    with pytest.raises(ValueError, match="multiple of 4"):
+        wire.frames(msg[:3] + msg[4:])
+
+
+def test_compressed_methods_fail_loudly():
+    """blosc is a third-party codec absent here; the reference fails on `import blosc` the same way."""
+    fx = load_golden("wire.npz")
+    for code in (b"0004", b"0005", b"0006", b"0007", b"0008"):
+        with pytest.raises(ModuleNotFoundError):
+            wire.loads([code] + _message(fx, "raw_bytes")[1:])
+    with pytest.raises(ModuleNotFoundError):
+        wire.dumps(_same_sample(fx), "obs_compress")
+    with pytest.raises(NotImplementedError):
+        wire.loads([b"0042", b""])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="live reference only in the build container")
+def test_live_reference_decodes_our_raw_bytes():
+    R = ref_loader.load()
+    fx = load_golden("wire.npz")
+    back = R.namedarray.loads(wire.dumps(_same_sample(fx), "raw_bytes"))
+    got = dict(R.namedarray.flatten(back))
+    assert np.array_equal(got["obs.frame"], fx["leaf.obs.frame"]) and got["truncated"] is None
+    assert np.array_equal(got["analyzed_result.log_probs"], fx["leaf.analyzed_result.log_probs"])
