@@ -321,6 +321,9 @@ def run_ours(args, cfg, rank, world, local_rank):
     # the loss launches exactly as the step issues them (one batched launch, one per epoch with PopArt, or one per
     # minibatch with --no-batch); PopArt's tiny update kernels ride along in the per-epoch case
     loss_launches = (E if cfg.popart else -(-(E * Mb) // 32)) if hp._immediate else E * Mb
+    # stand-alone there is no kernel ahead to overlap with: launched without the programmatic attribute (the loss kernel
+    # then also skips the L2 requests it only issues when it can become resident under the scan)
+    pdl_was = ops.set_pdl(False)
     g_loss = graph_of(lambda: hp._run_losses(pol_dev))
     lf = hp.leaf
     pack_kw = dict(old_logp=lf["old_logp"], pack=hp.pack) if hp.pack is not None else {}
@@ -328,6 +331,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                                           cfg.lmbda, row_lo=hp.row_lo, row_hi=hp.row_hi,
                                           popart_mean_std=hp.popart_mean_std(), adv=hp.adv, ret=hp.ret,
                                           lane_part=hp.lane_part, **pack_kw))
+    ops.set_pdl(pdl_was)
     hp.pg = pg_saved
     loss_ms = statistics.mean(timed_steps(k_reps, g_loss.replay)) / loss_launches
     gae_ms = statistics.mean(timed_steps(k_reps, g_gae.replay))
@@ -386,7 +390,10 @@ def run_ours(args, cfg, rank, world, local_rank):
                         if hp.fuse_stats else "srl_group_stats table between K2 and the loss",
                         minibatch_gather=("fused into the loss loads (lane_idx)" if hp.fuse_gather else "explicit K5 gather") +
                         f", Philox permutation of {hp.shuffle_block}-environment blocks",
-                        graph_branches=hp.graph_branches),
+                        graph_branches=hp.graph_branches,
+                        programmatic_dependent_launch=bool(ops.pdl_enabled()),
+                        kernel_timing="kernels[*]: each kernel alone in a graph, launched without the programmatic "
+                                      "attribute, CUDA events, L2 flushed"),
             clocks=clocks,
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=nbytes["h2d_bytes"],
                      d2h_bytes_per_step=nbytes["d2h_bytes"], ms_per_step=e2e_t.item() / e2e_steps * 1e3, steps=e2e_steps,

@@ -255,6 +255,7 @@ extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, in
   const bool smp_vec = pack == nullptr && (ld_smp % 4 == 0) && aligned(old_logp, 16) && aligned(ret, 16) &&
                        aligned(adv, 16) && (!s.h.clip_value || aligned(old_value, 16)) && aligned(on_reset_next, 4);
   s.smp_vec_ok = smp_vec ? 1 : 0;
+  s.prefetch_rows = 0;  // decided per launch (LossLauncher::launch)
   const int mode = pack ? kPack : ((!any_idx && dense_ok && smp_vec) ? kDense : kGather);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto fill = [](Problem& p, const srl_loss_problem& q) {
@@ -370,6 +371,7 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
   p.n = n;
   p.rows_per_tile = p.col_tiles = p.n_tiles = 0;
   p.smp_vec_ok = 0;
+  p.prefetch_rows = 0;
   Problem& pr = q.pr;
   pr.new_logp = pr.entropy = nullptr;
   pr.v_pred = v_pred;

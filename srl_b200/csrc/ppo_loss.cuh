@@ -73,6 +73,7 @@ struct LossShared {
   int T, n;
   int rows_per_tile, col_tiles, n_tiles;
   int smp_vec_ok;  // sample-side leaves allow 128-bit loads at 4-aligned lanes (alignment + row stride)
+  int prefetch_rows;  // policy-side rows a CTA asks into L2 before it waits for the kernel ahead of it (0: none)
   LossHyperDev h;
 };
 
@@ -437,6 +438,15 @@ __host__ __device__ constexpr size_t loss_smem_bytes(int threads) {
 // LANES = 4: a thread owns four adjacent lanes (n % 4 == 0, 16-byte aligned rows); LANES = 1: any shape.
 // PIPE (dense and pack forms, LANES = 4): row t + kStages is copied global -> shared (16 bytes per cp.async, each
 // thread into its own slots, so no block barrier) while row t is computed.
+// Policy-side rows a CTA asks into L2 before it waits for the scan.  Only for programmatic launches of short tiles
+// (cfg2: 5 rows per CTA, the whole tile): measured on one box (profiles/r1d_notes.md), the requests cost the kernel
+// ~2 us when it runs alone (26.6 -> 28.7 us at cfg2, 76.4 -> 78.6 us at cfg5: the demand loads follow at once and find
+// their lines still in flight), and win 1.3 us per step when they are issued under the scan (cfg2: 43.1 -> 41.7 us).
+#ifndef SRL_LOSS_PREFETCH_ROWS
+#define SRL_LOSS_PREFETCH_ROWS 6
+#endif
+constexpr int kPrefetchRows = SRL_LOSS_PREFETCH_ROWS;
+
 template <int LANES, int MODE, class CFG>
 __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(const __grid_constant__ LossBatch b) {
   constexpr bool PIPE = kUsePipe && (LANES == 4) && (MODE == kDense || MODE == kPack);
@@ -456,12 +466,13 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
   // Launched programmatically behind the scan (common.cuh), this CTA may be resident while the scan still runs.  The
   // policy-side rows do not depend on it: ask for this CTA's share (three tensors x its rows, one request per 128-byte
   // line) to be brought into L2 under the scan, then wait for the scan's results.
-  if constexpr (LANES == 4) {
-    if ((threadIdx.x & 7) == 0) {
+  if constexpr (LANES == 4 && kPrefetchRows > 0) {
+    if (s.prefetch_rows > 0 && (threadIdx.x & 7) == 0) {
       const int j = (blockIdx.x * blockDim.x + threadIdx.x) * LANES;
       if (j < n) {
         long long o = static_cast<long long>(r0) * s.ld_pol + j;
-        for (int t = r0; t < r1; ++t, o += s.ld_pol) {
+        const int r_pf = min(r1, r0 + s.prefetch_rows);
+        for (int t = r0; t < r_pf; ++t, o += s.ld_pol) {
           prefetch_l2(pr.new_logp + o);
           prefetch_l2(pr.v_pred + o);
           prefetch_l2(pr.entropy + o);
@@ -720,6 +731,7 @@ struct LossLauncher {
     if (gx * groups > kMaxGrid) gx = kMaxGrid / groups;  // one partial row per CTA in the workspace slot
     s.rows_per_tile = rows;
     s.n_tiles = static_cast<int>(groups);
+    s.prefetch_rows = (pdl_enabled() && rows <= kPrefetchRows) ? rows : 0;
     const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(groups), static_cast<unsigned>(n_problems));
     SRL_CUDA(launch_pdl(ppo_loss_kernel<LANES, MODE, CFG>, grid, dim3(threads), PIPE ? loss_smem_bytes(threads) : 0, st, b));
     return SRL_OK;

@@ -792,7 +792,10 @@ def test_group_stats_long_rows(ops):
         np.testing.assert_allclose(out[0, :7].cpu().numpy(), part[:7].sum(1).cpu().numpy(), rtol=1e-12)
 
 
-@pytest.mark.parametrize("L,N,lo,boot", [(40, 512, 3, 5), (65, 1024, 0, 17), (18, 256, 1, 1)])
+@pytest.mark.parametrize("L,N,lo,boot", [(40, 512, 3, 5), (65, 1024, 0, 17), (18, 256, 1, 1),
+                                          # trajectories longer than the 9-slot ring holds (26 and 10 chunks: the ring wraps
+                                          # with the delta pass 8 chunks ahead), and 3-slot-ring shapes (> 148 lane groups)
+                                          (401, 1024, 2, 1), (146, 4096, 0, 1), (161, 6400, 0, 3), (33, 8192, 1, 2)])
 def test_gae_ws_kernel_popart_rows_and_stats(ops, L, N, lo, boot):
     """Shapes that route to the warp-specialised kernel, with PopArt denormalisation, burn-in / bootstrap rows and the
     per-lane statistics checked against the oracle (adv / ret bit-exact)."""
