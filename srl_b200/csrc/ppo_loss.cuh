@@ -20,6 +20,14 @@ constexpr int kMaxGrid = 2048;                // partial rows per workspace slot
 constexpr int kNumSums = 8;
 constexpr size_t kPartialsOffset = 64;
 constexpr int kMaxBatch = SRL_MAX_LOSS_BATCH;
+// SRL_LOSS_EARLY_ROW=1: the first row's loads are issued ahead of the statistics prologue and every later row right after
+// the stores of the row before it.  Built and measured on B200 (profiles/r1d_notes.md): it loses -- cfg2 26.7 -> 33.0 us,
+// cfg5 79.7 -> 93.4 us, 212 instead of 148 bytes of spills at the 80-register cap (the row's 28 load registers stay live
+// across the loop's back edge and through the prologue) -- so it is compiled out.
+#ifndef SRL_LOSS_EARLY_ROW
+#define SRL_LOSS_EARLY_ROW 0
+#endif
+constexpr bool kEarlyRow = SRL_LOSS_EARLY_ROW != 0;
 constexpr int kFlushRows = 8;  // rows whose masked terms are summed in fp32 before they enter the float64 sums
 
 // First 64 bytes of a workspace slot; the partial rows [n_rows][8] f64 follow.
@@ -587,13 +595,6 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
     }
     cp_async_wait<0>();
   } else {
-    if (!have_u) {
-      if (s.lane_part != nullptr)
-        u = self_uniforms<LANES>(s.lane_part, s.lane_part_n, c, active, h.adv_eps, mask_sum);
-      else
-        u = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
-      have_u = true;
-    }
     // a run of four consecutive, 4-aligned lanes (agents of one environment, sector-aligned environment blocks) is
     // fetched with one 128-bit load per leaf
     bool run4 = false;
@@ -607,59 +608,71 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
     float* gv_row = pr.g_value + static_cast<long long>(r0) * s.ld_grad;
     float* ge_row = pr.g_entropy + static_cast<long long>(r0) * s.ld_grad;
     long long ob = static_cast<long long>(r0) * s.ld_smp;  // sample-side row base (elements)
+    float nl[LANES], vp[LANES], en[LANES], ol[LANES], ov[LANES], rt[LANES], ad[LANES];
+    bool valid[LANES];
+    // every global load of the row at (nl_row, vp_row, en_row, ob)
+    auto load_row = [&]() {
+      if constexpr (LANES == 4) {
+        unpack4(ldg_stream(reinterpret_cast<const float4*>(nl_row + j)), nl);
+        unpack4(ldg_stream(reinterpret_cast<const float4*>(vp_row + j)), vp);
+        unpack4(ldg_stream(reinterpret_cast<const float4*>(en_row + j)), en);
+      } else {
+        nl[0] = ldg_stream(nl_row + j);
+        vp[0] = ldg_stream(vp_row + j);
+        en[0] = ldg_stream(en_row + j);
+      }
+      if constexpr (MODE == kPack) {
+        const float4* pack_row = s.pack + ob;
+#pragma unroll
+        for (int q = 0; q < LANES; ++q) {
+          const float4 k = __ldg(pack_row + c[q]);
+          ol[q] = k.x;
+          ov[q] = k.y;
+          rt[q] = k.z;
+          ad[q] = k.w;
+          valid[q] = (k.w == k.w);
+        }
+      } else if (run4) {
+        if constexpr (LANES == 4) {
+          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.old_logp + ob + c[0])), ol);
+          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.ret + ob + c[0])), rt);
+          unpack4(ldg_stream(reinterpret_cast<const float4*>(s.adv + ob + c[0])), ad);
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (CFG::clip(h)) o = ldg_stream(reinterpret_cast<const float4*>(s.old_value + ob + c[0]));
+          unpack4(o, ov);
+          const uint32_t m = ldg_stream(reinterpret_cast<const uint32_t*>(s.reset_next + ob + c[0]));
+#pragma unroll
+          for (int q = 0; q < LANES; ++q) valid[q] = ((m >> (8 * q)) & 0xffu) == 0u;
+        }
+      } else {
+        const float* ol_row = s.old_logp + ob;
+        const float* rt_row = s.ret + ob;
+        const float* ad_row = s.adv + ob;
+        const float* ov_row = CFG::clip(h) ? s.old_value + ob : nullptr;
+        const uint8_t* rs_row = s.reset_next + ob;
+#pragma unroll
+        for (int q = 0; q < LANES; ++q) {
+          ol[q] = __ldg(ol_row + c[q]);
+          rt[q] = __ldg(rt_row + c[q]);
+          ad[q] = __ldg(ad_row + c[q]);
+          ov[q] = CFG::clip(h) ? __ldg(ov_row + c[q]) : 0.f;
+          valid[q] = __ldg(rs_row + c[q]) == 0;
+        }
+      }
+    };
+    // kEarlyRow (off, see the top of this file): first row's loads before the statistics prologue
+    if (kEarlyRow && active && r0 < r1) load_row();
+    if (!have_u) {
+      if (s.lane_part != nullptr)
+        u = self_uniforms<LANES>(s.lane_part, s.lane_part_n, c, active, h.adv_eps, mask_sum);
+      else
+        u = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
+      have_u = true;
+    }
     if (active) {
 #pragma unroll kLossUnroll
-      for (int t = r0; t < r1; ++t, nl_row += s.ld_pol, vp_row += s.ld_pol, en_row += s.ld_pol, glp_row += s.ld_grad,
-               gv_row += s.ld_grad, ge_row += s.ld_grad, ob += s.ld_smp) {
-        float nl[LANES], vp[LANES], en[LANES], ol[LANES], ov[LANES], rt[LANES], ad[LANES];
-        bool valid[LANES];
-        if constexpr (LANES == 4) {
-          unpack4(ldg_stream(reinterpret_cast<const float4*>(nl_row + j)), nl);
-          unpack4(ldg_stream(reinterpret_cast<const float4*>(vp_row + j)), vp);
-          unpack4(ldg_stream(reinterpret_cast<const float4*>(en_row + j)), en);
-        } else {
-          nl[0] = ldg_stream(nl_row + j);
-          vp[0] = ldg_stream(vp_row + j);
-          en[0] = ldg_stream(en_row + j);
-        }
-        if constexpr (MODE == kPack) {
-          const float4* pack_row = s.pack + ob;
-#pragma unroll
-          for (int q = 0; q < LANES; ++q) {
-            const float4 k = __ldg(pack_row + c[q]);
-            ol[q] = k.x;
-            ov[q] = k.y;
-            rt[q] = k.z;
-            ad[q] = k.w;
-            valid[q] = (k.w == k.w);
-          }
-        } else if (run4) {
-          if constexpr (LANES == 4) {
-            unpack4(ldg_stream(reinterpret_cast<const float4*>(s.old_logp + ob + c[0])), ol);
-            unpack4(ldg_stream(reinterpret_cast<const float4*>(s.ret + ob + c[0])), rt);
-            unpack4(ldg_stream(reinterpret_cast<const float4*>(s.adv + ob + c[0])), ad);
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (CFG::clip(h)) o = ldg_stream(reinterpret_cast<const float4*>(s.old_value + ob + c[0]));
-            unpack4(o, ov);
-            const uint32_t m = ldg_stream(reinterpret_cast<const uint32_t*>(s.reset_next + ob + c[0]));
-#pragma unroll
-            for (int q = 0; q < LANES; ++q) valid[q] = ((m >> (8 * q)) & 0xffu) == 0u;
-          }
-        } else {
-          const float* ol_row = s.old_logp + ob;
-          const float* rt_row = s.ret + ob;
-          const float* ad_row = s.adv + ob;
-          const float* ov_row = CFG::clip(h) ? s.old_value + ob : nullptr;
-          const uint8_t* rs_row = s.reset_next + ob;
-#pragma unroll
-          for (int q = 0; q < LANES; ++q) {
-            ol[q] = __ldg(ol_row + c[q]);
-            rt[q] = __ldg(rt_row + c[q]);
-            ad[q] = __ldg(ad_row + c[q]);
-            ov[q] = CFG::clip(h) ? __ldg(ov_row + c[q]) : 0.f;
-            valid[q] = __ldg(rs_row + c[q]) == 0;
-          }
-        }
+      for (int t = r0; t < r1; ++t) {
+        if (!kEarlyRow) load_row();
         float glp[LANES], gv[LANES], ge[LANES];
 #pragma unroll
         for (int q = 0; q < LANES; ++q)
@@ -678,6 +691,10 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
           stg_stream(gv_row + j, gv[0]);
           stg_stream(ge_row + j, ge[0]);
         }
+        nl_row += s.ld_pol, vp_row += s.ld_pol, en_row += s.ld_pol;
+        glp_row += s.ld_grad, gv_row += s.ld_grad, ge_row += s.ld_grad;
+        ob += s.ld_smp;
+        if (kEarlyRow && t + 1 < r1) load_row();
       }
     }
   }
