@@ -112,3 +112,56 @@ def test_plugin_registers_into_srl_registry_when_srl_is_importable():
     importlib.reload(plugin)
     assert plugin.REGISTERED_IN_SRL
     assert {"mappo", "mappo_b200"} <= set(R.trainer.ALL_TRAINER_CLASSES)
+
+
+# ---- chunk reshape descriptors (ops.to_chunk / back_to_trajectory build these for srl_batch_gather) ----------------
+def _emulate_gather(src_bytes, piece, t_stride, slot_stride, idx, L, B):
+    """What srl_batch_gather does with ONE leaf descriptor (include/srl_b200.h: srl_leaf_desc), in numpy."""
+    out = np.empty(L * B * piece, np.uint8)
+    for t in range(L):
+        for j in range(B):
+            o = t * t_stride + int(idx[j]) * slot_stride
+            out[(t * B + j) * piece:(t * B + j + 1) * piece] = src_bytes[o:o + piece]
+    return out
+
+
+@pytest.mark.parametrize("T,B,D,C,split", [(24, 8, 1, 8, 1), (24, 8, 4, 4, 2), (12, 6, 8, 3, 4), (6, 5, 2, 1, 1)])
+def test_chunk_reshape_descriptors_reproduce_to_chunk(T, B, D, C, split):
+    """The (piece, strides, index vector) ops.to_chunk / back_to_trajectory hand to K1 reproduce
+    torch.cat(torch.split(...)) (legacy/algorithm/modules/utils.py:180,195) byte for byte, with and without row splitting."""
+    import torch
+    from srl_b200 import ops
+    x = torch.randn(T, B, D)
+    ref = torch.cat(torch.split(x, T // C, dim=0), dim=1).contiguous()
+    raw = x.numpy().view(np.uint8).reshape(-1)
+    Tc, row = T // C, B * D * 4
+    piece = row // split
+    idx = ops._split_index("cpu", C, Tc * split, split).numpy()
+    got = _emulate_gather(raw, piece, row, piece, idx, Tc, C * split)
+    assert np.array_equal(got, ref.numpy().view(np.uint8).reshape(-1))
+    idx_back = ops._split_index("cpu", Tc, C * split, split).numpy()
+    back = _emulate_gather(ref.numpy().view(np.uint8).reshape(-1), piece, row, piece, idx_back, C, Tc * split)
+    assert np.array_equal(back, raw)
+
+
+def test_row_split_keeps_16_byte_granules_and_bounds_items():
+    from srl_b200 import ops
+    assert ops._row_split(32, 24) == 1  # short rows move whole
+    for row_bytes, items in [(4096 * 28224, 128), (1 << 20, 16), (48 * 1024, 4), (16384 * 3 + 16, 8)]:
+        s = ops._row_split(row_bytes, items)
+        assert s >= 1 and row_bytes % s == 0 and (s == 1 or ((row_bytes // s) % 16 == 0 and row_bytes // s >= 16384))
+        assert s * items <= 65536 or s == 1
+
+
+# ---- device buffer staging layout (host side of srl_b200/buffer.py) -------------------------------------------------
+def test_staging_layout_alignment_and_extension():
+    from srl_b200.buffer import _ALIGN, _Layout
+    leaves = [("a", np.zeros((5, 3), np.float32)), ("b", None), ("c.x", np.zeros((5, 7), np.uint8))]
+    lay = _Layout(leaves)
+    assert lay.L == 5 and set(lay.spec) == {"a", "c.x"}
+    assert all(off % _ALIGN == 0 for off, _, _ in lay.spec.values()) and lay.bytes % _ALIGN == 0
+    assert lay.matches("a", np.zeros((5, 3), np.float32)) and not lay.matches("a", np.zeros((5, 3), np.float64))
+    ext = lay.extended_with([("a", np.zeros((5, 3), np.float32)), ("b", np.zeros((5, 1), np.int64)), ("c.x", None)])
+    assert set(ext.spec) == {"a", "b", "c.x"} and ext.spec["b"][1] == np.int64 and ext.names == sorted(ext.names)
+    with pytest.raises(ValueError):
+        _Layout([("a", np.zeros((5, 3))), ("z", np.zeros((4, 3)))])

@@ -385,3 +385,26 @@ def test_traj_gae_restatement_vs_live_reference():
         a, r = M.traj_gae_process_ref(reward, value, trunc, has, 0.98, 0.9)
         assert np.array_equal(a, np.stack([m.analyzed_result.adv for m in memory[:-1]]))
         assert np.array_equal(r, np.stack([m.analyzed_result.ret for m in memory[:-1]]))
+
+
+def test_traj_gae_and_gae_trace_restatements_agree_on_one_episode():
+    """Two reference functions, one recurrence: for a single finished episode in float64, TrajGAE (gae.py:100-139) and
+    gae_trace (gae.py:8-97, float64 inside) compute the same products and sums (a + b == b + a), so their restatements
+    must agree to the bit once gae_trace's result is compared before / after the same float32 cast."""
+    rng = np.random.default_rng(8)
+    for truncated_end in (False, True):
+        n = 23
+        reward = rng.standard_normal((n, 1))
+        value = rng.standard_normal((n, 1))
+        reward[-1] = 0.0  # the final step carries no reward (gae.py:72)
+        a, _ = M.traj_gae_process_ref(reward, value, np.array([float(truncated_end)]), True, 0.97, 0.9)
+        # the same episode as a [n+1]-row batch lane: the row after the final step is a reset row
+        done = np.zeros((n + 1, 1)); trunc = np.zeros((n + 1, 1)); reset = np.zeros((n + 1, 1))
+        (trunc if truncated_end else done)[n - 1] = 1.0
+        reset[n] = 1.0
+        # TrajGAE bootstraps the last computed step with value[last] * truncated[last]; gae_trace reads value[t+1] as is,
+        # and mappo zeroes it where done (mappo.py:120-124)
+        v = np.concatenate([value, np.zeros((1, 1))]) * (1 - done)
+        got = M.gae_trace_ref(*(torch.from_numpy(x) for x in (reward, v, trunc, done, reset)), 0.97, 0.9)
+        # rows 0 .. n-2 are TrajGAE's steps; row n-1 is the final step itself (delta = -v there if truncated)
+        assert np.array_equal(got.numpy()[:n - 1], a.astype(np.float32))
