@@ -46,11 +46,13 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 // per loop iteration -- measured in profiles/r1_notes.md.  The intrinsics stay schedulable, so independent
 // loads are hoisted and overlap.)
 __device__ __forceinline__ float ldg_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ float2 ldg_stream(const float2* p) { return __ldcs(p); }
 __device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ uint32_t ldg_stream(const uint32_t* p) { return __ldcs(p); }
 __device__ __forceinline__ uint8_t ldg_stream(const uint8_t* p) { return __ldcs(p); }
 __device__ __forceinline__ int4 ldg_stream(const int4* p) { return __ldcs(p); }
 __device__ __forceinline__ void stg_stream(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void stg_stream(float2* p, float2 v) { __stcs(p, v); }
 __device__ __forceinline__ void stg_stream(float4* p, float4 v) { __stcs(p, v); }
 __device__ __forceinline__ void stg_stream(int4* p, int4 v) { __stcs(p, v); }
 

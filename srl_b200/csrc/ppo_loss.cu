@@ -26,6 +26,8 @@
 // Finalisation: immediate (out != NULL): the last CTA of the problem (atomic ticket) folds the rows in a fixed
 // order; deferred (out == NULL): srl_ppo_loss_finalize folds any number of slots later in ONE launch.
 // Either way the result is deterministic for a given launch shape and nothing syncs with the host.
+#include <stdlib.h>
+
 #include "ppo_loss.cuh"
 
 namespace srl {
@@ -256,6 +258,12 @@ extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, in
                        aligned(adv, 16) && (!s.h.clip_value || aligned(old_value, 16)) && aligned(on_reset_next, 4);
   s.smp_vec_ok = smp_vec ? 1 : 0;
   s.prefetch_rows = 0;  // decided per launch (LossLauncher::launch)
+  // SRL_LOSS_LANES=2 (read once; a tuning knob for profiles/, not an API): small pack-form minibatches run two lanes per
+  // thread.  Built for the next measurement round (profiles/r1d_notes.md); the default stays four lanes per thread.
+  static const bool lanes2_knob = [] {
+    const char* e = getenv("SRL_LOSS_LANES");
+    return e != nullptr && e[0] == '2';
+  }();
   const int mode = pack ? kPack : ((!any_idx && dense_ok && smp_vec) ? kDense : kGather);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto fill = [](Problem& p, const srl_loss_problem& q) {
@@ -277,7 +285,9 @@ extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, in
     LossBatch b;
     b.s = s;
     for (int k = 0; k < kMaxBatch; ++k) fill(b.prob[k], problems[k0 + (k < nb ? k : 0)]);
-    if (mode == kPack)
+    if (mode == kPack && dense_ok && lanes2_knob && n <= 512)
+      rc = launch_loss_pack2(b, nb, st);
+    else if (mode == kPack)
       rc = launch_loss_pack(b, nb, dense_ok, st);
     else if (mode == kDense)
       rc = launch_loss_dense(b, nb, dense_ok, st);

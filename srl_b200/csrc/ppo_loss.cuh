@@ -474,8 +474,8 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
   // Launched programmatically behind the scan (common.cuh), this CTA may be resident while the scan still runs.  The
   // policy-side rows do not depend on it: ask for this CTA's share (three tensors x its rows, one request per 128-byte
   // line) to be brought into L2 under the scan, then wait for the scan's results.
-  if constexpr (LANES == 4 && kPrefetchRows > 0) {
-    if (s.prefetch_rows > 0 && (threadIdx.x & 7) == 0) {
+  if constexpr (LANES >= 2 && kPrefetchRows > 0) {
+    if (s.prefetch_rows > 0 && (threadIdx.x & (32 / LANES - 1)) == 0) {  // one thread per 128-byte line
       const int j = (blockIdx.x * blockDim.x + threadIdx.x) * LANES;
       if (j < n) {
         long long o = static_cast<long long>(r0) * s.ld_pol + j;
@@ -500,6 +500,9 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
     if constexpr (LANES == 4) {
       const int4 q = __ldg(reinterpret_cast<const int4*>(pr.lane_idx + j));
       c[0] = q.x, c[1] = q.y, c[2] = q.z, c[3] = q.w;
+    } else if constexpr (LANES == 2) {
+      const int2 q = __ldg(reinterpret_cast<const int2*>(pr.lane_idx + j));
+      c[0] = q.x, c[1] = q.y;
     } else {
       c[0] = __ldg(pr.lane_idx + j);
     }
@@ -616,6 +619,11 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
         unpack4(ldg_stream(reinterpret_cast<const float4*>(nl_row + j)), nl);
         unpack4(ldg_stream(reinterpret_cast<const float4*>(vp_row + j)), vp);
         unpack4(ldg_stream(reinterpret_cast<const float4*>(en_row + j)), en);
+      } else if constexpr (LANES == 2) {
+        const float2 a = ldg_stream(reinterpret_cast<const float2*>(nl_row + j));
+        const float2 b2 = ldg_stream(reinterpret_cast<const float2*>(vp_row + j));
+        const float2 e2 = ldg_stream(reinterpret_cast<const float2*>(en_row + j));
+        nl[0] = a.x, nl[1] = a.y, vp[0] = b2.x, vp[1] = b2.y, en[0] = e2.x, en[1] = e2.y;
       } else {
         nl[0] = ldg_stream(nl_row + j);
         vp[0] = ldg_stream(vp_row + j);
@@ -686,6 +694,10 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
           stg_stream(reinterpret_cast<float4*>(glp_row + j), make_float4(glp[0], glp[1], glp[2], glp[3]));
           stg_stream(reinterpret_cast<float4*>(gv_row + j), make_float4(gv[0], gv[1], gv[2], gv[3]));
           stg_stream(reinterpret_cast<float4*>(ge_row + j), make_float4(ge[0], ge[1], ge[2], ge[3]));
+        } else if constexpr (LANES == 2) {
+          stg_stream(reinterpret_cast<float2*>(glp_row + j), make_float2(glp[0], glp[1]));
+          stg_stream(reinterpret_cast<float2*>(gv_row + j), make_float2(gv[0], gv[1]));
+          stg_stream(reinterpret_cast<float2*>(ge_row + j), make_float2(ge[0], ge[1]));
         } else {
           stg_stream(glp_row + j, glp[0]);
           stg_stream(gv_row + j, gv[0]);
@@ -757,21 +769,15 @@ struct LossLauncher {
 
 // Picks the instantiation for the launch's hyper-parameters.  Static configurations: {mse, huber} x clip_value x
 // dual_clip x popart with four lanes per thread; everything else (smoothl1, odd shapes) runs the general instantiation.
-template <int MODE>
-int launch_loss_mode(LossBatch& b, int n_problems, bool lanes4, cudaStream_t st) {
+template <int LANES, int MODE>
+int launch_loss_static(LossBatch& b, int n_problems, cudaStream_t st) {
   const LossHyperDev& h = b.s.h;
-  if (!lanes4) {
-    if constexpr (MODE == kDense)
-      return SRL_ERR_INVALID_ARG;  // the dense form needs 128-bit rows; callers route odd shapes to kGather
-    else
-      return LossLauncher<1, MODE, RuntimeCfg>::launch(b, n_problems, st);
-  }
   const bool popart = b.s.popart != nullptr;
   const int key = (h.value_loss == SRL_VL_MSE ? 0 : h.value_loss == SRL_VL_HUBER ? 1 : 2) * 8 + (h.clip_value ? 4 : 0) +
                   (h.dual_clip ? 2 : 0) + (popart ? 1 : 0);
 #define SRL_LOSS_CASE(k, vl, clip, dual, pa) \
   case k:                                    \
-    return LossLauncher<4, MODE, StaticCfg<vl, clip, dual, pa>>::launch(b, n_problems, st)
+    return LossLauncher<LANES, MODE, StaticCfg<vl, clip, dual, pa>>::launch(b, n_problems, st)
   switch (key) {
     SRL_LOSS_CASE(0, SRL_VL_MSE, false, false, false);
     SRL_LOSS_CASE(1, SRL_VL_MSE, false, false, true);
@@ -790,15 +796,29 @@ int launch_loss_mode(LossBatch& b, int n_problems, bool lanes4, cudaStream_t st)
     SRL_LOSS_CASE(14, SRL_VL_HUBER, true, true, false);
     SRL_LOSS_CASE(15, SRL_VL_HUBER, true, true, true);
     default:
-      return LossLauncher<4, MODE, RuntimeCfg>::launch(b, n_problems, st);
+      return LossLauncher<LANES, MODE, RuntimeCfg>::launch(b, n_problems, st);
   }
 #undef SRL_LOSS_CASE
+}
+
+template <int MODE>
+int launch_loss_mode(LossBatch& b, int n_problems, bool lanes4, cudaStream_t st) {
+  if (!lanes4) {
+    if constexpr (MODE == kDense)
+      return SRL_ERR_INVALID_ARG;  // the dense form needs 128-bit rows; callers route odd shapes to kGather
+    else
+      return LossLauncher<1, MODE, RuntimeCfg>::launch(b, n_problems, st);
+  }
+  return launch_loss_static<4, MODE>(b, n_problems, st);
 }
 
 // defined in ppo_loss_dense.cu / ppo_loss_gather.cu / ppo_loss_pack.cu
 int launch_loss_dense(LossBatch& b, int n_problems, bool lanes4, cudaStream_t st);
 int launch_loss_gather(LossBatch& b, int n_problems, bool lanes4, cudaStream_t st);
 int launch_loss_pack(LossBatch& b, int n_problems, bool lanes4, cudaStream_t st);
+// ppo_loss_pack2.cu: the pack form with TWO lanes per thread (twice the threads per row, half the registers a row's loads
+// hold): an experiment for small minibatches, reached only with SRL_LOSS_LANES=2 in the environment (ppo_loss.cu)
+int launch_loss_pack2(LossBatch& b, int n_problems, cudaStream_t st);
 
 }  // namespace loss
 }  // namespace srl
