@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SRL_B200_ABI_VERSION 3
+#define SRL_B200_ABI_VERSION 4
 
 typedef void* srl_stream_t; /* cudaStream_t */
 
@@ -324,6 +324,12 @@ typedef struct srl_leaf_desc {
 
 int srl_batch_gather(const srl_leaf_desc* leaves_host, int n_leaves, const int32_t* idx /* device [B] or NULL */,
                      int L, int B, srl_stream_t stream);
+
+/* HOST helper of the device sample buffer (no CUDA call; host pointers): copies `bytes` bytes with up to `threads`
+ * participants (a persistent pool inside the library + the caller; small copies fall back to one memcpy).  It replaces the
+ * single-threaded copy into the staging block that bounded the per-sample `put` -- in the reference that copy is the
+ * np.stack of PriorityQueueBuffer.put (base/buffer.py:118-126), also on one thread.  Calls are serialised. */
+int srl_host_copy(void* dst, const void* src, size_t bytes, int threads);
 
 /* ------------------------------------------------------------------------------------------
  * One-shot SUM all-reduce of a small float64 table over NVLink peer memory (one process per GPU of ONE node).

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--B", type=int, default=256)
     ap.add_argument("--L", type=int, default=129)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--copy-threads", type=int, default=1, help="host threads per large-leaf copy into pinned memory")
     a = ap.parse_args()
     rng = np.random.default_rng(0)
     samples = [sample(rng, a.L) for _ in range(a.B)]
@@ -61,7 +62,7 @@ def main():
         t_h2d.append(t2 - t1)
         del dev
     # ---- ours -----------------------------------------------------------------------------------------------------
-    buf = DeviceSlabBuffer(max_size=2, reuses=1, batch_size=a.B)
+    buf = DeviceSlabBuffer(max_size=2, reuses=1, batch_size=a.B, copy_threads=a.copy_threads)
     t_put, t_total = [], []
     for _ in range(a.reps + 1):
         torch.cuda.synchronize()

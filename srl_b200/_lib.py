@@ -19,7 +19,7 @@ SRL_LANE_PART = 8
 SRL_LOSS_OUT_LEN = 16
 SRL_MAX_LEAVES = 32
 SRL_MAX_HEADS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 SRL_MAX_LOSS_BATCH = 32
 
 # enum srl_loss_out
@@ -105,6 +105,7 @@ SIGNATURES = {
     "srl_philox_perm": (c_int, [c_uint64, c_uint32, c_int, c_int, c_int, c_void_p, c_void_p]),
     "srl_philox4x32_10": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "srl_batch_gather": (c_int, [POINTER(LeafDesc), c_int, c_void_p, c_int, c_int, c_void_p]),
+    "srl_host_copy": (c_int, [c_void_p, c_void_p, c_size_t, c_int]),
     "srl_group_stats_xchg": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                      c_void_p, c_void_p]),
     "srl_xchg_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),

@@ -33,6 +33,7 @@ from srl_b200 import ops, wire
 from srl_b200._lib import LeafDesc
 from srl_b200.namedarray import flatten, from_flattened
 
+_MT_COPY_MIN = 1 << 20  # leaves at least this large go through the multi-threaded host copy (copy_threads > 1)
 _ALIGN = 256  # leaf offsets inside a staged sample (keeps every leaf 16-byte aligned for 128-bit copies)
 
 
@@ -87,7 +88,8 @@ class _Layout:
 class DeviceSlabBuffer:
     """`make_buffer("priority_queue", ...)` with device-resident batches (see the module docstring)."""
 
-    def __init__(self, max_size: int = 16, reuses: int = 1, batch_size: int = 1, device=None, staging_batches: int = 2):
+    def __init__(self, max_size: int = 16, reuses: int = 1, batch_size: int = 1, device=None, staging_batches: int = 2,
+                 copy_threads: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("DeviceSlabBuffer needs a CUDA device (srl_b200 has no CPU path; use SRL's own "
                                "base.buffer.PriorityQueueBuffer on CPU)")
@@ -105,6 +107,8 @@ class DeviceSlabBuffer:
         self._slot_ready: Dict[int, torch.cuda.Event] = {}
         self._slot_free_after: Dict[int, torch.cuda.Event] = {}
         self.bytes_staged = 0
+        # host threads that copy a large leaf into the pinned block (srl_host_copy); 1 = numpy's own single copy
+        self.copy_threads = max(1, int(copy_threads))
 
     # ---- reference interface -------------------------------------------------------------------------------------
     @property
@@ -212,7 +216,11 @@ class DeviceSlabBuffer:
                 raise ValueError(f"leaf {k}: dtype/shape {v.dtype}{v.shape} differs from the first sample's "
                                  f"{lay.spec.get(k, ('-', None, None))[1:]} (samples of one buffer share their layout)")
             off = lay.spec[k][0]
-            pin[off:off + v.nbytes] = np.ascontiguousarray(v).view(np.uint8).reshape(-1)
+            if self.copy_threads > 1 and v.nbytes >= _MT_COPY_MIN:
+                src = np.ascontiguousarray(v)
+                ops._lib.call("srl_host_copy", pin.ctypes.data + off, src.ctypes.data, src.nbytes, self.copy_threads)
+            else:
+                pin[off:off + v.nbytes] = np.ascontiguousarray(v).view(np.uint8).reshape(-1)
             present.add(k)
         with torch.cuda.stream(self._copy_stream):
             self._stage_dev[slot].copy_(self._stage_pin[slot], non_blocking=True)

@@ -95,3 +95,37 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+@pytest.mark.parametrize("nbytes", [0, 1, 4097, 300_000, (1 << 20) + 13, 9_000_001])
+@pytest.mark.parametrize("threads", [1, 2, 5, 16])
+def test_host_copy_is_a_memcpy_for_every_size_and_thread_count(lib, nbytes, threads):
+    """srl_host_copy (host-only entry point: pure host memory, no GPU needed): byte-exact, does not touch a byte outside
+    [dst, dst + bytes), unaligned pointers included."""
+    rng = np.random.default_rng(nbytes + threads)
+    src = rng.integers(0, 256, nbytes + 3, dtype=np.uint8)
+    dst = np.full(nbytes + 64, 0xAB, dtype=np.uint8)
+    _lib.call("srl_host_copy", dst.ctypes.data + 7, src.ctypes.data + 3, nbytes, threads)
+    assert np.array_equal(dst[7:7 + nbytes], src[3:3 + nbytes])
+    assert (dst[:7] == 0xAB).all() and (dst[7 + nbytes:] == 0xAB).all()
+
+
+def test_host_copy_concurrent_callers_and_bad_arguments(lib):
+    import threading
+    rng = np.random.default_rng(0)
+    srcs = [rng.integers(0, 256, 3_000_000 + i, dtype=np.uint8) for i in range(4)]
+    dsts = [np.zeros_like(s) for s in srcs]
+
+    def work(i):
+        for _ in range(5):
+            dsts[i][:] = 0
+            _lib.call("srl_host_copy", dsts[i].ctypes.data, srcs[i].ctypes.data, srcs[i].nbytes, 2 + i)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert all(np.array_equal(d, s) for d, s in zip(dsts, srcs))
+    with pytest.raises(_lib.SrlCudaError, match="threads"):
+        _lib.call("srl_host_copy", dsts[0].ctypes.data, srcs[0].ctypes.data, 10, 0)
+    with pytest.raises(_lib.SrlCudaError, match="null"):
+        _lib.call("srl_host_copy", None, srcs[0].ctypes.data, 10, 1)
