@@ -408,6 +408,21 @@ __device__ __forceinline__ void reduce_and_finalize(const Problem& pr, const Los
 
 __device__ __forceinline__ void unpack4(const float4 v, float (&a)[4]) { a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w; }
 
+// Policy-side loads of the register path.  Default: streaming loads (ld.global.cs, evict-first).  SRL_LOSS_POLICY_NC=1
+// (a build variant for profiles/, with SRL_LOSS_UNROLL=2): non-coherent loads (ld.global.nc), which the compiler may hoist
+// above the gradient stores of the previous row -- the policy outputs are never written by this kernel.
+#ifndef SRL_LOSS_POLICY_NC
+#define SRL_LOSS_POLICY_NC 0
+#endif
+template <class V>
+__device__ __forceinline__ V ld_policy(const V* p) {
+#if SRL_LOSS_POLICY_NC
+  return __ldg(p);
+#else
+  return ldg_stream(p);
+#endif
+}
+
 // ---- asynchronous global -> shared copies (LDGSTS): the loads of the next rows are in flight while the current
 // row is computed, without holding registers for them -----------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -616,18 +631,18 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
     // every global load of the row at (nl_row, vp_row, en_row, ob)
     auto load_row = [&]() {
       if constexpr (LANES == 4) {
-        unpack4(ldg_stream(reinterpret_cast<const float4*>(nl_row + j)), nl);
-        unpack4(ldg_stream(reinterpret_cast<const float4*>(vp_row + j)), vp);
-        unpack4(ldg_stream(reinterpret_cast<const float4*>(en_row + j)), en);
+        unpack4(ld_policy(reinterpret_cast<const float4*>(nl_row + j)), nl);
+        unpack4(ld_policy(reinterpret_cast<const float4*>(vp_row + j)), vp);
+        unpack4(ld_policy(reinterpret_cast<const float4*>(en_row + j)), en);
       } else if constexpr (LANES == 2) {
-        const float2 a = ldg_stream(reinterpret_cast<const float2*>(nl_row + j));
-        const float2 b2 = ldg_stream(reinterpret_cast<const float2*>(vp_row + j));
-        const float2 e2 = ldg_stream(reinterpret_cast<const float2*>(en_row + j));
+        const float2 a = ld_policy(reinterpret_cast<const float2*>(nl_row + j));
+        const float2 b2 = ld_policy(reinterpret_cast<const float2*>(vp_row + j));
+        const float2 e2 = ld_policy(reinterpret_cast<const float2*>(en_row + j));
         nl[0] = a.x, nl[1] = a.y, vp[0] = b2.x, vp[1] = b2.y, en[0] = e2.x, en[1] = e2.y;
       } else {
-        nl[0] = ldg_stream(nl_row + j);
-        vp[0] = ldg_stream(vp_row + j);
-        en[0] = ldg_stream(en_row + j);
+        nl[0] = ld_policy(nl_row + j);
+        vp[0] = ld_policy(vp_row + j);
+        en[0] = ld_policy(en_row + j);
       }
       if constexpr (MODE == kPack) {
         const float4* pack_row = s.pack + ob;
