@@ -311,14 +311,21 @@ def gen_wire(R):
         action=NA(x=rng.integers(0, 18, (L, 1)).astype(np.int32)), reward=rng.standard_normal((L, 1)).astype(np.float32),
         analyzed_result=NA(value=rng.standard_normal((L, 1)).astype(np.float32), log_probs=rng.standard_normal((L, 1)),
                            adv=None, ret=None),
+        policy_state=NA(hx=rng.standard_normal((L, 1, 4)).astype(np.float32)),
         policy_version_steps=np.full((L, 1), 7, np.int64), sampling_weight=2.5)
     out = {}
-    for method in ("raw_bytes", "pickle_dict"):
+    # the compressed methods need `blosc` (absent): the unmodified reference runs with a stand-in codec injected under
+    # that name (tests/util.py::StandInBlosc), which pins the FRAMING of these methods, not the codec
+    from tests.util import StandInBlosc
+    sys.modules["blosc"] = StandInBlosc
+    for method in ("raw_bytes", "pickle_dict", "raw_compress", "compress_pickle", "obs_compress",
+                   "compress_except_policy_state"):
         frames = R.namedarray.dumps(x, method=method)
         out[f"{method}.stream"] = np.frombuffer(b"".join(frames), dtype=np.uint8)
         out[f"{method}.lens"] = np.array([len(f) for f in frames], np.int64)
         back = R.namedarray.loads(frames)
         assert back.metadata == x.metadata
+    del sys.modules["blosc"]
     for k, v in R.namedarray.flatten(x):
         if v is not None:
             out[f"leaf.{k}"] = v

@@ -134,8 +134,10 @@ class DeviceSlabBuffer:
         return self._batch_if_complete()
 
     def put_frames(self, b) -> bool:
-        """`put(namedarray.loads(b))` for a raw_bytes message (base/namedarray.py:115-128,166-218) without building the
-        sample: every leaf's payload is copied once, from the received bytes into the pinned staging block."""
+        """`put(namedarray.loads(b))` for a framed message (raw_bytes, raw_compress, compress_pickle, obs_compress,
+        compress_except_policy_state; base/namedarray.py:115-128,166-218) without building the sample: every leaf's payload
+        is copied once, from the received (or, for a compressed leaf, the decompressed) bytes into the pinned staging
+        block.  The compressed methods need the `blosc` package, as in the reference."""
         if not self.batch_size:
             return self.put(wire.loads(b))
         entries, metadata = wire.frames(b)

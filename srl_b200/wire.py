@@ -5,16 +5,22 @@ A message is a list of byte strings: `[method code] + body + [pickle(metadata)]`
 For the array methods the body is four frames per leaf -- key, dtype, shape, payload, all ASCII except the payload
 (namedarray.py:115-128); a `None` leaf has empty dtype / shape / payload frames.
 
-  method                        code    here
-  pickle_dict                   0001    dumps / loads
-  pickle                        0002    dumps / loads
-  raw_bytes                     0003    dumps / loads / frames() / DeviceSlabBuffer.put_frames (zero intermediate copies)
-  raw_compress, compress_pickle,
-  pickle_compress, obs_compress,
-  compress_except_policy_state  0004-8  need the third-party `blosc` codec (blosc.compress(typesize=4, cname='lz4'),
-                                        namedarray.py:126), which is absent from this image and from /root/reference:
-                                        its container format cannot be pinned to a single golden vector here, so these
-                                        raise instead of guessing (the reference itself fails on `import blosc`).
+  method                        code    body
+  pickle_dict                   0001    pickle((class name, nested dict))
+  pickle                        0002    pickle(object)
+  raw_bytes                     0003    four frames per leaf
+  raw_compress                  0004    four frames per leaf, every payload blosc-compressed
+  compress_pickle               0005    pickle(list of the raw_compress frames)
+  pickle_compress               0006    blosc(pickle(object))
+  obs_compress                  0007    four frames per leaf, payloads of leaves with 'obs' in the key compressed
+  compress_except_policy_state  0008    four frames per leaf, all payloads but those with 'policy_state' in the key compressed
+
+The codec is the third-party `blosc` package (`blosc.compress(payload, typesize=4, cname='lz4')`, namedarray.py:126),
+imported lazily exactly where the reference imports it (namedarray.py:101-103,168-171): with blosc installed (any SRL
+deployment that uses these methods) all eight methods work; without it (this image, /root/reference) the compressed
+ones raise ModuleNotFoundError, as the reference's do.  What is pinned here is the FRAMING -- which leaves are compressed,
+frame order, None leaves, metadata -- against messages the unmodified reference wrote with a stand-in codec injected as
+`blosc` (tests/golden/wire.npz, tests/test_wire.py); the codec's own byte format never passes through this file's logic.
 
 The reference's `loads` allocates a fresh ndarray per leaf per message on the trainer's main thread
 (distributed/system/sample_stream.py:176-198) and the buffer then copies every leaf again in `np.stack`.  `frames()`
@@ -32,9 +38,19 @@ import numpy as np
 from srl_b200.namedarray import NamedArray, flatten, from_dict, from_flattened
 
 PICKLE_DICT, PICKLE, RAW_BYTES = b"0001", b"0002", b"0003"
-_COMPRESSED = {b"0004": "raw_compress", b"0005": "compress_pickle", b"0006": "pickle_compress", b"0007": "obs_compress",
-               b"0008": "compress_except_policy_state"}
-_METHODS = {"pickle_dict": PICKLE_DICT, "pickle": PICKLE, "raw_bytes": RAW_BYTES}
+RAW_COMPRESS, COMPRESS_PICKLE, PICKLE_COMPRESS, OBS_COMPRESS, COMPRESS_EXCEPT_POLICY_STATE = (
+    b"0004", b"0005", b"0006", b"0007", b"0008")
+_METHODS = {"pickle_dict": PICKLE_DICT, "pickle": PICKLE, "raw_bytes": RAW_BYTES, "raw_compress": RAW_COMPRESS,
+            "compress_pickle": COMPRESS_PICKLE, "pickle_compress": PICKLE_COMPRESS, "obs_compress": OBS_COMPRESS,
+            "compress_except_policy_state": COMPRESS_EXCEPT_POLICY_STATE}
+# which leaves of a framed message are compressed (namedarray.py:141-156,199-208)
+_COMPRESS_IF = {RAW_BYTES: lambda k: False, RAW_COMPRESS: lambda k: True, COMPRESS_PICKLE: lambda k: True,
+                OBS_COMPRESS: lambda k: "obs" in k, COMPRESS_EXCEPT_POLICY_STATE: lambda k: "policy_state" not in k}
+
+
+def _blosc():
+    import blosc  # third-party; raises ModuleNotFoundError where it is not installed, like namedarray.py:103,171
+    return blosc
 
 
 def encode_dtype(dtype) -> str:
@@ -54,35 +70,53 @@ def _to_dict(x) -> Dict[str, Any]:
     return {k: (_to_dict(v) if isinstance(v, NamedArray) else v) for k, v in x.items()}
 
 
+def _leaf_frames(x: NamedArray, compress_if) -> List[bytes]:
+    """namedarray.py:112-128: key, dtype, shape, payload per leaf (empty frames for a None leaf)."""
+    out: List[bytes] = []
+    for k, v in flatten(x):
+        if v is None:
+            out += [k.encode("ascii"), b"", b"", b""]
+            continue
+        v = np.asarray(v)
+        payload = v.tobytes()
+        if compress_if(k):
+            payload = _blosc().compress(payload, typesize=4, cname="lz4")
+        out += [k.encode("ascii"), encode_dtype(v.dtype).encode("ascii"), str(tuple(v.shape)).encode("ascii"), payload]
+    return out
+
+
 def dumps(x: NamedArray, method: str = "pickle_dict") -> List[bytes]:
-    """namedarray.py:100-163 for the methods this image can serve."""
+    """namedarray.py:100-163."""
+    if method not in _METHODS:
+        raise NotImplementedError(f"Unknown method {method}. Available are {sorted(_METHODS)}.")
+    code = _METHODS[method]
     if "compress" in method:
-        raise ModuleNotFoundError(f"method {method!r} needs the `blosc` codec, which is not installed")
-    if method == "pickle_dict":
-        body = [PICKLE_DICT, pickle.dumps((type(x).__name__, _to_dict(x)))]
-    elif method == "pickle":
-        body = [PICKLE, pickle.dumps(x)]
-    elif method == "raw_bytes":
-        body = [RAW_BYTES]
-        for k, v in flatten(x):
-            if v is None:
-                body += [k.encode("ascii"), b"", b"", b""]
-            else:
-                v = np.asarray(v)
-                body += [k.encode("ascii"), encode_dtype(v.dtype).encode("ascii"), str(tuple(v.shape)).encode("ascii"),
-                         v.tobytes()]
+        _blosc()  # fail before any work, as the reference does (namedarray.py:101-103)
+    if code == PICKLE_DICT:
+        body = [pickle.dumps((type(x).__name__, _to_dict(x)))]
+    elif code == PICKLE:
+        body = [pickle.dumps(x)]
+    elif code == COMPRESS_PICKLE:
+        body = [pickle.dumps(_leaf_frames(x, _COMPRESS_IF[code]))]
+    elif code == PICKLE_COMPRESS:
+        body = [_blosc().compress(pickle.dumps(x), typesize=4, cname="lz4")]
     else:
-        raise NotImplementedError(f"Unknown method {method}. Available are {sorted(_METHODS) + sorted(_COMPRESSED.values())}.")
-    return body + [pickle.dumps(dict(**x.metadata))]
+        body = _leaf_frames(x, _COMPRESS_IF[code])
+    return [code] + body + [pickle.dumps(dict(**x.metadata))]
 
 
 def frames(b: Sequence[bytes]) -> Tuple[List[Tuple[str, Optional[np.dtype], Optional[Tuple[int, ...]], Optional[memoryview]]], Dict]:
-    """A raw_bytes message as [(dotted key, dtype, shape, payload view)] + metadata, without touching the payloads."""
-    if bytes(b[0]) != RAW_BYTES:
-        raise ValueError(f"frames() reads raw_bytes messages (code {RAW_BYTES!r}), got {bytes(b[0])!r}")
-    xs = b[1:-1]
+    """A framed message (raw_bytes, raw_compress, compress_pickle, obs_compress, compress_except_policy_state) as
+    [(dotted key, dtype, shape, payload view)] + metadata.  Uncompressed payloads stay views of the received bytes;
+    compressed ones are decompressed once (needs blosc)."""
+    code = bytes(b[0])
+    if code not in _COMPRESS_IF:
+        raise ValueError(f"frames() reads the framed methods {sorted(c.decode() for c in _COMPRESS_IF)}, got {code!r}")
+    codec = _blosc() if code != RAW_BYTES else None  # namedarray.py:168-171: imported up front for codes 0004-0008
+    xs = pickle.loads(bytes(b[1])) if code == COMPRESS_PICKLE else b[1:-1]
     if len(xs) % 4 != 0:
-        raise ValueError(f"raw_bytes body has {len(xs)} frames, not a multiple of 4")
+        raise ValueError(f"framed body has {len(xs)} frames, not a multiple of 4")
+    compress_if = _COMPRESS_IF[code]
     out = []
     for i in range(len(xs) // 4):
         key = bytes(xs[4 * i]).decode("ascii")
@@ -91,7 +125,10 @@ def frames(b: Sequence[bytes]) -> Tuple[List[Tuple[str, Optional[np.dtype], Opti
             continue
         dtype = np.dtype(bytes(xs[4 * i + 1]).decode("ascii"))
         shape = tuple(ast.literal_eval(bytes(xs[4 * i + 2]).decode("ascii")))
-        payload = memoryview(xs[4 * i + 3]).cast("B")
+        buf = xs[4 * i + 3]
+        if compress_if(key):
+            buf = codec.decompress(bytes(buf))
+        payload = memoryview(buf).cast("B")
         need = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
         if payload.nbytes != need:
             raise ValueError(f"leaf {key}: payload of {payload.nbytes} bytes, dtype {dtype} x shape {shape} needs {need}")
@@ -100,23 +137,22 @@ def frames(b: Sequence[bytes]) -> Tuple[List[Tuple[str, Optional[np.dtype], Opti
 
 
 def loads(b: Sequence[bytes]) -> NamedArray:
-    """namedarray.py:166-218: back to a NamedArray of (read-only, zero-copy) numpy arrays."""
+    """namedarray.py:166-218: back to a NamedArray of (read-only, zero-copy where uncompressed) numpy arrays."""
     code = bytes(b[0])
-    if code in _COMPRESSED:
-        raise ModuleNotFoundError(f"method {_COMPRESSED[code]!r} needs the `blosc` codec, which is not installed")
     if code == PICKLE_DICT:
         _, values = pickle.loads(bytes(b[1]))
         x = from_dict(values)
-        metadata = pickle.loads(bytes(b[-1]))
     elif code == PICKLE:
         x = pickle.loads(bytes(b[1]))
-        metadata = pickle.loads(bytes(b[-1]))
-    elif code == RAW_BYTES:
-        entries, metadata = frames(b)
+    elif code == PICKLE_COMPRESS:
+        x = pickle.loads(_blosc().decompress(bytes(b[1])))
+    elif code in _COMPRESS_IF:
+        entries, _ = frames(b)
         x = from_flattened([(k, None if dt is None else np.frombuffer(p, dtype=dt).reshape(shape))
                             for k, dt, shape, p in entries])
     else:
         raise NotImplementedError(f"Unknown NamedArrayEncodingMethod value {code!r}.")
+    metadata = pickle.loads(bytes(b[-1]))
     x.metadata.clear()
     x.register_metadata(**metadata)
     return x

@@ -9,7 +9,17 @@ from oracle import ref_loader
 from srl_b200 import wire
 from srl_b200.api import AnalyzedResult, SampleBatch
 from srl_b200.namedarray import NamedArray, flatten
-from tests.util import load_golden
+from tests.util import StandInBlosc, load_golden
+
+FRAMED = ["raw_bytes", "raw_compress", "compress_pickle", "obs_compress", "compress_except_policy_state"]
+
+
+@pytest.fixture
+def blosc_stand_in(monkeypatch):
+    """`blosc` is not installed here; the compressed fixtures were written by the unmodified reference with this
+    stand-in codec under that name (oracle/make_golden.py::gen_wire)."""
+    import sys
+    monkeypatch.setitem(sys.modules, "blosc", StandInBlosc)
 
 
 def _message(fx, method):
@@ -25,12 +35,14 @@ def _same_sample(fx):
                        done=leaf("done"), truncated=None, action=NamedArray(x=leaf("action.x")), reward=leaf("reward"),
                        analyzed_result=AnalyzedResult(value=leaf("analyzed_result.value"),
                                                       log_probs=leaf("analyzed_result.log_probs")),
+                       policy_state=NamedArray(hx=leaf("policy_state.hx")),
                        policy_version_steps=leaf("policy_version_steps"), sampling_weight=2.5)
 
 
-def test_raw_bytes_decode_of_reference_message():
+@pytest.mark.parametrize("method", FRAMED)
+def test_framed_decode_of_reference_message(method, blosc_stand_in):
     fx = load_golden("wire.npz")
-    x = wire.loads(_message(fx, "raw_bytes"))
+    x = wire.loads(_message(fx, method))
     got = dict(flatten(x))
     for k in [k[5:] for k in fx if k.startswith("leaf.")]:
         ref = fx[f"leaf.{k}"]
@@ -42,13 +54,28 @@ def test_raw_bytes_decode_of_reference_message():
     assert x.metadata == dict(sampling_weight=2.5)
 
 
-def test_raw_bytes_encode_is_byte_identical_to_reference():
+@pytest.mark.parametrize("method", FRAMED)
+def test_framed_encode_is_byte_identical_to_reference(method, blosc_stand_in):
+    """Same frames in the same order; exactly the reference's choice of compressed leaves ('obs' in key /
+    'policy_state' not in key / all / none, namedarray.py:141-156) -- the stand-in codec is deterministic, so equality
+    of the payload bytes means the same leaves went through it."""
     fx = load_golden("wire.npz")
-    ours = wire.dumps(_same_sample(fx), "raw_bytes")
-    ref = _message(fx, "raw_bytes")
+    ours = wire.dumps(_same_sample(fx), method)
+    ref = _message(fx, method)
     assert len(ours) == len(ref)
-    assert ours[:-1] == ref[:-1]  # code + four frames per leaf, in the reference's (sorted) leaf order
+    if method == "compress_pickle":
+        assert pickle.loads(ours[1]) == pickle.loads(ref[1])
+    else:
+        assert ours[:-1] == ref[:-1]
     assert pickle.loads(ours[-1]) == pickle.loads(ref[-1])
+    payloads = pickle.loads(ours[1]) if method == "compress_pickle" else ours[1:-1]
+    marked = {bytes(payloads[i]).decode() for i in range(0, len(payloads), 4)
+              if bytes(payloads[i + 3]).startswith(StandInBlosc.MARK)}
+    present = {k[5:] for k in fx if k.startswith("leaf.")}
+    want = {"raw_bytes": set(), "raw_compress": present, "compress_pickle": present,
+            "obs_compress": {k for k in present if "obs" in k},
+            "compress_except_policy_state": {k for k in present if "policy_state" not in k}}[method]
+    assert marked == want
 
 
 def test_pickle_dict_decode_of_reference_message():
@@ -59,8 +86,9 @@ def test_pickle_dict_decode_of_reference_message():
     assert got["truncated"] is None and x.metadata == dict(sampling_weight=2.5)
 
 
-@pytest.mark.parametrize("method", ["raw_bytes", "pickle_dict", "pickle"])
-def test_round_trip(method):
+@pytest.mark.parametrize("method", ["raw_bytes", "pickle_dict", "pickle", "raw_compress", "compress_pickle",
+                                    "pickle_compress", "obs_compress", "compress_except_policy_state"])
+def test_round_trip(method, blosc_stand_in):
     fx = load_golden("wire.npz")
     x = _same_sample(fx)
     y = wire.loads(wire.dumps(x, method))
@@ -85,16 +113,36 @@ def test_frames_are_zero_copy_views_and_checked():
         wire.frames(msg[:3] + msg[4:])
 
 
-def test_compressed_methods_fail_loudly():
-    """blosc is a third-party codec absent here; the reference fails on `import blosc` the same way."""
+def test_compressed_methods_need_blosc_like_the_reference():
+    """Without the third-party codec the compressed methods raise at the import, exactly where the reference's do
+    (namedarray.py:101-103,168-171); unknown codes / method names raise NotImplementedError (namedarray.py:158-160,209-211)."""
+    import importlib.util
+    if importlib.util.find_spec("blosc") is not None:
+        pytest.skip("blosc is installed here")
     fx = load_golden("wire.npz")
     for code in (b"0004", b"0005", b"0006", b"0007", b"0008"):
         with pytest.raises(ModuleNotFoundError):
             wire.loads([code] + _message(fx, "raw_bytes")[1:])
     with pytest.raises(ModuleNotFoundError):
+        wire.frames(_message(fx, "obs_compress"))
+    with pytest.raises(ModuleNotFoundError):
         wire.dumps(_same_sample(fx), "obs_compress")
     with pytest.raises(NotImplementedError):
         wire.loads([b"0042", b""])
+    with pytest.raises(NotImplementedError):
+        wire.dumps(_same_sample(fx), "zstd")
+
+
+def test_frames_of_a_compressed_message_keep_uncompressed_payloads_zero_copy(blosc_stand_in):
+    fx = load_golden("wire.npz")
+    msg = _message(fx, "obs_compress")
+    entries, _ = wire.frames(msg)
+    keys = [k for k, *_ in entries]
+    i = 1 + 4 * keys.index("reward") + 3
+    assert entries[keys.index("reward")][3].obj is msg[i]          # not compressed: a view of the message
+    assert entries[keys.index("obs.frame")][3].obj is not msg[1 + 4 * keys.index("obs.frame") + 3]  # decompressed copy
+    with pytest.raises(ValueError):  # pickle-bodied methods carry no leaf frames
+        wire.frames(_message(fx, "pickle_dict"))
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="live reference only in the build container")

@@ -43,3 +43,25 @@ def assert_grad_close(g, ref, mask_sum, tol=TOL, what=""):
     """Gradients of a masked MEAN are O(1/M); compare them on the O(1) scale (g * M) so the stated
     tolerance is meaningful instead of vacuous."""
     assert_close_ref(to_np(g).astype(np.float64) * mask_sum, to_np(ref).astype(np.float64) * mask_sum, tol, what)
+
+
+class StandInBlosc:
+    """A stand-in for the third-party `blosc` module (absent here): same call signatures as the reference uses
+    (`compress(bytes, typesize=4, cname='lz4')`, `decompress(bytes)`, base/namedarray.py:126,185), zlib inside and a marker
+    in front so that an uncompressed payload can never pass for a compressed one.  Injected as sys.modules['blosc'] both
+    when oracle/make_golden.py lets the UNMODIFIED reference write the compressed fixtures and when the tests read them:
+    what gets pinned is the framing (which leaves are compressed, order, None leaves), not the codec."""
+    MARK = b"STANDIN-BLOSC:"
+
+    @classmethod
+    def compress(cls, data, typesize=8, clevel=9, shuffle=1, cname="blosclz"):
+        import zlib
+        assert typesize == 4 and cname == "lz4", "the reference always passes typesize=4, cname='lz4'"
+        return cls.MARK + zlib.compress(bytes(data), 1)
+
+    @classmethod
+    def decompress(cls, data):
+        import zlib
+        data = bytes(data)
+        assert data.startswith(cls.MARK), "payload was not written by compress()"
+        return zlib.decompress(data[len(cls.MARK):])
