@@ -12,6 +12,9 @@ namespace loss {
 #ifndef SRL_LOSS_UNROLL
 #define SRL_LOSS_UNROLL 1
 #endif
+#ifndef SRL_LOSS_NORM_FP32
+#define SRL_LOSS_NORM_FP32 0  // 1: advantage normalisation in float32 (a measurement variant; default float64 as the reference)
+#endif
 #ifndef SRL_LOSS_MIN_BLOCKS
 #define SRL_LOSS_MIN_BLOCKS 3  // CTAs of 256 threads per SM the register allocator must leave room for
 #endif
@@ -288,7 +291,12 @@ __device__ __forceinline__ void element(const LossHyperDev& h, const Uniforms& u
   const float ratio = expf(nl - ol);
   // masked_normalization (utils.py:38-67) in float64, cast to float at the end; masked entries are centred
   // zeros there (x = adv * mask) and here
+#if SRL_LOSS_NORM_FP32
+  // build variant for profiles/ (profiles/r1d_notes.md, candidate 2): ~1e-7 relative instead of the reference's float64
+  const float nadv = (ad - static_cast<float>(u.mean)) * static_cast<float>(u.rdenom);
+#else
   const float nadv = static_cast<float>(div_by(__dsub_rn(static_cast<double>(ad), u.mean), u.denom, u.rdenom));
+#endif
   const float s1 = ratio * nadv;
   const float s2 = fminf(fmaxf(ratio, h.clip_lo), h.clip_hi) * nadv;
   const bool in_clip = ratio >= h.clip_lo && ratio <= h.clip_hi;
