@@ -8,6 +8,7 @@ echo "## two-lane kernel: bit-equality of the gradients with the four-lane kerne
 SRL_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q 2>&1 | tail -3
 python -m srl_b200.build --out $PWD/srl_b200/libsrl_v_nc2.so -- -DSRL_LOSS_POLICY_NC=1 -DSRL_LOSS_UNROLL=2 > /dev/null
 python -m srl_b200.build --out $PWD/srl_b200/libsrl_v_norm32.so -- -DSRL_LOSS_NORM_FP32=1 > /dev/null
+python -m srl_b200.build --out $PWD/srl_b200/libsrl_v_mb4.so -- -DSRL_LOSS_MIN_BLOCKS=4 > /dev/null  # two-lane kernel at 64 registers: 32 warps per SM, 116 B of spills
 run() {  # tag, library, extra env
   for c in ${CFGS:-cfg2_atari_large cfg5_hns_scale}; do
     env SRL_B200_LIB=$PWD/srl_b200/$2 $3 python bench.py --config $c --steps 400 --warmup 10 --e2e-steps 3 --no-cpu-baseline 2> gpurun_out/k4v.err |
@@ -26,5 +27,6 @@ for rep in 1 2; do
   run nc_unroll2 libsrl_v_nc2.so SRL_X=0
   run lanes2+nc_unroll2 libsrl_v_nc2.so SRL_LOSS_LANES=2
   run norm_fp32 libsrl_v_norm32.so SRL_X=0
+  CFGS=cfg2_atari_large run lanes2+64regs libsrl_v_mb4.so SRL_LOSS_LANES=2
 done
-rm -f srl_b200/libsrl_v_nc2.so srl_b200/libsrl_v_norm32.so
+rm -f srl_b200/libsrl_v_nc2.so srl_b200/libsrl_v_norm32.so srl_b200/libsrl_v_mb4.so
