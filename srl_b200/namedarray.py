@@ -33,7 +33,16 @@ class NamedArray:
 
     # -- metadata (not sliced, not aggregated; base/namedarray.py:262-279) -------------------------
     def register_metadata(self, **kw) -> None:
+        for k in self._fields:
+            if k in kw:  # base/namedarray.py:292-294
+                raise KeyError("Keys of metadata should be different from data fields!")
         self._metadata.update(kw)
+
+    def pop_metadata(self, key):
+        return self._metadata.pop(key)
+
+    def clear_metadata(self) -> None:
+        self._metadata.clear()
 
     @property
     def metadata(self) -> Dict[str, Any]:

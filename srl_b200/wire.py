@@ -153,6 +153,6 @@ def loads(b: Sequence[bytes]) -> NamedArray:
     else:
         raise NotImplementedError(f"Unknown NamedArrayEncodingMethod value {code!r}.")
     metadata = pickle.loads(bytes(b[-1]))
-    x.metadata.clear()
+    x.clear_metadata()  # namedarray.py:213-215
     x.register_metadata(**metadata)
     return x

@@ -89,8 +89,10 @@ def test_pickle_dict_decode_of_reference_message():
 @pytest.mark.parametrize("method", ["raw_bytes", "pickle_dict", "pickle", "raw_compress", "compress_pickle",
                                     "pickle_compress", "obs_compress", "compress_except_policy_state"])
 def test_round_trip(method, blosc_stand_in):
+    """base/tests/namedarray_test.py:261-284 (test_serialization): every encoding method round-trips data and metadata."""
     fx = load_golden("wire.npz")
     x = _same_sample(fx)
+    x.register_metadata(a=1, b="xxx")
     y = wire.loads(wire.dumps(x, method))
     for (ka, va), (kb, vb) in zip(flatten(x), flatten(y)):
         assert ka == kb and ((va is None and vb is None) or np.array_equal(np.asarray(va).astype(vb.dtype), vb))
@@ -153,3 +155,14 @@ def test_live_reference_decodes_our_raw_bytes():
     got = dict(R.namedarray.flatten(back))
     assert np.array_equal(got["obs.frame"], fx["leaf.obs.frame"]) and got["truncated"] is None
     assert np.array_equal(got["analyzed_result.log_probs"], fx["leaf.analyzed_result.log_probs"])
+
+
+def test_metadata_keys_must_differ_from_fields():
+    """base/tests/namedarray_test.py:286-289 (test_metadata)."""
+    x = NamedArray(obs=np.zeros(3), reward=np.zeros(3))
+    with pytest.raises(KeyError):
+        x.register_metadata(obs=3)
+    x.register_metadata(a=1, b="xxx")
+    assert x.metadata == dict(a=1, b="xxx") and x.pop_metadata("a") == 1 and x.metadata == dict(b="xxx")
+    x.clear_metadata()
+    assert x.metadata == {}
