@@ -44,7 +44,11 @@ int srl_abi_version(void);
  * launched with cudaLaunchAttributeProgrammaticStreamSerialization, so that on ONE stream the order
  * srl_philox_perm -> srl_gae_scan -> srl_ppo_loss_* overlaps: the scan starts beside the permutation kernel, and the loss
  * kernel's CTAs become resident and pull their policy-side rows into L2 while the scan still runs; each kernel waits
- * (griddepcontrol.wait) before it touches anything an earlier kernel writes, so results do not change. */
+ * (griddepcontrol.wait) before it touches anything an earlier kernel writes, so results do not change.
+ * The scan is launched programmatically ONLY directly behind srl_philox_perm on the same stream and thread (the library
+ * notes that launch): it waits for its predecessor only at its end, which is correct exactly when the predecessor writes
+ * nothing the scan reads.  Behind any other kernel it is an ordinary launch.  The loss kernels wait first and are always
+ * launched programmatically. */
 int srl_pdl_enabled(void);
 int srl_set_pdl(int on);
 /* Fills SM count and compute capability of the current device. */

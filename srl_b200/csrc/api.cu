@@ -33,6 +33,24 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+namespace {
+thread_local cudaStream_t g_perm_stream = nullptr;
+thread_local bool g_perm_noted = false;
+}  // namespace
+
+void pdl_note_perm(cudaStream_t st) {
+  g_perm_stream = st;
+  g_perm_noted = true;
+}
+
+bool pdl_take_perm(cudaStream_t st) {
+  const bool yes = g_perm_noted && g_perm_stream == st;
+  g_perm_noted = false;
+  return yes;
+}
+
+void pdl_forget() { g_perm_noted = false; }
+
 int sm_count() {
   static int cached[64];
   int dev = 0;

@@ -35,6 +35,13 @@ int sm_count();  // cached per device
 // pdl_launch_dependents() (or exited) -- and must execute pdl_wait() before it touches anything the earlier kernel
 // writes.  Off: plain launches (the device-side instructions are no-ops then).
 bool pdl_enabled();
+// The scan may only start ahead of the kernel before it when that kernel is this library's permutation kernel (which
+// writes nothing the scan reads): srl_philox_perm notes its launch, the scan's launcher takes the note (once).  Behind
+// anything else the scan is an ordinary launch -- it executes griddepcontrol.wait only at its end, so a programmatic
+// launch behind a kernel that PRODUCES its inputs would read them without a visibility guarantee.
+void pdl_note_perm(cudaStream_t st);
+bool pdl_take_perm(cudaStream_t st);
+void pdl_forget();
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
@@ -63,7 +70,8 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <class... KArgs, class... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+inline cudaError_t launch_maybe_pdl(bool programmatic, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                    cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -73,8 +81,20 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (programmatic && pdl_enabled()) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+// a kernel that waits (pdl_wait) BEFORE it reads anything: always safe to launch programmatically (the loss kernels)
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  pdl_forget();
+  return launch_maybe_pdl(true, kern, grid, block, smem, st, static_cast<Args&&>(args)...);
+}
+// the scan kernels (pdl_wait only at their end): programmatic only directly behind srl_philox_perm on the same stream
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl_scan(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   Args&&... args) {
+  return launch_maybe_pdl(pdl_take_perm(st), kern, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -257,7 +257,7 @@ int launch_un(const GaeParams& p, cudaStream_t st) {
     opted_in[dev] = true;
   }
   const int grid = (p.N + LW - 1) / LW;
-  SRL_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, st, p));
+  SRL_CUDA(launch_pdl_scan(kern, dim3(grid), dim3(kThreads), smem, st, p));
   return SRL_OK;
 }
 

@@ -349,7 +349,7 @@ int launch(const GaeTmaParams& q, cudaStream_t st) {
     opted_in[dev] = true;
   }
   const int grid = (q.p.N + LPW - 1) / LPW;
-  SRL_CUDA(launch_pdl(kern, dim3(grid), dim3(LPW), smem, st, q));
+  SRL_CUDA(launch_pdl_scan(kern, dim3(grid), dim3(LPW), smem, st, q));
   return SRL_OK;
 }
 

@@ -290,7 +290,7 @@ int launch_ws(const WsParams& q, cudaStream_t st) {
     opted_in[dev] = true;
   }
   const int grid = (q.p.N + 31) / 32;
-  SRL_CUDA(launch_pdl(kern, dim3(grid), dim3(32 * (2 + kW)), smem, st, q));
+  SRL_CUDA(launch_pdl_scan(kern, dim3(grid), dim3(32 * (2 + kW)), smem, st, q));
   return SRL_OK;
 }
 

@@ -113,6 +113,7 @@ extern "C" int srl_philox_perm(uint64_t seed, uint32_t epoch, int n_epochs, int 
   philox_perm_kernel<<<dim3(grid, n_epochs), threads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<uint32_t>(seed & 0xffffffffull), static_cast<uint32_t>(seed >> 32), epoch, n_env, group, bits, out);
   SRL_CUDA(cudaGetLastError());
+  pdl_note_perm(static_cast<cudaStream_t>(stream));  // a scan launched next on this stream may start beside this kernel
   return SRL_OK;
 }
 

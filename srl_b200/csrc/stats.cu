@@ -220,6 +220,7 @@ int launch_group_stats(const char* fn, const double* lane_part, int N, const int
     ws.ticket = static_cast<unsigned int*>(workspace);
     ws.partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + ticket_bytes(rows));
   }
+  pdl_forget();
   group_stats_kernel<<<dim3(max_chunks, rows), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(lane_part, N, idx, per,
                                                                                                  whole_first, out, ws, fx);
   SRL_CUDA(cudaGetLastError());
