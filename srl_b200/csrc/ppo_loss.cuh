@@ -23,14 +23,6 @@ constexpr int kMaxGrid = 2048;                // partial rows per workspace slot
 constexpr int kNumSums = 8;
 constexpr size_t kPartialsOffset = 64;
 constexpr int kMaxBatch = SRL_MAX_LOSS_BATCH;
-// SRL_LOSS_EARLY_ROW=1: the first row's loads are issued ahead of the statistics prologue and every later row right after
-// the stores of the row before it.  Built and measured on B200 (profiles/r1d_notes.md): it loses -- cfg2 26.7 -> 33.0 us,
-// cfg5 79.7 -> 93.4 us, 212 instead of 148 bytes of spills at the 80-register cap (the row's 28 load registers stay live
-// across the loop's back edge and through the prologue) -- so it is compiled out.
-#ifndef SRL_LOSS_EARLY_ROW
-#define SRL_LOSS_EARLY_ROW 0
-#endif
-constexpr bool kEarlyRow = SRL_LOSS_EARLY_ROW != 0;
 constexpr int kFlushRows = 8;  // rows whose masked terms are summed in fp32 before they enter the float64 sums
 
 // First 64 bytes of a workspace slot; the partial rows [n_rows][8] f64 follow.
@@ -691,8 +683,8 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
         }
       }
     };
-    // kEarlyRow (off, see the top of this file): first row's loads before the statistics prologue
-    if (kEarlyRow && active && r0 < r1) load_row();
+    // (Issuing the first row's loads here, ahead of the statistics prologue, and each later row right after the stores of
+    // the row before it was built and measured: it loses, 26.7 -> 33.0 us at cfg2 -- profiles/r1d_notes.md.)
     if (!have_u) {
       if (s.lane_part != nullptr)
         u = self_uniforms<LANES>(s.lane_part, s.lane_part_n, c, active, h.adv_eps, mask_sum);
@@ -703,7 +695,7 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
     if (active) {
 #pragma unroll kLossUnroll
       for (int t = r0; t < r1; ++t) {
-        if (!kEarlyRow) load_row();
+        load_row();
         float glp[LANES], gv[LANES], ge[LANES];
 #pragma unroll
         for (int q = 0; q < LANES; ++q)
@@ -729,7 +721,6 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
         nl_row += s.ld_pol, vp_row += s.ld_pol, en_row += s.ld_pol;
         glp_row += s.ld_grad, gv_row += s.ld_grad, ge_row += s.ld_grad;
         ob += s.ld_smp;
-        if (kEarlyRow && t + 1 < r1) load_row();
       }
     }
   }
