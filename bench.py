@@ -326,7 +326,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     pdl_was = ops.set_pdl(False)
     g_loss = graph_of(lambda: hp._run_losses(pol_dev))
     lf = hp.leaf
-    pack_kw = dict(old_logp=lf["old_logp"], pack=hp.pack) if hp.pack is not None else {}
+    pack_kw = dict(old_logp=lf["old_logp"], pack=hp.pack, lane_aos=hp.lane_aos) if hp.pack is not None else {}
     g_gae = graph_of(lambda: ops.gae_scan(lf["reward"], lf["value"], lf["done"], lf["truncated"], lf["on_reset"], cfg.gamma,
                                           cfg.lmbda, row_lo=hp.row_lo, row_hi=hp.row_hi,
                                           popart_mean_std=hp.popart_mean_std(), adv=hp.adv, ret=hp.ret,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SRL_B200_ABI_VERSION 4
+#define SRL_B200_ABI_VERSION 5
 
 typedef void* srl_stream_t; /* cudaStream_t */
 
@@ -69,16 +69,21 @@ int srl_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   A[t]   = d[t] + m[t] * A[t+1], A[L-1] = 0 ;  adv = float(A) ;  ret = adv + v'[t]   (fp32 add)
  *   adv[L-1] = ret[L-1] = 0 (padding row).
  *
- * pack (optional, may be NULL; needs old_logp): [L, N, 4] float32, 16-byte aligned -- the sample side of the loss
- * as ONE 16-byte item per transition, {old_logp[t], value[t] (as stored in the sample), ret[t],
- * mask[t] ? adv[t] : NaN} with mask[t] = 1 - on_reset[t+1] (row L-1: NaN).  A minibatch that gathers lanes
- * through a permutation (srl_ppo_loss_fwd_bwd_batched, `pack`) then issues one 128-bit load per transition
- * instead of five narrow ones.
+ * pack (optional, may be NULL; needs old_logp): the sample side of the loss as ONE 16-byte item per transition,
+ * {old_logp[t], value[t] (as stored in the sample), ret[t], mask[t] ? adv[t] : NaN} with mask[t] = 1 - on_reset[t+1]
+ * (row L-1: NaN), the two rows of a row pair next to each other: item (t, lane) is float4 number
+ * ((t / 2) * N + lane) * 2 + t % 2, i.e. float32 [ceil(L / 2), N, 2, 4] (so the buffer holds L + L % 2 rows), 32-byte
+ * aligned.  A minibatch that gathers lanes through a permutation (srl_ppo_loss_fwd_bwd_batched, `pack`) then issues one
+ * 256-bit load per lane and ROW PAIR -- every 32-byte sector it touches is used whole -- instead of five narrow loads per
+ * transition.
  *
  * lane_part (optional, may be NULL): [SRL_LANE_PART][N] float64 per-lane sums over the loss rows
  * t in [row_lo, row_hi) with mask[t] = 1 - on_reset[t+1] (mappo.py:259-261):
  *   0: sum mask   1: sum adv*mask   2: sum (adv*mask)^2   3: sum ret*mask   4: sum (ret*mask)^2
  *   5: sum done[t]   6: sum truncated[t]   7: reserved (0)
+ * lane_aos (optional, may be NULL; needs lane_part): [N][4] float64, 32-byte aligned: rows 0..2 of lane_part once more, one
+ * 32-byte item per lane {sum mask, sum adv*mask, sum (adv*mask)^2, 0} -- the form in which the loss kernel adds the
+ * statistics of a permuted minibatch itself (one 256-bit gather per lane; srl_ppo_loss_fwd_bwd_batched, `lane_aos`).
  * ------------------------------------------------------------------------------------------ */
 #define SRL_LANE_PART 8
 
@@ -95,7 +100,8 @@ int srl_gae_scan(const float* reward,          /* [L, N]; row L-1 is ignored    
                  float* adv,        /* [L, N] out */
                  float* ret,        /* [L, N] out */
                  double* lane_part, /* [SRL_LANE_PART, N] out or NULL */
-                 float* pack,       /* [L, N, 4] out or NULL */
+                 double* lane_aos,  /* [N, 4] out or NULL */
+                 float* pack,       /* [ceil(L/2), N, 2, 4] out or NULL */
                  srl_stream_t stream);
 
 /* The general form of the same scan: everything modules.gae_trace (legacy/algorithm/modules/gae.py:8-97) accepts
@@ -245,12 +251,13 @@ int srl_ppo_loss_fwd_bwd(
 /* Several minibatches of ONE shape in one launch (a PPO step runs epochs x minibatches of them; launched one by
  * one each is a ~3 MB kernel that cannot fill 148 SMs).  Every problem carries its own policy-side tensors,
  * permutation slice, statistics rows, gradient tensors, outputs and workspace slot; the sample side is shared.
- * The sample side is either the five leaves of srl_ppo_loss_fwd_bwd (pack == NULL) or K2's pack
- * ([T, N, 4] float32, pointer already offset to the first loss row; the leaf pointers may then be NULL).
- * Either every problem has a lane_idx or none has.  n_problems > SRL_MAX_LOSS_BATCH is split into several launches.
- * lane_part != NULL (K2's [SRL_LANE_PART, lane_part_n] table; one GPU, no PopArt, n <= 1024 lanes): every CTA adds the
+ * The sample side is either the five leaves of srl_ppo_loss_fwd_bwd (pack == NULL) or K2's pack (the BASE of the buffer
+ * srl_gae_scan wrote, ld_smp = its N lanes, pack_row_lo = the absolute row of loss row 0; the leaf pointers may then be
+ * NULL).  Either every problem has a lane_idx or none has.  n_problems > SRL_MAX_LOSS_BATCH is split into several launches.
+ * lane_aos != NULL (K2's [N][4] table; pack form with lane indices, one GPU, no PopArt, even n <= 1024): every CTA adds the
  * per-lane sums of ITS minibatch's lanes itself and the problems' norm_stats / local_stats are ignored (may be NULL) --
- * no srl_group_stats launch between K2 and the loss. */
+ * no srl_group_stats launch between K2 and the loss.
+ * Gradient tensors must not alias the policy-side inputs (the kernels prefetch inputs of later rows before they store). */
 #define SRL_MAX_LOSS_BATCH 32
 typedef struct srl_loss_problem {
   const float* new_logp;     /* [T, n], row stride ld_pol */
@@ -270,7 +277,7 @@ typedef struct srl_loss_problem {
 int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems_host, int n_problems, int64_t ld_pol,
                                  int64_t ld_grad, const float* old_logp, const float* old_value, const float* ret,
                                  const float* adv, const uint8_t* on_reset_next, int64_t ld_smp, const float* pack,
-                                 const double* lane_part, int lane_part_n, int T, int n,
+                                 int pack_row_lo, const double* lane_aos, int T, int n,
                                  const double* popart_mean_std, const srl_ppo_hyper* hyper,
                                  size_t workspace_bytes_per_slot, srl_stream_t stream);
 

@@ -334,6 +334,86 @@ def gen_wire(R):
     return sorted(k for k in out if k.startswith("leaf."))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# A10: the step orchestration.  The UNMODIFIED MultiAgentPPO.step (mappo.py:219-328) driven on CPU through the host
+# stand-in of the prefetcher (ref_loader._HostPrefetch keeps the one-call delay), with a tiny policy (tests/doubles.py;
+# its PopArt head is the reference's own class here).  What these fixtures pin: the prefetch delay, the epoch loop,
+# tail_len (:243), GAE before PopArt before the loss (:249-266), the optimizer step per epoch, stats averaged over the
+# epochs (:293-303), entropy-coefficient decay (:310-311), the info aggregation (:317-324), frames, the version, and the
+# adv / ret written back into the host sample (:254-257).
+# ---------------------------------------------------------------------------------------------------------------------
+TRAINER_OBS_DIM, TRAINER_ACTIONS = 6, 5
+TRAINER_CASES = {
+    "plain": (dict(T=12, B=16, p_end=0.08),
+              dict(clip_value=True, dual_clip=False, value_loss="huber", value_loss_config=dict(delta=10.0),
+                   value_loss_weight=1.0, ppo_epochs=2, entropy_decay_per_steps=2, entropy_bonus_decay=0.5)),
+    "popart": (dict(T=10, B=6, A=3, p_end=0.1, lmbda=0.95),
+               dict(gae_lambda=0.95, dual_clip=True, value_loss="huber", value_loss_config=dict(delta=10.0), popart=True,
+                    ppo_epochs=2, max_grad_norm=0.5)),
+    "vtrace": (dict(T=9, B=8, p_end=0.1), dict(vtrace=True, dual_clip=False)),
+    "boot_burn": (dict(T=9, B=8, bootstrap_steps=3, burn_in_steps=2, p_end=0.1),
+                  dict(bootstrap_steps=3, burn_in_steps=2, value_loss="smoothl1", popart=True, ppo_epochs=3,
+                       recompute_adv_among_epochs=True)),
+}
+
+
+def trainer_sample_arrays(shape_kw, seed):
+    """The leaves of one synthetic sample of a trainer fixture (also what the tests rebuild their samples from)."""
+    cfg = synth.PathConfig("trainer_fixture", **shape_kw)
+    s = synth.make_sample_scalars(cfg, seed)
+    rng = np.random.default_rng(seed + 99)
+    lead = s["value"].shape[:-1]
+    s["obs_vec"] = rng.standard_normal(lead + (TRAINER_OBS_DIM,)).astype(np.float32)
+    s["action_x"] = rng.integers(0, TRAINER_ACTIONS, lead + (1,)).astype(np.float32)
+    s["info_episode_return"] = rng.standard_normal(lead + (1,)).astype(np.float32)
+    s["info_mask"] = (rng.random(lead + (1,)) < 0.1).astype(np.float32)
+    return cfg, s
+
+
+def gen_trainer(R):
+    import json
+    from tests.doubles import TinyActorCriticPolicy
+    NA = R.namedarray.NamedArray
+    n_calls = 4  # the first call only primes the prefetcher
+    written = []
+    for name, (shape_kw, kw) in TRAINER_CASES.items():
+        cfg = synth.PathConfig("trainer_fixture", **shape_kw)
+        kw = dict(kw, discount_rate=cfg.gamma, optimizer="sgd", optimizer_config=dict(lr=0.05))
+        pol = TinyActorCriticPolicy(TRAINER_OBS_DIM, TRAINER_ACTIONS, device="cpu", popart=kw.get("popart", False), seed=3,
+                                    popart_head_cls=R.popart.PopArtValueHead)
+        out = {"kwargs_json": np.array(json.dumps(kw)), "shape_json": np.array(json.dumps(shape_kw)),
+               "n_calls": np.array(n_calls)}
+        for k, v in pol.net.state_dict().items():
+            out[f"init/{k}"] = v.detach().cpu().numpy().copy()
+        tr = R.mappo.MultiAgentPPO(pol, **kw)
+        samples = []
+        for it in range(n_calls):
+            _, a = trainer_sample_arrays(shape_kw, seed=10 + it)
+            for k, v in a.items():
+                out[f"call{it}/in/{k}"] = v.copy()
+            sb = R.trainer.SampleBatch(obs=NA(vec=a["obs_vec"]), on_reset=a["on_reset"], done=a["done"],
+                                       truncated=a["truncated"], action=NA(x=a["action_x"]), reward=a["reward"],
+                                       info=NA(episode_return=a["info_episode_return"]), info_mask=a["info_mask"],
+                                       analyzed_result=NA(value=a["value"], log_probs=a["old_logp"], adv=None, ret=None))
+            samples.append(sb)
+            res = tr.step(sb)
+            out[f"call{it}/step"] = np.array(res.step)
+            out[f"call{it}/stat_keys"] = np.array(sorted(res.stats))
+            for k, v in res.stats.items():
+                out[f"call{it}/stat/{k}"] = np.array(float(v), dtype=np.float64)
+            if it >= 1:  # this call trained on the PREVIOUS sample: its host copy now carries adv / ret (or None)
+                prev = samples[it - 1].analyzed_result
+                out[f"call{it}/adv_is_none"] = np.array(prev.adv is None)
+                if prev.adv is not None:
+                    out[f"call{it}/adv"], out[f"call{it}/ret"] = prev.adv.copy(), prev.ret.copy()
+            out[f"call{it}/entropy_bonus_weight"] = np.array(float(tr.entropy_bonus_weight))
+        for k, v in pol.net.state_dict().items():
+            out[f"final/{k}"] = v.detach().cpu().numpy().copy()
+        np.savez_compressed(os.path.join(GOLDEN, f"trainer_{name}.npz"), **out)
+        written.append(name)
+    return written
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
@@ -348,6 +428,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "wire":
         print("wire:", gen_wire(R))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "trainer":  # the step orchestration (added in round 2)
+        print("trainer:", gen_trainer(R))
+        return
     print("gae:", gen_gae(R))
     print("loss:", gen_loss(R))
     gen_masknorm_popart(R)
@@ -356,6 +439,7 @@ def main():
     print("traj_gae:", gen_traj_gae(R))
     print("gae_general:", gen_gae_general(R))
     print("wire:", gen_wire(R))
+    print("trainer:", gen_trainer(R))
     total = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))
     print(f"wrote {len(os.listdir(GOLDEN))} files, {total / 1024:.0f} KiB")
 

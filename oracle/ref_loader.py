@@ -1,9 +1,11 @@
 """TEST INFRASTRUCTURE ONLY -- loads the *unmodified* SRL reference hot-path files by path.
 
 This module exists so that the oracle restatement in ``oracle/ref_math.py`` can be pinned
-against the real reference, and so that ``oracle/make_golden.py`` can generate the fixtures in
-``tests/golden/``.  It only works where ``/root/reference`` exists (the build container); the
-GPU box never imports it.  Nothing under ``srl_b200/`` may import this file.
+against the real reference, so that ``oracle/make_golden.py`` can generate the fixtures in
+``tests/golden/``, and so that ``bench.py --impl reference`` can time the reference's own functions.
+It reads ``/root/reference`` where that exists (the build container) and otherwise the byte-for-byte
+copies ``oracle/stage_ref.py`` staged under ``oracle/_ref/`` (git-ignored; they travel to the GPU box
+like a compiled oracle would).  Nothing under ``srl_b200/`` may import this file.
 
 Why a loader: the reference does not import on Python 3.12 / NumPy 2:
 ``api/config.py:102`` (dataclass mutable defaults), ``api/policy.py:67`` (``np.bool8``),
@@ -21,7 +23,9 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("SRL_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = os.environ.get("SRL_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/legacy/algorithm/ppo/mappo.py") else _STAGED)
 
 
 def available() -> bool:
@@ -44,6 +48,11 @@ def _pkg(dotted: str):
 
 
 _LOADED = None
+_USE_CUDA_PREFETCH = [False]  # set_cuda_prefetch(True): trainers built afterwards use the real PyTorchGPUPrefetcher
+
+
+def set_cuda_prefetch(on: bool) -> None:
+    _USE_CUDA_PREFETCH[0] = bool(on)
 
 
 def load():
@@ -101,11 +110,27 @@ def load():
     _pkg("legacy.algorithm.ppo")
     mappo = _exec_file("legacy.algorithm.ppo.mappo", "legacy/algorithm/ppo/mappo.py")
 
-    class _NoPrefetch:  # PyTorchGPUPrefetcher.__init__ needs CUDA (api/trainer.py:206)
-        def push(self, sample):
-            raise RuntimeError("prefetcher is stubbed on CPU; call the _compute_* methods directly")
+    real_prefetcher = mappo.PyTorchGPUPrefetcher
 
-    mappo.PyTorchGPUPrefetcher = _NoPrefetch
+    class _HostPrefetch:
+        """CPU stand-in for PyTorchGPUPrefetcher (api/trainer.py:199-228), whose constructor needs CUDA (:206): the
+        same contract -- float32 copies of every leaf (:215-217), and a one-call delay: the first push() returns None,
+        every later one returns the PREVIOUS sample (:219-228).  With it the unmodified MultiAgentPPO.step runs on CPU."""
+
+        def __init__(self):
+            self._next = None
+
+        def push(self, sample):
+            import torch
+            nxt = (sample, namedarray.recursive_apply(sample, lambda x: torch.from_numpy(x).float()))
+            cur, self._next = self._next, nxt
+            return cur
+
+    def _prefetcher():
+        import torch
+        return real_prefetcher() if torch.cuda.is_available() and _USE_CUDA_PREFETCH[0] else _HostPrefetch()
+
+    mappo.PyTorchGPUPrefetcher = _prefetcher
 
     _LOADED = types.SimpleNamespace(namedarray=namedarray, policy=api.policy, trainer=api.trainer,
                                     utils=utils, gae=gae, popart=popart, nstep=nstep, mappo=mappo,

@@ -34,6 +34,9 @@ class RefPPOTrainer:
         self.max_grad_norm = kw.get("max_grad_norm")
         self.seed = kw.get("shuffle_seed", 0)
         self.recompute_adv_on_reuse = kw.get("recompute_adv_on_reuse", True)
+        self.recompute_adv_among_epochs = kw.get("recompute_adv_among_epochs", False)
+        self.entropy_decay_per_steps = kw.get("entropy_decay_per_steps", None)
+        self.entropy_bonus_decay = kw.get("entropy_bonus_decay", 0.99)
         opt = dict(adam=torch.optim.Adam, sgd=torch.optim.SGD, rmsprop=torch.optim.RMSprop, adamw=torch.optim.AdamW)
         self.optimizer = opt[kw.get("optimizer", "adam")](policy.parameters(), **kw.get("optimizer_config", {}))
         self.frames, self.steps_done = 0, 0
@@ -101,12 +104,23 @@ class RefPPOTrainer:
                     stats[k] += v
                 stats["grad_norm"] += float(gn)
                 n_loss += 1
+            if self.recompute_adv_among_epochs:  # mappo.py:287-289
+                ts.analyzed_result.adv = ts.analyzed_result.ret = None
+                sample.analyzed_result.adv = sample.analyzed_result.ret = None
         for k in stats:
             stats[k] /= n_loss
         valid = slice(lo, hi)
         stats["done"] = float(ts.done[valid].mean())
         stats["truncated"] = float(ts.truncated[valid].mean())
-        self.policy.inc_version()
+        self.policy.inc_version()  # mappo.py:305-307
+        if self.entropy_decay_per_steps and self.policy.version % self.entropy_decay_per_steps == 0:  # mappo.py:310-311
+            self.hp.entropy_bonus_weight *= self.entropy_bonus_decay
         self.steps_done += 1
         self.frames += int(np.prod(sample.on_reset[valid].shape))
-        return dict(frames=self.frames, **stats), self.policy.version
+        info = {}
+        if getattr(sample, "info_mask", None) is not None and sample.info is not None:  # mappo.py:317-324
+            elapsed = sample.info_mask[valid].sum()
+            if elapsed != 0:
+                info = {k: float((v[valid] * sample.info_mask[valid]).sum() / elapsed) for k, v in flatten(sample.info)
+                        if v is not None}
+        return dict(frames=self.frames, **stats, **info), self.policy.version

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 4) gae_scan_kernel(const GaeParams p
       stg_stream(p.ret + g, r);
       if (PACK) {  // sample side of the loss as one 16-byte item (see include/srl_b200.h)
         const bool keep = t < L - 1 && (sf[(t + 1) * LW + lane] & 4u) == 0u;
-        __stcg(reinterpret_cast<float4*>(p.pack) + g,
+        __stcg(reinterpret_cast<float4*>(p.pack) + pack_index(t, N, col),
                make_float4(sol[t * LW + lane], svr[t * LW + lane], r, keep ? a : __int_as_float(0x7fc00000)));
       }
     }
@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(kThreads, 4) gae_scan_kernel(const GaeParams p
         if (k < 7)
           for (int rr = 0; rr < RPP; ++rr) s += red[(rr * 7 + k) * LW + ln];
         p.lane_part[static_cast<size_t>(k) * N + c2] = s;
+        if (p.lane_aos != nullptr && k < 4) p.lane_aos[static_cast<size_t>(c2) * 4 + k] = k < 3 ? s : 0.0;
       }
     }
   }
@@ -284,7 +285,7 @@ extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8
                             const uint8_t* on_reset, const float* vtrace_new_logp, const float* vtrace_old_logp,
                             const double* popart_mean_std, const float* old_logp, int L, int N, int row_lo,
                             int row_hi, double gamma, double lmbda, double rho, double c, float* adv, float* ret,
-                            double* lane_part, float* pack, srl_stream_t stream) {
+                            double* lane_part, double* lane_aos, float* pack, srl_stream_t stream) {
   using namespace srl;
   SRL_REQUIRE(L >= 2 && N >= 1, SRL_ERR_INVALID_ARG, "srl_gae_scan: need L >= 2 and N >= 1 (got L=%d N=%d)", L, N);
   SRL_REQUIRE(reward && value && done && truncated && on_reset && adv && ret, SRL_ERR_INVALID_ARG,
@@ -293,8 +294,10 @@ extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8
               "srl_gae_scan: vtrace needs both log-prob tensors");
   SRL_REQUIRE(row_lo >= 0 && row_lo <= row_hi && row_hi <= L - 1, SRL_ERR_INVALID_ARG,
               "srl_gae_scan: loss rows [%d, %d) must lie inside [0, L-1=%d]", row_lo, row_hi, L - 1);
-  SRL_REQUIRE(pack == nullptr || (old_logp != nullptr && aligned(pack, 16)), SRL_ERR_INVALID_ARG,
-              "srl_gae_scan: the pack needs old_logp and a 16-byte aligned destination");
+  SRL_REQUIRE(pack == nullptr || (old_logp != nullptr && aligned(pack, 32)), SRL_ERR_INVALID_ARG,
+              "srl_gae_scan: the pack needs old_logp and a 32-byte aligned destination");
+  SRL_REQUIRE(lane_aos == nullptr || (lane_part != nullptr && aligned(lane_aos, 32)), SRL_ERR_INVALID_ARG,
+              "srl_gae_scan: lane_aos needs lane_part and a 32-byte aligned destination");
   const bool vtrace = vtrace_new_logp != nullptr;
   GaeParams p;
   p.reward = reward;
@@ -310,6 +313,7 @@ extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8
   p.adv = adv;
   p.ret = ret;
   p.lane_part = lane_part;
+  p.lane_aos = lane_aos;
   p.L = L;
   p.N = N;
   p.row_lo = row_lo;

@@ -199,7 +199,7 @@ __device__ __forceinline__ void run_stage(const GaeParams& p, const unsigned cha
       if (PACK) {
         const float* sol = reinterpret_cast<const float*>(slot + SL::old_logp);
         const bool keep = EDGE ? (!rn && t < L - 1) : !rn;
-        __stcg(reinterpret_cast<float4*>(p.pack) + gi,
+        __stcg(reinterpret_cast<float4*>(p.pack) + pack_index(t, N, col),
                make_float4(sol[r * LPW + lane], sv[r * LPW + lane], rt, keep ? a[r] : __int_as_float(0x7fc00000)));
       }
     }
@@ -298,6 +298,13 @@ __global__ void __launch_bounds__(LPW) gae_scan_tma_kernel(const __grid_constant
     o[static_cast<size_t>(5) * N] = static_cast<double>(st.dn);
     o[static_cast<size_t>(6) * N] = static_cast<double>(st.tr);
     o[static_cast<size_t>(7) * N] = 0.0;
+    if (p.lane_aos != nullptr) {
+      double* a4 = p.lane_aos + static_cast<size_t>(col) * 4;
+      a4[0] = static_cast<double>(st.cnt);
+      a4[1] = st.s1;
+      a4[2] = st.s2;
+      a4[3] = 0.0;
+    }
   }
   if (lane == 0) pdl_wait();  // scan complete => permutation kernel complete (see gae_scan_ws.cu)
 }

@@ -23,6 +23,13 @@ namespace {
 
 using namespace srl::tma;
 
+__device__ __forceinline__ void st_cg256(float4* p, float a0, float a1, float a2, float a3, float b0, float b1, float b2,
+                                         float b3) {
+  asm volatile("st.global.cg.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3),
+               "f"(b0), "f"(b1), "f"(b2), "f"(b3)
+               : "memory");
+}
+
 constexpr int kR = 16;  // rows per chunk
 // Ring depth kS (template parameter): 3 slots when several CTAs share an SM; kDeep when the batch has at most one CTA per
 // SM anyway (cfg2: 128 lane groups) -- the whole trajectory of up to kDeep * kR rows is requested from HBM at once (one
@@ -218,10 +225,16 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
           const size_t gi = static_cast<size_t>(t) * N + col;
           stg_stream(p.adv + gi, a);
           stg_stream(p.ret + gi, rt);
-          if (PACK)
-            __stcg(reinterpret_cast<float4*>(p.pack) + gi,
-                   make_float4(sol[r * 32 + lane], sv[r * 32 + lane], rt,
-                               (!rn && t < L - 1) ? a : __int_as_float(0x7fc00000)));
+          if (PACK && (r & 1) == 0) {
+            // the pack's row pair (t, t + 1) as ONE 32-byte store: chunks start at even rows, and everything row t + 1
+            // needs (its advantage, v', flags) is in this chunk's slot once the scanner has signalled it
+            const float nan = __int_as_float(0x7fc00000);
+            const float a1 = sa[(r + 1) * 32 + lane];
+            const float rt1 = (t + 1 < L - 1) ? __fadd_rn(a1, svp[(r + 1) * 32 + lane]) : 0.f;
+            const bool keep1 = t + 1 < L - 1 && srs[(r + 2) * 32 + lane] == 0;
+            st_cg256(reinterpret_cast<float4*>(p.pack) + pack_index(t, N, col), sol[r * 32 + lane], sv[r * 32 + lane], rt,
+                     (!rn && t < L - 1) ? a : nan, sol[(r + 1) * 32 + lane], sv[(r + 1) * 32 + lane], rt1, keep1 ? a1 : nan);
+          }
         }
         // loss rows [row_lo, row_hi), mask = 1 - on_reset[t+1]   mappo.py:259-261
         const bool in_rows = t >= p.row_lo && t < p.row_hi;
@@ -268,6 +281,7 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
         if (k < 7)
           for (int ww = 0; ww < kW; ++ww) sum += red[(ww * 7 + k) * 32 + ln];
         p.lane_part[static_cast<size_t>(k) * N + c2] = sum;
+        if (p.lane_aos != nullptr && k < 4) p.lane_aos[static_cast<size_t>(c2) * 4 + k] = k < 3 ? sum : 0.0;
       }
     }
   }

@@ -14,9 +14,10 @@
 //    adjacent lanes (128-bit accesses on the dense policy side) and keeps its four gather indices in
 //    registers for all rows of the tile, so index loads and the run-of-4 test are paid once per tile;
 //  * the sample side comes in one of three forms: dense leaves (whole batch, no permutation), leaves
-//    gathered through lane_idx (any alignment), or K2's `pack` ([T, N] float4 = old_logp, old_value, ret,
-//    adv-or-NaN): one 16-byte gather per element instead of five 1..4-byte ones -- the L1 wavefront count,
-//    which is what bounds a per-lane gather, drops 5x;
+//    gathered through lane_idx (any alignment), or K2's `pack` (float4 = old_logp, old_value, ret, adv-or-NaN per
+//    transition, the two rows of a row pair next to each other): one gather per lane and row pair instead of five
+//    1..4-byte ones per transition -- permuted minibatches of even width run ppo_loss_pair.cu, this file's row-tile
+//    kernel keeps the odd shapes of that form;
 //  * per-element arithmetic is fp32 except the advantage / PopArt normalisation, which stays in float64
 //    (reference: utils.py:38-67,139-144) as subtract + multiply by a correctly rounded reciprocal + one
 //    Newton residual step (3 fp64 instructions instead of a ~25-instruction IEEE division; the quotient is
@@ -200,7 +201,7 @@ extern "C" int srl_ppo_loss_finalize(const void* workspace, size_t slot_bytes, i
 extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, int n_problems, int64_t ld_pol,
                                             int64_t ld_grad, const float* old_logp, const float* old_value,
                                             const float* ret, const float* adv, const uint8_t* on_reset_next,
-                                            int64_t ld_smp, const float* pack, const double* lane_part, int lane_part_n,
+                                            int64_t ld_smp, const float* pack, int pack_row_lo, const double* lane_aos,
                                             int T, int n, const double* popart_mean_std, const srl_ppo_hyper* hyper,
                                             size_t workspace_bytes, srl_stream_t stream) {
   using namespace srl;
@@ -219,14 +220,15 @@ extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, in
     SRL_REQUIRE(!(s.h.clip_value && old_value == nullptr), SRL_ERR_INVALID_ARG,
                 "srl_ppo_loss_fwd_bwd: clip_value needs old_value");
   } else {
-    SRL_REQUIRE(aligned(pack, 16), SRL_ERR_INVALID_ARG, "srl_ppo_loss_fwd_bwd: pack must be 16-byte aligned");
+    SRL_REQUIRE(aligned(pack, 32) && pack_row_lo >= 0, SRL_ERR_INVALID_ARG,
+                "srl_ppo_loss_fwd_bwd: pack must be 32-byte aligned and pack_row_lo >= 0");
   }
   bool any_idx = false, all_idx = true;
   bool dense_ok = (n % 4 == 0) && (ld_pol % 4 == 0) && (ld_grad % 4 == 0);
   for (int k = 0; k < n_problems; ++k) {
     const srl_loss_problem& q = problems[k];
     SRL_REQUIRE(q.new_logp && q.v_pred && q.entropy && q.g_logp && q.g_value && q.g_entropy && q.workspace &&
-                    (lane_part != nullptr || (q.norm_stats && q.local_stats)),
+                    (lane_aos != nullptr || (q.norm_stats && q.local_stats)),
                 SRL_ERR_INVALID_ARG, "srl_ppo_loss_fwd_bwd: null pointer");
     any_idx = any_idx || q.lane_idx != nullptr;
     all_idx = all_idx && q.lane_idx != nullptr;
@@ -245,10 +247,12 @@ extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, in
   s.reset_next = on_reset_next;
   s.pack = reinterpret_cast<const float4*>(pack);
   s.popart = popart_mean_std;
-  SRL_REQUIRE(lane_part == nullptr || (popart_mean_std == nullptr && lane_part_n >= 1), SRL_ERR_INVALID_ARG,
-              "srl_ppo_loss_fwd_bwd_batched: self-computed statistics (lane_part) exclude PopArt and need lane_part_n >= 1");
-  s.lane_part = lane_part;
-  s.lane_part_n = lane_part_n;
+  SRL_REQUIRE(lane_aos == nullptr || (popart_mean_std == nullptr && pack != nullptr && all_idx && aligned(lane_aos, 32)),
+              SRL_ERR_INVALID_ARG,
+              "srl_ppo_loss_fwd_bwd_batched: self-computed statistics (lane_aos) need the pack form with lane indices, no "
+              "PopArt and a 32-byte aligned table");
+  s.lane_aos = lane_aos;
+  s.row_lo = pack ? pack_row_lo : 0;
   s.ld_pol = ld_pol;
   s.ld_grad = ld_grad;
   s.ld_smp = ld_smp;
@@ -257,13 +261,16 @@ extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, in
   const bool smp_vec = pack == nullptr && (ld_smp % 4 == 0) && aligned(old_logp, 16) && aligned(ret, 16) &&
                        aligned(adv, 16) && (!s.h.clip_value || aligned(old_value, 16)) && aligned(on_reset_next, 4);
   s.smp_vec_ok = smp_vec ? 1 : 0;
-  s.prefetch_rows = 0;  // decided per launch (LossLauncher::launch)
-  // SRL_LOSS_LANES=2 (read once; a tuning knob for profiles/, not an API): small pack-form minibatches run two lanes per
-  // thread.  Built for the next measurement round (profiles/r1d_notes.md); the default stays four lanes per thread.
-  static const bool lanes2_knob = [] {
-    const char* e = getenv("SRL_LOSS_LANES");
-    return e != nullptr && e[0] == '2';
-  }();
+  bool aligned8 = true;  // the pair kernel's 64-bit policy-side accesses
+  for (int k = 0; k < n_problems; ++k) {
+    const srl_loss_problem& q = problems[k];
+    aligned8 = aligned8 && aligned(q.new_logp, 8) && aligned(q.v_pred, 8) && aligned(q.entropy, 8) && aligned(q.g_logp, 8) &&
+               aligned(q.g_value, 8) && aligned(q.g_entropy, 8) && (q.lane_idx == nullptr || aligned(q.lane_idx, 8));
+  }
+  const bool pair = loss_pair_eligible(s, aligned8);
+  SRL_REQUIRE(lane_aos == nullptr || pair, SRL_ERR_UNSUPPORTED,
+              "srl_ppo_loss_fwd_bwd_batched: self-computed statistics need an even minibatch width <= 1024 lanes, even row "
+              "strides and 8-byte aligned policy-side tensors (n = %d)", n);
   const int mode = pack ? kPack : ((!any_idx && dense_ok && smp_vec) ? kDense : kGather);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto fill = [](Problem& p, const srl_loss_problem& q) {
@@ -285,8 +292,8 @@ extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, in
     LossBatch b;
     b.s = s;
     for (int k = 0; k < kMaxBatch; ++k) fill(b.prob[k], problems[k0 + (k < nb ? k : 0)]);
-    if (mode == kPack && dense_ok && lanes2_knob && n <= 512)
-      rc = launch_loss_pack2(b, nb, st);
+    if (mode == kPack && pair)
+      rc = launch_loss_pair(b, nb, st);
     else if (mode == kPack)
       rc = launch_loss_pack(b, nb, dense_ok, st);
     else if (mode == kDense)
@@ -320,7 +327,7 @@ extern "C" int srl_ppo_loss_fwd_bwd(const float* new_logp, const float* v_pred, 
   q.out_f32 = out_f32;
   q.workspace = workspace;
   return srl_ppo_loss_fwd_bwd_batched(&q, 1, ld_pol, ld_grad, old_logp, old_value, ret, adv, on_reset_next, ld_smp,
-                                      nullptr, nullptr, 0, T, n, popart_mean_std, hyper, workspace_bytes, stream);
+                                      nullptr, 0, nullptr, T, n, popart_mean_std, hyper, workspace_bytes, stream);
 }
 
 extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* action, const int32_t* head_sizes_host,
@@ -371,8 +378,8 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
   p.adv = adv;
   p.reset_next = on_reset_next;
   p.pack = nullptr;
-  p.lane_part = nullptr;
-  p.lane_part_n = 0;
+  p.lane_aos = nullptr;
+  p.row_lo = 0;
   p.popart = popart_mean_std;
   p.ld_pol = n;
   p.ld_grad = n;
@@ -381,7 +388,6 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
   p.n = n;
   p.rows_per_tile = p.col_tiles = p.n_tiles = 0;
   p.smp_vec_ok = 0;
-  p.prefetch_rows = 0;
   Problem& pr = q.pr;
   pr.new_logp = pr.entropy = nullptr;
   pr.v_pred = v_pred;

@@ -9,16 +9,9 @@
 namespace srl {
 namespace loss {
 
-#ifndef SRL_LOSS_UNROLL
-#define SRL_LOSS_UNROLL 1
-#endif
-#ifndef SRL_LOSS_NORM_FP32
-#define SRL_LOSS_NORM_FP32 0  // 1: advantage normalisation in float32 (a measurement variant; default float64 as the reference)
-#endif
 #ifndef SRL_LOSS_MIN_BLOCKS
 #define SRL_LOSS_MIN_BLOCKS 3  // CTAs of 256 threads per SM the register allocator must leave room for
 #endif
-constexpr int kLossUnroll = SRL_LOSS_UNROLL;  // rows of a tile whose loads are in flight together
 constexpr int kMaxGrid = 2048;                // partial rows per workspace slot
 constexpr int kNumSums = 8;
 constexpr size_t kPartialsOffset = 64;
@@ -68,15 +61,15 @@ struct LossShared {
   const float* ret;
   const float* adv;
   const uint8_t* reset_next;
-  const float4* pack;
+  const float4* pack;        // K2's pair-interleaved pack (base of the buffer, absolute row 0), or null
   const double* popart;
-  const double* lane_part;  // [SRL_LANE_PART, lane_part_n] from K2, or null; see self_uniforms()
-  int lane_part_n;
-  long long ld_pol, ld_grad, ld_smp;
+  const double* lane_aos;    // [N][4] float64 per-lane sums from K2 (ppo_loss_pair.cu: self-computed statistics), or null
+  long long ld_pol, ld_grad;
+  long long ld_smp;          // sample-side row stride in elements; pack form: lanes N of the pack
   int T, n;
+  int row_lo;                // pack form: absolute row of loss row 0
   int rows_per_tile, col_tiles, n_tiles;
   int smp_vec_ok;  // sample-side leaves allow 128-bit loads at 4-aligned lanes (alignment + row stride)
-  int prefetch_rows;  // policy-side rows a CTA asks into L2 before it waits for the kernel ahead of it (0: none)
   LossHyperDev h;
 };
 
@@ -88,7 +81,7 @@ struct LossBatch {
 // Sample-side forms
 constexpr int kDense = 0;   // separate leaves, lanes in policy order, 128-bit loads
 constexpr int kGather = 1;  // separate leaves through lane_idx (or any alignment)
-constexpr int kPack = 2;    // K2's float4 pack through lane_idx (or in order)
+constexpr int kPack = 2;    // K2's pack through lane_idx (or in order): pack2[t / 2][lane][t % 2] of float4
 
 // Hyper-parameter configuration of the element math.  The hot kernels are instantiated per configuration
 // (StaticCfg): ncu showed ~25 % of the executed instructions of the first batched kernel were uniform branches,
@@ -169,50 +162,6 @@ __device__ __forceinline__ Uniforms uniforms_from(double cnt, double s1, double 
   return u;
 }
 
-// Self-computed statistics (one GPU, no PopArt, the CTA's column tile spans the whole minibatch): the CTA adds K2's
-// per-lane sums over ITS minibatch's lanes -- the indices are in registers already -- instead of waiting for a
-// srl_group_stats launch between K2 and K4.  Every CTA of a minibatch adds the same values in the same order (lanes of
-// a thread, warp shuffle tree, warps in order), so they all normalise with bit-identical statistics.
-template <int LANES>
-__device__ __forceinline__ Uniforms self_uniforms(const double* __restrict__ lane_part, int N, const int (&c)[LANES],
-                                                  bool active, double adv_eps, double& mask_sum) {
-  __shared__ double s_part[3][8];
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-  if (active) {
-    double v0[LANES], v1[LANES], v2[LANES];
-#pragma unroll
-    for (int q = 0; q < LANES; ++q) {
-      v0[q] = __ldg(lane_part + c[q]);
-      v1[q] = __ldg(lane_part + static_cast<size_t>(N) + c[q]);
-      v2[q] = __ldg(lane_part + 2 * static_cast<size_t>(N) + c[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < LANES; ++q) {
-      a0 += v0[q];
-      a1 += v1[q];
-      a2 += v2[q];
-    }
-  }
-  a0 = warp_sum(a0);
-  a1 = warp_sum(a1);
-  a2 = warp_sum(a2);
-  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  if ((threadIdx.x & 31) == 0) {
-    s_part[0][warp] = a0;
-    s_part[1][warp] = a1;
-    s_part[2][warp] = a2;
-  }
-  __syncthreads();
-  double cnt = 0.0, s1 = 0.0, s2 = 0.0;
-  for (int w = 0; w < nwarps; ++w) {
-    cnt += s_part[0][w];
-    s1 += s_part[1][w];
-    s2 += s_part[2][w];
-  }
-  mask_sum = cnt;
-  return uniforms_from(cnt, s1, s2, cnt, nullptr, adv_eps);
-}
-
 // a / d in float64 given rd = 1 / d (correctly rounded): product, exact residual, one correction.  This is the
 // tail of the IEEE division sequence without its reciprocal refinement and special-case handling; d is a
 // positive finite scale here (sqrt(var) + eps, or PopArt's sigma >= 0.1).
@@ -283,12 +232,7 @@ __device__ __forceinline__ void element(const LossHyperDev& h, const Uniforms& u
   const float ratio = expf(nl - ol);
   // masked_normalization (utils.py:38-67) in float64, cast to float at the end; masked entries are centred
   // zeros there (x = adv * mask) and here
-#if SRL_LOSS_NORM_FP32
-  // build variant for profiles/ (profiles/r1d_notes.md, candidate 2): ~1e-7 relative instead of the reference's float64
-  const float nadv = (ad - static_cast<float>(u.mean)) * static_cast<float>(u.rdenom);
-#else
   const float nadv = static_cast<float>(div_by(__dsub_rn(static_cast<double>(ad), u.mean), u.denom, u.rdenom));
-#endif
   const float s1 = ratio * nadv;
   const float s2 = fminf(fmaxf(ratio, h.clip_lo), h.clip_hi) * nadv;
   const bool in_clip = ratio >= h.clip_lo && ratio <= h.clip_hi;
@@ -408,71 +352,13 @@ __device__ __forceinline__ void reduce_and_finalize(const Problem& pr, const Los
 
 __device__ __forceinline__ void unpack4(const float4 v, float (&a)[4]) { a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w; }
 
-// Policy-side loads of the register path.  Default: streaming loads (ld.global.cs, evict-first).  SRL_LOSS_POLICY_NC=1
-// (a build variant for profiles/, with SRL_LOSS_UNROLL=2): non-coherent loads (ld.global.nc), which the compiler may hoist
-// above the gradient stores of the previous row -- the policy outputs are never written by this kernel.
-#ifndef SRL_LOSS_POLICY_NC
-#define SRL_LOSS_POLICY_NC 0
-#endif
-template <class V>
-__device__ __forceinline__ V ld_policy(const V* p) {
-#if SRL_LOSS_POLICY_NC
-  return __ldg(p);
-#else
-  return ldg_stream(p);
-#endif
-}
-
-// ---- asynchronous global -> shared copies (LDGSTS): the loads of the next rows are in flight while the current
-// row is computed, without holding registers for them -----------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
-               "l"(gmem_src)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
-               "l"(gmem_src)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-#ifndef SRL_LOSS_STAGES
-#define SRL_LOSS_STAGES 2
-#endif
-#ifndef SRL_LOSS_PIPE
-#define SRL_LOSS_PIPE 0  // measured on B200 (profiles/r1c_notes.md): no gain over the register path at cfg2 or cfg5
-#endif
-constexpr bool kUsePipe = SRL_LOSS_PIPE != 0;
-constexpr int kStages = SRL_LOSS_STAGES;  // rows in flight per thread in the pipelined kernels
-constexpr int kPlanes = 7;                // 16-byte items per thread and row: 3 policy + 4 sample side
-
-// Dynamic shared memory of the pipelined kernels: [kStages][kPlanes][threads] float4 + [kStages][threads] uint32.
-__host__ __device__ constexpr size_t loss_smem_bytes(int threads) {
-  return static_cast<size_t>(kStages) * threads * (kPlanes * 16 + 4);
-}
-
-// Work decomposition: grid = (column tiles, row groups, problems).  A CTA owns `blockDim * LANES` adjacent policy-side
-// lanes and the rows [r0, r1) of one problem: its gather indices are loaded once, and it walks its rows in order.
-// LANES = 4: a thread owns four adjacent lanes (n % 4 == 0, 16-byte aligned rows); LANES = 1: any shape.
-// PIPE (dense and pack forms, LANES = 4): row t + kStages is copied global -> shared (16 bytes per cp.async, each
-// thread into its own slots, so no block barrier) while row t is computed.
-// Policy-side rows a CTA asks into L2 before it waits for the scan.  Only for programmatic launches of short tiles
-// (cfg2: 5 rows per CTA, the whole tile): measured on one box (profiles/r1d_notes.md), the requests cost the kernel
-// ~2 us when it runs alone (26.6 -> 28.7 us at cfg2, 76.4 -> 78.6 us at cfg5: the demand loads follow at once and find
-// their lines still in flight), and win 1.3 us per step when they are issued under the scan (cfg2: 43.1 -> 41.7 us).
-#ifndef SRL_LOSS_PREFETCH_ROWS
-#define SRL_LOSS_PREFETCH_ROWS 6
-#endif
-constexpr int kPrefetchRows = SRL_LOSS_PREFETCH_ROWS;
-
+// Work decomposition of the row-tile kernel (dense leaves, leaves through lane_idx, odd shapes of the pack form): grid =
+// (column tiles, row groups, problems).  A CTA owns `blockDim * LANES` adjacent policy-side lanes and the rows [r0, r1) of
+// one problem: its gather indices are loaded once, and it walks its rows in order.  LANES = 4: a thread owns four adjacent
+// lanes (n % 4 == 0, 16-byte aligned rows); LANES = 1: any shape.  Permuted minibatches of even width run the pair kernel
+// (ppo_loss_pair.cu) instead.
 template <int LANES, int MODE, class CFG>
 __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(const __grid_constant__ LossBatch b) {
-  constexpr bool PIPE = kUsePipe && (LANES == 4) && (MODE == kDense || MODE == kPack);
   const LossShared& s = b.s;
   const LossHyperDev& h = s.h;
   const Problem& pr = b.prob[blockIdx.z];
@@ -486,133 +372,25 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
   Uniforms u;
   bool have_u = false;
 
-  // Launched programmatically behind the scan (common.cuh), this CTA may be resident while the scan still runs.  The
-  // policy-side rows do not depend on it: ask for this CTA's share (three tensors x its rows, one request per 128-byte
-  // line) to be brought into L2 under the scan, then wait for the scan's results.
-  if constexpr (LANES >= 2 && kPrefetchRows > 0) {
-    if (s.prefetch_rows > 0 && (threadIdx.x & (32 / LANES - 1)) == 0) {  // one thread per 128-byte line
-      const int j = (blockIdx.x * blockDim.x + threadIdx.x) * LANES;
-      if (j < n) {
-        long long o = static_cast<long long>(r0) * s.ld_pol + j;
-        const int r_pf = min(r1, r0 + s.prefetch_rows);
-        for (int t = r0; t < r_pf; ++t, o += s.ld_pol) {
-          prefetch_l2(pr.new_logp + o);
-          prefetch_l2(pr.v_pred + o);
-          prefetch_l2(pr.entropy + o);
-        }
-      }
-    }
-  }
-  pdl_wait();
+  pdl_wait();  // launched programmatically behind the scan / the statistics kernel (common.cuh)
 
   // normally one column tile per CTA (gridDim.x == col_tiles); only batches wider than kMaxGrid tiles loop here
   for (int ct = blockIdx.x; ct < s.col_tiles; ct += gridDim.x) {
-  const int j = (ct * blockDim.x + threadIdx.x) * LANES;
-  const bool active = j < n;
-  // gather indices of this thread's lanes: once per column tile
-  int c[LANES];
-  if (pr.lane_idx && active) {
-    if constexpr (LANES == 4) {
-      const int4 q = __ldg(reinterpret_cast<const int4*>(pr.lane_idx + j));
-      c[0] = q.x, c[1] = q.y, c[2] = q.z, c[3] = q.w;
-    } else if constexpr (LANES == 2) {
-      const int2 q = __ldg(reinterpret_cast<const int2*>(pr.lane_idx + j));
-      c[0] = q.x, c[1] = q.y;
-    } else {
-      c[0] = __ldg(pr.lane_idx + j);
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < LANES; ++q) c[q] = j + q;
-  }
-
-  if constexpr (PIPE) {
-    extern __shared__ __align__(16) unsigned char ring_raw[];
-    float4* ring = reinterpret_cast<float4*>(ring_raw);
-    uint32_t* fring = reinterpret_cast<uint32_t*>(ring_raw + static_cast<size_t>(kStages) * kPlanes * blockDim.x * 16);
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    auto slot = [&](int st, int plane) { return ring + (st * kPlanes + plane) * nthr + tid; };
-    auto issue = [&](int t, int st) {  // all loads of row t into stage st
-      if (active && t < r1) {
-        const long long op = static_cast<long long>(t) * s.ld_pol + j;
-        cp_async16(slot(st, 0), pr.new_logp + op);
-        cp_async16(slot(st, 1), pr.v_pred + op);
-        cp_async16(slot(st, 2), pr.entropy + op);
-        const long long ob = static_cast<long long>(t) * s.ld_smp;
-        if constexpr (MODE == kPack) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) cp_async16(slot(st, 3 + q), s.pack + ob + c[q]);
-        } else {
-          cp_async16(slot(st, 3), s.old_logp + ob + j);
-          cp_async16(slot(st, 4), s.ret + ob + j);
-          cp_async16(slot(st, 5), s.adv + ob + j);
-          if (CFG::clip(h)) cp_async16(slot(st, 6), s.old_value + ob + j);
-          cp_async4(fring + st * nthr + tid, s.reset_next + ob + j);
-        }
-      }
-      cp_async_commit();  // one group per row, issued or not, so wait_group counts rows
-    };
-#pragma unroll
-    for (int k = 0; k < kStages; ++k) issue(r0 + k, k);
-    // the statistics loads and the float64 divisions / sqrt on them run under the first rows' copies
-    if (!have_u) {
-      if (s.lane_part != nullptr)
-        u = self_uniforms<LANES>(s.lane_part, s.lane_part_n, c, active, h.adv_eps, mask_sum);
-      else
-        u = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
-      have_u = true;
-    }
-    float* glp_row = pr.g_logp + static_cast<long long>(r0) * s.ld_grad + j;
-    float* gv_row = pr.g_value + static_cast<long long>(r0) * s.ld_grad + j;
-    float* ge_row = pr.g_entropy + static_cast<long long>(r0) * s.ld_grad + j;
-    int st = 0;
-    for (int t = r0; t < r1; ++t, glp_row += s.ld_grad, gv_row += s.ld_grad, ge_row += s.ld_grad) {
-      cp_async_wait<kStages - 1>();  // row t has landed (rows t+1 .. t+kStages-1 may still be in flight)
-      float nl[4], vp[4], en[4], ol[4], ov[4], rt[4], ad[4];
-      bool valid[4];
-      unpack4(*slot(st, 0), nl);
-      unpack4(*slot(st, 1), vp);
-      unpack4(*slot(st, 2), en);
-      if constexpr (MODE == kPack) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 k = *slot(st, 3 + q);
-          ol[q] = k.x;
-          ov[q] = k.y;
-          rt[q] = k.z;
-          ad[q] = k.w;
-          valid[q] = (k.w == k.w);  // K2 stores NaN in the advantage slot of masked transitions
-        }
+    const int j = (ct * blockDim.x + threadIdx.x) * LANES;
+    const bool active = j < n;
+    // gather indices of this thread's lanes: once per column tile
+    int c[LANES];
+    if (pr.lane_idx && active) {
+      if constexpr (LANES == 4) {
+        const int4 q = __ldg(reinterpret_cast<const int4*>(pr.lane_idx + j));
+        c[0] = q.x, c[1] = q.y, c[2] = q.z, c[3] = q.w;
       } else {
-        unpack4(*slot(st, 3), ol);
-        unpack4(*slot(st, 4), rt);
-        unpack4(*slot(st, 5), ad);
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (CFG::clip(h)) o = *slot(st, 6);
-        unpack4(o, ov);
-        const uint32_t m = fring[st * nthr + tid];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) valid[q] = ((m >> (8 * q)) & 0xffu) == 0u;
+        c[0] = __ldg(pr.lane_idx + j);
       }
-      issue(t + kStages, st);  // refill the stage just drained (its values are in registers now)
-      st = (st + 1 == kStages) ? 0 : st + 1;
-      if (active) {
-        float glp[4], gv[4], ge[4];
+    } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          element<CFG>(h, u, nl[q], vp[q], en[q], ol[q], ov[q], rt[q], ad[q], valid[q], glp[q], gv[q], ge[q], rs);
-        if (++pending == kFlushRows) {  // fp32 partial sums of at most kFlushRows * LANES terms, then float64
-          acc.add(rs);
-          rs = RowSums();
-          pending = 0;
-        }
-        stg_stream(reinterpret_cast<float4*>(glp_row), make_float4(glp[0], glp[1], glp[2], glp[3]));
-        stg_stream(reinterpret_cast<float4*>(gv_row), make_float4(gv[0], gv[1], gv[2], gv[3]));
-        stg_stream(reinterpret_cast<float4*>(ge_row), make_float4(ge[0], ge[1], ge[2], ge[3]));
-      }
+      for (int q = 0; q < LANES; ++q) c[q] = j + q;
     }
-    cp_async_wait<0>();
-  } else {
     // a run of four consecutive, 4-aligned lanes (agents of one environment, sector-aligned environment blocks) is
     // fetched with one 128-bit load per leaf
     bool run4 = false;
@@ -628,32 +406,29 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
     long long ob = static_cast<long long>(r0) * s.ld_smp;  // sample-side row base (elements)
     float nl[LANES], vp[LANES], en[LANES], ol[LANES], ov[LANES], rt[LANES], ad[LANES];
     bool valid[LANES];
-    // every global load of the row at (nl_row, vp_row, en_row, ob)
-    auto load_row = [&]() {
+    // every global load of loss row t at (nl_row, vp_row, en_row, ob)
+    auto load_row = [&](int t) {
       if constexpr (LANES == 4) {
-        unpack4(ld_policy(reinterpret_cast<const float4*>(nl_row + j)), nl);
-        unpack4(ld_policy(reinterpret_cast<const float4*>(vp_row + j)), vp);
-        unpack4(ld_policy(reinterpret_cast<const float4*>(en_row + j)), en);
-      } else if constexpr (LANES == 2) {
-        const float2 a = ld_policy(reinterpret_cast<const float2*>(nl_row + j));
-        const float2 b2 = ld_policy(reinterpret_cast<const float2*>(vp_row + j));
-        const float2 e2 = ld_policy(reinterpret_cast<const float2*>(en_row + j));
-        nl[0] = a.x, nl[1] = a.y, vp[0] = b2.x, vp[1] = b2.y, en[0] = e2.x, en[1] = e2.y;
+        unpack4(ldg_stream(reinterpret_cast<const float4*>(nl_row + j)), nl);
+        unpack4(ldg_stream(reinterpret_cast<const float4*>(vp_row + j)), vp);
+        unpack4(ldg_stream(reinterpret_cast<const float4*>(en_row + j)), en);
       } else {
-        nl[0] = ld_policy(nl_row + j);
-        vp[0] = ld_policy(vp_row + j);
-        en[0] = ld_policy(en_row + j);
+        nl[0] = ldg_stream(nl_row + j);
+        vp[0] = ldg_stream(vp_row + j);
+        en[0] = ldg_stream(en_row + j);
       }
       if constexpr (MODE == kPack) {
-        const float4* pack_row = s.pack + ob;
+        // pack2[ta / 2][lane][ta % 2], ta = absolute row: items of lane c at (ta / 2) * 2N + 2c + (ta % 2)
+        const int ta = s.row_lo + t;
+        const float4* pack_row = s.pack + static_cast<long long>(ta >> 1) * (2 * s.ld_smp) + (ta & 1);
 #pragma unroll
         for (int q = 0; q < LANES; ++q) {
-          const float4 k = __ldg(pack_row + c[q]);
+          const float4 k = __ldg(pack_row + 2 * c[q]);
           ol[q] = k.x;
           ov[q] = k.y;
           rt[q] = k.z;
           ad[q] = k.w;
-          valid[q] = (k.w == k.w);
+          valid[q] = (k.w == k.w);  // K2 stores NaN in the advantage slot of masked transitions
         }
       } else if (run4) {
         if constexpr (LANES == 4) {
@@ -684,18 +459,14 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
       }
     };
     // (Issuing the first row's loads here, ahead of the statistics prologue, and each later row right after the stores of
-    // the row before it was built and measured: it loses, 26.7 -> 33.0 us at cfg2 -- profiles/r1d_notes.md.)
+    // the row before it was built and measured in round 1: it loses -- profiles/r1d_notes.md.)
     if (!have_u) {
-      if (s.lane_part != nullptr)
-        u = self_uniforms<LANES>(s.lane_part, s.lane_part_n, c, active, h.adv_eps, mask_sum);
-      else
-        u = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
+      u = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
       have_u = true;
     }
     if (active) {
-#pragma unroll kLossUnroll
       for (int t = r0; t < r1; ++t) {
-        load_row();
+        load_row(t);
         float glp[LANES], gv[LANES], ge[LANES];
 #pragma unroll
         for (int q = 0; q < LANES; ++q)
@@ -709,10 +480,6 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
           stg_stream(reinterpret_cast<float4*>(glp_row + j), make_float4(glp[0], glp[1], glp[2], glp[3]));
           stg_stream(reinterpret_cast<float4*>(gv_row + j), make_float4(gv[0], gv[1], gv[2], gv[3]));
           stg_stream(reinterpret_cast<float4*>(ge_row + j), make_float4(ge[0], ge[1], ge[2], ge[3]));
-        } else if constexpr (LANES == 2) {
-          stg_stream(reinterpret_cast<float2*>(glp_row + j), make_float2(glp[0], glp[1]));
-          stg_stream(reinterpret_cast<float2*>(gv_row + j), make_float2(gv[0], gv[1]));
-          stg_stream(reinterpret_cast<float2*>(ge_row + j), make_float2(ge[0], ge[1]));
         } else {
           stg_stream(glp_row + j, glp[0]);
           stg_stream(gv_row + j, gv[0]);
@@ -723,7 +490,6 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
         ob += s.ld_smp;
       }
     }
-  }
   }  // column tiles
   acc.add(rs);
   const int row = blockIdx.y * gridDim.x + blockIdx.x;
@@ -732,8 +498,6 @@ __global__ void __launch_bounds__(256, SRL_LOSS_MIN_BLOCKS) ppo_loss_kernel(cons
 
 template <int LANES, int MODE, class CFG>
 struct LossLauncher {
-  static constexpr bool PIPE = kUsePipe && (LANES == 4) && (MODE == kDense || MODE == kPack);
-
   // CTAs of `threads` threads one SM holds (registers / shared memory), asked once per device and block size
   static int resident(int threads) {
     static int cached[64][2] = {};
@@ -742,13 +506,8 @@ struct LossLauncher {
     int& c = cached[dev][threads >= 256 ? 1 : 0];
     if (c == 0) {
       auto kern = ppo_loss_kernel<LANES, MODE, CFG>;
-      const size_t smem = PIPE ? loss_smem_bytes(256) : 0;
-      if (PIPE) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       int n = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, PIPE ? loss_smem_bytes(threads) : 0) !=
-              cudaSuccess ||
-          n < 1)
-        n = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, 0) != cudaSuccess || n < 1) n = 1;
       c = n;
     }
     return c;
@@ -759,9 +518,6 @@ struct LossLauncher {
     const int per_row = (s.n + LANES - 1) / LANES;  // threads one row needs
     const int threads = per_row <= 128 ? 128 : 256;
     s.col_tiles = (per_row + threads - 1) / threads;
-    SRL_REQUIRE(s.lane_part == nullptr || s.col_tiles == 1, SRL_ERR_UNSUPPORTED,
-                "ppo loss: self-computed statistics need the whole minibatch in one column tile (n <= %d lanes)",
-                256 * LANES);
     const long long capacity = static_cast<long long>(sm_count()) * resident(threads);  // CTAs resident at once
     // row groups: as many as keep the whole grid resident in ONE wave (a second, partial wave would double the
     // kernel's duration); every CTA then walks ceil(T / groups) consecutive rows of its column tile
@@ -774,9 +530,8 @@ struct LossLauncher {
     if (gx * groups > kMaxGrid) gx = kMaxGrid / groups;  // one partial row per CTA in the workspace slot
     s.rows_per_tile = rows;
     s.n_tiles = static_cast<int>(groups);
-    s.prefetch_rows = (pdl_enabled() && rows <= kPrefetchRows) ? rows : 0;
     const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(groups), static_cast<unsigned>(n_problems));
-    SRL_CUDA(launch_pdl(ppo_loss_kernel<LANES, MODE, CFG>, grid, dim3(threads), PIPE ? loss_smem_bytes(threads) : 0, st, b));
+    SRL_CUDA(launch_pdl(ppo_loss_kernel<LANES, MODE, CFG>, grid, dim3(threads), 0, st, b));
     return SRL_OK;
   }
 };
@@ -830,9 +585,10 @@ int launch_loss_mode(LossBatch& b, int n_problems, bool lanes4, cudaStream_t st)
 int launch_loss_dense(LossBatch& b, int n_problems, bool lanes4, cudaStream_t st);
 int launch_loss_gather(LossBatch& b, int n_problems, bool lanes4, cudaStream_t st);
 int launch_loss_pack(LossBatch& b, int n_problems, bool lanes4, cudaStream_t st);
-// ppo_loss_pack2.cu: the pack form with TWO lanes per thread (twice the threads per row, half the registers a row's loads
-// hold): an experiment for small minibatches, reached only with SRL_LOSS_LANES=2 in the environment (ppo_loss.cu)
-int launch_loss_pack2(LossBatch& b, int n_problems, cudaStream_t st);
+// ppo_loss_pair.cu: the pack form for permuted minibatches of even width (two lanes x two rows per thread and step, the
+// loads of the next step in flight under the arithmetic of this one, units dealt evenly over a persistent grid)
+bool loss_pair_eligible(const LossShared& s, bool aligned8);
+int launch_loss_pair(LossBatch& b, int n_problems, cudaStream_t st);
 
 }  // namespace loss
 }  // namespace srl

@@ -1,0 +1,329 @@
+// K4, pack form: the kernel behind every permuted minibatch (4 epochs x 8 minibatches of cfg2 in one launch, or one
+// minibatch per launch in the trainer's dependency order).  Replaces the row-tile kernel of round 1 for this form; what the
+// profiles of that kernel said (profiles/r1d_ncu_cfg2.txt, VERDICT r1 "What's weak" 3) and what is different here:
+//
+//  * every CTA of the one-wave grid started together and stayed in lockstep: a burst of loads for one row, then ~500
+//    instructions of arithmetic per warp with nothing in flight, five times over -- load time, issue time and latency
+//    ADDED instead of overlapping (26.6 us for 86 MB).  Here a thread owns 2 adjacent lanes x 2 rows per step and keeps
+//    TWO steps in registers: the loads of step i+1 are issued before the arithmetic of step i.
+//  * the pack was one 16-byte item per transition: a per-environment permutation fetched a 32-byte sector for 16 bytes
+//    (L2 -> L1: 117 MB for 61 MB of use).  K2 now interleaves row pairs -- pack2[t / 2][lane] = 32 bytes = {row t, row t+1}
+//    of {old_logp, value, ret, mask ? adv : NaN} -- and a thread fetches its lane's pair with ONE 256-bit load: every
+//    sector is used whole, and the gather costs one L1 wavefront per two transitions instead of one per transition.
+//  * every one of the 26 row-group CTAs of a minibatch re-gathered K2's per-lane sums, three 8-byte gathers per lane out
+//    of three 32-byte sectors (~40 MB).  K2 now also writes them as one 32-byte item per lane (lane_aos) and a CTA adds
+//    them with one 256-bit gather per lane.
+//  * the grid was (column tile, row group, problem) sized to one wave: 832 CTAs on 888 slots, and 9.25 row groups per
+//    column do not divide 128 rows.  Here the (problem, column tile, row pair) units are numbered in one line and CTA g of
+//    G takes units [g * U / G, (g + 1) * U / G): every CTA gets the same number of steps (+-1), for any shape.
+//
+// A CTA's range may cross into the next problem: it then writes one partial row per problem it touched; a problem's rows are
+// the CTAs whose ranges intersect it (computable from the unit numbering alone), folded in CTA order by the last one to
+// arrive (ticket) -- deterministic for a given launch shape, as before.
+#include <stdlib.h>
+
+#include "ppo_loss.cuh"
+
+namespace srl {
+namespace loss {
+namespace {
+
+#ifndef SRL_PAIR_THREADS
+#define SRL_PAIR_THREADS 128
+#endif
+#ifndef SRL_PAIR_MIN_BLOCKS
+#define SRL_PAIR_MIN_BLOCKS 4
+#endif
+constexpr int kPairThreads = SRL_PAIR_THREADS;
+constexpr int kPairLanes = 2 * kPairThreads;  // lanes per column tile
+constexpr int kStatMax = 1024 / kPairThreads; // lanes per thread in the statistics prologue (n <= 1024)
+
+struct PairSched {
+  int pair_lo;    // absolute index of the first row pair that holds a loss row: row_lo >> 1
+  int pairs;      // row pairs per column
+  int col_tiles;  // column tiles per problem
+  int cpp;        // units per problem = col_tiles * pairs
+  long long units;
+};
+
+// Both rows' policy outputs of this thread's two lanes, and its two lanes' row pairs of the pack.
+struct Stage {
+  float2 nl[2], vp[2], en[2];
+  float pk[2][8];
+};
+
+__device__ __forceinline__ float2 ld_cs2(const float* p) {
+  float2 v;
+  asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void ld_nc256(const float4* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ld_nc256(const double* p, double (&v)[4]) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+
+// Minibatch statistics from K2's per-lane sums (lane_aos[lane] = {sum mask, sum adv*mask, sum (adv*mask)^2, 0}), added
+// over ALL lanes of the problem by every CTA that works on it: thread i adds lanes i, i + THREADS, ... in that order, then
+// the warp tree, then the warps in order -- the same order in every CTA, so they normalise with bit-identical statistics.
+__device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__ lane_aos, const int32_t* __restrict__ idx,
+                                                      int n, double adv_eps, double& mask_sum, double (*s_part)[8]) {
+  int ci[kStatMax];
+#pragma unroll
+  for (int q = 0; q < kStatMax; ++q) {
+    const int i = threadIdx.x + q * kPairThreads;
+    ci[q] = i < n ? __ldg(idx + i) : -1;
+  }
+  double v[kStatMax][4];
+#pragma unroll
+  for (int q = 0; q < kStatMax; ++q) {
+    if (ci[q] >= 0) {
+      ld_nc256(lane_aos + 4 * static_cast<size_t>(ci[q]), v[q]);
+    } else {
+      v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.0;
+    }
+  }
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+  for (int q = 0; q < kStatMax; ++q) {
+    a0 += v[q][0];
+    a1 += v[q][1];
+    a2 += v[q][2];
+  }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  a2 = warp_sum(a2);
+  const int warp = threadIdx.x >> 5;
+  __syncthreads();  // a previous problem's readers are done with s_part
+  if ((threadIdx.x & 31) == 0) {
+    s_part[0][warp] = a0;
+    s_part[1][warp] = a1;
+    s_part[2][warp] = a2;
+  }
+  __syncthreads();
+  double cnt = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+  for (int w = 0; w < kPairThreads / 32; ++w) {
+    cnt += s_part[0][w];
+    s1 += s_part[1][w];
+    s2 += s_part[2][w];
+  }
+  mask_sum = cnt;
+  return uniforms_from(cnt, s1, s2, cnt, nullptr, adv_eps);
+}
+
+template <class CFG>
+__global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pair_kernel(const __grid_constant__ LossBatch b,
+                                                                                          const PairSched sc) {
+  __shared__ double s_part[3][8];
+  const LossShared& s = b.s;
+  const LossHyperDev& h = s.h;
+  const int n = s.n, T = s.T, row_lo = s.row_lo;
+  const long long N2 = 2 * s.ld_smp;  // float4 items per row pair of the pack
+  const long long u_begin = static_cast<long long>(blockIdx.x) * sc.units / gridDim.x;
+  const long long u_end = static_cast<long long>(blockIdx.x + 1) * sc.units / gridDim.x;
+
+  // ---- where this CTA starts ------------------------------------------------------------------------------------
+  long long u = u_begin;
+  int col = static_cast<int>(u / sc.pairs);
+  int pi = static_cast<int>(u - static_cast<long long>(col) * sc.pairs);
+  int k = col / sc.col_tiles;
+  int ct = col - k * sc.col_tiles;
+
+  Stage sA, sB;
+  // policy-side loads of row pair `p` (index within the column) of problem `pr`, lanes j, j + 1
+  auto issue_policy = [&](Stage& st, const Problem& pr, int p, int j) {
+    const int r0 = 2 * (sc.pair_lo + p) - row_lo;  // loss row of the pair's first row (-1: before the first loss row)
+    const long long o = static_cast<long long>(r0) * s.ld_pol + j;
+    if (r0 >= 0) {
+      st.nl[0] = ld_cs2(pr.new_logp + o);
+      st.vp[0] = ld_cs2(pr.v_pred + o);
+      st.en[0] = ld_cs2(pr.entropy + o);
+    }
+    if (r0 + 1 < T) {
+      st.nl[1] = ld_cs2(pr.new_logp + o + s.ld_pol);
+      st.vp[1] = ld_cs2(pr.v_pred + o + s.ld_pol);
+      st.en[1] = ld_cs2(pr.entropy + o + s.ld_pol);
+    }
+  };
+  auto issue_pack = [&](Stage& st, int p, const int (&c)[2]) {
+    const float4* row = s.pack + static_cast<long long>(sc.pair_lo + p) * N2;
+    ld_nc256(row + 2 * c[0], st.pk[0]);
+    ld_nc256(row + 2 * c[1], st.pk[1]);
+  };
+
+  // Launched programmatically behind the scan, this CTA may be resident while the scan still runs: the policy outputs do
+  // not depend on it, so the first step's policy-side loads are in flight before the wait.
+  {
+    const int j = (ct * kPairThreads + threadIdx.x) * 2;
+    if (j < n) issue_policy(sA, b.prob[k], pi, j);
+  }
+  pdl_wait();
+
+  Acc acc;
+  RowSums rs;
+  int pending = 0;
+  bool first = true;
+  while (u < u_end) {
+    const Problem& pr = b.prob[k];
+    double mask_sum = 0.0;
+    Uniforms uf;
+    bool have_u = false;
+    // ---- all column segments of this problem that fall into the CTA's range -----------------------------------
+    while (u < u_end) {
+      const int j = (ct * kPairThreads + threadIdx.x) * 2;
+      const bool active = j < n;
+      const int p_end = static_cast<int>(min(static_cast<long long>(sc.pairs), pi + (u_end - u)));
+      int c[2] = {j, j + 1};
+      if (pr.lane_idx && active) {
+        const int2 q = __ldg(reinterpret_cast<const int2*>(pr.lane_idx + j));
+        c[0] = q.x, c[1] = q.y;
+      }
+      if (active) {
+        if (!first) issue_policy(sA, pr, pi, j);
+        issue_pack(sA, pi, c);
+      }
+      first = false;
+      if (!have_u) {  // once per problem; the first step's loads are in flight underneath
+        if (s.lane_aos != nullptr)
+          uf = self_uniforms_aos(s.lane_aos, pr.lane_idx, n, h.adv_eps, mask_sum, s_part);
+        else
+          uf = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
+        have_u = true;
+      }
+      if (active) {
+        // one step: both rows of the pair, both lanes; masked or out-of-range rows produce nothing
+        auto compute = [&](const Stage& st, int p) {
+          const int r0 = 2 * (sc.pair_lo + p) - row_lo;
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int r = r0 + rr;
+            if (r < 0 || r >= T) continue;
+            float glp[2], gv[2], ge[2];
+            const float nl[2] = {st.nl[rr].x, st.nl[rr].y}, vp[2] = {st.vp[rr].x, st.vp[rr].y},
+                        en[2] = {st.en[rr].x, st.en[rr].y};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const float ad = st.pk[q][4 * rr + 3];
+              element<CFG>(h, uf, nl[q], vp[q], en[q], st.pk[q][4 * rr + 0], st.pk[q][4 * rr + 1], st.pk[q][4 * rr + 2], ad,
+                           ad == ad, glp[q], gv[q], ge[q], rs);
+            }
+            const long long o = static_cast<long long>(r) * s.ld_grad + j;
+            stg_stream(reinterpret_cast<float2*>(pr.g_logp + o), make_float2(glp[0], glp[1]));
+            stg_stream(reinterpret_cast<float2*>(pr.g_value + o), make_float2(gv[0], gv[1]));
+            stg_stream(reinterpret_cast<float2*>(pr.g_entropy + o), make_float2(ge[0], ge[1]));
+          }
+          if (++pending == kFlushRows / 2) {  // fp32 partial sums of at most kFlushRows * 2 terms, then float64
+            acc.add(rs);
+            rs = RowSums();
+            pending = 0;
+          }
+        };
+        int p = pi;
+        while (true) {
+          if (p + 1 < p_end) {
+            issue_policy(sB, pr, p + 1, j);
+            issue_pack(sB, p + 1, c);
+          }
+          compute(sA, p);
+          if (++p >= p_end) break;
+          if (p + 1 < p_end) {
+            issue_policy(sA, pr, p + 1, j);
+            issue_pack(sA, p + 1, c);
+          }
+          compute(sB, p);
+          if (++p >= p_end) break;
+        }
+      }
+      u += p_end - pi;
+      // next column: same problem (next column tile) or the next problem
+      pi = 0;
+      if (++ct == sc.col_tiles) {
+        ct = 0;
+        break;
+      }
+    }
+    // ---- this CTA's partial row of problem k ----------------------------------------------------------------------
+    acc.add(rs);
+    rs = RowSums();
+    pending = 0;
+    const long long x0 = static_cast<long long>(k) * sc.cpp, x1 = x0 + sc.cpp - 1;  // the problem's first and last unit
+    const int g0 = static_cast<int>(((x0 + 1) * gridDim.x - 1) / sc.units);         // CTA that holds unit x0
+    const int g1 = static_cast<int>(((x1 + 1) * gridDim.x - 1) / sc.units);
+    reduce_and_finalize(pr, h, acc, mask_sum, static_cast<int>(blockIdx.x) - g0, g1 - g0 + 1);
+    acc = Acc();
+    ++k;
+  }
+}
+
+template <class CFG>
+int launch_pair(LossBatch& b, int n_problems, cudaStream_t st) {
+  const LossShared& s = b.s;
+  auto kern = ppo_loss_pair_kernel<CFG>;
+  static int resident[64] = {};
+  int dev = 0;
+  SRL_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (resident[dev] == 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kPairThreads, 0) != cudaSuccess || nb < 1) nb = 1;
+    resident[dev] = nb;
+  }
+  PairSched sc;
+  sc.pair_lo = s.row_lo >> 1;
+  sc.pairs = ((s.row_lo + s.T - 1) >> 1) - sc.pair_lo + 1;
+  sc.col_tiles = (s.n + kPairLanes - 1) / kPairLanes;
+  sc.cpp = sc.col_tiles * sc.pairs;
+  sc.units = static_cast<long long>(sc.cpp) * n_problems;
+  long long grid = static_cast<long long>(sm_count()) * resident[dev];
+  if (grid > sc.units) grid = sc.units;
+  // a problem's partial rows: one per CTA whose range intersects it
+  SRL_REQUIRE(grid / n_problems + 2 <= kMaxGrid, SRL_ERR_UNSUPPORTED, "ppo loss: %lld CTAs per problem exceed the workspace slot",
+              grid / n_problems + 2);
+  SRL_CUDA(launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(kPairThreads), 0, st, b, sc));
+  return SRL_OK;
+}
+
+}  // namespace
+
+bool loss_pair_eligible(const LossShared& s, bool aligned8) {
+  return s.pack != nullptr && aligned8 && (s.n % 2 == 0) && (s.ld_pol % 2 == 0) && (s.ld_grad % 2 == 0) &&
+         (s.lane_aos == nullptr || s.n <= 1024);
+}
+
+int launch_loss_pair(LossBatch& b, int n_problems, cudaStream_t st) {
+  const LossHyperDev& h = b.s.h;
+  const bool popart = b.s.popart != nullptr;
+  const int key = (h.value_loss == SRL_VL_MSE ? 0 : h.value_loss == SRL_VL_HUBER ? 1 : 2) * 8 + (h.clip_value ? 4 : 0) +
+                  (h.dual_clip ? 2 : 0) + (popart ? 1 : 0);
+#define SRL_PAIR_CASE(k, vl, clip, dual, pa) \
+  case k:                                    \
+    return launch_pair<StaticCfg<vl, clip, dual, pa>>(b, n_problems, st)
+  switch (key) {
+    SRL_PAIR_CASE(0, SRL_VL_MSE, false, false, false);
+    SRL_PAIR_CASE(1, SRL_VL_MSE, false, false, true);
+    SRL_PAIR_CASE(2, SRL_VL_MSE, false, true, false);
+    SRL_PAIR_CASE(3, SRL_VL_MSE, false, true, true);
+    SRL_PAIR_CASE(4, SRL_VL_MSE, true, false, false);
+    SRL_PAIR_CASE(5, SRL_VL_MSE, true, false, true);
+    SRL_PAIR_CASE(6, SRL_VL_MSE, true, true, false);
+    SRL_PAIR_CASE(7, SRL_VL_MSE, true, true, true);
+    SRL_PAIR_CASE(8, SRL_VL_HUBER, false, false, false);
+    SRL_PAIR_CASE(9, SRL_VL_HUBER, false, false, true);
+    SRL_PAIR_CASE(10, SRL_VL_HUBER, false, true, false);
+    SRL_PAIR_CASE(11, SRL_VL_HUBER, false, true, true);
+    SRL_PAIR_CASE(12, SRL_VL_HUBER, true, false, false);
+    SRL_PAIR_CASE(13, SRL_VL_HUBER, true, false, true);
+    SRL_PAIR_CASE(14, SRL_VL_HUBER, true, true, false);
+    SRL_PAIR_CASE(15, SRL_VL_HUBER, true, true, true);
+    default:
+      return launch_pair<RuntimeCfg>(b, n_problems, st);
+  }
+#undef SRL_PAIR_CASE
+}
+
+}  // namespace loss
+}  // namespace srl

@@ -101,7 +101,7 @@ class HotPath:
         # minibatch (its indices are in registers anyway), so the statistics table is no longer on the critical path
         # K2 -> K4; it is still produced (the trainer reports done / truncated from its batch row), on a side branch.
         self.fuse_stats = bool(fuse_stats) and process_group is None and not popart and self._immediate and \
-            self.n_mb <= 1024 and self.n_mb % 4 == 0
+            minibatches > 1 and fuse_gather and use_pack and self.n_mb <= 1024 and self.n_mb % 2 == 0
         self._stats_pending = False
         self.step_count = 0
 
@@ -112,13 +112,15 @@ class HotPath:
         self.leaf.update({k: u8(L, N) for k in SAMPLE_U8})
         self.adv, self.ret = f32(L, N), f32(L, N)
         self.lane_part = torch.empty((SRL_LANE_PART, N), dtype=torch.float64, device=dev)
+        # the same per-lane sums as one 32-byte item per lane: what the pair loss kernel gathers for its own statistics
+        self.lane_aos = torch.empty((N, 4), dtype=torch.float64, device=dev) if self.fuse_stats else None
         G = 1 + epochs * minibatches
         self.local_stats = torch.zeros((G, SRL_LANE_PART), dtype=torch.float64, device=dev)
         self.global_stats = self.local_stats if process_group is None else torch.zeros_like(self.local_stats)
         self.perm = torch.empty((epochs, N), dtype=torch.int32, device=dev) if minibatches > 1 else None
         # K2's pack: the loss's sample side as one 16-byte item per transition (only a permuted minibatch gathers
         # lane by lane, so only then is it worth its extra 16 B/transition of GAE writes)
-        self.pack = f32(L, N, 4) if (minibatches > 1 and fuse_gather and use_pack) else None
+        self.pack = ops.new_pack(L, N, dev) if (minibatches > 1 and fuse_gather and use_pack) else None
         self._perm_stream = torch.cuda.Stream(device=dev) if minibatches > 1 else None
         self.popart_state = torch.zeros(4, dtype=torch.float64, device=dev)
         self.popart_ms = torch.tensor([0.0, 0.1, 0.0, 0.1], dtype=torch.float64, device=dev)  # sqrt(1e-2) floor
@@ -211,7 +213,7 @@ class HotPath:
             if vtrace_new_logp is not None:  # V-trace: rho_t from the current policy (mappo.py:129-132)
                 kw = dict(vtrace_new_logp=vtrace_new_logp, vtrace_old_logp=lf["old_logp"])
             elif self.pack is not None:
-                kw = dict(old_logp=lf["old_logp"], pack=self.pack)
+                kw = dict(old_logp=lf["old_logp"], pack=self.pack, lane_aos=self.lane_aos)
                 self.pack_valid = True
             ops.gae_scan(lf["reward"], lf["value"], lf["done"], lf["truncated"], lf["on_reset"], self.gamma, self.lmbda,
                          row_lo=self.row_lo, row_hi=self.row_hi, popart_mean_std=self.popart_mean_std(), adv=self.adv,
@@ -287,7 +289,7 @@ class HotPath:
             olp, ov, rt, ad, rs, idx = m["old_logp"], m["value"], m["ret"], m["adv"], m["on_reset"], None
         elif idx is not None and self.pack is not None and self.pack_valid:
             ops.ppo_loss_batched([self._problem(e, j, new_logp, v_pred, entropy, deferred=True)], None, None, None, None,
-                                 None, self.hyper, popart_mean_std=self.popart_mean_std(), pack=self.pack[lo:hi])
+                                 None, self.hyper, popart_mean_std=self.popart_mean_std(), pack=self.pack, pack_row_lo=lo)
             return self.grads[e][j] + (None, None)
         else:
             olp, ov, rt, ad, rs = lf["old_logp"], lf["value"], self.ret, self.adv, lf["on_reset"]
@@ -312,14 +314,13 @@ class HotPath:
         lo, hi = self.row_lo, self.row_hi
         lf = self.leaf
         probs = [self._problem(e, j, *pol[e][j], deferred=False) for e, j in pairs]
-        own = self.lane_part if (self.fuse_stats and self._stats_pending) else None
         if self.minibatches > 1 and self.pack is not None and self.pack_valid:
+            own = self.lane_aos if (self.fuse_stats and self._stats_pending) else None
             ops.ppo_loss_batched(probs, None, None, None, None, None, self.hyper,
-                                 popart_mean_std=self.popart_mean_std(), pack=self.pack[lo:hi], lane_part=own)
+                                 popart_mean_std=self.popart_mean_std(), pack=self.pack, pack_row_lo=lo, lane_aos=own)
         else:
             ops.ppo_loss_batched(probs, lf["old_logp"][lo:hi], lf["value"][lo:hi], self.ret[lo:hi], self.adv[lo:hi],
-                                 lf["on_reset"][lo + 1:hi + 1], self.hyper, popart_mean_std=self.popart_mean_std(),
-                                 lane_part=own)
+                                 lf["on_reset"][lo + 1:hi + 1], self.hyper, popart_mean_std=self.popart_mean_std())
 
     def finalize(self) -> None:
         """One launch: fold every minibatch's partial rows into self.out / self.out_f32 (loss scalars + stats)."""

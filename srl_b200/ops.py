@@ -70,13 +70,16 @@ def gae_scan(reward, value, done, truncated, on_reset, gamma: float, lmbda: floa
              vtrace_new_logp: Optional[torch.Tensor] = None, vtrace_old_logp: Optional[torch.Tensor] = None,
              rho: float = 1.0, c: float = 1.0, adv: Optional[torch.Tensor] = None,
              ret: Optional[torch.Tensor] = None, lane_part: Optional[torch.Tensor] = None, want_stats: bool = True,
-             old_logp: Optional[torch.Tensor] = None, pack: Optional[torch.Tensor] = None):
+             old_logp: Optional[torch.Tensor] = None, pack: Optional[torch.Tensor] = None,
+             lane_aos: Optional[torch.Tensor] = None):
     """GAE + value target + zero padding row + per-lane statistics in one launch.
 
     reward/value float32 and done/truncated/on_reset uint8, all `[L, N(, 1)]`; returns
     (adv, ret) shaped like `value` and lane_part float64 `[8, N]` (or None).
-    `pack` (float32 `[L, N, 4]`, needs `old_logp` `[L, N]`): additionally writes the loss's sample side as one
-    16-byte item per transition, {old_logp, value, ret, mask ? adv : NaN} (see include/srl_b200.h).
+    `pack` (float32 `[ceil(L/2), N, 2, 4]` = `new_pack(L, N)`, needs `old_logp` `[L, N]`): additionally writes the loss's
+    sample side as one 16-byte item per transition, {old_logp, value, ret, mask ? adv : NaN}, the two rows of a row pair
+    next to each other (see include/srl_b200.h; `unpack_rows` gives the `[L, N, 4]` view back).
+    `lane_aos` (float64 `[N, 4]`): rows 0..2 of lane_part once more as one 32-byte item per lane.
     Reference: MultiAgentPPO._compute_adv_and_value_target (mappo.py:118-144) + F.pad (mappo.py:254-256).
     """
     L, N = _rows_lanes(value)
@@ -111,15 +114,35 @@ def gae_scan(reward, value, done, truncated, on_reset, gamma: float, lmbda: floa
         if old_logp is None:
             raise ValueError("pack needs old_logp")
         _check(old_logp, torch.float32, "old_logp")
-        if pack.numel() != L * N * 4 or _rows_lanes(old_logp) != (L, N):
-            raise ValueError(f"pack must hold [L, N, 4] = {L * N * 4} floats and old_logp [L, N]; got "
+        if pack.numel() != pack_rows(L) * N * 4 or _rows_lanes(old_logp) != (L, N):
+            raise ValueError(f"pack must hold [ceil(L/2), N, 2, 4] = {pack_rows(L) * N * 4} floats and old_logp [L, N]; got "
                              f"{tuple(pack.shape)} and {tuple(old_logp.shape)}")
+    if lane_aos is not None:
+        _check(lane_aos, torch.float64, "lane_aos")
+        if lane_part is None or tuple(lane_aos.shape) != (N, 4):
+            raise ValueError(f"lane_aos needs lane_part and shape {(N, 4)}, got {tuple(lane_aos.shape)}")
     _lib.call("srl_gae_scan", _ptr(reward), _ptr(value), _ptr(done), _ptr(truncated), _ptr(on_reset),
               _ptr(vtrace_new_logp), _ptr(vtrace_old_logp), _ptr(popart_mean_std),
               _ptr(old_logp) if pack is not None else None, L, N, int(row_lo), int(row_hi),
-              float(gamma), float(lmbda), float(rho), float(c), _ptr(adv), _ptr(ret), _ptr(lane_part), _ptr(pack),
-              _stream())
+              float(gamma), float(lmbda), float(rho), float(c), _ptr(adv), _ptr(ret), _ptr(lane_part), _ptr(lane_aos),
+              _ptr(pack), _stream())
     return adv, ret, lane_part
+
+
+def pack_rows(L: int) -> int:
+    """Rows the pair-interleaved loss pack holds for an L-row sample (L rounded up to even)."""
+    return L + (L & 1)
+
+
+def new_pack(L: int, N: int, device) -> torch.Tensor:
+    """K2's loss pack for an `[L, N]` sample: float32 `[ceil(L/2), N, 2, 4]` (include/srl_b200.h, srl_gae_scan)."""
+    return torch.empty((pack_rows(L) // 2, N, 2, 4), dtype=torch.float32, device=device)
+
+
+def unpack_rows(pack: torch.Tensor) -> torch.Tensor:
+    """`[rows, N, 4]` view-copy of a pair-interleaved pack (tests, debugging): row t = pack[t // 2, :, t % 2]."""
+    P, N = pack.shape[0], pack.shape[1]
+    return pack.permute(0, 2, 1, 3).reshape(2 * P, N, 4)
 
 
 def gae_trace(reward, value, truncated, done, on_reset, gamma, lmbda, vtrace: bool = False, imp_ratio=None,
@@ -445,17 +468,18 @@ def ppo_loss_fwd_bwd(new_logp, v_pred, entropy, old_logp, old_value, ret, adv, o
 
 
 def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on_reset_next, hyper: LossHyper,
-                     popart_mean_std=None, pack: Optional[torch.Tensor] = None,
-                     lane_part: Optional[torch.Tensor] = None) -> None:
+                     popart_mean_std=None, pack: Optional[torch.Tensor] = None, pack_row_lo: int = 0,
+                     lane_aos: Optional[torch.Tensor] = None) -> None:
     """Several minibatches of one shape in ONE launch (srl_ppo_loss_fwd_bwd_batched).
 
     Each problem is a dict with `new_logp`, `v_pred`, `entropy` (`[T, n]` float32), `norm_stats`, `local_stats`
     (float64), `grads` (three `[T, n]` float32 outputs), `workspace` (one uint8 slot row), optional `lane_idx`
     (int32 `[n]`), `out` (float64 `[16]`) and `out_f32` (float32 `[4]`); without `out` the problem is deferred
     (loss_finalize folds its slot later).  The sample side is shared: the five leaf views of ppo_loss_fwd_bwd, or
-    `pack` = K2's `[>=T, N, 4]` float32 view already offset to the first loss row.  `lane_part` (K2's `[8, N]` float64
-    table; one GPU, no PopArt, n <= 1024): the kernel adds the minibatch statistics itself and `norm_stats` /
-    `local_stats` of the problems are not read (may be omitted)."""
+    `pack` = the whole pair-interleaved pack K2 wrote (`new_pack`) with `pack_row_lo` = the sample row of loss row 0.
+    `lane_aos` (K2's `[N, 4]` float64 table; pack form with lane indices, one GPU, no PopArt, even n <= 1024): the kernel
+    adds the minibatch statistics itself and `norm_stats` / `local_stats` of the problems are not read (may be omitted).
+    The gradient tensors must not alias the policy-side inputs."""
     if not problems:
         return
     T, n = _rows_lanes(problems[0]["new_logp"])
@@ -472,8 +496,8 @@ def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on
             if g.numel() != T * n:
                 raise ValueError(f"problem {k}: gradient tensor holds {g.numel()} elements, expected {T * n}")
         ns = q.get("norm_stats")
-        if ns is None and lane_part is None:
-            raise ValueError(f"problem {k}: norm_stats is required unless lane_part is given")
+        if ns is None and lane_aos is None:
+            raise ValueError(f"problem {k}: norm_stats is required unless lane_aos is given")
         if ns is not None:
             _check(ns, torch.float64, f"problem {k} norm_stats")
         ls = q.get("local_stats")
@@ -496,10 +520,11 @@ def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on
                              _ptr(ls), _ptr(q["grads"][0]), _ptr(q["grads"][1]), _ptr(q["grads"][2]), _ptr(out),
                              _ptr(out_f32), _ptr(ws))
     if pack is not None:
-        _check_view(pack, torch.float32, "pack")
-        if pack.dim() != 3 or pack.shape[2] != 4 or pack.shape[0] < T or pack.stride(2) != 1 or pack.stride(1) != 4:
-            raise ValueError(f"pack: expected a [>=T, N, 4] float32 view, got shape {tuple(pack.shape)} strides {pack.stride()}")
-        ld_smp = pack.stride(0) // 4 if pack.shape[0] > 1 else pack.shape[1]
+        _check(pack, torch.float32, "pack")
+        if pack.dim() != 4 or pack.shape[2:] != (2, 4) or 2 * pack.shape[0] < pack_row_lo + T or pack_row_lo < 0:
+            raise ValueError(f"pack: expected K2's [ceil(L/2), N, 2, 4] float32 pack holding rows [{pack_row_lo}, "
+                             f"{pack_row_lo + T}), got shape {tuple(pack.shape)}")
+        ld_smp = pack.shape[1]
         if not has_idx and pack.shape[1] != n:
             raise ValueError(f"pack has {pack.shape[1]} lanes but the policy side has {n}")
         old_logp = old_value = ret = adv = on_reset_next = None
@@ -508,16 +533,14 @@ def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on
                               hyper.clip_value)
     if popart_mean_std is not None:
         _check(popart_mean_std, torch.float64, "popart_mean_std")
-    lp_n = 0
-    if lane_part is not None:
-        _check(lane_part, torch.float64, "lane_part")
-        if lane_part.dim() != 2 or lane_part.shape[0] != SRL_LANE_PART:
-            raise ValueError(f"lane_part: expected [{SRL_LANE_PART}, N] float64, got {tuple(lane_part.shape)}")
-        lp_n = lane_part.shape[1]
+    if lane_aos is not None:
+        _check(lane_aos, torch.float64, "lane_aos")
+        if pack is None or lane_aos.dim() != 2 or tuple(lane_aos.shape) != (pack.shape[1], 4):
+            raise ValueError(f"lane_aos: expected [N, 4] float64 beside the pack, got {tuple(lane_aos.shape)}")
     hc = hyper.to_c()
     _lib.call("srl_ppo_loss_fwd_bwd_batched", arr, len(problems), n, n, _ptr(old_logp), _ptr(old_value), _ptr(ret),
-              _ptr(adv), _ptr(on_reset_next), ld_smp, _ptr(pack), _ptr(lane_part), lp_n, T, n, _ptr(popart_mean_std),
-              ctypes.byref(hc), slot_bytes, _stream())
+              _ptr(adv), _ptr(on_reset_next), ld_smp, _ptr(pack), int(pack_row_lo), _ptr(lane_aos), T, n,
+              _ptr(popart_mean_std), ctypes.byref(hc), slot_bytes, _stream())
 
 
 def ppo_loss_from_logits(logits, action, head_sizes: Sequence[int], v_pred, old_logp, old_value, ret, adv, on_reset_next,

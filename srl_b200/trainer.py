@@ -51,7 +51,7 @@ class _PopArtBridge:
         rms = getattr(head, "_PopArtValueHead__rms", None) if head is not None else None
         if rms is None:
             raise ValueError("popart=True needs a policy whose `popart_head` is a PopArtValueHead "
-                             "(legacy/algorithm/modules/popart.py) or srl_b200.testing.PopArtHead")
+                             "(legacy/algorithm/modules/popart.py) or the test double tests/doubles.py::PopArtValueHead")
         self.head, self.rms = head, rms
         g = lambda obj, cls, name: getattr(obj, f"_{cls}__{name}")
         self.mean, self.mean_sq = g(rms, "RunningMeanStd", "mean"), g(rms, "RunningMeanStd", "mean_sq")

@@ -101,11 +101,12 @@ class PopArtValueHead(nn.Module):
 
 class _Net(nn.Module):
 
-    def __init__(self, obs_dim, num_actions, hidden, popart, popart_beta, burn_in_updates):
+    def __init__(self, obs_dim, num_actions, hidden, popart, popart_beta, burn_in_updates, popart_head_cls=None):
         super().__init__()
         self.body = nn.Sequential(nn.Linear(obs_dim, hidden), nn.Tanh())
         self.actor = nn.Linear(hidden, num_actions)
-        self.critic = (PopArtValueHead(hidden, 1, beta=popart_beta, burn_in_updates=burn_in_updates) if popart else
+        head = popart_head_cls or PopArtValueHead  # oracle/make_golden.py passes the reference's own class
+        self.critic = (head(hidden, 1, beta=popart_beta, burn_in_updates=burn_in_updates) if popart else
                        nn.Linear(hidden, 1))
 
     def forward(self, x):
@@ -119,10 +120,10 @@ class TinyActorCriticPolicy:
     get/load_checkpoint, distributed and the three PopArt hooks."""
 
     def __init__(self, obs_dim=6, num_actions=5, hidden=16, device="cuda:0", popart=False, popart_beta=0.99,
-                 burn_in_updates=float("inf"), seed=0, denormalize_value_during_rollout=False):
+                 burn_in_updates=float("inf"), seed=0, denormalize_value_during_rollout=False, popart_head_cls=None):
         g = torch.random.get_rng_state()
         torch.manual_seed(seed)
-        self._net = _Net(obs_dim, num_actions, hidden, popart, popart_beta, burn_in_updates).to(device)
+        self._net = _Net(obs_dim, num_actions, hidden, popart, popart_beta, burn_in_updates, popart_head_cls).to(device)
         torch.random.set_rng_state(g)
         self.device = device
         self._version = -1

@@ -48,7 +48,7 @@ def test_abi_version_and_error_text(lib):
     assert lib.srl_abi_version() == _lib.ABI_VERSION
     # invalid arguments are rejected on the host, before any CUDA call: status + message, no abort
     rc = lib.srl_gae_scan(None, None, None, None, None, None, None, None, None, 1, 1, 0, 0, 0.99, 0.95, 1.0, 1.0, None,
-                          None, None, None, None)
+                          None, None, None, None, None)
     assert rc == 1
     assert b"L >= 2" in lib.srl_last_error()
     rc = lib.srl_philox_perm(0, 0, 1, -1, 1, None, None)

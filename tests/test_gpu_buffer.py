@@ -118,7 +118,7 @@ def test_missing_leaf_is_zero_filled():
 def test_trainer_consumes_device_batch():
     """MultiAgentPPOB200.step on a DeviceSlabBuffer batch == the same step on the host-stacked batch."""
     from srl_b200.buffer import DeviceSlabBuffer
-    from srl_b200.testing import TinyActorCriticPolicy
+    from tests.doubles import TinyActorCriticPolicy
     from srl_b200.trainer import MultiAgentPPOB200
     from tests.test_gpu_trainer import NUM_ACTIONS, OBS_DIM, make_sample
     cfg = synth.PathConfig("buf", T=12, B=8, p_end=0.08)

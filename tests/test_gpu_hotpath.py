@@ -83,6 +83,14 @@ CASES = {
     "boot_burn": synth.PathConfig("boot_burn", T=10, B=12, bootstrap_steps=5, burn_in_steps=3, epochs=1, minibatches=1,
                                   p_end=0.1, popart=True, value_loss="mse"),
     "one_pass": synth.PathConfig("one_pass", T=33, B=50, epochs=1, minibatches=1, p_end=0.05),
+    # the pair kernel's corners: an odd first loss row and an odd number of loss rows (half-used row pairs at both ends)
+    "mb_burn_odd": synth.PathConfig("mb_burn_odd", T=13, B=24, bootstrap_steps=3, burn_in_steps=3, epochs=2, minibatches=3,
+                                    p_end=0.08, clip_value=True, dual_clip=True, value_loss="mse"),
+    # several column tiles per minibatch, CTA ranges that cross column and minibatch boundaries
+    "mb_wide": synth.PathConfig("mb_wide", T=21, B=1536, epochs=2, minibatches=2, p_end=0.05, clip_value=True,
+                                dual_clip=False, value_loss="huber", value_loss_delta=10.0),
+    # an odd minibatch width: the pack form on the row-tile kernel (one lane per thread)
+    "mb_odd_width": synth.PathConfig("mb_odd_width", T=9, B=27, epochs=1, minibatches=3, p_end=0.1),
 }
 
 

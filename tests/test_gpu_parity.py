@@ -581,14 +581,17 @@ def test_gae_pack_matches_leaves(ops, L, N):
     cfg = synth.PathConfig("pack", T=L - 1, B=N, p_end=0.1, gamma=0.995, lmbda=0.9)
     s = synth.make_sample_scalars(cfg, seed=L + N)
     d = {k: dev(flat2(v)) for k, v in s.items()}
-    pack = torch.full((L, N, 4), 7.0, dtype=torch.float32, device="cuda")
+    pack = ops.new_pack(L, N, "cuda").fill_(7.0)
+    aos = torch.full((N, 4), 7.0, dtype=torch.float64, device="cuda")
     adv, ret, part = ops.gae_scan(d["reward"], d["value"], d["done"], d["truncated"], d["on_reset"], cfg.gamma, cfg.lmbda,
-                                  old_logp=d["old_logp"], pack=pack)
+                                  old_logp=d["old_logp"], pack=pack, lane_aos=aos)
     adv2, ret2, part2 = ops.gae_scan(d["reward"], d["value"], d["done"], d["truncated"], d["on_reset"], cfg.gamma,
                                      cfg.lmbda)
     torch.cuda.synchronize()
     assert torch.equal(adv, adv2) and torch.equal(ret, ret2) and torch.equal(part, part2)
-    pk = pack.cpu().numpy()
+    # lane_aos: rows 0..2 of lane_part once more, one 32-byte item per lane
+    assert torch.equal(aos[:, :3], part[:3].t()) and not aos[:, 3].any()
+    pk = ops.unpack_rows(pack)[:L].cpu().numpy()  # pair-interleaved [ceil(L/2), N, 2, 4] -> rows
     assert np.array_equal(pk[..., 0], flat2(s["old_logp"]))
     assert np.array_equal(pk[..., 1], flat2(s["value"]))
     assert np.array_equal(pk[..., 2], ret.cpu().numpy())
@@ -609,7 +612,7 @@ def test_loss_batched_equals_single_launches(ops, mode, T, N, n, K):
     s = synth.make_sample_scalars(cfg, seed=5)
     L = cfg.L
     d = {k: dev(flat2(v)) for k, v in s.items()}
-    pack = torch.empty((L, N, 4), dtype=torch.float32, device="cuda")
+    pack = ops.new_pack(L, N, "cuda")
     adv, ret, part = ops.gae_scan(d["reward"], d["value"], d["done"], d["truncated"], d["on_reset"], cfg.gamma, cfg.lmbda,
                                   row_lo=0, row_hi=T, old_logp=d["old_logp"], pack=pack)
     rng = np.random.default_rng(1)
@@ -636,7 +639,7 @@ def test_loss_batched_equals_single_launches(ops, mode, T, N, n, K):
         singles.append(ops.ppo_loss_fwd_bwd(nl, vp, en, d["old_logp"][:T], d["value"][:T], ret[:T], adv[:T],
                                             d["on_reset"][1:T + 1], stats, hp, lane_idx=li, workspace=ws[K + k]))
     if mode == "pack":
-        ops.ppo_loss_batched(probs, None, None, None, None, None, hp, pack=pack[:T])
+        ops.ppo_loss_batched(probs, None, None, None, None, None, hp, pack=pack, pack_row_lo=0)
     else:
         ops.ppo_loss_batched(probs, d["old_logp"][:T], d["value"][:T], ret[:T], adv[:T], d["on_reset"][1:T + 1], hp)
     torch.cuda.synchronize()
@@ -644,7 +647,9 @@ def test_loss_batched_equals_single_launches(ops, mode, T, N, n, K):
         g_lp, g_v, g_en, out, out32 = singles[k]
         for a, b in zip(probs[k]["grads"], (g_lp, g_v, g_en)):
             assert torch.equal(a, b), f"problem {k}: batched gradient differs from the single launch"
-        np.testing.assert_allclose(probs[k]["out"].cpu().numpy(), out.cpu().numpy(), rtol=1e-12, atol=1e-14)
+        # the pair kernel (even-width pack form) groups the fp32 partial sums differently from the row-tile kernel
+        rtol = 2e-6 if (mode == "pack" and n % 2 == 0) else 1e-12
+        np.testing.assert_allclose(probs[k]["out"].cpu().numpy(), out.cpu().numpy(), rtol=rtol, atol=1e-9 if rtol > 1e-9 else 1e-14)
         np.testing.assert_allclose(probs[k]["out_f32"].cpu().numpy(), out32.cpu().numpy(), rtol=1e-6)
 
 
@@ -833,7 +838,7 @@ def test_gae_ws_kernel_repeatable_under_load(ops):
     s = synth.make_sample_scalars(cfg, seed=11)
     d = {k: dev(flat2(v)) for k, v in s.items()}
     L, N = cfg.L, cfg.N
-    pack = torch.empty((L, N, 4), dtype=torch.float32, device="cuda")
+    pack = ops.new_pack(L, N, "cuda")
     run = lambda: ops.gae_scan(d["reward"], d["value"], d["done"], d["truncated"], d["on_reset"], cfg.gamma, cfg.lmbda,
                                row_lo=0, row_hi=cfg.T, old_logp=d["old_logp"], pack=pack)
     adv0, ret0, part0 = (x.clone() for x in run())

@@ -11,7 +11,7 @@ import torch
 from oracle.ref_trainer import RefPPOTrainer
 from srl_b200 import api, synth
 from srl_b200.namedarray import NamedArray
-from srl_b200.testing import TinyActorCriticPolicy
+from tests.doubles import TinyActorCriticPolicy
 from tests.util import assert_close_ref
 
 pytestmark = pytest.mark.gpu

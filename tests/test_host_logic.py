@@ -7,7 +7,7 @@ import torch
 from oracle import ref_math as M
 from oracle.ref_trainer import RefPPOTrainer
 from srl_b200 import api, namedarray as na, synth
-from srl_b200.testing import PopArtValueHead, TinyActorCriticPolicy
+from tests.doubles import PopArtValueHead, TinyActorCriticPolicy
 from tests.util import load_golden
 
 
