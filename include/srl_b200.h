@@ -352,7 +352,11 @@ int srl_host_copy(void* dst, const void* src, size_t bytes, int threads);
  *   handle  : 64-byte IPC handle of the local mailbox, to be sent to every peer (any host channel)
  *   connect : `handles` = world * 64 bytes, rank-major; opens the peers' mailboxes
  *   allreduce_sum : global[i] = sum over ranks of local[i], i < n; every rank must call it the same number of times
- *   status  : 0, or 1 when a wait timed out (a peer never arrived); synchronises the device
+ *   status  : 0, or 1 when a wait timed out (a peer never arrived); synchronises the device.  status_async copies the
+ *             same word into PINNED host memory on `stream` (read it after the caller's own synchronisation).
+ *   set_timeout : how long a rank waits for its peers' words (default ~10 minutes: a late peer is late, not gone).  When
+ *             the wait does expire NO sums are produced: the whole output table is NaN and the status is sticky, so
+ *             nothing downstream can silently train on stale statistics; callers check the status every step and raise.
  * ------------------------------------------------------------------------------------------ */
 #define SRL_XCHG_HANDLE_BYTES 64
 typedef struct srl_xchg srl_xchg;
@@ -366,6 +370,8 @@ int srl_xchg_local_handle(srl_xchg* x, void* handle_out);
 int srl_xchg_connect(srl_xchg* x, const void* handles);
 int srl_xchg_allreduce_sum(srl_xchg* x, const double* local, double* global, int n, srl_stream_t stream);
 int srl_xchg_status(srl_xchg* x, int* status_out);
+int srl_xchg_status_async(srl_xchg* x, int* pinned_status_out, srl_stream_t stream);
+int srl_xchg_set_timeout(srl_xchg* x, double seconds);
 int srl_xchg_destroy(srl_xchg* x);
 
 #ifdef __cplusplus

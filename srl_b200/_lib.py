@@ -113,6 +113,8 @@ SIGNATURES = {
     "srl_xchg_connect": (c_int, [c_void_p, c_void_p]),
     "srl_xchg_allreduce_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "srl_xchg_status": (c_int, [c_void_p, POINTER(c_int)]),
+    "srl_xchg_status_async": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "srl_xchg_set_timeout": (c_int, [c_void_p, c_double]),
     "srl_xchg_destroy": (c_int, [c_void_p]),
 }
 

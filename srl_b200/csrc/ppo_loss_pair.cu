@@ -14,12 +14,15 @@
 //    of three 32-byte sectors (~40 MB).  K2 now also writes them as one 32-byte item per lane (lane_aos) and a CTA adds
 //    them with one 256-bit gather per lane.
 //  * the grid was (column tile, row group, problem) sized to one wave: 832 CTAs on 888 slots, and 9.25 row groups per
-//    column do not divide 128 rows.  Here the (problem, column tile, row pair) units are numbered in one line and CTA g of
-//    G takes units [g * U / G, (g + 1) * U / G): every CTA gets the same number of steps (+-1), for any shape.
+//    column do not divide 128 rows.  Here a problem's (column tile, row pair) units are numbered in one line and dealt to
+//    its CTAs in equal runs (+-1 unit), for any shape; small CTAs (64 threads) keep the units fine.
+//  * the epilogue held every CTA through three block barriers, eight fences and an atomic round trip; here the warps
+//    leave after one barrier and warp 0 alone writes the partial row and takes the ticket.
 //
-// A CTA's range may cross into the next problem: it then writes one partial row per problem it touched; a problem's rows are
-// the CTAs whose ranges intersect it (computable from the unit numbering alone), folded in CTA order by the last one to
-// arrive (ticket) -- deterministic for a given launch shape, as before.
+// A problem's partial rows are its CTAs, folded in CTA order by the last one to arrive (ticket) -- deterministic for a
+// given launch shape, as before.  (First version of this file: one line of units over ALL problems; the 16 of 592 CTAs
+// whose run crossed a problem boundary paid prologue and epilogue twice and set the kernel's duration -- ncu: slowest SM
+// 51.6 K active cycles, average 36.7 K, profiles/r2_notes.md.)
 #include <stdlib.h>
 
 #include "ppo_loss.cuh"
@@ -29,10 +32,10 @@ namespace loss {
 namespace {
 
 #ifndef SRL_PAIR_THREADS
-#define SRL_PAIR_THREADS 128
+#define SRL_PAIR_THREADS 64
 #endif
 #ifndef SRL_PAIR_MIN_BLOCKS
-#define SRL_PAIR_MIN_BLOCKS 4
+#define SRL_PAIR_MIN_BLOCKS 8
 #endif
 constexpr int kPairThreads = SRL_PAIR_THREADS;
 constexpr int kPairLanes = 2 * kPairThreads;  // lanes per column tile
@@ -43,7 +46,6 @@ struct PairSched {
   int pairs;      // row pairs per column
   int col_tiles;  // column tiles per problem
   int cpp;        // units per problem = col_tiles * pairs
-  long long units;
 };
 
 // Both rows' policy outputs of this thread's two lanes, and its two lanes' row pairs of the pack.
@@ -71,27 +73,34 @@ __device__ __forceinline__ void ld_nc256(const double* p, double (&v)[4]) {
 // the warp tree, then the warps in order -- the same order in every CTA, so they normalise with bit-identical statistics.
 __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__ lane_aos, const int32_t* __restrict__ idx,
                                                       int n, double adv_eps, double& mask_sum, double (*s_part)[8]) {
+  // kStatBatch gathers in flight per thread at a time (all index loads first): two dependent rounds for 1024 lanes on
+  // 64 threads instead of sixteen, without holding 16 x 4 doubles in registers
+  constexpr int kStatBatch = kStatMax < 8 ? kStatMax : 8;
   int ci[kStatMax];
 #pragma unroll
   for (int q = 0; q < kStatMax; ++q) {
     const int i = threadIdx.x + q * kPairThreads;
     ci[q] = i < n ? __ldg(idx + i) : -1;
   }
-  double v[kStatMax][4];
-#pragma unroll
-  for (int q = 0; q < kStatMax; ++q) {
-    if (ci[q] >= 0) {
-      ld_nc256(lane_aos + 4 * static_cast<size_t>(ci[q]), v[q]);
-    } else {
-      v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.0;
-    }
-  }
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
 #pragma unroll
-  for (int q = 0; q < kStatMax; ++q) {
-    a0 += v[q][0];
-    a1 += v[q][1];
-    a2 += v[q][2];
+  for (int q0 = 0; q0 < kStatMax; q0 += kStatBatch) {
+    if (q0 * kPairThreads >= n) break;  // uniform: the minibatch ends before this batch
+    double v[kStatBatch][4];
+#pragma unroll
+    for (int q = 0; q < kStatBatch; ++q) {
+      if (ci[q0 + q] >= 0) {
+        ld_nc256(lane_aos + 4 * static_cast<size_t>(ci[q0 + q]), v[q]);
+      } else {
+        v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kStatBatch; ++q) {
+      a0 += v[q][0];
+      a1 += v[q][1];
+      a2 += v[q][2];
+    }
   }
   a0 = warp_sum(a0);
   a1 = warp_sum(a1);
@@ -115,27 +124,119 @@ __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__
   return uniforms_from(cnt, s1, s2, cnt, nullptr, adv_eps);
 }
 
+// Block reduction of the eight masked sums for the pair kernel: every warp's tree, then warp 0 alone adds the warps, writes
+// the CTA's partial row and takes the problem's ticket -- the other warps are done after ONE block barrier (the round-1
+// epilogue held the whole CTA through three barriers, eight fences and the atomic's round trip).  The last CTA's warp 0
+// folds the problem's rows in row order (deterministic for a given launch shape).
+__device__ __forceinline__ void pair_reduce_and_finalize(const Problem& pr, const LossHyperDev& h, const Acc& acc,
+                                                         double mask_sum, int row, int n_rows, double (*sred)[8]) {
+  double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(pr.slot) + kPartialsOffset);
+  double v[kNumSums] = {acc.pl, acc.vl, acc.en, acc.adv, acc.ratio, static_cast<double>(acc.clip), acc.vt, acc.ret};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWarps = kPairThreads / 32;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double w[kNumSums];
+#pragma unroll
+    for (int k = 0; k < kNumSums; ++k) w[k] = __shfl_xor_sync(0xffffffffu, v[k], o);
+#pragma unroll
+    for (int k = 0; k < kNumSums; ++k) v[k] += w[k];
+  }
+  if (kWarps > 1) {
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < kNumSums; ++k) sred[k][warp] = v[k];
+    }
+    __syncthreads();
+    if (warp != 0) return;
+  }
+  if (lane < kNumSums) {
+    double s = 0.0;
+    if (kWarps > 1) {
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += sred[lane][w];
+    } else {
+      // lane k keeps sum k: all lanes hold all sums after the butterfly
+#pragma unroll
+      for (int k = 0; k < kNumSums; ++k) s = (lane == k) ? v[k] : s;
+    }
+    partials[static_cast<size_t>(row) * kNumSums + lane] = s;
+  }
+  if (pr.out == nullptr) {  // deferred: publish what the finaliser needs and leave
+    if (row == 0 && lane == 0) {
+      pr.slot->n_rows = n_rows;
+      pr.slot->mask_sum = mask_sum;
+      pr.slot->wv = static_cast<double>(h.wv);
+      pr.slot->we = static_cast<double>(h.we);
+    }
+    return;
+  }
+  __syncwarp();
+  unsigned int done = 0;
+  if (lane == 0) {
+    __threadfence();  // the row above (written by this warp, ordered by the warp barrier) before the ticket
+    done = atomicAdd(&pr.slot->ticket, 1u);
+  }
+  done = __shfl_sync(0xffffffffu, done, 0);
+  if (done != static_cast<unsigned int>(n_rows) - 1u) return;
+  __threadfence();
+  // fold: lane k (and k + 8, k + 16, k + 24) walks the rows of sum k in row order, then the four quarter sums are added
+  const int k = lane & 7, part = lane >> 3;
+  double s = 0.0;
+  for (int r = part; r < n_rows; r += 4) s += __ldcg(partials + static_cast<size_t>(r) * kNumSums + k);
+  s += __shfl_down_sync(0xffffffffu, s, 16);
+  s += __shfl_down_sync(0xffffffffu, s, 8);
+  // lanes 0..7 hold the eight sums; gather them into lane 0
+  double t[kNumSums];
+#pragma unroll
+  for (int q = 0; q < kNumSums; ++q) t[q] = __shfl_sync(0xffffffffu, s, q);
+  if (lane == 0) {
+    const double M = mask_sum, wv = static_cast<double>(h.wv), we = static_cast<double>(h.we);
+    const double pl = t[0] / M, vl = t[1] / M, el = -t[2] / M;
+    const double loss = pl + wv * vl + we * el;
+    double* o = pr.out;
+    o[SRL_OUT_LOSS] = loss;
+    o[SRL_OUT_POLICY_LOSS] = pl;
+    o[SRL_OUT_VALUE_LOSS] = vl;
+    o[SRL_OUT_ENTROPY_LOSS] = el;
+    o[SRL_OUT_ADVANTAGE] = t[3] / M;
+    o[SRL_OUT_IMPORTANCE_WEIGHT] = t[4] / M;
+    o[SRL_OUT_CLIP_RATIO] = t[5] / M;
+    o[SRL_OUT_VALUE_TARGETS] = t[6] / M;
+    o[SRL_OUT_DENORM_VALUE] = t[7] / M;
+    o[SRL_OUT_MASK_SUM] = M;
+    for (int q = SRL_OUT_MASK_SUM + 1; q < SRL_LOSS_OUT_LEN; ++q) o[q] = 0.0;
+    if (pr.out_f32) {
+      pr.out_f32[0] = static_cast<float>(loss);
+      pr.out_f32[1] = static_cast<float>(pl);
+      pr.out_f32[2] = static_cast<float>(vl);
+      pr.out_f32[3] = static_cast<float>(el);
+    }
+    pr.slot->ticket = 0u;  // ready for the next launch on this slot
+  }
+}
+
+// grid = (slices, problems): CTA (x, k) owns units [x * cpp / slices, (x + 1) * cpp / slices) of problem k, a unit being one
+// row pair of one column tile, numbered column tile by column tile.  A CTA never leaves its problem: the statistics
+// prologue and the reduction epilogue (a few microseconds of dependent latency each) are paid exactly once per CTA, and
+// a problem's partial rows are its `slices` CTAs.
 template <class CFG>
 __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pair_kernel(const __grid_constant__ LossBatch b,
                                                                                           const PairSched sc) {
-  __shared__ double s_part[3][8];
+  __shared__ double s_part[8][8];
   const LossShared& s = b.s;
   const LossHyperDev& h = s.h;
+  const Problem& pr = b.prob[blockIdx.y];
   const int n = s.n, T = s.T, row_lo = s.row_lo;
   const long long N2 = 2 * s.ld_smp;  // float4 items per row pair of the pack
-  const long long u_begin = static_cast<long long>(blockIdx.x) * sc.units / gridDim.x;
-  const long long u_end = static_cast<long long>(blockIdx.x + 1) * sc.units / gridDim.x;
-
-  // ---- where this CTA starts ------------------------------------------------------------------------------------
-  long long u = u_begin;
-  int col = static_cast<int>(u / sc.pairs);
-  int pi = static_cast<int>(u - static_cast<long long>(col) * sc.pairs);
-  int k = col / sc.col_tiles;
-  int ct = col - k * sc.col_tiles;
+  const int u_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * sc.cpp / gridDim.x);
+  const int u_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * sc.cpp / gridDim.x);
+  int ct = u_begin / sc.pairs;
+  int pi = u_begin - ct * sc.pairs;
 
   Stage sA, sB;
-  // policy-side loads of row pair `p` (index within the column) of problem `pr`, lanes j, j + 1
-  auto issue_policy = [&](Stage& st, const Problem& pr, int p, int j) {
+  // policy-side loads of row pair `p` (index within the column), lanes j, j + 1
+  auto issue_policy = [&](Stage& st, int p, int j) {
     const int r0 = 2 * (sc.pair_lo + p) - row_lo;  // loss row of the pair's first row (-1: before the first loss row)
     const long long o = static_cast<long long>(r0) * s.ld_pol + j;
     if (r0 >= 0) {
@@ -159,7 +260,7 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
   // not depend on it, so the first step's policy-side loads are in flight before the wait.
   {
     const int j = (ct * kPairThreads + threadIdx.x) * 2;
-    if (j < n) issue_policy(sA, b.prob[k], pi, j);
+    if (j < n) issue_policy(sA, pi, j);
   }
   pdl_wait();
 
@@ -167,96 +268,80 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
   RowSums rs;
   int pending = 0;
   bool first = true;
-  while (u < u_end) {
-    const Problem& pr = b.prob[k];
-    double mask_sum = 0.0;
-    Uniforms uf;
-    bool have_u = false;
-    // ---- all column segments of this problem that fall into the CTA's range -----------------------------------
-    while (u < u_end) {
-      const int j = (ct * kPairThreads + threadIdx.x) * 2;
-      const bool active = j < n;
-      const int p_end = static_cast<int>(min(static_cast<long long>(sc.pairs), pi + (u_end - u)));
-      int c[2] = {j, j + 1};
-      if (pr.lane_idx && active) {
-        const int2 q = __ldg(reinterpret_cast<const int2*>(pr.lane_idx + j));
-        c[0] = q.x, c[1] = q.y;
-      }
-      if (active) {
-        if (!first) issue_policy(sA, pr, pi, j);
-        issue_pack(sA, pi, c);
-      }
-      first = false;
-      if (!have_u) {  // once per problem; the first step's loads are in flight underneath
-        if (s.lane_aos != nullptr)
-          uf = self_uniforms_aos(s.lane_aos, pr.lane_idx, n, h.adv_eps, mask_sum, s_part);
-        else
-          uf = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
-        have_u = true;
-      }
-      if (active) {
-        // one step: both rows of the pair, both lanes; masked or out-of-range rows produce nothing
-        auto compute = [&](const Stage& st, int p) {
-          const int r0 = 2 * (sc.pair_lo + p) - row_lo;
+  double mask_sum = 0.0;
+  Uniforms uf;
+  bool have_u = false;
+  for (int u = u_begin; u < u_end;) {  // the column segments of this CTA's range
+    const int j = (ct * kPairThreads + threadIdx.x) * 2;
+    const bool active = j < n;
+    const int p_end = min(sc.pairs, pi + (u_end - u));
+    int c[2] = {j, j + 1};
+    if (pr.lane_idx && active) {
+      const int2 q = __ldg(reinterpret_cast<const int2*>(pr.lane_idx + j));
+      c[0] = q.x, c[1] = q.y;
+    }
+    if (active) {
+      if (!first) issue_policy(sA, pi, j);
+      issue_pack(sA, pi, c);
+    }
+    first = false;
+    if (!have_u) {  // once per CTA; the first step's loads are in flight underneath
+      if (s.lane_aos != nullptr)
+        uf = self_uniforms_aos(s.lane_aos, pr.lane_idx, n, h.adv_eps, mask_sum, s_part);
+      else
+        uf = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
+      have_u = true;
+    }
+    if (active) {
+      // one step: both rows of the pair, both lanes; masked or out-of-range rows produce nothing
+      auto compute = [&](const Stage& st, int p) {
+        const int r0 = 2 * (sc.pair_lo + p) - row_lo;
 #pragma unroll
-          for (int rr = 0; rr < 2; ++rr) {
-            const int r = r0 + rr;
-            if (r < 0 || r >= T) continue;
-            float glp[2], gv[2], ge[2];
-            const float nl[2] = {st.nl[rr].x, st.nl[rr].y}, vp[2] = {st.vp[rr].x, st.vp[rr].y},
-                        en[2] = {st.en[rr].x, st.en[rr].y};
+        for (int rr = 0; rr < 2; ++rr) {
+          const int r = r0 + rr;
+          if (r < 0 || r >= T) continue;
+          float glp[2], gv[2], ge[2];
+          const float nl[2] = {st.nl[rr].x, st.nl[rr].y}, vp[2] = {st.vp[rr].x, st.vp[rr].y},
+                      en[2] = {st.en[rr].x, st.en[rr].y};
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const float ad = st.pk[q][4 * rr + 3];
-              element<CFG>(h, uf, nl[q], vp[q], en[q], st.pk[q][4 * rr + 0], st.pk[q][4 * rr + 1], st.pk[q][4 * rr + 2], ad,
-                           ad == ad, glp[q], gv[q], ge[q], rs);
-            }
-            const long long o = static_cast<long long>(r) * s.ld_grad + j;
-            stg_stream(reinterpret_cast<float2*>(pr.g_logp + o), make_float2(glp[0], glp[1]));
-            stg_stream(reinterpret_cast<float2*>(pr.g_value + o), make_float2(gv[0], gv[1]));
-            stg_stream(reinterpret_cast<float2*>(pr.g_entropy + o), make_float2(ge[0], ge[1]));
+          for (int q = 0; q < 2; ++q) {
+            const float ad = st.pk[q][4 * rr + 3];
+            element<CFG>(h, uf, nl[q], vp[q], en[q], st.pk[q][4 * rr + 0], st.pk[q][4 * rr + 1], st.pk[q][4 * rr + 2], ad,
+                         ad == ad, glp[q], gv[q], ge[q], rs);
           }
-          if (++pending == kFlushRows / 2) {  // fp32 partial sums of at most kFlushRows * 2 terms, then float64
-            acc.add(rs);
-            rs = RowSums();
-            pending = 0;
-          }
-        };
-        int p = pi;
-        while (true) {
-          if (p + 1 < p_end) {
-            issue_policy(sB, pr, p + 1, j);
-            issue_pack(sB, p + 1, c);
-          }
-          compute(sA, p);
-          if (++p >= p_end) break;
-          if (p + 1 < p_end) {
-            issue_policy(sA, pr, p + 1, j);
-            issue_pack(sA, p + 1, c);
-          }
-          compute(sB, p);
-          if (++p >= p_end) break;
+          const long long o = static_cast<long long>(r) * s.ld_grad + j;
+          stg_stream(reinterpret_cast<float2*>(pr.g_logp + o), make_float2(glp[0], glp[1]));
+          stg_stream(reinterpret_cast<float2*>(pr.g_value + o), make_float2(gv[0], gv[1]));
+          stg_stream(reinterpret_cast<float2*>(pr.g_entropy + o), make_float2(ge[0], ge[1]));
         }
-      }
-      u += p_end - pi;
-      // next column: same problem (next column tile) or the next problem
-      pi = 0;
-      if (++ct == sc.col_tiles) {
-        ct = 0;
-        break;
+        if (++pending == kFlushRows) {  // fp32 partial sums of at most kFlushRows * 4 terms, then float64
+          acc.add(rs);
+          rs = RowSums();
+          pending = 0;
+        }
+      };
+      int p = pi;
+      while (true) {
+        if (p + 1 < p_end) {
+          issue_policy(sB, p + 1, j);
+          issue_pack(sB, p + 1, c);
+        }
+        compute(sA, p);
+        if (++p >= p_end) break;
+        if (p + 1 < p_end) {
+          issue_policy(sA, p + 1, j);
+          issue_pack(sA, p + 1, c);
+        }
+        compute(sB, p);
+        if (++p >= p_end) break;
       }
     }
-    // ---- this CTA's partial row of problem k ----------------------------------------------------------------------
-    acc.add(rs);
-    rs = RowSums();
-    pending = 0;
-    const long long x0 = static_cast<long long>(k) * sc.cpp, x1 = x0 + sc.cpp - 1;  // the problem's first and last unit
-    const int g0 = static_cast<int>(((x0 + 1) * gridDim.x - 1) / sc.units);         // CTA that holds unit x0
-    const int g1 = static_cast<int>(((x1 + 1) * gridDim.x - 1) / sc.units);
-    reduce_and_finalize(pr, h, acc, mask_sum, static_cast<int>(blockIdx.x) - g0, g1 - g0 + 1);
-    acc = Acc();
-    ++k;
+    u += p_end - pi;
+    pi = 0;
+    ++ct;
   }
+  acc.add(rs);
+  pair_reduce_and_finalize(pr, h, acc, mask_sum, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), s_part);
 }
 
 template <class CFG>
@@ -277,13 +362,13 @@ int launch_pair(LossBatch& b, int n_problems, cudaStream_t st) {
   sc.pairs = ((s.row_lo + s.T - 1) >> 1) - sc.pair_lo + 1;
   sc.col_tiles = (s.n + kPairLanes - 1) / kPairLanes;
   sc.cpp = sc.col_tiles * sc.pairs;
-  sc.units = static_cast<long long>(sc.cpp) * n_problems;
-  long long grid = static_cast<long long>(sm_count()) * resident[dev];
-  if (grid > sc.units) grid = sc.units;
-  // a problem's partial rows: one per CTA whose range intersects it
-  SRL_REQUIRE(grid / n_problems + 2 <= kMaxGrid, SRL_ERR_UNSUPPORTED, "ppo loss: %lld CTAs per problem exceed the workspace slot",
-              grid / n_problems + 2);
-  SRL_CUDA(launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(kPairThreads), 0, st, b, sc));
+  // slices per problem: the whole grid resident at once (one wave), every CTA inside ONE problem
+  long long slices = static_cast<long long>(sm_count()) * resident[dev] / n_problems;
+  if (slices > sc.cpp) slices = sc.cpp;
+  if (slices > kMaxGrid) slices = kMaxGrid;  // one partial row per CTA in the workspace slot
+  if (slices < 1) slices = 1;
+  SRL_CUDA(launch_pdl(kern, dim3(static_cast<unsigned>(slices), static_cast<unsigned>(n_problems)), dim3(kPairThreads), 0, st,
+                      b, sc));
   return SRL_OK;
 }
 

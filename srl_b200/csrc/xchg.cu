@@ -74,6 +74,7 @@ extern "C" int srl_xchg_create(int world, int rank, int capacity_doubles, srl_xc
   x->view.world = world;
   x->view.rank = rank;
   x->view.cap = capacity_doubles;
+  x->view.spin_limit = kDefaultSpinLimit;
   for (int p = 0; p < kMaxWorld; ++p) x->view.mailbox[p] = nullptr;
   fill_view_for(x->view, rank, x->local_base, world, capacity_doubles);
   char* tail = static_cast<char*>(x->local_base) + mailbox_bytes(world, capacity_doubles);
@@ -131,6 +132,23 @@ extern "C" int srl_xchg_status(srl_xchg* h, int* status_out) {
   SRL_REQUIRE(h && status_out, SRL_ERR_INVALID_ARG, "srl_xchg_status: null pointer");
   Xchg* x = reinterpret_cast<Xchg*>(h);
   SRL_CUDA(cudaMemcpy(status_out, x->view.status, sizeof(int), cudaMemcpyDeviceToHost));
+  return SRL_OK;
+}
+
+extern "C" int srl_xchg_status_async(srl_xchg* h, int* pinned_status_out, srl_stream_t stream) {
+  using namespace srl;
+  SRL_REQUIRE(h && pinned_status_out, SRL_ERR_INVALID_ARG, "srl_xchg_status_async: null pointer");
+  Xchg* x = reinterpret_cast<Xchg*>(h);
+  SRL_CUDA(cudaMemcpyAsync(pinned_status_out, x->view.status, sizeof(int), cudaMemcpyDeviceToHost,
+                           static_cast<cudaStream_t>(stream)));
+  return SRL_OK;
+}
+
+extern "C" int srl_xchg_set_timeout(srl_xchg* h, double seconds) {
+  using namespace srl;
+  SRL_REQUIRE(h && seconds > 0.0, SRL_ERR_INVALID_ARG, "srl_xchg_set_timeout: need a handle and seconds > 0");
+  Xchg* x = reinterpret_cast<Xchg*>(h);
+  x->view.spin_limit = static_cast<long long>(seconds * 2.0e9);  // clock64 runs at the SM clock, ~2 GHz
   return SRL_OK;
 }
 

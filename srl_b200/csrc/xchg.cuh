@@ -6,12 +6,17 @@
 namespace srl {
 
 constexpr int kMaxWorld = 16;
-constexpr long long kSpinLimit = 4000000000ll;  // ~2 s of clock64 ticks: then give up with an error status
+// A rank waits for its peers like a collective does: minutes, not seconds -- a peer that autotunes its first step, saves a
+// checkpoint or waits for samples is late, not gone.  Only after `spin_limit` clock64 ticks (default ~10 min, the order of
+// NCCL's watchdog; srl_xchg_set_timeout) does it give up, and then it produces NO sums: the whole output table is NaN and
+// the sticky status says why, so a caller that does not look at the status still cannot train on stale numbers.
+constexpr long long kDefaultSpinLimit = 1200000000000ll;
 
 struct XchgView {
   unsigned long long* mailbox[kMaxWorld];  // peer p's mailbox base (mailbox[rank] = local); words = seq << 32 | payload
   unsigned int* seq;          // local: exchanges so far
   int* status;                // local: 0 ok, 1 timed out
+  long long spin_limit;       // clock64 ticks a rank waits for a peer's words
   int world, rank, cap;
 };
 
@@ -47,7 +52,7 @@ __device__ __forceinline__ void xchg_exchange(const XchgView& v, const double* _
       const volatile unsigned long long* src = mine + (static_cast<size_t>(q) * v.cap + i) * 2;
       unsigned long long lo = src[0], hi = src[1];
       while (static_cast<unsigned int>(lo >> 32) != seq || static_cast<unsigned int>(hi >> 32) != seq) {
-        if (clock64() - t0 > kSpinLimit) {
+        if (clock64() - t0 > v.spin_limit) {
           s_bad = 1;
           break;
         }
@@ -59,6 +64,10 @@ __device__ __forceinline__ void xchg_exchange(const XchgView& v, const double* _
     global[i] = s;
   }
   __syncthreads();
+  if (s_bad) {  // a peer never arrived: no partial sums leave this kernel
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) global[i] = nan;
+  }
   if (threadIdx.x == 0) {
     *v.seq = seq;
     if (s_bad) *v.status = 1;

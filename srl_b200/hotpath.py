@@ -51,7 +51,7 @@ class HotPath:
                  popart: bool = False, popart_beta: float = 0.99999, popart_eps: float = 1e-5,
                  device: Optional[torch.device] = None, process_group=None, fuse_gather: bool = True,
                  graph_branches: int = 16, shuffle_block: int = 1, use_pack: bool = True, batch_losses: bool = True,
-                 stats_exchange: str = "auto", fuse_stats: bool = True):
+                 stats_exchange: str = "auto", fuse_stats: bool = True, exchange_timeout_s: Optional[float] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("srl_b200.HotPath needs a CUDA device (there is no CPU path)")
         if bootstrap_steps < 1:
@@ -82,12 +82,13 @@ class HotPath:
         self.exchange_kind = "none" if process_group is None else "nccl"
         if process_group is not None and stats_exchange in ("auto", "p2p") and \
                 torch.distributed.get_backend(process_group) == "nccl":
-            try:
-                from srl_b200.xchg import PeerExchange
+            from srl_b200.xchg import PeerExchange, PeerExchangeUnavailable
+            try:  # collective: every rank ends up with the exchange, or every rank falls back (xchg.py)
                 self.peer = PeerExchange(process_group, (1 + epochs * minibatches) * SRL_LANE_PART,
-                                         torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device))
+                                         torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device),
+                                         timeout_s=exchange_timeout_s)
                 self.exchange_kind = "p2p"
-            except Exception:
+            except PeerExchangeUnavailable:
                 if stats_exchange == "p2p":
                     raise
         self.fuse_gather = fuse_gather
@@ -246,6 +247,13 @@ class HotPath:
             self.peer.allreduce_sum(self.local_stats, self.global_stats)
         else:
             exchange_stats(self.local_stats, self.global_stats, self.pg)
+
+    def check_exchange(self) -> None:
+        """Synchronises and raises when a rank never arrived at a statistics exchange (the table is NaN then)."""
+        if self.peer is not None:
+            self.peer.check_async()
+            torch.cuda.current_stream().synchronize()
+            self.peer.raise_if_failed()
 
     def _join_stats(self) -> None:
         if self._stats_pending:

@@ -58,17 +58,24 @@ class NamedArray:
     def items(self):
         return self._fields.items()
 
-    def __iter__(self) -> Iterator[str]:
-        return iter(self._fields)
+    def __iter__(self) -> Iterator[Any]:
+        """The VALUES in key order, as base/namedarray.py:307-309 (not the keys: `zip(record, other)` pairs leaves)."""
+        return iter(self._fields.values())
 
     def __contains__(self, k) -> bool:
         return k in self._fields
 
     def __len__(self) -> int:
+        """Number of fields (base/namedarray.py:417-418); `length()` is the size along an array dimension."""
+        return len(self._fields)
+
+    def length(self, dim: int = 0) -> int:
+        """Size of the first non-None leaf along `dim` (base/namedarray.py:420-430)."""
         for v in self._fields.values():
-            if v is not None:
-                return len(v)
-        return 0
+            if v is None:
+                continue
+            return v.length(dim) if isinstance(v, NamedArray) else v.shape[dim]
+        raise IndexError("No entries in the NamedArray.")
 
     def __getattr__(self, name):
         fields = object.__getattribute__(self, "_fields")
@@ -123,10 +130,20 @@ def is_record(x) -> bool:
                                          not isinstance(x, _TENSOR + (dict,)))
 
 
-def from_dict(values: Optional[Dict[str, Any]]) -> Optional[NamedArray]:
+def record_class(x) -> type:
+    """The generic record class to rebuild records of x's kind with: SRL's own `base.namedarray.NamedArray` when x is
+    one (its `recursive_apply` / `from_flattened` return that class too, base/namedarray.py:636-692, and SRL policies
+    test `isinstance(..., NamedArray)` against it), this module's mirror otherwise."""
+    for c in type(x).__mro__:
+        if c.__name__ == "NamedArray" and c is not NamedArray and c is not object:
+            return c
+    return NamedArray
+
+
+def from_dict(values: Optional[Dict[str, Any]], cls: type = NamedArray):
     if values is None or len(values) == 0:
         return None
-    return NamedArray(**{k: (from_dict(v) if isinstance(v, dict) else v) for k, v in values.items()})
+    return cls(**{k: (from_dict(v, cls) if isinstance(v, dict) else v) for k, v in values.items()})
 
 
 def flatten(x) -> List[Tuple[str, Any]]:
@@ -141,7 +158,7 @@ def flatten(x) -> List[Tuple[str, Any]]:
     return out
 
 
-def from_flattened(entries: List[Tuple[str, Any]]) -> NamedArray:
+def from_flattened(entries: List[Tuple[str, Any]], cls: type = NamedArray):
     tree: Dict[str, Any] = {}
     for name, v in entries:
         node = tree
@@ -149,14 +166,17 @@ def from_flattened(entries: List[Tuple[str, Any]]) -> NamedArray:
         for p in parts[:-1]:
             node = node.setdefault(p, {})
         node[parts[-1]] = v
-    return from_dict(tree)
+    return from_dict(tree, cls)
 
 
-def recursive_apply(x, fn: Callable):
+def recursive_apply(x, fn: Callable, cls: Optional[type] = None):
+    """Maps fn over the leaves.  The result is built from `cls` (default: the generic record class of x's own family,
+    record_class(x)) -- like the reference's recursive_apply, subclasses such as SampleBatch come back as plain records."""
     if x is None:
         return None
     if is_record(x):
-        return NamedArray(**{k: recursive_apply(x[k], fn) for k in x.keys()})
+        cls = cls or record_class(x)
+        return cls(**{k: recursive_apply(x[k], fn, cls) for k in x.keys()})
     return fn(x)
 
 

@@ -7,7 +7,8 @@ sample (mappo.py:254-257).  What changes is who does the work between `policy.an
 
   reference                                              here
   ---------------------------------------------------------------------------------------------------------
-  per-leaf H2D + .float() of every flag                  flags stay uint8 in HBM; float views only for the policy
+  per-leaf pageable H2D + .float() of EVERY leaf          one pinned H2D per leaf in its own dtype; float views only for
+                                                         what the policy reads, of the gathered minibatch when minibatched
   gae_trace: python loop, 3 kernels per time step        K2, one launch, float64 scan bit-identical to it
   masked_normalization + 3 all-reduces per loss          statistics table from K2's per-lane sums, 1 all-reduce/step
   PopArt update: ~10 kernels + 3 all-reduces             K3, one thread, state stays on device
@@ -30,7 +31,7 @@ import torch.nn as nn
 from srl_b200 import ops
 from srl_b200.api import PytorchTrainer, TrainerStepResult, register
 from srl_b200.hotpath import HotPath
-from srl_b200.namedarray import flatten, from_flattened, is_record, recursive_apply
+from srl_b200.namedarray import flatten, from_flattened, record_class, recursive_apply
 
 
 def init_optimizer(parameters, name: str, config: Dict):
@@ -142,12 +143,18 @@ class MultiAgentPPOB200(PytorchTrainer):
         self.shuffle_seed = int(kwargs.get("shuffle_seed", 0))
         self.shuffle_block = int(kwargs.get("shuffle_block", 1))  # environments per shuffled block
         self.prefetch = bool(kwargs.get("prefetch", True))  # one-call delay of api/trainer.py:219-228
+        self.copy_threads = int(kwargs.get("copy_threads", 8))  # host threads filling the pinned staging blocks
         if self.vtrace and (self.num_minibatches > 1 or self.recompute_adv_among_epochs):
             raise ValueError("vtrace supports num_minibatches == 1 without recompute_adv_among_epochs")
         self.frames = 0
         self._hp: Optional[HotPath] = None
         self._pending = None  # (host sample, device float sample) staged by the previous step() call
         self._copy_stream = torch.cuda.Stream()
+        self._mirror_stream = torch.cuda.Stream()
+        self._stage_done = torch.cuda.Event()
+        self._stage_pin: Dict[str, torch.Tensor] = {}
+        self._mirror, self._mirror_key = None, None
+        self.h2d_bytes = 0  # bytes this trainer has sent over PCIe (tests: == the host sample's bytes, A2)
         self._popart = _PopArtBridge(policy) if self.popart else None
 
     # ----------------------------------------------------------------------------------------------------
@@ -171,16 +178,52 @@ class MultiAgentPPOB200(PytorchTrainer):
         hp.hyper = self._hyper()  # entropy_bonus_weight decays over time (mappo.py:310-311)
         return hp
 
+    # ----------------------------------------------------------------------------------------------------
+    # A2: staging.  The reference's prefetcher copies every leaf from pageable memory and inflates ALL of them to float32
+    # on the device (api/trainer.py:211-217: 4 x the bytes of a uint8 frame stack, a 4-byte float per 1-byte flag).  Here a
+    # leaf crosses PCIe ONCE, in its own dtype, from a pinned staging block (filled by the library's multi-threaded host
+    # copy), and stays in that dtype in HBM; `policy.analyze` receives float32 views that are made where they are used --
+    # of the gathered minibatch only, when the step is minibatched.
+    # ----------------------------------------------------------------------------------------------------
+    def _pinned(self, name: str, x: np.ndarray) -> torch.Tensor:
+        t = self._stage_pin.get(name)
+        if t is None or t.numel() != x.size or t.dtype != torch.from_numpy(x.reshape(-1)[:1]).dtype:
+            t = torch.empty(x.size, dtype=torch.from_numpy(x.reshape(-1)[:1]).dtype).pin_memory()
+            self._stage_pin[name] = t
+        return t
+
+    def _to_device(self, name: str, x):
+        if isinstance(x, torch.Tensor):  # a DeviceSlabBuffer batch: already in HBM, in the sample's own dtype
+            return x if x.is_cuda else x.cuda(non_blocking=True)
+        x = np.ascontiguousarray(x)
+        if x.dtype.kind not in "fiub":
+            raise TypeError(f"leaf {name}: dtype {x.dtype} cannot live on the device (SRL's trainer worker clears "
+                            f"policy_name before step(), trainer_worker.py:169)")
+        if x.size == 0:
+            return torch.from_numpy(x).cuda()
+        pin = self._pinned(name, x)
+        if x.nbytes >= (1 << 20) and self.copy_threads > 1:
+            ops._lib.call("srl_host_copy", pin.data_ptr(), x.ctypes.data, x.nbytes, self.copy_threads)
+        else:
+            pin.numpy()[:] = x.reshape(-1)
+        self.h2d_bytes += x.nbytes
+        return pin.cuda(non_blocking=True).view(x.shape)
+
     def _stage(self, sample):
-        """Host -> device copy of the whole sample as float32 on a side stream: the tensors `policy.analyze`
-        receives, exactly what PyTorchGPUPrefetcher builds (api/trainer.py:211-217).  A batch that already lives in
-        HBM (srl_b200.buffer.DeviceSlabBuffer) is only cast, on the same side stream."""
+        """Host -> device copy of the whole sample on the side stream, every leaf in its own dtype (the reference:
+        api/trainer.py:211-217).  Returns (host sample, device sample of the same record family)."""
+        self._stage_done.synchronize()  # the pinned staging blocks are free again (the copy ahead of this one has landed)
         self._copy_stream.wait_stream(torch.cuda.current_stream())
+        names, leaves = zip(*flatten(sample))
         with torch.cuda.stream(self._copy_stream):
-            tensors = recursive_apply(
-                sample, lambda x: x.float() if isinstance(x, torch.Tensor) else
-                torch.from_numpy(x).cuda(non_blocking=True).float())
-        return sample, tensors
+            dev = [None if v is None else self._to_device(k, v) for k, v in zip(names, leaves)]
+            self._stage_done.record(self._copy_stream)
+        return sample, from_flattened(list(zip(names, dev)), record_class(sample))
+
+    @staticmethod
+    def _float_view(rec):
+        """What `policy.analyze` is handed: float32 leaves, as the reference's prefetcher produces (api/trainer.py:217)."""
+        return recursive_apply(rec, lambda x: x if x.dtype == torch.float32 else x.float())
 
     @staticmethod
     def _lanes(x) -> tuple:
@@ -199,32 +242,40 @@ class MultiAgentPPOB200(PytorchTrainer):
         if self.recompute_adv_on_reuse:  # mappo.py:224-225
             sample.analyzed_result.adv = sample.analyzed_result.ret = None
 
-        staged = self._stage(sample)
-        if self.prefetch:
-            staged, self._pending = self._pending, staged
+        if self.prefetch:  # api/trainer.py:219-228: wait for the copy in flight, take it, start the next one
+            torch.cuda.current_stream().wait_stream(self._copy_stream)
+            staged, self._pending = self._pending, self._stage(sample)
             if staged is None:
                 return TrainerStepResult({}, 0)  # api/trainer.py:220-223: the first call only primes the pipeline
-        torch.cuda.current_stream().wait_stream(self._copy_stream)
+        else:
+            staged = self._stage(sample)
+            torch.cuda.current_stream().wait_stream(self._copy_stream)
         sample, tensor_sample = staged
         on_device = isinstance(sample.on_reset, torch.Tensor)
 
         L = tensor_sample.on_reset.shape[0]
         B, A = self._lanes(sample.on_reset)
         hp = self._hot_path(L, B, A)
-        ar = sample.analyzed_result
-        hp.load_sample(dict(reward=sample.reward, value=ar.value, old_logp=ar.log_probs, done=sample.done,
-                            truncated=sample.truncated, on_reset=sample.on_reset))
+        ar, tar = sample.analyzed_result, tensor_sample.analyzed_result
+        # the six scalar leaves go from the staged device sample into the hot path's own [L, N] buffers: a device copy
+        # (flags that arrived as floats are narrowed to uint8 there), no second trip over PCIe
+        hp.load_sample(dict(reward=tensor_sample.reward, value=tar.value, old_logp=tar.log_probs, done=tensor_sample.done,
+                            truncated=tensor_sample.truncated, on_reset=tensor_sample.on_reset))
         if self._popart:
             self._popart.pull(hp)
-        cached_adv = ar.adv is not None
+        # decided from what was STAGED (mappo.py:249): with the prefetch delay the host sample may have gained its
+        # adv / ret only after its device copy was made (a buffer entry served twice in a row), and then they are recomputed
+        cached_adv = tar.adv is not None
         if cached_adv:  # re-served sample with cached advantages (recompute_adv_on_reuse=False)
-            hp.adv.copy_(tensor_sample.analyzed_result.adv.reshape(L, hp.N))
-            hp.ret.copy_(tensor_sample.analyzed_result.ret.reshape(L, hp.N))
+            hp.adv.copy_(tar.adv.reshape(L, hp.N))
+            hp.ret.copy_(tar.ret.reshape(L, hp.N))
 
         lo, hi, T = hp.row_lo, hp.row_hi, hp.T
         lead = tuple(sample.on_reset.shape[1:])  # (B, 1) or (B, A, 1)
+        whole = self._float_view(tensor_sample) if self.num_minibatches == 1 else None
         have_adv = False
-        grad_norm_sum = 0.0
+        mirrored = False
+        grad_norm_sum = torch.zeros((), device=hp.device)
         for e in range(self.ppo_epochs):
             for j in range(self.num_minibatches):
                 idx = hp.minibatch_lanes(e, j) if have_adv else None
@@ -232,7 +283,7 @@ class MultiAgentPPOB200(PytorchTrainer):
                     # the first analyze of the step needs the permutation before the advantages exist
                     hp.permute()
                     idx = hp.minibatch_lanes(e, j)
-                mb = tensor_sample if idx is None else self._gather_minibatch(tensor_sample, idx, hp)
+                mb = whole if idx is None else self._float_view(self._gather_minibatch(tensor_sample, idx, hp))
                 # mappo.py:243-246
                 tail_len = 1 if (self.vtrace and not cached_adv and not have_adv) else self.bootstrap_steps
                 res = self.policy.analyze(mb[:L - tail_len], target="ppo", burn_in_steps=self.burn_in_steps)
@@ -242,6 +293,9 @@ class MultiAgentPPOB200(PytorchTrainer):
                         vt = res.new_action_log_probs.detach().reshape(-1, hp.N).contiguous()
                     hp.advantages(cached=cached_adv, vtrace_new_logp=vt, permute=False)
                     have_adv = True
+                    if not on_device and not self.recompute_adv_among_epochs and not mirrored:
+                        self._mirror_adv_ret(hp)  # D2H of adv / ret under the epochs' compute (mappo.py:254-257)
+                        mirrored = True
                 if self._popart and j == 0:  # once per epoch, before the loss (mappo.py:263-264)
                     hp.update_popart()
                     self._popart.push(hp)
@@ -263,18 +317,27 @@ class MultiAgentPPOB200(PytorchTrainer):
         hp.finalize()
         hp.step_count += 1
 
-        # ---- one device -> host read for everything the step reports (mappo.py:254-257, 293-303) ---------------
-        out = hp.out.cpu().numpy()  # [E*M, 16]; synchronises the step
-        whole = hp.local_stats[0].cpu().numpy()
+        # ---- ONE synchronisation for everything the step reports (mappo.py:254-257, 293-303): the loss / stats table,
+        # the batch row and the gradient norm follow adv / ret into pinned mirrors, then the stream is waited for once
         n_loss = self.ppo_epochs * self.num_minibatches
+        m = self._host_mirror(hp)
+        m["out"].copy_(hp.out, non_blocking=True)
+        m["whole"].copy_(hp.local_stats[0], non_blocking=True)
+        m["gn"].copy_(grad_norm_sum.reshape(1).double(), non_blocking=True)
+        self._xchg_check(hp)
+        torch.cuda.current_stream().synchronize()
+        self._mirror_stream.synchronize()
+        if hp.peer is not None:
+            hp.peer.raise_if_failed()
+        out, whole_row = m["out"].numpy(), m["whole"].numpy()
         if self.recompute_adv_among_epochs:  # mappo.py:287-289 leaves the host copies cleared
             ar.adv = ar.ret = None
         elif on_device:  # the cached copies stay in HBM next to the batch
             ar.adv = hp.adv.reshape((L,) + lead).clone()
             ar.ret = hp.ret.reshape((L,) + lead).clone()
         else:  # mappo.py:254-257: the buffer may serve this sample again and reuse them
-            ar.adv = hp.adv.cpu().numpy().reshape((L,) + lead)
-            ar.ret = hp.ret.cpu().numpy().reshape((L,) + lead)
+            ar.adv = m["adv"].numpy().reshape((L,) + lead).copy()
+            ar.ret = m["ret"].numpy().reshape((L,) + lead).copy()
         train_stats = defaultdict(lambda: 0)
         names = dict(advantage=4, entropy=3, policy_loss=1, value_loss=2, clip_ratio=6, importance_weight=5, value_targets=7)
         if self.popart:
@@ -283,9 +346,9 @@ class MultiAgentPPOB200(PytorchTrainer):
             v = float(out[:, slot].mean())
             train_stats[k] = -v if k == "entropy" else v  # entropy = -entropy_loss (mappo.py:207)
         valid_count = float(T * hp.N)
-        train_stats["done"] = float(whole[5]) / valid_count  # unmasked means over the valid rows (mappo.py:210-211)
-        train_stats["truncated"] = float(whole[6]) / valid_count
-        train_stats["grad_norm"] = float(grad_norm_sum) / n_loss
+        train_stats["done"] = float(whole_row[5]) / valid_count  # unmasked means over the valid rows (mappo.py:210-211)
+        train_stats["truncated"] = float(whole_row[6]) / valid_count
+        train_stats["grad_norm"] = float(m["gn"][0]) / n_loss
 
         self.policy.inc_version()  # mappo.py:305-307
         if self.entropy_decay_per_steps and self.policy.version % self.entropy_decay_per_steps == 0:
@@ -302,9 +365,33 @@ class MultiAgentPPOB200(PytorchTrainer):
         return TrainerStepResult(stats=stats, step=self.policy.version)
 
     # ----------------------------------------------------------------------------------------------------
+    def _host_mirror(self, hp: HotPath) -> Dict[str, torch.Tensor]:
+        """Pinned host images of what a step reports, allocated once per batch shape."""
+        key = (hp.L, hp.N, hp.epochs, hp.minibatches)
+        if self._mirror_key != key:
+            pin = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype).pin_memory()
+            self._mirror = dict(adv=pin(hp.L, hp.N), ret=pin(hp.L, hp.N), out=pin(*hp.out.shape, dtype=torch.float64),
+                                whole=pin(hp.local_stats.shape[1], dtype=torch.float64), gn=pin(1, dtype=torch.float64))
+            self._mirror_key = key
+        return self._mirror
+
+    def _mirror_adv_ret(self, hp: HotPath) -> None:
+        """adv / ret -> pinned host mirrors on a side stream, right behind K2 (the reference's blocking `.cpu()` calls at
+        mappo.py:254-257; here the copy runs under the epochs' compute and is waited for once, at the end of the step)."""
+        m = self._host_mirror(hp)
+        self._mirror_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._mirror_stream):
+            m["adv"].copy_(hp.adv, non_blocking=True)
+            m["ret"].copy_(hp.ret, non_blocking=True)
+
+    def _xchg_check(self, hp: HotPath) -> None:
+        """A peer that never arrived at the statistics exchange must fail the step, not feed it stale sums."""
+        if hp.peer is not None:
+            hp.peer.check_async()
+
     def _gather_minibatch(self, tensor_sample, idx: torch.Tensor, hp: HotPath):
         """K5: every leaf `[L, B, ...]` of the device sample -> `[L, n_env, ...]` for the environments of this
-        minibatch, one C-ABI call for all leaves (bit-exact; numpy equivalent: x[:, env_idx])."""
+        minibatch, one C-ABI call for all leaves (bit-exact, in the leaves' own dtypes; numpy equivalent: x[:, env_idx])."""
         env_idx = idx.view(-1, hp.A)[:, 0].contiguous() // hp.A if hp.A > 1 else idx
         env_idx = env_idx.to(torch.int32)
         names, pairs = [], []
@@ -314,10 +401,11 @@ class MultiAgentPPOB200(PytorchTrainer):
                 continue
             v = v.contiguous()
             dst = torch.empty((v.shape[0], env_idx.numel()) + tuple(v.shape[2:]), dtype=v.dtype, device=v.device)
-            pairs.append((v, dst))
+            if v.numel() > 0:
+                pairs.append((v, dst))
             names.append((name, dst))
         ops.batch_gather(pairs, env_idx)
-        return from_flattened(names)
+        return from_flattened(names, record_class(tensor_sample))
 
 
 register("mappo_b200", MultiAgentPPOB200)
