@@ -1,20 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- GAE + PPO-loss transitions/s on the B200 hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2_atari_large] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2_atari_large] [--scaling weak|strong]
+                    [--impl reference]
 
 A "step" = one pass of the hot path over one synthetic batch: GAE once, then
 (epochs x minibatches) fused loss forward+backward covering every transition once per epoch.
-`value` = T*N transitions per step (x ranks) / device time with inputs resident in HBM; `e2e` = the same
+`value` = transitions per step (all ranks) / device time with inputs resident in HBM; `e2e` = the same
 through `HotPath.run_host` with pinned HOST buffers in and out (H2D + D2H inside the timed region).
-N > 1 (torchrun): every rank owns its own slice of environments (weak scaling, the full config per GPU);
-the only data-path exchange is the SUM of the float64 statistics table (NVLink peer-memory mailboxes, or NCCL).
-`--impl reference` times the reference's CPU path (the oracle port: /root/reference is a Python tree that
-does not exist on the GPU box) on the host cores, same config / metric / unit.
+N > 1 (torchrun): every rank owns its own slice of environments -- `--scaling weak`: the full config per GPU
+(cfg5's sweep); `--scaling strong`: the config's B environments split over the ranks (cfg4: 2048 / 8 = 256 per GPU,
+football.py:135,227-228).  The only data-path exchange is the SUM of the float64 statistics table (NVLink peer-memory
+mailboxes, or NCCL); at N > 1 the line carries `parity_check`: the exchanged table against the rank-ordered float64 sum,
+bit for bit on every rank, and one minibatch's loss / gradients against the oracle evaluated with the global sums.
+Beside the headline the line reports `step_trainer_order` (the same work issued as a trainer must issue it: one loss
+launch per minibatch, each behind the previous) and `trainer_step` (the drop-in `MultiAgentPPOB200.step` with a small
+policy, host sample in, stats out).
+`--impl reference` times the reference's OWN functions (`MultiAgentPPO._compute_adv_and_value_target`, `_compute_loss` +
+backward, loaded unmodified through oracle/ref_loader.py from oracle/_ref) on the host cores, same config / metric / unit,
+per stage; where a GPU is visible it adds the same functions on cuda (the ATen-eager path SRL users have today).
 """
 from __future__ import annotations
 
 import argparse
+import dataclasses
 import json
 import os
 import statistics
@@ -60,25 +69,154 @@ def hyper_kwargs(cfg):
                                    {"beta": cfg.value_loss_delta} if cfg.value_loss == "smoothl1" else None))
 
 
+def shard_config(cfg, world, scaling):
+    """The slice of the workload one rank owns.  weak: the whole config per GPU; strong: B / world environments."""
+    if scaling == "weak" or world == 1:
+        return cfg
+    if cfg.B % world != 0 or (cfg.B // world) % cfg.minibatches != 0:
+        raise SystemExit(f"--scaling strong: B={cfg.B} environments do not split over {world} ranks x {cfg.minibatches} minibatches")
+    return dataclasses.replace(cfg, B=cfg.B // world)
+
+
 # ----------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on host cores
+# reference arm / cpu baseline: the reference's own functions (oracle/_ref), else the oracle port
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_run(cfg, steps, warmup, budget_s=None):
-    """Times oracle.ref_math.hot_path_ref (GAE in float64 with the reference's python scan, then
-    epochs x minibatches of loss + autograd backward) on all host threads, full config per step."""
+def _minibatch_indices(cfg, seed=0):
+    """The environment slices of every (epoch, minibatch), as int64 lane-index tensors (the reference has no minibatching:
+    its loss runs on `sample[:, idx]`, the definition oracle/ref_trainer.py uses too)."""
+    from oracle import ref_math as M
+    out = []
+    n_env = cfg.B // cfg.minibatches
+    for e in range(cfg.epochs):
+        if cfg.minibatches == 1:
+            out.append([None])
+            continue
+        env = M.philox_perm_ref(seed, e, cfg.B).astype(np.int64)
+        lanes = (env[:, None] * cfg.A + np.arange(cfg.A)[None]).reshape(-1) if cfg.A > 1 else env
+        out.append([torch.from_numpy(np.ascontiguousarray(env[j * n_env:(j + 1) * n_env])) for j in range(cfg.minibatches)])
+        del lanes
+    return out
+
+
+def reference_functions_run(cfg, steps, warmup, device="cpu", budget_s=None):
+    """Times the UNMODIFIED reference: MultiAgentPPO._compute_adv_and_value_target (mappo.py:118-144; gae.py:8-97) once, then
+    per (epoch, minibatch) the PopArt update (:263-264), _compute_loss (:146-217), loss.backward() to the three policy
+    outputs and the .mean().item() reads of mappo.py:293-299 -- on `device` ('cpu': all host threads; 'cuda': the
+    ATen-eager path).  Returns per-stage seconds per step."""
+    from oracle import ref_loader
+    R = ref_loader.load()
+    dev = torch.device(device)
+    if dev.type == "cpu":
+        torch.set_num_threads(os.cpu_count() or 1)
+    s = synth.make_sample_scalars(cfg, seed=0)
+    pol = synth.make_policy_outputs(cfg, s, seed=1)
+    t = {k: torch.from_numpy(v).float().to(dev) for k, v in s.items()}  # the prefetcher's .float() (api/trainer.py:217)
+    head = None
+    if cfg.popart:
+        head = R.popart.PopArtValueHead(4, 1, beta=0.99999).to(dev)
+        head.update(torch.randn(64, 1, device=dev) * 2.0 + 0.5, mask=None)
+    fake = ref_loader.FakePolicy(popart_head=head)
+    fake.device = str(dev)
+    tr = R.mappo.MultiAgentPPO(fake, discount_rate=cfg.gamma, gae_lambda=cfg.lmbda, popart=cfg.popart,
+                               bootstrap_steps=cfg.bootstrap_steps, burn_in_steps=cfg.burn_in_steps, **hyper_kwargs(cfg))
+    NA = R.namedarray.NamedArray
+    sample = R.trainer.SampleBatch(obs=None, on_reset=t["on_reset"], done=t["done"], truncated=t["truncated"],
+                                   reward=t["reward"], analyzed_result=NA(value=t["value"], log_probs=t["old_logp"],
+                                                                          adv=None, ret=None))
+    lo, hi, L = cfg.burn_in_steps, cfg.L - cfg.bootstrap_steps, cfg.L
+    idx = _minibatch_indices(cfg)
+    idx = [[None if i is None else i.to(dev) for i in row] for row in idx]
+    pol_t = {k: torch.from_numpy(v).to(dev) for k, v in pol.items()}  # [E, T, B, (A,) 1]
+    sync = (lambda: torch.cuda.synchronize(dev)) if dev.type == "cuda" else (lambda: None)
+    rapply = R.namedarray.recursive_apply
+
+    def one():
+        sync()
+        t0 = time.perf_counter()
+        adv, ret = tr._compute_adv_and_value_target(sample, None)
+        dims = len(t["value"].shape)
+        pad = (0,) * (dims * 2 - 1) + (1,)
+        sample.analyzed_result.adv = torch.nn.functional.pad(adv, pad)  # mappo.py:254-257, host mirror included
+        sample.analyzed_result.ret = torch.nn.functional.pad(ret, pad)
+        _ = sample.analyzed_result.adv.cpu().numpy(), sample.analyzed_result.ret.cpu().numpy()
+        sync()
+        t1 = time.perf_counter()
+        valid = sample[lo:hi]
+        mask = 1 - t["on_reset"][lo + 1:hi + 1]
+        for e in range(cfg.epochs):
+            if cfg.popart:
+                fake.update_popart(valid.analyzed_result.ret, mask=mask)
+            for j, ii in enumerate(idx[e]):
+                take = (lambda x: x) if ii is None else (lambda x: x.index_select(1, ii))
+                vmb = valid if ii is None else rapply(valid, take)
+                nl, vp, en = (take(pol_t[k][e]).detach().requires_grad_(True) for k in ("new_logp", "v_pred", "entropy"))
+                analyzed = R.mappo.SampleAnalyzedResult(old_action_log_probs=vmb.analyzed_result.log_probs,
+                                                        new_action_log_probs=nl, state_values=vp, entropy=en)
+                loss, res = tr._compute_loss(vmb, analyzed, take(mask))
+                loss.backward()
+                _ = {f.name: getattr(res, f.name).detach().mean().item() for f in dataclasses.fields(res)
+                     if getattr(res, f.name) is not None}  # mappo.py:293-299
+        sync()
+        t2 = time.perf_counter()
+        sample.analyzed_result.adv = sample.analyzed_result.ret = None
+        return t1 - t0, t2 - t1
+
+    for _ in range(warmup):
+        one()
+    gae_s, loss_s = [], []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        a, b = one()
+        gae_s.append(a)
+        loss_s.append(b)
+        if budget_s is not None and time.perf_counter() - t_begin > budget_s and len(gae_s) >= 3:
+            break
+    g, l_ = sum(gae_s) / len(gae_s), sum(loss_s) / len(loss_s)
+    return dict(value=cfg.transitions / (g + l_), ms_per_step=(g + l_) * 1e3, steps=len(gae_s),
+                cores=torch.get_num_threads() if dev.type == "cpu" else 0, kind="reference",
+                stages=dict(gae_ms=g * 1e3, loss_bwd_ms=l_ * 1e3, gae_transitions_per_s=cfg.transitions / g,
+                            loss_transitions_per_s=cfg.transitions * cfg.epochs / l_))
+
+
+def reference_assembly_run(cfg, n_env=64, reps=3):
+    """Stage 1 of the reference on the host: recursive_aggregate(np.stack(axis=1)) of per-environment samples
+    (base/buffer.py:118-126, base/namedarray.py:598-633), one thread, on a bounded sample of n_env environments."""
+    from oracle import ref_loader
+    R = ref_loader.load()
+    NA = R.namedarray.NamedArray
+    rng = np.random.default_rng(0)
+    L = cfg.L
+    shape = tuple(cfg.obs_shape) if cfg.obs_shape else (64,)
+    mk = lambda: R.trainer.SampleBatch(
+        obs=NA(x=rng.integers(0, 255, (L,) + shape, dtype=np.uint8)), on_reset=np.zeros((L, 1), dtype=np.uint8),
+        done=np.zeros((L, 1), dtype=np.uint8), truncated=np.zeros((L, 1), dtype=np.uint8),
+        reward=rng.standard_normal((L, 1)).astype(np.float32),
+        analyzed_result=NA(value=rng.standard_normal((L, 1)).astype(np.float32),
+                           log_probs=-rng.random((L, 1)).astype(np.float32)))
+    samples = [mk() for _ in range(n_env)]
+    nbytes = int(R.namedarray.size_bytes(samples[0])) * n_env
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        R.namedarray.recursive_aggregate(list(samples), lambda xs: np.stack(xs, axis=1))
+        ts.append(time.perf_counter() - t0)
+    best = min(ts)
+    return dict(what=f"recursive_aggregate(np.stack, axis=1) of {n_env} samples, L={L}, obs {shape} uint8, 1 thread",
+                bytes=nbytes, ms=best * 1e3, gbs=nbytes / best / 1e9, transitions_per_s=n_env * (L - 1) / best)
+
+
+def port_run(cfg, steps, warmup, budget_s=None):
+    """Fallback when oracle/_ref is not staged: the oracle port (oracle/ref_math.py::hot_path_ref) on all host threads."""
     from oracle import ref_math as M  # checker / baseline only
     torch.set_num_threads(os.cpu_count() or 1)
     s = synth.make_sample_scalars(cfg, seed=0)
     pol = synth.make_policy_outputs(cfg, s, seed=1)
-    batch = {k: torch.from_numpy(v).float() for k, v in s.items()}  # the prefetcher's .float() (api/trainer.py:217)
+    batch = {k: torch.from_numpy(v).float() for k, v in s.items()}
     batch.update({k: torch.from_numpy(v) for k, v in pol.items()})
     hp = M.LossHyper(**hyper_kwargs(cfg))
     pa = M.RunningMeanStdRef((1,)) if cfg.popart else None
-
-    def one():
-        M.hot_path_ref(batch, hp, cfg.gamma, cfg.lmbda, cfg.epochs, cfg.minibatches, seed=0, popart=pa,
-                       bootstrap_steps=cfg.bootstrap_steps, burn_in_steps=cfg.burn_in_steps)
-
+    one = lambda: M.hot_path_ref(batch, hp, cfg.gamma, cfg.lmbda, cfg.epochs, cfg.minibatches, seed=0, popart=pa,
+                                 bootstrap_steps=cfg.bootstrap_steps, burn_in_steps=cfg.burn_in_steps)
     for _ in range(warmup):
         one()
     times = []
@@ -90,31 +228,61 @@ def cpu_reference_run(cfg, steps, warmup, budget_s=None):
         if budget_s is not None and time.perf_counter() - t_begin > budget_s and len(times) >= 3:
             break
     mean = sum(times) / len(times)
-    return dict(value=cfg.transitions / mean, ms_per_step=mean * 1e3, steps=len(times),
-                cores=torch.get_num_threads(), best_ms=min(times) * 1e3)
+    return dict(value=cfg.transitions / mean, ms_per_step=mean * 1e3, steps=len(times), cores=torch.get_num_threads(),
+                kind="port", stages=None)
+
+
+def cpu_reference_run(cfg, steps, warmup, budget_s=None):
+    from oracle import ref_loader
+    if ref_loader.available():
+        return reference_functions_run(cfg, steps, warmup, "cpu", budget_s)
+    return port_run(cfg, steps, warmup, budget_s)
+
+
+def _sample_text(r, cfg):
+    if r["kind"] == "reference":
+        return (f"{r['steps']} full steps ({r['ms_per_step']:.1f} ms each) of {workload_name(cfg)} on {r['cores']} host threads: the "
+                f"UNMODIFIED reference functions MultiAgentPPO._compute_adv_and_value_target + per minibatch _compute_loss, "
+                f"backward and the .item() reads (oracle/_ref, torch-CPU, float64 GAE)")
+    return (f"{r['steps']} full steps ({r['ms_per_step']:.1f} ms each) of {workload_name(cfg)} on {r['cores']} host threads "
+            f"(oracle port of mappo.py:118-217 + gae.py:8-97; oracle/_ref not staged)")
 
 
 def run_reference_arm(args, cfg, rank, world):
     if rank != 0:
         return  # rank 0 alone runs the CPU arm; the others exit 0 without work
+    cfg = shard_config(cfg, args.gpus, args.scaling)  # the per-GPU slice of our arm, on the host cores
     r = cpu_reference_run(cfg, args.steps, args.warmup)
-    sample = (f"{r['steps']} full steps of {workload_name(cfg)} on {r['cores']} host threads "
-              f"(oracle port of mappo.py:118-217 + gae.py:8-97, torch-CPU, float64 GAE)")
+    extra = {}
+    try:
+        extra["assembly"] = reference_assembly_run(cfg)
+    except Exception as e:  # noqa: BLE001
+        extra["assembly"] = dict(error=str(e))
+    if torch.cuda.is_available() and r["kind"] == "reference":
+        try:  # "what SRL users get today on this GPU": the same unmodified functions, tensors on cuda
+            g = reference_functions_run(cfg, min(args.steps, 20), 2, "cuda:0")
+            extra["reference_gpu_eager"] = dict(value=g["value"], unit=UNIT, ms_per_step=g["ms_per_step"], stages=g["stages"],
+                                                what="the same unmodified reference functions with the batch on cuda:0 "
+                                                     "(ATen eager kernels, python scan over T), inputs resident in HBM")
+        except Exception as e:  # noqa: BLE001
+            extra["reference_gpu_eager"] = dict(error=str(e))
     line = dict(metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=r["steps"], warmup=args.warmup,
-                ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                ms_per_step=r["ms_per_step"], higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference", config=dict(workload=workload_name(cfg)),
-                cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=sample),
-                e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+                cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=_sample_text(r, cfg),
+                                  stages=r["stages"]),
+                e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0, **extra)
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------
 # host placement
 # ----------------------------------------------------------------------------------------------------
-def bind_to_gpu_numa(device_index):
-    """Runs this process on the CPUs NVML reports as local to the GPU, so that the pinned staging buffers are
-    allocated on that NUMA node and the e2e copies do not cross the socket interconnect (box to box the same bench
-    measured 0.72 and 1.27 ms per e2e step without it).  Returns the previous affinity (restored for the CPU arm)."""
+def bind_to_gpu_numa(device_index, local_rank=0, local_world=1):
+    """Runs this process on ITS OWN share of the CPUs NVML reports as local to the GPU (the pinned staging buffers are then
+    allocated on that NUMA node).  With several ranks whose GPUs report the same CPU set (SCALE_r01: all eight GPUs of the
+    box list CPUs 0-31) every rank takes a disjoint slice of it instead of all ranks piling onto the same cores.
+    Returns the previous affinity (restored for the CPU arm)."""
     try:
         import pynvml
         before = os.sched_getaffinity(0)
@@ -123,69 +291,142 @@ def bind_to_gpu_numa(device_index):
         h = pynvml.nvmlDeviceGetHandleByUUID((uuid if uuid.startswith("GPU-") else "GPU-" + uuid).encode())
         words = (max(before) + 64) // 64
         mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-        cpus = {i for i in before if (mask[i // 64] >> (i % 64)) & 1}
+        cpus = sorted(i for i in before if (mask[i // 64] >> (i % 64)) & 1)
+        if cpus and local_world > 1:
+            per = max(1, len(cpus) // local_world)
+            mine = cpus[local_rank * per:(local_rank + 1) * per] or cpus
+            cpus = mine
         if cpus:
-            os.sched_setaffinity(0, cpus)
+            os.sched_setaffinity(0, set(cpus))
         return before
     except Exception:
         return None
 
 
 # ----------------------------------------------------------------------------------------------------
-# clocks
+# clocks: NVML polled in-process (a thread, ~1 kHz) around the timed regions
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    _REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
-    def __init__(self, device_index):
-        self.rows, self.proc = [], None
+    def __init__(self, device_index, period_s=0.001):
+        self.rows, self.ok, self._stop = [], False, False
         try:
+            import pynvml
+            pynvml.nvmlInit()
             uuid = str(torch.cuda.get_device_properties(device_index).uuid)
-            ident = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
-        except Exception:
-            ident = str(device_index)
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", ident, f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+            self.h = pynvml.nvmlDeviceGetHandleByUUID((uuid if uuid.startswith("GPU-") else "GPU-" + uuid).encode())
+            self.nv = pynvml
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.period = period_s
+            self.ok = True
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.ok = False
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
-
-    def stop(self, t0=None, t1=None):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.12)
-        self.proc.terminate()
-        sm, mx, reasons, loaded = [], [], set(), []
-        for ts, line in self.rows:
-            p = [x.strip() for x in line.split(",")]
-            if len(p) < 8:
-                continue
+        nv = self.nv
+        while not self._stop:
             try:
-                c, m, util = float(p[0]), float(p[1]), float(p[3])
-            except ValueError:
-                continue
-            inside = t0 is None or (t0 - 0.05 <= ts <= t1 + 0.05)
-            if not inside:
-                continue
-            sm.append(c)
-            mx.append(m)
-            if util > 0:
-                loaded.append(c)
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        pick = loaded or sm
-        return dict(sm_mhz=statistics.median(pick) if pick else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm), samples_under_load=len(loaded))
+                c = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.perf_counter(), c, r))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self, windows=None):
+        """windows: [(t0, t1)] perf_counter intervals of the timed regions; samples outside them are dropped."""
+        if not self.ok:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvml unavailable"], samples=0)
+        self._stop = True
+        self.thread.join(timeout=1.0)
+        rows = [r for r in self.rows if windows is None or any(a <= r[0] <= b for a, b in windows)]
+        sm = [c for _, c, _ in rows]
+        reasons = sorted({name for _, _, r in rows for name, bit in self._REASONS if r & bit})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_min_mhz=min(sm) if sm else None,
+                    sm_max_mhz=self.max_sm, reasons=reasons, samples=len(sm), sampler="pynvml in-process, 1 ms period, "
+                    "samples inside the timed regions only")
+
+
+# ----------------------------------------------------------------------------------------------------
+# a small policy for the trainer_step line: what MultiAgentPPO calls on a policy (SURVEY.md §8b), a two-layer MLP
+# ----------------------------------------------------------------------------------------------------
+class _BenchPolicy:
+
+    def __init__(self, obs_dim, num_actions, device, hidden=64):
+        import torch.nn as nn
+        torch.manual_seed(0)
+        self.net = nn.Sequential(nn.Linear(obs_dim, hidden), nn.Tanh(), nn.Linear(hidden, num_actions + 1)).to(device)
+        self.device, self._version, self.k = device, -1, num_actions
+        self.denormalize_value_during_rollout = False
+
+    version = property(lambda self: self._version)
+
+    def inc_version(self):
+        self._version += 1
+
+    def parameters(self):
+        return self.net.parameters()
+
+    def train_mode(self):
+        self.net.train()
+
+    def analyze(self, sample, target="ppo", burn_in_steps=0, **kw):
+        from types import SimpleNamespace
+        out = self.net(sample.obs.vec[burn_in_steps:])
+        dist = torch.distributions.Categorical(logits=out[..., :self.k])
+        action = sample.action.x[burn_in_steps:, ..., 0].long()
+        return SimpleNamespace(old_action_log_probs=sample.analyzed_result.log_probs[burn_in_steps:],
+                               new_action_log_probs=dist.log_prob(action).unsqueeze(-1), state_values=out[..., self.k:],
+                               entropy=dist.entropy().unsqueeze(-1))
+
+
+def trainer_step_run(cfg, dev, steps=5):
+    """The drop-in `MultiAgentPPOB200.step` end to end: host numpy sample in (scalar leaves of the workload + a 16-float
+    observation vector per transition), prefetch on, policy forward / backward / optimizer in PyTorch, stats out."""
+    from srl_b200 import api
+    from srl_b200.namedarray import NamedArray, size_bytes
+    from srl_b200.trainer import MultiAgentPPOB200
+    if cfg.A != 1:
+        return None
+    obs_dim, K = 16, int(cfg.num_actions[0])
+    rng = np.random.default_rng(5)
+    pol = _BenchPolicy(obs_dim, K, f"cuda:{dev.index}")
+    hk = hyper_kwargs(cfg)
+    tr = MultiAgentPPOB200(pol, discount_rate=cfg.gamma, gae_lambda=cfg.lmbda, bootstrap_steps=cfg.bootstrap_steps,
+                           burn_in_steps=cfg.burn_in_steps, ppo_epochs=cfg.epochs, num_minibatches=cfg.minibatches,
+                           popart=False, optimizer="adam", optimizer_config=dict(lr=1e-4),
+                           **{k: v for k, v in hk.items() if v is not None})
+
+    def sample(seed):
+        s = synth.make_sample_scalars(cfg, seed)
+        lead = s["value"].shape[:-1]
+        return api.SampleBatch(obs=NamedArray(vec=rng.standard_normal(lead + (obs_dim,)).astype(np.float32)),
+                               on_reset=s["on_reset"], done=s["done"], truncated=s["truncated"],
+                               action=NamedArray(x=rng.integers(0, K, lead + (1,)).astype(np.uint8)), reward=s["reward"],
+                               analyzed_result=api.AnalyzedResult(value=s["value"], log_probs=s["old_logp"]))
+
+    samples = [sample(100 + i) for i in range(3)]
+    host_bytes = size_bytes(samples[0])
+    for i in range(3):  # the first call primes the prefetcher; two warm-up steps
+        tr.step(samples[i % 3])
+    torch.cuda.synchronize()
+    h2d0 = tr.h2d_bytes
+    t0 = time.perf_counter()
+    for i in range(steps):
+        tr.step(samples[i % 3])
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    return dict(ms_per_step=dt * 1e3, value=cfg.transitions / dt, unit=UNIT, steps=steps,
+                h2d_bytes_per_step=(tr.h2d_bytes - h2d0) // steps, host_sample_bytes=int(host_bytes),
+                what=f"MultiAgentPPOB200.step: host numpy sample (scalars + a {obs_dim}-float observation) -> pinned H2D in the "
+                     f"leaves' own dtypes -> per minibatch: K5 gather, a 2-layer MLP policy (PyTorch), K4, backward, Adam "
+                     f"-> stats; {cfg.epochs} epochs x {cfg.minibatches} minibatches; wall clock per call, prefetch on")
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -195,21 +436,83 @@ def event_ms(pairs):
     return [a.elapsed_time(b) for a, b in pairs]
 
 
-def run_ours(args, cfg, rank, world, local_rank):
+def parity_check(hp, cfg, pol_np, sample_np, rank, world, dist, dev):
+    """Before anything is timed: one eager step, then (1) on several ranks, the exchanged statistics table against the
+    float64 sum of the ranks' local tables added in rank order -- bit for bit, on every rank; (2) the loss scalars and the
+    gradients of minibatch (0, 0) against the oracle (oracle/ref_math.py::ppo_loss_ref) on this rank's data, normalised with
+    the GLOBAL sums (the reference's semantics across ranks, utils.py:58-61), within 1e-5."""
+    from oracle import ref_math as M  # the checker
+    out = dict(ranks=world)
+    if world > 1:
+        tables = [torch.empty_like(hp.local_stats) for _ in range(world)]
+        dist.all_gather(tables, hp.local_stats.contiguous())
+        expect = torch.zeros_like(hp.local_stats)
+        for t in tables:
+            expect += t
+        same = bool(torch.equal(expect, hp.global_stats))
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        out["stats_table_bit_exact_on_every_rank"] = bool(flag.item())
+    e, j = hp.epochs - 1, 0  # the last epoch: with PopArt its statistics are the ones still in hp.popart_ms
+    T, n = hp.T, hp.n_mb
+    lo, hi = hp.row_lo, hp.row_hi
+    idx = hp.minibatch_lanes(e, j)
+    ii = torch.arange(hp.N) if idx is None else idx.cpu().long()
+    flat = lambda x: torch.from_numpy(np.ascontiguousarray(x.reshape(x.shape[0], -1)))
+    take = lambda x: x.index_select(1, ii).unsqueeze(-1)
+    t = {k: flat(v).float() for k, v in sample_np.items()}
+    adv, ret = hp.adv.cpu(), hp.ret.cpu()
+    mask = 1 - t["on_reset"][lo + 1:hi + 1]
+    nl, vp, en = (hp_t.cpu().unsqueeze(-1) for hp_t in pol_np)
+    row = hp.stats_row(e, j)
+    g = hp.global_stats[row].cpu()
+    pa = None
+    if cfg.popart:  # an oracle RunningMeanStd whose mean_std() is the device's current (mu, sigma)
+        ms = hp.popart_ms.cpu()
+        pa = M.RunningMeanStdRef((1,))
+        pa.debias = torch.ones(1, dtype=torch.float64)
+        pa.mean = ms[0:1].clone()
+        pa.mean_sq = (ms[1:2] ** 2 + ms[0:1] ** 2).clone()
+    ref = M.ppo_loss_ref(nl, take(t["old_logp"][lo:hi]), vp, take(t["value"][lo:hi]), take(ret[lo:hi]), take(adv[lo:hi]), en,
+                         take(mask), M.LossHyper(**hyper_kwargs(cfg)), popart=pa,
+                         global_sums=(g[0].clone(), g[1].clone(), g[2].clone()))
+    got = hp.out[e * hp.minibatches + j].cpu()
+    m = float(got[9])
+    rel = lambda a, b: float(abs(a - b) / max(1.0, abs(b)))
+    out["loss_err"] = rel(float(got[0]), float(ref["loss"]))
+    errs = []
+    for q, k in enumerate(("g_logp", "g_value", "g_entropy")):
+        a = hp.grads[e][j][q].cpu().double() * m
+        b = ref[k][..., 0].double() * m
+        errs.append(float(((a - b).abs() / b.abs().clamp(min=1.0)).max()))
+    out["grad_err"] = max(errs)
+    ok = out["loss_err"] <= 1e-5 and out["grad_err"] <= 1e-5 and out.get("stats_table_bit_exact_on_every_rank", True)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["ok"] = bool(flag.item())
+    out["what"] = ("eager step before the timed region: exchanged stats table == rank-ordered float64 sum (bit for bit, all ranks); "
+                   "the last epoch's first minibatch: loss and gradients vs oracle.ppo_loss_ref with the global sums, |x-ref| <= 1e-5*max(1,|ref|), "
+                   "gradients on the g*M scale; min over ranks")
+    return out
+
+
+def run_ours(args, cfg_full, rank, world, local_rank):
     import torch.distributed as dist
     from srl_b200 import ops
     from srl_b200.hotpath import HotPath
 
+    cfg = shard_config(cfg_full, world, args.scaling)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    affinity_before = bind_to_gpu_numa(local_rank)
+    affinity_before = bind_to_gpu_numa(local_rank, local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     pg = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     ops._lib.load_library()  # fail loudly if the CUDA library is missing
 
-    # ---- synthetic batch for this rank's slice of environments (weak scaling) ----------------------
+    # ---- synthetic batch for this rank's slice of environments -------------------------------------
     s = synth.make_sample_scalars(cfg, seed=1000 * rank)
     pol = synth.make_policy_outputs(cfg, s, seed=1000 * rank + 1)
     E, Mb, T, N = cfg.epochs, cfg.minibatches, cfg.T, cfg.N
@@ -217,7 +520,8 @@ def run_ours(args, cfg, rank, world, local_rank):
                  bootstrap_steps=cfg.bootstrap_steps, burn_in_steps=cfg.burn_in_steps, epochs=E, minibatches=Mb, seed=0,
                  popart=cfg.popart, device=dev, process_group=pg, fuse_gather=not args.explicit_gather,
                  graph_branches=args.branches, shuffle_block=args.shuffle_block, use_pack=not args.no_pack,
-                 batch_losses=not args.no_batch, stats_exchange=args.exchange, fuse_stats=not args.no_fuse_stats)
+                 batch_losses=not args.no_batch, stats_exchange=args.exchange, fuse_stats=not args.no_fuse_stats,
+                 exchange_timeout_s=30.0)
     n = hp.n_mb
     pinned = {k: torch.from_numpy(np.ascontiguousarray(v.reshape(cfg.L, N))).pin_memory() for k, v in s.items()}
     hp.load_sample(pinned)
@@ -235,6 +539,16 @@ def run_ours(args, cfg, rank, world, local_rank):
     out_host = dict(adv=torch.empty((cfg.L, N), dtype=torch.float32).pin_memory(),
                     ret=torch.empty((cfg.L, N), dtype=torch.float32).pin_memory(),
                     out=torch.empty((E * Mb, 16), dtype=torch.float64).pin_memory())
+
+    # ---- parity first: an eager step checked against the oracle (and, on several ranks, the exchange) --
+    hp.run_device(pol_dev, use_graph=False)
+    hp.step_count = 0
+    torch.cuda.synchronize()
+    hp.check_exchange()
+    pc = None
+    if not args.no_parity_check:
+        pc = parity_check(hp, cfg, pol_dev[E - 1][0], s, rank, world, dist, dev)
+
     # L2 flush between timed iterations: write a 256 MiB buffer (> 126 MB L2), then READ a second one.  The write
     # alone leaves the L2 full of dirty lines whose write-back the timed kernels would then pay for (it showed as
     # ~20 us on a 65 us kernel); the read pass evicts them and leaves clean lines, so the step starts cold.
@@ -250,13 +564,11 @@ def run_ours(args, cfg, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    flush_l2_fn = flush_l2
-
-    def timed_steps(k, fn, flush_l2=True):
+    def timed_steps(k, fn, flush_first=True):
         pairs = []
         for _ in range(k):
-            if flush_l2:
-                flush_l2_fn()
+            if flush_first:
+                flush_l2()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
@@ -265,41 +577,71 @@ def run_ours(args, cfg, rank, world, local_rank):
         torch.cuda.synchronize()
         return event_ms(pairs)
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    windows = []
     step = lambda: hp.run_device(pol_dev, use_graph=True)
     for _ in range(max(args.warmup, 3)):
         flush_l2()
         step()
     barrier()
-    t_region0 = time.perf_counter()
+    w0 = time.perf_counter()
     ms = timed_steps(args.steps, step)
     barrier()
-    total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = total_ms.item() / args.steps
-    value = cfg.transitions * world / (ms_per_step * 1e-3)
+    windows.append((w0, time.perf_counter()))
+    ms_per_step = max_over_ranks(sum(ms)) / args.steps
+    total_transitions = cfg.transitions * world
+    value = total_transitions / (ms_per_step * 1e-3)
 
     # ---- warm-L2 variant (no flush), informational ------------------------------------------------
-    ms_warm = timed_steps(min(args.steps, 200), step, flush_l2=False)
+    ms_warm = timed_steps(min(args.steps, 200), step, flush_first=False)
+
+    # ---- the same work in the order a trainer must issue it: one loss launch per minibatch, each behind the previous
+    # (minibatch j+1's policy outputs do not exist before the optimizer step on minibatch j) -- one stream, a linear graph
+    trainer_order = None
+    if Mb > 1 or E > 1:
+        for _ in range(3):
+            flush_l2()
+            hp.run_trainer_order(pol_dev)
+        barrier()
+        w0 = time.perf_counter()
+        ms_to = timed_steps(min(args.steps, 500), lambda: hp.run_trainer_order(pol_dev))
+        barrier()
+        windows.append((w0, time.perf_counter()))
+        to_ms = max_over_ranks(sum(ms_to)) / len(ms_to)
+        g_chain = hp.loss_chain_graph(pol_dev)
+        chain_ms = statistics.mean(timed_steps(50, g_chain.replay)) / (E * Mb)
+        trainer_order = dict(ms_per_step=to_ms, value=total_transitions / (to_ms * 1e-3), unit=UNIT,
+                             loss_launches_per_step=E * Mb, us_per_dependent_loss_launch=chain_ms * 1e3,
+                             what="GAE once, then one loss launch per (epoch, minibatch), each waiting for the one before it, "
+                                  "one stream (a linear CUDA graph); CUDA events, L2 flushed per step")
 
     # ---- e2e: pinned host buffers in / out through HotPath.run_host -------------------------------
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    for _ in range(3):
-        hp.run_host(pinned, pol_host, out_host)
-    barrier()
-    wall = []
-    nbytes = None
-    for _ in range(e2e_steps):
-        flush_l2()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        nbytes = hp.run_host(pinned, pol_host, out_host)
-        wall.append(time.perf_counter() - t0)
-    e2e_t = torch.tensor([sum(wall)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = cfg.transitions * world / (e2e_t.item() / e2e_steps)
+
+    def e2e_run(**kw):
+        for _ in range(3):
+            hp.run_host(pinned, pol_host, out_host, **kw)
+        barrier()
+        wall, nb = [], None
+        w0_ = time.perf_counter()
+        for _ in range(e2e_steps):
+            flush_l2()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nb = hp.run_host(pinned, pol_host, out_host, **kw)
+            wall.append(time.perf_counter() - t0)
+        windows.append((w0_, time.perf_counter()))
+        return max_over_ranks(sum(wall)) / e2e_steps, nb
+
+    e2e_s, nbytes = e2e_run()
+    e2e_res_s, nbytes_res = e2e_run(pol_device=pol_all)  # policy outputs born on the GPU, as in production
+    e2e_value = total_transitions / e2e_s
 
     # ---- per-kernel durations for the roofline: CUDA events around graphs of one kernel kind ------
     peak, peak_src = peaks()
@@ -321,8 +663,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     # the loss launches exactly as the step issues them (one batched launch, one per epoch with PopArt, or one per
     # minibatch with --no-batch); PopArt's tiny update kernels ride along in the per-epoch case
     loss_launches = (E if cfg.popart else -(-(E * Mb) // 32)) if hp._immediate else E * Mb
-    # stand-alone there is no kernel ahead to overlap with: launched without the programmatic attribute (the loss kernel
-    # then also skips the L2 requests it only issues when it can become resident under the scan)
+    # stand-alone there is no kernel ahead to overlap with: launched without the programmatic attribute
     pdl_was = ops.set_pdl(False)
     g_loss = graph_of(lambda: hp._run_losses(pol_dev))
     lf = hp.leaf
@@ -333,10 +674,12 @@ def run_ours(args, cfg, rank, world, local_rank):
                                           lane_part=hp.lane_part, **pack_kw))
     ops.set_pdl(pdl_was)
     hp.pg = pg_saved
+    w0 = time.perf_counter()
     loss_ms = statistics.mean(timed_steps(k_reps, g_loss.replay)) / loss_launches
     gae_ms = statistics.mean(timed_steps(k_reps, g_gae.replay))
-    loss_ms_warm = statistics.mean(timed_steps(k_reps, g_loss.replay, flush_l2=False)) / loss_launches
-    gae_ms_warm = statistics.mean(timed_steps(k_reps, g_gae.replay, flush_l2=False))
+    windows.append((w0, time.perf_counter()))
+    loss_ms_warm = statistics.mean(timed_steps(k_reps, g_loss.replay, flush_first=False)) / loss_launches
+    gae_ms_warm = statistics.mean(timed_steps(k_reps, g_gae.replay, flush_first=False))
     loss_bytes = LOSS_BYTES[bool(cfg.clip_value)] * T * n * (E * Mb // loss_launches)
     gae_bytes = GAE_BYTES * (cfg.L - 1) * N
     kern = {
@@ -359,8 +702,25 @@ def run_ours(args, cfg, rank, world, local_rank):
                     algorithmic_bytes_per_launch=kern[dom]["bytes_per_launch"],
                     ms_per_launch=kern[dom]["ms_per_launch"])
     step_bytes = gae_bytes + LOSS_BYTES[bool(cfg.clip_value)] * T * N * E
-    t_region1 = time.perf_counter()
-    clocks = sampler.stop(t_region0, t_region1) if sampler else None
+
+    # ---- the neighbours of the path, each with its own roofline (rank 0, N = 1) --------------------
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extra = {}
+        try:
+            extra.update(extras_run(cfg_full, dev, peak, timed_steps))
+        except Exception as e:  # noqa: BLE001
+            extra["error"] = f"{type(e).__name__}: {e}"
+    clocks = sampler.stop(windows) if sampler else None
+
+    trainer_line = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            del flush, flush_rd
+            torch.cuda.empty_cache()
+            trainer_line = trainer_step_run(cfg, dev)
+        except Exception as e:  # noqa: BLE001
+            trainer_line = dict(error=f"{type(e).__name__}: {e}")
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------
     cpu = None
@@ -368,24 +728,25 @@ def run_ours(args, cfg, rank, world, local_rank):
         if affinity_before:
             os.sched_setaffinity(0, affinity_before)  # the CPU arm gets every host core
         r = cpu_reference_run(cfg, steps=200, warmup=2, budget_s=args.cpu_budget_s)
-        cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port",
-                   sample=f"{r['steps']} full steps ({r['ms_per_step']:.1f} ms each) of the same workload, oracle port "
-                          f"(torch-CPU, float64 GAE python scan + loss + autograd backward), {r['cores']} threads")
+        cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=_sample_text(r, cfg),
+                   stages=r["stages"])
     if rank == 0:
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-            ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+            ms_per_step=ms_per_step, higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32",
             data="synthetic",
-            config=dict(workload=workload_name(cfg), transitions_per_step_per_gpu=cfg.transitions,
+            config=dict(workload=workload_name(cfg_full), per_gpu=workload_name(cfg) if world > 1 else "the whole workload",
+                        transitions_per_step_per_gpu=cfg.transitions,
                         l2="flushed between timed iterations (256 MiB device write, then 256 MiB device read, before each step; working set "
                            f"{step_bytes / 1e6:.0f} MB algorithmic)",
                         timing="CUDA events per step on the launch stream, sum over steps, max over ranks",
                         launch="one CUDA graph per step" + ("" if world == 1 else (
                             f" ({hp.exchange_kind} exchange of the float64 stats table captured inside)"
                             if hp._graph_a is None else f" split in two around the {hp.exchange_kind} exchange of the float64 stats table")),
-                        loss_launch=("batched: %d launch(es) per step covering %d minibatches each" %
+                        loss_launch=("batched: %d launch(es) per step covering %d minibatches each (every minibatch's policy outputs "
+                                     "given up front; see step_trainer_order for the dependency order of a real trainer)" %
                                      (loss_launches, E * Mb // loss_launches)) if hp._immediate else "one launch per minibatch",
-                        sample_side="K2 pack (float4 per transition)" if hp.pack is not None else "separate leaves",
+                        sample_side="K2 pack (float4 per transition, row pairs interleaved)" if hp.pack is not None else "separate leaves",
                         minibatch_stats="added inside the loss kernel from K2's per-lane sums (table on a side branch)"
                         if hp.fuse_stats else "srl_group_stats table between K2 and the loss",
                         minibatch_gather=("fused into the loss loads (lane_idx)" if hp.fuse_gather else "explicit K5 gather") +
@@ -394,19 +755,25 @@ def run_ours(args, cfg, rank, world, local_rank):
                         programmatic_dependent_launch=bool(ops.pdl_enabled()),
                         kernel_timing="kernels[*]: each kernel alone in a graph, launched without the programmatic "
                                       "attribute, CUDA events, L2 flushed"),
-            clocks=clocks,
+            clocks=clocks, parity_check=pc,
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=nbytes["h2d_bytes"],
-                     d2h_bytes_per_step=nbytes["d2h_bytes"], ms_per_step=e2e_t.item() / e2e_steps * 1e3, steps=e2e_steps,
-                     what="HotPath.run_host: pinned host sample + policy outputs -> H2D -> step -> D2H of adv, ret (the "
-                          "reference's host mirror, mappo.py:254-257) and the loss/stats table; gradients stay in HBM for "
-                          "the policy's backward; one CUDA graph; wall clock incl. final stream sync"),
+                     d2h_bytes_per_step=nbytes["d2h_bytes"], ms_per_step=e2e_s * 1e3, steps=e2e_steps,
+                     what="HotPath.run_host: pinned host sample + policy outputs of every minibatch -> H2D -> step -> D2H of adv, "
+                          "ret (the reference's host mirror, mappo.py:254-257) and the loss/stats table; gradients stay in HBM for "
+                          "the policy's backward; one CUDA graph; wall clock incl. final stream sync",
+                     policy_outputs_resident=dict(
+                         value=total_transitions / e2e_res_s, ms_per_step=e2e_res_s * 1e3,
+                         h2d_bytes_per_step=nbytes_res["h2d_bytes"], d2h_bytes_per_step=nbytes_res["d2h_bytes"],
+                         what="the same call with the policy outputs already in HBM (where the policy network produces them in "
+                              "production): only the sample crosses PCIe")),
             gpu_launches=hp.count_launches() * args.steps,
             gpu_launches_per_step=hp.count_launches(),
             roofline=roofline, kernels=kern,
             step=dict(algorithmic_bytes=step_bytes, gbs=step_bytes / ms_per_step / 1e6,
                       frac_of_peak=step_bytes / ms_per_step / 1e6 / peak,
                       ms_per_step_l2_warm=statistics.mean(ms_warm),
-                      value_l2_warm=cfg.transitions * world / (statistics.mean(ms_warm) * 1e-3)),
+                      value_l2_warm=total_transitions / (statistics.mean(ms_warm) * 1e-3)),
+            step_trainer_order=trainer_order, trainer_step=trainer_line, extra=extra,
             cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
     del hp, g_loss, g_gae  # CUDA graphs and peer mailboxes go before the process group does
@@ -416,6 +783,51 @@ def run_ours(args, cfg, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def extras_run(cfg, dev, peak, timed_steps):
+    """The callers either side of the path, each against the same HBM roofline."""
+    from srl_b200 import ops
+    out = {}
+    # ---- K1: the batch gather on frame-shaped rows: [L, slots, row] -> [L, B, row] through an index vector ------------
+    L, slots, row = 32, 512, int(np.prod(cfg.obs_shape)) if cfg.obs_shape else 4096
+    src = torch.randint(0, 255, (L, slots, row), dtype=torch.uint8, device=dev)
+    dst = torch.empty_like(src)
+    idx = torch.randperm(slots, device=dev).to(torch.int32)
+    fn = lambda: ops.batch_gather([(src, dst)], idx)
+    fn()
+    ms = statistics.mean(timed_steps(10, fn))
+    nbytes = 2 * src.numel()
+    out["batch_gather_k1"] = dict(ms_per_launch=ms, bytes_per_launch=nbytes, what=f"srl_batch_gather of uint8 rows of {row} B, "
+                                  f"[{L}, {slots}] items through a random permutation (read + write)",
+                                  roofline=dict(bound="hbm", achieved=nbytes / ms / 1e6, peak=peak, unit="GB/s",
+                                                frac=nbytes / ms / 1e6 / peak))
+    del src, dst
+    # ---- K4b: the loss from the actor head's logits (Categorical log-prob / entropy fused in) -----------------------
+    T, N = cfg.T, min(cfg.N, 4096)
+    c1 = dataclasses.replace(cfg, B=N // cfg.A, epochs=1, minibatches=1)
+    s = synth.make_sample_scalars(c1, 7)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v.reshape(c1.L, -1))).to(dev) for k, v in s.items()}
+    adv, ret, part = ops.gae_scan(d["reward"], d["value"], d["done"], d["truncated"], d["on_reset"], cfg.gamma, cfg.lmbda,
+                                  row_lo=0, row_hi=T)
+    stats = ops.group_stats(part, groups=1, per=c1.N)[0]
+    logits_np, act_np = synth.make_logits_actions(c1, (T, c1.N), 3)
+    logits, act = torch.from_numpy(logits_np).to(dev), torch.from_numpy(act_np).to(dev)
+    vp = d["value"][:T].clone()
+    hpk = ops.LossHyper(**hyper_kwargs(cfg))
+    fn = lambda: ops.ppo_loss_from_logits(logits, act, list(cfg.num_actions), vp, d["old_logp"][:T], d["value"][:T], ret[:T],
+                                          adv[:T], d["on_reset"][1:T + 1], stats, hpk)
+    fn()
+    ms = statistics.mean(timed_steps(10, fn))
+    SK, heads = int(sum(cfg.num_actions)), len(cfg.num_actions)
+    per = 8 * SK + 4 * heads + 25  # SURVEY.md §8(d)
+    nbytes = per * T * c1.N
+    out["loss_from_logits_k4b"] = dict(ms_per_launch=ms, bytes_per_launch=nbytes,
+                                       what=f"srl_ppo_loss_from_logits, T={T}, N={c1.N}, heads {list(cfg.num_actions)}: "
+                                            f"{per} B per transition (SURVEY.md §8d)",
+                                       roofline=dict(bound="hbm", achieved=nbytes / ms / 1e6, peak=peak, unit="GB/s",
+                                                     frac=nbytes / ms / 1e6 / peak))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -423,9 +835,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2_atari_large", choices=sorted(synth.CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: the full config per GPU (weak) or the config's environments split over the GPUs (strong)")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the K1 / K4b / trainer_step lines")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--shuffle-block", type=int, default=1,
                     help="environments per shuffled block (1 = per-environment permutation; 8 = one 32-byte sector)")
     ap.add_argument("--branches", type=int, default=16, help="parallel CUDA-graph branches for the per-minibatch launches")
@@ -443,7 +859,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         if args.steps > 50:
-            args.steps = 50  # a CPU step of cfg2 is ~0.2 s; keep the whole arm within minutes
+            args.steps = 50  # a CPU step of cfg2 is ~0.1 s; keep the whole arm within minutes
         run_reference_arm(args, cfg, rank, world)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:

@@ -191,11 +191,23 @@ class DeviceSlabBuffer:
         self._slot_ready.clear()
         self._slot_free_after.clear()
         self._pending = []
-        for _, _, (old_leaves, old_meta) in pending:
+        for _, _, (old_leaves, old_meta), _ in pending:
             self._stage(old_leaves, old_meta)
+
+    @staticmethod
+    def _host_only(v) -> bool:
+        """Leaves that cannot (or need not) live on the device: non-numeric dtypes -- real SRL samples carry `policy_name`
+        as a '<U..' string array (policy_worker.py:186; the trainer worker clears it after get(), trainer_worker.py:169) --
+        and zero-size leaves.  They stay on the host and are stacked with np.stack, as the reference does for every leaf."""
+        v = np.asarray(v)
+        return v.dtype.kind not in "fiub" or v.size == 0
 
     def _stage(self, leaves, metadata) -> None:
         """One sample (its flattened leaves) -> one pinned block -> one async H2D into a device staging slot."""
+        all_leaves = leaves
+        host_only = {k: np.asarray(v) for k, v in leaves if v is not None and self._host_only(v)}
+        if host_only:
+            leaves = [(k, None if k in host_only else v) for k, v in leaves]
         if self._layout is None:
             self._init_layout(leaves)
         elif any(v is not None and k not in self._layout.spec for k, v in leaves):
@@ -230,13 +242,13 @@ class DeviceSlabBuffer:
             done.record(self._copy_stream)
         self._slot_ready[slot] = done
         self.bytes_staged += lay.bytes
-        self._pending.append((slot, present, (leaves, metadata)))
+        self._pending.append((slot, present, (all_leaves, metadata), host_only))
 
     def _assemble(self, items) -> Any:
         """np.stack(axis=1) of the staged samples, every leaf in one srl_batch_gather call."""
         lay = self._layout
         B = len(items)
-        slots = [s for s, _, _ in items]
+        slots = [it[0] for it in items]
         main = torch.cuda.current_stream()
         for s in slots:
             main.wait_event(self._slot_ready.pop(s))
@@ -245,13 +257,18 @@ class DeviceSlabBuffer:
         descs = []
         names = [k for k in lay.names if k in lay.spec or not any(n.startswith(k + ".") for n in lay.spec)]
         for k in names:
-            if k not in lay.spec or not any(k in present for _, present, _ in items):
+            host = [it[3].get(k) for it in items]
+            if any(h is not None for h in host):  # host-only leaf: np.stack(axis=1), zero-filled where a sample had None
+                like = next(h for h in host if h is not None)
+                out[k] = np.stack([np.zeros_like(like) if h is None else h for h in host], axis=1)
+                continue
+            if k not in lay.spec or not any(k in it[1] for it in items):
                 out[k] = None  # None in every sample stays None (base/namedarray.py:610)
                 continue
             off, dtype, shape = lay.spec[k]
             row_bytes = int(np.prod(shape[1:], dtype=np.int64)) * dtype.itemsize
             dst = torch.empty((lay.L, B) + shape[1:], dtype=_torch_dtype(dtype), device=self.device)
-            missing = [j for j, (_, present, _) in enumerate(items) if k not in present]
+            missing = [j for j, it in enumerate(items) if k not in it[1]]
             descs.append(LeafDesc(self._stage_dev.data_ptr() + off, dst.data_ptr(), row_bytes, self._n_slots, row_bytes,
                                   lay.bytes))
             out[k] = dst

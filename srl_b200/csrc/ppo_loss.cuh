@@ -101,26 +101,30 @@ struct RuntimeCfg {
   __device__ static __forceinline__ bool popart(bool have) { return have; }
 };
 
-// torch.nn.{MSELoss,HuberLoss,SmoothL1Loss}(reduction='none') value and derivative wrt the input.
-// Inside a kind both branches are evaluated and selected (the quadratic / linear choice is per element, and a
-// divergent branch costs more than the three spare flops).
-__device__ __forceinline__ void pointwise_loss(int kind, float prm, float d, float& l, float& dl) {
-  if (kind == SRL_VL_MSE) {
-    l = d * d;
-    dl = 2.f * d;
-  } else if (kind == SRL_VL_HUBER) {
-    const float z = fabsf(d);
-    const bool quad = z < prm;
+// torch.nn.{MSELoss,HuberLoss,SmoothL1Loss}(reduction='none'): value and derivative wrt the input, separately (the clipped
+// value loss needs the value of ONE difference and the derivative of both, see element()).  Inside a kind both branches
+// are evaluated and selected (the quadratic / linear choice is per element, and a divergent branch costs more than the
+// spare flops).
+__device__ __forceinline__ float pointwise_value(int kind, float prm, float d) {
+  if (kind == SRL_VL_MSE) return d * d;
+  const float z = fabsf(d);
+  const bool quad = z < prm;
+  if (kind == SRL_VL_HUBER) {
     const float lq = 0.5f * z * z, ll = prm * (z - 0.5f * prm);
-    l = quad ? lq : ll;
-    dl = quad ? d : copysignf(prm, d);  // d != 0 here (|d| >= prm > 0), so this is prm * sign(d)
-  } else {
-    const float z = fabsf(d);
-    const bool quad = z < prm;
-    const float lq = 0.5f * z * z / prm, ll = z - 0.5f * prm;
-    l = quad ? lq : ll;
-    dl = quad ? d / prm : copysignf(1.f, d);
+    return quad ? lq : ll;
   }
+  const float lq = 0.5f * z * z / prm, ll = z - 0.5f * prm;
+  return quad ? lq : ll;
+}
+__device__ __forceinline__ float pointwise_grad(int kind, float prm, float d) {
+  if (kind == SRL_VL_MSE) return 2.f * d;
+  const bool quad = fabsf(d) < prm;
+  if (kind == SRL_VL_HUBER) return quad ? d : copysignf(prm, d);  // d != 0 in the linear branch (|d| >= prm > 0)
+  return quad ? d / prm : copysignf(1.f, d);
+}
+__device__ __forceinline__ void pointwise_loss(int kind, float prm, float d, float& l, float& dl) {
+  l = pointwise_value(kind, prm, d);
+  dl = pointwise_grad(kind, prm, d);
 }
 
 struct Uniforms {
@@ -212,19 +216,26 @@ __device__ __forceinline__ void element(const LossHyperDev& h, const Uniforms& u
 
   // ---- critic: mappo.py:172-184, utils.py:228-239 ---------------------------------------------
   const float vt = CFG::popart(u.popart) ? popart_normalize(rt, u) : rt;
-  float l, dl;
-  pointwise_loss(CFG::vl(h), h.vl_param, vp - vt, l, dl);
-  float vl = l, gv = dl;
+  const float da = vp - vt;
+  float vl, gv;
   if (CFG::clip(h)) {
+    // max(loss(v - vt), loss(vc - vt)) with vc = old + clamp(v - old, +-eps).  All three pointwise losses are even and
+    // strictly increasing in |d|, so the larger loss is the loss of the larger |difference|: ONE loss evaluation instead of
+    // two, and torch.max's gradient rule (the larger operand's, ties split evenly) is decided on |d| -- no data-dependent
+    // branch (the round-1 form compared the two losses and branched; ncu showed the reconvergence barriers in the loop).
     const float ovn = (CFG::popart(u.popart) && h.normalize_old_value) ? popart_normalize(ov, u) : ov;
     const float dv = vp - ovn;
     const float vc = ovn + fminf(fmaxf(dv, -h.veps), h.veps);
+    const float db = vc - vt;
     const bool in = fabsf(dv) <= h.veps;  // clamp passes grad on the closed interval
-    float l2, dl2;
-    pointwise_loss(CFG::vl(h), h.vl_param, vc - vt, l2, dl2);
-    dl2 = in ? dl2 : 0.f;
-    vl = fmaxf(l, l2);
-    gv = l > l2 ? dl : (l < l2 ? dl2 : 0.5f * (dl + dl2));  // torch.max splits ties evenly
+    const float za = fabsf(da), zb = fabsf(db);
+    const float ga = pointwise_grad(CFG::vl(h), h.vl_param, da);
+    const float gb = in ? pointwise_grad(CFG::vl(h), h.vl_param, db) : 0.f;
+    vl = pointwise_value(CFG::vl(h), h.vl_param, za >= zb ? da : db);
+    gv = za > zb ? ga : gb;
+    gv = za == zb ? 0.5f * (ga + gb) : gv;  // torch.max splits ties evenly
+  } else {
+    pointwise_loss(CFG::vl(h), h.vl_param, da, vl, gv);
   }
   g_v = h.wv * scale * gv;
 
@@ -233,15 +244,14 @@ __device__ __forceinline__ void element(const LossHyperDev& h, const Uniforms& u
   // masked_normalization (utils.py:38-67) in float64, cast to float at the end; masked entries are centred
   // zeros there (x = adv * mask) and here
   const float nadv = static_cast<float>(div_by(__dsub_rn(static_cast<double>(ad), u.mean), u.denom, u.rdenom));
+  const float cr = fminf(fmaxf(ratio, h.clip_lo), h.clip_hi);
   const float s1 = ratio * nadv;
-  const float s2 = fminf(fmaxf(ratio, h.clip_lo), h.clip_hi) * nadv;
-  const bool in_clip = ratio >= h.clip_lo && ratio <= h.clip_hi;
-  // d min(s1, s2) / d ratio / nadv: 1 where s1 is the smaller, the clamp's pass-through where s2 is, the mean of
-  // the two on ties (torch.min splits ties evenly)
-  const float pass = in_clip ? 1.f : 0.f;
-  const float g12 = s1 < s2 ? 1.f : (s1 > s2 ? pass : 0.5f + 0.5f * pass);
+  const float s2 = cr * nadv;
+  // d min(s1, s2) / d new_logp = ratio * nadv (= s1) where s1 is the smaller or the clamp passes (cr == ratio, then
+  // s1 == s2 and torch.min's even split adds up to the whole); 0 where the clamped branch is the smaller.  (s1 == s2
+  // outside the clip range needs nadv == 0 or an underflow: the reference's half gradient is then a half of ~0.)
   float obj = fminf(s1, s2);
-  float gsum = g12 * nadv * ratio;
+  float gsum = (cr == ratio || s1 < s2) ? s1 : 0.f;
   if (CFG::dual(h)) {
     const float s3 = -h.c_clip * fabsf(nadv);  // -sign(nadv) * c * nadv
     gsum = obj > s3 ? gsum : (obj < s3 ? 0.f : 0.5f * gsum);
@@ -259,7 +269,7 @@ __device__ __forceinline__ void element(const LossHyperDev& h, const Uniforms& u
   rs.adv += mk * ad;
   rs.ratio += mk * ratio;
   rs.vt += mk * vt;
-  rs.ret += mk * rt;
+  if (CFG::popart(u.popart)) rs.ret += mk * rt;  // only reported with PopArt (mappo.py:215-216)
   rs.clip += (valid && s2 < s1) ? 1 : 0;
 }
 

@@ -400,6 +400,60 @@ class HotPath:
             self._graph.replay()
         self.step_count += 1
 
+    def run_trainer_order(self, pol, use_graph: bool = True) -> None:
+        """The step in the order a trainer must issue it (mappo.py:240-299 with minibatches): GAE once, then ONE loss launch
+        per (epoch, minibatch), each behind the previous one on the same stream -- minibatch j+1's policy outputs do not exist
+        before the optimizer step on minibatch j, so the launches cannot be batched.  With use_graph the chain is a linear
+        CUDA graph (what `bench.py` reports as step_trainer_order); `MultiAgentPPOB200.step` issues the same launches
+        eagerly between its policy calls."""
+        if not use_graph:
+            self._trainer_order_launches(pol)
+            self.step_count += 1
+            return
+        if getattr(self, "_graph_to", None) is None or self._graph_to_pol is not pol:
+            saved = self.step_count
+            self.step_count = 0
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._trainer_order_launches(pol)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._trainer_order_launches(pol)
+            self._graph_to, self._graph_to_pol = g, pol
+            self.step_count = saved
+        self._graph_to.replay()
+        self.step_count += 1
+
+    def _trainer_order_launches(self, pol) -> None:
+        self.advantages()
+        self._join_stats()  # per-minibatch launches read their statistics rows from the table
+        for e in range(self.epochs):
+            if self.popart:
+                self.update_popart()
+            for j in range(self.minibatches):
+                self.loss(e, j, *pol[e][j])
+        self.finalize()
+
+    def loss_chain_graph(self, pol) -> torch.cuda.CUDAGraph:
+        """Only the E*M dependent per-minibatch loss launches of run_trainer_order, as a graph (bench.py: time per launch)."""
+        def chain():
+            for e in range(self.epochs):
+                for j in range(self.minibatches):
+                    self.loss(e, j, *pol[e][j])
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            chain()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            chain()
+        return g
+
     def _capture(self, pol) -> None:
         # NOTE: launch arguments are frozen at capture, so a replayed graph re-uses the permutations of
         # step_count == 0 every step (what a benchmark wants); the trainer launches eagerly and reseeds per step.
@@ -460,7 +514,7 @@ class HotPath:
 
     # ------------------------------------------------------------------------------------------
     def run_host(self, sample: Dict[str, np.ndarray], pol_host: torch.Tensor, out_host: Dict[str, torch.Tensor],
-                 use_graph: bool = True) -> Dict[str, int]:
+                 use_graph: bool = True, pol_device: Optional[torch.Tensor] = None) -> Dict[str, int]:
         """Host buffers in, host buffers out -- the call a host-side user of the path makes.
 
         sample: the six scalar leaves (pinned tensors are copied directly, numpy arrays are staged through pinned
@@ -474,6 +528,8 @@ class HotPath:
         while the next epoch computes), so H2D, kernels and D2H overlap on the full-duplex link.  With use_graph the
         whole choreography -- copies, kernels, cross-stream dependencies -- is ONE CUDA graph keyed by the host buffer
         addresses (the ~40 host-side launches of the eager version cost more wall clock than the kernels).
+        `pol_device` (float32 [E, M, 3, T, n_mb] already in HBM, where the policy network produces it in production):
+        the policy outputs are taken from there and only the sample crosses PCIe (pol_host is ignored).
         Returns the bytes moved each way."""
         E, Mb = self.epochs, self.minibatches
         if not hasattr(self, "_pol_dev_all"):
@@ -482,18 +538,20 @@ class HotPath:
             self._s_in, self._s_out = torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)
             self._host_graph, self._host_graph_key = None, None
         pinned = self._stage_sample(sample)
+        pol_src = pol_host if pol_device is None else pol_device
         if use_graph and (self.pg is None or self.peer is not None):  # see _capture about captured NCCL collectives
-            key = tuple(pinned[k].data_ptr() for k in SAMPLE_F32 + SAMPLE_U8) + (pol_host.data_ptr(),) + \
+            key = tuple(pinned[k].data_ptr() for k in SAMPLE_F32 + SAMPLE_U8) + (pol_src.data_ptr(),) + \
                 tuple(out_host[k].data_ptr() for k in ("adv", "ret", "grads", "out") if k in out_host)
             if self._host_graph is None or self._host_graph_key != key:
-                self._capture_host(pinned, pol_host, out_host)
+                self._capture_host(pinned, pol_src, out_host)
                 self._host_graph_key = key
             self._host_graph.replay()
         else:
-            self._host_pipeline(pinned, pol_host, out_host, 1)
+            self._host_pipeline(pinned, pol_src, out_host, 1)
         self.step_count += 1
         torch.cuda.current_stream().synchronize()
-        h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in pinned) + pol_host.numel() * 4
+        h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in pinned) + \
+            (pol_host.numel() * 4 if pol_device is None else 0)
         d2h = 2 * self.adv.numel() * 4 + self.out.numel() * 8
         if "grads" in out_host:
             d2h += self.grads_all.numel() * 4
@@ -534,8 +592,12 @@ class HotPath:
             ev_sample = torch.cuda.Event()
             ev_sample.record(s_in)
             ev_pol = []
+            resident = pol_host.is_cuda  # policy outputs already in HBM: used in place
+            self._pol_run = [[tuple(pol_host[e, j, q] for q in range(3)) for j in range(self.minibatches)]
+                             for e in range(E)] if resident else self._pol_dev
             for e in range(E):
-                self._pol_dev_all[e].copy_(pol_host[e], non_blocking=True)
+                if not resident:
+                    self._pol_dev_all[e].copy_(pol_host[e], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(s_in)
                 ev_pol.append(ev)
@@ -584,11 +646,11 @@ class HotPath:
         if self.popart:
             self.update_popart()
         if self._immediate:
-            self.loss_batch([(e, j) for j in range(self.minibatches)], self._pol_dev)
+            self.loss_batch([(e, j) for j in range(self.minibatches)], self._pol_run)
             return
         if branches <= 1:
             for j in range(self.minibatches):
-                self.loss(e, j, *self._pol_dev[e][j])
+                self.loss(e, j, *self._pol_run[e][j])
             return
         if not hasattr(self, "_side") or len(self._side) < branches:
             self._side = [torch.cuda.Stream(device=self.device) for _ in range(branches)]
@@ -597,6 +659,6 @@ class HotPath:
             st.wait_stream(main)
         for j in range(self.minibatches):
             with torch.cuda.stream(used[j % len(used)]):
-                self.loss(e, j, *self._pol_dev[e][j])
+                self.loss(e, j, *self._pol_run[e][j])
         for st in used:
             main.wait_stream(st)

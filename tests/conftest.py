@@ -15,3 +15,21 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_collection_modifyitems(config, items):
+    """Without a CUDA device the gpu-marked tests are skipped instead of failing (plain `pytest tests` on a CPU machine is
+    then green like `-m "not gpu"`).  SRL_TEST_STRICT_GPU=1 keeps them hard failures -- for a box that SHOULD have a GPU."""
+    if os.environ.get("SRL_TEST_STRICT_GPU") == "1":
+        return
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (srl_b200 has no CPU path); SRL_TEST_STRICT_GPU=1 makes this a failure")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

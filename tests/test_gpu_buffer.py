@@ -185,3 +185,26 @@ def test_put_frames_equals_put_of_decoded_sample():
     assert xb.metadata == dict(sampling_weight=1.5)
     with pytest.raises(ValueError):  # only raw_bytes messages carry leaf frames
         b.put_frames(wire.dumps(samples[0], "pickle_dict"))
+
+
+def test_string_and_empty_leaves_stay_on_the_host():
+    """Real SRL samples carry `policy_name` as a '<U..' string array (policy_worker.py:186; the wire format ships it,
+    base/namedarray.py:115-128) and the reference's buffer stacks it like any other leaf before the trainer worker clears
+    it (trainer_worker.py:169).  Such leaves -- and zero-size ones -- cannot live in HBM: they are stacked on the host with
+    np.stack(axis=1) while the numeric leaves go through the device gather."""
+    from srl_b200.buffer import DeviceSlabBuffer
+    rng = np.random.default_rng(3)
+    B, L = 4, 9
+    samples = []
+    for i in range(B):
+        s = _sample(rng, L=L)
+        s.policy_name = np.full((L, 1), f"policy_{i % 2}")
+        s.send_timestamp = np.zeros((L, 0), dtype=np.int64)  # a zero-size leaf
+        samples.append(s)
+    buf = DeviceSlabBuffer(max_size=4, reuses=1, batch_size=B)
+    assert [buf.put(copy.deepcopy(s)) for s in samples] == [False] * (B - 1) + [True]
+    got = buf.get().sample
+    assert isinstance(got.policy_name, np.ndarray) and got.policy_name.shape == (L, B, 1)
+    assert np.array_equal(got.policy_name, np.stack([s.policy_name for s in samples], axis=1))
+    assert isinstance(got.send_timestamp, np.ndarray) and got.send_timestamp.shape == (L, B, 0)
+    assert got.reward.is_cuda and np.array_equal(got.reward.cpu().numpy(), np.stack([s.reward for s in samples], axis=1))

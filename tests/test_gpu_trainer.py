@@ -134,3 +134,86 @@ def test_constructor_contract():
     cpu_pol = TinyActorCriticPolicy(OBS_DIM, NUM_ACTIONS, device="cpu")
     with pytest.raises(RuntimeError, match="no CPU path"):
         MultiAgentPPOB200(cpu_pol)
+
+
+def test_staging_keeps_wire_dtypes_and_crosses_pcie_once():
+    """A2: every leaf is sent to the device ONCE, in its own dtype (the reference inflates all of them to float32 on the
+    device, api/trainer.py:215-217; the first drop-in sent the scalar leaves twice).  H2D bytes of a step == the host
+    sample's bytes; uint8 frames and flags are uint8 in HBM; what `policy.analyze` sees is float32."""
+    from srl_b200.namedarray import size_bytes
+    from srl_b200.trainer import MultiAgentPPOB200
+    cfg, kw = CASES["minibatch"]
+    seen = {}
+
+    class Spy(TinyActorCriticPolicy):
+
+        def analyze(self, sample, **k):
+            seen["analyze_dtypes"] = {str(sample.obs.vec.dtype), str(sample.obs.frame.dtype), str(sample.on_reset.dtype)}
+            return super().analyze(sample, **k)
+
+    pol = Spy(OBS_DIM, NUM_ACTIONS, device="cuda:0", seed=3)
+    tr = MultiAgentPPOB200(pol, prefetch=False, **dict(kw, optimizer="sgd", optimizer_config=dict(lr=0.01)))
+    s = make_sample(cfg, seed=2)
+    rng = np.random.default_rng(0)
+    s.obs = NamedArray(vec=s.obs.vec, frame=rng.integers(0, 255, s.obs.vec.shape[:2] + (4, 12, 12), dtype=np.uint8))
+    host_bytes = size_bytes(s)
+    staged_host, staged_dev = tr._stage(s)
+    torch.cuda.synchronize()
+    assert staged_dev.obs.frame.dtype == torch.uint8 and staged_dev.on_reset.dtype == torch.uint8
+    assert staged_dev.obs.vec.dtype == torch.float32 and staged_dev.obs.frame.is_cuda
+    assert tr.h2d_bytes == host_bytes
+    before = tr.h2d_bytes
+    tr.step(s)
+    assert tr.h2d_bytes - before == host_bytes  # one more staging of the same sample: again exactly its bytes, once
+    assert seen["analyze_dtypes"] == {"torch.float32"}
+
+
+def test_trainer_accepts_the_references_own_records():
+    """Inside an SRL checkout the sample is SRL's `SampleBatch` and SRL policies test `isinstance(x, NamedArray)` against
+    SRL's class (e.g. base.namedarray.recursive_apply inside analyze): the records handed to `policy.analyze` must be of
+    that family, not of this package's mirror.  Uses the unmodified reference classes (oracle/ref_loader.py)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("no reference files (neither /root/reference nor oracle/_ref)")
+    R = ref_loader.load()
+    from srl_b200.trainer import MultiAgentPPOB200
+    NA = R.namedarray.NamedArray
+    cfg, kw = CASES["minibatch"]
+    a = make_sample(cfg, seed=4)
+
+    class RefStylePolicy(TinyActorCriticPolicy):
+
+        def analyze(self, sample, **k):
+            assert isinstance(sample, NA) and isinstance(sample.obs, NA), type(sample)
+            sample = R.namedarray.recursive_apply(sample, lambda x: x)  # what SRL's _ppo_analyze does first
+            assert isinstance(sample, NA)
+            return super().analyze(sample, **k)
+
+    sb = R.trainer.SampleBatch(obs=NA(vec=a.obs.vec), on_reset=a.on_reset, done=a.done, truncated=a.truncated,
+                               action=NA(x=a.action.x), reward=a.reward, info=NA(episode_return=a.info.episode_return),
+                               info_mask=a.info_mask,
+                               analyzed_result=NA(value=a.analyzed_result.value, log_probs=a.analyzed_result.log_probs,
+                                                  adv=None, ret=None))
+    pol = RefStylePolicy(OBS_DIM, NUM_ACTIONS, device="cuda:0", seed=3)
+    tr = MultiAgentPPOB200(pol, prefetch=False, **dict(kw, optimizer="sgd", optimizer_config=dict(lr=0.01)))
+    res = tr.step(sb)
+    assert res.step == 0 and np.isfinite(res.stats["policy_loss"]) and "episode_return" in res.stats
+    assert isinstance(sb.analyzed_result.adv, np.ndarray) and sb.analyzed_result.adv.shape == a.on_reset.shape
+
+
+def test_reused_entry_with_prefetch_recomputes_when_staged_before_adv_existed():
+    """recompute_adv_on_reuse=False + prefetch: a buffer entry served on two consecutive calls is staged the second time
+    BEFORE the first processing wrote adv / ret into it.  The reference decides from the STAGED copy (mappo.py:249) and
+    simply recomputes; the first drop-in looked at the host sample and crashed."""
+    from srl_b200.trainer import MultiAgentPPOB200
+    cfg, kw = CASES["atari"]
+    pol = TinyActorCriticPolicy(OBS_DIM, NUM_ACTIONS, device="cuda:0", seed=4)
+    tr = MultiAgentPPOB200(pol, **dict(kw, recompute_adv_on_reuse=False, optimizer="sgd", optimizer_config=dict(lr=0.0)))
+    s = make_sample(cfg, 7)
+    assert tr.step(s).stats == {}          # primes the pipeline with s
+    r1 = tr.step(s)                        # stages s again (adv still None), processes the first copy -> s.adv is set
+    assert s.analyzed_result.adv is not None
+    r2 = tr.step(s)                        # processes the second copy, staged without adv: recomputed, no crash
+    assert_close_ref(r2.stats["advantage"], r1.stats["advantage"], what="advantage stat")
+    r3 = tr.step(s)                        # this copy was staged WITH adv: the cached branch
+    assert_close_ref(r3.stats["advantage"], r1.stats["advantage"], what="advantage stat (cached)")
