@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SRL_B200_ABI_VERSION 5
+#define SRL_B200_ABI_VERSION 6
 
 typedef void* srl_stream_t; /* cudaStream_t */
 
@@ -257,8 +257,15 @@ int srl_ppo_loss_fwd_bwd(
  * lane_aos != NULL (K2's [N][4] table; pack form with lane indices, one GPU, no PopArt, even n <= 1024): every CTA adds the
  * per-lane sums of ITS minibatch's lanes itself and the problems' norm_stats / local_stats are ignored (may be NULL) --
  * no srl_group_stats launch between K2 and the loss.
+ * xchg != NULL (with lane_aos, several ranks): the kernel also adds every problem's three sums over the RANKS itself -- the
+ * problem's first CTA stores this rank's sums into every rank's mailbox (NVLink peer memory, the srl_xchg_* protocol
+ * below; capacity >= 3 * SRL_MAX_LOSS_BATCH doubles), every CTA collects them in rank order -- so the statistics
+ * all-reduce of utils.py:58-61 costs one NVLink latency inside the loss kernel's prologue instead of two kernels between
+ * the scan and the loss.  Every rank must launch the same sequence of calls on this srl_xchg; it must not be the object
+ * srl_group_stats_xchg / srl_xchg_allreduce_sum use.
  * Gradient tensors must not alias the policy-side inputs (the kernels prefetch inputs of later rows before they store). */
 #define SRL_MAX_LOSS_BATCH 32
+struct srl_xchg; /* the peer-memory exchange handle, declared with its functions at the end of this header */
 typedef struct srl_loss_problem {
   const float* new_logp;     /* [T, n], row stride ld_pol */
   const float* v_pred;
@@ -279,7 +286,7 @@ int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems_host, int n_pr
                                  const float* adv, const uint8_t* on_reset_next, int64_t ld_smp, const float* pack,
                                  int pack_row_lo, const double* lane_aos, int T, int n,
                                  const double* popart_mean_std, const srl_ppo_hyper* hyper,
-                                 size_t workspace_bytes_per_slot, srl_stream_t stream);
+                                 size_t workspace_bytes_per_slot, struct srl_xchg* xchg /* or NULL */, srl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4b  Same loss, but starting from the actor head's logits: also replaces

@@ -19,7 +19,7 @@ SRL_LANE_PART = 8
 SRL_LOSS_OUT_LEN = 16
 SRL_MAX_LEAVES = 32
 SRL_MAX_HEADS = 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 SRL_MAX_LOSS_BATCH = 32
 
 # enum srl_loss_out
@@ -96,7 +96,7 @@ SIGNATURES = {
     "srl_ppo_loss_fwd_bwd_batched": (c_int, [POINTER(LossProblem), c_int, c_int64, c_int64,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                              c_int, c_void_p, c_int, c_int, c_void_p, POINTER(PpoHyper), c_size_t,
-                                             c_void_p]),
+                                             c_void_p, c_void_p]),
     "srl_ppo_loss_from_logits": (c_int, [c_void_p, c_void_p, POINTER(c_int32), c_int, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                          c_int, c_int, c_void_p, c_void_p, c_void_p, POINTER(PpoHyper),

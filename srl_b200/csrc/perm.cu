@@ -110,15 +110,6 @@ extern "C" int srl_philox_perm(uint64_t seed, uint32_t epoch, int n_epochs, int 
   int grid = (n_env + threads - 1) / threads;
   const int cap = sm_count() * 8;
   if (grid > cap) grid = cap;
-  // same shared-memory carve-out as the scan that starts beside this kernel (programmatic launch): an SM that has to be
-  // reconfigured between the two cannot host both
-#ifdef SRL_CARVEOUT_ALL
-  static bool carve_set = false;
-  if (!carve_set) {
-    cudaFuncSetAttribute(philox_perm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    carve_set = true;
-  }
-#endif
   philox_perm_kernel<<<dim3(grid, n_epochs), threads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<uint32_t>(seed & 0xffffffffull), static_cast<uint32_t>(seed >> 32), epoch, n_env, group, bits, out);
   SRL_CUDA(cudaGetLastError());

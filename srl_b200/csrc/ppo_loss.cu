@@ -28,6 +28,7 @@
 // order; deferred (out == NULL): srl_ppo_loss_finalize folds any number of slots later in ONE launch.
 // Either way the result is deterministic for a given launch shape and nothing syncs with the host.
 #include <stdlib.h>
+#include <string.h>
 
 #include "ppo_loss.cuh"
 
@@ -203,7 +204,7 @@ extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, in
                                             const float* ret, const float* adv, const uint8_t* on_reset_next,
                                             int64_t ld_smp, const float* pack, int pack_row_lo, const double* lane_aos,
                                             int T, int n, const double* popart_mean_std, const srl_ppo_hyper* hyper,
-                                            size_t workspace_bytes, srl_stream_t stream) {
+                                            size_t workspace_bytes, srl_xchg* xchg, srl_stream_t stream) {
   using namespace srl;
   using namespace srl::loss;
   SRL_REQUIRE(n_problems >= 0, SRL_ERR_INVALID_ARG, "srl_ppo_loss_fwd_bwd_batched: negative problem count");
@@ -287,10 +288,23 @@ extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, in
     p.out_f32 = q.out_f32;
     p.slot = reinterpret_cast<SlotHeader*>(q.workspace);
   };
+  const XchgView* xv = xchg_view(xchg);
+  SRL_REQUIRE(xchg == nullptr || (xv != nullptr && lane_aos != nullptr && xv->cap >= 3 * kMaxBatch), SRL_ERR_INVALID_ARG,
+              "srl_ppo_loss_fwd_bwd_batched: the in-kernel exchange needs a connected srl_xchg of >= %d doubles and the "
+              "self-computed statistics (lane_aos)", 3 * kMaxBatch);
+  for (int k = 0; k < n_problems && xv != nullptr; ++k)
+    SRL_REQUIRE(problems[k].out != nullptr, SRL_ERR_INVALID_ARG,
+                "srl_ppo_loss_fwd_bwd_batched: the in-kernel exchange needs immediate finalisation (out != NULL): the last CTA "
+                "of each problem ends the exchange round");
   for (int k0 = 0; k0 < n_problems; k0 += kMaxBatch) {
     const int nb = n_problems - k0 < kMaxBatch ? n_problems - k0 : kMaxBatch;
     LossBatch b;
     b.s = s;
+    if (xv != nullptr && xv->world > 1) {
+      b.xv = *xv;
+    } else {
+      memset(&b.xv, 0, sizeof(b.xv));
+    }
     for (int k = 0; k < kMaxBatch; ++k) fill(b.prob[k], problems[k0 + (k < nb ? k : 0)]);
     if (mode == kPack && pair)
       rc = launch_loss_pair(b, nb, st);
@@ -327,7 +341,7 @@ extern "C" int srl_ppo_loss_fwd_bwd(const float* new_logp, const float* v_pred, 
   q.out_f32 = out_f32;
   q.workspace = workspace;
   return srl_ppo_loss_fwd_bwd_batched(&q, 1, ld_pol, ld_grad, old_logp, old_value, ret, adv, on_reset_next, ld_smp,
-                                      nullptr, 0, nullptr, T, n, popart_mean_std, hyper, workspace_bytes, stream);
+                                      nullptr, 0, nullptr, T, n, popart_mean_std, hyper, workspace_bytes, nullptr, stream);
 }
 
 extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* action, const int32_t* head_sizes_host,

@@ -5,6 +5,7 @@
 #include <float.h>
 
 #include "common.cuh"
+#include "xchg.cuh"
 
 namespace srl {
 namespace loss {
@@ -76,6 +77,7 @@ struct LossShared {
 struct LossBatch {
   LossShared s;
   Problem prob[kMaxBatch];
+  XchgView xv;  // world <= 1: none.  Else the pair kernel adds every problem's sums over the ranks itself (xchg.cuh)
 };
 
 // Sample-side forms

@@ -37,11 +37,8 @@ namespace {
 #ifndef SRL_PAIR_MIN_BLOCKS
 #define SRL_PAIR_MIN_BLOCKS 8
 #endif
-#ifndef SRL_PAIR_LANES
-#define SRL_PAIR_LANES 2  // lanes per thread: 2 (64-bit policy accesses, software-pipelined) or 1 (no pipeline, more warps)
-#endif
 constexpr int kPairThreads = SRL_PAIR_THREADS;
-constexpr int kPairLanes = SRL_PAIR_LANES * kPairThreads;  // lanes per column tile
+constexpr int kPairLanes = 2 * kPairThreads;  // lanes per column tile
 constexpr int kStatMax = 1024 / kPairThreads; // lanes per thread in the statistics prologue (n <= 1024)
 
 struct PairSched {
@@ -49,36 +46,9 @@ struct PairSched {
   int pairs;      // row pairs per column
   int col_tiles;  // column tiles per problem
   int cpp;        // units per problem = col_tiles * pairs
+  int zero;       // 0 at run time, unknown at compile time: see the scoreboard note in the kernel
 };
 
-#ifndef SRL_PAIR_ASYNC
-#define SRL_PAIR_ASYNC 0  // 1: the next steps' loads as LDGSTS copies into per-thread shared-memory slots (measured: no better)
-#endif
-#ifndef SRL_CARVEOUT
-#define SRL_CARVEOUT 0  // 1: ask for the scan's shared-memory carve-out (A/B knob, profiles/r2_notes.md)
-#endif
-#if SRL_PAIR_ASYNC
-#ifndef SRL_PAIR_DEPTH
-#define SRL_PAIR_DEPTH 3
-#endif
-constexpr int kPairDepth = SRL_PAIR_DEPTH;  // steps resident in shared memory per thread: one computed, the others in flight
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
-               "l"(gmem_src)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
-               "l"(gmem_src)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-#elif SRL_PAIR_LANES == 2
 // Both rows' policy outputs of this thread's two lanes, and its two lanes' row pairs of the pack.
 struct Stage {
   float2 nl[2], vp[2], en[2];
@@ -95,7 +65,6 @@ __device__ __forceinline__ void ld_nc256(const float4* p, float (&v)[8]) {
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                : "l"(p));
 }
-#endif
 __device__ __forceinline__ void ld_nc256(const double* p, double (&v)[4]) {
   asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
@@ -104,7 +73,8 @@ __device__ __forceinline__ void ld_nc256(const double* p, double (&v)[4]) {
 // over ALL lanes of the problem by every CTA that works on it: thread i adds lanes i, i + THREADS, ... in that order, then
 // the warp tree, then the warps in order -- the same order in every CTA, so they normalise with bit-identical statistics.
 __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__ lane_aos, const int32_t* __restrict__ idx,
-                                                      int n, double adv_eps, double& mask_sum, double (*s_part)[8]) {
+                                                      int n, double adv_eps, double& mask_sum, double (*s_part)[8],
+                                                      const XchgView& xv, int slot, bool sender) {
   // kStatBatch gathers in flight per thread at a time (all index loads first): two dependent rounds for 1024 lanes on
   // 64 threads instead of sixteen, without holding 16 x 4 doubles in registers
   constexpr int kStatBatch = kStatMax < 8 ? kStatMax : 8;
@@ -152,7 +122,15 @@ __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__
     s1 += s_part[1][w];
     s2 += s_part[2][w];
   }
-  mask_sum = cnt;
+  mask_sum = cnt;  // the masked means of the loss stay rank-local
+  if (xv.world > 1) {
+    // several ranks: the normalisation statistics are the sums over ALL ranks' minibatches (utils.py:58-61).  The problem's
+    // first CTA sends this rank's three sums to every rank's mailbox; every CTA collects and adds them in rank order.
+    __shared__ unsigned int s_words[6 * kMaxWorld];
+    double x[3] = {cnt, s1, s2};
+    xchg_problem_sums(xv, slot, sender, x, s_words);
+    return uniforms_from(x[0], x[1], x[2], cnt, nullptr, adv_eps);
+  }
   return uniforms_from(cnt, s1, s2, cnt, nullptr, adv_eps);
 }
 
@@ -161,7 +139,8 @@ __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__
 // epilogue held the whole CTA through three barriers, eight fences and the atomic's round trip).  The last CTA's warp 0
 // folds the problem's rows in row order (deterministic for a given launch shape).
 __device__ __forceinline__ void pair_reduce_and_finalize(const Problem& pr, const LossHyperDev& h, const Acc& acc,
-                                                         double mask_sum, int row, int n_rows, double (*sred)[8]) {
+                                                         double mask_sum, int row, int n_rows, double (*sred)[8],
+                                                         const XchgView& xv, unsigned int n_problems) {
   double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(pr.slot) + kPartialsOffset);
   double v[kNumSums] = {acc.pl, acc.vl, acc.en, acc.adv, acc.ratio, static_cast<double>(acc.clip), acc.vt, acc.ret};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -245,315 +224,13 @@ __device__ __forceinline__ void pair_reduce_and_finalize(const Problem& pr, cons
       pr.out_f32[3] = static_cast<float>(el);
     }
     pr.slot->ticket = 0u;  // ready for the next launch on this slot
+    // every CTA of this problem is past the exchange (it has taken the ticket): the last PROBLEM to get here ends the
+    // launch's exchange round (n_problems atomics per launch instead of one per CTA)
+    if (xv.world > 1) xchg_launch_done(xv, n_problems);
   }
 }
 
-#if SRL_PAIR_ASYNC
-// grid = (slices, problems): CTA (x, k) owns units [x * cpp / slices, (x + 1) * cpp / slices) of problem k, a unit being one
-// row pair of one column tile, numbered column tile by column tile.  A CTA never leaves its problem: the statistics
-// prologue and the reduction epilogue (a few microseconds of dependent latency each) are paid exactly once per CTA, and
-// a problem's partial rows are its `slices` CTAs.
-//
-// The loads of the next kPairDepth - 1 steps are in flight while a step is computed, as asynchronous global -> shared
-// copies into per-thread slots (LDGSTS; a thread only ever reads what it copied itself, so cp.async.wait_group is the
-// only synchronisation).  Why not registers: the register version of this pipeline (first two versions of this file) was
-// defeated by the hardware scoreboards -- ptxas put every LDG of the loop on the same scoreboard (SB5; decoded from the
-// SASS control words), so the first use of step i's data also waited for the loads of step i+1 issued just before it:
-// 20 % of all warp samples sat on that one instruction, with a warm L2 (profiles/r2_notes.md).  LDGSTS completion is
-// counted per commit group, not per scoreboard.
-template <class CFG>
-__global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pair_kernel(const __grid_constant__ LossBatch b,
-                                                                                          const PairSched sc) {
-  __shared__ double s_part[8][8];
-  extern __shared__ __align__(16) unsigned char ring_raw[];
-  float4* pk_ring = reinterpret_cast<float4*>(ring_raw);                                        // [depth][4][threads]
-  float2* pol_ring = reinterpret_cast<float2*>(ring_raw + kPairDepth * 4 * kPairThreads * 16);  // [depth][6][threads]
-  const LossShared& s = b.s;
-  const LossHyperDev& h = s.h;
-  const Problem& pr = b.prob[blockIdx.y];
-  const int n = s.n, T = s.T, row_lo = s.row_lo, tid = threadIdx.x;
-  const long long N2 = 2 * s.ld_smp;  // float4 items per row pair of the pack
-  const int u_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * sc.cpp / gridDim.x);
-  const int u_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * sc.cpp / gridDim.x);
-  const int n_steps = u_end - u_begin;
-
-  // the two cursors over the CTA's run of units: where the copies are issued, where the arithmetic is
-  int ict = u_begin / sc.pairs, ip = u_begin - ict * sc.pairs;
-  int cct = ict, cp = ip;
-
-  // policy-side copies of row pair p of column tile ct into stage st: 6 x 8 bytes (2 lanes x {new_logp, v_pred, entropy} x
-  // 2 rows); rows outside [0, T) are skipped (their slots are never read)
-  auto issue_policy = [&](int st, int ct, int p) {
-    const int j = (ct * kPairThreads + tid) * 2;
-    if (j >= n) return;
-    const int r0 = 2 * (sc.pair_lo + p) - row_lo;  // loss row of the pair's first row (-1: before the first loss row)
-    const long long o = static_cast<long long>(r0) * s.ld_pol + j;
-    float2* dst = pol_ring + (st * 6) * kPairThreads + tid;
-    if (r0 >= 0) {
-      cp_async8(dst, pr.new_logp + o);
-      cp_async8(dst + kPairThreads, pr.v_pred + o);
-      cp_async8(dst + 2 * kPairThreads, pr.entropy + o);
-    }
-    if (r0 + 1 < T) {
-      cp_async8(dst + 3 * kPairThreads, pr.new_logp + o + s.ld_pol);
-      cp_async8(dst + 4 * kPairThreads, pr.v_pred + o + s.ld_pol);
-      cp_async8(dst + 5 * kPairThreads, pr.entropy + o + s.ld_pol);
-    }
-  };
-  // the two lanes' row pairs of the pack: 2 x 32 bytes as 4 x 16-byte copies {lane 0: row 0, row 1; lane 1: row 0, row 1}
-  auto issue_pack = [&](int st, int p, const int (&c)[2], bool active) {
-    if (!active) return;
-    const float4* row = s.pack + static_cast<long long>(sc.pair_lo + p) * N2;
-    float4* dst = pk_ring + (st * 4) * kPairThreads + tid;
-    cp_async16(dst, row + 2 * c[0]);
-    cp_async16(dst + kPairThreads, row + 2 * c[0] + 1);
-    cp_async16(dst + 2 * kPairThreads, row + 2 * c[1]);
-    cp_async16(dst + 3 * kPairThreads, row + 2 * c[1] + 1);
-  };
-  auto advance = [&](int& ct, int& p) {
-    if (++p == sc.pairs) p = 0, ++ct;
-  };
-
-  // Launched programmatically behind the scan, this CTA may be resident while the scan still runs: the policy outputs do
-  // not depend on it, so the policy-side copies of the first steps are in flight before the wait.
-  {
-    int ct = ict, p = ip;
-    for (int k = 0; k < kPairDepth - 1 && k < n_steps; ++k, advance(ct, p)) issue_policy(k, ct, p);
-  }
-  pdl_wait();
-
-  // gather indices of the issue cursor's column tile (reloaded when the cursor enters the next column tile)
-  int c[2];
-  int c_ct = -1;
-  bool c_active = false;
-  auto load_idx = [&](int ct) {
-    const int j = (ct * kPairThreads + tid) * 2;
-    c_active = j < n;
-    c[0] = j, c[1] = j + 1;
-    if (pr.lane_idx && c_active) {
-      const int2 q = __ldg(reinterpret_cast<const int2*>(pr.lane_idx + j));
-      c[0] = q.x, c[1] = q.y;
-    }
-    c_ct = ct;
-  };
-  for (int k = 0; k < kPairDepth - 1; ++k) {  // fill: the pack halves of the steps whose policy halves are already under way
-    if (k < n_steps) {
-      if (ict != c_ct) load_idx(ict);
-      issue_pack(k, ip, c, c_active);
-      advance(ict, ip);
-    }
-    cp_async_commit();
-  }
-
-  // minibatch statistics, once per CTA, with the first steps' copies in flight underneath
-  double mask_sum = 0.0;
-  Uniforms uf;
-  if (s.lane_aos != nullptr)
-    uf = self_uniforms_aos(s.lane_aos, pr.lane_idx, n, h.adv_eps, mask_sum, s_part);
-  else
-    uf = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
-
-  Acc acc;
-  RowSums rs;
-  int pending = 0;
-  int st_c = 0, st_i = (kPairDepth - 1) % kPairDepth;  // stage consumed / stage filled this iteration
-  for (int i = 0; i < n_steps; ++i) {
-    if (i + kPairDepth - 1 < n_steps) {  // step i + depth - 1 into the stage drained in the iteration before
-      if (ict != c_ct) load_idx(ict);
-      issue_policy(st_i, ict, ip);
-      issue_pack(st_i, ip, c, c_active);
-      advance(ict, ip);
-    }
-    cp_async_commit();  // one group per iteration, issued or not, so wait_group counts steps
-    cp_async_wait<kPairDepth - 1>();  // step i has landed
-    const int j = (cct * kPairThreads + tid) * 2;
-    if (j < n) {
-      const float4* pk = pk_ring + (st_c * 4) * kPairThreads + tid;
-      const float2* pl = pol_ring + (st_c * 6) * kPairThreads + tid;
-      const int r0 = 2 * (sc.pair_lo + cp) - row_lo;
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {  // both rows of the pair, both lanes; out-of-range rows produce nothing
-        const int r = r0 + rr;
-        if (r < 0 || r >= T) continue;
-        const float2 nl = pl[(3 * rr) * kPairThreads], vp = pl[(3 * rr + 1) * kPairThreads],
-                     en = pl[(3 * rr + 2) * kPairThreads];
-        const float4 k0 = pk[rr * kPairThreads], k1 = pk[(2 + rr) * kPairThreads];
-        float glp[2], gv[2], ge[2];
-        // K2 stores NaN in the advantage slot of masked transitions
-        element<CFG>(h, uf, nl.x, vp.x, en.x, k0.x, k0.y, k0.z, k0.w, k0.w == k0.w, glp[0], gv[0], ge[0], rs);
-        element<CFG>(h, uf, nl.y, vp.y, en.y, k1.x, k1.y, k1.z, k1.w, k1.w == k1.w, glp[1], gv[1], ge[1], rs);
-        const long long o = static_cast<long long>(r) * s.ld_grad + j;
-        stg_stream(reinterpret_cast<float2*>(pr.g_logp + o), make_float2(glp[0], glp[1]));
-        stg_stream(reinterpret_cast<float2*>(pr.g_value + o), make_float2(gv[0], gv[1]));
-        stg_stream(reinterpret_cast<float2*>(pr.g_entropy + o), make_float2(ge[0], ge[1]));
-      }
-      if (++pending == kFlushRows) {  // fp32 partial sums of at most kFlushRows * 4 terms, then float64
-        acc.add(rs);
-        rs = RowSums();
-        pending = 0;
-      }
-    }
-    advance(cct, cp);
-    st_c = (st_c + 1 == kPairDepth) ? 0 : st_c + 1;
-    st_i = (st_i + 1 == kPairDepth) ? 0 : st_i + 1;
-  }
-  cp_async_wait<0>();
-  acc.add(rs);
-  pair_reduce_and_finalize(pr, h, acc, mask_sum, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), s_part);
-}
-
-constexpr size_t kPairSmem = static_cast<size_t>(kPairDepth) * kPairThreads * (4 * 16 + 6 * 8);
-
-template <class CFG>
-int launch_pair(LossBatch& b, int n_problems, cudaStream_t st) {
-  const LossShared& s = b.s;
-  auto kern = ppo_loss_pair_kernel<CFG>;
-  static int resident[64] = {};
-  int dev = 0;
-  SRL_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) dev = 0;
-  if (resident[dev] == 0) {
-    if (kPairSmem > 48 * 1024)
-      SRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPairSmem)));
-    // the scan that runs ahead of this kernel takes most of an SM's shared memory: ask for the same carve-out, so that
-    // this kernel's CTAs can become resident beside it (programmatic launch) without the SM being reconfigured first
-#if SRL_CARVEOUT
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-#endif
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kPairThreads, kPairSmem) != cudaSuccess || nb < 1) nb = 1;
-    resident[dev] = nb;
-  }
-  PairSched sc;
-  sc.pair_lo = s.row_lo >> 1;
-  sc.pairs = ((s.row_lo + s.T - 1) >> 1) - sc.pair_lo + 1;
-  sc.col_tiles = (s.n + kPairLanes - 1) / kPairLanes;
-  sc.cpp = sc.col_tiles * sc.pairs;
-  // slices per problem: the whole grid resident at once (one wave), every CTA inside ONE problem
-  long long slices = static_cast<long long>(sm_count()) * resident[dev] / n_problems;
-  if (slices > sc.cpp) slices = sc.cpp;
-  if (slices > kMaxGrid) slices = kMaxGrid;  // one partial row per CTA in the workspace slot
-  if (slices < 1) slices = 1;
-  SRL_CUDA(launch_pdl(kern, dim3(static_cast<unsigned>(slices), static_cast<unsigned>(n_problems)), dim3(kPairThreads),
-                      kPairSmem, st, b, sc));
-  return SRL_OK;
-}
-
-#elif SRL_PAIR_LANES == 1
-// One lane x one row pair per thread and step, no software pipeline: the thread's state is small enough for 8 warps per
-// scheduler, which hide the load and arithmetic latencies the two-lane kernel's four warps per scheduler cannot.
-__device__ __forceinline__ void ld_nc256(const float4* p, float (&v)[8]) {
-  asm("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-      : "l"(p));
-}
-
-template <class CFG>
-__global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pair_kernel(const __grid_constant__ LossBatch b,
-                                                                                          const PairSched sc) {
-  __shared__ double s_part[8][8];
-  const LossShared& s = b.s;
-  const LossHyperDev& h = s.h;
-  const Problem& pr = b.prob[blockIdx.y];
-  const int n = s.n, T = s.T, row_lo = s.row_lo;
-  const long long N2 = 2 * s.ld_smp;  // float4 items per row pair of the pack
-  const int u_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * sc.cpp / gridDim.x);
-  const int u_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * sc.cpp / gridDim.x);
-  int ct = u_begin / sc.pairs;
-  int pi = u_begin - ct * sc.pairs;
-  pdl_wait();
-
-  Acc acc;
-  RowSums rs;
-  int pending = 0;
-  double mask_sum = 0.0;
-  Uniforms uf;
-  bool have_u = false;
-  for (int u = u_begin; u < u_end;) {  // the column segments of this CTA's range
-    const int j = ct * kPairThreads + threadIdx.x;
-    const bool active = j < n;
-    const int p_end = min(sc.pairs, pi + (u_end - u));
-    int c = j;
-    if (pr.lane_idx && active) c = __ldg(pr.lane_idx + j);
-    if (!have_u) {
-      if (s.lane_aos != nullptr)
-        uf = self_uniforms_aos(s.lane_aos, pr.lane_idx, n, h.adv_eps, mask_sum, s_part);
-      else
-        uf = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
-      have_u = true;
-    }
-    if (active) {
-      for (int p = pi; p < p_end; ++p) {
-        const int r0 = 2 * (sc.pair_lo + p) - row_lo;  // loss row of the pair's first row (-1: before the first loss row)
-        const bool ok0 = r0 >= 0, ok1 = r0 + 1 < T;
-        const long long o = static_cast<long long>(r0) * s.ld_pol + j;
-        float pk[8];
-        ld_nc256(s.pack + static_cast<long long>(sc.pair_lo + p) * N2 + 2 * c, pk);
-        float nl[2] = {0.f, 0.f}, vp[2] = {0.f, 0.f}, en[2] = {0.f, 0.f};
-        if (ok0) nl[0] = ldg_stream(pr.new_logp + o), vp[0] = ldg_stream(pr.v_pred + o), en[0] = ldg_stream(pr.entropy + o);
-        if (ok1)
-          nl[1] = ldg_stream(pr.new_logp + o + s.ld_pol), vp[1] = ldg_stream(pr.v_pred + o + s.ld_pol),
-          en[1] = ldg_stream(pr.entropy + o + s.ld_pol);
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          if (rr == 0 ? !ok0 : !ok1) continue;
-          float glp, gv, ge;
-          const float ad = pk[4 * rr + 3];
-          element<CFG>(h, uf, nl[rr], vp[rr], en[rr], pk[4 * rr], pk[4 * rr + 1], pk[4 * rr + 2], ad, ad == ad, glp, gv, ge, rs);
-          const long long og = static_cast<long long>(r0 + rr) * s.ld_grad + j;
-          stg_stream(pr.g_logp + og, glp);
-          stg_stream(pr.g_value + og, gv);
-          stg_stream(pr.g_entropy + og, ge);
-        }
-        if (++pending == 2 * kFlushRows) {  // fp32 partial sums of at most kFlushRows * 4 terms, then float64
-          acc.add(rs);
-          rs = RowSums();
-          pending = 0;
-        }
-      }
-    }
-    u += p_end - pi;
-    pi = 0;
-    ++ct;
-  }
-  acc.add(rs);
-  pair_reduce_and_finalize(pr, h, acc, mask_sum, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), s_part);
-}
-
-template <class CFG>
-int launch_pair(LossBatch& b, int n_problems, cudaStream_t st) {
-  const LossShared& s = b.s;
-  auto kern = ppo_loss_pair_kernel<CFG>;
-  static int resident[64] = {};
-  int dev = 0;
-  SRL_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) dev = 0;
-  if (resident[dev] == 0) {
-#if SRL_CARVEOUT
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-#endif
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kPairThreads, 0) != cudaSuccess || nb < 1) nb = 1;
-    resident[dev] = nb;
-  }
-  PairSched sc;
-  sc.pair_lo = s.row_lo >> 1;
-  sc.pairs = ((s.row_lo + s.T - 1) >> 1) - sc.pair_lo + 1;
-  sc.col_tiles = (s.n + kPairLanes - 1) / kPairLanes;
-  sc.cpp = sc.col_tiles * sc.pairs;
-  // slices per problem: the whole grid resident at once (one wave), every CTA inside ONE problem
-  long long slices = static_cast<long long>(sm_count()) * resident[dev] / n_problems;
-  if (slices > sc.cpp) slices = sc.cpp;
-  if (slices > kMaxGrid) slices = kMaxGrid;  // one partial row per CTA in the workspace slot
-  if (slices < 1) slices = 1;
-  SRL_CUDA(launch_pdl(kern, dim3(static_cast<unsigned>(slices), static_cast<unsigned>(n_problems)), dim3(kPairThreads), 0, st,
-                      b, sc));
-  return SRL_OK;
-}
-
-
-#else
-// grid = (slices, problems): CTA (x, k) owns units [x * cpp / slices, (x + 1) * cpp / slices) of problem k, a unit being one
+// grid = (problems, slices): CTA (k, x) owns units [x * cpp / slices, (x + 1) * cpp / slices) of problem k, a unit being one
 // row pair of one column tile, numbered column tile by column tile.  A CTA never leaves its problem: the statistics
 // prologue and the reduction epilogue (a few microseconds of dependent latency each) are paid exactly once per CTA, and
 // a problem's partial rows are its `slices` CTAs.
@@ -563,15 +240,25 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
   __shared__ double s_part[8][8];
   const LossShared& s = b.s;
   const LossHyperDev& h = s.h;
-  const Problem& pr = b.prob[blockIdx.y];
+  const Problem& pr = b.prob[blockIdx.x];
   const int n = s.n, T = s.T, row_lo = s.row_lo;
   const long long N2 = 2 * s.ld_smp;  // float4 items per row pair of the pack
-  const int u_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * sc.cpp / gridDim.x);
-  const int u_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * sc.cpp / gridDim.x);
+  const int u_begin = static_cast<int>(static_cast<long long>(blockIdx.y) * sc.cpp / gridDim.y);
+  const int u_end = static_cast<int>(static_cast<long long>(blockIdx.y + 1) * sc.cpp / gridDim.y);
   int ct = u_begin / sc.pairs;
   int pi = u_begin - ct * sc.pairs;
 
-  Stage sA, sB;
+  Stage sA = {}, sB = {};
+  // Scoreboards.  ptxas put every load of this loop on ONE hardware scoreboard (SB5; decoded from the SASS control words),
+  // so the first use of step i's data ALSO waited for the loads of step i+1 issued just before it -- 20 % of all warp
+  // samples sat on that one instruction (ncu, warm L2) and the software pipeline hid nothing.  The fix is an ordering the
+  // scheduler cannot undo: the addresses of step i+1's loads depend on a value derived from step i's data (`& sc.zero`, 0
+  // at run time), so the wait for step i happens BEFORE step i+1 is issued, when nothing younger is outstanding.
+  auto landed = [&](const Stage& st) -> int {
+    return (__float_as_int(st.nl[0].x) | __float_as_int(st.vp[0].x) | __float_as_int(st.en[0].x) | __float_as_int(st.nl[1].x) |
+            __float_as_int(st.vp[1].x) | __float_as_int(st.en[1].x) | __float_as_int(st.pk[0][0]) |
+            __float_as_int(st.pk[1][0])) & sc.zero;
+  };
   // policy-side loads of row pair `p` (index within the column), lanes j, j + 1
   auto issue_policy = [&](Stage& st, int p, int j) {
     const int r0 = 2 * (sc.pair_lo + p) - row_lo;  // loss row of the pair's first row (-1: before the first loss row)
@@ -624,7 +311,8 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
     first = false;
     if (!have_u) {  // once per CTA; the first step's loads are in flight underneath
       if (s.lane_aos != nullptr)
-        uf = self_uniforms_aos(s.lane_aos, pr.lane_idx, n, h.adv_eps, mask_sum, s_part);
+        uf = self_uniforms_aos(s.lane_aos, pr.lane_idx, n, h.adv_eps, mask_sum, s_part, b.xv, static_cast<int>(blockIdx.x),
+                               blockIdx.y == 0);
       else
         uf = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
       have_u = true;
@@ -660,14 +348,18 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
       int p = pi;
       while (true) {
         if (p + 1 < p_end) {
-          issue_policy(sB, p + 1, j);
-          issue_pack(sB, p + 1, c);
+          const int dep = landed(sA);
+          const int cd[2] = {c[0] + dep, c[1] + dep};
+          issue_policy(sB, p + 1, j + dep);
+          issue_pack(sB, p + 1, cd);
         }
         compute(sA, p);
         if (++p >= p_end) break;
         if (p + 1 < p_end) {
-          issue_policy(sA, p + 1, j);
-          issue_pack(sA, p + 1, c);
+          const int dep = landed(sB);
+          const int cd[2] = {c[0] + dep, c[1] + dep};
+          issue_policy(sA, p + 1, j + dep);
+          issue_pack(sA, p + 1, cd);
         }
         compute(sB, p);
         if (++p >= p_end) break;
@@ -678,7 +370,8 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
     ++ct;
   }
   acc.add(rs);
-  pair_reduce_and_finalize(pr, h, acc, mask_sum, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), s_part);
+  pair_reduce_and_finalize(pr, h, acc, mask_sum, static_cast<int>(blockIdx.y), static_cast<int>(gridDim.y), s_part, b.xv,
+                           gridDim.x);
 }
 
 template <class CFG>
@@ -690,9 +383,6 @@ int launch_pair(LossBatch& b, int n_problems, cudaStream_t st) {
   SRL_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) dev = 0;
   if (resident[dev] == 0) {
-#if SRL_CARVEOUT
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-#endif
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kPairThreads, 0) != cudaSuccess || nb < 1) nb = 1;
     resident[dev] = nb;
@@ -702,17 +392,20 @@ int launch_pair(LossBatch& b, int n_problems, cudaStream_t st) {
   sc.pairs = ((s.row_lo + s.T - 1) >> 1) - sc.pair_lo + 1;
   sc.col_tiles = (s.n + kPairLanes - 1) / kPairLanes;
   sc.cpp = sc.col_tiles * sc.pairs;
+  sc.zero = 0;
   // slices per problem: the whole grid resident at once (one wave), every CTA inside ONE problem
   long long slices = static_cast<long long>(sm_count()) * resident[dev] / n_problems;
   if (slices > sc.cpp) slices = sc.cpp;
   if (slices > kMaxGrid) slices = kMaxGrid;  // one partial row per CTA in the workspace slot
   if (slices < 1) slices = 1;
-  SRL_CUDA(launch_pdl(kern, dim3(static_cast<unsigned>(slices), static_cast<unsigned>(n_problems)), dim3(kPairThreads), 0, st,
+  // problems along x: the first n_problems CTAs to be dispatched are every problem's slice 0 -- the senders of the in-kernel
+  // exchange -- so they are resident (and sending) whatever else shares the machine; no CTA ever waits for a CTA that is
+  // not resident yet
+  SRL_CUDA(launch_pdl(kern, dim3(static_cast<unsigned>(n_problems), static_cast<unsigned>(slices)), dim3(kPairThreads), 0, st,
                       b, sc));
   return SRL_OK;
 }
 
-#endif
 }  // namespace
 
 bool loss_pair_eligible(const LossShared& s, bool aligned8) {

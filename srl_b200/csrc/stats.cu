@@ -221,13 +221,6 @@ int launch_group_stats(const char* fn, const double* lane_part, int N, const int
     ws.partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + ticket_bytes(rows));
   }
   pdl_forget();
-#ifdef SRL_CARVEOUT_ALL
-  static bool carve_set = false;
-  if (!carve_set) {  // see perm.cu: the kernels of a step share one carve-out
-    cudaFuncSetAttribute(group_stats_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    carve_set = true;
-  }
-#endif
   group_stats_kernel<<<dim3(max_chunks, rows), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(lane_part, N, idx, per,
                                                                                                  whole_first, out, ws, fx);
   SRL_CUDA(cudaGetLastError());

@@ -80,6 +80,7 @@ extern "C" int srl_xchg_create(int world, int rank, int capacity_doubles, srl_xc
   char* tail = static_cast<char*>(x->local_base) + mailbox_bytes(world, capacity_doubles);
   x->view.seq = reinterpret_cast<unsigned int*>(tail);
   x->view.status = reinterpret_cast<int*>(tail + 64);
+  x->view.done = reinterpret_cast<unsigned int*>(tail + 128);
   x->connected = (world == 1);
   *out = reinterpret_cast<srl_xchg*>(x);
   return SRL_OK;

@@ -91,6 +91,18 @@ class HotPath:
             except PeerExchangeUnavailable:
                 if stats_exchange == "p2p":
                     raise
+        # A second mailbox for the loss kernel's own exchange of each minibatch's three sums (ppo_loss_pair.cu): with it the
+        # multi-GPU step keeps the single-GPU critical path K2 -> K4 -- the statistics table (still exchanged, for PopArt-less
+        # reporting and the parity checks) moves to the side branch.  Collective, like the first one.
+        self.peer_loss = None
+        fusable = bool(fuse_stats) and not popart and batch_losses and minibatches > 1 and fuse_gather and use_pack and \
+            (self.N // minibatches) <= 1024 and (self.N // minibatches) % 2 == 0
+        if self.peer is not None and fusable:
+            from srl_b200.xchg import PeerExchange, PeerExchangeUnavailable
+            try:
+                self.peer_loss = PeerExchange(process_group, 4 * 32, self.device, timeout_s=exchange_timeout_s)
+            except PeerExchangeUnavailable:
+                self.peer_loss = None
         self.fuse_gather = fuse_gather
         self.graph_branches = max(1, int(graph_branches))
         self.batch_losses = bool(batch_losses)
@@ -101,9 +113,9 @@ class HotPath:
         # One GPU, no PopArt, minibatches of <= 1024 lanes: the batched loss kernel adds K2's per-lane sums over its own
         # minibatch (its indices are in registers anyway), so the statistics table is no longer on the critical path
         # K2 -> K4; it is still produced (the trainer reports done / truncated from its batch row), on a side branch.
-        self.fuse_stats = bool(fuse_stats) and process_group is None and not popart and self._immediate and \
-            minibatches > 1 and fuse_gather and use_pack and self.n_mb <= 1024 and self.n_mb % 2 == 0
+        self.fuse_stats = fusable and self._immediate and (process_group is None or self.peer_loss is not None)
         self._stats_pending = False
+        self._lazy_table, self._table_valid = False, False
         self.step_count = 0
 
         dev, N = self.device, self.N
@@ -221,24 +233,32 @@ class HotPath:
                          ret=self.ret, lane_part=self.lane_part, **kw)
         if fork_perm:
             main.wait_stream(self._perm_stream)
-        side = self.fuse_stats and not cached
-        if side:  # off the critical path: joined by _join_stats() after the loss launches
-            if self._perm_stream is None:
-                self._perm_stream = torch.cuda.Stream(device=self.device)
-            self._perm_stream.wait_stream(main)
+        # The statistics table (row 0 = batch, row 1 + e*M + j = minibatch (e, j); summed over the ranks).  When the batched
+        # loss kernel adds its minibatches' sums itself (fuse_stats) nothing on the step's critical path reads the table: it
+        # is then produced LAZILY (ensure_table(): the per-minibatch launches of the trainer, the reports, the parity checks).
+        # Round 1 put it on a side stream instead; but the loss kernel's one-wave grid takes every CTA slot of the machine,
+        # so the side branch only ever ran AFTER the loss kernel and the step waited for it (N = 2: 44 us against 41.4 us with
+        # the table between K2 and K4, profiles/r2_notes.md).
+        self._lazy_table = self.fuse_stats and not cached
+        self._stats_pending = self._lazy_table  # the batched loss adds its own statistics from lane_aos
+        self._table_valid = False
+        if not self._lazy_table:
+            self.ensure_table()
+
+    def ensure_table(self) -> None:
+        """Produces local_stats / global_stats for the current sample if advantages() left them for later."""
+        if self._table_valid:
+            return
         # with the peer-memory exchange the table is sent from the kernel that produces it (fused), see stats.cu
         xk = dict(exchange=self.peer, global_out=self.global_stats) if (self.peer is not None and self.pg is not None) else {}
-        with torch.cuda.stream(self._perm_stream if side else main):
-            if self.minibatches > 1:
-                ops.group_stats(self.lane_part, idx=self.perm.view(-1), groups=self.epochs * self.minibatches,
-                                per=self.n_mb, out=self.local_stats, whole_first=True, workspace=self.stats_ws, **xk)
-            else:
-                ops.group_stats(self.lane_part, groups=1, per=self.N, out=self.local_stats[0:1], workspace=self.stats_ws,
-                                **xk)
-        self._stats_pending = side
-        if xk:
-            return
-        if self.pg is not None:
+        if self.minibatches > 1:
+            ops.group_stats(self.lane_part, idx=self.perm.view(-1), groups=self.epochs * self.minibatches,
+                            per=self.n_mb, out=self.local_stats, whole_first=True, workspace=self.stats_ws, **xk)
+        else:
+            ops.group_stats(self.lane_part, groups=1, per=self.N, out=self.local_stats[0:1], workspace=self.stats_ws,
+                            **xk)
+        self._table_valid = True
+        if not xk and self.pg is not None:
             self.exchange()
 
     def exchange(self) -> None:
@@ -250,15 +270,17 @@ class HotPath:
 
     def check_exchange(self) -> None:
         """Synchronises and raises when a rank never arrived at a statistics exchange (the table is NaN then)."""
-        if self.peer is not None:
-            self.peer.check_async()
+        peers = [p for p in (self.peer, self.peer_loss) if p is not None]
+        for p in peers:
+            p.check_async()
+        if peers:
             torch.cuda.current_stream().synchronize()
-            self.peer.raise_if_failed()
+        for p in peers:
+            p.raise_if_failed()
 
     def _join_stats(self) -> None:
-        if self._stats_pending:
-            torch.cuda.current_stream().wait_stream(self._perm_stream)
-            self._stats_pending = False
+        """Before anything reads the table (kept under its round-1 name for the callers)."""
+        self.ensure_table()
 
     def permute(self) -> None:
         """K5a: the environment(-block) permutations of every epoch of this step, one launch."""
@@ -325,7 +347,8 @@ class HotPath:
         if self.minibatches > 1 and self.pack is not None and self.pack_valid:
             own = self.lane_aos if (self.fuse_stats and self._stats_pending) else None
             ops.ppo_loss_batched(probs, None, None, None, None, None, self.hyper,
-                                 popart_mean_std=self.popart_mean_std(), pack=self.pack, pack_row_lo=lo, lane_aos=own)
+                                 popart_mean_std=self.popart_mean_std(), pack=self.pack, pack_row_lo=lo, lane_aos=own,
+                                 exchange=self.peer_loss if own is not None else None)
         else:
             ops.ppo_loss_batched(probs, lf["old_logp"][lo:hi], lf["value"][lo:hi], self.ret[lo:hi], self.adv[lo:hi],
                                  lf["on_reset"][lo + 1:hi + 1], self.hyper, popart_mean_std=self.popart_mean_std())
@@ -347,7 +370,6 @@ class HotPath:
                     self.loss_batch([(e, j) for j in range(self.minibatches)], pol)
             else:  # every (epoch, minibatch) is independent: one launch
                 self.loss_batch([(e, j) for e in range(self.epochs) for j in range(self.minibatches)], pol)
-            self._join_stats()
             return
         main = torch.cuda.current_stream()
         if branches > 1 and not hasattr(self, "_side"):
@@ -398,6 +420,7 @@ class HotPath:
             self._graph_a.replay()
             self.exchange()
             self._graph.replay()
+        self._table_valid = not self._lazy_table  # a replay does not run ensure_table()'s python side
         self.step_count += 1
 
     def run_trainer_order(self, pol, use_graph: bool = True) -> None:
@@ -495,7 +518,7 @@ class HotPath:
 
     def count_launches(self) -> int:
         """Kernels of this library launched by one step (the claim behind bench.py's gpu_launches)."""
-        n = 2  # gae_scan + group_stats
+        n = 1 if self.fuse_stats else 2  # gae_scan (+ group_stats unless the batched loss adds its own statistics)
         if self.minibatches > 1:
             n += 1  # all epochs' permutations
         if self._immediate:
@@ -546,6 +569,7 @@ class HotPath:
                 self._capture_host(pinned, pol_src, out_host)
                 self._host_graph_key = key
             self._host_graph.replay()
+            self._table_valid = not self._lazy_table
         else:
             self._host_pipeline(pinned, pol_src, out_host, 1)
         self.step_count += 1
@@ -621,7 +645,6 @@ class HotPath:
         if not self._immediate:
             self.finalize()
         out_host["out"].copy_(self.out, non_blocking=True)
-        self._join_stats()
         main.wait_stream(s_out)
 
     def _capture_host(self, pinned, pol_host, out_host) -> None:

@@ -469,7 +469,7 @@ def ppo_loss_fwd_bwd(new_logp, v_pred, entropy, old_logp, old_value, ret, adv, o
 
 def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on_reset_next, hyper: LossHyper,
                      popart_mean_std=None, pack: Optional[torch.Tensor] = None, pack_row_lo: int = 0,
-                     lane_aos: Optional[torch.Tensor] = None) -> None:
+                     lane_aos: Optional[torch.Tensor] = None, exchange=None) -> None:
     """Several minibatches of one shape in ONE launch (srl_ppo_loss_fwd_bwd_batched).
 
     Each problem is a dict with `new_logp`, `v_pred`, `entropy` (`[T, n]` float32), `norm_stats`, `local_stats`
@@ -479,6 +479,8 @@ def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on
     `pack` = the whole pair-interleaved pack K2 wrote (`new_pack`) with `pack_row_lo` = the sample row of loss row 0.
     `lane_aos` (K2's `[N, 4]` float64 table; pack form with lane indices, one GPU, no PopArt, even n <= 1024): the kernel
     adds the minibatch statistics itself and `norm_stats` / `local_stats` of the problems are not read (may be omitted).
+    `exchange` (a srl_b200.xchg.PeerExchange of its own, with `lane_aos`, several ranks): the kernel adds every problem's sums
+    over the ranks itself (NVLink peer memory) -- no statistics kernels between the scan and the loss.
     The gradient tensors must not alias the policy-side inputs."""
     if not problems:
         return
@@ -540,7 +542,7 @@ def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on
     hc = hyper.to_c()
     _lib.call("srl_ppo_loss_fwd_bwd_batched", arr, len(problems), n, n, _ptr(old_logp), _ptr(old_value), _ptr(ret),
               _ptr(adv), _ptr(on_reset_next), ld_smp, _ptr(pack), int(pack_row_lo), _ptr(lane_aos), T, n,
-              _ptr(popart_mean_std), ctypes.byref(hc), slot_bytes, _stream())
+              _ptr(popart_mean_std), ctypes.byref(hc), slot_bytes, None if exchange is None else exchange._h, _stream())
 
 
 def ppo_loss_from_logits(logits, action, head_sizes: Sequence[int], v_pred, old_logp, old_value, ret, adv, on_reset_next,
