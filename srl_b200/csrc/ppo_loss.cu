@@ -63,8 +63,12 @@ struct LogitsParams {
   int head_size[SRL_MAX_HEADS];
 };
 
+// CACHE_E: a second shared-memory row per transition keeps e_k = exp(z_k - max) of the log-sum-exp pass, so that the entropy
+// and the gradient passes need no further exponentials (1 expf per logit instead of 3: the kernel is bound by the special
+// function unit, not by memory -- 72 us for 90 MB at cfg2's shape before, profiles/r2_notes.md); used when both rows fit.
+template <bool CACHE_E>
 __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const __grid_constant__ LogitsParams q) {
-  extern __shared__ float srow[];  // [256][SK + 1]
+  extern __shared__ float srow[];  // [256][SK + 1] (+ [256][SK + 1] with CACHE_E)
   const LossShared& p = q.s;
   const Problem& pr = q.pr;
   const LossHyperDev& h = p.h;
@@ -72,6 +76,7 @@ __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const __grid_const
   const Uniforms u = load_uniforms(pr.norm_stats, pr.local_stats, p.popart, h.adv_eps, mask_sum);
   Acc acc;
   const int SK = q.SK, stride = SK + 1;
+  float* erow = srow + 256 * stride;
   const long long W = static_cast<long long>(p.T) * p.n;
   const long long tiles = (W + 255) / 256;
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -91,7 +96,8 @@ __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const __grid_const
       const int c = pr.lane_idx ? pr.lane_idx[j] : j;
       const long long os = t * p.ld_smp + c;
       float* z = srow + threadIdx.x * stride;
-      float lse[SRL_MAX_HEADS], hent[SRL_MAX_HEADS];
+      float* ez = erow + threadIdx.x * stride;
+      float lse[SRL_MAX_HEADS], hent[SRL_MAX_HEADS], rse[SRL_MAX_HEADS];
       int act[SRL_MAX_HEADS];
       float logp = 0.f, ent = 0.f;
       int off = 0;
@@ -102,15 +108,22 @@ __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const __grid_const
           float mx = -INFINITY;
           for (int k = 0; k < K; ++k) mx = fmaxf(mx, z[off + k]);
           float se = 0.f;
-          for (int k = 0; k < K; ++k) se += expf(z[off + k] - mx);
+          for (int k = 0; k < K; ++k) {
+            const float ek = expf(z[off + k] - mx);
+            if (CACHE_E) ez[off + k] = ek;
+            se += ek;
+          }
           const float l = mx + logf(se);
+          const float inv = 1.f / se;
           float hh = 0.f;
           for (int k = 0; k < K; ++k) {
             const float lp = fmaxf(z[off + k] - l, -FLT_MAX);  // Categorical.entropy clamps at finfo.min
-            hh -= expf(lp) * lp;
+            const float pk = CACHE_E ? ez[off + k] * inv : expf(lp);
+            hh -= pk * lp;
           }
           const int a = q.action[i * q.heads + hd];
           lse[hd] = l;
+          rse[hd] = inv;
           hent[hd] = hh;
           act[hd] = a;
           logp += z[off + a] - l;
@@ -136,7 +149,7 @@ __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const __grid_const
           const int K = q.head_size[hd];
           for (int k = 0; k < K; ++k) {
             const float lp = z[off + k] - lse[hd];
-            const float pk = expf(lp);
+            const float pk = CACHE_E ? ez[off + k] * rse[hd] : expf(lp);
             // d logp / d z_k = [k == a] - p_k ;  d H / d z_k = -p_k (lp_k + H)
             z[off + k] = g_lp * ((k == act[hd] ? 1.f : 0.f) - pk) - g_en * pk * (fmaxf(lp, -FLT_MAX) + hent[hd]);
           }
@@ -376,8 +389,10 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
                 "srl_ppo_loss_from_logits: head %d has no actions", i);
     sk += q.head_size[i];
   }
-  const size_t smem = static_cast<size_t>(256) * (sk + 1) * sizeof(float);
-  SRL_REQUIRE(smem <= 200 * 1024, SRL_ERR_UNSUPPORTED, "srl_ppo_loss_from_logits: sum K = %d too wide (max 199)", sk);
+  const size_t row_bytes = static_cast<size_t>(256) * (sk + 1) * sizeof(float);
+  SRL_REQUIRE(row_bytes <= 200 * 1024, SRL_ERR_UNSUPPORTED, "srl_ppo_loss_from_logits: sum K = %d too wide (max 199)", sk);
+  const bool cache_e = 2 * row_bytes <= 200 * 1024;  // both shared-memory rows fit: one exponential per logit
+  const size_t smem = cache_e ? 2 * row_bytes : row_bytes;
   q.heads = heads;
   q.SK = sk;
   q.logits = logits;
@@ -417,13 +432,19 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
   int dev = 0;
   SRL_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !opted_in[dev]) {
-    SRL_CUDA(cudaFuncSetAttribute(ppo_loss_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SRL_CUDA(cudaFuncSetAttribute(ppo_loss_logits_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SRL_CUDA(cudaFuncSetAttribute(ppo_loss_logits_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     opted_in[dev] = true;
   }
   const long long tiles = (static_cast<long long>(T) * n + 255) / 256;
   const long long cap = static_cast<long long>(sm_count()) * 8 < kMaxGrid ? static_cast<long long>(sm_count()) * 8 : kMaxGrid;
-  const int grid = static_cast<int>(tiles < cap ? tiles : cap);
-  ppo_loss_logits_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(q);
+  // every CTA the same number of tiles (2048 tiles on 1184 slots would leave most CTAs one tile and the rest two)
+  const long long per_cta = (tiles + cap - 1) / cap;
+  const int grid = static_cast<int>((tiles + per_cta - 1) / per_cta);
+  if (cache_e)
+    ppo_loss_logits_kernel<true><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(q);
+  else
+    ppo_loss_logits_kernel<false><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(q);
   SRL_CUDA(cudaGetLastError());
   return SRL_OK;
 }

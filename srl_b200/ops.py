@@ -723,6 +723,35 @@ def to_chunk(x: torch.Tensor, num_chunks: int) -> torch.Tensor:
     return out
 
 
+def gather_to_chunk(x: torch.Tensor, env_idx: torch.Tensor, num_chunks: int) -> torch.Tensor:
+    """`to_chunk(x[:, env_idx], num_chunks)` in ONE K1 launch: the minibatch gather (K5) and the RNN-chunk reshape
+    (modules.to_chunk, legacy/algorithm/modules/utils.py:164-180) fused -- `[T, B, *D]` and int32 `env_idx [n]` ->
+    `[T//C, n*C, *D]` with chunk c of the time axis in columns [c*n, (c+1)*n); bit-exact.  What an RNN policy does to
+    every leaf of a minibatch before its recurrent core (actor_critic_policy.py: `recursive_apply(sample, to_chunk)`): two
+    full copies of the minibatch become one."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise ValueError("gather_to_chunk: expected a CUDA tensor (srl_b200 has no CPU path)")
+    _check(env_idx, torch.int32, "env_idx")
+    T, B = x.shape[0], x.shape[1]
+    if T % num_chunks != 0:  # same error as the reference (utils.py:176-179)
+        raise IndexError(f"The first dimension(usually the step/time) {T} must be a multiple of "
+                         f"num_chunks {num_chunks}. This usually means the sample_steps(config:AgentSpec) "
+                         f"is not dividable by chunk_len(config:Policy).")
+    Tc, n = T // num_chunks, env_idx.numel()
+    x = x if x.is_contiguous() else x.contiguous()
+    out = torch.empty((Tc, n * num_chunks) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+    if x.numel() == 0 or n == 0:
+        return out
+    row_bytes = x[0, 0].numel() * x.element_size() if x.dim() > 2 else x.element_size()
+    # destination item (t', c*n + j) = source item (row c*Tc + t', slot env_idx[j]): with a time stride of one source row
+    # ([B] items) that is slot c*Tc*B + env_idx[j] of row t'
+    base = torch.arange(num_chunks, dtype=torch.int32, device=x.device).view(-1, 1) * (Tc * B)
+    idx = (base + env_idx.view(1, -1)).reshape(-1).contiguous()
+    d = LeafDesc(x.data_ptr(), out.data_ptr(), row_bytes, T * B, B * row_bytes, row_bytes)
+    _lib.call("srl_batch_gather", (LeafDesc * 1)(d), 1, _ptr(idx), Tc, num_chunks * n, _stream())
+    return out
+
+
 def back_to_trajectory(x: torch.Tensor, num_chunks: int) -> torch.Tensor:
     """modules.back_to_trajectory (utils.py:183-195), the inverse of to_chunk: `[T//C, B*C, *D]` -> `[T, B, *D]`."""
     if not isinstance(x, torch.Tensor) or not x.is_cuda:

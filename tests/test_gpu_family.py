@@ -190,3 +190,20 @@ def test_to_chunk_rejects_indivisible_time_axis(ops):
         ops.to_chunk(torch.zeros(10, 4, 1, device="cuda"), 3)
     with pytest.raises(ValueError):
         ops.to_chunk(torch.zeros(10, 4, 1), 2)
+
+
+@pytest.mark.parametrize("T,B,C,n,D", [(12, 8, 3, 4, (5,)), (16, 32, 4, 8, (4, 6, 6)), (8, 16, 8, 16, ()), (10, 6, 1, 3, (2,))])
+def test_gather_to_chunk_equals_gather_then_to_chunk(T, B, C, n, D):
+    """(f)4: the minibatch gather and the RNN-chunk reshape in ONE K1 launch == modules.to_chunk(x[:, env_idx], C)
+    (legacy/algorithm/modules/utils.py:164-180), bit for bit, for float32 and uint8 leaves."""
+    from srl_b200 import ops
+    g = torch.Generator().manual_seed(T * 100 + B)
+    idx = torch.randperm(B, generator=g)[:n].to(torch.int32)
+    for dtype in (torch.float32, torch.uint8):
+        x = (torch.rand((T, B) + D, generator=g) * 200).to(dtype)
+        want = torch.cat(torch.split(x[:, idx.long()], T // C, dim=0), dim=1)  # the reference's to_chunk on the gathered leaf
+        got = ops.gather_to_chunk(x.cuda(), idx.cuda(), C)
+        assert got.dtype == dtype and tuple(got.shape) == tuple(want.shape)
+        assert torch.equal(got.cpu(), want)
+    with pytest.raises(IndexError, match="must be a multiple of"):
+        ops.gather_to_chunk(torch.zeros(7, 4, 2).cuda(), idx[:2].cuda() % 4, 2)

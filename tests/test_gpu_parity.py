@@ -302,6 +302,79 @@ def test_loss_vs_oracle_config_shapes(ops, cfg_name, B):
     assert_grad_close(g_en, ref["g_entropy"], msum, what="g_entropy")
 
 
+@pytest.mark.parametrize("cfg_name", ["cfg2_atari_large", "cfg3_smac_27m", "cfg4_football_11v11", "cfg5_hns_scale"])
+def test_loss_full_size_lane_subset(ops, cfg_name):
+    """BASELINE configs 2-5 at FULL size (up to 10.5 M transitions in one launch): the loss scalars and stats against the
+    oracle's forward pass over the whole batch, the gradients against the oracle's autograd on a lane subset (every 997th
+    lane, all rows) normalised with the batch's global sums -- the same construction test_gae_full_size_property_linearity
+    uses for the scan.  Gradients are compared on the O(1) scale g * sum(mask), each side with its own sum(mask).
+    Transitions on a decision boundary of the clipped surrogate (ratio == 1 +- eps to the ulp: torch's CPU exp and the
+    device's expf differ by one ulp there and the gradient switches between all and nothing) are excused and counted."""
+    cfg = synth.CONFIGS[cfg_name]
+    s = synth.make_sample_scalars(cfg, seed=5)
+    pol = synth.make_policy_outputs(cfg, s, seed=6, epochs=1)
+    fl = {k: flat2(v) for k, v in s.items()}
+    L, N, T = cfg.L, cfg.N, cfg.T
+    lo, hi = cfg.burn_in_steps, cfg.L - cfg.bootstrap_steps
+    pa, ms = None, None
+    if cfg.popart:
+        pa = M.RunningMeanStdRef((1,), beta=0.999)
+        pa.update(torch.randn(64, 1, generator=torch.Generator().manual_seed(1)) * 2 + 1)
+        m_, s_ = pa.mean_std()
+        ms = np.array([m_.item(), s_.item()])
+    d = {k: dev(v) for k, v in fl.items()}
+    pm = None if ms is None else dev(ms)
+    adv, ret, part = ops.gae_scan(d["reward"], d["value"], d["done"], d["truncated"], d["on_reset"], cfg.gamma, cfg.lmbda,
+                                  row_lo=lo, row_hi=hi, popart_mean_std=pm)
+    stats = ops.group_stats(part, groups=1, per=N)[0]
+    hp_kw = dict(eps_clip=cfg.eps_clip, clip_value=cfg.clip_value, dual_clip=cfg.dual_clip, c_clip=cfg.c_clip,
+                 value_loss=cfg.value_loss, value_loss_weight=cfg.value_loss_weight,
+                 entropy_bonus_weight=cfg.entropy_bonus_weight,
+                 value_loss_config=({"delta": cfg.value_loss_delta} if cfg.value_loss == "huber" else None))
+    nl, vp, en = (flat2(pol[k][0]) for k in ("new_logp", "v_pred", "entropy"))
+    g_lp, g_v, g_en, out, _ = ops.ppo_loss_fwd_bwd(dev(nl), dev(vp), dev(en), d["old_logp"][lo:hi], d["value"][lo:hi], ret[lo:hi],
+                                                   adv[lo:hi], d["on_reset"][lo + 1:hi + 1], stats, ops.LossHyper(**hp_kw),
+                                                   popart_mean_std=pm)
+    torch.cuda.synchronize()
+    adv_h, ret_h, out = adv.cpu(), ret.cpu(), out.cpu().numpy()
+    t = {k: torch.from_numpy(v).float() for k, v in fl.items()}
+    mask = 1 - t["on_reset"][lo + 1:hi + 1]
+    # (1) the statistics table row against float64 numpy sums of the device's own adv
+    x = adv_h[lo:hi].double() * mask.double()
+    np.testing.assert_allclose(stats.cpu().numpy()[:3], [float(mask.sum()), float(x.sum()), float(x.square().sum())], rtol=1e-11)
+    # (2) loss scalars / stats: the oracle's forward over the WHOLE batch
+    un = lambda v: torch.from_numpy(v).unsqueeze(-1)
+    tk = lambda v: v.unsqueeze(-1)
+    ref = M.ppo_loss_ref(un(nl), tk(t["old_logp"][lo:hi]), un(vp), tk(t["value"][lo:hi]), tk(ret_h[lo:hi]), tk(adv_h[lo:hi]),
+                         un(en), tk(mask), M.LossHyper(**hp_kw), popart=pa, want_grads=False)
+    assert out[9] == float(mask.sum())
+    for slot, k in ((0, "loss"), (1, "policy_loss"), (2, "value_loss"), (3, "entropy_loss")):
+        assert_close_ref(out[slot], ref[k], what=f"{cfg_name} {k}")
+    for k, slot in STAT_SLOTS.items():
+        if k in ref["stats"]:
+            assert_close_ref(out[slot], ref["stats"][k], what=f"{cfg_name} {k}")
+    # (3) gradients: autograd of the oracle on a lane subset, normalised with the batch's global sums
+    sel = torch.arange(0, N, 997)
+    sub = lambda v: v.index_select(1, sel).unsqueeze(-1)
+    g = stats.cpu()
+    rs = M.ppo_loss_ref(sub(torch.from_numpy(nl)), sub(t["old_logp"][lo:hi]), sub(torch.from_numpy(vp)), sub(t["value"][lo:hi]),
+                        sub(ret_h[lo:hi]), sub(adv_h[lo:hi]), sub(torch.from_numpy(en)), sub(mask), M.LossHyper(**hp_kw),
+                        popart=pa, global_sums=(g[0].clone(), g[1].clone(), g[2].clone()))
+    m_full, m_sub = float(mask.sum()), float(mask.index_select(1, sel).sum())
+    ratio = (torch.from_numpy(nl).index_select(1, sel).double() - t["old_logp"][lo:hi].index_select(1, sel).double()).exp()
+    edge = ((ratio - (1 - cfg.eps_clip)).abs() <= 4e-7) | ((ratio - (1 + cfg.eps_clip)).abs() <= 4e-7)
+    excused = 0
+    for name, got in (("g_logp", g_lp), ("g_value", g_v), ("g_entropy", g_en)):
+        a = got.cpu().index_select(1, sel).double() * m_full
+        b = rs[name][..., 0].double() * m_sub
+        bad = ((a - b).abs() > 1e-5 * b.abs().clamp(min=1.0))
+        if name == "g_logp":
+            excused += int((bad & edge).sum())
+            bad = bad & ~edge
+        assert not bool(bad.any()), f"{cfg_name} {name}: {int(bad.sum())} of {bad.numel()} subset gradients outside 1e-5"
+    assert excused <= 2, f"{excused} boundary elements in a subset of {edge.numel()}: more than rounding can explain"
+
+
 def test_loss_minibatch_gather_on_load_equals_explicit_gather(ops):
     """lane_idx fused into the loads == running on x[:, idx] (numpy fancy indexing), bit for bit."""
     cfg = synth.PathConfig("mb", T=24, B=64, p_end=0.05, clip_value=True, value_loss="huber")
