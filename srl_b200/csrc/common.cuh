@@ -97,6 +97,40 @@ inline cudaError_t launch_pdl_scan(void (*kern)(KArgs...), dim3 grid, dim3 block
   return launch_maybe_pdl(pdl_take_perm(st), kern, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 
+// ---- debug timeline (profiles/microbench/timeline.py; library built with -DSRL_TIMELINE, never the product build) ------
+// One record per (kernel, CTA, slot): %globaltimer (ns, common to all SMs) and the SM's clock64.  The buffer pointer is a
+// per-translation-unit device symbol set through the TU's own exported setter; a null pointer switches the stamps off.
+#ifdef SRL_TIMELINE
+namespace tl {
+struct Rec {
+  unsigned long long gt, clk;
+};
+constexpr int kCtas = 2048, kSlots = 16;
+static __device__ Rec* g_buf;
+__device__ __forceinline__ void stamp(int kernel, int cta, int slot) {
+  Rec* b = g_buf;
+  if (b != nullptr && cta < kCtas) {
+    // reading %globaltimer costs ~250 cycles: only a CTA's entry stamp (slot 0) carries it; every other stamp is the SM's
+    // cycle counter alone (the host places it on the global axis through the entry stamp of the same CTA)
+    unsigned long long g = 0;
+    if (slot == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    Rec r;
+    r.gt = g;
+    r.clk = static_cast<unsigned long long>(clock64());
+    b[(static_cast<size_t>(kernel) * kCtas + cta) * kSlots + slot] = r;
+  }
+}
+}  // namespace tl
+#define SRL_TL(kernel, cta, slot) ::srl::tl::stamp(kernel, cta, slot)
+#define SRL_TL_SETTER(name)                                                                                  \
+  extern "C" int name(void* p) {                                                                             \
+    return cudaMemcpyToSymbol(::srl::tl::g_buf, &p, sizeof(p)) == cudaSuccess ? 0 : 1;                      \
+  }
+#else
+#define SRL_TL(kernel, cta, slot) ((void)0)
+#define SRL_TL_SETTER(name)
+#endif
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
   using SL = Slot<PACK>;
   extern __shared__ __align__(128) unsigned char smem[];
   Bars<kS>* bars = reinterpret_cast<Bars<kS>*>(smem + kS * SL::bytes);
+  if (threadIdx.x == 0) SRL_TL(1, blockIdx.x, 0);
   // the kernel behind this one on the stream (the loss) may become resident now; it waits for this grid's completion
   // before it reads anything written here
   pdl_launch_dependents();
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
     mbar_fence_init();
   }
   __syncthreads();
+  if (threadIdx.x == 0) SRL_TL(1, blockIdx.x, 1);
 
   if (warp == 0) {
     // ---- producer ----------------------------------------------------------------------------------------------
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
         tma_load_2d(slot + SL::on_reset, &q.maps.on_reset, col0, row0, &bars->tma_full[s]);
         if (PACK) tma_load_2d(slot + SL::old_logp, &q.maps.old_logp, col0, row0, &bars->tma_full[s]);
       }
+      SRL_TL(1, blockIdx.x, 2);
     }
   } else if (warp == 1) {
     // ---- scanner: A_t = delta_t + m_t * A_{t+1}, separate multiply and add as the reference's two torch ops (gae.py:92)
@@ -149,6 +152,7 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->scanned[s]);
     }
+    if (lane == 0) SRL_TL(1, blockIdx.x, 4);
   } else {
     // ---- workers ---------------------------------------------------------------------------------------------------
     const int w = warp - 2;
@@ -172,6 +176,7 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
       const int s = c % kS;
       unsigned char* slot = smem + s * SL::bytes;
       mbar_wait(&bars->tma_full[s], (c / kS) & 1);
+      if (c == 0 && w == 0 && lane == 0) SRL_TL(1, blockIdx.x, 3);
       const float* sv = reinterpret_cast<const float*>(slot + SL::value);
       const float* sr = reinterpret_cast<const float*>(slot + SL::reward);
       const uint8_t* sdn = slot + SL::done;
@@ -258,6 +263,7 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
       if (c + kAhead < n_chunks) pass1(c + kAhead);  // stay ahead of the scanner
       pass3(c);
     }
+    if (w == 0 && lane == 0) SRL_TL(1, blockIdx.x, 5);
     // per-lane statistics of this worker -> shared memory; the workers' tables are added in worker order below (fixed)
     if (p.lane_part != nullptr) {
       double* red = reinterpret_cast<double*>(smem + kS * SL::bytes + kStatsOff) + (w * 7) * 32;  // [kW][7][32] f64, own region
@@ -288,7 +294,11 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
   // Launched programmatically behind the permutation kernel, this grid never waited for it (it does not read the
   // permutation).  Waiting here, before the grid completes, makes "scan complete" imply "permutation complete and
   // visible" for the loss kernel, whose own griddepcontrol.wait only covers this grid.
-  if (threadIdx.x == 0) pdl_wait();
+  if (threadIdx.x == 0) {
+    SRL_TL(1, blockIdx.x, 6);
+    pdl_wait();
+    SRL_TL(1, blockIdx.x, 7);
+  }
 }
 
 template <bool PACK, int kW, int kS>
@@ -309,6 +319,9 @@ int launch_ws(const WsParams& q, cudaStream_t st) {
 }
 
 }  // namespace
+}  // namespace srl
+SRL_TL_SETTER(srl_tl_set_gae)
+namespace srl {
 
 bool gae_ws_eligible(const GaeParams& p) {
   // same TMA requirements as the one-warp kernel (16-byte aligned bases and row pitches); no V-trace

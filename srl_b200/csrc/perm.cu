@@ -54,6 +54,7 @@ namespace {
 __global__ void __launch_bounds__(256) philox_perm_kernel(uint32_t seed_lo, uint32_t seed_hi, uint32_t epoch0, int n_env,
                                                          int group, int bits, int32_t* __restrict__ out) {
   __shared__ PermKeys keys;
+  if (threadIdx.x == 0) SRL_TL(0, blockIdx.y * gridDim.x + blockIdx.x, 0);
   pdl_launch_dependents();  // the scan that follows on the stream does not read the permutation: let it start now
   const uint32_t epoch = epoch0 + blockIdx.y;  // one grid row per epoch
   out += static_cast<size_t>(blockIdx.y) * n_env * group;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) philox_perm_kernel(uint32_t seed_lo, uint
     while (x >= static_cast<uint32_t>(n_env)) x = feistel8(x, k);  // cycle-walk back into [0, n_env)
     for (int a = 0; a < group; ++a) out[static_cast<size_t>(e) * group + a] = static_cast<int32_t>(x) * group + a;
   }
+  if (threadIdx.x == 0) SRL_TL(0, blockIdx.y * gridDim.x + blockIdx.x, 1);
 }
 
 __global__ void philox_blocks_kernel(const uint32_t* __restrict__ counter, const uint32_t* __restrict__ key, int n,
@@ -93,6 +95,8 @@ __global__ void philox_blocks_kernel(const uint32_t* __restrict__ counter, const
 
 }  // namespace
 }  // namespace srl
+
+SRL_TL_SETTER(srl_tl_set_perm)
 
 extern "C" int srl_philox_perm(uint64_t seed, uint32_t epoch, int n_epochs, int n_env, int group, int32_t* out,
                                srl_stream_t stream) {

@@ -25,7 +25,11 @@ struct SlotHeader {
   unsigned int n_rows;  // CTAs that wrote a partial row
   double mask_sum;      // this rank's sum(mask) for the minibatch
   double wv, we;        // loss weights, so the finaliser needs nothing but the slot
-  double pad[4];
+  // pair kernel, immediate mode: the minibatch's normalisation sums {count, sum, sum of squares} (over all ranks), computed
+  // by ONE CTA of the problem and read by the others once `ready` is set; the last CTA clears `ready` with the ticket
+  double bc[3];
+  unsigned int ready;
+  unsigned int pad;
 };
 static_assert(sizeof(SlotHeader) == kPartialsOffset, "slot header must stay 64 bytes");
 
@@ -288,18 +292,20 @@ __device__ __forceinline__ void fold_rows_and_write(const double* __restrict__ p
     if (lane == 0) sred[k][0] = s;
   }
   __syncthreads();
+  if (threadIdx.x < kNumSums) sred[threadIdx.x][1] = sred[threadIdx.x][0] / M;  // the eight divisions side by side
+  __syncthreads();
   if (threadIdx.x == 0) {
-    const double pl = sred[0][0] / M, vl = sred[1][0] / M, el = -sred[2][0] / M;
+    const double pl = sred[0][1], vl = sred[1][1], el = -sred[2][1];
     const double loss = pl + wv * vl + we * el;
     o[SRL_OUT_LOSS] = loss;
     o[SRL_OUT_POLICY_LOSS] = pl;
     o[SRL_OUT_VALUE_LOSS] = vl;
     o[SRL_OUT_ENTROPY_LOSS] = el;
-    o[SRL_OUT_ADVANTAGE] = sred[3][0] / M;
-    o[SRL_OUT_IMPORTANCE_WEIGHT] = sred[4][0] / M;
-    o[SRL_OUT_CLIP_RATIO] = sred[5][0] / M;
-    o[SRL_OUT_VALUE_TARGETS] = sred[6][0] / M;
-    o[SRL_OUT_DENORM_VALUE] = sred[7][0] / M;
+    o[SRL_OUT_ADVANTAGE] = sred[3][1];
+    o[SRL_OUT_IMPORTANCE_WEIGHT] = sred[4][1];
+    o[SRL_OUT_CLIP_RATIO] = sred[5][1];
+    o[SRL_OUT_VALUE_TARGETS] = sred[6][1];
+    o[SRL_OUT_DENORM_VALUE] = sred[7][1];
     o[SRL_OUT_MASK_SUM] = M;
     for (int k = SRL_OUT_MASK_SUM + 1; k < SRL_LOSS_OUT_LEN; ++k) o[k] = 0.0;
     if (o32) {

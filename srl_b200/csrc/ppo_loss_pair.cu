@@ -69,12 +69,50 @@ __device__ __forceinline__ void ld_nc256(const double* p, double (&v)[4]) {
   asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
 
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // Minibatch statistics from K2's per-lane sums (lane_aos[lane] = {sum mask, sum adv*mask, sum (adv*mask)^2, 0}), added
-// over ALL lanes of the problem by every CTA that works on it: thread i adds lanes i, i + THREADS, ... in that order, then
-// the warp tree, then the warps in order -- the same order in every CTA, so they normalise with bit-identical statistics.
+// over ALL lanes of the problem: thread i adds lanes i, i + THREADS, ... in that order, then the warp tree, then the warps
+// in order.  `share` (immediate mode: the problem has a ticket, so somebody can clear the flag afterwards): only the
+// problem's first CTA (`sender`) does this -- and, with several ranks, the exchange -- and publishes the sums in the
+// workspace slot; the other CTAs of the problem wait for them.  (Every CTA adding them for itself -- the first version --
+// put 1184 x 512 gathers of the same 16 K lane items through L2 at the same moment: the device timeline showed 4.6 us between
+// griddepcontrol.wait and the first row, profiles/r2_notes.md.)  Without `share` every CTA adds them itself, in the same
+// order, so all CTAs of a problem normalise with bit-identical statistics either way.
 __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__ lane_aos, const int32_t* __restrict__ idx,
                                                       int n, double adv_eps, double& mask_sum, double (*s_part)[8],
-                                                      const XchgView& xv, int slot, bool sender) {
+                                                      const XchgView& xv, int slot, bool sender, SlotHeader* hdr, bool share) {
+  if (share && !sender) {
+    if (threadIdx.x == 0) {
+      // the sender is resident (dispatched first, launch_pair) and waits for nothing but -- with several ranks -- its peers,
+      // for at most spin_limit ticks, after which it publishes NaN: twice that bound is never reached unless the sender died
+      const long long limit = 2 * (xv.world > 1 ? xv.spin_limit : kDefaultSpinLimit);
+      const long long t0 = clock64();
+      bool ok = true;
+      while (ld_acquire_u32(&hdr->ready) == 0u) {
+        if (clock64() - t0 > limit) {
+          ok = false;
+          break;
+        }
+        __nanosleep(64);
+      }
+      const double nan = __longlong_as_double(0x7ff8000000000000ll);
+      s_part[0][0] = ok ? __ldcg(&hdr->bc[0]) : nan;  // no statistics: nothing but NaN leaves this launch
+      s_part[1][0] = ok ? __ldcg(&hdr->bc[1]) : nan;
+      s_part[2][0] = ok ? __ldcg(&hdr->bc[2]) : nan;
+      s_part[3][0] = ok ? __ldcg(&hdr->mask_sum) : nan;
+    }
+    __syncthreads();
+    mask_sum = s_part[3][0];
+    return uniforms_from(s_part[0][0], s_part[1][0], s_part[2][0], mask_sum, nullptr, adv_eps);
+  }
   // kStatBatch gathers in flight per thread at a time (all index loads first): two dependent rounds for 1024 lanes on
   // 64 threads instead of sixteen, without holding 16 x 4 doubles in registers
   constexpr int kStatBatch = kStatMax < 8 ? kStatMax : 8;
@@ -123,15 +161,22 @@ __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__
     s2 += s_part[2][w];
   }
   mask_sum = cnt;  // the masked means of the loss stay rank-local
+  double x[3] = {cnt, s1, s2};
   if (xv.world > 1) {
     // several ranks: the normalisation statistics are the sums over ALL ranks' minibatches (utils.py:58-61).  The problem's
-    // first CTA sends this rank's three sums to every rank's mailbox; every CTA collects and adds them in rank order.
+    // first CTA sends this rank's three sums to every rank's mailbox; it (share) or every CTA collects the ranks' sums from
+    // its own rank's mailbox and adds them in rank order.
     __shared__ unsigned int s_words[6 * kMaxWorld];
-    double x[3] = {cnt, s1, s2};
     xchg_problem_sums(xv, slot, sender, x, s_words);
-    return uniforms_from(x[0], x[1], x[2], cnt, nullptr, adv_eps);
   }
-  return uniforms_from(cnt, s1, s2, cnt, nullptr, adv_eps);
+  if (share && threadIdx.x == 0) {  // sender
+    hdr->bc[0] = x[0];
+    hdr->bc[1] = x[1];
+    hdr->bc[2] = x[2];
+    hdr->mask_sum = cnt;
+    st_release_u32(&hdr->ready, 1u);
+  }
+  return uniforms_from(x[0], x[1], x[2], cnt, nullptr, adv_eps);
 }
 
 // Block reduction of the eight masked sums for the pair kernel: every warp's tree, then warp 0 alone adds the warps, writes
@@ -189,32 +234,48 @@ __device__ __forceinline__ void pair_reduce_and_finalize(const Problem& pr, cons
     done = atomicAdd(&pr.slot->ticket, 1u);
   }
   done = __shfl_sync(0xffffffffu, done, 0);
+  if (lane == 0) SRL_TL(2, row * gridDim.x + blockIdx.x, 4);
   if (done != static_cast<unsigned int>(n_rows) - 1u) return;
   __threadfence();
   // fold: lane k (and k + 8, k + 16, k + 24) walks the rows of sum k in row order, then the four quarter sums are added
+  // (the kernel ends with this CTA: all row loads of a batch in flight at once, and the eight divisions side by side in
+  // lanes 0..7 instead of one after the other in lane 0 -- same operations, same order of additions, same bits)
   const int k = lane & 7, part = lane >> 3;
   double s = 0.0;
-  for (int r = part; r < n_rows; r += 4) s += __ldcg(partials + static_cast<size_t>(r) * kNumSums + k);
+  constexpr int kFoldBatch = 16;
+  for (int r0 = part; r0 < n_rows; r0 += 4 * kFoldBatch) {
+    double v[kFoldBatch];
+#pragma unroll
+    for (int q = 0; q < kFoldBatch; ++q) {
+      const int r = r0 + 4 * q;
+      v[q] = r < n_rows ? __ldcg(partials + static_cast<size_t>(r) * kNumSums + k) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < kFoldBatch; ++q)
+      if (r0 + 4 * q < n_rows) s += v[q];
+  }
   s += __shfl_down_sync(0xffffffffu, s, 16);
   s += __shfl_down_sync(0xffffffffu, s, 8);
-  // lanes 0..7 hold the eight sums; gather them into lane 0
+  // lanes 0..7 hold the eight sums: each divides its own, then lane 0 gathers the quotients
+  const double M = mask_sum;
+  const double quo = s / M;
   double t[kNumSums];
 #pragma unroll
-  for (int q = 0; q < kNumSums; ++q) t[q] = __shfl_sync(0xffffffffu, s, q);
+  for (int q = 0; q < kNumSums; ++q) t[q] = __shfl_sync(0xffffffffu, quo, q);
   if (lane == 0) {
-    const double M = mask_sum, wv = static_cast<double>(h.wv), we = static_cast<double>(h.we);
-    const double pl = t[0] / M, vl = t[1] / M, el = -t[2] / M;
+    const double wv = static_cast<double>(h.wv), we = static_cast<double>(h.we);
+    const double pl = t[0], vl = t[1], el = -t[2];
     const double loss = pl + wv * vl + we * el;
     double* o = pr.out;
     o[SRL_OUT_LOSS] = loss;
     o[SRL_OUT_POLICY_LOSS] = pl;
     o[SRL_OUT_VALUE_LOSS] = vl;
     o[SRL_OUT_ENTROPY_LOSS] = el;
-    o[SRL_OUT_ADVANTAGE] = t[3] / M;
-    o[SRL_OUT_IMPORTANCE_WEIGHT] = t[4] / M;
-    o[SRL_OUT_CLIP_RATIO] = t[5] / M;
-    o[SRL_OUT_VALUE_TARGETS] = t[6] / M;
-    o[SRL_OUT_DENORM_VALUE] = t[7] / M;
+    o[SRL_OUT_ADVANTAGE] = t[3];
+    o[SRL_OUT_IMPORTANCE_WEIGHT] = t[4];
+    o[SRL_OUT_CLIP_RATIO] = t[5];
+    o[SRL_OUT_VALUE_TARGETS] = t[6];
+    o[SRL_OUT_DENORM_VALUE] = t[7];
     o[SRL_OUT_MASK_SUM] = M;
     for (int q = SRL_OUT_MASK_SUM + 1; q < SRL_LOSS_OUT_LEN; ++q) o[q] = 0.0;
     if (pr.out_f32) {
@@ -224,9 +285,11 @@ __device__ __forceinline__ void pair_reduce_and_finalize(const Problem& pr, cons
       pr.out_f32[3] = static_cast<float>(el);
     }
     pr.slot->ticket = 0u;  // ready for the next launch on this slot
+    pr.slot->ready = 0u;   // (every CTA of the problem has read the published statistics: it has taken the ticket)
     // every CTA of this problem is past the exchange (it has taken the ticket): the last PROBLEM to get here ends the
     // launch's exchange round (n_problems atomics per launch instead of one per CTA)
     if (xv.world > 1) xchg_launch_done(xv, n_problems);
+    SRL_TL(2, row * gridDim.x + blockIdx.x, 5);
   }
 }
 
@@ -249,6 +312,8 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
   int pi = u_begin - ct * sc.pairs;
 
   Stage sA = {}, sB = {};
+  const int tl_cta = blockIdx.y * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0) SRL_TL(2, tl_cta, 0);
   // Scoreboards.  ptxas put every load of this loop on ONE hardware scoreboard (SB5; decoded from the SASS control words),
   // so the first use of step i's data ALSO waited for the loads of step i+1 issued just before it -- 20 % of all warp
   // samples sat on that one instruction (ncu, warm L2) and the software pipeline hid nothing.  The fix is an ordering the
@@ -287,6 +352,7 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
     if (j < n) issue_policy(sA, pi, j);
   }
   pdl_wait();
+  if (threadIdx.x == 0) SRL_TL(2, tl_cta, 1);
 
   Acc acc;
   RowSums rs;
@@ -312,10 +378,11 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
     if (!have_u) {  // once per CTA; the first step's loads are in flight underneath
       if (s.lane_aos != nullptr)
         uf = self_uniforms_aos(s.lane_aos, pr.lane_idx, n, h.adv_eps, mask_sum, s_part, b.xv, static_cast<int>(blockIdx.x),
-                               blockIdx.y == 0);
+                               blockIdx.y == 0, pr.slot, pr.out != nullptr && gridDim.y > 1);
       else
         uf = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
       have_u = true;
+      if (threadIdx.x == 0) SRL_TL(2, tl_cta, 2);
     }
     if (active) {
       // one step: both rows of the pair, both lanes; masked or out-of-range rows produce nothing
@@ -370,6 +437,7 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
     ++ct;
   }
   acc.add(rs);
+  if (threadIdx.x == 0) SRL_TL(2, tl_cta, 3);
   pair_reduce_and_finalize(pr, h, acc, mask_sum, static_cast<int>(blockIdx.y), static_cast<int>(gridDim.y), s_part, b.xv,
                            gridDim.x);
 }
@@ -407,6 +475,11 @@ int launch_pair(LossBatch& b, int n_problems, cudaStream_t st) {
 }
 
 }  // namespace
+}  // namespace loss
+}  // namespace srl
+SRL_TL_SETTER(srl_tl_set_loss)
+namespace srl {
+namespace loss {
 
 bool loss_pair_eligible(const LossShared& s, bool aligned8) {
   return s.pack != nullptr && aligned8 && (s.n % 2 == 0) && (s.ld_pol % 2 == 0) && (s.ld_grad % 2 == 0) &&
