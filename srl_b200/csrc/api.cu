@@ -34,22 +34,27 @@ bool pdl_enabled() {
 }
 
 namespace {
-thread_local cudaStream_t g_perm_stream = nullptr;
-thread_local bool g_perm_noted = false;
+thread_local cudaStream_t g_note_stream = nullptr;
+thread_local int g_note_kind = 0;  // the last library launch of this thread: 0 anything else, 1 permutation, 2 scan
+bool take(cudaStream_t st, int kind) {
+  const bool yes = g_note_kind == kind && g_note_stream == st;
+  g_note_kind = 0;
+  return yes;
+}
 }  // namespace
 
 void pdl_note_perm(cudaStream_t st) {
-  g_perm_stream = st;
-  g_perm_noted = true;
+  g_note_stream = st;
+  g_note_kind = 1;
 }
-
-bool pdl_take_perm(cudaStream_t st) {
-  const bool yes = g_perm_noted && g_perm_stream == st;
-  g_perm_noted = false;
-  return yes;
+bool pdl_take_perm(cudaStream_t st) { return take(st, 1); }
+void pdl_note_scan(cudaStream_t st) {
+  g_note_stream = st;
+  g_note_kind = 2;
 }
+bool pdl_take_scan(cudaStream_t st) { return take(st, 2); }
 
-void pdl_forget() { g_perm_noted = false; }
+void pdl_forget() { g_note_kind = 0; }
 
 int sm_count() {
   static int cached[64];

@@ -41,6 +41,12 @@ bool pdl_enabled();
 // launch behind a kernel that PRODUCES its inputs would read them without a visibility guarantee.
 void pdl_note_perm(cudaStream_t st);
 bool pdl_take_perm(cudaStream_t st);
+// ... and the other way round (the order HotPath uses: the scan is the long pole of the step and starts first): the
+// permutation kernel directly behind a scan starts beside it (it touches nothing the scan touches) and executes
+// griddepcontrol.wait at ITS end, so that "permutation complete" implies "scan complete and visible" for the loss kernel
+// behind it.  Only one of the two kernels of a pair is ever launched programmatically.
+void pdl_note_scan(cudaStream_t st);
+bool pdl_take_scan(cudaStream_t st);
 void pdl_forget();
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
@@ -94,7 +100,10 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl_scan(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                    Args&&... args) {
-  return launch_maybe_pdl(pdl_take_perm(st), kern, grid, block, smem, st, static_cast<Args&&>(args)...);
+  const bool programmatic = pdl_take_perm(st);
+  const cudaError_t e = launch_maybe_pdl(programmatic, kern, grid, block, smem, st, static_cast<Args&&>(args)...);
+  if (!programmatic) pdl_note_scan(st);  // a permutation launched next on this stream may start beside this scan
+  return e;
 }
 
 // ---- debug timeline (profiles/microbench/timeline.py; library built with -DSRL_TIMELINE, never the product build) ------

@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(256) philox_perm_kernel(uint32_t seed_lo, uint
     for (int a = 0; a < group; ++a) out[static_cast<size_t>(e) * group + a] = static_cast<int32_t>(x) * group + a;
   }
   if (threadIdx.x == 0) SRL_TL(0, blockIdx.y * gridDim.x + blockIdx.x, 1);
+  // launched programmatically behind a scan (common.cuh): this grid only completes once the scan has
+  if (threadIdx.x == 0) pdl_wait();
 }
 
 __global__ void philox_blocks_kernel(const uint32_t* __restrict__ counter, const uint32_t* __restrict__ key, int n,
@@ -114,10 +116,12 @@ extern "C" int srl_philox_perm(uint64_t seed, uint32_t epoch, int n_epochs, int 
   int grid = (n_env + threads - 1) / threads;
   const int cap = sm_count() * 8;
   if (grid > cap) grid = cap;
-  philox_perm_kernel<<<dim3(grid, n_epochs), threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<uint32_t>(seed & 0xffffffffull), static_cast<uint32_t>(seed >> 32), epoch, n_env, group, bits, out);
-  SRL_CUDA(cudaGetLastError());
-  pdl_note_perm(static_cast<cudaStream_t>(stream));  // a scan launched next on this stream may start beside this kernel
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool behind_scan = pdl_take_scan(st);  // directly behind a scan on this stream: start beside it
+  SRL_CUDA(launch_maybe_pdl(behind_scan, philox_perm_kernel, dim3(grid, n_epochs), dim3(threads), 0, st,
+                            static_cast<uint32_t>(seed & 0xffffffffull), static_cast<uint32_t>(seed >> 32), epoch, n_env, group,
+                            bits, out));
+  if (!behind_scan) pdl_note_perm(st);  // a scan launched next on this stream may start beside this kernel
   return SRL_OK;
 }
 

@@ -37,6 +37,9 @@ namespace {
 #ifndef SRL_PAIR_MIN_BLOCKS
 #define SRL_PAIR_MIN_BLOCKS 8
 #endif
+#ifndef SRL_PAIR_PF_AHEAD
+#define SRL_PAIR_PF_AHEAD 2
+#endif
 constexpr int kPairThreads = SRL_PAIR_THREADS;
 constexpr int kPairLanes = 2 * kPairThreads;  // lanes per column tile
 constexpr int kStatMax = 1024 / kPairThreads; // lanes per thread in the statistics prologue (n <= 1024)
@@ -324,35 +327,61 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
             __float_as_int(st.vp[1].x) | __float_as_int(st.en[1].x) | __float_as_int(st.pk[0][0]) |
             __float_as_int(st.pk[1][0])) & sc.zero;
   };
-  // policy-side loads of row pair `p` (index within the column), lanes j, j + 1
-  auto issue_policy = [&](Stage& st, int p, int j) {
-    const int r0 = 2 * (sc.pair_lo + p) - row_lo;  // loss row of the pair's first row (-1: before the first loss row)
-    const long long o = static_cast<long long>(r0) * s.ld_pol + j;
+  // Addresses.  The first version recomputed every address of a step from (row, lane) -- 64-bit multiplies and the
+  // problem's pointers re-read from the parameter bank through blockIdx.x: ~125 of the 451 instructions of a step (ncu
+  // --page source).  Now: one running byte pointer per side (policy outputs, gradients) and one per pack lane, advanced by a
+  // constant per step; the other arrays and the pair's second row are that pointer plus a UNIFORM byte offset (the distance
+  // between the problem's arrays), so a load or store costs one 64-bit add.
+  typedef const char* cptr;
+  const long long pol_row = s.ld_pol * 4, grad_row = s.ld_grad * 4;  // bytes per row
+  const long long d_vp = reinterpret_cast<cptr>(pr.v_pred) - reinterpret_cast<cptr>(pr.new_logp);
+  const long long d_en = reinterpret_cast<cptr>(pr.entropy) - reinterpret_cast<cptr>(pr.new_logp);
+  const long long d_gv = reinterpret_cast<cptr>(pr.g_value) - reinterpret_cast<cptr>(pr.g_logp);
+  const long long d_ge = reinterpret_cast<cptr>(pr.g_entropy) - reinterpret_cast<cptr>(pr.g_logp);
+  const long long pack_step = N2 * static_cast<long long>(sizeof(float4));
+  // policy-side loads of the row pair whose first loss row is r0 (-1: before the first loss row); q = &new_logp[r0][j]
+  auto issue_policy = [&](Stage& st, int r0, cptr q) {
     if (r0 >= 0) {
-      st.nl[0] = ld_cs2(pr.new_logp + o);
-      st.vp[0] = ld_cs2(pr.v_pred + o);
-      st.en[0] = ld_cs2(pr.entropy + o);
+      st.nl[0] = ld_cs2(reinterpret_cast<const float*>(q));
+      st.vp[0] = ld_cs2(reinterpret_cast<const float*>(q + d_vp));
+      st.en[0] = ld_cs2(reinterpret_cast<const float*>(q + d_en));
     }
     if (r0 + 1 < T) {
-      st.nl[1] = ld_cs2(pr.new_logp + o + s.ld_pol);
-      st.vp[1] = ld_cs2(pr.v_pred + o + s.ld_pol);
-      st.en[1] = ld_cs2(pr.entropy + o + s.ld_pol);
+      st.nl[1] = ld_cs2(reinterpret_cast<const float*>(q + pol_row));
+      st.vp[1] = ld_cs2(reinterpret_cast<const float*>(q + (pol_row + d_vp)));
+      st.en[1] = ld_cs2(reinterpret_cast<const float*>(q + (pol_row + d_en)));
     }
   };
-  auto issue_pack = [&](Stage& st, int p, const int (&c)[2]) {
-    const float4* row = s.pack + static_cast<long long>(sc.pair_lo + p) * N2;
-    ld_nc256(row + 2 * c[0], st.pk[0]);
-    ld_nc256(row + 2 * c[1], st.pk[1]);
+  auto issue_pack = [&](Stage& st, cptr k0, cptr k1) {
+    ld_nc256(reinterpret_cast<const float4*>(k0), st.pk[0]);
+    ld_nc256(reinterpret_cast<const float4*>(k1), st.pk[1]);
   };
+  auto policy_ptr = [&](int r0, int j) { return reinterpret_cast<cptr>(pr.new_logp + static_cast<long long>(r0) * s.ld_pol + j); };
 
   // Launched programmatically behind the scan, this CTA may be resident while the scan still runs: the policy outputs do
   // not depend on it, so the first step's policy-side loads are in flight before the wait.
   {
     const int j = (ct * kPairThreads + threadIdx.x) * 2;
-    if (j < n) issue_policy(sA, pi, j);
+    const int r0 = 2 * (sc.pair_lo + pi) - row_lo;
+    if (j < n) issue_policy(sA, r0, policy_ptr(r0, j));
   }
   pdl_wait();
   if (threadIdx.x == 0) SRL_TL(2, tl_cta, 1);
+
+  // L2 requests for the policy-side rows a few steps ahead (prefetch.global.L2: no register, no scoreboard).  The loop keeps
+  // ONE step of loads in flight, which hides an L2 hit but not a DRAM round trip under load, and the policy outputs are the
+  // only DRAM-resident operand of the loop (the pack was just written by the scan).  A row pair of a column tile is 24
+  // lines (2 rows x 3 arrays x 512 bytes): thread t < 24 requests line t of the pair kPfAhead steps ahead, every step.
+  // (All of a CTA's rows requested at once -- before the wait, or right behind it -- was measured first: the burst of
+  // 25 MB delayed the scan's own traffic or the statistics prologue's dependent loads by as much as the loop gained.)
+  constexpr int kPfAhead = SRL_PAIR_PF_AHEAD;
+  const bool pf_thread = kPfAhead > 0 && threadIdx.x < 24;
+  const int pf_rr = (threadIdx.x % 24) / 12, pf_line = threadIdx.x & 3;
+  const long long pf_arr = ((threadIdx.x % 12) >> 2) == 0 ? 0 : (((threadIdx.x % 12) >> 2) == 1 ? d_vp : d_en);
+  auto request_pair = [&](int p, int ct_) {  // pair index within the column, column tile
+    const int r = 2 * (sc.pair_lo + p) - row_lo + pf_rr, lane0 = ct_ * kPairLanes + pf_line * 32;
+    if (r >= 0 && r < T && lane0 < n) prefetch_l2(policy_ptr(r, lane0) + pf_arr);
+  };
 
   Acc acc;
   RowSums rs;
@@ -370,10 +399,23 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
       const int2 q = __ldg(reinterpret_cast<const int2*>(pr.lane_idx + j));
       c[0] = q.x, c[1] = q.y;
     }
+    // the next pair to load / to store: loss row of its first row and the running pointers
+    int r_ld = 2 * (sc.pair_lo + pi) - row_lo;
+    cptr q_ld = policy_ptr(r_ld, j);
+    cptr k0 = reinterpret_cast<cptr>(s.pack + static_cast<long long>(sc.pair_lo + pi) * N2 + 2 * c[0]);
+    cptr k1 = reinterpret_cast<cptr>(s.pack + static_cast<long long>(sc.pair_lo + pi) * N2 + 2 * c[1]);
+    int r_st = r_ld;
+    char* g_st = reinterpret_cast<char*>(pr.g_logp + static_cast<long long>(r_st) * s.ld_grad + j);
     if (active) {
-      if (!first) issue_policy(sA, pi, j);
-      issue_pack(sA, pi, c);
+      if (!first) issue_policy(sA, r_ld, q_ld);
+      issue_pack(sA, k0, k1);
     }
+    if (pf_thread) {
+#pragma unroll
+      for (int a = 2; a < kPfAhead; ++a)
+        if (pi + a < p_end) request_pair(pi + a, ct);
+    }
+    r_ld += 2, q_ld += 2 * pol_row, k0 += pack_step, k1 += pack_step;
     first = false;
     if (!have_u) {  // once per CTA; the first step's loads are in flight underneath
       if (s.lane_aos != nullptr)
@@ -386,11 +428,10 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
     }
     if (active) {
       // one step: both rows of the pair, both lanes; masked or out-of-range rows produce nothing
-      auto compute = [&](const Stage& st, int p) {
-        const int r0 = 2 * (sc.pair_lo + p) - row_lo;
+      auto compute = [&](const Stage& st) {
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-          const int r = r0 + rr;
+          const int r = r_st + rr;
           if (r < 0 || r >= T) continue;
           float glp[2], gv[2], ge[2];
           const float nl[2] = {st.nl[rr].x, st.nl[rr].y}, vp[2] = {st.vp[rr].x, st.vp[rr].y},
@@ -401,11 +442,12 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
             element<CFG>(h, uf, nl[q], vp[q], en[q], st.pk[q][4 * rr + 0], st.pk[q][4 * rr + 1], st.pk[q][4 * rr + 2], ad,
                          ad == ad, glp[q], gv[q], ge[q], rs);
           }
-          const long long o = static_cast<long long>(r) * s.ld_grad + j;
-          stg_stream(reinterpret_cast<float2*>(pr.g_logp + o), make_float2(glp[0], glp[1]));
-          stg_stream(reinterpret_cast<float2*>(pr.g_value + o), make_float2(gv[0], gv[1]));
-          stg_stream(reinterpret_cast<float2*>(pr.g_entropy + o), make_float2(ge[0], ge[1]));
+          char* g = g_st + (rr ? grad_row : 0);
+          stg_stream(reinterpret_cast<float2*>(g), make_float2(glp[0], glp[1]));
+          stg_stream(reinterpret_cast<float2*>(g + d_gv), make_float2(gv[0], gv[1]));
+          stg_stream(reinterpret_cast<float2*>(g + d_ge), make_float2(ge[0], ge[1]));
         }
+        r_st += 2, g_st += 2 * grad_row;
         if (++pending == kFlushRows) {  // fp32 partial sums of at most kFlushRows * 4 terms, then float64
           acc.add(rs);
           rs = RowSums();
@@ -414,21 +456,23 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
       };
       int p = pi;
       while (true) {
+        if (pf_thread && p + kPfAhead < p_end) request_pair(p + kPfAhead, ct);
         if (p + 1 < p_end) {
-          const int dep = landed(sA);
-          const int cd[2] = {c[0] + dep, c[1] + dep};
-          issue_policy(sB, p + 1, j + dep);
-          issue_pack(sB, p + 1, cd);
+          const long long dep = landed(sA);
+          issue_policy(sB, r_ld, q_ld + dep);
+          issue_pack(sB, k0 + dep, k1 + dep);
+          r_ld += 2, q_ld += 2 * pol_row, k0 += pack_step, k1 += pack_step;
         }
-        compute(sA, p);
+        compute(sA);
         if (++p >= p_end) break;
+        if (pf_thread && p + kPfAhead < p_end) request_pair(p + kPfAhead, ct);
         if (p + 1 < p_end) {
-          const int dep = landed(sB);
-          const int cd[2] = {c[0] + dep, c[1] + dep};
-          issue_policy(sA, p + 1, j + dep);
-          issue_pack(sA, p + 1, cd);
+          const long long dep = landed(sB);
+          issue_policy(sA, r_ld, q_ld + dep);
+          issue_pack(sA, k0 + dep, k1 + dep);
+          r_ld += 2, q_ld += 2 * pol_row, k0 += pack_step, k1 += pack_step;
         }
-        compute(sB, p);
+        compute(sB);
         if (++p >= p_end) break;
       }
     }

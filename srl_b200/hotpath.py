@@ -21,6 +21,7 @@ Statistics table: float64 [1 + E*M, 8]; row 0 = whole batch, row 1 + e*M + j = m
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -211,7 +212,8 @@ class HotPath:
         # K2): no fork / join, three nodes in a line in the step graph.  Without it: a parallel branch.
         inline_perm = self.minibatches > 1 and permute and ops.pdl_enabled() and not cached
         fork_perm = self.minibatches > 1 and permute and not inline_perm
-        if inline_perm:
+        perm_first = inline_perm and os.environ.get("SRL_PERM_FIRST") == "1"  # A/B knob: round 1's order K5a -> K2 -> K4
+        if perm_first:
             self.permute()
         if fork_perm:
             self._perm_stream.wait_stream(main)
@@ -231,6 +233,10 @@ class HotPath:
             ops.gae_scan(lf["reward"], lf["value"], lf["done"], lf["truncated"], lf["on_reset"], self.gamma, self.lmbda,
                          row_lo=self.row_lo, row_hi=self.row_hi, popart_mean_std=self.popart_mean_std(), adv=self.adv,
                          ret=self.ret, lane_part=self.lane_part, **kw)
+        if inline_perm and not perm_first:
+            # K2 -> K5a -> K4 on one stream: the scan is the long pole and starts first; the permutation kernel starts beside
+            # it (programmatic launch) and only completes once the scan has, so the loss kernel behind it waits for both
+            self.permute()
         if fork_perm:
             main.wait_stream(self._perm_stream)
         # The statistics table (row 0 = batch, row 1 + e*M + j = minibatch (e, j); summed over the ranks).  When the batched
