@@ -589,11 +589,23 @@ def run_ours(args, cfg_full, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # Several ranks: the flush kernels of two GPUs do not end at the same moment (a few microseconds apart), and the step's
+    # statistics exchange makes the early rank wait for the late one -- inside the timed region.  An UNTIMED device-side
+    # rendezvous (the peer-memory exchange of one number) between the flush and the start event lines the ranks up, so
+    # that what is timed is the step, not the flush skew.  --no-align switches it off (A/B).
+    align = None
+    if world > 1 and hp.peer is not None and not args.no_align:
+        align_in = torch.ones(1, dtype=torch.float64, device=dev)
+        align_out = torch.zeros(1, dtype=torch.float64, device=dev)
+        align = lambda: hp.peer.allreduce_sum(align_in, align_out)
+
     def timed_steps(k, fn, flush_first=True):
         pairs = []
         for _ in range(k):
             if flush_first:
                 flush_l2()
+            if align is not None:
+                align()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
@@ -764,7 +776,9 @@ def run_ours(args, cfg_full, rank, world, local_rank):
                         transitions_per_step_per_gpu=cfg.transitions,
                         l2="flushed between timed iterations (256 MiB device write, then 256 MiB device read, before each step; working set "
                            f"{step_bytes / 1e6:.0f} MB algorithmic)",
-                        timing="CUDA events per step on the launch stream, sum over steps, max over ranks",
+                        timing="CUDA events per step on the launch stream, sum over steps, max over ranks" +
+                        ("; the ranks meet in an untimed device-side rendezvous between the L2 flush and each start event "
+                         "(flush skew between GPUs is not part of a step)" if align is not None else ""),
                         launch="one CUDA graph per step" + ("" if world == 1 else (
                             f" ({hp.exchange_kind} exchange of the float64 stats table captured inside)"
                             if hp._graph_a is None else f" split in two around the {hp.exchange_kind} exchange of the float64 stats table")),
@@ -803,6 +817,7 @@ def run_ours(args, cfg_full, rank, world, local_rank):
             step_trainer_order=trainer_order, trainer_step=trainer_line, extra=extra,
             cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
+    align = None
     del hp, g_loss, g_gae  # CUDA graphs and peer mailboxes go before the process group does
     torch.cuda.synchronize()
     if world > 1:
@@ -869,6 +884,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the K1 / K4b / trainer_step lines")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-align", action="store_true",
+                    help="N > 1: do not line the ranks up (untimed device-side rendezvous) before each timed step")
     ap.add_argument("--shuffle-block", type=int, default=1,
                     help="environments per shuffled block (1 = per-environment permutation; 8 = one 32-byte sector)")
     ap.add_argument("--branches", type=int, default=16, help="parallel CUDA-graph branches for the per-minibatch launches")

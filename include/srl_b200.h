@@ -221,14 +221,17 @@ enum srl_loss_out {
 };
 
 /* Bytes of one device scratch "slot" for a [T, n] problem: a 64-byte header + one float64[8] partial row per
- * CTA.  A slot must be zero before its FIRST use (the ticket counter lives in the header and the kernel
- * re-zeroes it); launches that may overlap in time need distinct slots. */
+ * CTA.  A slot must be ALL ZERO before its first use; every kernel that uses it leaves it all zero again (ticket
+ * counter, published statistics, partial rows: "zero" means "not there yet" to the kernels that wait for a row), so a
+ * deferred launch must be followed by srl_ppo_loss_finalize before the slot is used again.  Launches that may overlap
+ * in time need distinct slots. */
 size_t srl_ppo_loss_workspace_bytes(int T, int n);
 
 /* Deferred finalisation: when srl_ppo_loss_fwd_bwd / srl_ppo_loss_from_logits are called with out == NULL they
  * stop after writing gradients and partial rows.  This folds n_slots consecutive slots (slot k at
- * workspace + k * slot_bytes) into out[k][SRL_LOSS_OUT_LEN] (and out_f32[k][4] if not NULL) in one launch. */
-int srl_ppo_loss_finalize(const void* workspace, size_t slot_bytes, int n_slots, double* out, float* out_f32,
+ * workspace + k * slot_bytes) into out[k][SRL_LOSS_OUT_LEN] (and out_f32[k][4] if not NULL) in one launch, and
+ * clears the rows it folded. */
+int srl_ppo_loss_finalize(void* workspace, size_t slot_bytes, int n_slots, double* out, float* out_f32,
                           srl_stream_t stream);
 
 int srl_ppo_loss_fwd_bwd(

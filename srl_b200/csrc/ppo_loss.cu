@@ -36,12 +36,12 @@ namespace srl {
 namespace loss {
 namespace {
 
-__global__ void __launch_bounds__(256) loss_finalize_kernel(const unsigned char* __restrict__ ws, size_t slot_bytes,
+__global__ void __launch_bounds__(256) loss_finalize_kernel(unsigned char* __restrict__ ws, size_t slot_bytes,
                                                             double* __restrict__ out, float* __restrict__ out_f32) {
   __shared__ double sred[kNumSums][8];
-  const unsigned char* base = ws + static_cast<size_t>(blockIdx.x) * slot_bytes;
+  unsigned char* base = ws + static_cast<size_t>(blockIdx.x) * slot_bytes;
   const SlotHeader* hd = reinterpret_cast<const SlotHeader*>(base);
-  fold_rows_and_write(reinterpret_cast<const double*>(base + kPartialsOffset), static_cast<int>(hd->n_rows),
+  fold_rows_and_write(reinterpret_cast<double*>(base + kPartialsOffset), static_cast<int>(hd->n_rows),
                       hd->mask_sum, hd->wv, hd->we, sred, out + static_cast<size_t>(blockIdx.x) * SRL_LOSS_OUT_LEN,
                       out_f32 ? out_f32 + static_cast<size_t>(blockIdx.x) * 4 : nullptr);
 }
@@ -197,7 +197,7 @@ extern "C" size_t srl_ppo_loss_workspace_bytes(int, int) {
   return srl::loss::kPartialsOffset + static_cast<size_t>(srl::loss::kMaxGrid) * srl::loss::kNumSums * sizeof(double);
 }
 
-extern "C" int srl_ppo_loss_finalize(const void* workspace, size_t slot_bytes, int n_slots, double* out, float* out_f32,
+extern "C" int srl_ppo_loss_finalize(void* workspace, size_t slot_bytes, int n_slots, double* out, float* out_f32,
                                      srl_stream_t stream) {
   using namespace srl;
   using namespace srl::loss;
@@ -207,7 +207,7 @@ extern "C" int srl_ppo_loss_finalize(const void* workspace, size_t slot_bytes, i
   SRL_REQUIRE(slot_bytes >= srl_ppo_loss_workspace_bytes(1, 1) && slot_bytes % 8 == 0, SRL_ERR_INVALID_ARG,
               "srl_ppo_loss_finalize: slot_bytes=%zu smaller than one workspace or not 8-byte aligned", slot_bytes);
   loss_finalize_kernel<<<n_slots, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const unsigned char*>(workspace), slot_bytes, out, out_f32);
+      static_cast<unsigned char*>(workspace), slot_bytes, out, out_f32);
   SRL_CUDA(cudaGetLastError());
   return SRL_OK;
 }

@@ -25,12 +25,17 @@ struct SlotHeader {
   unsigned int n_rows;  // CTAs that wrote a partial row
   double mask_sum;      // this rank's sum(mask) for the minibatch
   double wv, we;        // loss weights, so the finaliser needs nothing but the slot
-  // pair kernel, immediate mode: the minibatch's normalisation sums {count, sum, sum of squares} (over all ranks), computed
-  // by ONE CTA of the problem and read by the others once `ready` is set; the last CTA clears `ready` with the ticket
-  double bc[3];
-  unsigned int ready;
-  unsigned int pad;
+  // pair kernel, immediate mode: the minibatch's normalisation sums {count, sum, sum of squares} over all ranks and this
+  // rank's count, computed by ONE CTA of the problem and read by the others.  Each word is the float64's bit pattern XOR
+  // kBoxKey: 0 (the workspace's initial state, restored by the last CTA with the ticket) means "not there yet", every
+  // word validates itself, and neither side needs a fence -- a release behind the exchange's stores into the peers'
+  // mailboxes would wait for their acknowledgement over NVLink.
+  unsigned long long bc[4];
 };
+// A signalling-NaN pattern no arithmetic produces (sums are finite, or the canonical quiet NaN of a failed exchange).
+constexpr unsigned long long kBoxKey = 0x7ff4deadbeef0001ull;
+__device__ __forceinline__ unsigned long long box(double x) { return static_cast<unsigned long long>(__double_as_longlong(x)) ^ kBoxKey; }
+__device__ __forceinline__ double unbox(unsigned long long w) { return __longlong_as_double(static_cast<long long>(w ^ kBoxKey)); }
 static_assert(sizeof(SlotHeader) == kPartialsOffset, "slot header must stay 64 bytes");
 
 struct LossHyperDev {
@@ -281,13 +286,18 @@ __device__ __forceinline__ void element(const LossHyperDev& h, const Uniforms& u
 
 // Folds n_rows partial rows (fixed order: lane-strided, then the warp-shuffle tree) and writes the results.
 // Called by one CTA; sred is [kNumSums][8] shared scratch.
-__device__ __forceinline__ void fold_rows_and_write(const double* __restrict__ partials, int n_rows, double M, double wv,
+// The rows are cleared behind the fold: between launches a slot's rows are all zero, whichever kernel used it last (the
+// pair kernel's immediate mode reads "zero" as "this CTA's row is not there yet").
+__device__ __forceinline__ void fold_rows_and_write(double* __restrict__ partials, int n_rows, double M, double wv,
                                                     double we, double (*sred)[8], double* __restrict__ o,
                                                     float* __restrict__ o32) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int k = warp; k < kNumSums; k += nwarps) {
     double s = 0.0;
-    for (int b = lane; b < n_rows; b += 32) s += __ldcg(partials + static_cast<size_t>(b) * kNumSums + k);
+    for (int b = lane; b < n_rows; b += 32) {
+      s += __ldcg(partials + static_cast<size_t>(b) * kNumSums + k);
+      partials[static_cast<size_t>(b) * kNumSums + k] = 0.0;
+    }
     s = warp_sum(s);
     if (lane == 0) sred[k][0] = s;
   }

@@ -72,15 +72,6 @@ __device__ __forceinline__ void ld_nc256(const double* p, double (&v)[4]) {
   asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // Minibatch statistics from K2's per-lane sums (lane_aos[lane] = {sum mask, sum adv*mask, sum (adv*mask)^2, 0}), added
 // over ALL lanes of the problem: thread i adds lanes i, i + THREADS, ... in that order, then the warp tree, then the warps
 // in order.  `share` (immediate mode: the problem has a ticket, so somebody can clear the flag afterwards): only the
@@ -99,7 +90,12 @@ __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__
       const long long limit = 2 * (xv.world > 1 ? xv.spin_limit : kDefaultSpinLimit);
       const long long t0 = clock64();
       bool ok = true;
-      while (ld_acquire_u32(&hdr->ready) == 0u) {
+      unsigned long long w[4];
+      const volatile unsigned long long* src = hdr->bc;
+      while (true) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = src[q];
+        if (w[0] != 0ull && w[1] != 0ull && w[2] != 0ull && w[3] != 0ull) break;
         if (clock64() - t0 > limit) {
           ok = false;
           break;
@@ -107,10 +103,8 @@ __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__
         __nanosleep(64);
       }
       const double nan = __longlong_as_double(0x7ff8000000000000ll);
-      s_part[0][0] = ok ? __ldcg(&hdr->bc[0]) : nan;  // no statistics: nothing but NaN leaves this launch
-      s_part[1][0] = ok ? __ldcg(&hdr->bc[1]) : nan;
-      s_part[2][0] = ok ? __ldcg(&hdr->bc[2]) : nan;
-      s_part[3][0] = ok ? __ldcg(&hdr->mask_sum) : nan;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s_part[q][0] = ok ? unbox(w[q]) : nan;  // no statistics: nothing but NaN leaves this launch
     }
     __syncthreads();
     mask_sum = s_part[3][0];
@@ -172,12 +166,9 @@ __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__
     __shared__ unsigned int s_words[6 * kMaxWorld];
     xchg_problem_sums(xv, slot, sender, x, s_words);
   }
-  if (share && threadIdx.x == 0) {  // sender
-    hdr->bc[0] = x[0];
-    hdr->bc[1] = x[1];
-    hdr->bc[2] = x[2];
-    hdr->mask_sum = cnt;
-    st_release_u32(&hdr->ready, 1u);
+  if (share && threadIdx.x < 4) {  // sender: four self-validating words, no fence
+    volatile unsigned long long* dst = hdr->bc;
+    dst[threadIdx.x] = box(threadIdx.x < 3 ? x[threadIdx.x] : cnt);
   }
   return uniforms_from(x[0], x[1], x[2], cnt, nullptr, adv_eps);
 }
@@ -219,7 +210,12 @@ __device__ __forceinline__ void pair_reduce_and_finalize(const Problem& pr, cons
 #pragma unroll
       for (int k = 0; k < kNumSums; ++k) s = (lane == k) ? v[k] : s;
     }
-    partials[static_cast<size_t>(row) * kNumSums + lane] = s;
+    // deferred mode: plain float64 rows for srl_ppo_loss_finalize.  Immediate mode: boxed words (ppo_loss.cuh: 0 = not there
+    // yet), so the row needs no fence and no ticket -- the problem's first CTA waits for every row by looking at it.
+    if (pr.out == nullptr)
+      partials[static_cast<size_t>(row) * kNumSums + lane] = s;
+    else
+      reinterpret_cast<volatile unsigned long long*>(partials)[static_cast<size_t>(row) * kNumSums + lane] = box(s);
   }
   if (pr.out == nullptr) {  // deferred: publish what the finaliser needs and leave
     if (row == 0 && lane == 0) {
@@ -230,32 +226,43 @@ __device__ __forceinline__ void pair_reduce_and_finalize(const Problem& pr, cons
     }
     return;
   }
-  __syncwarp();
-  unsigned int done = 0;
-  if (lane == 0) {
-    __threadfence();  // the row above (written by this warp, ordered by the warp barrier) before the ticket
-    done = atomicAdd(&pr.slot->ticket, 1u);
-  }
-  done = __shfl_sync(0xffffffffu, done, 0);
   if (lane == 0) SRL_TL(2, row * gridDim.x + blockIdx.x, 4);
-  if (done != static_cast<unsigned int>(n_rows) - 1u) return;
-  __threadfence();
-  // fold: lane k (and k + 8, k + 16, k + 24) walks the rows of sum k in row order, then the four quarter sums are added
-  // (the kernel ends with this CTA: all row loads of a batch in flight at once, and the eight divisions side by side in
-  // lanes 0..7 instead of one after the other in lane 0 -- same operations, same order of additions, same bits)
+  if (row != 0) return;
+  // The problem's first CTA folds the rows (the round-2 first version: every CTA fenced its row and took a ticket, the last
+  // one folded -- 1.5 us of fence + atomic round trip per CTA behind its last stores, on the kernel's tail).  Lane k (and
+  // k + 8, k + 16, k + 24) walks the rows of sum k in row order, waiting for each word to appear and clearing it behind
+  // itself; then the four quarter sums are added -- the same order of additions as before, the same bits.  Every CTA of
+  // the problem is resident (one wave, launch_pair), so the wait ends; its bound is the statistics wait's.
   const int k = lane & 7, part = lane >> 3;
   double s = 0.0;
   constexpr int kFoldBatch = 16;
+  volatile unsigned long long* rows = reinterpret_cast<volatile unsigned long long*>(partials);
+  const long long limit = 2 * (xv.world > 1 ? xv.spin_limit : kDefaultSpinLimit);
+  const long long t0 = clock64();
   for (int r0 = part; r0 < n_rows; r0 += 4 * kFoldBatch) {
-    double v[kFoldBatch];
+    unsigned long long w[kFoldBatch];
+    bool all = false, ok = true;
+    while (!all) {
+      all = true;
+#pragma unroll
+      for (int q = 0; q < kFoldBatch; ++q) {
+        const int r = r0 + 4 * q;
+        w[q] = r < n_rows ? rows[static_cast<size_t>(r) * kNumSums + k] : 1ull;
+        all = all && w[q] != 0ull;
+      }
+      if (!all && clock64() - t0 > limit) {
+        ok = false;
+        break;
+      }
+    }
 #pragma unroll
     for (int q = 0; q < kFoldBatch; ++q) {
       const int r = r0 + 4 * q;
-      v[q] = r < n_rows ? __ldcg(partials + static_cast<size_t>(r) * kNumSums + k) : 0.0;
+      if (r < n_rows) {
+        s += ok ? unbox(w[q]) : __longlong_as_double(0x7ff8000000000000ll);  // a CTA never arrived: NaN, not a partial sum
+        rows[static_cast<size_t>(r) * kNumSums + k] = 0ull;
+      }
     }
-#pragma unroll
-    for (int q = 0; q < kFoldBatch; ++q)
-      if (r0 + 4 * q < n_rows) s += v[q];
   }
   s += __shfl_down_sync(0xffffffffu, s, 16);
   s += __shfl_down_sync(0xffffffffu, s, 8);
@@ -287,10 +294,10 @@ __device__ __forceinline__ void pair_reduce_and_finalize(const Problem& pr, cons
       pr.out_f32[2] = static_cast<float>(vl);
       pr.out_f32[3] = static_cast<float>(el);
     }
-    pr.slot->ticket = 0u;  // ready for the next launch on this slot
-    pr.slot->ready = 0u;   // (every CTA of the problem has read the published statistics: it has taken the ticket)
-    // every CTA of this problem is past the exchange (it has taken the ticket): the last PROBLEM to get here ends the
-    // launch's exchange round (n_problems atomics per launch instead of one per CTA)
+    // every CTA of the problem has written its row, so it has read the published statistics: ready for the next launch
+    pr.slot->bc[0] = pr.slot->bc[1] = pr.slot->bc[2] = pr.slot->bc[3] = 0ull;
+    // ... and is past the exchange: the last PROBLEM to get here ends the launch's exchange round (n_problems atomics per
+    // launch instead of one per CTA)
     if (xv.world > 1) xchg_launch_done(xv, n_problems);
     SRL_TL(2, row * gridDim.x + blockIdx.x, 5);
   }
