@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SRL_B200_ABI_VERSION 6
+#define SRL_B200_ABI_VERSION 7
 
 typedef void* srl_stream_t; /* cudaStream_t */
 

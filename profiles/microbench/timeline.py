@@ -22,14 +22,28 @@ extra = [a for a in sys.argv[1:] if a.startswith("-D")]
 tag = sys.argv[sys.argv.index("--tag") + 1] if "--tag" in sys.argv else "tl"
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 lib = os.path.join(ROOT, "gpurun_out", f"libsrl_{tag}.so")
-build.build(out=lib, extra_flags=["-DSRL_TIMELINE"] + extra)
+if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+    build.build(out=lib, extra_flags=["-DSRL_TIMELINE"] + extra)
+else:
+    import time
+    while not os.path.exists(lib + ".done"):
+        time.sleep(0.5)
+if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+    open(lib + ".done", "w").close()
 os.environ["SRL_B200_LIB"] = lib
 from srl_b200 import ops
 from srl_b200.hotpath import HotPath
 
 names = [a for a in sys.argv[1:] if not a.startswith("-") and a != tag]
 cfg = synth.CONFIGS[names[0] if names else "cfg2_atari_large"]
-dev = torch.device("cuda", 0)
+rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+torch.cuda.set_device(dev)
+pg = None
+if world > 1:  # torchrun: the same picture with the statistics exchanged between the ranks inside the loss kernel
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+    pg = dist.group.WORLD
 h = ops._lib.load_library()
 KC, KS = 2048, 16
 buf = torch.zeros((3, KC, KS, 2), dtype=torch.int64, device=dev)
@@ -46,7 +60,7 @@ pol = synth.make_policy_outputs(cfg, s, seed=1)
 E, Mb, T, N = cfg.epochs, cfg.minibatches, cfg.T, cfg.N
 hp = HotPath(cfg.L, cfg.B, cfg.A, gamma=cfg.gamma, lmbda=cfg.lmbda, hyper=ops.LossHyper(**bench.hyper_kwargs(cfg)),
              bootstrap_steps=cfg.bootstrap_steps, burn_in_steps=cfg.burn_in_steps, epochs=E, minibatches=Mb, seed=0,
-             popart=cfg.popart, device=dev)
+             popart=cfg.popart, device=dev, process_group=pg, exchange_timeout_s=30.0)
 n = hp.n_mb
 hp.load_sample({k: torch.from_numpy(np.ascontiguousarray(v.reshape(cfg.L, N))).pin_memory() for k, v in s.items()})
 perm = [ops.philox_perm(0, e, cfg.B, cfg.A).long() if Mb > 1 else None for e in range(E)]
@@ -76,14 +90,21 @@ SLOTS = {
     0: ["entry", "end"],
     1: ["entry", "barriers ready", "all TMA issued", "first chunk landed", "scan done", "last store pass done",
         "lane sums written", "after wait for K5a"],
-    2: ["entry", "after griddepcontrol.wait", "statistics ready", "loop done", "ticket taken", "problem finalised"],
+    2: ["entry", "after griddepcontrol.wait", "statistics ready", "loop done", "row written", "problem finalised",
+        "first CTA: local sums ready", "first CTA: sums of all ranks ready"],
 }
+
+
+_one = torch.ones(1, dtype=torch.float64, device=dev)
+_sum = torch.zeros(1, dtype=torch.float64, device=dev)
 
 
 def one(cold=True):
     buf.zero_()
     if cold:
         flush_l2()
+    if world > 1:  # line the ranks up on the device, as bench.py does before every timed step
+        hp.peer.allreduce_sum(_one, _sum)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     hp.run_device(pol_dev, use_graph=True)
@@ -119,6 +140,8 @@ def report(us, rec, label):
     return rows
 
 
+if rank != 0:
+    sys.stdout = open(os.devnull, "w")
 res = {}
 for label, cold in (("cold L2", True), ("cold L2 (again)", True), ("warm L2", False)):
     us, rec = one(cold)
@@ -127,6 +150,13 @@ for label, cold in (("cold L2", True), ("cold L2 (again)", True), ("warm L2", Fa
 g = np.unique(rec[..., 0][rec[..., 0] > 0])
 if g.size > 2:
     print("globaltimer smallest increment seen: %d ns" % int(np.diff(g).min()))
-np.save(os.path.join(ROOT, "gpurun_out", f"timeline_{tag}_{cfg.name}.npy"), rec)
-with open(os.path.join(ROOT, "gpurun_out", f"timeline_{tag}_{cfg.name}.json"), "w") as f:
-    json.dump(res, f, indent=1)
+if rank == 0:
+    np.save(os.path.join(ROOT, "gpurun_out", f"timeline_{tag}_{cfg.name}.npy"), rec)
+if rank == 0:
+    with open(os.path.join(ROOT, "gpurun_out", f"timeline_{tag}_{cfg.name}.json"), "w") as f:
+        json.dump(res, f, indent=1)
+if world > 1:
+    del hp
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()

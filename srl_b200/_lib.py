@@ -19,7 +19,7 @@ SRL_LANE_PART = 8
 SRL_LOSS_OUT_LEN = 16
 SRL_MAX_LEAVES = 32
 SRL_MAX_HEADS = 8
-ABI_VERSION = 6
+ABI_VERSION = 7
 SRL_MAX_LOSS_BATCH = 32
 
 # enum srl_loss_out

@@ -82,7 +82,8 @@ __device__ __forceinline__ void ld_nc256(const double* p, double (&v)[4]) {
 // order, so all CTAs of a problem normalise with bit-identical statistics either way.
 __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__ lane_aos, const int32_t* __restrict__ idx,
                                                       int n, double adv_eps, double& mask_sum, double (*s_part)[8],
-                                                      const XchgView& xv, int slot, bool sender, SlotHeader* hdr, bool share) {
+                                                      const XchgView& xv, int slot, bool sender, SlotHeader* hdr, bool share,
+                                                      unsigned int xchg_seq) {
   if (share && !sender) {
     if (threadIdx.x == 0) {
       // the sender is resident (dispatched first, launch_pair) and waits for nothing but -- with several ranks -- its peers,
@@ -100,7 +101,7 @@ __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__
           ok = false;
           break;
         }
-        __nanosleep(64);
+        __nanosleep(32);
       }
       const double nan = __longlong_as_double(0x7ff8000000000000ll);
 #pragma unroll
@@ -159,13 +160,15 @@ __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__
   }
   mask_sum = cnt;  // the masked means of the loss stay rank-local
   double x[3] = {cnt, s1, s2};
+  if (threadIdx.x == 0) SRL_TL(2, blockIdx.y * gridDim.x + blockIdx.x, 6);
   if (xv.world > 1) {
     // several ranks: the normalisation statistics are the sums over ALL ranks' minibatches (utils.py:58-61).  The problem's
     // first CTA sends this rank's three sums to every rank's mailbox; it (share) or every CTA collects the ranks' sums from
     // its own rank's mailbox and adds them in rank order.
     __shared__ unsigned int s_words[6 * kMaxWorld];
-    xchg_problem_sums(xv, slot, sender, x, s_words);
+    xchg_problem_sums(xv, slot, sender, x, s_words, xchg_seq);
   }
+  if (threadIdx.x == 0) SRL_TL(2, blockIdx.y * gridDim.x + blockIdx.x, 7);
   if (share && threadIdx.x < 4) {  // sender: four self-validating words, no fence
     volatile unsigned long long* dst = hdr->bc;
     dst[threadIdx.x] = box(threadIdx.x < 3 ? x[threadIdx.x] : cnt);
@@ -374,6 +377,9 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
   }
   pdl_wait();
   if (threadIdx.x == 0) SRL_TL(2, tl_cta, 1);
+  // the exchange's sequence number (it moved when the previous exchanging launch ended): loaded here, used after the local
+  // sums are added -- its latency hides under theirs
+  const unsigned int xchg_seq = b.xv.world > 1 ? *reinterpret_cast<volatile unsigned int*>(b.xv.seq) : 0u;
 
   // L2 requests for the policy-side rows a few steps ahead (prefetch.global.L2: no register, no scoreboard).  The loop keeps
   // ONE step of loads in flight, which hides an L2 hit but not a DRAM round trip under load, and the policy outputs are the
@@ -427,7 +433,7 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
     if (!have_u) {  // once per CTA; the first step's loads are in flight underneath
       if (s.lane_aos != nullptr)
         uf = self_uniforms_aos(s.lane_aos, pr.lane_idx, n, h.adv_eps, mask_sum, s_part, b.xv, static_cast<int>(blockIdx.x),
-                               blockIdx.y == 0, pr.slot, pr.out != nullptr && gridDim.y > 1);
+                               blockIdx.y == 0, pr.slot, pr.out != nullptr && gridDim.y > 1, xchg_seq);
       else
         uf = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
       have_u = true;

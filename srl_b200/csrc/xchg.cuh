@@ -81,8 +81,11 @@ __device__ __forceinline__ void xchg_exchange(const XchgView& v, const double* _
 // rank's mailbox and adds them in rank order (bit-identical on every rank and in every CTA).  Same word format and double
 // buffering as xchg_exchange; the sequence number advances once per LAUNCH (xchg_launch_done, by the last CTA to finish).
 // Called by all threads of the CTA after griddepcontrol.wait (the previous launch has advanced the sequence number by then).
-__device__ __forceinline__ bool xchg_problem_sums(const XchgView& v, int slot, bool sender, double (&x)[3], unsigned int* sh_words) {
-  unsigned int seq = *reinterpret_cast<volatile unsigned int*>(v.seq) + 1u;
+// `seq_now`: the mailbox's sequence number as read by the caller AFTER its griddepcontrol.wait (the number moves at the
+// end of a launch that exchanged), sparing this call a dependent load.
+__device__ __forceinline__ bool xchg_problem_sums(const XchgView& v, int slot, bool sender, double (&x)[3], unsigned int* sh_words,
+                                                  unsigned int seq_now) {
+  unsigned int seq = seq_now + 1u;
   if (seq == 0u) seq = 1u;
   const int par = static_cast<int>(seq & 1u);
   const unsigned long long tag = static_cast<unsigned long long>(seq) << 32;
@@ -109,8 +112,7 @@ __device__ __forceinline__ bool xchg_problem_sums(const XchgView& v, int slot, b
         bad = true;
         break;
       }
-      __nanosleep(40);  // hundreds of CTAs poll the same few sectors: leave the L2 slice room for the incoming stores
-      word = *src;
+      word = *src;  // (one CTA per problem polls: no back-off needed)
     }
     sh_words[i] = static_cast<unsigned int>(word);
   }
