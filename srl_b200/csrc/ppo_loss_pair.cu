@@ -101,7 +101,7 @@ __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__
           ok = false;
           break;
         }
-        __nanosleep(32);
+        __nanosleep(32);  // (a first long sleep or slower polling changed nothing: 30.24 - 30.42 us per step)
       }
       const double nan = __longlong_as_double(0x7ff8000000000000ll);
 #pragma unroll
