@@ -63,78 +63,204 @@ struct LogitsParams {
   int head_size[SRL_MAX_HEADS];
 };
 
-// CACHE_E: a second shared-memory row per transition keeps e_k = exp(z_k - max) of the log-sum-exp pass, so that the entropy
-// and the gradient passes need no further exponentials (1 expf per logit instead of 3: the kernel is bound by the special
-// function unit, not by memory -- 72 us for 90 MB at cfg2's shape before, profiles/r2_notes.md); used when both rows fit.
+// How the kernel got here (ncu, T=128 N=4096 K=18: profiles/r2_notes.md).  First version: 2180 instructions per transition --
+// the staged [256, SK + 1] block was walked once per pass (max, exp / sum, entropy, gradient) with a run-time trip count,
+// staged in and out element by element with an integer division each, every shared-memory store behind its own global
+// load -- 98 us for 91 MB, neither bandwidth- nor issue-bound.  Now:
+//  * staging is ONE bulk asynchronous copy per tile and direction (cp.async.bulk, completion on an mbarrier / a bulk
+//    group): the block is contiguous in global memory and dense in shared memory;
+//  * a head of <= 32 actions lives in registers for the forward passes and again for the gradient pass, in instantiations
+//    of 4, 8, ... 32 registers (loops unrolled, addresses immediate); e_k = exp(z_k - max) is kept in a second dense block
+//    when both fit (CACHE_E), so the gradient pass needs no exponential; wider heads keep the row walk;
+//  * the sample side is loaded before the passes, so its DRAM round trip hides under them.
+constexpr int kStage = 9;  // manual staging batch per thread (last, partial tile only)
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// forward passes of one head held in registers: log-sum-exp, 1 / sum, entropy; e_k to `ez` when CACHE_E
+template <int KM, bool CACHE_E>
+__device__ __forceinline__ void head_forward(const float* z, float* ez, int K, float& l, float& inv, float& hh) {
+  float v[KM];
+#pragma unroll
+  for (int k = 0; k < KM; ++k) v[k] = k < K ? z[k] : -INFINITY;
+  float mx = v[0];
+#pragma unroll
+  for (int k = 1; k < KM; ++k) mx = fmaxf(mx, v[k]);
+  float e[KM];
+  float se = 0.f;
+#pragma unroll
+  for (int k = 0; k < KM; ++k) {
+    e[k] = expf(v[k] - mx);  // exp(-inf) = 0 for the padding registers
+    se += e[k];
+  }
+  l = mx + logf(se);
+  inv = 1.f / se;
+  hh = 0.f;
+#pragma unroll
+  for (int k = 0; k < KM; ++k) {
+    if (k < K) {
+      const float lp = fmaxf(v[k] - l, -FLT_MAX);  // Categorical.entropy clamps at finfo.min
+      const float pk = CACHE_E ? e[k] * inv : expf(lp);
+      hh -= pk * lp;
+      if (CACHE_E) ez[k] = e[k];
+    }
+  }
+}
+
+// gradient pass of one head: z_k <- d loss / d z_k
+template <int KM, bool CACHE_E>
+__device__ __forceinline__ void head_backward(float* z, const float* ez, int K, int a, float l, float inv, float hh, float g_lp,
+                                              float g_en) {
+  float v[KM], e[KM];
+#pragma unroll
+  for (int k = 0; k < KM; ++k) {
+    v[k] = k < K ? z[k] : 0.f;
+    e[k] = (CACHE_E && k < K) ? ez[k] : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < KM; ++k) {
+    if (k < K) {
+      const float lp = v[k] - l;
+      const float pk = CACHE_E ? e[k] * inv : expf(lp);
+      // d logp / d z_k = [k == a] - p_k ;  d H / d z_k = -p_k (lp_k + H)
+      z[k] = g_lp * ((k == a ? 1.f : 0.f) - pk) - g_en * pk * (fmaxf(lp, -FLT_MAX) + hh);
+    }
+  }
+}
+
+#define SRL_HEAD_DISPATCH(FN, K, ...)                  \
+  do {                                                 \
+    if ((K) <= 4) FN<4, CACHE_E>(__VA_ARGS__);         \
+    else if ((K) <= 8) FN<8, CACHE_E>(__VA_ARGS__);    \
+    else if ((K) <= 12) FN<12, CACHE_E>(__VA_ARGS__);  \
+    else if ((K) <= 16) FN<16, CACHE_E>(__VA_ARGS__);  \
+    else if ((K) <= 20) FN<20, CACHE_E>(__VA_ARGS__);  \
+    else if ((K) <= 24) FN<24, CACHE_E>(__VA_ARGS__);  \
+    else if ((K) <= 28) FN<28, CACHE_E>(__VA_ARGS__);  \
+    else FN<32, CACHE_E>(__VA_ARGS__);                 \
+  } while (0)
+
 template <bool CACHE_E>
 __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const __grid_constant__ LogitsParams q) {
-  extern __shared__ float srow[];  // [256][SK + 1] (+ [256][SK + 1] with CACHE_E)
+  extern __shared__ __align__(128) float srow[];  // [256 * SK] dense (+ [256 * SK] with CACHE_E), then the mbarrier
   const LossShared& p = q.s;
   const Problem& pr = q.pr;
   const LossHyperDev& h = p.h;
   double mask_sum;
   const Uniforms u = load_uniforms(pr.norm_stats, pr.local_stats, p.popart, h.adv_eps, mask_sum);
   Acc acc;
-  const int SK = q.SK, stride = SK + 1;
-  float* erow = srow + 256 * stride;
+  const int SK = q.SK;
+  float* erow = srow + 256 * SK;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(srow + (CACHE_E ? 2 : 1) * 256 * SK);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+  const bool bulk_ok = ((reinterpret_cast<uintptr_t>(q.logits) | reinterpret_cast<uintptr_t>(q.g_logits)) & 15) == 0;
   const long long W = static_cast<long long>(p.T) * p.n;
   const long long tiles = (W + 255) / 256;
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long i0 = tile * 256;
     const int cnt = static_cast<int>(min(256ll, W - i0));
-    // coalesced stage-in of cnt*SK contiguous floats
+    const int total = cnt * SK;
     const float* src = q.logits + i0 * SK;
-    for (int e = threadIdx.x; e < cnt * SK; e += 256) {
-      const int r = e / SK;
-      srow[r * stride + (e - r * SK)] = ldg_stream(src + e);
+    float* dst = q.g_logits + i0 * SK;
+    const bool bulk = bulk_ok && cnt == 256;  // 256 * SK * 4 bytes: a multiple of 16 at a 16-byte aligned address
+    if (bulk) {
+      if (threadIdx.x == 0) {
+        const uint32_t bytes = static_cast<uint32_t>(total) * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr(srow)),
+                     "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                     : "memory");
+      }
+    } else {
+      for (int e0 = threadIdx.x; e0 < total; e0 += 256 * kStage) {
+        float v[kStage];
+#pragma unroll
+        for (int b = 0; b < kStage; ++b) v[b] = (e0 + b * 256 < total) ? ldg_stream(src + e0 + b * 256) : 0.f;
+#pragma unroll
+        for (int b = 0; b < kStage; ++b)
+          if (e0 + b * 256 < total) srow[e0 + b * 256] = v[b];
+      }
     }
-    __syncthreads();
-    if (static_cast<int>(threadIdx.x) < cnt) {
-      const long long i = i0 + threadIdx.x;
+    // the sample side of this thread's transition, in flight while the block lands
+    const bool mine = static_cast<int>(threadIdx.x) < cnt;
+    const long long i = i0 + threadIdx.x;
+    float vp = 0.f, ol = 0.f, rt = 0.f, ad = 0.f, ov = 0.f;
+    bool valid = false;
+    int act[SRL_MAX_HEADS];
+    if (mine) {
       const int t = static_cast<int>(i / p.n);
       const int j = static_cast<int>(i - static_cast<long long>(t) * p.n);
       const int c = pr.lane_idx ? pr.lane_idx[j] : j;
       const long long os = t * p.ld_smp + c;
-      float* z = srow + threadIdx.x * stride;
-      float* ez = erow + threadIdx.x * stride;
+      vp = ldg_stream(pr.v_pred + i);
+      ol = __ldg(p.old_logp + os), rt = __ldg(p.ret + os), ad = __ldg(p.adv + os);
+      ov = h.clip_value ? __ldg(p.old_value + os) : 0.f;
+      valid = __ldg(p.reset_next + os) == 0;
+#pragma unroll
+      for (int hd = 0; hd < SRL_MAX_HEADS; ++hd) act[hd] = hd < q.heads ? q.action[i * q.heads + hd] : 0;
+    }
+    if (bulk) {
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+      }
+      parity ^= 1u;
+    } else {
+      __syncthreads();
+    }
+    if (mine) {
+      float* z = srow + threadIdx.x * SK;
+      float* ez = erow + threadIdx.x * SK;
       float lse[SRL_MAX_HEADS], hent[SRL_MAX_HEADS], rse[SRL_MAX_HEADS];
-      int act[SRL_MAX_HEADS];
       float logp = 0.f, ent = 0.f;
       int off = 0;
 #pragma unroll
       for (int hd = 0; hd < SRL_MAX_HEADS; ++hd) {
         if (hd < q.heads) {
           const int K = q.head_size[hd];
-          float mx = -INFINITY;
-          for (int k = 0; k < K; ++k) mx = fmaxf(mx, z[off + k]);
-          float se = 0.f;
-          for (int k = 0; k < K; ++k) {
-            const float ek = expf(z[off + k] - mx);
-            if (CACHE_E) ez[off + k] = ek;
-            se += ek;
+          float l, inv, hh;
+          if (K <= 32) {
+            SRL_HEAD_DISPATCH(head_forward, K, z + off, ez + off, K, l, inv, hh);
+          } else {
+            float mx = -INFINITY;
+            for (int k = 0; k < K; ++k) mx = fmaxf(mx, z[off + k]);
+            float se = 0.f;
+            for (int k = 0; k < K; ++k) {
+              const float ek = expf(z[off + k] - mx);
+              if (CACHE_E) ez[off + k] = ek;
+              se += ek;
+            }
+            l = mx + logf(se);
+            inv = 1.f / se;
+            hh = 0.f;
+            for (int k = 0; k < K; ++k) {
+              const float lp = fmaxf(z[off + k] - l, -FLT_MAX);
+              const float pk = CACHE_E ? ez[off + k] * inv : expf(lp);
+              hh -= pk * lp;
+            }
           }
-          const float l = mx + logf(se);
-          const float inv = 1.f / se;
-          float hh = 0.f;
-          for (int k = 0; k < K; ++k) {
-            const float lp = fmaxf(z[off + k] - l, -FLT_MAX);  // Categorical.entropy clamps at finfo.min
-            const float pk = CACHE_E ? ez[off + k] * inv : expf(lp);
-            hh -= pk * lp;
-          }
-          const int a = q.action[i * q.heads + hd];
           lse[hd] = l;
           rse[hd] = inv;
           hent[hd] = hh;
-          act[hd] = a;
-          logp += z[off + a] - l;
+          logp += z[off + act[hd]] - l;
           ent += hh;
           off += K;
         }
       }
-      const float vp = ldg_stream(pr.v_pred + i);
-      const float ol = __ldg(p.old_logp + os), rt = __ldg(p.ret + os), ad = __ldg(p.adv + os);
-      const float ov = h.clip_value ? __ldg(p.old_value + os) : 0.f;
-      const bool valid = __ldg(p.reset_next + os) == 0;
       float g_lp, g_v, g_en;
       RowSums rs;
       element<RuntimeCfg>(h, u, logp, vp, ent, ol, ov, rt, ad, valid, g_lp, g_v, g_en, rs);
@@ -147,26 +273,46 @@ __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const __grid_const
       for (int hd = 0; hd < SRL_MAX_HEADS; ++hd) {
         if (hd < q.heads) {
           const int K = q.head_size[hd];
-          for (int k = 0; k < K; ++k) {
-            const float lp = z[off + k] - lse[hd];
-            const float pk = CACHE_E ? ez[off + k] * rse[hd] : expf(lp);
-            // d logp / d z_k = [k == a] - p_k ;  d H / d z_k = -p_k (lp_k + H)
-            z[off + k] = g_lp * ((k == act[hd] ? 1.f : 0.f) - pk) - g_en * pk * (fmaxf(lp, -FLT_MAX) + hent[hd]);
+          if (K <= 32) {
+            SRL_HEAD_DISPATCH(head_backward, K, z + off, ez + off, K, act[hd], lse[hd], rse[hd], hent[hd], g_lp, g_en);
+          } else {
+            for (int k = 0; k < K; ++k) {
+              const float lp = z[off + k] - lse[hd];
+              const float pk = CACHE_E ? ez[off + k] * rse[hd] : expf(lp);
+              z[off + k] = g_lp * ((k == act[hd] ? 1.f : 0.f) - pk) - g_en * pk * (fmaxf(lp, -FLT_MAX) + hent[hd]);
+            }
           }
           off += K;
         }
       }
     }
-    __syncthreads();
-    float* dst = q.g_logits + i0 * SK;
-    for (int e = threadIdx.x; e < cnt * SK; e += 256) {
-      const int r = e / SK;
-      stg_stream(dst + e, srow[r * stride + (e - r * SK)]);
+    if (bulk) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the gradients above, before the bulk copy reads them
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(srow)),
+                     "r"(static_cast<uint32_t>(total) * 4u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the block may be overwritten by the next tile
+      }
+      __syncthreads();
+    } else {
+      __syncthreads();
+      for (int e0 = threadIdx.x; e0 < total; e0 += 256 * kStage) {
+        float v[kStage];
+#pragma unroll
+        for (int b = 0; b < kStage; ++b) v[b] = (e0 + b * 256 < total) ? srow[e0 + b * 256] : 0.f;
+#pragma unroll
+        for (int b = 0; b < kStage; ++b)
+          if (e0 + b * 256 < total) stg_stream(dst + e0 + b * 256, v[b]);
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   reduce_and_finalize(pr, h, acc, mask_sum, blockIdx.x, gridDim.x);
 }
+#undef SRL_HEAD_DISPATCH
 
 int fill_loss_hyper(const srl_ppo_hyper* hyper, const double* popart_mean_std, LossHyperDev& h) {
   SRL_REQUIRE(hyper != nullptr, SRL_ERR_INVALID_ARG, "ppo loss: null hyper pointer");
@@ -389,10 +535,10 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
                 "srl_ppo_loss_from_logits: head %d has no actions", i);
     sk += q.head_size[i];
   }
-  const size_t row_bytes = static_cast<size_t>(256) * (sk + 1) * sizeof(float);
-  SRL_REQUIRE(row_bytes <= 200 * 1024, SRL_ERR_UNSUPPORTED, "srl_ppo_loss_from_logits: sum K = %d too wide (max 199)", sk);
-  const bool cache_e = 2 * row_bytes <= 200 * 1024;  // both shared-memory rows fit: one exponential per logit
-  const size_t smem = cache_e ? 2 * row_bytes : row_bytes;
+  const size_t row_bytes = static_cast<size_t>(256) * sk * sizeof(float);  // dense [256, sum K] block
+  SRL_REQUIRE(row_bytes + 16 <= 200 * 1024, SRL_ERR_UNSUPPORTED, "srl_ppo_loss_from_logits: sum K = %d too wide (max 199)", sk);
+  const bool cache_e = 2 * row_bytes + 16 <= 200 * 1024;  // both blocks fit: one exponential per logit
+  const size_t smem = (cache_e ? 2 * row_bytes : row_bytes) + 16;  // + the mbarrier of the bulk copies
   q.heads = heads;
   q.SK = sk;
   q.logits = logits;
@@ -437,7 +583,15 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
     opted_in[dev] = true;
   }
   const long long tiles = (static_cast<long long>(T) * n + 255) / 256;
-  const long long cap = static_cast<long long>(sm_count()) * 8 < kMaxGrid ? static_cast<long long>(sm_count()) * 8 : kMaxGrid;
+  // one wave: as many CTAs as are resident with this much shared memory (2048 tiles on 1184 assumed slots were 1024 CTAs on
+  // the 740 real ones -- a second, partial wave)
+  int per_sm = 0;
+  if ((cache_e ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppo_loss_logits_kernel<true>, 256, smem)
+               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppo_loss_logits_kernel<false>, 256, smem)) != cudaSuccess ||
+      per_sm < 1)
+    per_sm = 1;
+  const long long slots = static_cast<long long>(sm_count()) * per_sm;
+  const long long cap = slots < kMaxGrid ? slots : kMaxGrid;
   // every CTA the same number of tiles (2048 tiles on 1184 slots would leave most CTAs one tile and the rest two)
   const long long per_cta = (tiles + cap - 1) / cap;
   const int grid = static_cast<int>((tiles + per_cta - 1) / per_cta);
