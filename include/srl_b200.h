@@ -221,10 +221,11 @@ enum srl_loss_out {
 };
 
 /* Bytes of one device scratch "slot" for a [T, n] problem: a 64-byte header + one float64[8] partial row per
- * CTA.  A slot must be ALL ZERO before its first use; every kernel that uses it leaves it all zero again (ticket
- * counter, published statistics, partial rows: "zero" means "not there yet" to the kernels that wait for a row), so a
- * deferred launch must be followed by srl_ppo_loss_finalize before the slot is used again.  Launches that may overlap
- * in time need distinct slots. */
+ * CTA.  A slot must be ALL ZERO before its first use; every kernel that uses it leaves its state zero again (ticket
+ * counter in bytes 0-3, published statistics in bytes 32-63, partial rows from byte 64: "zero" means "not there yet" to
+ * the kernels that wait for a word; bytes 4-31 hand n_rows / sum(mask) / the weights from a deferred launch to
+ * srl_ppo_loss_finalize and keep their last values), so a deferred launch must be followed by srl_ppo_loss_finalize
+ * before the slot is used again.  Launches that may overlap in time need distinct slots. */
 size_t srl_ppo_loss_workspace_bytes(int T, int n);
 
 /* Deferred finalisation: when srl_ppo_loss_fwd_bwd / srl_ppo_loss_from_logits are called with out == NULL they

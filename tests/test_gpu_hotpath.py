@@ -236,3 +236,73 @@ def test_full_size_cfg2_pack_and_batch_equal_per_minibatch_launches():
     a.run_device(pol, use_graph=True)
     torch.cuda.synchronize()
     assert torch.equal(a.grads_all, ref_grads)
+
+
+def _slot_state_words(ws):
+    """What must be zero between launches: the ticket (bytes 0-3), the published statistics (bytes 32-63) and every
+    partial row (bytes 64-); bytes 4-31 are the deferred mode's hand-over to srl_ppo_loss_finalize (n_rows, sum(mask),
+    weights) and keep their last values."""
+    w = ws.view(torch.int32).view(ws.shape[0], -1)
+    return int(w[:, 0].count_nonzero()) + int(w[:, 8:].count_nonzero())
+
+
+def test_workspace_slots_are_left_all_zero_and_steps_repeat_bit_for_bit():
+    """The loss workspace contract (include/srl_b200.h): every kernel leaves a slot's state zero -- the pair kernel's immediate
+    mode reads "zero" as "not there yet" for the published statistics and the partial rows -- whichever path used it last:
+    the batched launch, the per-minibatch deferred launches + srl_ppo_loss_finalize, and again the batched launch."""
+    import numpy as np
+    from srl_b200 import ops, synth
+    from srl_b200.hotpath import HotPath
+    cfg = synth.PathConfig("ws", T=16, B=256, epochs=2, minibatches=4, clip_value=True)
+    s = synth.make_sample_scalars(cfg, 3)
+    hp = HotPath(cfg.L, cfg.B, cfg.A, gamma=cfg.gamma, lmbda=cfg.lmbda, hyper=ops.LossHyper(clip_value=True), epochs=2,
+                 minibatches=4, seed=0)
+    hp.load_sample({k: torch.from_numpy(np.ascontiguousarray(v.reshape(cfg.L, cfg.N))) for k, v in s.items()})
+    g = torch.Generator().manual_seed(0)
+    pol_all = (torch.randn((2, 4, 3, cfg.T, hp.n_mb), generator=g) * 0.1).cuda()
+    pol = [[tuple(pol_all[e, j, q] for q in range(3)) for j in range(4)] for e in range(2)]
+    assert hp.fuse_stats and hp.pack is not None  # the pair kernel with its own statistics
+    hp.run_device(pol, use_graph=False)
+    torch.cuda.synchronize()
+    assert _slot_state_words(hp.workspace) == 0
+    first = (hp.grads_all.clone(), hp.out.clone())
+    hp.step_count = 0
+    hp.run_trainer_order(pol, use_graph=False)  # deferred launches + finalize on the same slots
+    torch.cuda.synchronize()
+    assert _slot_state_words(hp.workspace) == 0
+    # (the table adds the lanes in another order than the loss kernel's own statistics: last-bit differences)
+    torch.testing.assert_close(hp.grads_all, first[0], rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(hp.out[:, :10], first[1][:, :10], rtol=1e-6, atol=1e-9)
+    hp.step_count = 0
+    hp.run_device(pol, use_graph=False)
+    torch.cuda.synchronize()
+    assert _slot_state_words(hp.workspace) == 0
+    assert torch.equal(hp.grads_all, first[0]) and torch.equal(hp.out, first[1])
+
+
+def test_scan_first_and_permutation_first_orders_agree(monkeypatch):
+    """K2 -> K5a -> K4 (the permutation kernel beside the scan, completing behind it) and round 1's K5a -> K2 -> K4 produce
+    the same step, bit for bit, eagerly and from a graph."""
+    import numpy as np
+    from srl_b200 import ops, synth
+    from srl_b200.hotpath import HotPath
+    cfg = synth.PathConfig("ord", T=32, B=512, epochs=2, minibatches=4, clip_value=True)
+    s = synth.make_sample_scalars(cfg, 5)
+    g = torch.Generator().manual_seed(1)
+    res = {}
+    for order in ("0", "1"):
+        monkeypatch.setenv("SRL_PERM_FIRST", order)
+        hp = HotPath(cfg.L, cfg.B, cfg.A, gamma=cfg.gamma, lmbda=cfg.lmbda, hyper=ops.LossHyper(clip_value=True), epochs=2,
+                     minibatches=4, seed=7)
+        hp.perm.fill_(-1)
+        hp.load_sample({k: torch.from_numpy(np.ascontiguousarray(v.reshape(cfg.L, cfg.N))) for k, v in s.items()})
+        g.manual_seed(1)
+        pol_all = (torch.randn((2, 4, 3, cfg.T, hp.n_mb), generator=g) * 0.1).cuda()
+        pol = [[tuple(pol_all[e, j, q] for q in range(3)) for j in range(4)] for e in range(2)]
+        for use_graph in (False, True, True):
+            hp.run_device(pol, use_graph=use_graph)
+            hp.step_count = 0
+            torch.cuda.synchronize()
+            cur = (hp.perm.clone(), hp.adv.clone(), hp.grads_all.clone(), hp.out.clone())
+            for a, b in zip(cur, res.setdefault("ref", cur)):
+                assert torch.equal(a, b)

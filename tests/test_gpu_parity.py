@@ -425,8 +425,14 @@ def test_loss_two_rank_statistics(ops):
 
 
 def test_loss_from_logits_matches_oracle(ops):
-    for cfg_name in ("cfg1_atari_cpu", "cfg5_hns_scale"):
-        cfg = synth.CONFIGS[cfg_name]
+    """Atari (one head of 18: registers, instantiation of 20), hide-and-seek (five narrow heads), SMAC's 36 actions and a
+    mixed set (heads wider than 32 keep the shared-memory row walk), on 2 full tiles + a partial one (bulk copies and the
+    element-wise staging of the last tile)."""
+    import dataclasses
+    cases = [synth.CONFIGS["cfg1_atari_cpu"], synth.CONFIGS["cfg5_hns_scale"],
+             dataclasses.replace(synth.CONFIGS["cfg1_atari_cpu"], num_actions=(36,)),
+             dataclasses.replace(synth.CONFIGS["cfg1_atari_cpu"], num_actions=(4, 33, 7, 32))]
+    for cfg in cases:
         T, n = 20, 37
         small = synth.PathConfig("fl", T=T, B=n, p_end=0.05, clip_value=cfg.clip_value, dual_clip=cfg.dual_clip)
         s = synth.make_sample_scalars(small, 13)
