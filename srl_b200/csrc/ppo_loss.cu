@@ -73,6 +73,9 @@ struct LogitsParams {
 //    of 4, 8, ... 32 registers (loops unrolled, addresses immediate); e_k = exp(z_k - max) is kept in a second dense block
 //    when both fit (CACHE_E), so the gradient pass needs no exponential; wider heads keep the row walk;
 //  * the sample side is loaded before the passes, so its DRAM round trip hides under them.
+#ifndef SRL_K4B_MIN_BLOCKS
+#define SRL_K4B_MIN_BLOCKS 2
+#endif
 constexpr int kStage = 9;  // manual staging batch per thread (last, partial tile only)
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -141,7 +144,7 @@ __device__ __forceinline__ void head_backward(float* z, const float* ez, int K, 
   } while (0)
 
 template <bool CACHE_E>
-__global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const __grid_constant__ LogitsParams q) {
+__global__ void __launch_bounds__(256, SRL_K4B_MIN_BLOCKS) ppo_loss_logits_kernel(const __grid_constant__ LogitsParams q) {
   extern __shared__ __align__(128) float srow[];  // [256 * SK] dense (+ [256 * SK] with CACHE_E), then the mbarrier
   const LossShared& p = q.s;
   const Problem& pr = q.pr;
@@ -225,12 +228,15 @@ __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const __grid_const
     if (mine) {
       float* z = srow + threadIdx.x * SK;
       float* ez = erow + threadIdx.x * SK;
+      // (the head loops are NOT unrolled: with the dispatch over eight widths inlined in each of SRL_MAX_HEADS slots the kernel
+      // was 128 copies of the passes and spent 27 % of its warp samples waiting for instructions; the per-head scalars
+      // below are indexed at run time and live in local memory -- four words per head)
       float lse[SRL_MAX_HEADS], hent[SRL_MAX_HEADS], rse[SRL_MAX_HEADS];
       float logp = 0.f, ent = 0.f;
       int off = 0;
-#pragma unroll
-      for (int hd = 0; hd < SRL_MAX_HEADS; ++hd) {
-        if (hd < q.heads) {
+#pragma unroll 1
+      for (int hd = 0; hd < q.heads; ++hd) {
+        {
           const int K = q.head_size[hd];
           float l, inv, hh;
           if (K <= 32) {
@@ -269,9 +275,9 @@ __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const __grid_const
       if (q.logp_out) q.logp_out[i] = logp;
       if (q.entropy_out) q.entropy_out[i] = ent;
       off = 0;
-#pragma unroll
-      for (int hd = 0; hd < SRL_MAX_HEADS; ++hd) {
-        if (hd < q.heads) {
+#pragma unroll 1
+      for (int hd = 0; hd < q.heads; ++hd) {
+        {
           const int K = q.head_size[hd];
           if (K <= 32) {
             SRL_HEAD_DISPATCH(head_backward, K, z + off, ez + off, K, act[hd], lse[hd], rse[hd], hent[hd], g_lp, g_en);
