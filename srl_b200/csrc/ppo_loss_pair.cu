@@ -1,28 +1,22 @@
 // K4, pack form: the kernel behind every permuted minibatch (4 epochs x 8 minibatches of cfg2 in one launch, or one
-// minibatch per launch in the trainer's dependency order).  Replaces the row-tile kernel of round 1 for this form; what the
-// profiles of that kernel said (profiles/r1d_ncu_cfg2.txt, VERDICT r1 "What's weak" 3) and what is different here:
+// minibatch per launch in the trainer's dependency order).  It replaced the row-tile kernel of round 1 for this form; what the
+// profiles said along the way (profiles/r1d_ncu_cfg2.txt, profiles/r2_notes.md, the device timeline of
+// profiles/microbench/timeline.py) and what the kernel does about it:
 //
-//  * every CTA of the one-wave grid started together and stayed in lockstep: a burst of loads for one row, then ~500
-//    instructions of arithmetic per warp with nothing in flight, five times over -- load time, issue time and latency
-//    ADDED instead of overlapping (26.6 us for 86 MB).  Here a thread owns 2 adjacent lanes x 2 rows per step and the
-//    loads of the next steps are in flight (asynchronous copies into its own shared-memory slots) under the arithmetic.
-//  * the pack was one 16-byte item per transition: a per-environment permutation fetched a 32-byte sector for 16 bytes
-//    (L2 -> L1: 117 MB for 61 MB of use).  K2 now interleaves row pairs -- pack2[t / 2][lane] = 32 bytes = {row t, row t+1}
-//    of {old_logp, value, ret, mask ? adv : NaN} -- and a thread fetches its lane's pair as one 32-byte sector: every
-//    sector that moves is used whole.
-//  * every one of the 26 row-group CTAs of a minibatch re-gathered K2's per-lane sums, three 8-byte gathers per lane out
-//    of three 32-byte sectors (~40 MB).  K2 now also writes them as one 32-byte item per lane (lane_aos) and a CTA adds
-//    them with one 256-bit gather per lane.
-//  * the grid was (column tile, row group, problem) sized to one wave: 832 CTAs on 888 slots, and 9.25 row groups per
-//    column do not divide 128 rows.  Here a problem's (column tile, row pair) units are numbered in one line and dealt to
-//    its CTAs in equal runs (+-1 unit), for any shape; small CTAs (64 threads) keep the units fine.
-//  * the epilogue held every CTA through three block barriers, eight fences and an atomic round trip; here the warps
-//    leave after one barrier and warp 0 alone writes the partial row and takes the ticket.
-//
-// A problem's partial rows are its CTAs, folded in CTA order by the last one to arrive (ticket) -- deterministic for a
-// given launch shape, as before.  (First version of this file: one line of units over ALL problems; the 16 of 592 CTAs
-// whose run crossed a problem boundary paid prologue and epilogue twice and set the kernel's duration -- ncu: slowest SM
-// 51.6 K active cycles, average 36.7 K, profiles/r2_notes.md.)
+//  * round 1: every CTA of the one-wave grid in lockstep -- a burst of loads for one row, then ~500 instructions of
+//    arithmetic per warp with nothing in flight, five times over (26.6 us for 86 MB).  Here a thread owns 2 adjacent lanes x
+//    2 rows per step, the next step's loads are in registers before this step's arithmetic, and 24 threads of the CTA
+//    request the policy-side lines two steps ahead from L2 (prefetch.global.L2).
+//  * the pack was one 16-byte item per transition: a per-environment permutation fetched a 32-byte sector for 16 bytes.
+//    K2 interleaves row pairs -- pack2[t / 2][lane] = 32 bytes = {row t, row t+1} of {old_logp, value, ret, mask ? adv :
+//    NaN} -- and a thread fetches its lane's pair as one 256-bit load: every sector that moves is used whole.
+//  * the minibatch statistics: ONE CTA per problem adds K2's per-lane sums (lane_aos, one 256-bit gather per lane),
+//    exchanges them with the other ranks when there are any, and publishes them in the workspace slot; the others wait.
+//  * the grid is (problems, slices): a problem's (column tile, row pair) units are numbered in one line and dealt to its
+//    CTAs in equal runs (+-1 unit), for any shape; 64-thread CTAs keep the units fine; the whole grid is one wave.
+//  * the tail: one block barrier, one partial row per CTA, no fence, no atomic -- published words validate themselves
+//    (ppo_loss.cuh: box / unbox) and the problem's first CTA folds the rows by looking at them, in CTA order
+//    (deterministic for a given launch shape).
 #include <stdlib.h>
 
 #include "ppo_loss.cuh"

@@ -8,9 +8,11 @@ Step structure (reference: MultiAgentPPO.step, legacy/algorithm/ppo/mappo.py:219
 
     load_sample        H2D of the six scalar leaves                      (api/trainer.py:215-217)
     advantages         K2 GAE scan -> adv, ret, loss pack, per-lane sums (mappo.py:252-257)
-                       K5 Philox permutations for all epochs, on a parallel branch (new)
-                       group statistics for the batch and every minibatch; with several ranks the same kernel
-                       exchanges the table over NVLink peer memory       (utils.py:58-61,121-124)
+                       K5a Philox permutations for all epochs, launched behind the scan and running beside it
+                       (programmatic dependent launch; a parallel branch without it)   (new)
+                       group statistics for the batch and every minibatch -- lazily when the batched loss adds its own;
+                       with several ranks the same kernel exchanges the table over NVLink peer memory
+                                                                          (utils.py:58-61,121-124)
     per epoch          PopArt update                                      (mappo.py:263-264)
       all minibatches  K4 fused loss forward+backward in ONE launch, gather fused in   (mappo.py:270-274)
                        (one GPU, no PopArt, minibatches <= 1024 lanes: K4 adds its own minibatch statistics and the
@@ -207,9 +209,9 @@ class HotPath:
         when distributed)."""
         lf = self.leaf
         main = torch.cuda.current_stream()
-        # The permutations do not depend on the scan.  With programmatic dependent launch the order K5a -> K2 -> K4 on
-        # ONE stream already overlaps (K2 is launched beside K5a and only joins it when it ends; K4 becomes resident under
-        # K2): no fork / join, three nodes in a line in the step graph.  Without it: a parallel branch.
+        # The permutations do not depend on the scan.  With programmatic dependent launch the order K2 -> K5a -> K4 on
+        # ONE stream already overlaps (K5a is launched beside K2 and only completes when K2 has; K4 becomes resident under
+        # both): no fork / join, three nodes in a line in the step graph.  Without it: a parallel branch.
         inline_perm = self.minibatches > 1 and permute and ops.pdl_enabled() and not cached
         fork_perm = self.minibatches > 1 and permute and not inline_perm
         perm_first = inline_perm and os.environ.get("SRL_PERM_FIRST") == "1"  # A/B knob: round 1's order K5a -> K2 -> K4
