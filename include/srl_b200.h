@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SRL_B200_ABI_VERSION 7
+#define SRL_B200_ABI_VERSION 8
 
 typedef void* srl_stream_t; /* cudaStream_t */
 
@@ -103,6 +103,18 @@ int srl_gae_scan(const float* reward,          /* [L, N]; row L-1 is ignored    
                  double* lane_aos,  /* [N, 4] out or NULL */
                  float* pack,       /* [ceil(L/2), N, 2, 4] out or NULL */
                  srl_stream_t stream);
+
+/* srl_gae_scan + the step's minibatch permutations (== srl_philox_perm(perm_seed, perm_epoch, perm_n_epochs, perm_n_env,
+ * perm_group, perm_out), bit for bit) in the same launch where the scan kernel chosen for this shape can: its worker
+ * threads compute them while they wait for their first tile (the warp-specialised kernel of small batches -- the shape
+ * whose step is latency-bound).  Otherwise the stand-alone permutation kernel is launched behind the scan.  *fused (host,
+ * may be NULL) says which: 1 = one launch.  New capability, like srl_philox_perm. */
+int srl_gae_scan_perm(const float* reward, const float* value, const uint8_t* done, const uint8_t* truncated,
+                      const uint8_t* on_reset, const float* vtrace_new_logp, const float* vtrace_old_logp,
+                      const double* popart_mean_std, const float* old_logp, int L, int N, int row_lo, int row_hi,
+                      double gamma, double lmbda, double rho, double c, float* adv, float* ret, double* lane_part,
+                      double* lane_aos, float* pack, uint64_t perm_seed, uint32_t perm_epoch, int perm_n_epochs,
+                      int perm_n_env, int perm_group, int32_t* perm_out, int* fused, srl_stream_t stream);
 
 /* The general form of the same scan: everything modules.gae_trace (legacy/algorithm/modules/gae.py:8-97) accepts
  * beyond what MultiAgentPPO passes -- vector critics (reward / value / adv / ret are [.., N, critic_dim], the flags stay

@@ -19,7 +19,7 @@ SRL_LANE_PART = 8
 SRL_LOSS_OUT_LEN = 16
 SRL_MAX_LEAVES = 32
 SRL_MAX_HEADS = 8
-ABI_VERSION = 7
+ABI_VERSION = 8
 SRL_MAX_LOSS_BATCH = 32
 
 # enum srl_loss_out
@@ -78,6 +78,9 @@ SIGNATURES = {
     "srl_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "srl_gae_scan": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double] +
                      [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "srl_gae_scan_perm": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double] +
+                          [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] +
+                          [ctypes.c_uint64, ctypes.c_uint32, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "srl_gae_trace": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_double, c_double, c_double, c_double, c_int,
                               c_void_p, c_void_p, c_void_p]),
     "srl_traj_gae": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p]),

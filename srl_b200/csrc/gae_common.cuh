@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "perm.cuh"
+
 namespace srl {
 
 struct GaeParams {
@@ -22,6 +24,7 @@ struct GaeParams {
   float* pack;  // pair-interleaved [ceil(L/2)][N][2] float4 or null (include/srl_b200.h)
   int L, N, row_lo, row_hi;
   double gamma, gamma_lmbda, rho, c;
+  PermJob perm;  // srl_gae_scan_perm: a permutation computed on the side (gae_scan_ws.cu only); out == nullptr: none
 };
 
 // Position (in float4 items) of transition (t, lane) in the loss pack: the two rows of a row pair sit next to each other,

@@ -281,12 +281,66 @@ int launch(const GaeParams& p, cudaStream_t st) {
 }  // namespace
 }  // namespace srl
 
+namespace srl {
+namespace {
+int gae_scan_impl(const float* reward, const float* value, const uint8_t* done, const uint8_t* truncated,
+                  const uint8_t* on_reset, const float* vtrace_new_logp, const float* vtrace_old_logp,
+                  const double* popart_mean_std, const float* old_logp, int L, int N, int row_lo, int row_hi, double gamma,
+                  double lmbda, double rho, double c, float* adv, float* ret, double* lane_part, double* lane_aos, float* pack,
+                  const PermJob* job, int* fused, srl_stream_t stream);
+}
+}  // namespace srl
+
 extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8_t* done, const uint8_t* truncated,
                             const uint8_t* on_reset, const float* vtrace_new_logp, const float* vtrace_old_logp,
                             const double* popart_mean_std, const float* old_logp, int L, int N, int row_lo,
                             int row_hi, double gamma, double lmbda, double rho, double c, float* adv, float* ret,
                             double* lane_part, double* lane_aos, float* pack, srl_stream_t stream) {
+  return srl::gae_scan_impl(reward, value, done, truncated, on_reset, vtrace_new_logp, vtrace_old_logp, popart_mean_std,
+                            old_logp, L, N, row_lo, row_hi, gamma, lmbda, rho, c, adv, ret, lane_part, lane_aos, pack, nullptr,
+                            nullptr, stream);
+}
+
+extern "C" int srl_gae_scan_perm(const float* reward, const float* value, const uint8_t* done, const uint8_t* truncated,
+                                 const uint8_t* on_reset, const float* vtrace_new_logp, const float* vtrace_old_logp,
+                                 const double* popart_mean_std, const float* old_logp, int L, int N, int row_lo,
+                                 int row_hi, double gamma, double lmbda, double rho, double c, float* adv, float* ret,
+                                 double* lane_part, double* lane_aos, float* pack, uint64_t perm_seed, uint32_t perm_epoch,
+                                 int perm_n_epochs, int perm_n_env, int perm_group, int32_t* perm_out, int* fused,
+                                 srl_stream_t stream) {
   using namespace srl;
+  SRL_REQUIRE(perm_out != nullptr && perm_n_env >= 1 && perm_group >= 1 && perm_n_epochs >= 1 && perm_n_epochs <= 65535,
+              SRL_ERR_INVALID_ARG, "srl_gae_scan_perm: need a permutation output, n_env >= 1, group >= 1, 1 <= n_epochs <= 65535");
+  SRL_REQUIRE(static_cast<long long>(perm_n_env) * perm_group < (1ll << 31), SRL_ERR_UNSUPPORTED,
+              "srl_gae_scan_perm: n_env * group must fit int32");
+  PermJob job;
+  job.seed_lo = static_cast<uint32_t>(perm_seed & 0xffffffffull);
+  job.seed_hi = static_cast<uint32_t>(perm_seed >> 32);
+  job.epoch0 = perm_epoch;
+  job.n_epochs = perm_n_epochs;
+  job.n_env = perm_n_env;
+  job.group = perm_group;
+  job.bits = perm_bits(perm_n_env);
+  job.out = perm_out;
+  int did = 0;
+  const int rc = gae_scan_impl(reward, value, done, truncated, on_reset, vtrace_new_logp, vtrace_old_logp, popart_mean_std,
+                               old_logp, L, N, row_lo, row_hi, gamma, lmbda, rho, c, adv, ret, lane_part, lane_aos, pack, &job,
+                               &did, stream);
+  if (rc != SRL_OK) return rc;
+  if (fused != nullptr) *fused = did;
+  if (did) return SRL_OK;
+  // the scan kernel chosen for this shape does not compute permutations: the stand-alone kernel, behind the scan
+  return srl_philox_perm(perm_seed, perm_epoch, perm_n_epochs, perm_n_env, perm_group, perm_out, stream);
+}
+
+namespace srl {
+namespace {
+int gae_scan_impl(const float* reward, const float* value, const uint8_t* done, const uint8_t* truncated,
+                  const uint8_t* on_reset, const float* vtrace_new_logp, const float* vtrace_old_logp,
+                  const double* popart_mean_std, const float* old_logp, int L, int N, int row_lo, int row_hi, double gamma,
+                  double lmbda, double rho, double c, float* adv, float* ret, double* lane_part, double* lane_aos, float* pack,
+                  const PermJob* job, int* fused, srl_stream_t stream) {
+
   SRL_REQUIRE(L >= 2 && N >= 1, SRL_ERR_INVALID_ARG, "srl_gae_scan: need L >= 2 and N >= 1 (got L=%d N=%d)", L, N);
   SRL_REQUIRE(reward && value && done && truncated && on_reset && adv && ret, SRL_ERR_INVALID_ARG,
               "srl_gae_scan: null tensor pointer");
@@ -322,6 +376,7 @@ extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8
   p.gamma_lmbda = gamma * lmbda;  // python evaluates gamma * lmbda first (gae.py:87)
   p.rho = rho;
   p.c = c;
+  p.perm.out = nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   // Three kernels, picked by how many 32-lane groups the batch has (SRL_GAE_PATH=tile|tma|ws, read once, overrides:
@@ -348,7 +403,13 @@ extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8
   if (path_env == 2) use_tma = gae_tma_eligible(p), use_ws = false;
   if (path_env == 3) use_ws = gae_ws_eligible(p), use_tma = use_tma && !use_ws;
   if (use_tma) return launch_gae_tma(p, st);
-  if (use_ws) return launch_gae_ws(p, st);
+  if (use_ws) {
+    if (job != nullptr) {  // the warp-specialised kernel's workers compute the permutation while they wait for data
+      p.perm = *job;
+      *fused = 1;
+    }
+    return launch_gae_ws(p, st);
+  }
 
   // General path (any N, any alignment): shared-memory tile kernel below.
   // Lane-tile width: the widest tile that (a) fits shared memory and (b) still gives every SM work.
@@ -371,3 +432,5 @@ extern "C" int srl_gae_scan(const float* reward, const float* value, const uint8
   if (lw == 16) return launch<16, false>(p, st);
   return launch<8, false>(p, st);
 }
+}  // namespace
+}  // namespace srl

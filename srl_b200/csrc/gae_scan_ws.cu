@@ -163,6 +163,27 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
       pa_std = p.popart[1];
     }
     const double gamma = p.gamma;
+    // srl_gae_scan_perm: the step's minibatch permutations, computed by the worker threads of all CTAs while their first
+    // chunk is in flight (~1.3 us in which they would only wait).  One launch and one completion hop less between the scan
+    // and the loss than with the permutation kernel beside the scan; bit-identical to srl_philox_perm (perm.cuh).
+    if (p.perm.out != nullptr) {
+      const long long total = static_cast<long long>(p.perm.n_epochs) * p.perm.n_env;
+      const int wt = w * 32 + lane;
+      uint32_t have_epoch = 0xffffffffu;
+      PermKeys keys;
+      for (long long g = static_cast<long long>(blockIdx.x) * (32 * kW) + wt; g < total;
+           g += static_cast<long long>(gridDim.x) * (32 * kW)) {
+        const uint32_t ep = static_cast<uint32_t>(g / p.perm.n_env);
+        const uint32_t e = static_cast<uint32_t>(g - static_cast<long long>(ep) * p.perm.n_env);
+        if (ep != have_epoch) {
+          keys = perm_keys(p.perm.seed_lo, p.perm.seed_hi, p.perm.epoch0 + ep, p.perm.bits);
+          have_epoch = ep;
+        }
+        const uint32_t x = perm_at(e, static_cast<uint32_t>(p.perm.n_env), keys);
+        int32_t* o = p.perm.out + (static_cast<size_t>(ep) * p.perm.n_env + e) * p.perm.group;
+        for (int a = 0; a < p.perm.group; ++a) o[a] = static_cast<int32_t>(x) * p.perm.group + a;
+      }
+    }
     double s1 = 0, s2 = 0, s3 = 0, s4 = 0;
     int cnt = 0, n_dn = 0, n_tr = 0;
 

@@ -1,53 +1,8 @@
 // K5a: Philox-keyed permutation of the environment axis (new capability).
 // Spec = oracle/ref_math.py:philox_perm_ref (numpy); this file must match it bit for bit.
-#include "common.cuh"
+#include "perm.cuh"
 
 namespace srl {
-
-struct Philox4 {
-  uint32_t c[4];
-};
-
-// Philox4x32-10, Salmon et al. SC'11 (Random123); constants as published.
-__host__ __device__ __forceinline__ Philox4 philox4x32_10(Philox4 ctr, uint32_t k0, uint32_t k1) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = static_cast<uint64_t>(M0) * ctr.c[0];
-    const uint64_t p1 = static_cast<uint64_t>(M1) * ctr.c[2];
-    Philox4 n;
-    n.c[0] = static_cast<uint32_t>(p1 >> 32) ^ ctr.c[1] ^ k0;
-    n.c[1] = static_cast<uint32_t>(p1);
-    n.c[2] = static_cast<uint32_t>(p0 >> 32) ^ ctr.c[3] ^ k1;
-    n.c[3] = static_cast<uint32_t>(p0);
-    ctr = n;
-    k0 += W0;
-    k1 += W1;
-  }
-  return ctr;
-}
-
-struct PermKeys {
-  uint32_t rk[8];
-  uint32_t lb, lmask, hmask;
-};
-
-__host__ __device__ __forceinline__ uint32_t feistel8(uint32_t x, const PermKeys& k) {
-  uint32_t lo = x & k.lmask, hi = (x >> k.lb) & k.hmask;
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    if ((r & 1) == 0) {
-      uint32_t f = static_cast<uint32_t>((static_cast<uint64_t>(0xD2511F53u) * (lo ^ k.rk[r])) >> 32);
-      f ^= (lo * 0x9E3779B9u) >> 16;
-      hi = (hi ^ f) & k.hmask;
-    } else {
-      uint32_t f = static_cast<uint32_t>((static_cast<uint64_t>(0xCD9E8D57u) * (hi ^ k.rk[r])) >> 32);
-      f ^= (hi * 0xBB67AE85u) >> 16;
-      lo = (lo ^ f) & k.lmask;
-    }
-  }
-  return (hi << k.lb) | lo;
-}
 
 namespace {
 
@@ -109,9 +64,7 @@ extern "C" int srl_philox_perm(uint64_t seed, uint32_t epoch, int n_epochs, int 
   SRL_REQUIRE(out != nullptr, SRL_ERR_INVALID_ARG, "srl_philox_perm: null output");
   SRL_REQUIRE(static_cast<long long>(n_env) * group < (1ll << 31), SRL_ERR_UNSUPPORTED,
               "srl_philox_perm: n_env * group must fit int32");
-  int bits = 0;
-  while ((1ll << bits) < n_env) ++bits;  // == (n_env - 1).bit_length()
-  if (bits < 2) bits = 2;
+  const int bits = perm_bits(n_env);
   const int threads = 256;
   int grid = (n_env + threads - 1) / threads;
   const int cap = sm_count() * 8;

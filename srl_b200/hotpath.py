@@ -157,6 +157,7 @@ class HotPath:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_a: Optional[torch.cuda.CUDAGraph] = None
         self._graph_pol = None
+        self._perm_fused = False
         self.launches_per_step = 0
 
     # ------------------------------------------------------------------------------------------
@@ -222,6 +223,7 @@ class HotPath:
             with torch.cuda.stream(self._perm_stream):
                 self.permute()
         self.pack_valid = False
+        job = None
         if cached:
             ops.lane_stats(self.adv, self.ret, lf["done"], lf["truncated"], lf["on_reset"], self.row_lo, self.row_hi,
                            lane_part=self.lane_part)
@@ -232,10 +234,19 @@ class HotPath:
             elif self.pack is not None:
                 kw = dict(old_logp=lf["old_logp"], pack=self.pack, lane_aos=self.lane_aos)
                 self.pack_valid = True
+            if inline_perm and not perm_first and os.environ.get("SRL_PERM_FUSED", "1") != "0":
+                # the scan kernel's own idle threads compute the permutations (one launch and one completion hop less
+                # between the scan and the loss); where the scan kernel for this shape cannot, the stand-alone kernel runs
+                # behind the scan as before
+                blk = self.shuffle_block
+                job = dict(seed=self.seed + self.step_count, epoch=0, n_epochs=self.epochs, n_env=self.B // blk,
+                           group=self.A * blk, out=self.perm)
+                kw["perm_job"] = job
             ops.gae_scan(lf["reward"], lf["value"], lf["done"], lf["truncated"], lf["on_reset"], self.gamma, self.lmbda,
                          row_lo=self.row_lo, row_hi=self.row_hi, popart_mean_std=self.popart_mean_std(), adv=self.adv,
                          ret=self.ret, lane_part=self.lane_part, **kw)
-        if inline_perm and not perm_first:
+            self._perm_fused = bool(job and job.get("fused"))
+        if inline_perm and not perm_first and job is None:
             # K2 -> K5a -> K4 on one stream: the scan is the long pole and starts first; the permutation kernel starts beside
             # it (programmatic launch) and only completes once the scan has, so the loss kernel behind it waits for both
             self.permute()
@@ -527,8 +538,8 @@ class HotPath:
     def count_launches(self) -> int:
         """Kernels of this library launched by one step (the claim behind bench.py's gpu_launches)."""
         n = 1 if self.fuse_stats else 2  # gae_scan (+ group_stats unless the batched loss adds its own statistics)
-        if self.minibatches > 1:
-            n += 1  # all epochs' permutations
+        if self.minibatches > 1 and not self._perm_fused:
+            n += 1  # all epochs' permutations (computed inside the scan kernel when it can: advantages())
         if self._immediate:
             per_launch = 32  # SRL_MAX_LOSS_BATCH
             if self.popart:

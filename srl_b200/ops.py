@@ -71,7 +71,7 @@ def gae_scan(reward, value, done, truncated, on_reset, gamma: float, lmbda: floa
              rho: float = 1.0, c: float = 1.0, adv: Optional[torch.Tensor] = None,
              ret: Optional[torch.Tensor] = None, lane_part: Optional[torch.Tensor] = None, want_stats: bool = True,
              old_logp: Optional[torch.Tensor] = None, pack: Optional[torch.Tensor] = None,
-             lane_aos: Optional[torch.Tensor] = None):
+             lane_aos: Optional[torch.Tensor] = None, perm_job: Optional[dict] = None):
     """GAE + value target + zero padding row + per-lane statistics in one launch.
 
     reward/value float32 and done/truncated/on_reset uint8, all `[L, N(, 1)]`; returns
@@ -80,6 +80,10 @@ def gae_scan(reward, value, done, truncated, on_reset, gamma: float, lmbda: floa
     sample side as one 16-byte item per transition, {old_logp, value, ret, mask ? adv : NaN}, the two rows of a row pair
     next to each other (see include/srl_b200.h; `unpack_rows` gives the `[L, N, 4]` view back).
     `lane_aos` (float64 `[N, 4]`): rows 0..2 of lane_part once more as one 32-byte item per lane.
+    `perm_job` (dict: seed, epoch, n_epochs, n_env, group, out int32 `[n_epochs, n_env * group]`): the step's minibatch
+    permutations (== `philox_perm` with the same arguments, bit for bit) computed by the scan kernel's own idle threads where
+    the kernel chosen for this shape can (srl_gae_scan_perm), by the stand-alone kernel behind the scan otherwise; the
+    dict's key "fused" says which (True / False).
     Reference: MultiAgentPPO._compute_adv_and_value_target (mappo.py:118-144) + F.pad (mappo.py:254-256).
     """
     L, N = _rows_lanes(value)
@@ -121,11 +125,22 @@ def gae_scan(reward, value, done, truncated, on_reset, gamma: float, lmbda: floa
         _check(lane_aos, torch.float64, "lane_aos")
         if lane_part is None or tuple(lane_aos.shape) != (N, 4):
             raise ValueError(f"lane_aos needs lane_part and shape {(N, 4)}, got {tuple(lane_aos.shape)}")
-    _lib.call("srl_gae_scan", _ptr(reward), _ptr(value), _ptr(done), _ptr(truncated), _ptr(on_reset),
-              _ptr(vtrace_new_logp), _ptr(vtrace_old_logp), _ptr(popart_mean_std),
-              _ptr(old_logp) if pack is not None else None, L, N, int(row_lo), int(row_hi),
-              float(gamma), float(lmbda), float(rho), float(c), _ptr(adv), _ptr(ret), _ptr(lane_part), _ptr(lane_aos),
-              _ptr(pack), _stream())
+    args = (_ptr(reward), _ptr(value), _ptr(done), _ptr(truncated), _ptr(on_reset),
+            _ptr(vtrace_new_logp), _ptr(vtrace_old_logp), _ptr(popart_mean_std),
+            _ptr(old_logp) if pack is not None else None, L, N, int(row_lo), int(row_hi),
+            float(gamma), float(lmbda), float(rho), float(c), _ptr(adv), _ptr(ret), _ptr(lane_part), _ptr(lane_aos),
+            _ptr(pack))
+    if perm_job is None:
+        _lib.call("srl_gae_scan", *args, _stream())
+    else:
+        out = _check(perm_job["out"], torch.int32, "perm_job['out']")
+        n_ep, n_env, group = int(perm_job["n_epochs"]), int(perm_job["n_env"]), int(perm_job.get("group", 1))
+        if out.numel() != n_ep * n_env * group:
+            raise ValueError(f"perm_job['out'] must hold [n_epochs, n_env * group] = {n_ep * n_env * group} int32")
+        fused = ctypes.c_int(0)
+        _lib.call("srl_gae_scan_perm", *args, ctypes.c_uint64(int(perm_job["seed"]) & (2 ** 64 - 1)),
+                  ctypes.c_uint32(int(perm_job.get("epoch", 0))), n_ep, n_env, group, _ptr(out), ctypes.byref(fused), _stream())
+        perm_job["fused"] = bool(fused.value)
     return adv, ret, lane_part
 
 

@@ -207,3 +207,25 @@ def test_gather_to_chunk_equals_gather_then_to_chunk(T, B, C, n, D):
         assert torch.equal(got.cpu(), want)
     with pytest.raises(IndexError, match="must be a multiple of"):
         ops.gather_to_chunk(torch.zeros(7, 4, 2).cuda(), idx[:2].cuda() % 4, 2)
+
+
+@pytest.mark.parametrize("N,n_env,group,epochs", [(4096, 4096, 1, 4), (1024, 100, 3, 2), (512, 37, 1, 5), (64, 64, 1, 2), (20480, 2048, 10, 1)])
+def test_scan_with_permutation_on_the_side_equals_philox_perm(N, n_env, group, epochs):
+    """srl_gae_scan_perm: the permutations computed by the scan kernel's worker threads (warp-specialised kernel: 256 <= N <
+    ~9500 lanes here) or by the stand-alone kernel behind the scan (the other shapes) are srl_philox_perm's, bit for bit, and
+    the scan's own outputs do not change."""
+    from srl_b200 import ops
+    L = 33
+    g = torch.Generator().manual_seed(N + n_env)
+    f = lambda: torch.randn((L, N), generator=g).cuda()
+    u = lambda p: (torch.rand((L, N), generator=g) < p).to(torch.uint8).cuda()
+    reward, value, done, trunc, reset = f(), f(), u(0.02), u(0.01), u(0.03)
+    want = ops.philox_perm(77, 3, n_env, group, n_epochs=epochs)
+    a0, r0, p0 = ops.gae_scan(reward, value, done, trunc, reset, 0.99, 0.95)
+    out = torch.full((epochs, n_env * group), -7, dtype=torch.int32, device="cuda")
+    job = dict(seed=77, epoch=3, n_epochs=epochs, n_env=n_env, group=group, out=out)
+    a1, r1, p1 = ops.gae_scan(reward, value, done, trunc, reset, 0.99, 0.95, perm_job=job)
+    torch.cuda.synchronize()
+    assert torch.equal(out, want.view(epochs, -1))
+    assert torch.equal(a0, a1) and torch.equal(r0, r1) and torch.equal(p0, p1)
+    assert job["fused"] == (256 <= N < 2 * 148 * 32)
