@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SRL_B200_ABI_VERSION 8
+#define SRL_B200_ABI_VERSION 9
 
 typedef void* srl_stream_t; /* cudaStream_t */
 
@@ -107,14 +107,23 @@ int srl_gae_scan(const float* reward,          /* [L, N]; row L-1 is ignored    
 /* srl_gae_scan + the step's minibatch permutations (== srl_philox_perm(perm_seed, perm_epoch, perm_n_epochs, perm_n_env,
  * perm_group, perm_out), bit for bit) in the same launch where the scan kernel chosen for this shape can: its worker
  * threads compute them while they wait for their first tile (the warp-specialised kernel of small batches -- the shape
- * whose step is latency-bound).  Otherwise the stand-alone permutation kernel is launched behind the scan.  *fused (host,
- * may be NULL) says which: 1 = one launch.  New capability, like srl_philox_perm. */
+ * whose step is latency-bound).  Otherwise the stand-alone permutation kernel is launched behind the scan.
+ * minibatch_part (optional, device [SRL_MAX_LOSS_BATCH][ceil(N / 32)][4] float64, 32-byte aligned; needs lane_part and
+ * n_env * group == N): every scan CTA also adds ITS 32 lanes' {sum mask, sum adv*mask, sum (adv*mask)^2, 0} per minibatch
+ * -- minibatch j of epoch e = positions [j * N / perm_minibatches, ...) of epoch e's permuted lane list, table slot
+ * e * perm_minibatches + j, item [slot][scan CTA] -- so that the loss kernel adds ceil(N / 32) partial sums per minibatch
+ * (one coalesced round of loads) instead of gathering the minibatch's lanes through the permutation (two dependent
+ * rounds): srl_ppo_loss_fwd_bwd_batched, `minibatch_part`.
+ * *fused (host, may be NULL): 0 = two launches and no partial sums, 1 = one launch (permutations only: more than 8
+ * epochs or SRL_MAX_LOSS_BATCH minibatches), 2 = one launch with the partial sums.  New capability, like
+ * srl_philox_perm. */
 int srl_gae_scan_perm(const float* reward, const float* value, const uint8_t* done, const uint8_t* truncated,
                       const uint8_t* on_reset, const float* vtrace_new_logp, const float* vtrace_old_logp,
                       const double* popart_mean_std, const float* old_logp, int L, int N, int row_lo, int row_hi,
                       double gamma, double lmbda, double rho, double c, float* adv, float* ret, double* lane_part,
                       double* lane_aos, float* pack, uint64_t perm_seed, uint32_t perm_epoch, int perm_n_epochs,
-                      int perm_n_env, int perm_group, int32_t* perm_out, int* fused, srl_stream_t stream);
+                      int perm_n_env, int perm_group, int32_t* perm_out, int perm_minibatches, double* minibatch_part,
+                      int* fused, srl_stream_t stream);
 
 /* The general form of the same scan: everything modules.gae_trace (legacy/algorithm/modules/gae.py:8-97) accepts
  * beyond what MultiAgentPPO passes -- vector critics (reward / value / adv / ret are [.., N, critic_dim], the flags stay
@@ -273,6 +282,9 @@ int srl_ppo_loss_fwd_bwd(
  * lane_aos != NULL (K2's [N][4] table; pack form with lane indices, one GPU, no PopArt, even n <= 1024): every CTA adds the
  * per-lane sums of ITS minibatch's lanes itself and the problems' norm_stats / local_stats are ignored (may be NULL) --
  * no srl_group_stats launch between K2 and the loss.
+ * minibatch_part != NULL (with lane_aos; the table srl_gae_scan_perm wrote when it reported *fused == 2, part_ctas =
+ * ceil(N / 32) of that scan): problem k's sums are the part_ctas items of table slot part_first + k, added in a fixed order
+ * -- problem k's lane_idx MUST be that slot's minibatch of the permutation the same scan wrote.
  * xchg != NULL (with lane_aos, several ranks): the kernel also adds every problem's three sums over the RANKS itself -- the
  * problem's first CTA stores this rank's sums into every rank's mailbox (NVLink peer memory, the srl_xchg_* protocol
  * below; capacity >= 3 * SRL_MAX_LOSS_BATCH doubles), every CTA collects them in rank order -- so the statistics
@@ -300,7 +312,8 @@ typedef struct srl_loss_problem {
 int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems_host, int n_problems, int64_t ld_pol,
                                  int64_t ld_grad, const float* old_logp, const float* old_value, const float* ret,
                                  const float* adv, const uint8_t* on_reset_next, int64_t ld_smp, const float* pack,
-                                 int pack_row_lo, const double* lane_aos, int T, int n,
+                                 int pack_row_lo, const double* lane_aos, const double* minibatch_part, int part_ctas,
+                                 int part_first, int T, int n,
                                  const double* popart_mean_std, const srl_ppo_hyper* hyper,
                                  size_t workspace_bytes_per_slot, struct srl_xchg* xchg /* or NULL */, srl_stream_t stream);
 

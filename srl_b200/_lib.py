@@ -19,8 +19,8 @@ SRL_LANE_PART = 8
 SRL_LOSS_OUT_LEN = 16
 SRL_MAX_LEAVES = 32
 SRL_MAX_HEADS = 8
-ABI_VERSION = 8
 SRL_MAX_LOSS_BATCH = 32
+ABI_VERSION = 9
 
 # enum srl_loss_out
 OUT_LOSS, OUT_POLICY_LOSS, OUT_VALUE_LOSS, OUT_ENTROPY_LOSS = 0, 1, 2, 3
@@ -80,7 +80,8 @@ SIGNATURES = {
                      [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "srl_gae_scan_perm": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double] +
                           [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] +
-                          [ctypes.c_uint64, ctypes.c_uint32, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+                          [ctypes.c_uint64, ctypes.c_uint32, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                           c_void_p]),
     "srl_gae_trace": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_double, c_double, c_double, c_double, c_int,
                               c_void_p, c_void_p, c_void_p]),
     "srl_traj_gae": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p]),
@@ -98,8 +99,8 @@ SIGNATURES = {
                                      c_void_p]),
     "srl_ppo_loss_fwd_bwd_batched": (c_int, [POINTER(LossProblem), c_int, c_int64, c_int64,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
-                                             c_int, c_void_p, c_int, c_int, c_void_p, POINTER(PpoHyper), c_size_t,
-                                             c_void_p, c_void_p]),
+                                             c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, POINTER(PpoHyper),
+                                             c_size_t, c_void_p, c_void_p]),
     "srl_ppo_loss_from_logits": (c_int, [c_void_p, c_void_p, POINTER(c_int32), c_int, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                          c_int, c_int, c_void_p, c_void_p, c_void_p, POINTER(PpoHyper),

@@ -306,8 +306,8 @@ extern "C" int srl_gae_scan_perm(const float* reward, const float* value, const 
                                  const double* popart_mean_std, const float* old_logp, int L, int N, int row_lo,
                                  int row_hi, double gamma, double lmbda, double rho, double c, float* adv, float* ret,
                                  double* lane_part, double* lane_aos, float* pack, uint64_t perm_seed, uint32_t perm_epoch,
-                                 int perm_n_epochs, int perm_n_env, int perm_group, int32_t* perm_out, int* fused,
-                                 srl_stream_t stream) {
+                                 int perm_n_epochs, int perm_n_env, int perm_group, int32_t* perm_out,
+                                 int perm_minibatches, double* minibatch_part, int* fused, srl_stream_t stream) {
   using namespace srl;
   SRL_REQUIRE(perm_out != nullptr && perm_n_env >= 1 && perm_group >= 1 && perm_n_epochs >= 1 && perm_n_epochs <= 65535,
               SRL_ERR_INVALID_ARG, "srl_gae_scan_perm: need a permutation output, n_env >= 1, group >= 1, 1 <= n_epochs <= 65535");
@@ -322,12 +322,28 @@ extern "C" int srl_gae_scan_perm(const float* reward, const float* value, const 
   job.group = perm_group;
   job.bits = perm_bits(perm_n_env);
   job.out = perm_out;
+  job.minibatches = 1;
+  job.per_mb = perm_n_env * perm_group;
+  job.part = nullptr;
+  if (minibatch_part != nullptr) {
+    SRL_REQUIRE(perm_minibatches >= 1 && (static_cast<long long>(perm_n_env) * perm_group) % perm_minibatches == 0 &&
+                    perm_n_env * perm_group == N && lane_part != nullptr && aligned(minibatch_part, 32),
+                SRL_ERR_INVALID_ARG,
+                "srl_gae_scan_perm: minibatch_part needs lane_part, n_env * group == N lanes split evenly into the minibatches "
+                "and a 32-byte aligned table");
+    if (perm_n_epochs <= kPartEpochs && perm_n_epochs * perm_minibatches <= kPartSlots) {  // else: not produced (*fused = 0)
+      job.minibatches = perm_minibatches;
+      job.per_mb = perm_n_env * perm_group / perm_minibatches;
+      job.part = minibatch_part;
+    }
+  }
   int did = 0;
   const int rc = gae_scan_impl(reward, value, done, truncated, on_reset, vtrace_new_logp, vtrace_old_logp, popart_mean_std,
                                old_logp, L, N, row_lo, row_hi, gamma, lmbda, rho, c, adv, ret, lane_part, lane_aos, pack, &job,
                                &did, stream);
   if (rc != SRL_OK) return rc;
-  if (fused != nullptr) *fused = did;
+  // 1: permutations from the scan kernel; 2: and the minibatch partial sums
+  if (fused != nullptr) *fused = did ? (job.part != nullptr ? 2 : 1) : 0;
   if (did) return SRL_OK;
   // the scan kernel chosen for this shape does not compute permutations: the stand-alone kernel, behind the scan
   return srl_philox_perm(perm_seed, perm_epoch, perm_n_epochs, perm_n_env, perm_group, perm_out, stream);
@@ -377,6 +393,7 @@ int gae_scan_impl(const float* reward, const float* value, const uint8_t* done, 
   p.rho = rho;
   p.c = c;
   p.perm.out = nullptr;
+  p.perm.part = nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   // Three kernels, picked by how many 32-lane groups the batch has (SRL_GAE_PATH=tile|tma|ws, read once, overrides:

@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
   constexpr int kRowsPerWorker = kR / kW;
   constexpr int kAhead = kS > 3 ? kS - 1 : 1;  // chunks the workers' delta pass runs ahead of their store pass
   constexpr int kStatsOff = (sizeof(Bars<kS>) + 255) / 256 * 256;
+  constexpr int kPartOff = kStatsOff + kW * 7 * 32 * static_cast<int>(sizeof(double));  // [3][32] f64 lane sums, [kPartEpochs][32] u8 map
   constexpr int kThreads = 32 * (2 + kW);
   using SL = Slot<PACK>;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -182,6 +183,23 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
         const uint32_t x = perm_at(e, static_cast<uint32_t>(p.perm.n_env), keys);
         int32_t* o = p.perm.out + (static_cast<size_t>(ep) * p.perm.n_env + e) * p.perm.group;
         for (int a = 0; a < p.perm.group; ++a) o[a] = static_cast<int32_t>(x) * p.perm.group + a;
+      }
+    }
+    // ... and, for the loss kernel's minibatch statistics, the minibatch of each of THIS CTA's 32 lanes in every epoch (the
+    // inverse permutation: a Feistel network runs backwards as well), kept in shared memory for the end of the kernel
+    if (p.perm.out != nullptr && p.perm.part != nullptr) {
+      uint8_t* s_mb = smem + kS * SL::bytes + kPartOff + 3 * 32 * sizeof(double);
+      for (int i = w * 32 + lane; i < p.perm.n_epochs * 32; i += 32 * kW) {
+        const int ep = i >> 5, c2 = col0 + (i & 31);
+        int slot = 255;
+        if (c2 < N) {
+          const PermKeys keys = perm_keys(p.perm.seed_lo, p.perm.seed_hi, p.perm.epoch0 + ep, p.perm.bits);
+          const uint32_t env = static_cast<uint32_t>(c2 / p.perm.group);
+          const long long pos = static_cast<long long>(perm_pos_of(env, static_cast<uint32_t>(p.perm.n_env), keys)) * p.perm.group +
+                                (c2 - static_cast<int>(env) * p.perm.group);
+          slot = ep * p.perm.minibatches + static_cast<int>(pos / p.perm.per_mb);
+        }
+        s_mb[i] = static_cast<uint8_t>(slot);
       }
     }
     double s1 = 0, s2 = 0, s3 = 0, s4 = 0;
@@ -309,6 +327,31 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
           for (int ww = 0; ww < kW; ++ww) sum += red[(ww * 7 + k) * 32 + ln];
         p.lane_part[static_cast<size_t>(k) * N + c2] = sum;
         if (p.lane_aos != nullptr && k < 4) p.lane_aos[static_cast<size_t>(c2) * 4 + k] = k < 3 ? sum : 0.0;
+        if (k < 3) reinterpret_cast<double*>(smem + kS * SL::bytes + kPartOff)[k * 32 + ln] = sum;
+      }
+    }
+    if (p.perm.out != nullptr && p.perm.part != nullptr) {
+      // this CTA's share of every minibatch's {count, sum, sum of squares}, part[slot][cta][4]: the loss kernel adds
+      // gridDim.x shares per minibatch (one coalesced round of loads) instead of gathering the minibatch's lane items
+      // through the permutation (two dependent rounds).  Four threads per output, 8 lanes each in lane order, then
+      // (q0 + q1) + (q2 + q3): a fixed order.
+      __syncthreads();
+      const double* lsum = reinterpret_cast<const double*>(smem + kS * SL::bytes + kPartOff);
+      const uint8_t* s_mb = smem + kS * SL::bytes + kPartOff + 3 * 32 * sizeof(double);
+      const int outs = p.perm.n_epochs * p.perm.minibatches * 4;
+      for (int i = threadIdx.x; i < ((outs * 4 + 31) & ~31); i += kThreads) {  // whole warps iterate together
+        const int o = i >> 2, qr = i & 3;
+        const int slot = o >> 2, k = o & 3;
+        double acc = 0.0;
+        if (o < outs && k < 3) {
+          const uint8_t* mb = s_mb + (slot / p.perm.minibatches) * 32 + qr * 8;
+          const double* ls = lsum + k * 32 + qr * 8;
+#pragma unroll
+          for (int ln = 0; ln < 8; ++ln) acc += mb[ln] == slot ? ls[ln] : 0.0;
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (o < outs && qr == 0) p.perm.part[(static_cast<size_t>(slot) * gridDim.x + blockIdx.x) * 4 + k] = acc;
       }
     }
   }
@@ -324,7 +367,8 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
 
 template <bool PACK, int kW, int kS>
 int launch_ws(const WsParams& q, cudaStream_t st) {
-  const size_t smem = static_cast<size_t>(kS) * Slot<PACK>::bytes + (sizeof(Bars<kS>) + 255) / 256 * 256 +
+  const size_t smem = 3 * 32 * sizeof(double) + kPartEpochs * 32 +  // lane sums + lane -> minibatch map (srl_gae_scan_perm)
+                      static_cast<size_t>(kS) * Slot<PACK>::bytes + (sizeof(Bars<kS>) + 255) / 256 * 256 +
                       static_cast<size_t>(kW) * 7 * 32 * sizeof(double);
   auto kern = gae_scan_ws_kernel<PACK, kW, kS>;
   static bool opted_in[64] = {};

@@ -77,6 +77,31 @@ __host__ __device__ __forceinline__ uint32_t perm_at(uint32_t e, uint32_t n_env,
   return x;
 }
 
+// The inverse: the rounds of feistel8 undone in reverse order (each round XORs one half with a function of the other, which
+// it leaves alone), and the cycle walk walked backwards.
+__host__ __device__ __forceinline__ uint32_t feistel8_inv(uint32_t y, const PermKeys& k) {
+  uint32_t lo = y & k.lmask, hi = (y >> k.lb) & k.hmask;
+#pragma unroll
+  for (int r = 7; r >= 0; --r) {
+    if ((r & 1) == 0) {
+      uint32_t f = static_cast<uint32_t>((static_cast<uint64_t>(0xD2511F53u) * (lo ^ k.rk[r])) >> 32);
+      f ^= (lo * 0x9E3779B9u) >> 16;
+      hi = (hi ^ f) & k.hmask;
+    } else {
+      uint32_t f = static_cast<uint32_t>((static_cast<uint64_t>(0xCD9E8D57u) * (hi ^ k.rk[r])) >> 32);
+      f ^= (hi * 0xBB67AE85u) >> 16;
+      lo = (lo ^ f) & k.lmask;
+    }
+  }
+  return (hi << k.lb) | lo;
+}
+// position e with perm_at(e) == x
+__host__ __device__ __forceinline__ uint32_t perm_pos_of(uint32_t x, uint32_t n_env, const PermKeys& k) {
+  uint32_t e = feistel8_inv(x, k);
+  while (e >= n_env) e = feistel8_inv(e, k);
+  return e;
+}
+
 inline int perm_bits(int n_env) {
   int bits = 0;
   while ((1ll << bits) < n_env) ++bits;  // == (n_env - 1).bit_length()
@@ -88,6 +113,12 @@ struct PermJob {
   uint32_t seed_lo, seed_hi, epoch0;
   int n_epochs, n_env, group, bits;
   int32_t* out;
+  // optional (part != nullptr): every scan CTA also adds ITS lanes' {count, sum, sum of squares} per minibatch -- epoch e's
+  // minibatch j = positions [j * per_mb, (j + 1) * per_mb) of the permuted lane list -- into part[e * minibatches + j][cta][4]
+  int minibatches, per_mb;
+  double* part;
 };
+constexpr int kPartSlots = 32;   // minibatches of a step the partial sums cover (== SRL_MAX_LOSS_BATCH)
+constexpr int kPartEpochs = 8;
 
 }  // namespace srl

@@ -368,7 +368,8 @@ extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, in
                                             int64_t ld_grad, const float* old_logp, const float* old_value,
                                             const float* ret, const float* adv, const uint8_t* on_reset_next,
                                             int64_t ld_smp, const float* pack, int pack_row_lo, const double* lane_aos,
-                                            int T, int n, const double* popart_mean_std, const srl_ppo_hyper* hyper,
+                                            const double* minibatch_part, int part_ctas, int part_first, int T, int n,
+                                            const double* popart_mean_std, const srl_ppo_hyper* hyper,
                                             size_t workspace_bytes, srl_xchg* xchg, srl_stream_t stream) {
   using namespace srl;
   using namespace srl::loss;
@@ -418,6 +419,15 @@ extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, in
               "srl_ppo_loss_fwd_bwd_batched: self-computed statistics (lane_aos) need the pack form with lane indices, no "
               "PopArt and a 32-byte aligned table");
   s.lane_aos = lane_aos;
+  SRL_REQUIRE(minibatch_part == nullptr ||
+                  (lane_aos != nullptr && aligned(minibatch_part, 32) && part_ctas >= 1 && part_first >= 0 &&
+                   part_first + n_problems <= kMaxBatch),
+              SRL_ERR_INVALID_ARG,
+              "srl_ppo_loss_fwd_bwd_batched: minibatch_part needs lane_aos, a 32-byte aligned table, part_ctas >= 1 and table "
+              "slots part_first .. part_first + n_problems - 1 within %d", kMaxBatch);
+  s.part = minibatch_part;
+  s.part_ctas = part_ctas;
+  s.part_first = part_first;
   s.row_lo = pack ? pack_row_lo : 0;
   s.ld_pol = ld_pol;
   s.ld_grad = ld_grad;
@@ -465,6 +475,7 @@ extern "C" int srl_ppo_loss_fwd_bwd_batched(const srl_loss_problem* problems, in
     const int nb = n_problems - k0 < kMaxBatch ? n_problems - k0 : kMaxBatch;
     LossBatch b;
     b.s = s;
+    b.s.part_first = part_first + k0;
     if (xv != nullptr && xv->world > 1) {
       b.xv = *xv;
     } else {
@@ -506,7 +517,8 @@ extern "C" int srl_ppo_loss_fwd_bwd(const float* new_logp, const float* v_pred, 
   q.out_f32 = out_f32;
   q.workspace = workspace;
   return srl_ppo_loss_fwd_bwd_batched(&q, 1, ld_pol, ld_grad, old_logp, old_value, ret, adv, on_reset_next, ld_smp,
-                                      nullptr, 0, nullptr, T, n, popart_mean_std, hyper, workspace_bytes, nullptr, stream);
+                                      nullptr, 0, nullptr, nullptr, 0, 0, T, n, popart_mean_std, hyper, workspace_bytes, nullptr,
+                                      stream);
 }
 
 extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* action, const int32_t* head_sizes_host,
@@ -560,6 +572,8 @@ extern "C" int srl_ppo_loss_from_logits(const float* logits, const int32_t* acti
   p.reset_next = on_reset_next;
   p.pack = nullptr;
   p.lane_aos = nullptr;
+  p.part = nullptr;
+  p.part_ctas = p.part_first = 0;
   p.row_lo = 0;
   p.popart = popart_mean_std;
   p.ld_pol = n;

@@ -74,6 +74,8 @@ struct LossShared {
   const float4* pack;        // K2's pair-interleaved pack (base of the buffer, absolute row 0), or null
   const double* popart;
   const double* lane_aos;    // [N][4] float64 per-lane sums from K2 (ppo_loss_pair.cu: self-computed statistics), or null
+  const double* part;        // [slot][part_ctas][4] float64: K2's per-CTA shares of every minibatch's sums, or null
+  int part_ctas, part_first; // problem k of the launch is table slot part_first + k
   long long ld_pol, ld_grad;
   long long ld_smp;          // sample-side row stride in elements; pack form: lanes N of the pack
   int T, n;

@@ -34,6 +34,9 @@ namespace {
 #ifndef SRL_PAIR_PF_AHEAD
 #define SRL_PAIR_PF_AHEAD 2
 #endif
+#ifndef SRL_PAIR_PART_EACH
+#define SRL_PAIR_PART_EACH 1
+#endif
 constexpr int kPairThreads = SRL_PAIR_THREADS;
 constexpr int kPairLanes = 2 * kPairThreads;  // lanes per column tile
 constexpr int kStatMax = 1024 / kPairThreads; // lanes per thread in the statistics prologue (n <= 1024)
@@ -74,8 +77,13 @@ __device__ __forceinline__ void ld_nc256(const double* p, double (&v)[4]) {
 // put 1184 x 512 gathers of the same 16 K lane items through L2 at the same moment: the device timeline showed 4.6 us between
 // griddepcontrol.wait and the first row, profiles/r2_notes.md.)  Without `share` every CTA adds them itself, in the same
 // order, so all CTAs of a problem normalise with bit-identical statistics either way.
+//
+// `part` (K2's per-CTA shares of THIS problem's sums, srl_gae_scan_perm; [part_ctas][4]): the scan computed the permutation,
+// so it knew every lane's minibatch and left one {count, sum, sum of squares} item per scan CTA and minibatch.  The sums are
+// then part_ctas contiguous items -- ONE round of coalesced loads (128 items at cfg2) instead of the index round and the
+// dependent round of 512 scattered 32-byte gathers behind it.
 __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__ lane_aos, const int32_t* __restrict__ idx,
-                                                      int n, double adv_eps, double& mask_sum, double (*s_part)[8],
+                                                      const double* __restrict__ part, int part_ctas, int n, double adv_eps, double& mask_sum, double (*s_part)[8],
                                                       const XchgView& xv, int slot, bool sender, SlotHeader* hdr, bool share,
                                                       unsigned int xchg_seq) {
   if (share && !sender) {
@@ -105,33 +113,55 @@ __device__ __forceinline__ Uniforms self_uniforms_aos(const double* __restrict__
     mask_sum = s_part[3][0];
     return uniforms_from(s_part[0][0], s_part[1][0], s_part[2][0], mask_sum, nullptr, adv_eps);
   }
-  // kStatBatch gathers in flight per thread at a time (all index loads first): two dependent rounds for 1024 lanes on
-  // 64 threads instead of sixteen, without holding 16 x 4 doubles in registers
-  constexpr int kStatBatch = kStatMax < 8 ? kStatMax : 8;
-  int ci[kStatMax];
-#pragma unroll
-  for (int q = 0; q < kStatMax; ++q) {
-    const int i = threadIdx.x + q * kPairThreads;
-    ci[q] = i < n ? __ldg(idx + i) : -1;
-  }
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  if (part != nullptr) {
+    constexpr int kPartBatch = 4;  // items in flight per thread
+    for (int i0 = threadIdx.x; i0 < part_ctas; i0 += kPairThreads * kPartBatch) {
+      double v[kPartBatch][4];
 #pragma unroll
-  for (int q0 = 0; q0 < kStatMax; q0 += kStatBatch) {
-    if (q0 * kPairThreads >= n) break;  // uniform: the minibatch ends before this batch
-    double v[kStatBatch][4];
+      for (int q = 0; q < kPartBatch; ++q) {
+        const int i = i0 + q * kPairThreads;
+        if (i < part_ctas) {
+          ld_nc256(part + 4 * static_cast<size_t>(i), v[q]);
+        } else {
+          v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.0;
+        }
+      }
 #pragma unroll
-    for (int q = 0; q < kStatBatch; ++q) {
-      if (ci[q0 + q] >= 0) {
-        ld_nc256(lane_aos + 4 * static_cast<size_t>(ci[q0 + q]), v[q]);
-      } else {
-        v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.0;
+      for (int q = 0; q < kPartBatch; ++q) {
+        a0 += v[q][0];
+        a1 += v[q][1];
+        a2 += v[q][2];
       }
     }
+  } else {
+    // kStatBatch gathers in flight per thread at a time (all index loads first): two dependent rounds for 1024 lanes on
+    // 64 threads instead of sixteen, without holding 16 x 4 doubles in registers
+    constexpr int kStatBatch = kStatMax < 8 ? kStatMax : 8;
+    int ci[kStatMax];
 #pragma unroll
-    for (int q = 0; q < kStatBatch; ++q) {
-      a0 += v[q][0];
-      a1 += v[q][1];
-      a2 += v[q][2];
+    for (int q = 0; q < kStatMax; ++q) {
+      const int i = threadIdx.x + q * kPairThreads;
+      ci[q] = i < n ? __ldg(idx + i) : -1;
+    }
+#pragma unroll
+    for (int q0 = 0; q0 < kStatMax; q0 += kStatBatch) {
+      if (q0 * kPairThreads >= n) break;  // uniform: the minibatch ends before this batch
+      double v[kStatBatch][4];
+#pragma unroll
+      for (int q = 0; q < kStatBatch; ++q) {
+        if (ci[q0 + q] >= 0) {
+          ld_nc256(lane_aos + 4 * static_cast<size_t>(ci[q0 + q]), v[q]);
+        } else {
+          v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kStatBatch; ++q) {
+        a0 += v[q][0];
+        a1 += v[q][1];
+        a2 += v[q][2];
+      }
     }
   }
   a0 = warp_sum(a0);
@@ -425,9 +455,16 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
     r_ld += 2, q_ld += 2 * pol_row, k0 += pack_step, k1 += pack_step;
     first = false;
     if (!have_u) {  // once per CTA; the first step's loads are in flight underneath
-      if (s.lane_aos != nullptr)
-        uf = self_uniforms_aos(s.lane_aos, pr.lane_idx, n, h.adv_eps, mask_sum, s_part, b.xv, static_cast<int>(blockIdx.x),
-                               blockIdx.y == 0, pr.slot, pr.out != nullptr && gridDim.y > 1, xchg_seq);
+      if (s.lane_aos != nullptr) {
+        const double* part =
+            s.part != nullptr ? s.part + static_cast<size_t>(s.part_first + static_cast<int>(blockIdx.x)) * s.part_ctas * 4 : nullptr;
+        // with the scan's shares and one rank, every CTA adds them itself (SRL_PAIR_PART_EACH): 4 KB of contiguous L2 hits
+        // per CTA against a publication by the problem's first CTA and a poll by the others
+        const bool each = SRL_PAIR_PART_EACH && part != nullptr && b.xv.world <= 1;
+        uf = self_uniforms_aos(s.lane_aos, pr.lane_idx, part, s.part_ctas, n, h.adv_eps, mask_sum, s_part, b.xv,
+                               static_cast<int>(blockIdx.x), blockIdx.y == 0, pr.slot,
+                               pr.out != nullptr && gridDim.y > 1 && !each, xchg_seq);
+      }
       else
         uf = load_uniforms(pr.norm_stats, pr.local_stats, s.popart, h.adv_eps, mask_sum);
       have_u = true;

@@ -130,6 +130,12 @@ class HotPath:
         self.lane_part = torch.empty((SRL_LANE_PART, N), dtype=torch.float64, device=dev)
         # the same per-lane sums as one 32-byte item per lane: what the pair loss kernel gathers for its own statistics
         self.lane_aos = torch.empty((N, 4), dtype=torch.float64, device=dev) if self.fuse_stats else None
+        # ... and, where the scan kernel computes the permutations itself, every scan CTA's share of every minibatch's
+        # sums: the loss kernel then adds N / 32 contiguous items per minibatch instead of gathering the minibatch's lanes
+        # (SRL_MB_PART=0: an A/B knob for profiles/)
+        self.mb_part = ops.new_minibatch_part(N, dev) if (self.fuse_stats and epochs <= 8 and epochs * minibatches <= 32 and
+                                                          os.environ.get("SRL_MB_PART", "1") != "0") else None
+        self._part_valid = False
         G = 1 + epochs * minibatches
         self.local_stats = torch.zeros((G, SRL_LANE_PART), dtype=torch.float64, device=dev)
         self.global_stats = self.local_stats if process_group is None else torch.zeros_like(self.local_stats)
@@ -241,11 +247,14 @@ class HotPath:
                 blk = self.shuffle_block
                 job = dict(seed=self.seed + self.step_count, epoch=0, n_epochs=self.epochs, n_env=self.B // blk,
                            group=self.A * blk, out=self.perm)
+                if self.mb_part is not None and "lane_aos" in kw:
+                    job.update(minibatches=self.minibatches, part=self.mb_part)
                 kw["perm_job"] = job
             ops.gae_scan(lf["reward"], lf["value"], lf["done"], lf["truncated"], lf["on_reset"], self.gamma, self.lmbda,
                          row_lo=self.row_lo, row_hi=self.row_hi, popart_mean_std=self.popart_mean_std(), adv=self.adv,
                          ret=self.ret, lane_part=self.lane_part, **kw)
             self._perm_fused = bool(job and job.get("fused"))
+        self._part_valid = bool(job and job.get("part_valid"))
         if inline_perm and not perm_first and job is None:
             # K2 -> K5a -> K4 on one stream: the scan is the long pole and starts first; the permutation kernel starts beside
             # it (programmatic launch) and only completes once the scan has, so the loss kernel behind it waits for both
@@ -365,9 +374,14 @@ class HotPath:
         probs = [self._problem(e, j, *pol[e][j], deferred=False) for e, j in pairs]
         if self.minibatches > 1 and self.pack is not None and self.pack_valid:
             own = self.lane_aos if (self.fuse_stats and self._stats_pending) else None
+            # the scan's per-CTA shares serve a run of consecutive minibatches (table slot = e * minibatches + j)
+            slots = [e * self.minibatches + j for e, j in pairs]
+            part = self.mb_part if (own is not None and self._part_valid and
+                                    slots == list(range(slots[0], slots[0] + len(slots)))) else None
             ops.ppo_loss_batched(probs, None, None, None, None, None, self.hyper,
                                  popart_mean_std=self.popart_mean_std(), pack=self.pack, pack_row_lo=lo, lane_aos=own,
-                                 exchange=self.peer_loss if own is not None else None)
+                                 exchange=self.peer_loss if own is not None else None, minibatch_part=part,
+                                 part_first=slots[0] if part is not None else 0)
         else:
             ops.ppo_loss_batched(probs, lf["old_logp"][lo:hi], lf["value"][lo:hi], self.ret[lo:hi], self.adv[lo:hi],
                                  lf["on_reset"][lo + 1:hi + 1], self.hyper, popart_mean_std=self.popart_mean_std())

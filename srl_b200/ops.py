@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from srl_b200 import _lib
-from srl_b200._lib import (SRL_LANE_PART, SRL_LOSS_OUT_LEN, SRL_MAX_HEADS, SRL_MAX_LEAVES, LeafDesc, LossProblem,
+from srl_b200._lib import (SRL_LANE_PART, SRL_LOSS_OUT_LEN, SRL_MAX_HEADS, SRL_MAX_LEAVES, SRL_MAX_LOSS_BATCH, LeafDesc, LossProblem,
                            PpoHyper, VALUE_LOSS_CODES)
 
 
@@ -83,7 +83,10 @@ def gae_scan(reward, value, done, truncated, on_reset, gamma: float, lmbda: floa
     `perm_job` (dict: seed, epoch, n_epochs, n_env, group, out int32 `[n_epochs, n_env * group]`): the step's minibatch
     permutations (== `philox_perm` with the same arguments, bit for bit) computed by the scan kernel's own idle threads where
     the kernel chosen for this shape can (srl_gae_scan_perm), by the stand-alone kernel behind the scan otherwise; the
-    dict's key "fused" says which (True / False).
+    dict's key "fused" says which (True / False).  Optional keys `minibatches` and `part` (float64
+    `new_minibatch_part(N)` = `[32, ceil(N / 32), 4]`): every scan CTA also leaves its 32 lanes' share of every minibatch's
+    {count, sum, sum of squares} -- what `ppo_loss_batched(minibatch_part=...)` adds instead of gathering lane items; the
+    key "part_valid" says whether the table was written (only by the fused kernel, <= 8 epochs, <= 32 minibatches per step).
     Reference: MultiAgentPPO._compute_adv_and_value_target (mappo.py:118-144) + F.pad (mappo.py:254-256).
     """
     L, N = _rows_lanes(value)
@@ -137,11 +140,24 @@ def gae_scan(reward, value, done, truncated, on_reset, gamma: float, lmbda: floa
         n_ep, n_env, group = int(perm_job["n_epochs"]), int(perm_job["n_env"]), int(perm_job.get("group", 1))
         if out.numel() != n_ep * n_env * group:
             raise ValueError(f"perm_job['out'] must hold [n_epochs, n_env * group] = {n_ep * n_env * group} int32")
+        part = perm_job.get("part")
+        if part is not None:
+            _check(part, torch.float64, "perm_job['part']")
+            if tuple(part.shape) != (SRL_MAX_LOSS_BATCH, (N + 31) // 32, 4):
+                raise ValueError(f"perm_job['part']: expected new_minibatch_part(N) = {(SRL_MAX_LOSS_BATCH, (N + 31) // 32, 4)}, "
+                                 f"got {tuple(part.shape)}")
         fused = ctypes.c_int(0)
         _lib.call("srl_gae_scan_perm", *args, ctypes.c_uint64(int(perm_job["seed"]) & (2 ** 64 - 1)),
-                  ctypes.c_uint32(int(perm_job.get("epoch", 0))), n_ep, n_env, group, _ptr(out), ctypes.byref(fused), _stream())
-        perm_job["fused"] = bool(fused.value)
+                  ctypes.c_uint32(int(perm_job.get("epoch", 0))), n_ep, n_env, group, _ptr(out),
+                  int(perm_job.get("minibatches", 1)), _ptr(part), ctypes.byref(fused), _stream())
+        perm_job["fused"] = fused.value >= 1
+        perm_job["part_valid"] = fused.value == 2
     return adv, ret, lane_part
+
+
+def new_minibatch_part(N: int, device) -> torch.Tensor:
+    """The table srl_gae_scan_perm's `minibatch_part` writes: [minibatch slot][scan CTA = 32-lane group][4] float64."""
+    return torch.zeros((SRL_MAX_LOSS_BATCH, (N + 31) // 32, 4), dtype=torch.float64, device=device)
 
 
 def pack_rows(L: int) -> int:
@@ -484,7 +500,8 @@ def ppo_loss_fwd_bwd(new_logp, v_pred, entropy, old_logp, old_value, ret, adv, o
 
 def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on_reset_next, hyper: LossHyper,
                      popart_mean_std=None, pack: Optional[torch.Tensor] = None, pack_row_lo: int = 0,
-                     lane_aos: Optional[torch.Tensor] = None, exchange=None) -> None:
+                     lane_aos: Optional[torch.Tensor] = None, exchange=None,
+                     minibatch_part: Optional[torch.Tensor] = None, part_first: int = 0) -> None:
     """Several minibatches of one shape in ONE launch (srl_ppo_loss_fwd_bwd_batched).
 
     Each problem is a dict with `new_logp`, `v_pred`, `entropy` (`[T, n]` float32), `norm_stats`, `local_stats`
@@ -494,6 +511,8 @@ def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on
     `pack` = the whole pair-interleaved pack K2 wrote (`new_pack`) with `pack_row_lo` = the sample row of loss row 0.
     `lane_aos` (K2's `[N, 4]` float64 table; pack form with lane indices, one GPU, no PopArt, even n <= 1024): the kernel
     adds the minibatch statistics itself and `norm_stats` / `local_stats` of the problems are not read (may be omitted).
+    `minibatch_part` (with `lane_aos`; the table `gae_scan`'s perm_job wrote, "part_valid"): problem k's sums are table slot
+    `part_first + k`'s per-CTA shares -- its `lane_idx` must be that slot's minibatch of the same scan's permutation.
     `exchange` (a srl_b200.xchg.PeerExchange of its own, with `lane_aos`, several ranks): the kernel adds every problem's sums
     over the ranks itself (NVLink peer memory) -- no statistics kernels between the scan and the loss.
     The gradient tensors must not alias the policy-side inputs."""
@@ -554,9 +573,17 @@ def ppo_loss_batched(problems: Sequence[dict], old_logp, old_value, ret, adv, on
         _check(lane_aos, torch.float64, "lane_aos")
         if pack is None or lane_aos.dim() != 2 or tuple(lane_aos.shape) != (pack.shape[1], 4):
             raise ValueError(f"lane_aos: expected [N, 4] float64 beside the pack, got {tuple(lane_aos.shape)}")
+    part_ctas = 0
+    if minibatch_part is not None:
+        _check(minibatch_part, torch.float64, "minibatch_part")
+        if lane_aos is None or minibatch_part.dim() != 3 or \
+                tuple(minibatch_part.shape) != (SRL_MAX_LOSS_BATCH, (lane_aos.shape[0] + 31) // 32, 4):
+            raise ValueError(f"minibatch_part: expected new_minibatch_part(N) beside lane_aos, got {tuple(minibatch_part.shape)}")
+        part_ctas = minibatch_part.shape[1]
     hc = hyper.to_c()
     _lib.call("srl_ppo_loss_fwd_bwd_batched", arr, len(problems), n, n, _ptr(old_logp), _ptr(old_value), _ptr(ret),
-              _ptr(adv), _ptr(on_reset_next), ld_smp, _ptr(pack), int(pack_row_lo), _ptr(lane_aos), T, n,
+              _ptr(adv), _ptr(on_reset_next), ld_smp, _ptr(pack), int(pack_row_lo), _ptr(lane_aos), _ptr(minibatch_part),
+              part_ctas, int(part_first), T, n,
               _ptr(popart_mean_std), ctypes.byref(hc), slot_bytes, None if exchange is None else exchange._h, _stream())
 
 

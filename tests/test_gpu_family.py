@@ -229,3 +229,43 @@ def test_scan_with_permutation_on_the_side_equals_philox_perm(N, n_env, group, e
     assert torch.equal(out, want.view(epochs, -1))
     assert torch.equal(a0, a1) and torch.equal(r0, r1) and torch.equal(p0, p1)
     assert job["fused"] == (256 <= N < 2 * 148 * 32)
+
+
+@pytest.mark.parametrize("N,n_env,group,epochs,mbs", [(4096, 4096, 1, 4, 8), (1024, 128, 8, 2, 4), (272, 34, 8, 8, 2),
+                                                      (1536, 512, 3, 3, 1), (512, 512, 1, 9, 2), (20480, 2048, 10, 1, 4)])
+def test_scan_minibatch_shares_add_up_to_the_minibatch_sums(N, n_env, group, epochs, mbs):
+    """srl_gae_scan_perm's `minibatch_part`: table[slot][cta] is CTA cta's 32 lanes' share of minibatch slot's {count, sum,
+    sum of squares} -- exactly the lanes of that 32-lane group which the permutation of the SAME launch puts into the
+    minibatch.  Not written (part_valid False, table untouched) by the kernels that do not compute the permutation or for
+    more than 8 epochs."""
+    from srl_b200 import ops
+    L = 21
+    g = torch.Generator().manual_seed(N + n_env + mbs)
+    f = lambda: torch.randn((L, N), generator=g).cuda()
+    u = lambda p: (torch.rand((L, N), generator=g) < p).to(torch.uint8).cuda()
+    reward, value, done, trunc, reset = f(), f(), u(0.02), u(0.01), u(0.05)
+    perm = torch.empty((epochs, N), dtype=torch.int32, device="cuda")
+    part = ops.new_minibatch_part(N, "cuda").fill_(-3.0)
+    aos = torch.empty((N, 4), dtype=torch.float64, device="cuda")
+    pack = ops.new_pack(L, N, "cuda")
+    job = dict(seed=5, epoch=1, n_epochs=epochs, n_env=n_env, group=group, out=perm, minibatches=mbs, part=part)
+    _, _, lane_part = ops.gae_scan(reward, value, done, trunc, reset, 0.99, 0.95, old_logp=f(), pack=pack, lane_aos=aos,
+                                   perm_job=job)
+    torch.cuda.synchronize()
+    assert torch.equal(perm, ops.philox_perm(5, 1, n_env, group, n_epochs=epochs).view(epochs, -1))
+    want_valid = (256 <= N < 2 * 148 * 32) and epochs <= 8 and epochs * mbs <= 32
+    assert job["part_valid"] == want_valid
+    if not want_valid:
+        assert bool((part == -3.0).all())
+        return
+    lp, pm, tb = lane_part.cpu().numpy(), perm.cpu().numpy(), part.cpu().numpy()
+    ctas, per = (N + 31) // 32, N // mbs
+    assert bool((tb[epochs * mbs:] == -3.0).all()) and not tb[:epochs * mbs, :, 3].any()
+    for e in range(epochs):
+        for j in range(mbs):
+            lanes = pm[e, j * per:(j + 1) * per]
+            want = np.zeros((ctas, 3))
+            for k in range(3):
+                np.add.at(want[:, k], lanes // 32, lp[k, lanes])
+            np.testing.assert_allclose(tb[e * mbs + j, :, :3], want, rtol=1e-14, atol=1e-14)
+            assert np.array_equal(tb[e * mbs + j, :, 0], np.bincount(lanes // 32, weights=lp[0, lanes], minlength=ctas))

@@ -89,6 +89,12 @@ CASES = {
     # several column tiles per minibatch, CTA ranges that cross column and minibatch boundaries
     "mb_wide": synth.PathConfig("mb_wide", T=21, B=1536, epochs=2, minibatches=2, p_end=0.05, clip_value=True,
                                 dual_clip=False, value_loss="huber", value_loss_delta=10.0),
+    # the scan kernel that computes the permutations and every minibatch's per-CTA shares (256 <= N < ~9500 lanes): the loss
+    # kernel adds the shares instead of gathering lane items -- cfg2's width, agents in groups, a half-filled last scan CTA
+    "mb_shares": synth.PathConfig("mb_shares", T=6, B=4096, epochs=4, minibatches=8, p_end=0.1, clip_value=True,
+                                  value_loss="huber", value_loss_delta=10.0),
+    "mb_shares_agents": synth.PathConfig("mb_shares_agents", T=9, B=68, A=4, epochs=3, minibatches=2, p_end=0.1,
+                                         dead_agent_frac=0.2),
     # an odd minibatch width: the pack form on the row-tile kernel (one lane per thread)
     "mb_odd_width": synth.PathConfig("mb_odd_width", T=9, B=27, epochs=1, minibatches=3, p_end=0.1),
 }
@@ -113,6 +119,30 @@ def test_step_graph_replay_matches_oracle(name):
         hp.popart_ms.copy_(torch.tensor([0.0, 0.1, 0.0, 0.1], dtype=torch.float64))
         hp.run_device(pol_dev, use_graph=True)
     _compare(hp, cfg, ref, pa)
+
+
+@pytest.mark.parametrize("name", ["mb_wide", "mb_shares", "mb_shares_agents"])
+def test_step_uses_the_scan_shares_and_agrees_with_the_lane_gather(name, monkeypatch):
+    """Where the scan computes the permutations itself the batched loss adds the scan's per-CTA shares of its minibatch
+    (HotPath._part_valid); with SRL_MB_PART=0 it gathers the minibatch's lane items as before.  Same sums up to the order
+    of the float64 additions: gradients within 1e-12 relative of each other, eager and from the graph."""
+    cfg = CASES[name]
+    a, pol_dev, ref, pa = _setup(cfg, seed=8)
+    monkeypatch.setenv("SRL_MB_PART", "0")
+    b, _, _, _ = _setup(cfg, seed=8)
+    monkeypatch.delenv("SRL_MB_PART")
+    assert a.mb_part is not None and b.mb_part is None
+    a.run_device(pol_dev, use_graph=False)
+    b.run_device(pol_dev, use_graph=False)
+    assert a._part_valid and not b._part_valid
+    _compare(a, cfg, ref, pa)
+    torch.testing.assert_close(a.grads_all, b.grads_all, rtol=1e-6, atol=1e-12)
+    torch.testing.assert_close(a.out, b.out, rtol=1e-9, atol=1e-12)
+    eager = a.grads_all.clone()
+    a.grads_all.zero_()
+    a.run_device(pol_dev, use_graph=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a.grads_all, eager)
 
 
 def test_step_explicit_gather_equals_fused_gather():

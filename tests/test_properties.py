@@ -77,3 +77,17 @@ def test_wire_round_trip_of_arbitrary_nested_records(x, method):
             want = va.astype(np.uint8) if (va.dtype == np.bool_ and method == "raw_bytes") else va
             assert vb.dtype == want.dtype and vb.shape == want.shape and np.array_equal(vb, want)
     assert y.metadata == dict(tag="t", n=3)
+
+
+def test_feistel_permutation_and_its_inverse_on_the_host(tmp_path):
+    """perm.cuh on the host (its functions are __host__ __device__): perm_at is a permutation of [0, n_env) and perm_pos_of
+    undoes it -- the scan kernel derives every lane's minibatch from the inverse (tests/native/perm_inverse.cu)."""
+    import os
+    import subprocess
+    from srl_b200.build import CSRC, INCLUDE, find_nvcc
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "native", "perm_inverse.cu")
+    exe = str(tmp_path / "perm_inverse")
+    subprocess.run([find_nvcc(), "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", CSRC, "-I", INCLUDE, "-o", exe, src],
+                   check=True, capture_output=True)
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0 and "bad=0" in run.stdout, run.stdout + run.stderr
