@@ -622,7 +622,10 @@ def run_ours(args, cfg_full, rank, world, local_rank):
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     windows = []
-    step = lambda: hp.run_device(pol_dev, use_graph=True)
+    launch = args.launch if hp.plan_supported() else "graph"
+    steps_by_launch = {"graph": lambda: hp.run_device(pol_dev, use_graph=True),
+                       "plan": lambda: hp.run_device(pol_dev, plan=True)}
+    step = steps_by_launch[launch]
     for _ in range(max(args.warmup, 3)):
         flush_l2()
         step()
@@ -637,6 +640,14 @@ def run_ours(args, cfg_full, rank, world, local_rank):
 
     # ---- warm-L2 variant (no flush), informational ------------------------------------------------
     ms_warm = timed_steps(min(args.steps, 200), step, flush_first=False)
+    # ---- the other way of issuing the same launches (CUDA graph <-> recorded plan of stream launches), informational
+    other = "plan" if launch == "graph" else "graph"
+    ms_other = None
+    if hp.plan_supported():
+        for _ in range(3):
+            flush_l2()
+            steps_by_launch[other]()
+        ms_other = statistics.mean(timed_steps(min(args.steps, 300), steps_by_launch[other]))
 
     # ---- the same work in the order a trainer must issue it: one loss launch per minibatch, each behind the previous
     # (minibatch j+1's policy outputs do not exist before the optimizer step on minibatch j) -- one stream, a linear graph
@@ -812,6 +823,9 @@ def run_ours(args, cfg_full, rank, world, local_rank):
             roofline=roofline, kernels=kern,
             step=dict(algorithmic_bytes=step_bytes, gbs=step_bytes / ms_per_step / 1e6,
                       frac_of_peak=step_bytes / ms_per_step / 1e6 / peak,
+                      launch=launch + (": one CUDA graph replay per step" if launch == "graph" else
+                                       ": the step's recorded C-ABI calls issued as plain stream launches (HotPath.run_device(plan=True))"),
+                      ms_per_step_other_launch={other: ms_other},
                       ms_per_step_l2_warm=statistics.mean(ms_warm),
                       value_l2_warm=total_transitions / (statistics.mean(ms_warm) * 1e-3)),
             step_trainer_order=trainer_order, trainer_step=trainer_line, extra=extra,
@@ -881,6 +895,8 @@ def main():
                     help="N > 1: the full config per GPU (weak) or the config's environments split over the GPUs (strong)")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
+    ap.add_argument("--launch", default="graph", choices=["graph", "plan"],
+                    help="how the timed step is issued: one CUDA graph replay, or the recorded plan of stream launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the K1 / K4b / trainer_step lines")
     ap.add_argument("--no-parity-check", action="store_true")

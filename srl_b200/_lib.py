@@ -157,6 +157,44 @@ def check(fn_name: str, status: int) -> None:
         raise SrlCudaError(fn_name, status, msg.decode("utf-8", "replace") if msg else "")
 
 
+_recording = None  # a list while HotPath records a launch plan (record_calls)
+
+
 def call(fn_name: str, *args) -> None:
     """Calls a status-returning entry point and raises on failure."""
+    if _recording is not None:
+        _recording.append((fn_name, args))
     check(fn_name, getattr(load_library(), fn_name)(*args))
+
+
+class record_calls:
+    """Context manager: every `call()` inside is also appended to `calls` as (entry point, ctypes arguments) -- the launch plan
+    HotPath replays with `replay_calls` (the same C-ABI calls on the same buffers, none of the Python-side checking)."""
+
+    def __init__(self, calls: list):
+        self.calls = calls
+
+    def __enter__(self):
+        global _recording
+        if _recording is not None:
+            raise RuntimeError("record_calls does not nest")
+        _recording = self.calls
+        return self.calls
+
+    def __exit__(self, *exc):
+        global _recording
+        _recording = None
+        return False
+
+
+def bind_calls(calls):
+    """[(entry point name, args)] -> [(name, bound foreign function, args)] for replay_calls."""
+    lib = load_library()
+    return [(name, getattr(lib, name), args) for name, args in calls]
+
+
+def replay_calls(bound) -> None:
+    for name, fn, args in bound:
+        status = fn(*args)
+        if status != 0:
+            check(name, status)

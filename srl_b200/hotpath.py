@@ -436,10 +436,16 @@ class HotPath:
                 main.wait_stream(st)
         self.finalize()
 
-    def run_device(self, pol, use_graph: bool = True) -> None:
+    def run_device(self, pol, use_graph: bool = True, plan: bool = False) -> None:
         """The whole step on resident inputs: advantages() then every (epoch, minibatch) loss.
         pol[e][j] = (new_logp, v_pred, entropy), each [T, n_mb] float32 on device.  With use_graph the
-        launches are captured once into a CUDA graph (two graphs around the all-reduce when distributed)."""
+        launches are captured once into a CUDA graph (two graphs around the all-reduce when distributed).
+        plan=True: the step's C-ABI calls are recorded once (on the first call: an ordinary eager step) and from then on
+        issued again as they are -- plain stream launches of the same kernels on the same buffers, without the Python-side
+        argument checking of `ops` (tens of microseconds per launch) and without a graph launch."""
+        if plan:
+            self._run_plan(pol)
+            return
         if not use_graph:
             self.advantages()
             self._run_losses(pol)
@@ -454,6 +460,35 @@ class HotPath:
             self.exchange()
             self._graph.replay()
         self._table_valid = not self._lazy_table  # a replay does not run ensure_table()'s python side
+        self.step_count += 1
+
+    def plan_supported(self) -> bool:
+        """A recorded plan holds this library's launches only: every kernel of the step must be one (no torch.distributed
+        collective between them, no side streams)."""
+        return (self.pg is None or self.peer is not None) and self._immediate and \
+            (self.minibatches == 1 or ops.pdl_enabled())
+
+    def _run_plan(self, pol) -> None:
+        from srl_b200 import _lib
+        st = torch.cuda.current_stream().cuda_stream
+        if getattr(self, "_plan", None) is None or self._plan_pol is not pol or self._plan_stream != st:
+            if not self.plan_supported():
+                raise RuntimeError("HotPath.run_device(plan=True): the step holds launches that are not this library's (a "
+                                   "torch.distributed exchange, side streams); use the CUDA graph")
+            # like a captured graph, the plan re-uses the launch arguments of step_count == 0 (its permutations) every step
+            saved, self.step_count = self.step_count, 0
+            calls = []
+            try:
+                with _lib.record_calls(calls):
+                    self.advantages()
+                    self._run_losses(pol)
+            finally:
+                self.step_count = saved
+            self._plan, self._plan_pol, self._plan_stream = _lib.bind_calls(calls), pol, st
+            self.plan_launch_calls = len(calls)
+        else:
+            _lib.replay_calls(self._plan)
+            self._table_valid = not self._lazy_table
         self.step_count += 1
 
     def run_trainer_order(self, pol, use_graph: bool = True) -> None:

@@ -145,6 +145,27 @@ def test_step_uses_the_scan_shares_and_agrees_with_the_lane_gather(name, monkeyp
     assert torch.equal(a.grads_all, eager)
 
 
+@pytest.mark.parametrize("name", ["atari_mb", "mb_shares", "smac_popart", "one_pass"])
+def test_step_recorded_plan_matches_oracle(name):
+    """HotPath.run_device(plan=True): the first call records the step's C-ABI calls (an eager step), the following calls
+    issue them again as they are.  Both must be the oracle's step; a replay reproduces the recording bit for bit."""
+    cfg = CASES[name]
+    hp, pol_dev, ref, pa = _setup(cfg, seed=9)
+    assert hp.plan_supported()
+    hp.run_device(pol_dev, plan=True)  # records
+    _compare(hp, cfg, ref, pa)
+    first = hp.grads_all.clone()
+    assert 1 <= hp.plan_launch_calls <= hp.count_launches()  # C-ABI calls; one call may launch two kernels
+    hp.grads_all.zero_()
+    hp.out.zero_()
+    if cfg.popart:  # the recording advanced the PopArt EMA; restart it for the comparison
+        hp.popart_state.zero_()
+        hp.popart_ms.copy_(torch.tensor([0.0, 0.1, 0.0, 0.1], dtype=torch.float64))
+    hp.run_device(pol_dev, plan=True)  # replays
+    _compare(hp, cfg, ref, pa)
+    assert torch.equal(hp.grads_all, first)
+
+
 def test_step_explicit_gather_equals_fused_gather():
     cfg = CASES["atari_mb"]
     a, pol_dev, ref, pa = _setup(cfg, seed=5, fuse_gather=True, batch_losses=False)
