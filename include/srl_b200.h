@@ -372,6 +372,23 @@ typedef struct srl_leaf_desc {
 int srl_batch_gather(const srl_leaf_desc* leaves_host, int n_leaves, const int32_t* idx /* device [B] or NULL */,
                      int L, int B, srl_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (f)4  What a recurrent policy needs from a minibatch besides the chunked leaves, in one launch.  Replaces, for the
+ * reset flags and the hidden states, recursive_apply(sample, to_chunk) + x[0].transpose(0, 1)
+ * (legacy/algorithm/ppo/actor_critic_policies/actor_critic_policy.py:348-363) and the reset handling of
+ * AutoResetRNN.forward (legacy/algorithm/modules/autoreset_rnn.py:42-60): the rows in which any lane resets
+ * ((masks[1:] == 0).any(dim=1).nonzero(), a host synchronisation in the reference) and `hxs * masks[0]`.
+ *   on_reset    uint8  [T, B]                (the sample's rows from burn_in on)
+ *   hx          float32 [T, B, layers, H]    per-step hidden states, or NULL (then hx0 NULL)
+ *   env_idx     int32  [n]                   the minibatch's lanes (srl_philox_perm slice)
+ *   reset_chunk uint8  [T/C, C*n]  out       = to_chunk(on_reset[:, env_idx], C): column c*n + j = chunk c, lane env_idx[j]
+ *   row_any     uint8  [T/C]       out       1 where some column of that chunk-row resets (row 0 included)
+ *   hx0         float32 [layers, C*n, H] out = hx[c*T/C, env_idx[j]] layer-major, times (1 - reset_chunk[0])
+ * T % num_chunks != 0 is SRL_ERR_INVALID_ARG (the reference raises IndexError, utils.py:176-179). */
+int srl_rnn_chunk_prep(const uint8_t* on_reset, const float* hx, const int32_t* env_idx, int T, int B, int n,
+                       int num_chunks, int layers, int H, uint8_t* reset_chunk, uint8_t* row_any, float* hx0,
+                       srl_stream_t stream);
+
 /* HOST helper of the device sample buffer (no CUDA call; host pointers): copies `bytes` bytes with up to `threads`
  * participants (a persistent pool inside the library + the caller; small copies fall back to one memcpy).  It replaces the
  * single-threaded copy into the staging block that bounded the per-sample `put` -- in the reference that copy is the

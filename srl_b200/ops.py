@@ -794,6 +794,47 @@ def gather_to_chunk(x: torch.Tensor, env_idx: torch.Tensor, num_chunks: int) -> 
     return out
 
 
+def rnn_chunk_prep(on_reset: torch.Tensor, env_idx: torch.Tensor, num_chunks: int, hx: Optional[torch.Tensor] = None):
+    """What a recurrent policy needs from a minibatch's reset flags and hidden states, in ONE launch (srl_rnn_chunk_prep):
+
+      reset_chunk uint8 `[T//C, C*n]`        == `to_chunk(on_reset[:, env_idx], C)`
+      row_any     uint8 `[T//C]`             1 where any column of that chunk-row resets -- `reset_segments(row_any)` gives
+                                             AutoResetRNN's segment boundaries (autoreset_rnn.py:46-47) from ONE small
+                                             device-to-host read instead of `(masks[1:] == 0).any(dim=1).nonzero()`
+      hx0         float32 `[layers, C*n, H]` == `to_chunk(hx[:, env_idx], C)[0].transpose(0, 1) * (1 - reset_chunk[0])`
+                                             (actor_critic_policy.py:362-363 + the first segment's `hxs * masks[0]`), or None
+
+    `on_reset` uint8 `[T, B]` or `[T, B, 1]`, `hx` float32 `[T, B, layers, H]`, `env_idx` int32 `[n]`.  Bit-exact."""
+    _check(on_reset, torch.uint8, "on_reset")
+    _check(env_idx, torch.int32, "env_idx")
+    T, B = _rows_lanes(on_reset)
+    if T % num_chunks != 0:  # same error as the reference (utils.py:176-179)
+        raise IndexError(f"The first dimension(usually the step/time) {T} must be a multiple of "
+                         f"num_chunks {num_chunks}. This usually means the sample_steps(config:AgentSpec) "
+                         f"is not dividable by chunk_len(config:Policy).")
+    n, Tc = env_idx.numel(), T // num_chunks
+    dev = on_reset.device
+    reset_chunk = torch.empty((Tc, num_chunks * n), dtype=torch.uint8, device=dev)
+    row_any = torch.zeros((Tc,), dtype=torch.uint8, device=dev)
+    hx0, layers, H = None, 0, 0
+    if hx is not None:
+        _check(hx, torch.float32, "hx")
+        if hx.dim() != 4 or tuple(hx.shape[:2]) != (T, B):
+            raise ValueError(f"hx: expected [T, B, layers, H] = [{T}, {B}, layers, H], got {tuple(hx.shape)}")
+        layers, H = int(hx.shape[2]), int(hx.shape[3])
+        hx0 = torch.empty((layers, num_chunks * n, H), dtype=torch.float32, device=dev)
+    _lib.call("srl_rnn_chunk_prep", _ptr(on_reset), _ptr(hx), _ptr(env_idx), T, B, n, int(num_chunks), layers, H,
+              _ptr(reset_chunk), _ptr(row_any), _ptr(hx0), _stream())
+    return reset_chunk, row_any, hx0
+
+
+def reset_segments(row_any: torch.Tensor) -> list:
+    """AutoResetRNN's `has_zeros` (autoreset_rnn.py:46-47) from `rnn_chunk_prep`'s row_any: `[0] + (rows >= 1 in which some
+    lane resets) + [T']` -- the RNN runs each segment [a, b) in one call and masks its hidden state at every boundary."""
+    flags = row_any.cpu()
+    return [0] + [int(t) + 1 for t in torch.nonzero(flags[1:]).view(-1)] + [int(flags.shape[0])]
+
+
 def back_to_trajectory(x: torch.Tensor, num_chunks: int) -> torch.Tensor:
     """modules.back_to_trajectory (utils.py:183-195), the inverse of to_chunk: `[T//C, B*C, *D]` -> `[T, B, *D]`."""
     if not isinstance(x, torch.Tensor) or not x.is_cuda:

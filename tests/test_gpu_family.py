@@ -269,3 +269,33 @@ def test_scan_minibatch_shares_add_up_to_the_minibatch_sums(N, n_env, group, epo
                 np.add.at(want[:, k], lanes // 32, lp[k, lanes])
             np.testing.assert_allclose(tb[e * mbs + j, :, :3], want, rtol=1e-14, atol=1e-14)
             assert np.array_equal(tb[e * mbs + j, :, 0], np.bincount(lanes // 32, weights=lp[0, lanes], minlength=ctas))
+
+
+@pytest.mark.parametrize("T,B,C,n,layers,H", [(8, 6, 2, 4, 1, 16), (12, 40, 4, 17, 2, 33), (400, 64, 40, 32, 1, 64),
+                                              (10, 9, 1, 9, 1, 8), (6, 300, 3, 300, 1, 4)])
+def test_rnn_chunk_prep_equals_the_reference_expressions(ops, T, B, C, n, layers, H):
+    """(f)4: reset flags chunked, AutoResetRNN's segment boundaries and the masked, layer-major chunk-start hidden states in
+    one launch == to_chunk(x[:, env_idx], C) (utils.py:164-180), `(masks[1:] == 0).any(dim=1).nonzero()`
+    (autoreset_rnn.py:46-47) and `x[0].transpose(0, 1)` times `masks[0]` (actor_critic_policy.py:362-363,
+    autoreset_rnn.py:55), bit for bit (signed zeros included)."""
+    g = torch.Generator().manual_seed(T * 7 + B)
+    to_chunk = lambda x: torch.cat(torch.split(x, T // C, dim=0), dim=1)
+    idx = torch.randperm(B, generator=g)[:n].to(torch.int32)
+    on_reset = (torch.rand((T, B, 1), generator=g) < (0.5 / max(1, n * C // 4))).to(torch.uint8)
+    on_reset[0, idx[0].item()] = 1  # a reset in the first row: its chunk-start hidden state is masked
+    hx = torch.randn((T, B, layers, H), generator=g)
+    sample_reset = to_chunk(on_reset[:, idx.long()].float())  # [Tc, C*n, 1] as the policy sees it
+    masks = 1 - sample_reset
+    has_zeros = (masks[1:] == 0.0).any(dim=1).nonzero(as_tuple=True)[0].numpy()
+    want_segments = [0] + (has_zeros + 1).tolist() + [T // C]
+    want_hx0 = to_chunk(hx[:, idx.long()])[0].transpose(0, 1) * masks[0].view(1, -1, 1)
+    got_reset, row_any, got_hx0 = ops.rnn_chunk_prep(on_reset.cuda(), idx.cuda(), C, hx=hx.cuda())
+    assert torch.equal(got_reset.cpu(), sample_reset[..., 0].to(torch.uint8))
+    assert ops.reset_segments(row_any) == want_segments
+    assert int(row_any[0]) == int(sample_reset[0].any())
+    assert got_hx0.shape == want_hx0.shape
+    assert torch.equal(got_hx0.cpu().view(torch.int32), want_hx0.contiguous().view(torch.int32))
+    only_flags = ops.rnn_chunk_prep(on_reset.cuda(), idx.cuda(), C)
+    assert only_flags[2] is None and torch.equal(only_flags[0], got_reset) and torch.equal(only_flags[1], row_any)
+    with pytest.raises(IndexError, match="must be a multiple of"):
+        ops.rnn_chunk_prep(torch.zeros((7, 4), dtype=torch.uint8).cuda(), idx[:2].cuda() % 4, 2)
