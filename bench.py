@@ -716,6 +716,10 @@ def run_ours(args, cfg_full, rank, world, local_rank):
     g_loss = graph_of(lambda: hp._run_losses(pol_dev))
     lf = hp.leaf
     pack_kw = dict(old_logp=lf["old_logp"], pack=hp.pack, lane_aos=hp.lane_aos) if hp.pack is not None else {}
+    if hp._perm_fused:  # the scan as the step issues it: with the permutations (and the minibatch shares) computed on the side
+        saved_count, hp.step_count = hp.step_count, 0
+        pack_kw["perm_job"] = hp.perm_job(with_part=hp.lane_aos is not None)
+        hp.step_count = saved_count
     g_gae = graph_of(lambda: ops.gae_scan(lf["reward"], lf["value"], lf["done"], lf["truncated"], lf["on_reset"], cfg.gamma,
                                           cfg.lmbda, row_lo=hp.row_lo, row_hi=hp.row_hi,
                                           popart_mean_std=hp.popart_mean_std(), adv=hp.adv, ret=hp.ret,

@@ -244,11 +244,7 @@ class HotPath:
                 # the scan kernel's own idle threads compute the permutations (one launch and one completion hop less
                 # between the scan and the loss); where the scan kernel for this shape cannot, the stand-alone kernel runs
                 # behind the scan as before
-                blk = self.shuffle_block
-                job = dict(seed=self.seed + self.step_count, epoch=0, n_epochs=self.epochs, n_env=self.B // blk,
-                           group=self.A * blk, out=self.perm)
-                if self.mb_part is not None and "lane_aos" in kw:
-                    job.update(minibatches=self.minibatches, part=self.mb_part)
+                job = self.perm_job(with_part="lane_aos" in kw)
                 kw["perm_job"] = job
             ops.gae_scan(lf["reward"], lf["value"], lf["done"], lf["truncated"], lf["on_reset"], self.gamma, self.lmbda,
                          row_lo=self.row_lo, row_hi=self.row_hi, popart_mean_std=self.popart_mean_std(), adv=self.adv,
@@ -272,6 +268,16 @@ class HotPath:
         self._table_valid = False
         if not self._lazy_table:
             self.ensure_table()
+
+    def perm_job(self, with_part: bool = True) -> dict:
+        """The permutation job advantages() hands to the scan (ops.gae_scan, `perm_job`): this step's seed, every epoch, and
+        -- where the loss adds its own statistics -- the table of per-CTA minibatch shares."""
+        blk = self.shuffle_block
+        job = dict(seed=self.seed + self.step_count, epoch=0, n_epochs=self.epochs, n_env=self.B // blk,
+                   group=self.A * blk, out=self.perm)
+        if self.mb_part is not None and with_part:
+            job.update(minibatches=self.minibatches, part=self.mb_part)
+        return job
 
     def ensure_table(self) -> None:
         """Produces local_stats / global_stats for the current sample if advantages() left them for later."""
