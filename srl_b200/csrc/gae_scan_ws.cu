@@ -31,9 +31,6 @@ __device__ __forceinline__ void st_cg256(float4* p, float a0, float a1, float a2
 }
 
 constexpr int kR = 16;  // rows per chunk
-#ifndef SRL_WS_SKIP_PAD
-#define SRL_WS_SKIP_PAD 0  // A/B knob (profiles/microbench/r2x_final.sh)
-#endif
 // Ring depth kS (template parameter): 3 slots when several CTAs share an SM; kDeep when the batch has at most one CTA per
 // SM anyway (cfg2: 128 lane groups) -- the whole trajectory of up to kDeep * kR rows is requested from HBM at once (one
 // exposed DRAM round trip instead of one per ring turn), and the workers run the delta pass of all resident chunks ahead
@@ -141,26 +138,20 @@ __global__ void __launch_bounds__(32 * (2 + kW)) gae_scan_ws_kernel(const __grid
       const double* sd = reinterpret_cast<const double*>(slot + SL::delta);
       const uint8_t* sm = slot + SL::mflag;
       float* sa = reinterpret_cast<float*>(slot + SL::adv);
-      // When the first chunk processed holds nothing but the padding row and the zero-filled rows behind the trajectory
-      // (L - 1 a multiple of kR: cfg2's 129 rows), all its deltas and carry flags are 0 and the carry stays 0: its 16 chain
-      // steps are left out (0 + 0 * 0 = 0 either way).  One uniform branch per chunk; nothing inside the chain (a per-row
-      // `if (row is real)` put two selects on it: +1 us per step, profiles/r2_notes.md).
-      if (SRL_WS_SKIP_PAD && c == 0 && (L - 1) % kR == 0) {
+      // (Leaving out the chain steps of the rows behind the trajectory's end -- 15 of cfg2's 144 -- was measured twice:
+      // with a per-row predicate it put two selects on the chain, +1.0 us per step; as one uniform branch around the first
+      // chunk it changed nothing, 30.41 -> 30.55 us: the scanner waits for the workers there.  profiles/r2_notes.md)
+      double d[kR];
+      double m[kR];
 #pragma unroll
-        for (int r = 0; r < kR; ++r) sa[r * 32 + lane] = 0.f;
-      } else {
-        double d[kR];
-        double m[kR];
+      for (int r = 0; r < kR; ++r) {
+        d[r] = sd[r * 32 + lane];
+        m[r] = sm[r * 32 + lane] ? gl : 0.0;
+      }
 #pragma unroll
-        for (int r = 0; r < kR; ++r) {
-          d[r] = sd[r * 32 + lane];
-          m[r] = sm[r * 32 + lane] ? gl : 0.0;
-        }
-#pragma unroll
-        for (int r = kR - 1; r >= 0; --r) {
-          g = __dadd_rn(d[r], __dmul_rn(m[r], g));
-          sa[r * 32 + lane] = static_cast<float>(g);  // adv.float(), gae.py:97
-        }
+      for (int r = kR - 1; r >= 0; --r) {
+        g = __dadd_rn(d[r], __dmul_rn(m[r], g));
+        sa[r * 32 + lane] = static_cast<float>(g);  // adv.float(), gae.py:97
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->scanned[s]);

@@ -10,8 +10,10 @@
 //  * the pack was one 16-byte item per transition: a per-environment permutation fetched a 32-byte sector for 16 bytes.
 //    K2 interleaves row pairs -- pack2[t / 2][lane] = 32 bytes = {row t, row t+1} of {old_logp, value, ret, mask ? adv :
 //    NaN} -- and a thread fetches its lane's pair as one 256-bit load: every sector that moves is used whole.
-//  * the minibatch statistics: ONE CTA per problem adds K2's per-lane sums (lane_aos, one 256-bit gather per lane),
-//    exchanges them with the other ranks when there are any, and publishes them in the workspace slot; the others wait.
+//  * the minibatch statistics: where the scan computed the permutation itself it also left every scan CTA's share of every
+//    minibatch's sums (minibatch_part): a loss CTA adds N / 32 contiguous items -- one round of loads.  Otherwise ONE CTA per
+//    problem adds K2's per-lane sums (lane_aos, one 256-bit gather per lane behind the index load) and publishes them in
+//    the workspace slot; the others wait.  With several ranks that CTA also exchanges the sums before it publishes them.
 //  * the grid is (problems, slices): a problem's (column tile, row pair) units are numbered in one line and dealt to its
 //    CTAs in equal runs (+-1 unit), for any shape; 64-thread CTAs keep the units fine; the whole grid is one wave.
 //  * the tail: one block barrier, one partial row per CTA, no fence, no atomic -- published words validate themselves
@@ -33,9 +35,6 @@ namespace {
 #endif
 #ifndef SRL_PAIR_PF_AHEAD
 #define SRL_PAIR_PF_AHEAD 2
-#endif
-#ifndef SRL_PAIR_PART_EACH
-#define SRL_PAIR_PART_EACH 1
 #endif
 constexpr int kPairThreads = SRL_PAIR_THREADS;
 constexpr int kPairLanes = 2 * kPairThreads;  // lanes per column tile
@@ -458,9 +457,10 @@ __global__ void __launch_bounds__(kPairThreads, SRL_PAIR_MIN_BLOCKS) ppo_loss_pa
       if (s.lane_aos != nullptr) {
         const double* part =
             s.part != nullptr ? s.part + static_cast<size_t>(s.part_first + static_cast<int>(blockIdx.x)) * s.part_ctas * 4 : nullptr;
-        // with the scan's shares and one rank, every CTA adds them itself (SRL_PAIR_PART_EACH): 4 KB of contiguous L2 hits
-        // per CTA against a publication by the problem's first CTA and a poll by the others
-        const bool each = SRL_PAIR_PART_EACH && part != nullptr && b.xv.world <= 1;
+        // with the scan's shares and one rank, every CTA adds them itself: 4 KB of contiguous L2 hits per CTA, no
+        // publication by the problem's first CTA and no polling by the others (measured equal to publishing them, 30.2 us
+        // either way, profiles/r2_notes.md r2s; with several ranks the first CTA exchanges and publishes as before)
+        const bool each = part != nullptr && b.xv.world <= 1;
         uf = self_uniforms_aos(s.lane_aos, pr.lane_idx, part, s.part_ctas, n, h.adv_eps, mask_sum, s_part, b.xv,
                                static_cast<int>(blockIdx.x), blockIdx.y == 0, pr.slot,
                                pr.out != nullptr && gridDim.y > 1 && !each, xchg_seq);
