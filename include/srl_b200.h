@@ -389,6 +389,18 @@ int srl_rnn_chunk_prep(const uint8_t* on_reset, const float* hx, const int32_t* 
                        int num_chunks, int layers, int H, uint8_t* reset_chunk, uint8_t* row_any, float* hx0,
                        srl_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (f)2  HOST decoders of the compressed sample-wire payloads (no CUDA call; host pointers): what blosc.decompress does
+ * for the frames blosc.compress(payload, typesize=4, cname='lz4') writes (base/namedarray.py:126,150,184-185,203), decoded
+ * straight into the destination the caller names -- the buffer's pinned staging block -- with up to `threads`
+ * participants over the frame's blocks.  Byte-shuffled or plain, split or unsplit, LZ4 / LZ4HC streams and stored
+ * (memcpyed) frames; other codec families and bit-shuffle are SRL_ERR_UNSUPPORTED.  Malformed input is SRL_ERR_INVALID_ARG.
+ * srl_blosc1_info reads the 16-byte header (any pointer may be NULL); srl_lz4_block_decompress decodes one raw LZ4 block. */
+int srl_blosc1_info(const void* src, size_t src_bytes, size_t* nbytes, size_t* cbytes, size_t* blocksize, int* typesize,
+                    int* flags);
+int srl_blosc1_decompress(const void* src, size_t src_bytes, void* dst, size_t dst_bytes, int threads);
+int srl_lz4_block_decompress(const void* src, size_t src_bytes, void* dst, size_t dst_capacity, size_t* written);
+
 /* HOST helper of the device sample buffer (no CUDA call; host pointers): copies `bytes` bytes with up to `threads`
  * participants (a persistent pool inside the library + the caller; small copies fall back to one memcpy).  It replaces the
  * single-threaded copy into the staging block that bounded the per-sample `put` -- in the reference that copy is the

@@ -112,6 +112,10 @@ SIGNATURES = {
     "srl_rnn_chunk_prep": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     "srl_host_copy": (c_int, [c_void_p, c_void_p, c_size_t, c_int]),
+    "srl_blosc1_info": (c_int, [c_void_p, c_size_t, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_int),
+                                POINTER(c_int)]),
+    "srl_blosc1_decompress": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_int]),
+    "srl_lz4_block_decompress": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, POINTER(c_size_t)]),
     "srl_group_stats_xchg": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                      c_void_p, c_void_p]),
     "srl_xchg_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),

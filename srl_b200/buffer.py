@@ -50,6 +50,12 @@ class ReplayEntry:
         return len(self.sample)
 
 
+def _leaf(v):
+    """A leaf as the staging code looks at it (dtype, shape, nbytes, size): an ndarray, a still-compressed wire payload (kept
+    as it is -- _stage decodes it straight into the pinned block) or anything array-like."""
+    return v if isinstance(v, (np.ndarray, wire.CompressedLeaf)) else np.asarray(v)
+
+
 class _Layout:
     """Byte layout of one staged sample: leaf name -> (offset, dtype, shape [L, ...]); fixed by the first sample."""
 
@@ -61,7 +67,7 @@ class _Layout:
         for k, v in leaves:
             if v is None:
                 continue
-            v = np.asarray(v)
+            v = _leaf(v)
             if self.L is None:
                 self.L = v.shape[0]
             if v.shape[0] != self.L:
@@ -81,7 +87,7 @@ class _Layout:
             example[k] = np.empty(shape, dtype=dtype)
         for k, v in leaves:
             if example.get(k) is None:
-                example[k] = None if v is None else np.asarray(v)
+                example[k] = None if v is None else _leaf(v)
         return _Layout(sorted(example.items(), key=lambda kv: kv[0]))
 
 
@@ -136,12 +142,14 @@ class DeviceSlabBuffer:
     def put_frames(self, b) -> bool:
         """`put(namedarray.loads(b))` for a framed message (raw_bytes, raw_compress, compress_pickle, obs_compress,
         compress_except_policy_state; base/namedarray.py:115-128,166-218) without building the sample: every leaf's payload
-        is copied once, from the received (or, for a compressed leaf, the decompressed) bytes into the pinned staging
-        block.  The compressed methods need the `blosc` package, as in the reference."""
+        is written once into the pinned staging block -- copied from the received bytes, or, for a compressed leaf, decoded
+        there by the library's own Blosc-1 / LZ4 decoder (srl_blosc1_decompress; `wire.codec()` says when the `blosc`
+        package decodes instead)."""
         if not self.batch_size:
             return self.put(wire.loads(b))
-        entries, metadata = wire.frames(b)
-        leaves = [(k, None if dt is None else np.frombuffer(p, dtype=dt).reshape(shape)) for k, dt, shape, p in entries]
+        entries, metadata = wire.frames(b, lazy=True)  # compressed payloads stay compressed until _stage decodes them
+        leaves = [(k, None if dt is None else (p if isinstance(p, wire.CompressedLeaf) else
+                                               np.frombuffer(p, dtype=dt).reshape(shape))) for k, dt, shape, p in entries]
         shape = next(v.shape for k, v in leaves if k == "on_reset")
         stamp = np.full(shape=shape, fill_value=int(time.time()), dtype=np.int64)  # base/buffer.py:114-116
         leaves = [(k, stamp if k == "trainer_worker_recv_timestamp" else v) for k, v in leaves]
@@ -199,7 +207,7 @@ class DeviceSlabBuffer:
         """Leaves that cannot (or need not) live on the device: non-numeric dtypes -- real SRL samples carry `policy_name`
         as a '<U..' string array (policy_worker.py:186; the trainer worker clears it after get(), trainer_worker.py:169) --
         and zero-size leaves.  They stay on the host and are stacked with np.stack, as the reference does for every leaf."""
-        v = np.asarray(v)
+        v = _leaf(v)
         return v.dtype.kind not in "fiub" or v.size == 0
 
     def _stage(self, leaves, metadata) -> None:
@@ -225,12 +233,14 @@ class DeviceSlabBuffer:
         for k, v in leaves:
             if v is None:
                 continue
-            v = np.asarray(v)
+            v = _leaf(v)
             if not lay.matches(k, v):
                 raise ValueError(f"leaf {k}: dtype/shape {v.dtype}{v.shape} differs from the first sample's "
                                  f"{lay.spec.get(k, ('-', None, None))[1:]} (samples of one buffer share their layout)")
             off = lay.spec[k][0]
-            if self.copy_threads > 1 and v.nbytes >= _MT_COPY_MIN:
+            if isinstance(v, wire.CompressedLeaf):  # Blosc-1 / LZ4 frame -> pinned block, one pass (csrc/blosc_decode.cu)
+                v.decode_into(pin[off:off + v.nbytes], self.copy_threads)
+            elif self.copy_threads > 1 and v.nbytes >= _MT_COPY_MIN:
                 src = np.ascontiguousarray(v)
                 ops._lib.call("srl_host_copy", pin.ctypes.data + off, src.ctypes.data, src.nbytes, self.copy_threads)
             else:

@@ -16,11 +16,20 @@ For the array methods the body is four frames per leaf -- key, dtype, shape, pay
   compress_except_policy_state  0008    four frames per leaf, all payloads but those with 'policy_state' in the key compressed
 
 The codec is the third-party `blosc` package (`blosc.compress(payload, typesize=4, cname='lz4')`, namedarray.py:126),
-imported lazily exactly where the reference imports it (namedarray.py:101-103,168-171): with blosc installed (any SRL
-deployment that uses these methods) all eight methods work; without it (this image, /root/reference) the compressed
-ones raise ModuleNotFoundError, as the reference's do.  What is pinned here is the FRAMING -- which leaves are compressed,
-frame order, None leaves, metadata -- against messages the unmodified reference wrote with a stand-in codec injected as
-`blosc` (tests/golden/wire.npz, tests/test_wire.py); the codec's own byte format never passes through this file's logic.
+imported lazily exactly where the reference imports it (namedarray.py:101-103,168-171).  ENCODING always goes through it:
+without it (this image, /root/reference) `dumps` of a compressed method raises ModuleNotFoundError, as the reference's does.
+DECODING goes through the library's own decoder of the Blosc-1 / LZ4 frame (csrc/blosc_decode.cu: srl_blosc1_decompress) --
+straight into the destination the caller names, which for `DeviceSlabBuffer.put_frames` is the pinned staging block: one pass
+over the payload instead of blosc.decompress -> bytes -> copy -- chosen per process by `codec()`:
+  * `blosc` importable: the native decoder is cross-checked ONCE against frames the real package writes (several sizes,
+    compressible and incompressible payloads, the reference's typesize 4); it is used only if every one decodes identically,
+    otherwise a warning is issued and the package decodes;
+  * `blosc` not importable: the native decoder (its LZ4 layer is pinned to liblz4, its framing follows the published layout
+    but is UNPINNED against blosc itself -- there is no blosc here to write vectors; csrc/blosc_decode.cu, tests/blosc1_writer.py);
+  * `SRL_B200_WIRE_CODEC=blosc|native` overrides.
+What is pinned against the reference is the FRAMING of the message -- which leaves are compressed, frame order, None leaves,
+metadata -- from messages the unmodified reference wrote with a stand-in codec injected as `blosc` (tests/golden/wire.npz,
+tests/test_wire.py).
 
 The reference's `loads` allocates a fresh ndarray per leaf per message on the trainer's main thread
 (distributed/system/sample_stream.py:176-198) and the buffer then copies every leaf again in `np.stack`.  `frames()`
@@ -51,6 +60,122 @@ _COMPRESS_IF = {RAW_BYTES: lambda k: False, RAW_COMPRESS: lambda k: True, COMPRE
 def _blosc():
     import blosc  # third-party; raises ModuleNotFoundError where it is not installed, like namedarray.py:103,171
     return blosc
+
+
+DECODE_THREADS = 1  # participants of one native decode (the frame's blocks are independent); DeviceSlabBuffer sets its own
+_codec_choice: Optional[str] = None
+
+
+def _native_decode_into(src, dst: np.ndarray, threads: int = 0) -> None:
+    """One Blosc-1 frame -> `dst` (a contiguous uint8 array of exactly the frame's decoded size)."""
+    from srl_b200 import _lib
+    buf = np.frombuffer(src, dtype=np.uint8)
+    _lib.call("srl_blosc1_decompress", buf.ctypes.data, buf.size, dst.ctypes.data if dst.size else None, dst.size,
+              int(threads or DECODE_THREADS))
+
+
+def _native_nbytes(src) -> int:
+    import ctypes
+    from srl_b200 import _lib
+    buf = np.frombuffer(src, dtype=np.uint8)
+    n = ctypes.c_size_t(0)
+    _lib.call("srl_blosc1_info", buf.ctypes.data, buf.size, ctypes.byref(n), None, None, None, None)
+    return int(n.value)
+
+
+def _cross_check(blosc) -> bool:
+    """The native decoder against frames the real package writes, once per process."""
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 5, 127, 4096, 70_001, 1_300_003):
+        for payload in (rng.integers(0, 256, n, dtype=np.uint8).tobytes(),
+                        np.repeat(rng.integers(0, 256, n // 9 + 1, dtype=np.uint8), 9)[:n].tobytes()):
+            frame = blosc.compress(payload, typesize=4, cname="lz4")
+            out = np.empty(n, dtype=np.uint8)
+            try:
+                _native_decode_into(frame, out, 1)
+            except Exception:  # noqa: BLE001
+                return False
+            if out.tobytes() != payload:
+                return False
+    return True
+
+
+def codec() -> str:
+    """'native' or 'blosc': who decodes compressed payloads in this process (see the module docstring)."""
+    global _codec_choice
+    if _codec_choice is not None:
+        return _codec_choice
+    import os
+    import warnings
+    want = os.environ.get("SRL_B200_WIRE_CODEC", "auto")
+    if want not in ("auto", "native", "blosc"):
+        raise ValueError(f"SRL_B200_WIRE_CODEC={want!r}: expected auto, native or blosc")
+    choice = want
+    if want == "auto":
+        try:
+            from srl_b200 import _lib
+            _lib.load_library()
+            native_ok = True
+        except Exception:  # noqa: BLE001 -- no library (a host without the CUDA build): the package decodes, as in the reference
+            native_ok = False
+        try:
+            blosc = _blosc()
+        except ModuleNotFoundError:
+            blosc = None
+        if native_ok and blosc is not None:
+            native_ok = _cross_check(blosc)
+            if not native_ok:
+                warnings.warn("srl_b200.wire: the native Blosc-1 decoder disagrees with the installed blosc package; "
+                              "decoding with the package")
+        choice = "native" if native_ok else "blosc"
+    _codec_choice = choice
+    return choice
+
+
+def decompress(buf) -> bytes:
+    """blosc.decompress(buf) by whoever `codec()` names."""
+    if codec() == "blosc":
+        return _blosc().decompress(bytes(buf))
+    out = np.empty(_native_nbytes(buf), dtype=np.uint8)
+    _native_decode_into(buf, out)
+    return out.tobytes()
+
+
+class CompressedLeaf:
+    """A compressed payload that has not been decoded yet: `frames(b, lazy=True)` hands these out so that the buffer can
+    decode each one straight into its pinned staging block (`decode_into`).  Behaves like a read-only array where one is
+    asked for (`np.asarray(leaf)` decodes once and keeps the result)."""
+    __slots__ = ("buf", "dtype", "shape", "nbytes", "_array")
+
+    def __init__(self, buf, dtype: np.dtype, shape: Tuple[int, ...]):
+        self.buf, self.dtype, self.shape = buf, np.dtype(dtype), tuple(shape)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        self._array = None
+        have = _native_nbytes(buf)
+        if have != self.nbytes:
+            raise ValueError(f"compressed payload of {have} bytes, dtype {self.dtype} x shape {self.shape} needs {self.nbytes}")
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape, dtype=np.int64))
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    def decode_into(self, dst: np.ndarray, threads: int = 0) -> None:
+        """`dst`: contiguous uint8 view of exactly `nbytes` bytes."""
+        if dst.dtype != np.uint8 or dst.size != self.nbytes or not dst.flags.c_contiguous:
+            raise ValueError(f"decode_into: need a contiguous uint8 destination of {self.nbytes} bytes")
+        _native_decode_into(self.buf, dst, threads)
+
+    def __array__(self, dtype=None, copy=None):
+        if self._array is None:
+            raw = np.empty(self.nbytes, dtype=np.uint8)
+            self.decode_into(raw)
+            self._array = raw.view(self.dtype).reshape(self.shape)
+            self._array.flags.writeable = False
+        return self._array if dtype is None else self._array.astype(dtype)
 
 
 def encode_dtype(dtype) -> str:
@@ -105,14 +230,16 @@ def dumps(x: NamedArray, method: str = "pickle_dict") -> List[bytes]:
     return [code] + body + [pickle.dumps(dict(**x.metadata))]
 
 
-def frames(b: Sequence[bytes]) -> Tuple[List[Tuple[str, Optional[np.dtype], Optional[Tuple[int, ...]], Optional[memoryview]]], Dict]:
+def frames(b: Sequence[bytes], lazy: bool = False):
     """A framed message (raw_bytes, raw_compress, compress_pickle, obs_compress, compress_except_policy_state) as
     [(dotted key, dtype, shape, payload view)] + metadata.  Uncompressed payloads stay views of the received bytes;
-    compressed ones are decompressed once (needs blosc)."""
+    compressed ones are decompressed once -- or, with `lazy` and the native decoder, handed out as `CompressedLeaf`s for the
+    caller to decode where the bytes are needed."""
     code = bytes(b[0])
     if code not in _COMPRESS_IF:
         raise ValueError(f"frames() reads the framed methods {sorted(c.decode() for c in _COMPRESS_IF)}, got {code!r}")
-    codec = _blosc() if code != RAW_BYTES else None  # namedarray.py:168-171: imported up front for codes 0004-0008
+    who = codec() if code != RAW_BYTES else None
+    pkg = _blosc() if who == "blosc" else None  # namedarray.py:168-171: imported up front for codes 0004-0008
     xs = pickle.loads(bytes(b[1])) if code == COMPRESS_PICKLE else b[1:-1]
     if len(xs) % 4 != 0:
         raise ValueError(f"framed body has {len(xs)} frames, not a multiple of 4")
@@ -127,7 +254,14 @@ def frames(b: Sequence[bytes]) -> Tuple[List[Tuple[str, Optional[np.dtype], Opti
         shape = tuple(ast.literal_eval(bytes(xs[4 * i + 2]).decode("ascii")))
         buf = xs[4 * i + 3]
         if compress_if(key):
-            buf = codec.decompress(bytes(buf))
+            if who == "native":
+                leaf = CompressedLeaf(buf, dtype, shape)  # checks the decoded size against dtype x shape
+                if lazy:
+                    out.append((key, dtype, shape, leaf))
+                    continue
+                buf = np.asarray(leaf).reshape(-1).view(np.uint8)
+            else:
+                buf = pkg.decompress(bytes(buf))
         payload = memoryview(buf).cast("B")
         need = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
         if payload.nbytes != need:
@@ -145,7 +279,7 @@ def loads(b: Sequence[bytes]) -> NamedArray:
     elif code == PICKLE:
         x = pickle.loads(bytes(b[1]))
     elif code == PICKLE_COMPRESS:
-        x = pickle.loads(_blosc().decompress(bytes(b[1])))
+        x = pickle.loads(decompress(b[1]))
     elif code in _COMPRESS_IF:
         entries, _ = frames(b)
         x = from_flattened([(k, None if dt is None else np.frombuffer(p, dtype=dt).reshape(shape))

@@ -187,6 +187,50 @@ def test_put_frames_equals_put_of_decoded_sample():
         b.put_frames(wire.dumps(samples[0], "pickle_dict"))
 
 
+@pytest.mark.parametrize("method,copy_threads", [("obs_compress", 1), ("raw_compress", 4), ("compress_except_policy_state", 1),
+                                                 ("compress_pickle", 2)])
+def test_put_frames_decodes_compressed_leaves_into_the_pinned_block(method, copy_threads, monkeypatch):
+    """a compressed message's payloads are decoded by the library's own Blosc-1 / LZ4 decoder
+    (srl_blosc1_decompress) straight into the pinned staging block -- the batch equals the batch assembled from the samples
+    themselves, bit for bit, including a string leaf (compressed on the wire, kept on the host) and a leaf that is None in
+    some messages.  The frames are written by tests/blosc1_writer.py under the name `blosc` (no blosc here: see
+    tests/test_wire_native.py for what that pins); the package's decompress must never be called."""
+    import sys
+    import types
+    from srl_b200 import wire
+    from srl_b200.buffer import DeviceSlabBuffer
+    from tests import blosc1_writer as W
+    mod = types.ModuleType("blosc")
+    mod.compress = lambda data, typesize=8, clevel=9, shuffle=1, cname="blosclz": W.compress(bytes(data), typesize, 1 << 16)
+
+    def no_decompress(data):
+        raise AssertionError("the package must not decode")
+
+    mod.decompress = no_decompress
+    monkeypatch.setitem(sys.modules, "blosc", mod)
+    monkeypatch.setattr(wire, "_codec_choice", "native")
+    rng = np.random.default_rng(11)
+    B = 4
+    samples = [_sample(rng, big=True, with_info=(j % 2 == 0)) for j in range(B)]
+    for j, s in enumerate(samples):
+        s.policy_name = np.full((s.on_reset.shape[0], 1), f"policy_{j % 2}")
+    a, b = DeviceSlabBuffer(batch_size=B), DeviceSlabBuffer(batch_size=B, copy_threads=copy_threads)
+    assert [b.put_frames(wire.dumps(s, method)) for s in samples] == [False] * (B - 1) + [True]
+    for s in samples:
+        a.put(copy.deepcopy(s))
+    fa, fb = dict(flatten(a.get().sample)), dict(flatten(b.get().sample))
+    assert sorted(fa) == sorted(fb)
+    for k, v in fa.items():
+        if v is None:
+            assert fb[k] is None, k
+        elif k == "trainer_worker_recv_timestamp":
+            assert fb[k].shape == v.shape and fb[k].dtype == v.dtype
+        elif isinstance(v, np.ndarray):
+            assert isinstance(fb[k], np.ndarray) and np.array_equal(fb[k], v), k
+        else:
+            assert fb[k].dtype == v.dtype and torch.equal(fb[k], v), k
+
+
 def test_string_and_empty_leaves_stay_on_the_host():
     """Real SRL samples carry `policy_name` as a '<U..' string array (policy_worker.py:186; the wire format ships it,
     base/namedarray.py:115-128) and the reference's buffer stacks it like any other leaf before the trainer worker clears

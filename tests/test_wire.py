@@ -20,6 +20,9 @@ def blosc_stand_in(monkeypatch):
     stand-in codec under that name (oracle/make_golden.py::gen_wire)."""
     import sys
     monkeypatch.setitem(sys.modules, "blosc", StandInBlosc)
+    # the stand-in writes zlib streams behind a marker, not Blosc-1 frames: the package under that name decodes them, not
+    # the library's native decoder (wire.codec(); tests/test_wire_native.py covers that one)
+    monkeypatch.setattr(wire, "_codec_choice", "blosc")
 
 
 def _message(fx, method):
@@ -115,12 +118,14 @@ def test_frames_are_zero_copy_views_and_checked():
         wire.frames(msg[:3] + msg[4:])
 
 
-def test_compressed_methods_need_blosc_like_the_reference():
-    """Without the third-party codec the compressed methods raise at the import, exactly where the reference's do
-    (namedarray.py:101-103,168-171); unknown codes / method names raise NotImplementedError (namedarray.py:158-160,209-211)."""
+def test_compressed_methods_need_blosc_like_the_reference(monkeypatch):
+    """With the package as the decoder (SRL_B200_WIRE_CODEC=blosc) and no package installed, the compressed methods raise at
+    the import, exactly where the reference's do (namedarray.py:101-103,168-171) -- encoding always does; unknown codes /
+    method names raise NotImplementedError (namedarray.py:158-160,209-211)."""
     import importlib.util
     if importlib.util.find_spec("blosc") is not None:
         pytest.skip("blosc is installed here")
+    monkeypatch.setattr(wire, "_codec_choice", "blosc")
     fx = load_golden("wire.npz")
     for code in (b"0004", b"0005", b"0006", b"0007", b"0008"):
         with pytest.raises(ModuleNotFoundError):
