@@ -885,6 +885,52 @@ def extras_run(cfg, dev, peak, timed_steps):
                                             f"{per} B per transition (SURVEY.md §8d)",
                                        roofline=dict(bound="hbm", achieved=nbytes / ms / 1e6, peak=peak, unit="GB/s",
                                                      frac=nbytes / ms / 1e6 / peak))
+    del logits, act
+    # ---- (f)4: a recurrent policy's minibatch -- chunked reset flags, segment boundaries, masked chunk-start states ------
+    try:
+        Tq, Bq = cfg.T, min(cfg.N, 4096)
+        nq, Cq, layers, H = max(2, Bq // max(cfg.minibatches, 1)), (8 if Tq % 8 == 0 else 1), 1, 256
+        g = torch.Generator(device="cpu").manual_seed(3)
+        on_reset = (torch.rand((Tq, Bq), generator=g) < 0.01).to(torch.uint8).to(dev)
+        hx = torch.randn((Tq, Bq, layers, H), generator=g).to(dev)
+        env_idx = torch.randperm(Bq, generator=g)[:nq].to(torch.int32).to(dev)
+        fn = lambda: ops.rnn_chunk_prep(on_reset, env_idx, Cq, hx=hx)
+        fn()
+        ms = statistics.mean(timed_steps(10, fn))
+        nbytes = 2 * Tq * nq + 2 * Cq * nq * layers * H * 4
+        out["rnn_chunk_prep"] = dict(ms_per_launch=ms, bytes_per_launch=nbytes,
+                                     what=f"srl_rnn_chunk_prep (+ three torch.empty): T={Tq}, B={Bq}, minibatch of {nq} lanes, {Cq} "
+                                          f"chunks, hidden state [{layers}, {H}] float32 per lane and step; an {nbytes / 1e6:.1f} MB "
+                                          "launch, latency-bound",
+                                     roofline=dict(bound="hbm", achieved=nbytes / ms / 1e6, peak=peak, unit="GB/s",
+                                                   frac=nbytes / ms / 1e6 / peak))
+        del hx
+    except Exception as e:  # noqa: BLE001
+        out["rnn_chunk_prep"] = dict(error=f"{type(e).__name__}: {e}")
+    # ---- (f)2: a compressed frame leaf decoded into pinned memory by the library's own Blosc-1 / LZ4 decoder (host code) ----
+    try:
+        from tests import blosc1_writer  # the only Blosc-1 WRITER here (test double; blosc itself is absent): liblz4 streams
+        rng = np.random.default_rng(0)
+        img = np.zeros((129 * 4, 84, 84), dtype=np.uint8)
+        for k in range(img.shape[0]):
+            img[k, 10:60, 20:70] = rng.integers(0, 256)
+            img[k, rng.integers(0, 84, 20), rng.integers(0, 84, 20)] = rng.integers(0, 256, 20)
+        payload = img.tobytes()
+        frame = np.frombuffer(blosc1_writer.compress(payload, 4, 1 << 18), dtype=np.uint8)
+        pin = torch.empty(len(payload), dtype=torch.uint8).pin_memory()
+        res = {}
+        for th in (1, 8):
+            t0 = time.perf_counter()
+            for _ in range(20):
+                ops._lib.call("srl_blosc1_decompress", frame.ctypes.data, frame.size, pin.data_ptr(), len(payload), th)
+            res[f"threads_{th}_gbs"] = len(payload) / ((time.perf_counter() - t0) / 20) / 1e9
+        ok = pin.numpy().tobytes() == payload
+        out["wire_decode_native"] = dict(decoded_bytes=len(payload), compressed_bytes=int(frame.size), bit_exact=ok, **res,
+                                         what="srl_blosc1_decompress: one Atari-like frame leaf [129, 4, 84, 84] uint8 (byte-"
+                                              "shuffled, split, LZ4 streams written by liblz4) into pinned host memory; host wall "
+                                              "clock; the Blosc-1 framing is unpinned against blosc itself (DESIGN.md 7.5)")
+    except Exception as e:  # noqa: BLE001
+        out["wire_decode_native"] = dict(error=f"{type(e).__name__}: {e}")
     return out
 
 
