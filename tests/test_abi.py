@@ -129,3 +129,26 @@ def test_host_copy_concurrent_callers_and_bad_arguments(lib):
         _lib.call("srl_host_copy", dsts[0].ctypes.data, srcs[0].ctypes.data, 10, 0)
     with pytest.raises(_lib.SrlCudaError, match="null"):
         _lib.call("srl_host_copy", None, srcs[0].ctypes.data, 10, 1)
+
+
+def test_recorded_calls_replay_the_same_entry_points(lib):
+    """_lib.record_calls / bind_calls / replay_calls (HotPath.run_device(plan=True)): every call() inside the context is
+    kept as (entry point, ctypes arguments) and can be issued again as it is; a failing status still raises on replay.
+    Exercised with a host-only entry point (srl_host_copy), so no GPU is needed."""
+    src = np.arange(4096, dtype=np.uint8) % 251
+    dst = np.zeros_like(src)
+    calls = []
+    with _lib.record_calls(calls):
+        _lib.call("srl_host_copy", dst.ctypes.data, src.ctypes.data, src.nbytes, 1)
+        with pytest.raises(RuntimeError, match="does not nest"):
+            with _lib.record_calls([]):
+                pass
+    _lib.call("srl_host_copy", dst.ctypes.data, src.ctypes.data, 16, 1)  # outside the context: not recorded
+    assert [name for name, _ in calls] == ["srl_host_copy"] and np.array_equal(dst, src)
+    bound = _lib.bind_calls(calls)
+    src[:] = 7  # same buffers, new contents: the replay copies them again
+    _lib.replay_calls(bound)
+    assert (dst == 7).all()
+    bad = _lib.bind_calls([("srl_host_copy", (dst.ctypes.data, src.ctypes.data, src.nbytes, 0))])  # threads = 0
+    with pytest.raises(_lib.SrlCudaError, match="threads"):
+        _lib.replay_calls(bad)
