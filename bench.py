@@ -15,7 +15,11 @@ mailboxes, or NCCL); at N > 1 the line carries `parity_check`: the exchanged tab
 bit for bit on every rank, and one minibatch's loss / gradients against the oracle evaluated with the global sums.
 Beside the headline the line reports `step_trainer_order` (the same work issued as a trainer must issue it: one loss
 launch per minibatch, each behind the previous) and `trainer_step` (the drop-in `MultiAgentPPOB200.step` with a small
-policy, host sample in, stats out).
+policy, host sample in, stats out).  `step.launch` says how the timed step was issued (`--launch graph`: one CUDA graph
+replay, the default; `--launch plan`: the step's recorded C-ABI calls as plain stream launches) and
+`step.ms_per_step_other_launch` the same step issued the other way.  `extra` holds the neighbours of the path, each with its
+own roofline: K1 (`srl_batch_gather`), K4b (`srl_ppo_loss_from_logits`), `srl_rnn_chunk_prep`, and the native decode of a
+compressed frame leaf into pinned memory (`wire_decode_native`, host GB/s).
 `--impl reference` times the reference's OWN functions (`MultiAgentPPO._compute_adv_and_value_target`, `_compute_loss` +
 backward, loaded unmodified through oracle/ref_loader.py from oracle/_ref) on the host cores, same config / metric / unit,
 per stage; where a GPU is visible it adds the same functions on cuda (the ATen-eager path SRL users have today).
