@@ -180,8 +180,11 @@ def test_step_explicit_gather_equals_fused_gather():
     assert b.count_launches() == a.count_launches() + cfg.epochs * cfg.minibatches
 
 
-def test_host_entry_point_roundtrip():
-    cfg = CASES["atari_mb"]
+@pytest.mark.parametrize("name", ["atari_mb", "mb_shares"])
+def test_host_entry_point_roundtrip(name):
+    """HotPath.run_host: host buffers in and out.  It launches the loss once per EPOCH (each epoch as soon as its policy
+    outputs have landed): with the scan's minibatch shares (mb_shares) every such launch starts at its epoch's first table slot."""
+    cfg = CASES[name]
     hp, pol_dev, ref, pa = _setup(cfg, seed=6)
     n = cfg.N // cfg.minibatches
     pol_host = torch.stack([torch.stack([torch.stack(list(trip)) for trip in row]) for row in pol_dev]).cpu().pin_memory()
@@ -191,6 +194,7 @@ def test_host_entry_point_roundtrip():
     s = synth.make_sample_scalars(cfg, 6)
     nbytes = hp.run_host(s, pol_host, out_host, use_graph=False)
     ref_grads = out_host["grads"].clone()  # permutations of step 0, the ones pol_host was laid out for
+    assert hp._part_valid == (name == "mb_shares")
     assert nbytes["h2d_bytes"] == cfg.L * cfg.N * 15 + cfg.epochs * cfg.T * cfg.N * 12
     assert nbytes["d2h_bytes"] == cfg.L * cfg.N * 8 + cfg.epochs * cfg.T * cfg.N * 12 + cfg.epochs * cfg.minibatches * 128
     assert np.array_equal(out_host["adv"].numpy(), ref["adv"].numpy()[..., 0])
